@@ -1,0 +1,267 @@
+"""The oracle pinned against outputs of the unmodified reference
+(tests/golden/*.npz, produced by tests/golden/make_golden.py)."""
+
+import numpy as np
+import pytest
+
+import synth
+from oracle import arena, gomoku, mcts, net, replay, selfplay
+
+SIZES = ((5, 4), (9, 5), (15, 5), (19, 5))
+
+
+# ---- rules ---------------------------------------------------------------------
+@pytest.mark.parametrize("size,win", SIZES)
+def test_rules_playouts(golden, size, win):
+    g = golden(f"rules_{size}x{size}_w{win}.npz")
+    for i in range(len(g["lens"])):
+        s = gomoku.State(size, win)
+        for k in range(int(g["lens"][i])):
+            assert not s.is_terminal()
+            s = s.play(tuple(g["moves"][i, k]))
+        assert np.array_equal(s.board, g["boards"][i])
+        assert s.to_move == g["to_move"][i]
+        assert np.array_equal(s.legal_mask().astype(np.uint8), g["legal"][i])
+        assert s.result() == g["result"][i]
+        assert s.is_terminal() == (g["term_ply"][i] >= 0)
+        assert np.array_equal(s.planes(), g["planes"][i].astype(np.float32))
+        assert gomoku.result_vectorised(s.board, win) == g["result"][i]
+
+
+@pytest.mark.parametrize("size,win", SIZES)
+def test_rules_fuzz_boards(golden, size, win):
+    g = golden(f"rules_{size}x{size}_w{win}.npz")
+    for b, res, nleg in zip(g["fuzz"], g["fuzz_result"], g["fuzz_legal_count"]):
+        s = gomoku.State.from_board(b, win=win)
+        assert s.result() == res
+        assert gomoku.result_vectorised(b, win) == res
+        assert len(s.legal_actions()) == nleg          # no terminal guard (games.py:35-47)
+
+
+def test_occupied_cell_raises():
+    s = gomoku.State(5, 4).play((2, 2))
+    with pytest.raises(ValueError, match="Invalid move"):
+        s.play((2, 2))
+
+
+def test_legal_actions_row_major():
+    s = gomoku.State(3, 3).play((0, 1)).play((2, 0))
+    assert s.legal_actions() == [(0, 0), (0, 2), (1, 0), (1, 1), (1, 2), (2, 1), (2, 2)]
+
+
+# ---- z labelling: the reference's only own known-answer test ---------------------
+def test_value_labelling_truth_table():
+    """alphazero/tests/tests.py:11-22."""
+    X, O, D = gomoku.X, gomoku.O, gomoku.DRAW
+    assert selfplay.label(D, X) == 0 and selfplay.label(D, O) == 0
+    assert selfplay.label(X, X) == 1 and selfplay.label(X, O) == -1
+    assert selfplay.label(O, O) == 1 and selfplay.label(O, X) == -1
+
+
+# ---- network --------------------------------------------------------------------
+@pytest.mark.parametrize("size", [5, 9, 15, 19])
+def test_net_forward_synthetic_weights(golden, size):
+    g = golden("net_stem.npz")
+    params = net.synthetic_stem_params(size, seed=size)
+    logits, value = net.stem_forward(params, g[f"x_{size}"].astype(np.float32))
+    # same torch build => normally bit-identical; 1e-5 is the north-star fp32 tolerance
+    assert np.abs(logits.numpy() - g[f"logits_{size}"]).max() <= 1e-5
+    assert np.abs(value.numpy() - g[f"value_{size}"]).max() <= 1e-5
+    ev = net.make_evaluator(params)
+    for i in range(3):
+        s = _state_from_planes(g[f"x_{size}"][i])
+        p, v = ev(s)
+        assert p.shape == (size, size) and p.dtype == np.float32
+        assert np.abs(p - g[f"policy_{size}"][i]).max() <= 1e-6
+        assert abs(v - g[f"value1_{size}"][i]) <= 1e-5
+
+
+def test_net_forward_shipped_checkpoint(golden):
+    g = golden("net_stem.npz")
+    ck = golden("ref_ckpt_5x5.npz")
+    params = {k: ck[k] for k in ck.files}
+    assert {k: v.shape for k, v in params.items()} == net.stem_shapes(5)
+    logits, value = net.stem_forward(params, g["x_ckpt"].astype(np.float32))
+    assert np.abs(logits.numpy() - g["logits_ckpt"]).max() <= 1e-5
+    assert np.abs(value.numpy() - g["value_ckpt"]).max() <= 1e-5
+
+
+def _state_from_planes(x):
+    """Planes are from the side to move's view; colours are arbitrary for the net."""
+    b = np.zeros(x.shape[1:], dtype=np.int8)
+    b[x[0] > 0] = gomoku.X
+    b[x[1] > 0] = gomoku.O
+    last = np.argwhere(x[2] > 0)
+    return gomoku.State.from_board(b, to_move=gomoku.X, last=None if len(last) == 0 else last[0])
+
+
+# ---- search -----------------------------------------------------------------------
+def _case_state(g, tag):
+    size, win, tm, sims, lr, lc = (int(v) for v in g[f"meta_{tag}"])
+    s = gomoku.State.from_board(g[f"board_{tag}"], to_move=tm, win=win,
+                                last=None if lr < 0 else (lr, lc))
+    return s, size, sims
+
+
+def test_mcts_visit_counts_match_reference(golden):
+    g = golden("mcts.npz")
+    depth = 0
+    for tag in g["cases"]:
+        s, size, sims = _case_state(g, tag)
+        sharp = float(tag.split("_")[-1])
+        T, is_np = g[f"temp_{tag}"]
+        T = np.float64(T) if is_np else float(T)
+        res = mcts.Search(synth.oracle_evaluator(salt=size, sharp=sharp), sims, 2.0).run(
+            s, T, add_root_noise=False, forced_action=tuple(g[f"action_{tag}"]))
+        assert np.array_equal(res.visits, g[f"visits_{tag}"]), tag
+        assert np.abs(res.pi - g[f"pi_{tag}"]).max() <= 1e-6, tag
+        depth = max(depth, res.stats["sum_depth"] / sims)
+    assert depth > 2.0          # the corpus exercises trees deeper than the root's children
+
+
+def test_mcts_sampled_action_with_seeded_numpy(golden):
+    g = golden("mcts.npz")
+    if str(g["numpy_version"]) != np.__version__:
+        pytest.skip("sample-level parity needs the numpy version the fixture was made with")
+    for tag in g["cases"]:
+        s, size, sims = _case_state(g, tag)
+        sharp = float(tag.split("_")[-1])
+        T, is_np = g[f"temp_{tag}"]
+        T = np.float64(T) if is_np else float(T)
+        np.random.seed(int(g[f"seed_{tag}"]))
+        res = mcts.Search(synth.oracle_evaluator(salt=size, sharp=sharp), sims, 2.0).run(s, T)
+        assert res.action == tuple(g[f"action_{tag}"]), tag
+
+
+def test_mcts_root_noise_with_seeded_numpy(golden):
+    g = golden("mcts.npz")
+    if str(g["numpy_version"]) != np.__version__:
+        pytest.skip("sample-level parity needs the numpy version the fixture was made with")
+    for tag in g["noise_cases"]:
+        size, win, tm, sims, seed = (int(v) for v in g[f"meta_{tag}"])
+        s = gomoku.State.from_board(g[f"board_{tag}"], to_move=tm, win=win)
+        np.random.seed(seed)
+        res = mcts.Search(synth.oracle_evaluator(salt=size + 100, sharp=3.0), sims, 2.0).run(
+            s, selfplay.default_temperature_schedule(3), add_root_noise=True)
+        assert np.array_equal(res.visits, g[f"visits_{tag}"])
+        assert np.abs(res.pi - g[f"pi_{tag}"]).max() <= 1e-6
+        assert res.action == tuple(g[f"action_{tag}"])
+
+
+def test_mcts_edge_cases(golden):
+    g = golden("mcts.npz")
+    s = gomoku.State.from_board(g["edge_won_board"], to_move=gomoku.O, win=4)
+    assert s.is_terminal()
+    res = mcts.Search(synth.oracle_evaluator(1), 20, 2.0).run(s, 1.0, forced_action=(4, 4))
+    assert np.array_equal(res.visits, g["edge_won_visits"]) and res.visits.sum() == 0
+    assert np.abs(res.pi - g["edge_won_pi"]).max() <= 1e-6       # uniform over the empties
+    full = gomoku.State.from_board(np.array([[1, 2, 1], [1, 2, 2], [2, 1, 1]], dtype=np.int8), win=3)
+    res = mcts.Search(synth.oracle_evaluator(1), 5, 2.0).run(full, 1.0)
+    assert res.action is None and np.array_equal(res.pi, g["edge_full_pi"])
+
+
+def test_mcts_with_shipped_checkpoint_replayed(golden):
+    """Trees driven by the reference's trained 5x5 net reach depth 5 and hit
+    terminal leaves; the evaluator outputs are replayed from the fixture."""
+    g = golden("mcts_ckpt5.npz")
+    terminal = 0
+    for j in range(int(g["count"])):
+        table = {}
+        for b, tm, la, p, v in zip(g[f"rec_boards_{j}"], g[f"rec_tomove_{j}"], g[f"rec_last_{j}"],
+                                   g[f"rec_policy_{j}"], g[f"rec_value_{j}"]):
+            table[(b.tobytes(), int(tm), int(la[0]), int(la[1]))] = (p, float(v))
+
+        def ev(state, _t=table):
+            la = (-1, -1) if state.last is None else state.last
+            p, v = _t[(state.board.tobytes(), state.to_move, la[0], la[1])]
+            return p.copy(), v
+
+        la = g[f"last_{j}"]
+        s = gomoku.State.from_board(g[f"board_{j}"], to_move=int(g[f"tomove_{j}"]), win=4,
+                                    last=None if la[0] < 0 else (int(la[0]), int(la[1])))
+        res = mcts.Search(ev, 200, 2.0).run(s, 1.0, forced_action=(0, 0))
+        assert np.array_equal(res.visits, g[f"visits_{j}"]), j
+        assert np.abs(res.pi - g[f"pi_{j}"]).max() <= 1e-6
+        terminal += res.stats["terminal_leaves"]
+    assert terminal > 100
+
+
+# ---- self-play pieces ---------------------------------------------------------------
+def test_temperature_schedules(golden):
+    g = golden("selfplay.npz")
+    for ply, T in zip(g["sched_plies"], g["sched_T"]):
+        assert selfplay.default_temperature_schedule(int(ply)) == T
+    for step, T in enumerate(g["eval_T"]):
+        assert arena.eval_temperature(step) == T
+
+
+@pytest.mark.parametrize("size", [3, 5, 15])
+def test_augment_reference_mode(golden, size):
+    g = golden("selfplay.npz")
+    out = selfplay.augment_reference(g[f"aug_state_in_{size}"], g[f"aug_pi_in_{size}"])
+    assert len(out) == 4
+    for k, (s, p) in enumerate(out):
+        assert np.array_equal(s, g[f"aug_state_out_{size}"][k])
+        assert np.array_equal(p, g[f"aug_pi_out_{size}"][k])
+
+
+def test_augment_d4_is_a_consistent_group_action():
+    rs = np.random.RandomState(3)
+    planes = rs.random_sample((4, 5, 5)).astype(np.float32)
+    pi = planes[2].copy()                      # tie pi to a plane: must stay tied under every element
+    out = selfplay.augment_d4(planes, pi)
+    assert len(out) == 8
+    seen = set()
+    for s, p in out:
+        assert np.array_equal(s[2], p)
+        seen.add(s.tobytes())
+    assert len(seen) == 8
+    assert np.array_equal(out[1][0], np.rot90(planes, 1, axes=(1, 2)))
+
+
+def test_episode_loop_matches_reference_worker(golden):
+    g = golden("selfplay.npz")
+    if str(g["numpy_version"]) != np.__version__:
+        pytest.skip("sample-level parity needs the numpy version the fixture was made with")
+    np.random.seed(int(g["ep_seed"]))
+    for gi in range(int(g["ep_count"])):
+        examples, result, moves = selfplay.play_episode(
+            synth.oracle_evaluator(salt=55, sharp=3.0), 5, 4, 60, 2.0)
+        assert len(examples) == len(g[f"ep_z_{gi}"])
+        for (planes, pi, z), gs, gp, gz in zip(examples, g[f"ep_states_{gi}"],
+                                               g[f"ep_pi_{gi}"], g[f"ep_z_{gi}"]):
+            assert np.array_equal(planes, gs.astype(np.float32))
+            assert np.abs(pi - gp).max() <= 1e-6
+            assert z == gz
+
+
+def test_arena_matches_reference_evaluator(golden):
+    g = golden("arena.npz")
+    # the step counters: first mover 0,1,2,..., second mover 1,2,3,... (evaluator.py:71-90)
+    assert [arena.step_counters(True, p) for p in range(6)] == [0, 1, 1, 2, 2, 3]
+    if str(np.__version__):
+        np.random.seed(int(g["seed"]))
+        steps = []
+        orig = arena.eval_temperature
+        try:
+            arena.eval_temperature = lambda step, *a, **k: (steps.append(step), orig(step))[1]
+            wr, m = arena.play_match(synth.oracle_evaluator(1), synth.oracle_evaluator(2),
+                                     6, 5, 4, int(g["sims"]), 2.0)
+        finally:
+            arena.eval_temperature = orig
+        assert [m["wins"], m["losses"], m["draws"]] == list(g["wld"])
+        assert wr == float(g["win_rate"])
+        assert steps == list(g["steps"])
+    assert arena.should_promote(0.5501) and not arena.should_promote(0.55)
+
+
+def test_replay_fifo(golden):
+    g = golden("replay.npz")
+    buf = replay.Fifo(10)
+    buf.extend(list(range(7)))
+    buf.extend(list(range(100, 108)))
+    assert buf.all() == list(g["final"]) and len(buf) == int(g["len"])
+    small = replay.Fifo(10)
+    small.extend([1, 2, 3])
+    assert list(small.sample_batch(5)) == list(g["undersized_sample"])
+    assert len(set(buf.sample_batch(4))) == 4
