@@ -1,0 +1,148 @@
+// Internal declarations shared by the translation units of libazp_b200.so.
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+#include <vector>
+#include "azp_common.cuh"
+
+// ---- launch bookkeeping / error plumbing ------------------------------------------------
+void azp_count_launch(int n = 1);
+uint64_t azp_launch_count();
+int azp_check_launch();                       // cudaGetLastError -> status, records message
+void azp_set_global_error(const std::string& msg);
+const char* azp_global_error();
+RulesParams azp_make_rules(int board, int win_length);
+
+#define AZP_DISPATCH_NW(nw, kernel, grid, block, smem, stream, ...)                         \
+  do {                                                                                      \
+    switch (nw) {                                                                           \
+      case 1: kernel<1><<<grid, block, smem, stream>>>(__VA_ARGS__); break;                 \
+      case 2: kernel<2><<<grid, block, smem, stream>>>(__VA_ARGS__); break;                 \
+      case 3: kernel<3><<<grid, block, smem, stream>>>(__VA_ARGS__); break;                 \
+      case 4: kernel<4><<<grid, block, smem, stream>>>(__VA_ARGS__); break;                 \
+      case 5: kernel<5><<<grid, block, smem, stream>>>(__VA_ARGS__); break;                 \
+      default: kernel<6><<<grid, block, smem, stream>>>(__VA_ARGS__); break;                \
+    }                                                                                       \
+  } while (0)
+
+#define AZP_CUDA(e, call)                                                                   \
+  do {                                                                                      \
+    cudaError_t err__ = (call);                                                             \
+    if (err__ != cudaSuccess) {                                                             \
+      (e)->set_error(std::string(#call) + ": " + cudaGetErrorString(err__));                \
+      return AZP_ERR_CUDA;                                                                  \
+    }                                                                                       \
+  } while (0)
+
+// ---- device-side views ------------------------------------------------------------------
+// Structure-of-arrays node table.  Node `nd` of game `g` owns A edge slots, one per CELL
+// (slot index == r*B+c, so the reference's row-major child order is the slot order and
+// occupied cells are simply skipped).  Edge statistics are the child NODE's N/W of
+// alphazero/mcts.py:25-48; the root's own N lives in root_n.
+struct TreeView {
+  int G, A, NW, cap, maxd, S;
+  int32_t* N;        // [G][cap][A] visit count of the child reached through the edge
+  double* W;         // [G][cap][A] total value (float64, as the reference's Python floats)
+  float* P;          // [G][cap][A] prior (float32 widened at use, mcts.py:63)
+  int32_t* child;    // [G][cap][A] node index of the expanded child, -1 if not expanded
+  int32_t* node_count;   // [G]
+  int32_t* root_n;       // [G]  root.N (== simulations done this move)
+  // per-game root position
+  uint64_t* root_x; uint64_t* root_o;      // [G][NW]
+  uint8_t* root_tm; int16_t* root_last;    // [G]
+  int32_t* ply; int64_t* game_id;          // [G]
+  uint8_t* root_result;                    // [G] result of the ROOT position (0 if playable)
+  uint8_t* active;                         // [G] 1 = this slot searches
+  uint8_t* net_of_game;                    // [G] weight slot that evaluates this game's leaves
+  // per-step leaf records
+  int32_t* path;         // [G][maxd] (node*A + cell) of every edge on the descent
+  int32_t* path_len;     // [G]
+  uint8_t* leaf_kind;    // [G] 0 = evaluate+expand, 1 = terminal, 2 = idle
+  float* leaf_tvalue;    // [G] value of a terminal leaf from its side to move's view
+  int32_t* leaf_slot;    // [G] row of the leaf in the contiguous evaluation batch (-1 if none)
+  int32_t* slot_game;    // [G] inverse
+  uint64_t* leaf_x; uint64_t* leaf_o;      // [G][NW] indexed by SLOT (contiguous batch)
+  uint8_t* leaf_tm; int16_t* leaf_last;    // [G]     indexed by SLOT
+  int32_t* n_leaves;     // [4]: {front count, back count} x step parity
+  int32_t* error_flag;   // [1] device-side error (capacity overflow, illegal move)
+  unsigned long long* counters;  // azp_counters as 64-bit words
+};
+
+enum CounterIndex {
+  CNT_SIMS = 0, CNT_EVALS, CNT_TERMINAL, CNT_SCANNED, CNT_PATH, CNT_EXPANSIONS, CNT_GAMES, CNT_PLIES,
+  CNT_POSITIONS, CNT_EXAMPLES, CNT_LAUNCHES, CNT_XWINS, CNT_OWINS, CNT_DRAWS, CNT_COUNT
+};
+
+// ---- network ------------------------------------------------------------------------------
+struct NetWeights;       // defined in azp_net.cu
+struct NetWorkspace;
+
+struct azp_engine {
+  azp_config cfg;
+  RulesParams rp;
+  TreeView tv;
+  int A, NW;
+  std::string error;
+  std::vector<void*> allocs;
+  NetWeights* weights[2] = {nullptr, nullptr};
+  NetWorkspace* ws = nullptr;
+  // evaluation outputs indexed by slot
+  float* d_policy = nullptr;   // [G][A]
+  float* d_logits = nullptr;   // [G][A]
+  float* d_value = nullptr;    // [G]
+  // self-play state
+  double* d_temperature = nullptr; int n_temperature = 0;
+  uint16_t* d_moves = nullptr;     // [G][max_plies]
+  float* d_pi_hist = nullptr;      // [G][max_plies][A]
+  uint8_t* d_result = nullptr;     // [G] result of a finished game awaiting its flush
+  uint8_t* d_status = nullptr;     // [G] slot status (see azp_tree.cu)
+  float* d_raw_planes = nullptr; float* d_raw_pi = nullptr; int32_t* d_raw_z = nullptr;
+  int32_t* d_raw_count = nullptr;  // [1]
+  long long raw_capacity = 0;
+  long long* d_sched = nullptr;    // [4]: next local game index, games to play, finished, (spare)
+  int max_plies = 0;
+  int search_n = 0;                // number of game slots in the current step-by-step search
+  int parity = 0;                  // which pair of leaf counters the current step uses
+  long long sp_first = 0, sp_total = 0;  // current self-play job
+  void set_error(const std::string& m) { error = m; azp_set_global_error(m); }
+  template <typename T> int alloc(T** p, size_t count) {
+    void* q = nullptr;
+    cudaError_t err = cudaMalloc(&q, count * sizeof(T) + 256);
+    if (err != cudaSuccess) { set_error(std::string("cudaMalloc: ") + cudaGetErrorString(err)); return AZP_ERR_CUDA; }
+    allocs.push_back(q);
+    *p = (T*)q;
+    return AZP_OK;
+  }
+};
+
+// azp_rules.cu
+int azp_augment_launch(int board, int mode, int n_max, const int* n_dev, const float* planes, const float* pi,
+                       const int32_t* z, float* out_planes, float* out_pi, int32_t* out_z,
+                       long long out_offset, const long long* out_offset_dev, long long out_capacity,
+                       cudaStream_t stream);
+
+// azp_tree.cu
+int azp_tree_begin_move(azp_engine* e, int n, int emit, int compact, int parity, cudaStream_t s);  // reset trees, root result, roots -> eval batch
+int azp_tree_root_expand(azp_engine* e, int n, const float* policy, int by_slot, int add_noise, cudaStream_t s);
+int azp_tree_select(azp_engine* e, int n, int compact, int parity, cudaStream_t s);
+int azp_tree_expand_backup(azp_engine* e, int n, const float* policy, const float* value, int by_slot, cudaStream_t s);
+int azp_tree_root_visits(azp_engine* e, int n, int32_t* visits, cudaStream_t s);
+int azp_tree_leaf_states(azp_engine* e, int n, uint64_t* x, uint64_t* o, uint8_t* tm, int16_t* last, uint8_t* kind, cudaStream_t s);
+int azp_episode_seat(azp_engine* e, int n, int arena, cudaStream_t s);
+int azp_episode_end_move(azp_engine* e, int n, int arena, cudaStream_t s);
+int azp_episode_finish(azp_engine* e, int n, int arena, cudaStream_t s);
+int azp_episode_drain(azp_engine* e, long long* out_written_dev, int mult, cudaStream_t s);
+
+// azp_net.cu
+int azp_net_create(azp_engine* e);
+void azp_net_destroy(azp_engine* e);
+int azp_net_load(azp_engine* e, int slot, const float* blob, size_t n, bool on_device, cudaStream_t s);
+size_t azp_net_weight_count(const azp_engine* e);
+// evaluate the contiguous leaf batch: rows [0,count) (front) or [G-count, G) read backwards
+// (back=1); count is read on the device from *count_dev (or count_host if count_dev == null)
+int azp_net_eval_leaves(azp_engine* e, int slot, const int32_t* count_dev, int count_host, int back, cudaStream_t s);
+int azp_net_eval_planes(azp_engine* e, int slot, int n, const float* planes, float* logits, float* policy,
+                        float* value, cudaStream_t s);

@@ -1,0 +1,534 @@
+// Node-table kernels: PUCT selection, expansion, backup, root noise, move selection and the
+// (state, pi, z) position writer.  One warp per game everywhere (SURVEY.md section 8 rows
+// a6-a12, a16).  All PUCT arithmetic is float64 in the reference's operation order, so visit
+// counts are identical to alphazero/mcts.py whenever the evaluator numbers are identical.
+#include "azp_internal.cuh"
+
+#define SLOT_IDLE 0
+#define SLOT_PLAYING 1
+#define SLOT_PENDING 2     // game over, positions not yet emitted (raw slab was full)
+
+__device__ __forceinline__ void count(const TreeView& tv, int idx, unsigned long long v) {
+  if (v) atomicAdd(tv.counters + idx, v);
+}
+
+// Claim a row of the contiguous evaluation batch and store the position there.  Games evaluated
+// by weight slot 0 fill rows from the front, slot 1 (arena baseline) from the back.
+template <int NW>
+__device__ __forceinline__ int emit_leaf(const TreeView& tv, int g, const BB<NW>& x, const BB<NW>& o, int tm,
+                                         int last, int compact, int parity, int lane) {
+  int slot = g;
+  if (compact) {
+    if (lane == 0) {
+      int side = tv.net_of_game[g];
+      int idx = atomicAdd(&tv.n_leaves[parity * 2 + side], 1);
+      slot = side ? tv.G - 1 - idx : idx;
+    }
+    slot = __shfl_sync(AZP_FULL, slot, 0);
+  }
+  if (lane == 0) {
+    tv.leaf_slot[g] = slot;
+    tv.slot_game[slot] = g;
+    bb_store<NW>(tv.leaf_x + (size_t)slot * NW, x);
+    bb_store<NW>(tv.leaf_o + (size_t)slot * NW, o);
+    tv.leaf_tm[slot] = (uint8_t)tm;
+    tv.leaf_last[slot] = (int16_t)last;
+  }
+  return slot;
+}
+
+// ---- MCTS.run prologue (mcts.py:106): fresh tree per move --------------------------------
+template <int NW>
+__global__ void begin_move_kernel(RulesParams rp, TreeView tv, int n, int emit, int compact, int parity) {
+  int g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    tv.n_leaves[(parity ^ 1) * 2 + 0] = 0;
+    tv.n_leaves[(parity ^ 1) * 2 + 1] = 0;
+  }
+  if (g >= n) return;
+  if (!tv.active[g]) {
+    if (lane == 0) { tv.leaf_kind[g] = 2; tv.leaf_slot[g] = -1; tv.path_len[g] = 0; }
+    return;
+  }
+  BB<NW> x = bb_load<NW>(tv.root_x + (size_t)g * NW), o = bb_load<NW>(tv.root_o + (size_t)g * NW);
+  int res = warp_result<NW>(rp, x, o, lane);
+  if (lane == 0) {
+    tv.node_count[g] = 1;
+    tv.root_n[g] = 0;
+    tv.root_result[g] = (uint8_t)res;
+    tv.leaf_kind[g] = 0;
+    tv.path_len[g] = 0;
+  }
+  // the root is evaluated unconditionally (mcts.py:109), even when it is terminal
+  if (emit) {
+    emit_leaf<NW>(tv, g, x, o, tv.root_tm[g], tv.root_last[g], compact, parity, lane);
+    if (lane == 0) count(tv, CNT_EVALS, 1);
+  }
+}
+
+// ---- root priors (+ Dirichlet noise), mcts.py:109-120 ---------------------------------------
+template <int NW>
+__global__ void root_expand_kernel(RulesParams rp, TreeView tv, int n, const float* __restrict__ policy,
+                                   int by_slot, int add_noise, double alpha, double weight, uint64_t seed) {
+  int g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (g >= n || !tv.active[g]) return;
+  const int A = rp.A;
+  BB<NW> x = bb_load<NW>(tv.root_x + (size_t)g * NW), o = bb_load<NW>(tv.root_o + (size_t)g * NW);
+  BB<NW> occ;
+#pragma unroll
+  for (int k = 0; k < NW; k++) occ.w[k] = x.w[k] | o.w[k];
+  const float* prow = policy + (size_t)(by_slot ? tv.leaf_slot[g] : g) * A;
+  const size_t base = (size_t)g * tv.cap * A;   // node 0
+  double gsum = 0.0;
+  Philox rng = philox_for_game(seed, tv.game_id[g]);
+  const uint32_t ply = (uint32_t)tv.ply[g];
+  if (add_noise) {
+    for (int a = lane; a < A; a += 32)
+      if (!bb_test<NW>(occ, a)) gsum += gamma_variate(rng, alpha, (uint32_t)a, ply);
+    gsum = warp_sum_d(gsum);
+  }
+  for (int a = lane; a < A; a += 32) {
+    bool legal = !bb_test<NW>(occ, a);
+    float p = 0.f;
+    if (legal) {
+      p = prow[a];
+      if (add_noise) {
+        // policy[r,c] = (1-w)*policy[r,c] + w*eta with a float32 policy array (mcts.py:116):
+        // float32 product, float64 sum, rounded back to float32 on store
+        double eta = gamma_variate(rng, alpha, (uint32_t)a, ply) / gsum;
+        float keep = __fmul_rn((float)(1.0 - weight), p);
+        p = (float)__dadd_rn((double)keep, __dmul_rn(weight, eta));
+      }
+    }
+    tv.P[base + a] = p;
+    tv.N[base + a] = 0;
+    tv.W[base + a] = 0.0;
+    tv.child[base + a] = -1;
+  }
+  if (lane == 0) count(tv, CNT_EXPANSIONS, 1);
+}
+
+// ---- one PUCT descent per game (mcts.py:126-129 + 66-74) -------------------------------------
+template <int NW>
+__global__ void select_kernel(RulesParams rp, TreeView tv, int n, double c_puct, int compact, int parity) {
+  int g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    tv.n_leaves[(parity ^ 1) * 2 + 0] = 0;
+    tv.n_leaves[(parity ^ 1) * 2 + 1] = 0;
+  }
+  if (g >= n) return;
+  if (!tv.active[g]) {
+    if (lane == 0) { tv.leaf_kind[g] = 2; tv.leaf_slot[g] = -1; tv.path_len[g] = 0; }
+    return;
+  }
+  const int A = rp.A;
+  BB<NW> x = bb_load<NW>(tv.root_x + (size_t)g * NW), o = bb_load<NW>(tv.root_o + (size_t)g * NW);
+  int tm = tv.root_tm[g], last = tv.root_last[g];
+  const size_t gbase = (size_t)g * tv.cap * A;
+  int32_t* path = tv.path + (size_t)g * tv.maxd;
+  int node = 0, nparent = tv.root_n[g], depth = 0;
+  int result = tv.root_result[g];
+  int kind;
+  float tvalue = 0.f;
+  unsigned long long scanned = 0;
+  while (true) {
+    if (result != 0) {   // terminal position: value from its side to move's view (mcts.py:132-134)
+      kind = 1;
+      tvalue = result == 3 ? 0.f : (result == tm ? 1.f : -1.f);
+      break;
+    }
+    const size_t nb = gbase + (size_t)node * A;
+    // score = Q + c_puct * P * sqrt(N_parent + 1e-8) / (1 + N_child), float64, left to right
+    const double sq = __dsqrt_rn(__dadd_rn((double)nparent, 1e-8));
+    double best = -1.0e308;
+    int besta = 0x7fffffff;
+    int stones = 0;
+#pragma unroll
+    for (int k = 0; k < NW; k++) stones += __popcll(x.w[k] | o.w[k]);
+    for (int a = lane; a < A; a += 32) {
+      bool occupied = bb_test<NW>(x, a) || bb_test<NW>(o, a);
+      if (occupied) continue;
+      int nn = tv.N[nb + a];
+      double q = nn ? __ddiv_rn(tv.W[nb + a], (double)nn) : 0.0;
+      double u = __ddiv_rn(__dmul_rn(__dmul_rn(c_puct, (double)tv.P[nb + a]), sq), (double)(1 + nn));
+      double s = __dadd_rn(q, u);
+      if (s > best) { best = s; besta = a; }    // ascending a: the FIRST maximum is kept
+    }
+#pragma unroll
+    for (int off = 16; off; off >>= 1) {       // argmax with lowest-cell tie-break
+      double ob = __shfl_xor_sync(AZP_FULL, best, off);
+      int oa = __shfl_xor_sync(AZP_FULL, besta, off);
+      if (ob > best || (ob == best && oa < besta)) { best = ob; besta = oa; }
+    }
+    scanned += (unsigned long long)(A - stones);
+    const int a = besta;
+    if (a >= A) {          // cannot happen on a non-terminal position; never loop forever
+      if (lane == 0) atomicExch(tv.error_flag, AZP_ERR_CAPACITY);
+      kind = 2;
+      break;
+    }
+    const int cn = tv.N[nb + a], ch = tv.child[nb + a];
+    if (depth >= tv.maxd) {
+      if (lane == 0) atomicExch(tv.error_flag, AZP_ERR_CAPACITY);
+      kind = 2;
+      break;
+    }
+    if (lane == 0) path[depth] = node * A + a;
+    depth++;
+    if (tm == 1) bb_set<NW>(x, a); else bb_set<NW>(o, a);
+    tm = 3 - tm;
+    last = a;
+    result = warp_result<NW>(rp, x, o, lane);
+    if (result != 0) continue;
+    if (ch < 0) { kind = 0; break; }     // reached a child that has not been expanded
+    node = ch;
+    nparent = cn;
+  }
+  if (kind == 0) emit_leaf<NW>(tv, g, x, o, tm, last, compact, parity, lane);
+  if (lane == 0) {
+    tv.path_len[g] = depth;
+    tv.leaf_kind[g] = (uint8_t)kind;
+    tv.leaf_tvalue[g] = tvalue;
+    if (kind != 0) tv.leaf_slot[g] = -1;
+    count(tv, CNT_SCANNED, scanned);
+    count(tv, CNT_PATH, (unsigned long long)depth);
+    if (kind == 0) count(tv, CNT_EVALS, 1);
+    if (kind == 1) count(tv, CNT_TERMINAL, 1);
+  }
+}
+
+// ---- expand the evaluated leaf and back the value up (mcts.py:136-141, 50-64, 76-82) --------
+template <int NW>
+__global__ void expand_backup_kernel(RulesParams rp, TreeView tv, int n, const float* __restrict__ policy,
+                                     const float* __restrict__ value, int by_slot) {
+  int g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (g >= n || !tv.active[g]) return;
+  const int kind = tv.leaf_kind[g];
+  if (kind == 2) return;
+  const int A = rp.A;
+  const size_t gbase = (size_t)g * tv.cap * A;
+  const int32_t* path = tv.path + (size_t)g * tv.maxd;
+  const int depth = tv.path_len[g];
+  float v;
+  if (kind == 0) {
+    const int slot = tv.leaf_slot[g];
+    const size_t row = (size_t)(by_slot ? slot : g);
+    v = value[row];
+    int nid = tv.node_count[g];
+    if (nid >= tv.cap) {
+      if (lane == 0) atomicExch(tv.error_flag, AZP_ERR_CAPACITY);
+      return;
+    }
+    BB<NW> lx = bb_load<NW>(tv.leaf_x + (size_t)slot * NW), lo = bb_load<NW>(tv.leaf_o + (size_t)slot * NW);
+    const size_t nb = gbase + (size_t)nid * A;
+    const float* prow = policy + row * A;
+    for (int a = lane; a < A; a += 32) {
+      bool legal = !(bb_test<NW>(lx, a) || bb_test<NW>(lo, a));
+      tv.P[nb + a] = legal ? prow[a] : 0.f;     // prior = policy[r,c], not renormalised (mcts.py:63)
+      tv.N[nb + a] = 0;
+      tv.W[nb + a] = 0.0;
+      tv.child[nb + a] = -1;
+    }
+    if (lane == 0) {
+      tv.node_count[g] = nid + 1;
+      if (depth > 0) tv.child[gbase + path[depth - 1]] = nid;
+      count(tv, CNT_EXPANSIONS, 1);
+    }
+  } else {
+    v = tv.leaf_tvalue[g];
+  }
+  // node.backup(-value): the leaf's own statistics (last edge) take -v, signs alternate upwards
+  for (int i = lane; i < depth; i += 32) {
+    const size_t e = gbase + path[i];
+    const double val = ((depth - 1 - i) & 1) ? (double)v : -(double)v;
+    tv.N[e] += 1;
+    tv.W[e] = __dadd_rn(tv.W[e], val);
+  }
+  if (lane == 0) {
+    tv.root_n[g] += 1;
+    count(tv, CNT_SIMS, 1);
+  }
+}
+
+// ---- root visit counts (mcts.py:144) -----------------------------------------------------------
+__global__ void root_visits_kernel(TreeView tv, int n, int32_t* __restrict__ visits) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (size_t)n * tv.A) return;
+  int g = i / tv.A, a = i % tv.A;
+  uint64_t occ = tv.root_x[(size_t)g * tv.NW + (a >> 6)] | tv.root_o[(size_t)g * tv.NW + (a >> 6)];
+  bool legal = !((occ >> (a & 63)) & 1);
+  visits[i] = legal ? tv.N[(size_t)g * tv.cap * tv.A + a] : 0;
+}
+
+__global__ void leaf_states_kernel(TreeView tv, int n, uint64_t* x, uint64_t* o, uint8_t* tm, int16_t* last,
+                                   uint8_t* kind) {
+  int g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= n) return;
+  int k = tv.leaf_kind[g];
+  kind[g] = (uint8_t)k;
+  int slot = tv.leaf_slot[g];
+  for (int w = 0; w < tv.NW; w++) {
+    x[(size_t)g * tv.NW + w] = (k == 0) ? tv.leaf_x[(size_t)slot * tv.NW + w] : 0;
+    o[(size_t)g * tv.NW + w] = (k == 0) ? tv.leaf_o[(size_t)slot * tv.NW + w] : 0;
+  }
+  tm[g] = (k == 0) ? tv.leaf_tm[slot] : 0;
+  last[g] = (k == 0) ? tv.leaf_last[slot] : (int16_t)-1;
+}
+
+// ================= self-play / arena episode machinery (self_play.py:47-72) ====================
+struct EpisodeView {
+  uint8_t* status;          // [G]
+  uint16_t* moves;          // [G][max_plies]
+  float* pi_hist;           // [G][max_plies][A]
+  uint8_t* result;          // [G] result of a finished game
+  const double* temperature; int n_temperature;
+  long long* sched;         // {next local index, n_local, finished, local_first}
+  float* raw_planes; float* raw_pi; int32_t* raw_z; int32_t* raw_count; long long raw_capacity;
+  int max_plies;
+  uint64_t seed;
+};
+
+// Hand the slot its next game (or park it).  Lane 0 only.
+__device__ __forceinline__ void seat_next_game(const TreeView& tv, const EpisodeView& ev, int g, int NW, int arena) {
+  long long idx = atomicAdd((unsigned long long*)&ev.sched[0], 1ull);
+  if (idx < ev.sched[1]) {
+    long long gid = ev.sched[3] + idx;
+    for (int k = 0; k < NW; k++) { tv.root_x[(size_t)g * NW + k] = 0; tv.root_o[(size_t)g * NW + k] = 0; }
+    // arena: X (candidate) moves first in even games, O in odd games (evaluator.py:64-69)
+    int first = (arena && (gid & 1)) ? 2 : 1;
+    tv.root_tm[g] = (uint8_t)first;
+    tv.root_last[g] = -1;
+    tv.ply[g] = 0;
+    tv.game_id[g] = gid;
+    tv.active[g] = 1;
+    tv.net_of_game[g] = (uint8_t)(arena ? (first == 1 ? 0 : 1) : 0);
+    ev.status[g] = SLOT_PLAYING;
+  } else {
+    tv.active[g] = 0;
+    ev.status[g] = SLOT_IDLE;
+  }
+}
+
+__global__ void seat_games_kernel(TreeView tv, EpisodeView ev, int n, int arena) {
+  int g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= n) return;
+  seat_next_game(tv, ev, g, tv.NW, arena);
+}
+
+// MCTS.run epilogue + the worker's bookkeeping: pi from root visits at T(ply), sample the move,
+// record (pi, move), play it, detect the end of the game.
+template <int NW>
+__global__ void end_move_kernel(RulesParams rp, TreeView tv, EpisodeView ev, int n, int arena) {
+  int g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (g >= n || ev.status[g] != SLOT_PLAYING) return;
+  const int A = rp.A;
+  BB<NW> x = bb_load<NW>(tv.root_x + (size_t)g * NW), o = bb_load<NW>(tv.root_o + (size_t)g * NW);
+  const int ply = tv.ply[g];
+  int tm = tv.root_tm[g];
+  // temperature index: the ply in self-play (self_play.py:53); in the arena the mover's own step
+  // counter, 0,1,2.. for the first mover and 1,2,3.. for the second (evaluator.py:71-90)
+  int tidx = arena ? ((ply & 1) ? ply / 2 + 1 : ply / 2) : ply;
+  if (tidx >= ev.n_temperature) tidx = ev.n_temperature - 1;
+  double T = ev.temperature[tidx];
+  if (T <= 1e-7) T = 1e-7;
+  const int32_t* Nroot = tv.N + (size_t)g * tv.cap * A;
+  float* pi = ev.pi_hist + ((size_t)g * ev.max_plies + ply) * A;
+
+  double mx = -1.0e300;
+  int k = 0;
+  for (int a = lane; a < A; a += 32) {
+    if (bb_test<NW>(x, a) || bb_test<NW>(o, a)) continue;
+    mx = fmax(mx, (double)logf((float)Nroot[a] + 1e-8f) / T);
+    k++;
+  }
+  mx = warp_max_d(mx);
+  k = warp_sum_i(k);
+  double sum = 0.0;
+  for (int a = lane; a < A; a += 32) {
+    if (bb_test<NW>(x, a) || bb_test<NW>(o, a)) continue;
+    sum += exp((double)logf((float)Nroot[a] + 1e-8f) / T - mx);
+  }
+  sum = warp_sum_d(sum);
+  const bool uniform = !(sum >= 1e-8);
+
+  // action ~ Categorical(probs) by inverse CDF over the children in row-major order (mcts.py:177)
+  Philox rng = philox_for_game(ev.seed, tv.game_id[g]);
+  uint32_t r[4];
+  rng(0u, (uint32_t)ply, AZP_RNG_ACTION, 0u, r);
+  const double u = u01_open(r[0], r[1]);
+  double run = 0.0;        // probability mass of all earlier chunks
+  int action = -1, lastlegal = -1;
+  for (int a0 = 0; a0 < A; a0 += 32) {
+    int a = a0 + lane;
+    bool legal = a < A && !(bb_test<NW>(x, a) || bb_test<NW>(o, a));
+    double p = 0.0;
+    if (legal) p = uniform ? 1.0 / k : exp((double)logf((float)Nroot[a] + 1e-8f) / T - mx) / sum;
+    if (!arena && a < A) pi[a] = (float)p;
+    double c = p;            // inclusive scan inside the chunk
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+      double t = __shfl_up_sync(AZP_FULL, c, off);
+      if (lane >= off) c += t;
+    }
+    c += run;
+    unsigned hit = __ballot_sync(AZP_FULL, legal && c > u);
+    unsigned leg = __ballot_sync(AZP_FULL, legal);
+    if (leg) lastlegal = a0 + 31 - __clz(leg);
+    if (action < 0 && hit) action = a0 + __ffs(hit) - 1;
+    run = __shfl_sync(AZP_FULL, c, 31);
+  }
+  if (action < 0) action = lastlegal;   // u beyond the rounded total mass
+  if (action < 0) {                     // no legal move on a playing game: cannot happen
+    if (lane == 0) atomicExch(tv.error_flag, AZP_ERR_INVALID_MOVE);
+    return;
+  }
+  if (tm == 1) bb_set<NW>(x, action); else bb_set<NW>(o, action);
+  int res = warp_result<NW>(rp, x, o, lane);
+  if (res == 0 && ply + 1 >= ev.max_plies) res = 3;     // ply cap (only when max_plies < B*B): scored as a draw
+  if (lane == 0) {
+    ev.moves[(size_t)g * ev.max_plies + ply] = (uint16_t)action;
+    bb_store<NW>(tv.root_x + (size_t)g * NW, x);
+    bb_store<NW>(tv.root_o + (size_t)g * NW, o);
+    tv.root_tm[g] = (uint8_t)(3 - tm);
+    tv.root_last[g] = (int16_t)action;
+    tv.ply[g] = ply + 1;
+    if (arena) tv.net_of_game[g] = (uint8_t)((3 - tm) == 1 ? 0 : 1);
+    count(tv, CNT_PLIES, 1);
+    if (res) {
+      ev.result[g] = (uint8_t)res;
+      ev.status[g] = SLOT_PENDING;
+      tv.active[g] = 0;
+      count(tv, CNT_GAMES, 1);
+      count(tv, res == 1 ? CNT_XWINS : (res == 2 ? CNT_OWINS : CNT_DRAWS), 1);
+    }
+  }
+}
+
+// Emit the finished game's positions as raw (planes, pi, z) rows and seat the next game.
+// z = 0 on a draw, +1 if the player to move at that position won, else -1 (self_play.py:71).
+template <int NW>
+__global__ void finish_games_kernel(RulesParams rp, TreeView tv, EpisodeView ev, int n, int arena) {
+  int g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (g >= n || ev.status[g] != SLOT_PENDING) return;
+  const int A = rp.A;
+  const int L = tv.ply[g];
+  if (!arena) {
+    int base = 0;
+    if (lane == 0) {
+      base = atomicAdd(ev.raw_count, L);
+      if ((long long)base + L > ev.raw_capacity) { atomicSub(ev.raw_count, L); base = -1; }
+    }
+    base = __shfl_sync(AZP_FULL, base, 0);
+    if (base < 0) return;      // slab full: stay pending, retry after the next drain
+    const int res = ev.result[g];
+    BB<NW> x, o;
+#pragma unroll
+    for (int k = 0; k < NW; k++) { x.w[k] = 0; o.w[k] = 0; }
+    int tm = 1, last = -1;     // self-play games start with X on the empty board (games.py:29)
+    for (int p = 0; p < L; p++) {
+      float* op = ev.raw_planes + (size_t)(base + p) * 4 * A;
+      for (int a = lane; a < A; a += 32) {
+        bool isx = bb_test<NW>(x, a), iso = bb_test<NW>(o, a);
+        op[a] = ((tm == 1) ? isx : iso) ? 1.f : 0.f;
+        op[A + a] = ((tm == 1) ? iso : isx) ? 1.f : 0.f;
+        op[2 * A + a] = (a == last) ? 1.f : 0.f;
+        op[3 * A + a] = 0.f;
+      }
+      const float* ip = ev.pi_hist + ((size_t)g * ev.max_plies + p) * A;
+      float* opi = ev.raw_pi + (size_t)(base + p) * A;
+      for (int a = lane; a < A; a += 32) opi[a] = ip[a];
+      if (lane == 0) ev.raw_z[base + p] = res == 3 ? 0 : (res == tm ? 1 : -1);
+      int mv = ev.moves[(size_t)g * ev.max_plies + p];
+      if (tm == 1) bb_set<NW>(x, mv); else bb_set<NW>(o, mv);
+      tm = 3 - tm;
+      last = mv;
+    }
+    if (lane == 0) count(tv, CNT_POSITIONS, (unsigned long long)L);
+  }
+  if (lane == 0) {
+    atomicAdd((unsigned long long*)&ev.sched[2], 1ull);
+    seat_next_game(tv, ev, g, NW, arena);
+  }
+}
+
+// after the augmenting writer: advance the output cursor and empty the raw slab
+__global__ void drain_raw_kernel(int32_t* raw_count, long long* out_written, int mult, unsigned long long* counters) {
+  long long nraw = *raw_count;
+  *out_written += nraw * mult;
+  atomicAdd(counters + CNT_EXAMPLES, (unsigned long long)(nraw * mult));
+  *raw_count = 0;
+}
+
+// ================= host side ====================================================================
+static inline int warp_grid(int n) { return (n * 32 + 127) / 128; }
+
+static EpisodeView episode_view(azp_engine* e) {
+  EpisodeView ev;
+  ev.status = e->d_status;
+  ev.moves = e->d_moves;
+  ev.pi_hist = e->d_pi_hist;
+  ev.result = e->d_result;
+  ev.temperature = e->d_temperature;
+  ev.n_temperature = e->n_temperature;
+  ev.sched = e->d_sched;
+  ev.raw_planes = e->d_raw_planes; ev.raw_pi = e->d_raw_pi; ev.raw_z = e->d_raw_z;
+  ev.raw_count = e->d_raw_count; ev.raw_capacity = e->raw_capacity;
+  ev.max_plies = e->max_plies;
+  ev.seed = e->cfg.seed;
+  return ev;
+}
+
+int azp_tree_begin_move(azp_engine* e, int n, int emit, int compact, int parity, cudaStream_t s) {
+  AZP_DISPATCH_NW(e->NW, begin_move_kernel, warp_grid(n), 128, 0, s, e->rp, e->tv, n, emit, compact, parity);
+  azp_count_launch();
+  return azp_check_launch();
+}
+int azp_tree_root_expand(azp_engine* e, int n, const float* policy, int by_slot, int add_noise, cudaStream_t s) {
+  AZP_DISPATCH_NW(e->NW, root_expand_kernel, warp_grid(n), 128, 0, s, e->rp, e->tv, n, policy, by_slot, add_noise,
+                  e->cfg.dirichlet_alpha, e->cfg.dirichlet_weight, e->cfg.seed);
+  azp_count_launch();
+  return azp_check_launch();
+}
+int azp_tree_select(azp_engine* e, int n, int compact, int parity, cudaStream_t s) {
+  AZP_DISPATCH_NW(e->NW, select_kernel, warp_grid(n), 128, 0, s, e->rp, e->tv, n, e->cfg.c_puct, compact, parity);
+  azp_count_launch();
+  return azp_check_launch();
+}
+int azp_tree_expand_backup(azp_engine* e, int n, const float* policy, const float* value, int by_slot, cudaStream_t s) {
+  AZP_DISPATCH_NW(e->NW, expand_backup_kernel, warp_grid(n), 128, 0, s, e->rp, e->tv, n, policy, value, by_slot);
+  azp_count_launch();
+  return azp_check_launch();
+}
+int azp_tree_root_visits(azp_engine* e, int n, int32_t* visits, cudaStream_t s) {
+  root_visits_kernel<<<(int)(((size_t)n * e->A + 255) / 256), 256, 0, s>>>(e->tv, n, visits);
+  azp_count_launch();
+  return azp_check_launch();
+}
+int azp_tree_leaf_states(azp_engine* e, int n, uint64_t* x, uint64_t* o, uint8_t* tm, int16_t* last, uint8_t* kind,
+                         cudaStream_t s) {
+  leaf_states_kernel<<<(n + 127) / 128, 128, 0, s>>>(e->tv, n, x, o, tm, last, kind);
+  azp_count_launch();
+  return azp_check_launch();
+}
+int azp_episode_seat(azp_engine* e, int n, int arena, cudaStream_t s) {
+  seat_games_kernel<<<(n + 127) / 128, 128, 0, s>>>(e->tv, episode_view(e), n, arena);
+  azp_count_launch();
+  return azp_check_launch();
+}
+int azp_episode_end_move(azp_engine* e, int n, int arena, cudaStream_t s) {
+  EpisodeView ev = episode_view(e);
+  AZP_DISPATCH_NW(e->NW, end_move_kernel, warp_grid(n), 128, 0, s, e->rp, e->tv, ev, n, arena);
+  azp_count_launch();
+  return azp_check_launch();
+}
+int azp_episode_finish(azp_engine* e, int n, int arena, cudaStream_t s) {
+  EpisodeView ev = episode_view(e);
+  AZP_DISPATCH_NW(e->NW, finish_games_kernel, warp_grid(n), 128, 0, s, e->rp, e->tv, ev, n, arena);
+  azp_count_launch();
+  return azp_check_launch();
+}
+int azp_episode_drain(azp_engine* e, long long* out_written_dev, int mult, cudaStream_t s) {
+  drain_raw_kernel<<<1, 1, 0, s>>>(e->d_raw_count, out_written_dev, mult, e->tv.counters);
+  azp_count_launch();
+  return azp_check_launch();
+}

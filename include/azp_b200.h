@@ -1,0 +1,181 @@
+/* azp_b200.h -- C ABI of the B200-native batched self-play engine.
+ *
+ * This is the drop-in boundary for the ONE hot path of AlphaZero-Piskvorky
+ * (SURVEY.md section 8b).  The reference has no FFI layer -- its seams are plain
+ * Python call signatures -- so every entry point below names the reference
+ * callable it replaces (file:line relative to /root/reference/).  The Python
+ * facade in alphazero-piskvorky_b200/ binds these with ctypes and mirrors the
+ * reference's class/method names on top.
+ *
+ * Conventions
+ *   - every function returns an int status (AZP_OK == 0); no exceptions or aborts
+ *     cross the ABI; azp_last_error() gives the text of the last failure;
+ *   - all buffers are caller-allocated DEVICE memory unless the name says host;
+ *     the engine owns only its node table and workspaces;
+ *   - `stream` is a cudaStream_t passed as void*; calls are asynchronous w.r.t.
+ *     the host unless documented otherwise;
+ *   - one engine per device per process; not thread-safe;
+ *   - boards are bitboards: bit (r*B + c) of a little-endian array of
+ *     AZP_WORDS(B) uint64 words per colour; to_move is 1 (X) or 2 (O);
+ *     last is r*B+c of the last move or -1; results are 0 none / 1 X / 2 O / 3 draw.
+ */
+#ifndef AZP_B200_H
+#define AZP_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define AZP_OK 0
+#define AZP_ERR_INVALID_ARG 1
+#define AZP_ERR_CUDA 2
+#define AZP_ERR_INVALID_MOVE 3   /* analogue of ValueError("Invalid move"), games.py:76-77 */
+#define AZP_ERR_CAPACITY 4       /* node table / slab overflow reported by the device flag */
+#define AZP_ERR_UNSUPPORTED 5
+#define AZP_ERR_NO_WEIGHTS 6
+#define AZP_MORE 100             /* driver stopped because the output slab is full; call again */
+
+#define AZP_MAX_BOARD 19
+#define AZP_MAX_WORDS 6
+#define AZP_WORDS(B) (((B) * (B) + 63) / 64)
+
+#define AZP_NET_STEM 0           /* GomokuNet, alphazero/net.py:28-72 */
+#define AZP_NET_TOWER 1          /* residual tower of BASELINE config 4 */
+#define AZP_DTYPE_F32 0          /* SIMT fp32 path: <=1e-5 vs the reference net */
+#define AZP_DTYPE_BF16 1         /* tcgen05 implicit-GEMM path: <=2e-2 */
+#define AZP_AUGMENT_REFERENCE 0  /* 4 outputs exactly as self_play.py:94-108 is written */
+#define AZP_AUGMENT_D4 1         /* 8 outputs, consistent dihedral group action */
+#define AZP_AUGMENT_NONE 2       /* 1 output (raw positions, used before an all-gather) */
+
+typedef struct azp_engine azp_engine;
+
+typedef struct azp_config {
+  int32_t board;            /* BOARD_SIZE, constants.py:2 */
+  int32_t win_length;       /* WIN_LENGTH, constants.py:3 */
+  int32_t games;            /* concurrent game slots on this GPU */
+  int32_t sims;             /* MCTS simulations per move (MCTS.num_simulations, mcts.py:94) */
+  double c_puct;            /* mcts.py:95 */
+  double dirichlet_alpha;   /* mcts.py:91 */
+  double dirichlet_weight;  /* mcts.py:92 */
+  int32_t net_kind;         /* AZP_NET_* */
+  int32_t net_dtype;        /* AZP_DTYPE_* */
+  int32_t tower_blocks;     /* tower only */
+  int32_t tower_channels;   /* tower only */
+  int32_t augment_mode;     /* AZP_AUGMENT_* */
+  int32_t max_plies;        /* 0 = board*board */
+  uint64_t seed;            /* Philox key; streams are keyed by GLOBAL game id */
+  int32_t rank, world;      /* game sharding: this engine plays global ids == rank (mod world) blocks */
+  int32_t device;           /* CUDA device ordinal */
+  int32_t reserved;
+} azp_config;
+
+typedef struct azp_counters {
+  uint64_t simulations;     /* iterations of the loop at mcts.py:123-141, all games */
+  uint64_t leaf_evals;      /* network evaluations (non-terminal leaves + roots) */
+  uint64_t terminal_leaves; /* simulations that ended on a terminal position */
+  uint64_t children_scanned;/* sum over select steps of slots scanned */
+  uint64_t path_length;     /* sum over simulations of select steps */
+  uint64_t expansions;      /* nodes expanded */
+  uint64_t games_finished;
+  uint64_t plies;           /* moves played */
+  uint64_t positions;       /* raw positions emitted */
+  uint64_t examples;        /* examples written after augmentation */
+  uint64_t kernel_launches; /* launches of this library's kernels */
+  uint64_t x_wins, o_wins, draws;
+} azp_counters;
+
+int azp_version(void);
+int azp_create(const azp_config* cfg, azp_engine** out);
+void azp_destroy(azp_engine* e);
+const char* azp_last_error(const azp_engine* e);   /* e may be NULL: error of the last failed create */
+
+/* ---- stateless batched rules primitives (each parity-testable alone) -------- */
+/* cells: int8 [n][B*B], 0 empty / 1 X / 2 O  <->  bitboards x,o: uint64 [n][AZP_WORDS(B)] */
+int azp_pack_boards(int board, int n, const int8_t* cells, uint64_t* x, uint64_t* o, void* stream);
+int azp_unpack_boards(int board, int n, const uint64_t* x, const uint64_t* o, int8_t* cells, void* stream);
+/* Gomoku.get_legal_actions, games.py:35-47: mask uint8 [n][B*B] of empties (no terminal guard) */
+int azp_legal_mask(int board, int n, const uint64_t* x, const uint64_t* o, uint8_t* mask, void* stream);
+/* Gomoku.apply_action, games.py:64-82: in place; status[i]=AZP_ERR_INVALID_MOVE and board i
+ * untouched when the cell is occupied or off-board */
+int azp_apply_moves(int board, int n, uint64_t* x, uint64_t* o, uint8_t* to_move, int16_t* last,
+                    const int16_t* moves, int32_t* status, void* stream);
+/* Gomoku.is_terminal/_check_line/get_game_result, games.py:133-179, 212-227 (full-board rule
+ * incl. overlines and the row-major-first line start on two-winner boards) */
+int azp_terminal_status(int board, int win_length, int n, const uint64_t* x, const uint64_t* o,
+                        uint8_t* result, void* stream);
+/* Gomoku.encode, games.py:86-129: float32 [n][4][B][B] */
+int azp_encode(int board, int n, const uint64_t* x, const uint64_t* o, const uint8_t* to_move,
+               const int16_t* last, float* planes, void* stream);
+/* MCTS.run epilogue, mcts.py:143-170: visit counts int32 [n][B*B] (+ legal mask) and a
+ * temperature per row -> pi float32 [n][B*B] */
+int azp_extract_policy(int board, int n, const int32_t* visits, const uint8_t* legal,
+                       const double* temperature, float* pi, void* stream);
+/* SelfPlayManager._augment_symmetries, self_play.py:94-108 (mode REFERENCE) or the 8-fold D4
+ * action (mode D4): n positions -> n*mult examples, position-major */
+int azp_augment_write(int board, int mode, int n, const float* planes, const float* pi,
+                      const int32_t* z, float* out_planes, float* out_pi, int32_t* out_z, void* stream);
+
+/* ---- network ------------------------------------------------------------------ */
+/* weights: float32 blob on the HOST holding the reference state_dict tensors concatenated in
+ * key order (stem: conv1.weight, conv1.bias, conv2.*, conv3.*, policy_conv.*, policy_fc.*,
+ * value_conv.*, value_fc1.*, value_fc2.*; net.py:37-53), PyTorch layouts.  slot 0 = the
+ * self-play / candidate net, slot 1 = the arena baseline.  Synchronous. */
+int azp_load_weights(azp_engine* e, int slot, const float* host_blob, size_t n_floats);
+/* same, blob already on this device (after an NCCL broadcast of promoted weights) */
+int azp_load_weights_device(azp_engine* e, int slot, const float* dev_blob, size_t n_floats, void* stream);
+size_t azp_weight_count(const azp_engine* e);
+/* GomokuNet.forward + controller.py:33-55: planes float32 [n][4][B][B] ->
+ * logits [n][B*B] (raw), policy [n][B*B] (softmax over ALL cells), value [n]; any output may be NULL */
+int azp_net_forward(azp_engine* e, int slot, int n, const float* planes, float* logits,
+                    float* policy, float* value, void* stream);
+
+/* ---- search, step by step (lets a host evaluator be injected: the operator-level hook
+ *      policy_value_fn of mcts.py:88-93) --------------------------------------------- */
+/* MCTS.run prologue, mcts.py:106: new trees rooted at n positions (n <= games) */
+int azp_search_begin(azp_engine* e, int n, const uint64_t* x, const uint64_t* o,
+                     const uint8_t* to_move, const int16_t* last, const int32_t* ply,
+                     const int64_t* game_id, void* stream);
+/* mcts.py:109-120: root priors from policy float32 [n][B*B]; Dirichlet mix if add_noise */
+int azp_root_expand(azp_engine* e, const float* policy, int add_noise, void* stream);
+/* mcts.py:126-129: one PUCT descent per game; leaves are left in the engine */
+int azp_select(azp_engine* e, void* stream);
+/* the leaves of the last azp_select: kind uint8 [n] (0 = needs evaluation, 1 = terminal,
+ * 2 = idle), boards as for azp_encode */
+int azp_leaf_states(azp_engine* e, uint64_t* x, uint64_t* o, uint8_t* to_move, int16_t* last,
+                    uint8_t* kind, void* stream);
+/* mcts.py:131-141: expand the evaluated leaves with policy float32 [n][B*B] / value float32 [n]
+ * (indexed by game), terminal leaves use their game result; back up along each path */
+int azp_expand_backup(azp_engine* e, const float* policy, const float* value, void* stream);
+/* root child visit counts int32 [n][B*B] (the reference computes them at mcts.py:144) */
+int azp_root_visits(azp_engine* e, int32_t* visits, void* stream);
+/* whole search with the engine's own net: begin + root eval + S x (select, net, expand_backup) */
+int azp_search(azp_engine* e, int slot, int n, const uint64_t* x, const uint64_t* o,
+               const uint8_t* to_move, const int16_t* last, const int32_t* ply,
+               const int64_t* game_id, int add_noise, int32_t* visits, void* stream);
+
+/* ---- drivers ------------------------------------------------------------------- */
+/* temperature per ply, host doubles (default_temperature_schedule, self_play.py:24-26, is
+ * evaluated by the facade so user-supplied schedules keep working) */
+int azp_set_temperature_table(azp_engine* e, const double* host_table, int n);
+/* SelfPlayManager.generate_self_play, self_play.py:110-159 + _worker, :29-77.
+ * Plays global game ids [first_game, first_game + n_games) that belong to this rank, S sims per
+ * move with root noise, writes augmented examples to out_* (capacity in examples).  Returns
+ * AZP_OK when every game is finished, AZP_MORE when out_* ran full (drain, then call again with
+ * resume != 0).  *host_written = examples written by this call.  Synchronous at return. */
+int azp_selfplay_run(azp_engine* e, int64_t first_game, int64_t n_games, int resume,
+                     int max_move_steps, float* out_planes, float* out_pi, int32_t* out_z,
+                     int64_t capacity, int64_t* host_written, void* stream);
+/* ModelEvaluator.evaluate, evaluator.py:38-122: candidate (slot 0, plays X) vs baseline (slot 1,
+ * plays O); game i has X to move first iff i is even; no root noise; T = table[step].
+ * host_wld = {candidate wins, baseline wins, draws} for this rank's games. */
+int azp_arena_run(azp_engine* e, int64_t first_game, int64_t n_games, int64_t* host_wld, void* stream);
+int azp_get_counters(azp_engine* e, azp_counters* host_out);
+int azp_reset_counters(azp_engine* e);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AZP_B200_H */

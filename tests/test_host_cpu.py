@@ -1,0 +1,173 @@
+"""CPU-side tests (no GPU): the C-ABI library loads and exports every symbol the header
+declares, the engine refuses to run without a device, host logic, and the world_size-2
+gloo path of the multi-GPU plumbing."""
+
+import ctypes as C
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def az():
+    import alphazero_piskvorky_b200 as az
+    return az
+
+
+def header_symbols():
+    text = open(os.path.join(ROOT, "include", "azp_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(azp_[a-z_0-9]+)\s*\(", text)))
+
+
+def test_library_exports_every_header_symbol(az):
+    lib = az._lib.load()
+    names = header_symbols()
+    assert len(names) >= 28
+    assert sorted(az._lib.SIGNATURES) == names, "ctypes table and header disagree"
+    for n in names:
+        assert hasattr(lib, n), n
+    out = subprocess.run(["nm", "-D", az._lib.LIB_PATH], capture_output=True, text=True).stdout
+    exported = set(re.findall(r" T (azp_[a-z_0-9]+)", out))
+    assert set(names) <= exported
+    assert lib.azp_version() >= 100
+
+
+def test_library_is_sm100a_native(az):
+    """The shipped cubin targets sm_100a (no PTX-JIT fallback for other archs is relied on)."""
+    out = subprocess.run(["cuobjdump", "-lelf", az._lib.LIB_PATH], capture_output=True, text=True).stdout
+    assert "sm_100a" in out
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU failure mode")
+def test_engine_fails_loudly_without_gpu(az):
+    lib = az._lib.load()
+    cfg = az._lib.Config(board=5, win_length=4, games=4, sims=10, c_puct=2.0, dirichlet_alpha=0.3,
+                         dirichlet_weight=0.25, net_kind=0, net_dtype=0, tower_blocks=0, tower_channels=0,
+                         augment_mode=1, max_plies=0, seed=0, rank=0, world=1, device=0, reserved=0)
+    h = C.c_void_p()
+    st = lib.azp_create(C.byref(cfg), C.byref(h))
+    assert st == az._lib.ERR_CUDA and not h.value
+    assert b"no CPU fallback" in lib.azp_last_error(None)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        az.Engine(board=5, win_length=4, games=4, sims=10)
+    with pytest.raises(RuntimeError):
+        az.Gomoku(5, 4).get_legal_actions()
+
+
+def test_create_rejects_bad_config(az):
+    lib = az._lib.load()
+    h = C.c_void_p()
+    for kw in (dict(board=2), dict(board=20), dict(win_length=9, board=5), dict(games=0), dict(sims=0),
+               dict(world=2, rank=2), dict(net_dtype=7)):
+        base = dict(board=5, win_length=4, games=4, sims=10, c_puct=2.0, dirichlet_alpha=0.3, dirichlet_weight=0.25,
+                    net_kind=0, net_dtype=0, tower_blocks=0, tower_channels=0, augment_mode=1, max_plies=0, seed=0,
+                    rank=0, world=1, device=0, reserved=0)
+        base.update(kw)
+        cfg = az._lib.Config(**base)
+        assert lib.azp_create(C.byref(cfg), C.byref(h)) == az._lib.ERR_INVALID_ARG, kw
+
+
+def test_flatten_state_dict_matches_reference_layout(az):
+    net = az.GomokuNet(board_size=9)
+    sd = net.state_dict()
+    assert list(sd.keys()) == [f"{k}.{f}" for k in ("conv1", "conv2", "conv3", "policy_conv", "policy_fc",
+                                                     "value_conv", "value_fc1", "value_fc2")
+                               for f in ("weight", "bias")]
+    blob = az.flatten_state_dict(sd)
+    assert blob.dtype == np.float32 and blob.size == sum(v.numel() for v in sd.values()) == 131132
+    assert np.array_equal(blob[:32 * 36], sd["conv1.weight"].numpy().reshape(-1))
+    tower = az.GomokuTowerNet(board_size=9, channels=32, blocks=2)
+    tsd = {k: v for k, v in tower.state_dict().items() if not k.endswith("num_batches_tracked")}
+    tblob = az.flatten_state_dict(tower.state_dict(), az.NET_TOWER, 2)
+    assert tblob.size == sum(v.numel() for v in tsd.values())
+    from oracle import net as onet
+    assert set(onet.tower_shapes(9, 32, 2)) == set(tsd)
+
+
+def test_reference_shapes_and_schedule(az):
+    from oracle import net as onet, selfplay
+    for b, count in ((5, 100164), (9, 131132), (15, 325964), (19, 662292)):
+        assert sum(int(np.prod(s)) for s in onet.stem_shapes(b).values()) == count
+    for m in (0, 10, 100, 225):
+        assert az.default_temperature_schedule(m) == selfplay.default_temperature_schedule(m)
+
+
+def test_replay_buffer_host_and_ring_semantics(az):
+    from oracle import replay
+    buf, ref = az.ReplayBuffer(10), replay.Fifo(10)
+    for chunk in (list(range(7)), list(range(100, 108)), [5]):
+        buf.extend(chunk); ref.extend(chunk)
+    assert buf.all() == ref.all() and len(buf) == len(ref) == 10
+    assert list(az.ReplayBuffer(10).sample_batch(5)) == []
+    # ring: same eviction order as the deque
+    ring, ref = az.ReplayBuffer(10), replay.Fifo(10)
+    k = 0
+    for n in (4, 5, 3, 12, 1):
+        planes = torch.arange(k, k + n, dtype=torch.float32).view(n, 1, 1, 1).expand(n, 4, 2, 2).contiguous()
+        pi = torch.arange(k, k + n, dtype=torch.float32).view(n, 1, 1).expand(n, 2, 2).contiguous()
+        z = torch.arange(k, k + n, dtype=torch.int32)
+        ring.extend_device(planes, pi, z)
+        ref.extend(list(range(k, k + n)))
+        k += n
+        got = ring.device_all()
+        assert got[2].tolist() == ref.all()
+        assert got[0][:, 0, 0, 0].tolist() == [float(v) for v in ref.all()]
+    assert ring.device_len() == 10
+    s = ring.sample_device(4)
+    assert len(set(s[2].tolist())) == 4
+
+
+def test_rank_block_partitions_games(az):
+    from alphazero_piskvorky_b200 import dist as d
+    for total, world in ((16384, 8), (400, 8), (7, 3), (2, 4), (0, 2)):
+        blocks = [d.rank_block(100, total, r, world) for r in range(world)]
+        assert sum(c for _, c in blocks) == total
+        nxt = 100
+        for first, c in blocks:
+            assert first == nxt
+            nxt += c
+    assert d.rank_block(0, 16384, 3, 8) == (6144, 2048)           # config 3: 2048 games per GPU
+
+
+def _gloo_worker(rank, world, port, q):
+    import torch.distributed as dist
+    sys.path.insert(0, ROOT)
+    from alphazero_piskvorky_b200 import dist as d
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    n = 3 + 2 * rank                                      # ragged contributions
+    planes = torch.full((n, 4, 3, 3), float(rank))
+    pi = torch.full((n, 3, 3), float(rank) + 0.5)
+    z = torch.full((n,), rank, dtype=torch.int32)
+    gp, gpi, gz = d.all_gather_examples(planes, pi, z)
+    blob = torch.arange(10, dtype=torch.float32) if rank == 0 else torch.zeros(10)
+    d.broadcast_weights(blob, src=0)
+    wld = d.all_reduce_wld(rank + 1, 2, 0, device="cpu")
+    q.put((rank, gz.tolist(), gp[:, 0, 0, 0].tolist(), gpi.shape, blob.tolist(), wld))
+    dist.destroy_process_group()
+
+
+def test_multi_gpu_plumbing_on_gloo_world2():
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_gloo_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    results = [q.get(timeout=180) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, gz, gp0, pishape, blob, wld in results:
+        assert gz == [0, 0, 0, 1, 1, 1, 1, 1]              # rank order, trimmed to the true counts
+        assert gp0 == [0.0] * 3 + [1.0] * 5 and tuple(pishape) == (8, 3, 3)
+        assert blob == [float(i) for i in range(10)]
+        assert wld == (3, 4, 0)
