@@ -177,6 +177,19 @@ class Engine:
                    self.h)
         return st, planes, pi, z, int(written.value)
 
+    def selfplay_all(self, n_games, first_game=0, capacity=None):
+        """Run to completion, draining the output slab whenever it fills (AZP_MORE).  Returns
+        (planes, pi, z) with every example generated, in generation order."""
+        chunks, out, resume = [], None, False
+        while True:
+            st, planes, pi, z, w = self.selfplay(n_games, first_game, capacity, out=out, resume=resume)
+            out = (planes, pi, z)
+            chunks.append((planes[:w].clone(), pi[:w].clone(), z[:w].clone()))
+            if st != MORE:
+                break
+            resume = True
+        return tuple(torch.cat([c[i] for c in chunks]) for i in range(3))
+
     def arena(self, n_games, first_game=0):
         wld = (C.c_int64 * 3)()
         check(self.lib.azp_arena_run(self.h, first_game, n_games, wld, stream_ptr()), self.h)

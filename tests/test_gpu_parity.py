@@ -343,9 +343,9 @@ def test_selfplay_games_are_legal_and_labelled(az):
     size, win, sims, ngames = 5, 4, 40, 48
     eng = az.Engine(board=size, win_length=win, games=32, sims=sims, augment=az.AUGMENT_NONE, seed=7)
     eng.load_state_dict(onet.synthetic_stem_params(size, seed=1, scale=2.0))
-    st, planes, pi, z, written = eng.selfplay(ngames)
-    assert st == 0
-    ex = (planes[:written].cpu().numpy(), pi[:written].cpu().numpy(), z[:written].cpu().numpy())
+    planes, pi, z = eng.selfplay_all(ngames)
+    written = planes.shape[0]
+    ex = (planes.cpu().numpy(), pi.cpu().numpy(), z.cpu().numpy())
     assert _check_raw_games(ex, size, win) == ngames
     c = eng.counters()
     assert c["games_finished"] == ngames and c["positions"] == written == c["plies"]
@@ -364,8 +364,8 @@ def test_selfplay_shard_invariance(az):
         eng = az.Engine(board=size, win_length=win, games=games, sims=sims, augment=az.AUGMENT_NONE, seed=11,
                         rank=rank, world=world)
         eng.load_state_dict(params)
-        st, planes, pi, z, w = eng.selfplay(ngames)
-        out = [(planes[i].cpu().numpy().tobytes(), pi[i].cpu().numpy().tobytes(), int(z[i])) for i in range(w)]
+        planes, pi, z = (t.cpu().numpy() for t in eng.selfplay_all(ngames))
+        out = [(planes[i].tobytes(), pi[i].tobytes(), int(z[i])) for i in range(len(z))]
         eng.close()
         return out
 
