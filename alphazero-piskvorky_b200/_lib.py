@@ -71,6 +71,8 @@ SIGNATURES = {
     "azp_arena_run": (C.c_int, [P, C.c_int64, C.c_int64, C.POINTER(C.c_int64), P]),
     "azp_get_counters": (C.c_int, [P, C.POINTER(Counters)]),
     "azp_reset_counters": (C.c_int, [P]),
+    "azp_set_profiling": (C.c_int, [P, C.c_int]),
+    "azp_get_profile": (C.c_int, [P, C.POINTER(C.c_double), C.POINTER(C.c_uint64), C.POINTER(C.c_double)]),
 }
 
 _lib = None

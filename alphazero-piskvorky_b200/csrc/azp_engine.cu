@@ -103,6 +103,7 @@ static int create_impl(azp_engine* e) {
   if ((st = e->alloc(&e->d_raw_z, (size_t)e->raw_capacity))) return st;
   if ((st = e->alloc(&e->d_raw_count, 2))) return st;
   if ((st = e->alloc(&e->d_sched, 8))) return st;
+  if ((st = e->alloc(&e->d_prof_counts, (size_t)AZP_PROF_MAX))) return st;
   AZP_CUDA(e, cudaMemset(tv.n_leaves, 0, 4 * sizeof(int32_t)));
   AZP_CUDA(e, cudaMemset(tv.error_flag, 0, sizeof(int32_t)));
   AZP_CUDA(e, cudaMemset(tv.counters, 0, CNT_COUNT * sizeof(unsigned long long)));
@@ -163,6 +164,7 @@ extern "C" void azp_destroy(azp_engine* e) {
   if (!e) return;
   cudaSetDevice(e->cfg.device);
   cudaDeviceSynchronize();
+  for (cudaEvent_t ev : e->prof_events) cudaEventDestroy(ev);
   if (e->cfg.net_dtype == AZP_DTYPE_BF16) azp_umma_destroy(e);
   azp_net_destroy(e);
   for (void* p : e->allocs) cudaFree(p);
@@ -404,6 +406,61 @@ extern "C" int azp_get_counters(azp_engine* e, azp_counters* out) {
   out->x_wins = c[CNT_XWINS]; out->o_wins = c[CNT_OWINS]; out->draws = c[CNT_DRAWS];
   return AZP_OK;
 }
+// ---- per-kernel profiling ---------------------------------------------------------------------------------
+__global__ void prof_copy_count_kernel(const int32_t* src, int32_t* dst) { *dst = *src; }
+
+void azp_prof_begin(azp_engine* e, const int32_t* count_dev, int count_host, cudaStream_t s) {
+  if (!e->profiling) return;
+  if (e->prof_used >= AZP_PROF_MAX) azp_prof_collect(e);
+  size_t i = e->prof_used;
+  while (e->prof_events.size() < 2 * (i + 1)) {
+    cudaEvent_t ev;
+    cudaEventCreate(&ev);
+    e->prof_events.push_back(ev);
+  }
+  if (count_dev) { prof_copy_count_kernel<<<1, 1, 0, s>>>(count_dev, e->d_prof_counts + i); azp_count_launch(); }
+  e->prof_count_dev.push_back(count_dev ? e->d_prof_counts + i : nullptr);
+  e->prof_count_host.push_back(count_host);
+  cudaEventRecord(e->prof_events[2 * i], s);
+}
+void azp_prof_end(azp_engine* e, cudaStream_t s) {
+  if (!e->profiling) return;
+  cudaEventRecord(e->prof_events[2 * e->prof_used + 1], s);
+  e->prof_used++;
+}
+int azp_prof_collect(azp_engine* e) {
+  if (e->prof_used == 0) return AZP_OK;
+  AZP_CUDA(e, cudaDeviceSynchronize());
+  std::vector<int32_t> counts(AZP_PROF_MAX);
+  AZP_CUDA(e, cudaMemcpy(counts.data(), e->d_prof_counts, AZP_PROF_MAX * sizeof(int32_t), cudaMemcpyDeviceToHost));
+  for (size_t i = 0; i < e->prof_used; i++) {
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e->prof_events[2 * i], e->prof_events[2 * i + 1]);
+    int boards = e->prof_count_dev[i] ? counts[i] : e->prof_count_host[i];
+    if (boards <= 0) continue;
+    e->prof_ms += ms;
+    e->prof_launches++;
+    e->prof_flops += e->prof_flops_per_board * boards;
+  }
+  e->prof_used = 0;
+  e->prof_count_dev.clear();
+  e->prof_count_host.clear();
+  return AZP_OK;
+}
+extern "C" int azp_set_profiling(azp_engine* e, int enabled) {
+  if (!e) return AZP_ERR_INVALID_ARG;
+  int st = azp_prof_collect(e);
+  e->profiling = enabled != 0;
+  return st;
+}
+extern "C" int azp_get_profile(azp_engine* e, double* ms, uint64_t* launches, double* flops) {
+  if (!e || !ms || !launches || !flops) return AZP_ERR_INVALID_ARG;
+  int st = azp_prof_collect(e);
+  *ms = e->prof_ms; *launches = e->prof_launches; *flops = e->prof_flops;
+  e->prof_ms = 0.0; e->prof_flops = 0.0; e->prof_launches = 0;
+  return st;
+}
+
 extern "C" int azp_reset_counters(azp_engine* e) {
   if (!e) return AZP_ERR_INVALID_ARG;
   AZP_CUDA(e, cudaDeviceSynchronize());

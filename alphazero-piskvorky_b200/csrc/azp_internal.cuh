@@ -106,6 +106,14 @@ struct azp_engine {
   int max_plies = 0;
   int search_n = 0;                // number of game slots in the current step-by-step search
   int parity = 0;                  // which pair of leaf counters the current step uses
+  // per-kernel profiling of the dominant kernel (roofline.achieved in bench.py)
+  bool profiling = false;
+  std::vector<cudaEvent_t> prof_events;      // pairs (start, stop), recycled after each collect
+  std::vector<const int32_t*> prof_count_dev; std::vector<int> prof_count_host;
+  size_t prof_used = 0;
+  double prof_ms = 0.0, prof_flops = 0.0; uint64_t prof_launches = 0;
+  double prof_flops_per_board = 0.0;
+  int32_t* d_prof_counts = nullptr;          // [PROF_MAX] leaf counts copied at launch time
   long long sp_first = 0, sp_total = 0;  // current self-play job
   void set_error(const std::string& m) { error = m; azp_set_global_error(m); }
   template <typename T> int alloc(T** p, size_t count) {
@@ -135,6 +143,12 @@ int azp_episode_seat(azp_engine* e, int n, int arena, cudaStream_t s);
 int azp_episode_end_move(azp_engine* e, int n, int arena, cudaStream_t s);
 int azp_episode_finish(azp_engine* e, int n, int arena, cudaStream_t s);
 int azp_episode_drain(azp_engine* e, long long* out_written_dev, int mult, cudaStream_t s);
+
+// profiling helpers (azp_engine.cu)
+#define AZP_PROF_MAX 4096
+void azp_prof_begin(azp_engine* e, const int32_t* count_dev, int count_host, cudaStream_t s);
+void azp_prof_end(azp_engine* e, cudaStream_t s);
+int azp_prof_collect(azp_engine* e);
 
 // azp_net.cu
 int azp_net_create(azp_engine* e);

@@ -315,6 +315,10 @@ static int build_f32(azp_engine* e, const HostNet& net, NetWeights* W) {
   if ((st = upload(e, &W->vfc2_w, net.vfc2_w))) return st;
   if ((st = upload(e, &W->vfc2_b, net.vfc2_b))) return st;
   W->C = net.C; W->PC = net.PC; W->VC = net.VC;
+  size_t best = 0;
+  for (size_t i = 0; i < net.convs.size(); i++)
+    if ((size_t)net.convs[i].cin * net.convs[i].cout >= (size_t)net.convs[best].cin * net.convs[best].cout) best = i;
+  W->dominant_layer = best;
   return AZP_OK;
 }
 
@@ -387,6 +391,11 @@ static int run_f32(azp_engine* e, NetWeights* W, const float* in4, const int32_t
     else { out_idx = (xi + 2) % 3; cur = ws->act[yi]; residual = ws->act[xi]; }
     float* out = ws->act[out_idx];
     dim3 grid((A + 63) / 64, 1, zmax);
+    const bool dominant = li == W->dominant_layer;
+    if (dominant) {
+      e->prof_flops_per_board = 2.0 * 9.0 * L.cin * L.cout * A;
+      azp_prof_begin(e, count_dev, count_host, s);
+    }
     if (L.cin % 16 == 0 && L.cout % 64 == 0) {
       grid.y = L.cout / 64;
       conv3x3_f32_kernel<16, 64><<<grid, 256, 0, s>>>(cur, L.w, L.b, residual, out, B, L.cin, L.cout, L.relu,
@@ -408,6 +417,7 @@ static int run_f32(azp_engine* e, NetWeights* W, const float* in4, const int32_t
       return AZP_ERR_UNSUPPORTED;
     }
     azp_count_launch();
+    if (dominant) azp_prof_end(e, s);
     if (!tower_block || second) { xi = out_idx; cur = out; }
   }
   const int NJ = W->PC + W->VC;

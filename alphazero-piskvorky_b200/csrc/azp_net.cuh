@@ -32,6 +32,7 @@ struct DevConv {
 struct NetWeights {
   bool loaded = false;
   int C = 0, PC = 0, VC = 0;
+  size_t dominant_layer = 0;    // index of the conv with the most FLOPs (profiled for the roofline)
   std::vector<DevConv> layers;
   float* head_w = nullptr; float* head_b = nullptr;
   float* pfc_t = nullptr; float* pfc_b = nullptr;       // [PC*A][A]

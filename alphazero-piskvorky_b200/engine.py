@@ -200,6 +200,15 @@ class Engine:
         check(self.lib.azp_get_counters(self.h, C.byref(c)), self.h)
         return c.as_dict()
 
+    def set_profiling(self, enabled=True):
+        check(self.lib.azp_set_profiling(self.h, int(enabled)), self.h)
+
+    def get_profile(self):
+        """(ms, launches, algorithmic flops) of the dominant kernel since the last call."""
+        ms, n, fl = C.c_double(0), C.c_uint64(0), C.c_double(0)
+        check(self.lib.azp_get_profile(self.h, C.byref(ms), C.byref(n), C.byref(fl)), self.h)
+        return float(ms.value), int(n.value), float(fl.value)
+
     def reset_counters(self):
         check(self.lib.azp_reset_counters(self.h), self.h)
 

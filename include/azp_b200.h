@@ -173,6 +173,12 @@ int azp_selfplay_run(azp_engine* e, int64_t first_game, int64_t n_games, int res
  * host_wld = {candidate wins, baseline wins, draws} for this rank's games. */
 int azp_arena_run(azp_engine* e, int64_t first_game, int64_t n_games, int64_t* host_wld, void* stream);
 int azp_get_counters(azp_engine* e, azp_counters* host_out);
+/* Per-kernel timing for the roofline: when enabled, every launch of the DOMINANT kernel (the
+ * largest convolution of the net) is bracketed by CUDA events on its own stream.
+ * azp_get_profile synchronises, returns the summed duration (ms), the number of launches and the
+ * algorithmic FLOPs those launches performed, and resets the accumulators. */
+int azp_set_profiling(azp_engine* e, int enabled);
+int azp_get_profile(azp_engine* e, double* host_ms, uint64_t* host_launches, double* host_flops);
 int azp_reset_counters(azp_engine* e);
 
 #ifdef __cplusplus
