@@ -58,6 +58,7 @@ SIGNATURES = {
     "azp_load_weights_device": (C.c_int, [P, C.c_int, P, C.c_size_t, P]),
     "azp_weight_count": (C.c_size_t, [P]),
     "azp_net_forward": (C.c_int, [P, C.c_int, C.c_int, P, P, P, P, P]),
+    "azp_debug_activations": (C.c_int, [P, C.c_int, C.c_int, P, P]),
     "azp_search_begin": (C.c_int, [P, C.c_int, P, P, P, P, P, P, P]),
     "azp_root_expand": (C.c_int, [P, P, C.c_int, P]),
     "azp_select": (C.c_int, [P, P]),

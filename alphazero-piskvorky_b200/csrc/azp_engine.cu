@@ -188,6 +188,12 @@ extern "C" int azp_net_forward(azp_engine* e, int slot, int n, const float* plan
   return azp_net_eval_planes(e, slot, n, planes, logits, policy, value, (cudaStream_t)stream);
 }
 
+extern "C" int azp_debug_activations(azp_engine* e, int layer, int n, float* out, void* stream) {
+  if (!e || !out || n < 1 || n > e->cfg.games) return AZP_ERR_INVALID_ARG;
+  if (e->cfg.net_dtype != AZP_DTYPE_BF16) { e->set_error("debug activations exist on the bf16 path only"); return AZP_ERR_UNSUPPORTED; }
+  return azp_umma_debug(e, layer, n, out, (cudaStream_t)stream);
+}
+
 // ---- step-by-step search -----------------------------------------------------------------------------------
 __global__ void set_roots_kernel(TreeView tv, int n, const uint64_t* x, const uint64_t* o, const uint8_t* tm,
                                  const int16_t* last, const int32_t* ply, const int64_t* game_id) {

@@ -57,5 +57,6 @@ void azp_umma_destroy(azp_engine* e);
 int azp_umma_build(azp_engine* e, const HostNet& net, NetWeights* W);
 int azp_umma_eval_leaves(azp_engine* e, NetWeights* W, const int32_t* count_dev, int count_host, int back,
                          cudaStream_t s);
+int azp_umma_debug(azp_engine* e, int layer, int n, float* out, cudaStream_t s);
 int azp_umma_eval_planes(azp_engine* e, NetWeights* W, int n, const float* planes, float* logits, float* policy,
                          float* value, cudaStream_t s);

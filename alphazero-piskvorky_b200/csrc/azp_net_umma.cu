@@ -1,8 +1,750 @@
-// bf16 tcgen05 implicit-GEMM path (AZP_DTYPE_BF16) -- placeholder until the kernels land.
+// Policy/value network, bf16 tcgen05 path (AZP_DTYPE_BF16) for the conv-stem GomokuNet
+// (alphazero/net.py:28-72).  Hand-written sm_100a: TMA-staged activations, weights resident in
+// shared memory, tcgen05.mma (UMMA) implicit GEMM with fp32 accumulators in TMEM, fused epilogues.
+//
+// Activation layout in HBM ("padded NHWC", bf16): one row of C channels per padded board position;
+// a board occupies (B+1) row groups of P positions (P = 16 for B <= 15, 24 for B <= 23):
+//     row(slot, r, c) = slot*(B+1)*P + (r+1)*P + (c+1)
+// Row group 0 and column 0 of every row group (and columns > B) are ZERO and double as the bottom /
+// right halo of the previous row group / board, so a 3x3 tap (dy,dx) is the constant row offset
+// dy*P + dx and the implicit-GEMM A operand of a tap is a plain [128 rows x C] window of that matrix.
+// P is a multiple of 8, so the three dy windows of one dx-shifted 160-row TMA load all start on a
+// swizzle-atom boundary: 3 TMA loads (not 9) feed the 9 taps of a 128-row output tile.
+//
+// Pipeline per step (leaf batch of n positions):
+//   conv1_bits_kernel   bitboards -> act1 [rows][32]      SIMT (inputs are 0/1: K = 27 adds)
+//   conv_umma<32,64>    act1 -> act2 [rows][64]           tcgen05, bias+ReLU+pad-zero epilogue
+//   conv_umma<64,128>   act2 -> head features [n][6][A]   tcgen05, epilogue = bias+ReLU + both 1x1 head
+//                                                         convs (act3 never leaves the SM)
+//   heads_fc_kernel     features -> logits/softmax/value  SIMT fp32, weights shared by 8 boards per CTA
 #include "azp_net.cuh"
+#include <cuda.h>
 
-int azp_umma_create(azp_engine* e) { e->set_error("bf16 tcgen05 path not built yet"); return AZP_ERR_UNSUPPORTED; }
-void azp_umma_destroy(azp_engine*) {}
-int azp_umma_build(azp_engine* e, const HostNet&, NetWeights*) { e->set_error("bf16 tcgen05 path not built yet"); return AZP_ERR_UNSUPPORTED; }
-int azp_umma_eval_leaves(azp_engine* e, NetWeights*, const int32_t*, int, int, cudaStream_t) { e->set_error("bf16 tcgen05 path not built yet"); return AZP_ERR_UNSUPPORTED; }
-int azp_umma_eval_planes(azp_engine* e, NetWeights*, int, const float*, float*, float*, float*, cudaStream_t) { e->set_error("bf16 tcgen05 path not built yet"); return AZP_ERR_UNSUPPORTED; }
+namespace {
+
+constexpr int TILE_M = 128;
+
+// ---- PTX wrappers -----------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred P1;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n\t"
+      "selp.b32 %0, 1, 0, P1;\n\t}"
+      : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+  return ok != 0;
+}
+// Bounded wait: a protocol bug must become a trapped launch, never a hung GPU.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    if (clock64() - t0 > 4000000000ll) __trap();
+  }
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c_inner, int c_row) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(dst)), "l"((uint64_t)map), "r"(smem_u32(bar)), "r"(c_inner), "r"(c_row) : "memory");
+}
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols));
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t addr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(ncols));
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem]^T, bf16 inputs, fp32 accumulate; one thread issues for the CTA
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// Shared-memory matrix descriptor, K-major operand with a hardware swizzle whose span is one row
+// (64 B rows -> SWIZZLE_64B, 128 B rows -> SWIZZLE_128B): 8-row atoms, stride between atoms = 8 rows.
+__device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr, uint32_t row_bytes) {
+  const uint64_t layout = row_bytes == 128 ? 2ull : 4ull;        // SWIZZLE_128B : SWIZZLE_64B
+  const uint64_t sbo = (8u * row_bytes) >> 4;
+  return (uint64_t)((smem_addr >> 4) & 0x3FFF) | (1ull << 16) | (sbo << 32) | (1ull << 46) | (layout << 61);
+}
+// instruction descriptor: D=f32, A=B=bf16, both K-major, M=128, N
+__device__ __forceinline__ uint32_t umma_idesc(uint32_t n) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((n >> 3) << 17) | ((uint32_t)(TILE_M >> 4) << 24);
+}
+
+struct ConvGeom {
+  int B, A, P, stride;        // board side, cells, row pitch, rows per board = (B+1)*P
+  int G;                      // slots
+};
+
+// ---- conv1 from bitboards (SIMT) ------------------------------------------------------------------------
+// One block per slot, one thread per padded position.  Inputs are 0/1 planes (games.py:86-129; plane 3
+// is all zero), so the convolution is a sum of at most 27 weight rows.  w: [tap][plane(3)][32] fp32.
+template <int NWT>
+__global__ void __launch_bounds__(256) conv1_bits_kernel(ConvGeom g, const uint64_t* __restrict__ lx,
+                                                         const uint64_t* __restrict__ lo,
+                                                         const uint8_t* __restrict__ ltm,
+                                                         const int16_t* __restrict__ llast,
+                                                         const float* __restrict__ w, const float* __restrict__ bias,
+                                                         __nv_bfloat16* __restrict__ act1,
+                                                         const int32_t* __restrict__ count_dev, int count_host,
+                                                         int back) {
+  const int count = count_dev ? *count_dev : count_host;
+  __shared__ float sw[27 * 32];
+  __shared__ float sb[32];
+  __shared__ int8_t cells[AZP_MAX_BOARD * AZP_MAX_BOARD + 3];
+  for (int i = threadIdx.x; i < 27 * 32; i += blockDim.x) sw[i] = w[i];
+  if (threadIdx.x < 32) sb[threadIdx.x] = bias[threadIdx.x];
+  for (int bi = blockIdx.x; bi < count; bi += gridDim.x) {
+    const int slot = back ? g.G - 1 - bi : bi;
+    __syncthreads();
+    const bool xm = ltm[slot] == 1;
+    const int last = llast[slot];
+    for (int a = threadIdx.x; a < g.A; a += blockDim.x) {
+      uint64_t wx = lx[(size_t)slot * NWT + (a >> 6)], wo = lo[(size_t)slot * NWT + (a >> 6)];
+      bool isx = (wx >> (a & 63)) & 1, iso = (wo >> (a & 63)) & 1;
+      int v = ((xm ? isx : iso) ? 1 : 0) | ((xm ? iso : isx) ? 2 : 0) | (a == last ? 4 : 0);
+      cells[a] = (int8_t)v;
+    }
+    __syncthreads();
+    for (int pos = threadIdx.x; pos < g.stride; pos += blockDim.x) {
+      const int y = pos / g.P, x = pos % g.P;
+      uint4* dst = reinterpret_cast<uint4*>(act1 + ((size_t)slot * g.stride + pos) * 32);
+      if (y < 1 || x < 1 || x > g.B) {                 // halo rows/columns stay zero
+#pragma unroll
+        for (int q = 0; q < 4; q++) dst[q] = make_uint4(0, 0, 0, 0);
+        continue;
+      }
+      const int r = y - 1, c = x - 1;
+      float acc[32];
+#pragma unroll
+      for (int j = 0; j < 32; j++) acc[j] = sb[j];
+#pragma unroll
+      for (int tap = 0; tap < 9; tap++) {
+        const int rr = r + tap / 3 - 1, cc = c + tap % 3 - 1;
+        if (rr < 0 || rr >= g.B || cc < 0 || cc >= g.B) continue;
+        const int v = cells[rr * g.B + cc];
+        if (!v) continue;
+#pragma unroll
+        for (int pl = 0; pl < 3; pl++) {
+          if (!(v & (1 << pl))) continue;
+          const float* wr = sw + (tap * 3 + pl) * 32;
+#pragma unroll
+          for (int j = 0; j < 32; j++) acc[j] += wr[j];
+        }
+      }
+      uint32_t packed[16];
+#pragma unroll
+      for (int j = 0; j < 16; j++) {
+        __nv_bfloat162 h = __floats2bfloat162_rn(fmaxf(acc[2 * j], 0.f), fmaxf(acc[2 * j + 1], 0.f));
+        packed[j] = *reinterpret_cast<uint32_t*>(&h);
+      }
+#pragma unroll
+      for (int q = 0; q < 4; q++) dst[q] = make_uint4(packed[4 * q], packed[4 * q + 1], packed[4 * q + 2], packed[4 * q + 3]);
+    }
+  }
+}
+
+// general float32 planes [n][4][A] -> act1 (used by azp_net_forward on arbitrary inputs)
+__global__ void __launch_bounds__(256) conv1_planes_kernel(ConvGeom g, int n, const float* __restrict__ planes,
+                                                           const float* __restrict__ w4 /*[tap][4][32]*/,
+                                                           const float* __restrict__ bias,
+                                                           __nv_bfloat16* __restrict__ act1) {
+  __shared__ float sw[36 * 32];
+  __shared__ float sb[32];
+  extern __shared__ float sp[];          // [4][A]
+  for (int i = threadIdx.x; i < 36 * 32; i += blockDim.x) sw[i] = w4[i];
+  if (threadIdx.x < 32) sb[threadIdx.x] = bias[threadIdx.x];
+  for (int slot = blockIdx.x; slot < n; slot += gridDim.x) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < 4 * g.A; i += blockDim.x) sp[i] = planes[(size_t)slot * 4 * g.A + i];
+    __syncthreads();
+    for (int pos = threadIdx.x; pos < g.stride; pos += blockDim.x) {
+      const int y = pos / g.P, x = pos % g.P;
+      uint4* dst = reinterpret_cast<uint4*>(act1 + ((size_t)slot * g.stride + pos) * 32);
+      if (y < 1 || x < 1 || x > g.B) {
+#pragma unroll
+        for (int q = 0; q < 4; q++) dst[q] = make_uint4(0, 0, 0, 0);
+        continue;
+      }
+      const int r = y - 1, c = x - 1;
+      float acc[32];
+#pragma unroll
+      for (int j = 0; j < 32; j++) acc[j] = sb[j];
+      for (int tap = 0; tap < 9; tap++) {
+        const int rr = r + tap / 3 - 1, cc = c + tap % 3 - 1;
+        if (rr < 0 || rr >= g.B || cc < 0 || cc >= g.B) continue;
+        for (int pl = 0; pl < 4; pl++) {
+          const float v = sp[pl * g.A + rr * g.B + cc];
+          const float* wr = sw + (tap * 4 + pl) * 32;
+#pragma unroll
+          for (int j = 0; j < 32; j++) acc[j] = fmaf(v, wr[j], acc[j]);
+        }
+      }
+      uint32_t packed[16];
+#pragma unroll
+      for (int j = 0; j < 16; j++) {
+        __nv_bfloat162 h = __floats2bfloat162_rn(fmaxf(acc[2 * j], 0.f), fmaxf(acc[2 * j + 1], 0.f));
+        packed[j] = *reinterpret_cast<uint32_t*>(&h);
+      }
+#pragma unroll
+      for (int q = 0; q < 4; q++) dst[q] = make_uint4(packed[4 * q], packed[4 * q + 1], packed[4 * q + 2], packed[4 * q + 3]);
+    }
+  }
+}
+
+// ---- tcgen05 implicit-GEMM 3x3 convolution ---------------------------------------------------------------
+// Persistent, warp-specialised: warp 0 = TMA producer, warp 1 = TMEM owner + MMA issuer, warps 2..5 =
+// epilogue (warp w owns TMEM lanes 32*(w%4)..+31 == tile rows).
+// Per 128-row tile: three (dx = -1,0,+1) TMA loads of (128+2P) rows; each feeds 3 taps (dy) x CIN/16
+// UMMAs (M=128, N=COUT, K=16).  Weights [tap][COUT][CIN] stay in shared memory for the kernel's lifetime.
+template <int CIN, int COUT, int STAGES, bool HEADS>
+struct ConvSmem {
+  static constexpr int ROWB = CIN * 2;
+  static constexpr int W_TAP_BYTES = COUT * ROWB;
+  static constexpr int W_BYTES = 9 * W_TAP_BYTES;
+};
+
+struct ConvArgs {
+  ConvGeom g;
+  const float* bias;              // [COUT]
+  __nv_bfloat16* out;             // !HEADS: activations [rows][COUT]
+  // HEADS: 1x1 head convs fused into the epilogue
+  const float* head_w;            // [COUT][8]  (transposed, zero padded to 8 outputs)
+  const float* head_b;            // [8]
+  float* feat;                    // [G][NJ][A]
+  int NJ;
+  const int32_t* count_dev; int count_host; int back;
+  int stage_rows;                 // 128 + 2P
+};
+
+template <int CIN, int COUT, int STAGES, bool HEADS>
+__global__ void __launch_bounds__(192, 1) conv_umma_kernel(const __grid_constant__ CUtensorMap map_act,
+                                                           const __grid_constant__ CUtensorMap map_w,
+                                                           const ConvArgs args) {
+  using S = ConvSmem<CIN, COUT, STAGES, HEADS>;
+  constexpr int ROWB = S::ROWB;
+  constexpr int KSTEPS = CIN / 16;
+  constexpr uint32_t TMEM_COLS = (2 * COUT <= 32) ? 32 : (2 * COUT <= 64 ? 64 : (2 * COUT <= 128 ? 128 : 256));
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  const int stage_bytes = args.stage_rows * ROWB;          // multiple of 1024 (P multiple of 8)
+  uint8_t* s_w = smem;                                      // 9 taps x [COUT][CIN]
+  uint8_t* s_a = s_w + S::W_BYTES;                          // STAGES x [stage_rows][CIN]
+  uint8_t* s_tail = s_a + (size_t)STAGES * stage_bytes;
+  uint64_t* full = reinterpret_cast<uint64_t*>(s_tail);     // [STAGES]
+  uint64_t* empty = full + STAGES;                          // [STAGES]
+  uint64_t* tfull = empty + STAGES;                         // [2]
+  uint64_t* tempty = tfull + 2;                             // [2]
+  uint64_t* wbar = tempty + 2;                              // [1]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(wbar + 1);
+  float* s_bias = reinterpret_cast<float*>(tmem_slot + 2);  // [COUT]
+  float* s_hw = s_bias + COUT;                              // HEADS: [COUT][8] then [8]
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const ConvGeom g = args.g;
+  const int count = args.count_dev ? *args.count_dev : args.count_host;
+  const int slot0 = args.back ? g.G - count : 0;
+  const long long row_begin = (long long)slot0 * g.stride;
+  const long long rows_total = (long long)count * g.stride;
+  const int n_tiles = (int)((rows_total + TILE_M - 1) / TILE_M);
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < STAGES; i++) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+    for (int i = 0; i < 2; i++) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 4); }
+    mbar_init(wbar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  for (int i = threadIdx.x; i < COUT; i += blockDim.x) s_bias[i] = args.bias[i];
+  if (HEADS) {
+    for (int i = threadIdx.x; i < COUT * 8 + 8; i += blockDim.x)
+      s_hw[i] = i < COUT * 8 ? args.head_w[i] : args.head_b[i - COUT * 8];
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===== TMA producer =====
+    if (lane == 0) {
+      mbar_expect_tx(wbar, S::W_BYTES);
+      for (int tap = 0; tap < 9; tap++) tma_load_2d(s_w + tap * S::W_TAP_BYTES, &map_w, wbar, 0, tap * COUT);
+      int it = 0;
+      for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+        for (int dxi = 0; dxi < 3; dxi++, it++) {
+          const int st = it % STAGES;
+          const uint32_t ph = (it / STAGES) & 1;
+          mbar_wait(&empty[st], ph ^ 1);
+          mbar_expect_tx(&full[st], (uint32_t)stage_bytes);
+          const long long row = row_begin + (long long)t * TILE_M - g.P + (dxi - 1);
+          tma_load_2d(s_a + (size_t)st * stage_bytes, &map_act, &full[st], 0, (int)row);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer =====
+    if (lane == 0) {
+      const uint32_t idesc = umma_idesc(COUT);
+      const uint32_t a_base = smem_u32(s_a), w_base = smem_u32(s_w);
+      mbar_wait(wbar, 0);
+      tc_fence_after();
+      int it = 0, tl = 0;
+      for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, tl++) {
+        const int acc = tl & 1;
+        const uint32_t acc_ph = (tl >> 1) & 1;
+        mbar_wait(&tempty[acc], acc_ph ^ 1);              // epilogue has drained this accumulator
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * COUT);
+        uint32_t accumulate = 0;
+        for (int dxi = 0; dxi < 3; dxi++, it++) {
+          const int st = it % STAGES;
+          const uint32_t ph = (it / STAGES) & 1;
+          mbar_wait(&full[st], ph);
+          tc_fence_after();
+          const uint32_t a_stage = a_base + (uint32_t)st * (uint32_t)stage_bytes;
+#pragma unroll
+          for (int dyi = 0; dyi < 3; dyi++) {
+            const uint32_t a_tap = a_stage + (uint32_t)(dyi * g.P * ROWB);
+            const uint32_t w_tap = w_base + (uint32_t)((dyi * 3 + dxi) * S::W_TAP_BYTES);
+#pragma unroll
+            for (int k = 0; k < KSTEPS; k++) {
+              umma_bf16(d_tmem, umma_desc(a_tap + k * 32, ROWB), umma_desc(w_tap + k * 32, ROWB), idesc, accumulate);
+              accumulate = 1;
+            }
+          }
+          umma_commit(&empty[st]);                        // stage reusable once these MMAs retire
+        }
+        umma_commit(&tfull[acc]);                         // accumulator complete
+      }
+    }
+  } else {
+    // ===== epilogue =====
+    const int q = warp & 3;                               // TMEM lane quarter this warp may access
+    int tl = 0;
+    for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, tl++) {
+      const int acc = tl & 1;
+      const uint32_t acc_ph = (tl >> 1) & 1;
+      mbar_wait(&tfull[acc], acc_ph);
+      tc_fence_after();
+      const long long R = row_begin + (long long)t * TILE_M + q * 32 + lane;     // global padded row
+      const int slot = (int)(R / g.stride);
+      const int pos = (int)(R % g.stride);
+      const int y = pos / g.P, x = pos % g.P;
+      const bool interior = y >= 1 && x >= 1 && x <= g.B && slot < g.G;
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * COUT);
+      if (!HEADS) {
+        uint4* dst = reinterpret_cast<uint4*>(args.out + (size_t)R * COUT);
+        const bool in_range = slot < g.G;
+#pragma unroll
+        for (int c0 = 0; c0 < COUT; c0 += 32) {
+          uint32_t r[32];
+          tmem_ld32(taddr + c0, r);
+          uint32_t packed[16];
+#pragma unroll
+          for (int j = 0; j < 16; j++) {
+            float v0 = interior ? fmaxf(__uint_as_float(r[2 * j]) + s_bias[c0 + 2 * j], 0.f) : 0.f;
+            float v1 = interior ? fmaxf(__uint_as_float(r[2 * j + 1]) + s_bias[c0 + 2 * j + 1], 0.f) : 0.f;
+            __nv_bfloat162 h = __floats2bfloat162_rn(v0, v1);
+            packed[j] = *reinterpret_cast<uint32_t*>(&h);
+          }
+          if (in_range) {
+#pragma unroll
+            for (int v = 0; v < 4; v++)
+              dst[c0 / 8 + v] = make_uint4(packed[4 * v], packed[4 * v + 1], packed[4 * v + 2], packed[4 * v + 3]);
+          }
+        }
+      } else {
+        float dot[8];
+#pragma unroll
+        for (int j = 0; j < 8; j++) dot[j] = 0.f;
+#pragma unroll
+        for (int c0 = 0; c0 < COUT; c0 += 32) {
+          uint32_t r[32];
+          tmem_ld32(taddr + c0, r);
+#pragma unroll
+          for (int i = 0; i < 32; i++) {
+            const float v = fmaxf(__uint_as_float(r[i]) + s_bias[c0 + i], 0.f);
+            const float4 w0 = *reinterpret_cast<const float4*>(s_hw + (c0 + i) * 8);
+            const float4 w1 = *reinterpret_cast<const float4*>(s_hw + (c0 + i) * 8 + 4);
+            dot[0] = fmaf(v, w0.x, dot[0]); dot[1] = fmaf(v, w0.y, dot[1]);
+            dot[2] = fmaf(v, w0.z, dot[2]); dot[3] = fmaf(v, w0.w, dot[3]);
+            dot[4] = fmaf(v, w1.x, dot[4]); dot[5] = fmaf(v, w1.y, dot[5]);
+            dot[6] = fmaf(v, w1.z, dot[6]); dot[7] = fmaf(v, w1.w, dot[7]);
+          }
+        }
+        if (interior) {
+          const int pix = (y - 1) * g.B + (x - 1);
+          float* f = args.feat + (size_t)slot * args.NJ * g.A + pix;
+#pragma unroll
+          for (int j = 0; j < 8; j++)
+            if (j < args.NJ) f[(size_t)j * g.A] = fmaxf(dot[j] + s_hw[COUT * 8 + j], 0.f);
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty[acc]);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, TMEM_COLS);
+}
+
+// ---- FC heads (SIMT fp32): BT boards share every weight read ----------------------------------------------
+template <int BT>
+__global__ void __launch_bounds__(256) heads_fc_kernel(
+    const float* __restrict__ feat /*[G][NJ][A]*/, int A, int PC, int VC, const float* __restrict__ pfc_t,
+    const float* __restrict__ pfc_b, const float* __restrict__ vfc1_t, const float* __restrict__ vfc1_b,
+    const float* __restrict__ vfc2_w, const float* __restrict__ vfc2_b, float* __restrict__ logits_out,
+    float* __restrict__ policy_out, float* __restrict__ value_out, const int32_t* __restrict__ count_dev,
+    int count_host, int back, int G, int out_by_index) {
+  const int count = count_dev ? *count_dev : count_host;
+  const int NJ = PC + VC;
+  extern __shared__ float sm[];
+  float* sf = sm;                      // [BT][NJ*A]
+  float* lg = sf + BT * NJ * A;        // [BT][A]
+  float* hid = lg + BT * A;            // [BT][64]
+  const int tid = threadIdx.x;
+  for (int b0 = blockIdx.x * BT; b0 < count; b0 += gridDim.x * BT) {
+    const int nb = min(BT, count - b0);
+    __syncthreads();
+    for (int i = tid; i < BT * NJ * A; i += 256) {
+      int b = i / (NJ * A), k = i % (NJ * A);
+      int row = back ? G - 1 - (b0 + b) : b0 + b;
+      sf[i] = b < nb ? feat[(size_t)row * NJ * A + k] : 0.f;
+    }
+    __syncthreads();
+    const int PK = PC * A, VK = VC * A;
+    for (int a = tid; a < A; a += 256) {
+      float acc[BT];
+      const float bias = pfc_b[a];
+#pragma unroll
+      for (int b = 0; b < BT; b++) acc[b] = bias;
+      for (int k = 0; k < PK; k++) {
+        const float w = pfc_t[(size_t)k * A + a];
+#pragma unroll
+        for (int b = 0; b < BT; b++) acc[b] = fmaf(sf[b * NJ * A + k], w, acc[b]);
+      }
+#pragma unroll
+      for (int b = 0; b < BT; b++) lg[b * A + a] = acc[b];
+    }
+    for (int i = tid; i < BT * 64; i += 256) {
+      const int b = i / 64, j = i % 64;
+      float s = vfc1_b[j];
+      const float* vf = sf + b * NJ * A + PK;
+      for (int k = 0; k < VK; k++) s = fmaf(vf[k], vfc1_t[(size_t)k * 64 + j], s);
+      hid[i] = fmaxf(s, 0.f);
+    }
+    __syncthreads();
+    // one warp per board: value head tail + softmax
+    const int warp = tid >> 5, lane = tid & 31;
+    for (int b = warp; b < nb; b += 8) {
+      const int row = back ? G - 1 - (b0 + b) : b0 + b;
+      const int orow = out_by_index ? b0 + b : row;
+      float s = hid[b * 64 + lane] * vfc2_w[lane] + hid[b * 64 + lane + 32] * vfc2_w[lane + 32];
+#pragma unroll
+      for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(AZP_FULL, s, o);
+      if (lane == 0 && value_out) value_out[orow] = tanhf(s + vfc2_b[0]);
+      float m = -INFINITY;
+      for (int a = lane; a < A; a += 32) m = fmaxf(m, lg[b * A + a]);
+#pragma unroll
+      for (int o = 16; o; o >>= 1) m = fmaxf(m, __shfl_xor_sync(AZP_FULL, m, o));
+      float z = 0.f;
+      for (int a = lane; a < A; a += 32) z += expf(lg[b * A + a] - m);
+#pragma unroll
+      for (int o = 16; o; o >>= 1) z += __shfl_xor_sync(AZP_FULL, z, o);
+      for (int a = lane; a < A; a += 32) {
+        const float l = lg[b * A + a];
+        if (logits_out) logits_out[(size_t)orow * A + a] = l;
+        if (policy_out) policy_out[(size_t)orow * A + a] = expf(l - m) / z;
+      }
+    }
+  }
+}
+
+// ---- host side -----------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)p;
+  }
+  return fn;
+}
+
+// 2-D bf16 tensor [rows][cols] row-major; box = [box_rows][cols]; swizzle span == one row
+int make_map(azp_engine* e, CUtensorMap* map, const void* base, uint64_t rows, int cols, int box_rows) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) { e->set_error("cuTensorMapEncodeTiled unavailable"); return AZP_ERR_CUDA; }
+  cuuint64_t dims[2] = {(cuuint64_t)cols, rows};
+  cuuint64_t strides[1] = {(cuuint64_t)cols * 2};
+  cuuint32_t box[2] = {(cuuint32_t)cols, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUtensorMapSwizzle sw = cols * 2 == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { e->set_error("cuTensorMapEncodeTiled failed: " + std::to_string((int)r)); return AZP_ERR_CUDA; }
+  return AZP_OK;
+}
+
+struct UmmaWorkspace {
+  ConvGeom g;
+  __nv_bfloat16* act1 = nullptr;      // [rows][32]
+  __nv_bfloat16* act2 = nullptr;      // [rows][64]
+  float* feat = nullptr;              // [G][6][A]
+  CUtensorMap map_act1, map_act2;
+  size_t rows = 0;
+  int sms = 148;
+  int smem2 = 0, smem3 = 0;
+};
+struct UmmaWeights {
+  __nv_bfloat16* w2 = nullptr;        // [9][64][32]
+  __nv_bfloat16* w3 = nullptr;        // [9][128][64]
+  float* b1 = nullptr; float* b2 = nullptr; float* b3 = nullptr;
+  float* w1_bits = nullptr;           // [tap][3][32]
+  float* w1_planes = nullptr;         // [tap][4][32]
+  float* head_wt = nullptr;           // [128][8]
+  float* head_b8 = nullptr;           // [8]
+  CUtensorMap map_w2, map_w3;
+};
+
+constexpr int STAGES2 = 6, STAGES3 = 3;
+
+template <int CIN, int COUT, int STAGES, bool HEADS>
+int conv_smem_bytes(int stage_rows) {
+  using S = ConvSmem<CIN, COUT, STAGES, HEADS>;
+  return 1024 + S::W_BYTES + STAGES * stage_rows * S::ROWB + (2 * STAGES + 5) * 8 + 16 + COUT * 4 +
+         (HEADS ? (COUT * 8 + 8) * 4 : 0) + 64;
+}
+
+}  // namespace
+
+int azp_umma_create(azp_engine* e) {
+  if (e->cfg.net_kind != AZP_NET_STEM) {
+    e->set_error("bf16 tcgen05 path currently covers the conv-stem GomokuNet; the tower runs on the fp32 path");
+    return AZP_ERR_UNSUPPORTED;
+  }
+  if (e->cfg.board > 23) { e->set_error("board too large for the padded layout"); return AZP_ERR_UNSUPPORTED; }
+  UmmaWorkspace* ws = new UmmaWorkspace();
+  e->ws->umma = ws;
+  ConvGeom& g = ws->g;
+  g.B = e->cfg.board; g.A = e->A; g.P = g.B <= 15 ? 16 : 24; g.stride = (g.B + 1) * g.P; g.G = e->cfg.games;
+  ws->rows = (size_t)g.G * g.stride + 2 * g.P + TILE_M;        // tail halo + a partial last tile
+  int st;
+  if ((st = e->alloc(&ws->act1, ws->rows * 32))) return st;
+  if ((st = e->alloc(&ws->act2, ws->rows * 64))) return st;
+  if ((st = e->alloc(&ws->feat, (size_t)g.G * 8 * g.A))) return st;
+  AZP_CUDA(e, cudaMemset(ws->act1, 0, ws->rows * 32 * sizeof(__nv_bfloat16)));
+  AZP_CUDA(e, cudaMemset(ws->act2, 0, ws->rows * 64 * sizeof(__nv_bfloat16)));
+  const int stage_rows = TILE_M + 2 * g.P;
+  if ((st = make_map(e, &ws->map_act1, ws->act1, ws->rows, 32, stage_rows))) return st;
+  if ((st = make_map(e, &ws->map_act2, ws->act2, ws->rows, 64, stage_rows))) return st;
+  cudaDeviceProp prop;
+  AZP_CUDA(e, cudaGetDeviceProperties(&prop, e->cfg.device));
+  ws->sms = prop.multiProcessorCount;
+  ws->smem2 = conv_smem_bytes<32, 64, STAGES2, false>(stage_rows);
+  ws->smem3 = conv_smem_bytes<64, 128, STAGES3, true>(stage_rows);
+  AZP_CUDA(e, cudaFuncSetAttribute(conv_umma_kernel<32, 64, STAGES2, false>,
+                                   cudaFuncAttributeMaxDynamicSharedMemorySize, ws->smem2));
+  AZP_CUDA(e, cudaFuncSetAttribute(conv_umma_kernel<64, 128, STAGES3, true>,
+                                   cudaFuncAttributeMaxDynamicSharedMemorySize, ws->smem3));
+  AZP_CUDA(e, cudaFuncSetAttribute(heads_fc_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   (int)((8 * 6 * g.A + 8 * g.A + 8 * 64) * sizeof(float))));
+  return AZP_OK;
+}
+
+void azp_umma_destroy(azp_engine* e) {
+  if (e->ws && e->ws->umma) { delete (UmmaWorkspace*)e->ws->umma; e->ws->umma = nullptr; }
+  for (int i = 0; i < 2; i++)
+    if (e->weights[i] && e->weights[i]->umma) { delete (UmmaWeights*)e->weights[i]->umma; e->weights[i]->umma = nullptr; }
+}
+
+template <typename T>
+static int up(azp_engine* e, T** dst, const std::vector<T>& src) {
+  int st = e->alloc(dst, src.size());
+  if (st) return st;
+  AZP_CUDA(e, cudaMemcpy(*dst, src.data(), src.size() * sizeof(T), cudaMemcpyHostToDevice));
+  return AZP_OK;
+}
+
+int azp_umma_build(azp_engine* e, const HostNet& net, NetWeights* W) {
+  if (net.convs.size() != 3 || net.convs[0].cout != 32 || net.convs[1].cout != 64 || net.convs[2].cout != 128) {
+    e->set_error("bf16 path expects the 4->32->64->128 stem");
+    return AZP_ERR_UNSUPPORTED;
+  }
+  const int A = e->A;
+  UmmaWeights* U = new UmmaWeights();
+  W->umma = U;
+  int st;
+  // conv1: fp32 [tap][plane][32]
+  const HostConv& c1 = net.convs[0];
+  std::vector<float> w1b(27 * 32), w1p(36 * 32);
+  for (int co = 0; co < 32; co++)
+    for (int ci = 0; ci < 4; ci++)
+      for (int t = 0; t < 9; t++) {
+        float v = c1.w[((size_t)co * 4 + ci) * 9 + t];
+        w1p[(t * 4 + ci) * 32 + co] = v;
+        if (ci < 3) w1b[(t * 3 + ci) * 32 + co] = v;
+      }
+  if ((st = up(e, &U->w1_bits, w1b))) return st;
+  if ((st = up(e, &U->w1_planes, w1p))) return st;
+  if ((st = up(e, &U->b1, c1.b))) return st;
+  // conv2/conv3: bf16 [tap][cout][cin] (K-major rows of one tap = UMMA B operand)
+  auto pack = [&](const HostConv& c, __nv_bfloat16** dst) {
+    std::vector<__nv_bfloat16> w((size_t)9 * c.cout * c.cin);
+    for (int co = 0; co < c.cout; co++)
+      for (int ci = 0; ci < c.cin; ci++)
+        for (int t = 0; t < 9; t++)
+          w[((size_t)t * c.cout + co) * c.cin + ci] = __float2bfloat16(c.w[((size_t)co * c.cin + ci) * 9 + t]);
+    return up(e, dst, w);
+  };
+  if ((st = pack(net.convs[1], &U->w2))) return st;
+  if ((st = pack(net.convs[2], &U->w3))) return st;
+  if ((st = up(e, &U->b2, net.convs[1].b))) return st;
+  if ((st = up(e, &U->b3, net.convs[2].b))) return st;
+  if ((st = make_map(e, &U->map_w2, U->w2, 9 * 64, 32, 64))) return st;
+  if ((st = make_map(e, &U->map_w3, U->w3, 9 * 128, 64, 128))) return st;
+  // heads: [C][8] transposed 1x1 conv weights (policy rows first), fp32
+  const int NJ = net.PC + net.VC;
+  std::vector<float> hw((size_t)net.C * 8, 0.f), hb(8, 0.f);
+  for (int j = 0; j < NJ; j++) {
+    hb[j] = net.head_b[j];
+    for (int c = 0; c < net.C; c++) hw[(size_t)c * 8 + j] = net.head_w[(size_t)j * net.C + c];
+  }
+  if ((st = up(e, &U->head_wt, hw))) return st;
+  if ((st = up(e, &U->head_b8, hb))) return st;
+  const int PK = net.PC * A, VK = net.VC * A;
+  std::vector<float> pt((size_t)PK * A), vt((size_t)VK * 64);
+  for (int a = 0; a < A; a++) for (int k = 0; k < PK; k++) pt[(size_t)k * A + a] = net.pfc_w[(size_t)a * PK + k];
+  for (int j = 0; j < 64; j++) for (int k = 0; k < VK; k++) vt[(size_t)k * 64 + j] = net.vfc1_w[(size_t)j * VK + k];
+  if ((st = up(e, &W->pfc_t, pt))) return st;
+  if ((st = up(e, &W->pfc_b, net.pfc_b))) return st;
+  if ((st = up(e, &W->vfc1_t, vt))) return st;
+  if ((st = up(e, &W->vfc1_b, net.vfc1_b))) return st;
+  if ((st = up(e, &W->vfc2_w, net.vfc2_w))) return st;
+  if ((st = up(e, &W->vfc2_b, net.vfc2_b))) return st;
+  W->C = net.C; W->PC = net.PC; W->VC = net.VC;
+  return AZP_OK;
+}
+
+// conv2 + conv3(+heads) + FC on rows already holding act1
+static int run_trunk(azp_engine* e, NetWeights* W, const int32_t* count_dev, int count_host, int back,
+                     float* logits, float* policy, float* value, int out_by_index, cudaStream_t s) {
+  UmmaWorkspace* ws = (UmmaWorkspace*)e->ws->umma;
+  UmmaWeights* U = (UmmaWeights*)W->umma;
+  const ConvGeom& g = ws->g;
+  const int zmax = count_dev ? g.G : count_host;
+  const int max_tiles = (int)(((long long)zmax * g.stride + TILE_M - 1) / TILE_M);
+  const int grid = max_tiles < ws->sms ? max_tiles : ws->sms;
+  ConvArgs a2;
+  a2.g = g; a2.bias = U->b2; a2.out = ws->act2; a2.head_w = nullptr; a2.head_b = nullptr; a2.feat = nullptr; a2.NJ = 0;
+  a2.count_dev = count_dev; a2.count_host = count_host; a2.back = back; a2.stage_rows = TILE_M + 2 * g.P;
+  conv_umma_kernel<32, 64, STAGES2, false><<<grid, 192, ws->smem2, s>>>(ws->map_act1, U->map_w2, a2);
+  azp_count_launch();
+  ConvArgs a3 = a2;
+  a3.bias = U->b3; a3.out = nullptr; a3.head_w = U->head_wt; a3.head_b = U->head_b8; a3.feat = ws->feat;
+  a3.NJ = W->PC + W->VC;
+  e->prof_flops_per_board = 2.0 * 9.0 * 64 * 128 * g.A;
+  azp_prof_begin(e, count_dev, count_host, s);
+  conv_umma_kernel<64, 128, STAGES3, true><<<grid, 192, ws->smem3, s>>>(ws->map_act2, U->map_w3, a3);
+  azp_count_launch();
+  azp_prof_end(e, s);
+  const int NJ = W->PC + W->VC;
+  const size_t smem = (size_t)(8 * NJ * g.A + 8 * g.A + 8 * 64) * sizeof(float);
+  const int fc_grid = (zmax + 7) / 8;
+  heads_fc_kernel<8><<<fc_grid, 256, smem, s>>>(ws->feat, g.A, W->PC, W->VC, W->pfc_t, W->pfc_b, W->vfc1_t,
+                                                W->vfc1_b, W->vfc2_w, W->vfc2_b, logits, policy, value, count_dev,
+                                                count_host, back, g.G, out_by_index);
+  azp_count_launch();
+  return azp_check_launch();
+}
+
+int azp_umma_eval_leaves(azp_engine* e, NetWeights* W, const int32_t* count_dev, int count_host, int back,
+                         cudaStream_t s) {
+  UmmaWorkspace* ws = (UmmaWorkspace*)e->ws->umma;
+  UmmaWeights* U = (UmmaWeights*)W->umma;
+  const ConvGeom& g = ws->g;
+  const int zmax = count_dev ? g.G : count_host;
+  if (zmax <= 0) return AZP_OK;
+  const int grid = zmax < 4 * ws->sms ? zmax : 4 * ws->sms;
+  AZP_DISPATCH_NW(e->NW, conv1_bits_kernel, grid, 256, 0, s, g, e->tv.leaf_x, e->tv.leaf_o, e->tv.leaf_tm,
+                  e->tv.leaf_last, U->w1_bits, U->b1, ws->act1, count_dev, count_host, back);
+  azp_count_launch();
+  return run_trunk(e, W, count_dev, count_host, back, e->d_logits, e->d_policy, e->d_value, 0, s);
+}
+
+// diagnostics: intermediate activations of the last evaluation as dense float32
+__global__ void unpad_act_kernel(ConvGeom g, int n, int C, const __nv_bfloat16* __restrict__ act, float* __restrict__ out) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (size_t)n * g.A * C) return;
+  int c = i % C; size_t t = i / C; int a = t % g.A; int slot = t / g.A;
+  size_t row = (size_t)slot * g.stride + (size_t)(a / g.B + 1) * g.P + (a % g.B + 1);
+  out[i] = __bfloat162float(act[row * C + c]);
+}
+int azp_umma_debug(azp_engine* e, int layer, int n, float* out, cudaStream_t s) {
+  UmmaWorkspace* ws = (UmmaWorkspace*)e->ws->umma;
+  const ConvGeom& g = ws->g;
+  if (layer == 1 || layer == 2) {
+    int C = layer == 1 ? 32 : 64;
+    size_t total = (size_t)n * g.A * C;
+    unpad_act_kernel<<<(int)((total + 255) / 256), 256, 0, s>>>(g, n, C, layer == 1 ? ws->act1 : ws->act2, out);
+    azp_count_launch();
+    return azp_check_launch();
+  }
+  if (layer == 3) {
+    AZP_CUDA(e, cudaMemcpyAsync(out, ws->feat, (size_t)n * 6 * g.A * sizeof(float), cudaMemcpyDeviceToDevice, s));
+    return AZP_OK;
+  }
+  return AZP_ERR_INVALID_ARG;
+}
+
+int azp_umma_eval_planes(azp_engine* e, NetWeights* W, int n, const float* planes, float* logits, float* policy,
+                         float* value, cudaStream_t s) {
+  UmmaWorkspace* ws = (UmmaWorkspace*)e->ws->umma;
+  UmmaWeights* U = (UmmaWeights*)W->umma;
+  const ConvGeom& g = ws->g;
+  const int grid = n < 4 * ws->sms ? n : 4 * ws->sms;
+  conv1_planes_kernel<<<grid, 256, 4 * g.A * sizeof(float), s>>>(g, n, planes, U->w1_planes, U->b1, ws->act1);
+  azp_count_launch();
+  return run_trunk(e, W, nullptr, n, 0, logits, policy, value, 1, s);
+}

@@ -111,6 +111,13 @@ class Engine:
                                        stream_ptr()), self.h)
         return logits, policy, value
 
+    def debug_activations(self, layer, n):
+        c = {1: 32, 2: 64}.get(layer)
+        shape = (n, self.A, c) if c else (n, 6, self.A)
+        out = torch.empty(shape, device=self.device)
+        check(self.lib.azp_debug_activations(self.h, layer, n, ptr(out), stream_ptr()), self.h)
+        return out
+
     # ---- step-by-step search (host evaluator hook) ------------------------------------------------
     def search_begin(self, x, o, to_move, last, ply=None, game_id=None):
         n = x.shape[0]

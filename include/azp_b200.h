@@ -132,6 +132,10 @@ size_t azp_weight_count(const azp_engine* e);
 int azp_net_forward(azp_engine* e, int slot, int n, const float* planes, float* logits,
                     float* policy, float* value, void* stream);
 
+/* diagnostics (bf16 path): intermediate activations of the LAST evaluation of slots [0,n) as dense
+ * float32: layer 1 -> [n][B*B][32], layer 2 -> [n][B*B][64], layer 3 -> head features [n][6][B*B] */
+int azp_debug_activations(azp_engine* e, int layer, int n, float* out, void* stream);
+
 /* ---- search, step by step (lets a host evaluator be injected: the operator-level hook
  *      policy_value_fn of mcts.py:88-93) --------------------------------------------- */
 /* MCTS.run prologue, mcts.py:106: new trees rooted at n positions (n <= games) */

@@ -204,12 +204,50 @@ def test_mcts_edge_cases(az, golden):
     assert action is None and float(torch.as_tensor(pi).abs().sum()) == 0.0
 
 
-@pytest.mark.parametrize("size,win,sims,n", [(5, 4, 120, 24), (9, 5, 200, 16), (15, 5, 160, 8)])
-def test_fused_search_matches_oracle_with_engine_net(az, size, win, sims, n):
-    """Whole search on the device (compacted leaf batch + fp32 net kernels) vs the oracle search
-    fed with the SAME network numbers: visit counts must be identical."""
+@pytest.mark.parametrize("size", [5, 9, 15, 19])
+def test_net_bf16_tcgen05_vs_reference_golden(az, golden, size):
+    """bf16 tcgen05 path: policy / value within 2e-2 of the reference net (north-star tolerance)."""
+    g = golden("net_stem.npz")
+    params = onet.synthetic_stem_params(size, seed=size)
+    eng = az.Engine(board=size, win_length=4 if size == 5 else 5, games=8, sims=2, net_dtype=az.DTYPE_BF16)
+    eng.load_state_dict(params)
+    x = torch.from_numpy(g[f"x_{size}"].astype(np.float32)).cuda()
+    logits, policy, value = eng.net_forward(x)
+    assert np.abs(logits.cpu().numpy() - g[f"logits_{size}"]).max() <= 2e-2
+    assert np.abs(value.cpu().numpy() - g[f"value_{size}"].reshape(-1)).max() <= 2e-2
+    assert np.abs(policy.cpu().numpy().reshape(-1, size, size) - g[f"policy_{size}"]).max() <= 2e-2
+    eng.close()
+
+
+def test_net_bf16_large_batch_and_scaled_weights(az):
+    """Many tiles per CTA, both accumulator stages, O(1) activations: relative error stays at bf16 level."""
+    size, n = 15, 1500
+    params = onet.synthetic_stem_params(size, seed=4, scale=3.0)
+    eng = az.Engine(board=size, win_length=5, games=n, sims=2, net_dtype=az.DTYPE_BF16)
+    eng.load_state_dict(params)
+    rs = np.random.RandomState(0)
+    occ = rs.random_sample((n, size, size))
+    x = np.zeros((n, 4, size, size), dtype=np.float32)
+    x[:, 0], x[:, 1] = occ < 0.2, (occ >= 0.2) & (occ < 0.4)
+    x[np.arange(n), 2, rs.randint(size, size=n), rs.randint(size, size=n)] = 1
+    logits, policy, value = eng.net_forward(torch.from_numpy(x).cuda())
+    ol, ov = onet.stem_forward(params, x)
+    scale = float(ol.abs().max())
+    assert float((logits.cpu() - ol).abs().max()) <= 2e-2 * max(1.0, scale)
+    assert float((value.cpu() - ov.reshape(-1)).abs().max()) <= 2e-2
+    assert float((policy.cpu() - torch.softmax(ol, 1)).abs().max()) <= 2e-2
+    eng.close()
+
+
+@pytest.mark.parametrize("size,win,sims,n,dtype", [(5, 4, 120, 24, "f32"), (9, 5, 200, 16, "f32"),
+                                                   (15, 5, 160, 8, "f32"), (9, 5, 150, 16, "bf16"),
+                                                   (15, 5, 200, 40, "bf16")])
+def test_fused_search_matches_oracle_with_engine_net(az, size, win, sims, n, dtype):
+    """Whole search on the device (compacted leaf batch + the engine's net kernels, fp32 SIMT or bf16
+    tcgen05) vs the oracle search fed with the SAME network numbers: visit counts must be identical."""
     params = onet.synthetic_stem_params(size, seed=100 + size, scale=2.0)
-    eng = az.Engine(board=size, win_length=win, games=n, sims=sims, c_puct=2.0)
+    eng = az.Engine(board=size, win_length=win, games=n, sims=sims, c_puct=2.0,
+                    net_dtype=az.DTYPE_BF16 if dtype == "bf16" else az.DTYPE_F32)
     eng.load_state_dict(params)
     states = []
     for i in range(n):
