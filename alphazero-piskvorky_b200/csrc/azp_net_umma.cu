@@ -239,37 +239,72 @@ struct ConvArgs {
   ConvGeom g;
   const float* bias;              // [COUT]
   __nv_bfloat16* out;             // !HEADS: activations [rows][COUT]
-  // HEADS: 1x1 head convs fused into the epilogue
-  const float* head_w;            // [COUT][8]  (transposed, zero padded to 8 outputs)
-  const float* head_b;            // [8]
-  float* feat;                    // [G][NJ][A]
+  const float* head_b;            // HEADS: [8] bias of the fused 1x1 head convs (policy rows first)
+  float* feat;                    // HEADS: [G][NJ][A]
   int NJ;
   const int32_t* count_dev; int count_host; int back;
   int stage_rows;                 // 128 + 2P
 };
 
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+      ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]),
+        "r"(v[8]), "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]) : "memory");
+}
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&r)[8]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+// D[tmem] (+)= A[tmem] * B[smem]^T : A is read from tensor memory (lane = row, two bf16 per column)
+__device__ __forceinline__ void umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+}
+
+constexpr int CONV_THREADS = 320;     // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue (2 per TMEM lane quarter)
+constexpr int HEAD_N = 16;            // fused 1x1 head convs: 6 (or 3) outputs padded to the UMMA minimum N
+
+// HEADS = true additionally fuses both 1x1 head convolutions (net.py:47,51) as a SECOND tensor-core
+// GEMM per tile: the epilogue writes relu(acc + bias) as bf16 straight back into tensor memory, and a
+// TS-mode UMMA (A from TMEM) multiplies it with the [16 x COUT] head weights; the wide activation never
+// leaves the SM and the epilogue warps only touch each accumulator element once.
 template <int CIN, int COUT, int STAGES, bool HEADS>
-__global__ void __launch_bounds__(192, 1) conv_umma_kernel(const __grid_constant__ CUtensorMap map_act,
-                                                           const __grid_constant__ CUtensorMap map_w,
-                                                           const ConvArgs args) {
+__global__ void __launch_bounds__(CONV_THREADS, 1) conv_umma_kernel(const __grid_constant__ CUtensorMap map_act,
+                                                                    const __grid_constant__ CUtensorMap map_w,
+                                                                    const __grid_constant__ CUtensorMap map_hw,
+                                                                    const ConvArgs args) {
   using S = ConvSmem<CIN, COUT, STAGES, HEADS>;
   constexpr int ROWB = S::ROWB;
   constexpr int KSTEPS = CIN / 16;
-  constexpr uint32_t TMEM_COLS = (2 * COUT <= 32) ? 32 : (2 * COUT <= 64 ? 64 : (2 * COUT <= 128 ? 128 : 256));
+  constexpr int HW_BYTES = HEADS ? (COUT / 64) * HEAD_N * 128 : 0;     // head weights: K chunks of 64 x 16 rows
+  constexpr uint32_t COL_ACT = 2 * COUT;                    // bf16 copy of the activated tile (COUT/2 columns)
+  constexpr uint32_t COL_HEAD = COL_ACT + COUT / 2;         // head accumulator (HEAD_N columns)
+  constexpr uint32_t NEED = HEADS ? COL_HEAD + HEAD_N : 2 * COUT;
+  constexpr uint32_t TMEM_COLS = NEED <= 32 ? 32 : (NEED <= 64 ? 64 : (NEED <= 128 ? 128 : (NEED <= 256 ? 256 : 512)));
+  constexpr int HALF = COUT / 2;                            // channels per epilogue warp
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   const int stage_bytes = args.stage_rows * ROWB;          // multiple of 1024 (P multiple of 8)
   uint8_t* s_w = smem;                                      // 9 taps x [COUT][CIN]
   uint8_t* s_a = s_w + S::W_BYTES;                          // STAGES x [stage_rows][CIN]
-  uint8_t* s_tail = s_a + (size_t)STAGES * stage_bytes;
+  uint8_t* s_hw = s_a + (size_t)STAGES * stage_bytes;       // HEADS: [COUT/64][16][64] bf16, 128B swizzle
+  uint8_t* s_tail = s_hw + HW_BYTES;
   uint64_t* full = reinterpret_cast<uint64_t*>(s_tail);     // [STAGES]
   uint64_t* empty = full + STAGES;                          // [STAGES]
   uint64_t* tfull = empty + STAGES;                         // [2]
   uint64_t* tempty = tfull + 2;                             // [2]
   uint64_t* wbar = tempty + 2;                              // [1]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(wbar + 1);
-  float* s_bias = reinterpret_cast<float*>(tmem_slot + 2);  // [COUT]
-  float* s_hw = s_bias + COUT;                              // HEADS: [COUT][8] then [8]
+  uint64_t* act_full = wbar + 1;                            // [1] epilogue -> MMA: bf16 tile is in TMEM
+  uint64_t* head_full = act_full + 1;                       // [1] MMA -> epilogue: head accumulator ready
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(head_full + 1);
+  float* s_bias = reinterpret_cast<float*>(tmem_slot + 2);  // [COUT] (+ [8] head bias)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const ConvGeom g = args.g;
@@ -281,15 +316,14 @@ __global__ void __launch_bounds__(192, 1) conv_umma_kernel(const __grid_constant
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < STAGES; i++) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
-    for (int i = 0; i < 2; i++) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 4); }
+    for (int i = 0; i < 2; i++) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 8); }
     mbar_init(wbar, 1);
+    mbar_init(act_full, 8);
+    mbar_init(head_full, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   for (int i = threadIdx.x; i < COUT; i += blockDim.x) s_bias[i] = args.bias[i];
-  if (HEADS) {
-    for (int i = threadIdx.x; i < COUT * 8 + 8; i += blockDim.x)
-      s_hw[i] = i < COUT * 8 ? args.head_w[i] : args.head_b[i - COUT * 8];
-  }
+  if (HEADS && threadIdx.x < 8) s_bias[COUT + threadIdx.x] = args.head_b[threadIdx.x];
   if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
   tc_fence_before();
   __syncthreads();
@@ -299,8 +333,10 @@ __global__ void __launch_bounds__(192, 1) conv_umma_kernel(const __grid_constant
   if (warp == 0) {
     // ===== TMA producer =====
     if (lane == 0) {
-      mbar_expect_tx(wbar, S::W_BYTES);
+      mbar_expect_tx(wbar, S::W_BYTES + HW_BYTES);
       for (int tap = 0; tap < 9; tap++) tma_load_2d(s_w + tap * S::W_TAP_BYTES, &map_w, wbar, 0, tap * COUT);
+      if (HEADS)
+        for (int kc = 0; kc < COUT / 64; kc++) tma_load_2d(s_hw + kc * HEAD_N * 128, &map_hw, wbar, kc * 64, 0);
       int it = 0;
       for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
         for (int dxi = 0; dxi < 3; dxi++, it++) {
@@ -317,7 +353,18 @@ __global__ void __launch_bounds__(192, 1) conv_umma_kernel(const __grid_constant
     // ===== MMA issuer =====
     if (lane == 0) {
       const uint32_t idesc = umma_idesc(COUT);
-      const uint32_t a_base = smem_u32(s_a), w_base = smem_u32(s_w);
+      const uint32_t idesc_head = umma_idesc(HEAD_N);
+      const uint32_t a_base = smem_u32(s_a), w_base = smem_u32(s_w), hw_base = smem_u32(s_hw);
+      // 1x1 head GEMM of local tile j: [128 x COUT] (TMEM, bf16) x [COUT x 16] (smem) -> TMEM cols COL_HEAD..
+      auto issue_head = [&](int j) {
+        mbar_wait(act_full, (uint32_t)(j & 1));
+        tc_fence_after();
+#pragma unroll
+        for (int k = 0; k < COUT / 16; k++)
+          umma_bf16_ts(tmem_base + COL_HEAD, tmem_base + COL_ACT + k * 8,
+                       umma_desc(hw_base + (k / 4) * HEAD_N * 128 + (k % 4) * 32, 128), idesc_head, k > 0 ? 1u : 0u);
+        umma_commit(head_full);
+      };
       mbar_wait(wbar, 0);
       tc_fence_after();
       int it = 0, tl = 0;
@@ -347,37 +394,61 @@ __global__ void __launch_bounds__(192, 1) conv_umma_kernel(const __grid_constant
           umma_commit(&empty[st]);                        // stage reusable once these MMAs retire
         }
         umma_commit(&tfull[acc]);                         // accumulator complete
+        if (HEADS && tl > 0) issue_head(tl - 1);          // queued behind this tile's conv MMAs
       }
+      if (HEADS && tl > 0) issue_head(tl - 1);
     }
   } else {
-    // ===== epilogue =====
-    const int q = warp & 3;                               // TMEM lane quarter this warp may access
-    int tl = 0;
+    // ===== epilogue: warp (q, h) owns TMEM lanes 32q..32q+31 (tile rows) and channel half h =====
+    const int q = warp & 3;
+    const int h = (warp - 2) >> 2;
+    const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
+    // head outputs of local tile j (global tile tj): +bias, ReLU, scatter to feat[slot][j][pixel]
+    auto write_heads = [&](int tj) {
+      uint32_t r[8];
+      tmem_ld8(tmem_base + lane_addr + COL_HEAD, r);
+      const long long R = row_begin + (long long)tj * TILE_M + q * 32 + lane;
+      const int slot = (int)(R / g.stride), pos = (int)(R % g.stride);
+      const int y = pos / g.P, x = pos % g.P;
+      if (y >= 1 && x >= 1 && x <= g.B && slot < g.G) {
+        float* f = args.feat + (size_t)slot * args.NJ * g.A + (y - 1) * g.B + (x - 1);
+#pragma unroll
+        for (int j = 0; j < 8; j++)
+          if (j < args.NJ) f[(size_t)j * g.A] = fmaxf(__uint_as_float(r[j]) + s_bias[COUT + j], 0.f);
+      }
+    };
+    int tl = 0, t_prev = 0;
     for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, tl++) {
       const int acc = tl & 1;
       const uint32_t acc_ph = (tl >> 1) & 1;
       mbar_wait(&tfull[acc], acc_ph);
+      if (HEADS && tl > 0) {
+        // previous tile's head GEMM has retired: its TMEM input may be overwritten, its output read
+        mbar_wait(head_full, (uint32_t)((tl - 1) & 1));
+        tc_fence_after();
+        if (h == 0) write_heads(t_prev);
+      }
       tc_fence_after();
       const long long R = row_begin + (long long)t * TILE_M + q * 32 + lane;     // global padded row
       const int slot = (int)(R / g.stride);
       const int pos = (int)(R % g.stride);
       const int y = pos / g.P, x = pos % g.P;
       const bool interior = y >= 1 && x >= 1 && x <= g.B && slot < g.G;
-      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * COUT);
+      const uint32_t taddr = tmem_base + lane_addr + (uint32_t)(acc * COUT + h * HALF);
       if (!HEADS) {
-        uint4* dst = reinterpret_cast<uint4*>(args.out + (size_t)R * COUT);
+        uint4* dst = reinterpret_cast<uint4*>(args.out + (size_t)R * COUT + h * HALF);
         const bool in_range = slot < g.G;
 #pragma unroll
-        for (int c0 = 0; c0 < COUT; c0 += 32) {
+        for (int c0 = 0; c0 < HALF; c0 += 32) {
           uint32_t r[32];
           tmem_ld32(taddr + c0, r);
           uint32_t packed[16];
 #pragma unroll
           for (int j = 0; j < 16; j++) {
-            float v0 = interior ? fmaxf(__uint_as_float(r[2 * j]) + s_bias[c0 + 2 * j], 0.f) : 0.f;
-            float v1 = interior ? fmaxf(__uint_as_float(r[2 * j + 1]) + s_bias[c0 + 2 * j + 1], 0.f) : 0.f;
-            __nv_bfloat162 h = __floats2bfloat162_rn(v0, v1);
-            packed[j] = *reinterpret_cast<uint32_t*>(&h);
+            float v0 = interior ? fmaxf(__uint_as_float(r[2 * j]) + s_bias[h * HALF + c0 + 2 * j], 0.f) : 0.f;
+            float v1 = interior ? fmaxf(__uint_as_float(r[2 * j + 1]) + s_bias[h * HALF + c0 + 2 * j + 1], 0.f) : 0.f;
+            __nv_bfloat162 hh = __floats2bfloat162_rn(v0, v1);
+            packed[j] = *reinterpret_cast<uint32_t*>(&hh);
           }
           if (in_range) {
 #pragma unroll
@@ -385,36 +456,35 @@ __global__ void __launch_bounds__(192, 1) conv_umma_kernel(const __grid_constant
               dst[c0 / 8 + v] = make_uint4(packed[4 * v], packed[4 * v + 1], packed[4 * v + 2], packed[4 * v + 3]);
           }
         }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tempty[acc]);
       } else {
-        float dot[8];
 #pragma unroll
-        for (int j = 0; j < 8; j++) dot[j] = 0.f;
-#pragma unroll
-        for (int c0 = 0; c0 < COUT; c0 += 32) {
+        for (int c0 = 0; c0 < HALF; c0 += 32) {
           uint32_t r[32];
           tmem_ld32(taddr + c0, r);
+          uint32_t packed[16];
 #pragma unroll
-          for (int i = 0; i < 32; i++) {
-            const float v = fmaxf(__uint_as_float(r[i]) + s_bias[c0 + i], 0.f);
-            const float4 w0 = *reinterpret_cast<const float4*>(s_hw + (c0 + i) * 8);
-            const float4 w1 = *reinterpret_cast<const float4*>(s_hw + (c0 + i) * 8 + 4);
-            dot[0] = fmaf(v, w0.x, dot[0]); dot[1] = fmaf(v, w0.y, dot[1]);
-            dot[2] = fmaf(v, w0.z, dot[2]); dot[3] = fmaf(v, w0.w, dot[3]);
-            dot[4] = fmaf(v, w1.x, dot[4]); dot[5] = fmaf(v, w1.y, dot[5]);
-            dot[6] = fmaf(v, w1.z, dot[6]); dot[7] = fmaf(v, w1.w, dot[7]);
+          for (int j = 0; j < 16; j++) {
+            float v0 = fmaxf(__uint_as_float(r[2 * j]) + s_bias[h * HALF + c0 + 2 * j], 0.f);
+            float v1 = fmaxf(__uint_as_float(r[2 * j + 1]) + s_bias[h * HALF + c0 + 2 * j + 1], 0.f);
+            __nv_bfloat162 hh = __floats2bfloat162_rn(v0, v1);
+            packed[j] = *reinterpret_cast<uint32_t*>(&hh);
           }
+          tmem_st16(tmem_base + lane_addr + COL_ACT + (uint32_t)((h * HALF + c0) / 2), packed);
         }
-        if (interior) {
-          const int pix = (y - 1) * g.B + (x - 1);
-          float* f = args.feat + (size_t)slot * args.NJ * g.A + pix;
-#pragma unroll
-          for (int j = 0; j < 8; j++)
-            if (j < args.NJ) f[(size_t)j * g.A] = fmaxf(dot[j] + s_hw[COUT * 8 + j], 0.f);
-        }
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) { mbar_arrive(&tempty[acc]); mbar_arrive(act_full); }
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty[acc]);
+      t_prev = t;
+    }
+    if (HEADS && tl > 0) {
+      mbar_wait(head_full, (uint32_t)((tl - 1) & 1));
+      tc_fence_after();
+      if (h == 0) write_heads(t_prev);
     }
   }
   tc_fence_before();
@@ -512,14 +582,16 @@ EncodeTiledFn get_encode() {
 }
 
 // 2-D bf16 tensor [rows][cols] row-major; box = [box_rows][cols]; swizzle span == one row
-int make_map(azp_engine* e, CUtensorMap* map, const void* base, uint64_t rows, int cols, int box_rows) {
+int make_map(azp_engine* e, CUtensorMap* map, const void* base, uint64_t rows, int cols, int box_rows,
+             int box_cols = 0) {
+  if (box_cols == 0) box_cols = cols;
   EncodeTiledFn enc = get_encode();
   if (!enc) { e->set_error("cuTensorMapEncodeTiled unavailable"); return AZP_ERR_CUDA; }
   cuuint64_t dims[2] = {(cuuint64_t)cols, rows};
   cuuint64_t strides[1] = {(cuuint64_t)cols * 2};
-  cuuint32_t box[2] = {(cuuint32_t)cols, (cuuint32_t)box_rows};
+  cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
-  CUtensorMapSwizzle sw = cols * 2 == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
+  CUtensorMapSwizzle sw = box_cols * 2 == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
   CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -543,9 +615,9 @@ struct UmmaWeights {
   float* b1 = nullptr; float* b2 = nullptr; float* b3 = nullptr;
   float* w1_bits = nullptr;           // [tap][3][32]
   float* w1_planes = nullptr;         // [tap][4][32]
-  float* head_wt = nullptr;           // [128][8]
+  __nv_bfloat16* head_w16 = nullptr;  // [16][128] 1x1 head conv weights (policy rows first, zero padded)
   float* head_b8 = nullptr;           // [8]
-  CUtensorMap map_w2, map_w3;
+  CUtensorMap map_w2, map_w3, map_hw;
 };
 
 constexpr int STAGES2 = 6, STAGES3 = 3;
@@ -553,8 +625,8 @@ constexpr int STAGES2 = 6, STAGES3 = 3;
 template <int CIN, int COUT, int STAGES, bool HEADS>
 int conv_smem_bytes(int stage_rows) {
   using S = ConvSmem<CIN, COUT, STAGES, HEADS>;
-  return 1024 + S::W_BYTES + STAGES * stage_rows * S::ROWB + (2 * STAGES + 5) * 8 + 16 + COUT * 4 +
-         (HEADS ? (COUT * 8 + 8) * 4 : 0) + 64;
+  return 1024 + S::W_BYTES + STAGES * stage_rows * S::ROWB + (HEADS ? (COUT / 64) * HEAD_N * 128 : 0) +
+         (2 * STAGES + 7) * 8 + 16 + (COUT + 8) * 4 + 64;
 }
 
 }  // namespace
@@ -644,15 +716,17 @@ int azp_umma_build(azp_engine* e, const HostNet& net, NetWeights* W) {
   if ((st = up(e, &U->b3, net.convs[2].b))) return st;
   if ((st = make_map(e, &U->map_w2, U->w2, 9 * 64, 32, 64))) return st;
   if ((st = make_map(e, &U->map_w3, U->w3, 9 * 128, 64, 128))) return st;
-  // heads: [C][8] transposed 1x1 conv weights (policy rows first), fp32
+  // heads: [16][C] bf16 1x1 conv weights (policy rows first, rows >= NJ zero) = B operand of the head GEMM
   const int NJ = net.PC + net.VC;
-  std::vector<float> hw((size_t)net.C * 8, 0.f), hb(8, 0.f);
+  std::vector<__nv_bfloat16> hw((size_t)HEAD_N * net.C, __float2bfloat16(0.f));
+  std::vector<float> hb(8, 0.f);
   for (int j = 0; j < NJ; j++) {
     hb[j] = net.head_b[j];
-    for (int c = 0; c < net.C; c++) hw[(size_t)c * 8 + j] = net.head_w[(size_t)j * net.C + c];
+    for (int c = 0; c < net.C; c++) hw[(size_t)j * net.C + c] = __float2bfloat16(net.head_w[(size_t)j * net.C + c]);
   }
-  if ((st = up(e, &U->head_wt, hw))) return st;
+  if ((st = up(e, &U->head_w16, hw))) return st;
   if ((st = up(e, &U->head_b8, hb))) return st;
+  if ((st = make_map(e, &U->map_hw, U->head_w16, HEAD_N, net.C, HEAD_N, 64))) return st;
   const int PK = net.PC * A, VK = net.VC * A;
   std::vector<float> pt((size_t)PK * A), vt((size_t)VK * 64);
   for (int a = 0; a < A; a++) for (int k = 0; k < PK; k++) pt[(size_t)k * A + a] = net.pfc_w[(size_t)a * PK + k];
@@ -677,16 +751,16 @@ static int run_trunk(azp_engine* e, NetWeights* W, const int32_t* count_dev, int
   const int max_tiles = (int)(((long long)zmax * g.stride + TILE_M - 1) / TILE_M);
   const int grid = max_tiles < ws->sms ? max_tiles : ws->sms;
   ConvArgs a2;
-  a2.g = g; a2.bias = U->b2; a2.out = ws->act2; a2.head_w = nullptr; a2.head_b = nullptr; a2.feat = nullptr; a2.NJ = 0;
+  a2.g = g; a2.bias = U->b2; a2.out = ws->act2; a2.head_b = nullptr; a2.feat = nullptr; a2.NJ = 0;
   a2.count_dev = count_dev; a2.count_host = count_host; a2.back = back; a2.stage_rows = TILE_M + 2 * g.P;
-  conv_umma_kernel<32, 64, STAGES2, false><<<grid, 192, ws->smem2, s>>>(ws->map_act1, U->map_w2, a2);
+  conv_umma_kernel<32, 64, STAGES2, false><<<grid, CONV_THREADS, ws->smem2, s>>>(ws->map_act1, U->map_w2, U->map_w2, a2);
   azp_count_launch();
   ConvArgs a3 = a2;
-  a3.bias = U->b3; a3.out = nullptr; a3.head_w = U->head_wt; a3.head_b = U->head_b8; a3.feat = ws->feat;
+  a3.bias = U->b3; a3.out = nullptr; a3.head_b = U->head_b8; a3.feat = ws->feat;
   a3.NJ = W->PC + W->VC;
   e->prof_flops_per_board = 2.0 * 9.0 * 64 * 128 * g.A;
   azp_prof_begin(e, count_dev, count_host, s);
-  conv_umma_kernel<64, 128, STAGES3, true><<<grid, 192, ws->smem3, s>>>(ws->map_act2, U->map_w3, a3);
+  conv_umma_kernel<64, 128, STAGES3, true><<<grid, CONV_THREADS, ws->smem3, s>>>(ws->map_act2, U->map_w3, U->map_hw, a3);
   azp_count_launch();
   azp_prof_end(e, s);
   const int NJ = W->PC + W->VC;
