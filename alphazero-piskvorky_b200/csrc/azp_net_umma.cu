@@ -16,7 +16,7 @@
 //   conv_umma<32,64>    act1 -> act2 [rows][64]           tcgen05, bias+ReLU+pad-zero epilogue
 //   conv_umma<64,128>   act2 -> head features [n][6][A]   tcgen05, epilogue = bias+ReLU + both 1x1 head
 //                                                         convs (act3 never leaves the SM)
-//   heads_fc_kernel     features -> logits/softmax/value  SIMT fp32, weights shared by 8 boards per CTA
+//   fc_umma_kernel      features -> logits/softmax/value  tcgen05 GEMMs (policy_fc, value_fc1), thread-per-row tails
 #include "azp_net.cuh"
 #include <cuda.h>
 
@@ -137,18 +137,20 @@ __global__ void __launch_bounds__(256) conv1_bits_kernel(ConvGeom g, const uint6
       cells[a] = (int8_t)v;
     }
     __syncthreads();
-    for (int pos = threadIdx.x; pos < g.stride; pos += blockDim.x) {
+    // 4 threads per padded position, 8 output channels each: one 16-byte store per thread, 64 contiguous
+    // bytes per position
+    for (int item = threadIdx.x; item < g.stride * 4; item += blockDim.x) {
+      const int pos = item >> 2, cg = item & 3;
       const int y = pos / g.P, x = pos % g.P;
-      uint4* dst = reinterpret_cast<uint4*>(act1 + ((size_t)slot * g.stride + pos) * 32);
+      uint4* dst = reinterpret_cast<uint4*>(act1 + ((size_t)slot * g.stride + pos) * 32 + cg * 8);
       if (y < 1 || x < 1 || x > g.B) {                 // halo rows/columns stay zero
-#pragma unroll
-        for (int q = 0; q < 4; q++) dst[q] = make_uint4(0, 0, 0, 0);
+        *dst = make_uint4(0, 0, 0, 0);
         continue;
       }
       const int r = y - 1, c = x - 1;
-      float acc[32];
+      float acc[8];
 #pragma unroll
-      for (int j = 0; j < 32; j++) acc[j] = sb[j];
+      for (int j = 0; j < 8; j++) acc[j] = sb[cg * 8 + j];
 #pragma unroll
       for (int tap = 0; tap < 9; tap++) {
         const int rr = r + tap / 3 - 1, cc = c + tap % 3 - 1;
@@ -158,19 +160,18 @@ __global__ void __launch_bounds__(256) conv1_bits_kernel(ConvGeom g, const uint6
 #pragma unroll
         for (int pl = 0; pl < 3; pl++) {
           if (!(v & (1 << pl))) continue;
-          const float* wr = sw + (tap * 3 + pl) * 32;
+          const float* wr = sw + (tap * 3 + pl) * 32 + cg * 8;
 #pragma unroll
-          for (int j = 0; j < 32; j++) acc[j] += wr[j];
+          for (int j = 0; j < 8; j++) acc[j] += wr[j];
         }
       }
-      uint32_t packed[16];
+      uint32_t packed[4];
 #pragma unroll
-      for (int j = 0; j < 16; j++) {
+      for (int j = 0; j < 4; j++) {
         __nv_bfloat162 h = __floats2bfloat162_rn(fmaxf(acc[2 * j], 0.f), fmaxf(acc[2 * j + 1], 0.f));
         packed[j] = *reinterpret_cast<uint32_t*>(&h);
       }
-#pragma unroll
-      for (int q = 0; q < 4; q++) dst[q] = make_uint4(packed[4 * q], packed[4 * q + 1], packed[4 * q + 2], packed[4 * q + 3]);
+      *dst = make_uint4(packed[0], packed[1], packed[2], packed[3]);
     }
   }
 }
@@ -240,8 +241,8 @@ struct ConvArgs {
   const float* bias;              // [COUT]
   __nv_bfloat16* out;             // !HEADS: activations [rows][COUT]
   const float* head_b;            // HEADS: [8] bias of the fused 1x1 head convs (policy rows first)
-  float* feat;                    // HEADS: [G][NJ][A]
-  int NJ;
+  __nv_bfloat16* feat;            // HEADS: [G][FK] bf16: policy features at ch*A+pix, value features at PKp+ch*A+pix
+  int NJ, PC, PKp, FK;
   const int32_t* count_dev; int count_host; int back;
   int stage_rows;                 // 128 + 2P
 };
@@ -411,10 +412,12 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_umma_kernel(const __grid
       const int slot = (int)(R / g.stride), pos = (int)(R % g.stride);
       const int y = pos / g.P, x = pos % g.P;
       if (y >= 1 && x >= 1 && x <= g.B && slot < g.G) {
-        float* f = args.feat + (size_t)slot * args.NJ * g.A + (y - 1) * g.B + (x - 1);
+        __nv_bfloat16* f = args.feat + (size_t)slot * args.FK + (y - 1) * g.B + (x - 1);
 #pragma unroll
         for (int j = 0; j < 8; j++)
-          if (j < args.NJ) f[(size_t)j * g.A] = fmaxf(__uint_as_float(r[j]) + s_bias[COUT + j], 0.f);
+          if (j < args.NJ)
+            f[j < args.PC ? j * g.A : args.PKp + (j - args.PC) * g.A] =
+                __float2bfloat16(fmaxf(__uint_as_float(r[j]) + s_bias[COUT + j], 0.f));
       }
     };
     int tl = 0, t_prev = 0;
@@ -492,76 +495,170 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_umma_kernel(const __grid
   if (warp == 1) tmem_dealloc(tmem_base, TMEM_COLS);
 }
 
-// ---- FC heads (SIMT fp32): BT boards share every weight read ----------------------------------------------
-template <int BT>
-__global__ void __launch_bounds__(256) heads_fc_kernel(
-    const float* __restrict__ feat /*[G][NJ][A]*/, int A, int PC, int VC, const float* __restrict__ pfc_t,
-    const float* __restrict__ pfc_b, const float* __restrict__ vfc1_t, const float* __restrict__ vfc1_b,
-    const float* __restrict__ vfc2_w, const float* __restrict__ vfc2_b, float* __restrict__ logits_out,
-    float* __restrict__ policy_out, float* __restrict__ value_out, const int32_t* __restrict__ count_dev,
-    int count_host, int back, int G, int out_by_index) {
-  const int count = count_dev ? *count_dev : count_host;
-  const int NJ = PC + VC;
-  extern __shared__ float sm[];
-  float* sf = sm;                      // [BT][NJ*A]
-  float* lg = sf + BT * NJ * A;        // [BT][A]
-  float* hid = lg + BT * A;            // [BT][64]
-  const int tid = threadIdx.x;
-  for (int b0 = blockIdx.x * BT; b0 < count; b0 += gridDim.x * BT) {
-    const int nb = min(BT, count - b0);
-    __syncthreads();
-    for (int i = tid; i < BT * NJ * A; i += 256) {
-      int b = i / (NJ * A), k = i % (NJ * A);
-      int row = back ? G - 1 - (b0 + b) : b0 + b;
-      sf[i] = b < nb ? feat[(size_t)row * NJ * A + k] : 0.f;
-    }
-    __syncthreads();
-    const int PK = PC * A, VK = VC * A;
-    for (int a = tid; a < A; a += 256) {
-      float acc[BT];
-      const float bias = pfc_b[a];
-#pragma unroll
-      for (int b = 0; b < BT; b++) acc[b] = bias;
-      for (int k = 0; k < PK; k++) {
-        const float w = pfc_t[(size_t)k * A + a];
-#pragma unroll
-        for (int b = 0; b < BT; b++) acc[b] = fmaf(sf[b * NJ * A + k], w, acc[b]);
+// ---- FC heads as tensor-core GEMMs -------------------------------------------------------------------------
+// job 0 (blockIdx.y == 0): policy_fc  logits[b][a] = feat[b][0:PK] . Wp[a][:] + bp[a]  then softmax over ALL cells
+// job 1 (blockIdx.y == 1): value_fc1 (+ReLU), value_fc2, tanh                          (net.py:64-70)
+// One CTA = 128 boards (UMMA M).  A = bf16 feature rows, B = bf16 weight rows (both K-major, TMA, 128B
+// swizzle, K chunks of 64), fp32 accumulators in TMEM; every epilogue thread owns one board's whole row, so
+// softmax / the value tail need no cross-thread reduction.
+struct FcJob {
+  int n_total;                    // accumulator columns (multiple of 16)
+  int n_first;                    // N of the first UMMA (the second covers n_total - n_first, 0 if none)
+  int n_valid;                    // real outputs
+  int k_chunks;                   // ceil(K / 64)
+  int k_off;                      // first feature column of this job
+  const float* bias;              // [n_valid]
+};
+struct FcArgs {
+  FcJob job[2];
+  int A, G, stages, b_rows;       // b_rows = rows of B staged per K chunk (multiple of 64)
+  const float* vfc2_w; const float* vfc2_b;
+  float* logits; float* policy; float* value;
+  const int32_t* count_dev; int count_host; int back; int out_by_index;
+};
+
+__global__ void __launch_bounds__(192, 1) fc_umma_kernel(const __grid_constant__ CUtensorMap map_feat,
+                                                         const __grid_constant__ CUtensorMap map_wp,
+                                                         const __grid_constant__ CUtensorMap map_wv,
+                                                         const FcArgs args) {
+  const int count = args.count_dev ? *args.count_dev : args.count_host;
+  const int tile = blockIdx.x;
+  if (tile * TILE_M >= count) return;
+  const FcJob job = args.job[blockIdx.y];
+  const CUtensorMap* map_w = blockIdx.y == 0 ? &map_wp : &map_wv;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  const int stage_bytes = TILE_M * 128 + args.b_rows * 128;
+  uint8_t* s_tail = smem + (size_t)args.stages * stage_bytes;
+  uint64_t* full = reinterpret_cast<uint64_t*>(s_tail);
+  uint64_t* empty = full + 8;
+  uint64_t* tfull = empty + 8;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tfull + 1);
+  float* s_bias = reinterpret_cast<float*>(tmem_slot + 2);          // [n_total]
+  float* s_w2 = s_bias + 512;                                       // [64] + [1]
+  float* s_inv = s_w2 + 72;                                         // [128] per-row 1/sum
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int row0 = (args.back ? args.G - count : 0) + tile * TILE_M;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < args.stages; i++) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+    mbar_init(tfull, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  for (int i = threadIdx.x; i < job.n_total; i += blockDim.x) s_bias[i] = i < job.n_valid ? job.bias[i] : 0.f;
+  if (threadIdx.x < 65) s_w2[threadIdx.x] = threadIdx.x < 64 ? args.vfc2_w[threadIdx.x] : args.vfc2_b[0];
+  if (warp == 1) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int kc = 0; kc < job.k_chunks; kc++) {
+        const int st = kc % args.stages;
+        const uint32_t ph = (kc / args.stages) & 1;
+        mbar_wait(&empty[st], ph ^ 1);
+        mbar_expect_tx(&full[st], (uint32_t)stage_bytes);
+        uint8_t* sa = smem + (size_t)st * stage_bytes;
+        tma_load_2d(sa, &map_feat, &full[st], job.k_off + kc * 64, row0);
+        for (int r = 0; r < args.b_rows; r += 64) tma_load_2d(sa + TILE_M * 128 + r * 128, map_w, &full[st], kc * 64, r);
       }
-#pragma unroll
-      for (int b = 0; b < BT; b++) lg[b * A + a] = acc[b];
     }
-    for (int i = tid; i < BT * 64; i += 256) {
-      const int b = i / 64, j = i % 64;
-      float s = vfc1_b[j];
-      const float* vf = sf + b * NJ * A + PK;
-      for (int k = 0; k < VK; k++) s = fmaf(vf[k], vfc1_t[(size_t)k * 64 + j], s);
-      hid[i] = fmaxf(s, 0.f);
-    }
-    __syncthreads();
-    // one warp per board: value head tail + softmax
-    const int warp = tid >> 5, lane = tid & 31;
-    for (int b = warp; b < nb; b += 8) {
-      const int row = back ? G - 1 - (b0 + b) : b0 + b;
-      const int orow = out_by_index ? b0 + b : row;
-      float s = hid[b * 64 + lane] * vfc2_w[lane] + hid[b * 64 + lane + 32] * vfc2_w[lane + 32];
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc1 = umma_idesc(job.n_first);
+      const uint32_t idesc2 = umma_idesc(job.n_total - job.n_first);
+      uint32_t accumulate = 0;
+      for (int kc = 0; kc < job.k_chunks; kc++) {
+        const int st = kc % args.stages;
+        const uint32_t ph = (kc / args.stages) & 1;
+        mbar_wait(&full[st], ph);
+        tc_fence_after();
+        const uint32_t a_addr = smem_u32(smem + (size_t)st * stage_bytes);
+        const uint32_t b_addr = a_addr + TILE_M * 128;
 #pragma unroll
-      for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(AZP_FULL, s, o);
-      if (lane == 0 && value_out) value_out[orow] = tanhf(s + vfc2_b[0]);
+        for (int k = 0; k < 4; k++) {
+          umma_bf16(tmem_base, umma_desc(a_addr + k * 32, 128), umma_desc(b_addr + k * 32, 128), idesc1, accumulate);
+          if (job.n_total > job.n_first)
+            umma_bf16(tmem_base + job.n_first, umma_desc(a_addr + k * 32, 128),
+                      umma_desc(b_addr + job.n_first * 128 + k * 32, 128), idesc2, accumulate);
+          accumulate = 1;
+        }
+        umma_commit(&empty[st]);
+      }
+      umma_commit(tfull);
+    }
+  } else {
+    const int q = warp & 3;
+    mbar_wait(tfull, 0);
+    tc_fence_after();
+    const int bi = tile * TILE_M + q * 32 + lane;              // index within the evaluated batch
+    const bool valid = bi < count;
+    const int row = args.back ? args.G - count + bi : bi;
+    const int orow = args.out_by_index ? bi : row;
+    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
+    if (blockIdx.y == 0) {
+      const int A = args.A;
       float m = -INFINITY;
-      for (int a = lane; a < A; a += 32) m = fmaxf(m, lg[b * A + a]);
+      for (int c0 = 0; c0 < job.n_total; c0 += 32) {           // pass 1: logits out, row max
+        uint32_t r[32];
+        tmem_ld32(taddr + c0, r);
 #pragma unroll
-      for (int o = 16; o; o >>= 1) m = fmaxf(m, __shfl_xor_sync(AZP_FULL, m, o));
-      float z = 0.f;
-      for (int a = lane; a < A; a += 32) z += expf(lg[b * A + a] - m);
-#pragma unroll
-      for (int o = 16; o; o >>= 1) z += __shfl_xor_sync(AZP_FULL, z, o);
-      for (int a = lane; a < A; a += 32) {
-        const float l = lg[b * A + a];
-        if (logits_out) logits_out[(size_t)orow * A + a] = l;
-        if (policy_out) policy_out[(size_t)orow * A + a] = expf(l - m) / z;
+        for (int i = 0; i < 32; i++) {
+          if (c0 + i < A) {
+            const float l = __uint_as_float(r[i]) + s_bias[c0 + i];
+            m = fmaxf(m, l);
+            if (valid && args.logits) args.logits[(size_t)orow * A + c0 + i] = l;
+          }
+        }
       }
+      // pass 2: exp(l - max) staged (unnormalised) through the now idle pipeline buffers; the row sum is
+      // applied during the copy-out, so the tile leaves the SM as one contiguous, coalesced block
+      float* stage = reinterpret_cast<float*>(smem);
+      const int pitch = A | 1;                                 // odd pitch: conflict-free row-per-thread writes
+      float* srow = stage + (size_t)(q * 32 + lane) * pitch;
+      float z = 0.f;
+      for (int c0 = 0; c0 < job.n_total; c0 += 32) {
+        uint32_t r[32];
+        tmem_ld32(taddr + c0, r);
+#pragma unroll
+        for (int i = 0; i < 32; i++) {
+          if (c0 + i < A) {
+            const float ex = __expf(__uint_as_float(r[i]) + s_bias[c0 + i] - m);
+            z += ex;
+            srow[c0 + i] = ex;
+          }
+        }
+      }
+      s_inv[q * 32 + lane] = 1.f / z;                          // softmax over ALL cells (controller.py:49)
+      asm volatile("bar.sync 1, 128;" ::: "memory");           // the four epilogue warps only
+      if (args.policy) {
+        const int nrows = min(TILE_M, count - tile * TILE_M);
+        const int orow0 = args.out_by_index ? tile * TILE_M : (args.back ? args.G - count + tile * TILE_M : tile * TILE_M);
+        float* out = args.policy + (size_t)orow0 * A;
+        const int et = threadIdx.x - 64;                       // 0..127
+        for (int rr = 0; rr < nrows; rr++) {
+          const float inv = s_inv[rr];
+          const float* src = stage + (size_t)rr * pitch;
+          for (int a = et; a < A; a += 128) out[(size_t)rr * A + a] = src[a] * inv;
+        }
+      }
+    } else {
+      float s = s_w2[64];
+#pragma unroll
+      for (int c0 = 0; c0 < 64; c0 += 32) {
+        uint32_t r[32];
+        tmem_ld32(taddr + c0, r);
+#pragma unroll
+        for (int i = 0; i < 32; i++) s = fmaf(fmaxf(__uint_as_float(r[i]) + s_bias[c0 + i], 0.f), s_w2[c0 + i], s);
+      }
+      if (valid && args.value) args.value[orow] = tanhf(s);
     }
   }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, 512);
 }
 
 // ---- host side -----------------------------------------------------------------------------------------------
@@ -603,8 +700,10 @@ struct UmmaWorkspace {
   ConvGeom g;
   __nv_bfloat16* act1 = nullptr;      // [rows][32]
   __nv_bfloat16* act2 = nullptr;      // [rows][64]
-  float* feat = nullptr;              // [G][6][A]
-  CUtensorMap map_act1, map_act2;
+  __nv_bfloat16* feat = nullptr;      // [G + 128][FK] bf16 head features (rows past G stay zero)
+  int PKp = 0, VKp = 0, FK = 0;       // padded feature widths (multiples of 8 elements = 16 bytes)
+  int fc_stages = 0, fc_b_rows = 0, fc_smem = 0;
+  CUtensorMap map_act1, map_act2, map_feat;
   size_t rows = 0;
   int sms = 148;
   int smem2 = 0, smem3 = 0;
@@ -617,7 +716,9 @@ struct UmmaWeights {
   float* w1_planes = nullptr;         // [tap][4][32]
   __nv_bfloat16* head_w16 = nullptr;  // [16][128] 1x1 head conv weights (policy rows first, zero padded)
   float* head_b8 = nullptr;           // [8]
-  CUtensorMap map_w2, map_w3, map_hw;
+  __nv_bfloat16* wp16 = nullptr;      // [A][PKp] policy_fc weights, K contiguous, zero padded
+  __nv_bfloat16* wv16 = nullptr;      // [64][VKp] value_fc1 weights
+  CUtensorMap map_w2, map_w3, map_hw, map_wp, map_wv;
 };
 
 constexpr int STAGES2 = 6, STAGES3 = 3;
@@ -645,7 +746,18 @@ int azp_umma_create(azp_engine* e) {
   int st;
   if ((st = e->alloc(&ws->act1, ws->rows * 32))) return st;
   if ((st = e->alloc(&ws->act2, ws->rows * 64))) return st;
-  if ((st = e->alloc(&ws->feat, (size_t)g.G * 8 * g.A))) return st;
+  ws->PKp = (4 * g.A + 7) / 8 * 8; ws->VKp = (2 * g.A + 7) / 8 * 8; ws->FK = ws->PKp + ws->VKp;
+  if ((st = e->alloc(&ws->feat, ((size_t)g.G + TILE_M) * ws->FK))) return st;
+  AZP_CUDA(e, cudaMemset(ws->feat, 0, ((size_t)g.G + TILE_M) * ws->FK * sizeof(__nv_bfloat16)));
+  if ((st = make_map(e, &ws->map_feat, ws->feat, (uint64_t)g.G + TILE_M, ws->FK, TILE_M, 64))) return st;
+  {
+    const int n_total = (g.A + 15) / 16 * 16;
+    ws->fc_b_rows = (n_total + 63) / 64 * 64;
+    const int stage = TILE_M * 128 + ws->fc_b_rows * 128;
+    ws->fc_stages = (200 * 1024) / stage; if (ws->fc_stages > 6) ws->fc_stages = 6;
+    ws->fc_smem = 1024 + ws->fc_stages * stage + 17 * 8 + 16 + (512 + 72 + 128) * 4 + 64;
+    if (n_total > 448 || ws->fc_stages < 2) { e->set_error("board too large for the FC head kernel"); return AZP_ERR_UNSUPPORTED; }
+  }
   AZP_CUDA(e, cudaMemset(ws->act1, 0, ws->rows * 32 * sizeof(__nv_bfloat16)));
   AZP_CUDA(e, cudaMemset(ws->act2, 0, ws->rows * 64 * sizeof(__nv_bfloat16)));
   const int stage_rows = TILE_M + 2 * g.P;
@@ -660,8 +772,7 @@ int azp_umma_create(azp_engine* e) {
                                    cudaFuncAttributeMaxDynamicSharedMemorySize, ws->smem2));
   AZP_CUDA(e, cudaFuncSetAttribute(conv_umma_kernel<64, 128, STAGES3, true>,
                                    cudaFuncAttributeMaxDynamicSharedMemorySize, ws->smem3));
-  AZP_CUDA(e, cudaFuncSetAttribute(heads_fc_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                   (int)((8 * 6 * g.A + 8 * g.A + 8 * 64) * sizeof(float))));
+  AZP_CUDA(e, cudaFuncSetAttribute(fc_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ws->fc_smem));
   return AZP_OK;
 }
 
@@ -727,13 +838,19 @@ int azp_umma_build(azp_engine* e, const HostNet& net, NetWeights* W) {
   if ((st = up(e, &U->head_w16, hw))) return st;
   if ((st = up(e, &U->head_b8, hb))) return st;
   if ((st = make_map(e, &U->map_hw, U->head_w16, HEAD_N, net.C, HEAD_N, 64))) return st;
-  const int PK = net.PC * A, VK = net.VC * A;
-  std::vector<float> pt((size_t)PK * A), vt((size_t)VK * 64);
-  for (int a = 0; a < A; a++) for (int k = 0; k < PK; k++) pt[(size_t)k * A + a] = net.pfc_w[(size_t)a * PK + k];
-  for (int j = 0; j < 64; j++) for (int k = 0; k < VK; k++) vt[(size_t)k * 64 + j] = net.vfc1_w[(size_t)j * VK + k];
-  if ((st = up(e, &W->pfc_t, pt))) return st;
+  {
+    UmmaWorkspace* ws = (UmmaWorkspace*)e->ws->umma;
+    const int PK = net.PC * A, VK = net.VC * A;
+    if (net.PC != 4 || net.VC != 2) { e->set_error("bf16 path expects 4 policy / 2 value head channels"); return AZP_ERR_UNSUPPORTED; }
+    std::vector<__nv_bfloat16> wp((size_t)A * ws->PKp, __float2bfloat16(0.f)), wv((size_t)64 * ws->VKp, __float2bfloat16(0.f));
+    for (int a = 0; a < A; a++) for (int k = 0; k < PK; k++) wp[(size_t)a * ws->PKp + k] = __float2bfloat16(net.pfc_w[(size_t)a * PK + k]);
+    for (int j = 0; j < 64; j++) for (int k = 0; k < VK; k++) wv[(size_t)j * ws->VKp + k] = __float2bfloat16(net.vfc1_w[(size_t)j * VK + k]);
+    if ((st = up(e, &U->wp16, wp))) return st;
+    if ((st = up(e, &U->wv16, wv))) return st;
+    if ((st = make_map(e, &U->map_wp, U->wp16, A, ws->PKp, 64, 64))) return st;
+    if ((st = make_map(e, &U->map_wv, U->wv16, 64, ws->VKp, 64, 64))) return st;
+  }
   if ((st = up(e, &W->pfc_b, net.pfc_b))) return st;
-  if ((st = up(e, &W->vfc1_t, vt))) return st;
   if ((st = up(e, &W->vfc1_b, net.vfc1_b))) return st;
   if ((st = up(e, &W->vfc2_w, net.vfc2_w))) return st;
   if ((st = up(e, &W->vfc2_b, net.vfc2_b))) return st;
@@ -752,23 +869,29 @@ static int run_trunk(azp_engine* e, NetWeights* W, const int32_t* count_dev, int
   const int grid = max_tiles < ws->sms ? max_tiles : ws->sms;
   ConvArgs a2;
   a2.g = g; a2.bias = U->b2; a2.out = ws->act2; a2.head_b = nullptr; a2.feat = nullptr; a2.NJ = 0;
+  a2.PC = 0; a2.PKp = 0; a2.FK = 0;
   a2.count_dev = count_dev; a2.count_host = count_host; a2.back = back; a2.stage_rows = TILE_M + 2 * g.P;
   conv_umma_kernel<32, 64, STAGES2, false><<<grid, CONV_THREADS, ws->smem2, s>>>(ws->map_act1, U->map_w2, U->map_w2, a2);
   azp_count_launch();
   ConvArgs a3 = a2;
   a3.bias = U->b3; a3.out = nullptr; a3.head_b = U->head_b8; a3.feat = ws->feat;
-  a3.NJ = W->PC + W->VC;
+  a3.NJ = W->PC + W->VC; a3.PC = W->PC; a3.PKp = ws->PKp; a3.FK = ws->FK;
   e->prof_flops_per_board = 2.0 * 9.0 * 64 * 128 * g.A;
   azp_prof_begin(e, count_dev, count_host, s);
   conv_umma_kernel<64, 128, STAGES3, true><<<grid, CONV_THREADS, ws->smem3, s>>>(ws->map_act2, U->map_w3, U->map_hw, a3);
   azp_count_launch();
   azp_prof_end(e, s);
-  const int NJ = W->PC + W->VC;
-  const size_t smem = (size_t)(8 * NJ * g.A + 8 * g.A + 8 * 64) * sizeof(float);
-  const int fc_grid = (zmax + 7) / 8;
-  heads_fc_kernel<8><<<fc_grid, 256, smem, s>>>(ws->feat, g.A, W->PC, W->VC, W->pfc_t, W->pfc_b, W->vfc1_t,
-                                                W->vfc1_b, W->vfc2_w, W->vfc2_b, logits, policy, value, count_dev,
-                                                count_host, back, g.G, out_by_index);
+  FcArgs fa;
+  const int n_total = (g.A + 15) / 16 * 16;
+  fa.job[0].n_total = n_total; fa.job[0].n_first = n_total <= 256 ? n_total : 192; fa.job[0].n_valid = g.A;
+  fa.job[0].k_chunks = (ws->PKp + 63) / 64; fa.job[0].k_off = 0; fa.job[0].bias = W->pfc_b;
+  fa.job[1].n_total = 64; fa.job[1].n_first = 64; fa.job[1].n_valid = 64;
+  fa.job[1].k_chunks = (ws->VKp + 63) / 64; fa.job[1].k_off = ws->PKp; fa.job[1].bias = W->vfc1_b;
+  fa.A = g.A; fa.G = g.G; fa.stages = ws->fc_stages; fa.b_rows = ws->fc_b_rows;
+  fa.vfc2_w = W->vfc2_w; fa.vfc2_b = W->vfc2_b; fa.logits = logits; fa.policy = policy; fa.value = value;
+  fa.count_dev = count_dev; fa.count_host = count_host; fa.back = back; fa.out_by_index = out_by_index;
+  dim3 fc_grid((zmax + TILE_M - 1) / TILE_M, 2);
+  fc_umma_kernel<<<fc_grid, 192, ws->fc_smem, s>>>(ws->map_feat, U->map_wp, U->map_wv, fa);
   azp_count_launch();
   return azp_check_launch();
 }
@@ -784,7 +907,7 @@ int azp_umma_eval_leaves(azp_engine* e, NetWeights* W, const int32_t* count_dev,
   AZP_DISPATCH_NW(e->NW, conv1_bits_kernel, grid, 256, 0, s, g, e->tv.leaf_x, e->tv.leaf_o, e->tv.leaf_tm,
                   e->tv.leaf_last, U->w1_bits, U->b1, ws->act1, count_dev, count_host, back);
   azp_count_launch();
-  return run_trunk(e, W, count_dev, count_host, back, e->d_logits, e->d_policy, e->d_value, 0, s);
+  return run_trunk(e, W, count_dev, count_host, back, nullptr, e->d_policy, e->d_value, 0, s);
 }
 
 // diagnostics: intermediate activations of the last evaluation as dense float32
@@ -794,6 +917,12 @@ __global__ void unpad_act_kernel(ConvGeom g, int n, int C, const __nv_bfloat16* 
   int c = i % C; size_t t = i / C; int a = t % g.A; int slot = t / g.A;
   size_t row = (size_t)slot * g.stride + (size_t)(a / g.B + 1) * g.P + (a % g.B + 1);
   out[i] = __bfloat162float(act[row * C + c]);
+}
+__global__ void unpack_feat_kernel(int A, int n, int PKp, int FK, const __nv_bfloat16* __restrict__ feat, float* __restrict__ out) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (size_t)n * 6 * A) return;
+  int pix = i % A, j = (i / A) % 6; size_t slot = i / (6 * (size_t)A);
+  out[i] = __bfloat162float(feat[slot * FK + (j < 4 ? j * A : PKp + (j - 4) * A) + pix]);
 }
 int azp_umma_debug(azp_engine* e, int layer, int n, float* out, cudaStream_t s) {
   UmmaWorkspace* ws = (UmmaWorkspace*)e->ws->umma;
@@ -806,8 +935,10 @@ int azp_umma_debug(azp_engine* e, int layer, int n, float* out, cudaStream_t s) 
     return azp_check_launch();
   }
   if (layer == 3) {
-    AZP_CUDA(e, cudaMemcpyAsync(out, ws->feat, (size_t)n * 6 * g.A * sizeof(float), cudaMemcpyDeviceToDevice, s));
-    return AZP_OK;
+    size_t total = (size_t)n * 6 * g.A;
+    unpack_feat_kernel<<<(int)((total + 255) / 256), 256, 0, s>>>(g.A, n, ws->PKp, ws->FK, ws->feat, out);
+    azp_count_launch();
+    return azp_check_launch();
   }
   return AZP_ERR_INVALID_ARG;
 }

@@ -145,12 +145,25 @@ __global__ void select_kernel(RulesParams rp, TreeView tv, int n, double c_puct,
     int stones = 0;
 #pragma unroll
     for (int k = 0; k < NW; k++) stones += __popcll(x.w[k] | o.w[k]);
-    for (int a = lane; a < A; a += 32) {
-      bool occupied = bb_test<NW>(x, a) || bb_test<NW>(o, a);
+    // all of a node's edge statistics are fetched before any arithmetic: one memory round trip per level
+    constexpr int MAXI = (AZP_MAX_BOARD * AZP_MAX_BOARD + 31) / 32;
+    int nn_[MAXI], ch_[MAXI];
+    double ww_[MAXI];
+    float pp_[MAXI];
+#pragma unroll
+    for (int i = 0; i < MAXI; i++) {
+      const int a = lane + 32 * i;
+      nn_[i] = 0; ww_[i] = 0.0; pp_[i] = 0.f; ch_[i] = -1;
+      if (a < A) { nn_[i] = tv.N[nb + a]; ww_[i] = tv.W[nb + a]; pp_[i] = tv.P[nb + a]; ch_[i] = tv.child[nb + a]; }
+    }
+#pragma unroll
+    for (int i = 0; i < MAXI; i++) {
+      const int a = lane + 32 * i;
+      const bool occupied = a >= A || bb_test<NW>(x, a) || bb_test<NW>(o, a);
       if (occupied) continue;
-      int nn = tv.N[nb + a];
-      double q = nn ? __ddiv_rn(tv.W[nb + a], (double)nn) : 0.0;
-      double u = __ddiv_rn(__dmul_rn(__dmul_rn(c_puct, (double)tv.P[nb + a]), sq), (double)(1 + nn));
+      const int nn = nn_[i];
+      double q = nn ? __ddiv_rn(ww_[i], (double)nn) : 0.0;
+      double u = __ddiv_rn(__dmul_rn(__dmul_rn(c_puct, (double)pp_[i]), sq), (double)(1 + nn));
       double s = __dadd_rn(q, u);
       if (s > best) { best = s; besta = a; }    // ascending a: the FIRST maximum is kept
     }
@@ -167,7 +180,12 @@ __global__ void select_kernel(RulesParams rp, TreeView tv, int n, double c_puct,
       kind = 2;
       break;
     }
-    const int cn = tv.N[nb + a], ch = tv.child[nb + a];
+    // the winning edge's N / child pointer are already in the owning lane's registers
+    int cn = 0, ch = -1;
+#pragma unroll
+    for (int i = 0; i < MAXI; i++) if (i == (a >> 5)) { cn = nn_[i]; ch = ch_[i]; }
+    cn = __shfl_sync(AZP_FULL, cn, a & 31);
+    ch = __shfl_sync(AZP_FULL, ch, a & 31);
     if (depth >= tv.maxd) {
       if (lane == 0) atomicExch(tv.error_flag, AZP_ERR_CAPACITY);
       kind = 2;
