@@ -19,6 +19,7 @@
 //   fc_umma_kernel      features -> logits/softmax/value  tcgen05 GEMMs (policy_fc, value_fc1), thread-per-row tails
 #include "azp_net.cuh"
 #include <cuda.h>
+#include <stdlib.h>
 
 namespace {
 
@@ -291,7 +292,7 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_umma_kernel(const __grid
   constexpr uint32_t TMEM_COLS = NEED <= 32 ? 32 : (NEED <= 64 ? 64 : (NEED <= 128 ? 128 : (NEED <= 256 ? 256 : 512)));
   constexpr int HALF = COUT / 2;                            // channels per epilogue warp
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // 1024-B aligned, still a shared pointer
   const int stage_bytes = args.stage_rows * ROWB;          // multiple of 1024 (P multiple of 8)
   uint8_t* s_w = smem;                                      // 9 taps x [COUT][CIN]
   uint8_t* s_a = s_w + S::W_BYTES;                          // STAGES x [stage_rows][CIN]
@@ -517,26 +518,29 @@ struct FcArgs {
   const int32_t* count_dev; int count_host; int back; int out_by_index;
 };
 
-__global__ void __launch_bounds__(192, 1) fc_umma_kernel(const __grid_constant__ CUtensorMap map_feat,
-                                                         const __grid_constant__ CUtensorMap map_wp,
-                                                         const __grid_constant__ CUtensorMap map_wv,
-                                                         const FcArgs args) {
+constexpr int FC_EPI_WARPS = 16;                       // 4 per TMEM lane quarter, 64 accumulator columns each
+constexpr int FC_THREADS = 64 + 32 * FC_EPI_WARPS;
+
+__global__ void __launch_bounds__(FC_THREADS, 1) fc_umma_kernel(const __grid_constant__ CUtensorMap map_feat,
+                                                                const __grid_constant__ CUtensorMap map_wp,
+                                                                const __grid_constant__ CUtensorMap map_wv,
+                                                                const FcArgs args) {
   const int count = args.count_dev ? *args.count_dev : args.count_host;
   const int tile = blockIdx.x;
   if (tile * TILE_M >= count) return;
   const FcJob job = args.job[blockIdx.y];
   const CUtensorMap* map_w = blockIdx.y == 0 ? &map_wp : &map_wv;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   const int stage_bytes = TILE_M * 128 + args.b_rows * 128;
   uint8_t* s_tail = smem + (size_t)args.stages * stage_bytes;
   uint64_t* full = reinterpret_cast<uint64_t*>(s_tail);
   uint64_t* empty = full + 8;
   uint64_t* tfull = empty + 8;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tfull + 1);
-  float* s_bias = reinterpret_cast<float*>(tmem_slot + 2);          // [n_total]
-  float* s_w2 = s_bias + 512;                                       // [64] + [1]
-  float* s_inv = s_w2 + 72;                                         // [128] per-row 1/sum
+  float* s_bias = reinterpret_cast<float*>(tmem_slot + 2);          // [512]
+  float* s_w2 = s_bias + 512;                                       // [64] + [1] (+pad)
+  float* s_part = s_w2 + 72;                                        // [4][128] per-row partial max / sum, [128] 1/sum
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int row0 = (args.back ? args.G - count : 0) + tile * TILE_M;
 
@@ -545,7 +549,7 @@ __global__ void __launch_bounds__(192, 1) fc_umma_kernel(const __grid_constant__
     mbar_init(tfull, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  for (int i = threadIdx.x; i < job.n_total; i += blockDim.x) s_bias[i] = i < job.n_valid ? job.bias[i] : 0.f;
+  for (int i = threadIdx.x; i < 512; i += blockDim.x) s_bias[i] = i < job.n_valid ? job.bias[i] : 0.f;
   if (threadIdx.x < 65) s_w2[threadIdx.x] = threadIdx.x < 64 ? args.vfc2_w[threadIdx.x] : args.vfc2_b[0];
   if (warp == 1) tmem_alloc(tmem_slot, 512);
   tc_fence_before();
@@ -590,61 +594,79 @@ __global__ void __launch_bounds__(192, 1) fc_umma_kernel(const __grid_constant__
       umma_commit(tfull);
     }
   } else {
-    const int q = warp & 3;
+    // ===== epilogue: warp (q, p) owns rows 32q..32q+31 and accumulator columns 64p..64p+63 =====
+    const int q = warp & 3, p = (warp - 2) >> 2;
+    const int ew = warp - 2;                                   // 0..15
     mbar_wait(tfull, 0);
     tc_fence_after();
-    const int bi = tile * TILE_M + q * 32 + lane;              // index within the evaluated batch
+    const int trow = q * 32 + lane;
+    const int bi = tile * TILE_M + trow;                       // index within the evaluated batch
     const bool valid = bi < count;
     const int row = args.back ? args.G - count + bi : bi;
     const int orow = args.out_by_index ? bi : row;
-    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
+    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(p * 64);
     if (blockIdx.y == 0) {
       const int A = args.A;
       float m = -INFINITY;
-      for (int c0 = 0; c0 < job.n_total; c0 += 32) {           // pass 1: logits out, row max
-        uint32_t r[32];
-        tmem_ld32(taddr + c0, r);
+      // column blocks of 64: this warp takes blocks p, p+4 (the second only exists for boards > 16x16)
+      for (int c_begin = p * 64; c_begin < job.n_total; c_begin += 256) {      // pass 1: row maximum (+ raw logits)
 #pragma unroll
-        for (int i = 0; i < 32; i++) {
-          if (c0 + i < A) {
-            const float l = __uint_as_float(r[i]) + s_bias[c0 + i];
-            m = fmaxf(m, l);
-            if (valid && args.logits) args.logits[(size_t)orow * A + c0 + i] = l;
+        for (int h = 0; h < 2; h++) {
+          uint32_t r[32];
+          tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c_begin + h * 32), r);
+#pragma unroll
+          for (int i = 0; i < 32; i++) {
+            const int c = c_begin + h * 32 + i;
+            const float l = __uint_as_float(r[i]) + s_bias[c];
+            if (c < A) {
+              m = fmaxf(m, l);
+              if (valid && args.logits) args.logits[(size_t)orow * A + c] = l;
+            }
           }
         }
       }
-      // pass 2: exp(l - max) staged (unnormalised) through the now idle pipeline buffers; the row sum is
-      // applied during the copy-out, so the tile leaves the SM as one contiguous, coalesced block
+      s_part[p * 128 + trow] = m;
+      asm volatile("bar.sync 1, 512;" ::: "memory");
+      m = fmaxf(fmaxf(s_part[trow], s_part[128 + trow]), fmaxf(s_part[256 + trow], s_part[384 + trow]));
+      asm volatile("bar.sync 1, 512;" ::: "memory");           // everyone has read the maxima
+      // pass 2: exp(l - max) staged unnormalised in the (now idle) pipeline buffers; TMEM is re-read, which
+      // is cheaper than keeping 64 values per thread in registers
       float* stage = reinterpret_cast<float*>(smem);
       const int pitch = A | 1;                                 // odd pitch: conflict-free row-per-thread writes
-      float* srow = stage + (size_t)(q * 32 + lane) * pitch;
       float z = 0.f;
-      for (int c0 = 0; c0 < job.n_total; c0 += 32) {
-        uint32_t r[32];
-        tmem_ld32(taddr + c0, r);
+      for (int c_begin = p * 64; c_begin < job.n_total; c_begin += 256) {
+        float* srow = stage + (size_t)trow * pitch;
 #pragma unroll
-        for (int i = 0; i < 32; i++) {
-          if (c0 + i < A) {
-            const float ex = __expf(__uint_as_float(r[i]) + s_bias[c0 + i] - m);
-            z += ex;
-            srow[c0 + i] = ex;
+        for (int h = 0; h < 2; h++) {
+          uint32_t r[32];
+          tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c_begin + h * 32), r);
+#pragma unroll
+          for (int i = 0; i < 32; i++) {
+            const int c = c_begin + h * 32 + i;
+            if (c < A) {
+              const float ex = __expf(__uint_as_float(r[i]) + s_bias[c] - m);
+              z += ex;
+              srow[c] = ex;
+            }
           }
         }
       }
-      s_inv[q * 32 + lane] = 1.f / z;                          // softmax over ALL cells (controller.py:49)
-      asm volatile("bar.sync 1, 128;" ::: "memory");           // the four epilogue warps only
-      if (args.policy) {
+      s_part[p * 128 + trow] = z;
+      asm volatile("bar.sync 1, 512;" ::: "memory");
+      if (p == 0)                                              // softmax over ALL cells (controller.py:49)
+        s_part[512 + trow] = 1.f / ((s_part[trow] + s_part[128 + trow]) + (s_part[256 + trow] + s_part[384 + trow]));
+      asm volatile("bar.sync 1, 512;" ::: "memory");
+      if (args.policy) {                                       // coalesced copy-out, 8 rows per warp
         const int nrows = min(TILE_M, count - tile * TILE_M);
         const int orow0 = args.out_by_index ? tile * TILE_M : (args.back ? args.G - count + tile * TILE_M : tile * TILE_M);
         float* out = args.policy + (size_t)orow0 * A;
-        const int et = threadIdx.x - 64;                       // 0..127
-        for (int rr = 0; rr < nrows; rr++) {
-          const float inv = s_inv[rr];
+        for (int rr = ew; rr < nrows; rr += FC_EPI_WARPS) {
           const float* src = stage + (size_t)rr * pitch;
-          for (int a = et; a < A; a += 128) out[(size_t)rr * A + a] = src[a] * inv;
+          const float inv = s_part[512 + rr];
+          for (int a = lane; a < A; a += 32) out[(size_t)rr * A + a] = src[a] * inv;
         }
       }
-    } else {
+    } else if (p == 0) {
       float s = s_w2[64];
 #pragma unroll
       for (int c0 = 0; c0 < 64; c0 += 32) {
@@ -755,7 +777,7 @@ int azp_umma_create(azp_engine* e) {
     ws->fc_b_rows = (n_total + 63) / 64 * 64;
     const int stage = TILE_M * 128 + ws->fc_b_rows * 128;
     ws->fc_stages = (200 * 1024) / stage; if (ws->fc_stages > 6) ws->fc_stages = 6;
-    ws->fc_smem = 1024 + ws->fc_stages * stage + 17 * 8 + 16 + (512 + 72 + 128) * 4 + 64;
+    ws->fc_smem = 1024 + ws->fc_stages * stage + 17 * 8 + 16 + (512 + 72 + 640) * 4 + 64;
     if (n_total > 448 || ws->fc_stages < 2) { e->set_error("board too large for the FC head kernel"); return AZP_ERR_UNSUPPORTED; }
   }
   AZP_CUDA(e, cudaMemset(ws->act1, 0, ws->rows * 32 * sizeof(__nv_bfloat16)));
@@ -891,7 +913,7 @@ static int run_trunk(azp_engine* e, NetWeights* W, const int32_t* count_dev, int
   fa.vfc2_w = W->vfc2_w; fa.vfc2_b = W->vfc2_b; fa.logits = logits; fa.policy = policy; fa.value = value;
   fa.count_dev = count_dev; fa.count_host = count_host; fa.back = back; fa.out_by_index = out_by_index;
   dim3 fc_grid((zmax + TILE_M - 1) / TILE_M, 2);
-  fc_umma_kernel<<<fc_grid, 192, ws->fc_smem, s>>>(ws->map_feat, U->map_wp, U->map_wv, fa);
+  fc_umma_kernel<<<fc_grid, FC_THREADS, ws->fc_smem, s>>>(ws->map_feat, U->map_wp, U->map_wv, fa);
   azp_count_launch();
   return azp_check_launch();
 }

@@ -29,6 +29,7 @@ sys.path.insert(0, ROOT)
 BOARD, WIN, SIMS, GAMES_PER_GPU, C_PUCT = 15, 5, 800, 2048, 2.0
 METRIC = "mcts_simulations_per_sec"
 UNIT = "sims/s"
+MEAN_GAME_PLIES = 57.3             # measured at this config: profiles/r1_game_length_probe.txt
 FLOPS_PER_LEAF = 42.799e6          # 2*MAC of GomokuNet(15) per position
 
 
@@ -161,19 +162,69 @@ def run_engine_arm(args):
     net = az.GomokuNet(BOARD)
     blob_host = torch.from_numpy(az.flatten_state_dict(net.state_dict())).pin_memory()
 
-    eng = az.Engine(board=BOARD, win_length=WIN, games=games, sims=args.sims, c_puct=C_PUCT, net_dtype=dtype,
-                    augment=az.AUGMENT_D4, seed=0, rank=rank, world=world, device=local)
-    eng.load_blob(blob_host.numpy())
-    total_games = 1 << 40                    # endless stream of games: finished slots are re-seated
-    cap = eng.example_capacity_floor() * 2
-    out = (torch.empty((cap, 4, BOARD, BOARD), device="cuda"), torch.empty((cap, BOARD, BOARD), device="cuda"),
-           torch.empty((cap,), dtype=torch.int32, device="cuda"))
+    import threading
+    E = max(1, args.engines)
+    assert games % E == 0
+    # E engines per GPU = E independent groups of games/E concurrent games, each driven by its own host
+    # thread on its own CUDA stream, so one group's latency-bound tree kernels overlap the other's convs
+    engines, streams, outs = [], [], []
+    for k in range(E):
+        eng = az.Engine(board=BOARD, win_length=WIN, games=games // E, sims=args.sims, c_puct=C_PUCT, net_dtype=dtype,
+                        augment=az.AUGMENT_D4, seed=0, rank=rank * E + k, world=world * E, device=local)
+        eng.load_blob(blob_host.numpy())
+        engines.append(eng)
+        streams.append(torch.cuda.Stream())
+        cap = eng.example_capacity_floor() * 2
+        outs.append((torch.empty((cap, 4, BOARD, BOARD), device="cuda"), torch.empty((cap, BOARD, BOARD), device="cuda"),
+                     torch.empty((cap,), dtype=torch.int32, device="cuda")))
+    cap = outs[0][0].shape[0]
     host_out = (torch.empty((cap, 4, BOARD, BOARD)).pin_memory(), torch.empty((cap, BOARD, BOARD)).pin_memory(),
                 torch.empty((cap,), dtype=torch.int32).pin_memory())
+    total_games = 1 << 40                    # endless stream of games: finished slots are re-seated
+    first_flag = [True] * E
 
-    def move_step(first):
-        st, _, _, _, written = eng.selfplay(total_games, first_game=0, out=out, resume=not first, max_move_steps=1)
-        return written
+    def move_steps(k, n, start_event, done_events, e2e, d2h_acc):
+        """n move steps of engine k on its stream (runs in its own host thread)."""
+        torch.cuda.set_device(local)
+        with torch.cuda.stream(streams[k]):
+            if start_event is not None:
+                streams[k].wait_event(start_event)
+            for _ in range(n):
+                if e2e:
+                    engines[k].load_blob(blob_host.numpy())            # weights: host -> device, every step
+                st, _, _, _, w = engines[k].selfplay(total_games, first_game=0, out=outs[k],
+                                                     resume=not first_flag[k], max_move_steps=1)
+                first_flag[k] = False
+                if e2e and w:                                          # examples: device -> pinned host
+                    for src, dst in zip(outs[k], host_out):
+                        dst[:w].copy_(src[:w], non_blocking=True)
+                    d2h_acc[k] += w * (5 * BOARD * BOARD + 1) * 4
+            done_events[k].record(streams[k])
+
+    def run_all(n, e2e=False):
+        """All engines advance n move steps concurrently; returns device milliseconds (start -> all done)."""
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        done = [torch.cuda.Event() for _ in range(E)]
+        d2h_acc = [0] * E
+        ev0.record()
+        threads = [threading.Thread(target=move_steps, args=(k, n, ev0, done, e2e, d2h_acc)) for k in range(E)]
+        for t in threads:
+            t.start()
+        for t in threads:
+            t.join()
+        for d in done:
+            torch.cuda.current_stream().wait_event(d)
+        ev1.record()
+        torch.cuda.synchronize()
+        return ev0.elapsed_time(ev1), sum(d2h_acc)
+
+    def counters():
+        tot = {}
+        for eng in engines:
+            for key, v in eng.counters().items():
+                tot[key] = tot.get(key, 0) + v
+        tot["kernel_launches"] = engines[0].counters()["kernel_launches"]      # process-wide counter
+        return tot
 
     def barrier():
         if world > 1:
@@ -181,29 +232,25 @@ def run_engine_arm(args):
         torch.cuda.synchronize()
 
     # ---- warm-up (also fast-forwards games so the timed region sees mid-game positions) ----------
-    first = True
-    for _ in range(max(args.warmup, 3)):
-        move_step(first)
-        first = False
+    run_all(max(args.warmup, 3))
 
     # ---- kernel-only arm: inputs resident in HBM --------------------------------------------------
-    eng.set_profiling(True)
-    c0 = eng.counters()
+    for eng in engines:
+        eng.set_profiling(True)
+    c0 = counters()
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
     barrier()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    ev0.record()
-    for _ in range(args.steps):
-        move_step(False)
-    ev1.record()
+    ms, _ = run_all(args.steps)
     barrier()
     clocks = sampler.stop() if rank == 0 else None
-    ms = ev0.elapsed_time(ev1)
-    c1 = eng.counters()
-    kms, klaunches, kflops = eng.get_profile()
-    eng.set_profiling(False)
+    c1 = counters()
+    kms = klaunches = kflops = 0
+    for eng in engines:
+        a, b, c = eng.get_profile()
+        kms += a; klaunches += b; kflops += c
+        eng.set_profiling(False)
     sims_done = c1["simulations"] - c0["simulations"]
     games_done = c1["games_finished"] - c0["games_finished"]
     plies_done = c1["plies"] - c0["plies"]
@@ -212,22 +259,10 @@ def run_engine_arm(args):
 
     # ---- end-to-end arm: the same move steps through the public call with HOST buffers -----------
     barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    ce0 = eng.counters()
-    d2h = 0
-    e0.record()
-    for _ in range(args.steps):
-        eng.load_blob(blob_host.numpy())                       # weights: host -> device, every step
-        w = move_step(False)
-        if w:                                                  # examples: device -> pinned host
-            for src, dst in zip(out, host_out):
-                dst[:w].copy_(src[:w], non_blocking=True)
-            d2h += w * (5 * BOARD * BOARD + 1) * 4
-        c_now = eng.counters()                                 # the step's result counters (sync + D2H)
-    e1.record()
+    ce0 = counters()
+    e2e_ms, d2h = run_all(args.steps, e2e=True)
     barrier()
-    e2e_ms = e0.elapsed_time(e1)
-    ce1 = eng.counters()
+    ce1 = counters()
     e2e_sims = ce1["simulations"] - ce0["simulations"]
 
     # ---- reduce over ranks: totals summed, time = max ----------------------------------------------
@@ -262,8 +297,11 @@ def run_engine_arm(args):
             "step": "one move step = every game searches and plays one move",
             "l2": "inputs larger than L2: node table working set is GBs per GPU (no flush needed)",
             "games_per_gpu": games, "sims_per_move": args.sims, "c_puct": C_PUCT, "augment": "d4",
+            "engines_per_gpu": E,
         },
         "games_per_sec": games_done / (ms / 1e3),
+        "games_per_sec_steady_state": (plies_done / (ms / 1e3)) / MEAN_GAME_PLIES,
+        "mean_game_plies": MEAN_GAME_PLIES,
         "plies_per_sec": plies_done / (ms / 1e3),
         "leaf_evals_per_sec": evals_done / (ms / 1e3),
         "clocks": clocks,
@@ -276,7 +314,7 @@ def run_engine_arm(args):
             "frac": achieved_tflops / peak_tf if peak_tf else None, "traffic": None,
             "peak_source": f"{peaks['source']} sustained bf16 (kernel timed inside a long step)",
             "kernel_ms_per_launch": kms / klaunches if klaunches else None, "kernel_launches": klaunches,
-            "kernel_share_of_step": kms / ms if ms else None,
+            "kernel_share_of_step": kms / ms / max(1, E) if ms else None,
             "net_tensor_frac_end_to_end": (evals_done / (ms / 1e3)) * FLOPS_PER_LEAF / 1e12 / world / peak_tf,
         },
         "cpu_baseline": cpu,
@@ -294,6 +332,8 @@ def main():
     ap.add_argument("--impl", default="engine", choices=["engine", "reference"])
     ap.add_argument("--dtype", default=os.environ.get("AZP_BENCH_DTYPE", "bf16"), choices=["bf16", "f32"])
     ap.add_argument("--games", type=int, default=GAMES_PER_GPU)
+    ap.add_argument("--engines", type=int, default=int(os.environ.get("AZP_BENCH_ENGINES", "1")),
+                    help="engines per GPU, each with games/engines slots on its own CUDA stream (host thread each)")
     ap.add_argument("--sims", type=int, default=SIMS)
     ap.add_argument("--cpu-budget", type=float, default=15.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
