@@ -203,14 +203,26 @@ __global__ void __launch_bounds__(256) conv1_planes_kernel(ConvGeom g, int n, co
       float acc[32];
 #pragma unroll
       for (int j = 0; j < 32; j++) acc[j] = sb[j];
-      for (int tap = 0; tap < 9; tap++) {
-        const int rr = r + tap / 3 - 1, cc = c + tap % 3 - 1;
-        if (rr < 0 || rr >= g.B || cc < 0 || cc >= g.B) continue;
-        for (int pl = 0; pl < 4; pl++) {
-          const float v = sp[pl * g.A + rr * g.B + cc];
-          const float* wr = sw + (tap * 4 + pl) * 32;
+      // same association order as the table-driven producer of the fused kernel: for every (plane, kernel
+      // row) the three column taps are summed first, then added to the accumulator -- bit-identical to it
+      // on 0/1 planes
+      for (int pl = 0; pl < 4; pl++) {
+        for (int ky = 0; ky < 3; ky++) {
+          const int rr = r + ky - 1;
+          if (rr < 0 || rr >= g.B) continue;
+          float part[32];
 #pragma unroll
-          for (int j = 0; j < 32; j++) acc[j] = fmaf(v, wr[j], acc[j]);
+          for (int j = 0; j < 32; j++) part[j] = 0.f;
+          for (int kx = 0; kx < 3; kx++) {
+            const int cc = c + kx - 1;
+            if (cc < 0 || cc >= g.B) continue;
+            const float v = sp[pl * g.A + rr * g.B + cc];
+            const float* wr = sw + ((ky * 3 + kx) * 4 + pl) * 32;
+#pragma unroll
+            for (int j = 0; j < 32; j++) part[j] = fmaf(v, wr[j], part[j]);
+          }
+#pragma unroll
+          for (int j = 0; j < 32; j++) acc[j] += part[j];
         }
       }
       uint32_t packed[16];
@@ -246,6 +258,11 @@ struct ConvArgs {
   int NJ, PC, PKp, FK;
   const int32_t* count_dev; int count_host; int back;
   int stage_rows;                 // 128 + 2P
+  // BITS: the A operand is produced in-kernel from the leaf batch's bitboards (conv1 fused in)
+  const uint64_t* lx; const uint64_t* lo; const uint8_t* ltm; const int16_t* llast; int NW;
+  const float* w1;                // [plane(3)][ky][pattern(8)][32] fp32 partial sums of conv1 weights
+  const float* b1;                // [32]
+  int debug;                      // bring-up switches (AZP_DEBUG_CONV): 1 skip epilogue math, 2 skip conv MMAs, 4 skip A loads
 };
 
 __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&v)[16]) {
@@ -271,14 +288,20 @@ __device__ __forceinline__ void umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, u
 }
 
 constexpr int CONV_THREADS = 320;     // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue (2 per TMEM lane quarter)
+constexpr int CONV_THREADS_BITS = 576; // + warps 10..17: conv1-from-bitboards producers of the A operand
+constexpr int CODES = 256;            // >= 128 + 4P + 2 codes per tile (P <= 24)
 constexpr int HEAD_N = 16;            // fused 1x1 head convs: 6 (or 3) outputs padded to the UMMA minimum N
 
 // HEADS = true additionally fuses both 1x1 head convolutions (net.py:47,51) as a SECOND tensor-core
 // GEMM per tile: the epilogue writes relu(acc + bias) as bf16 straight back into tensor memory, and a
 // TS-mode UMMA (A from TMEM) multiplies it with the [16 x COUT] head weights; the wide activation never
 // leaves the SM and the epilogue warps only touch each accumulator element once.
-template <int CIN, int COUT, int STAGES, bool HEADS>
-__global__ void __launch_bounds__(CONV_THREADS, 1) conv_umma_kernel(const __grid_constant__ CUtensorMap map_act,
+// BITS = true (conv2 only, CIN == 32) fuses conv1: eight producer warps compute relu(conv1) of the leaf
+// batch straight from its bitboards (inputs are 0/1, so <= 27 weight-row adds per position) and write the
+// three dx-shifted, 64B-swizzled A stages into shared memory themselves -- no act1 round trip through
+// HBM/L2 and no TMA loads for the activations.
+template <int CIN, int COUT, int STAGES, bool HEADS, bool BITS>
+__global__ void __launch_bounds__(BITS ? CONV_THREADS_BITS : CONV_THREADS, 1) conv_umma_kernel(const __grid_constant__ CUtensorMap map_act,
                                                                     const __grid_constant__ CUtensorMap map_w,
                                                                     const __grid_constant__ CUtensorMap map_hw,
                                                                     const ConvArgs args) {
@@ -307,6 +330,8 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_umma_kernel(const __grid
   uint64_t* head_full = act_full + 1;                       // [1] MMA -> epilogue: head accumulator ready
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(head_full + 1);
   float* s_bias = reinterpret_cast<float*>(tmem_slot + 2);  // [COUT] (+ [8] head bias)
+  float* s_w1 = s_bias + COUT + 8;                          // BITS: [3 planes][3 ky][8 patterns][32] conv1 tables + [32] bias
+  int16_t* s_cells = reinterpret_cast<int16_t*>(s_w1 + 72 * 32 + 32); // BITS: [2][CODES] column-pattern codes
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const ConvGeom g = args.g;
@@ -317,7 +342,7 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_umma_kernel(const __grid
   const int n_tiles = (int)((rows_total + TILE_M - 1) / TILE_M);
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < STAGES; i++) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+    for (int i = 0; i < STAGES; i++) { mbar_init(&full[i], BITS ? 8 : 1); mbar_init(&empty[i], 1); }
     for (int i = 0; i < 2; i++) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 8); }
     mbar_init(wbar, 1);
     mbar_init(act_full, 8);
@@ -340,16 +365,112 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_umma_kernel(const __grid
       if (HEADS)
         for (int kc = 0; kc < COUT / 64; kc++) tma_load_2d(s_hw + kc * HEAD_N * 128, &map_hw, wbar, kc * 64, 0);
       int it = 0;
-      for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+      for (int t = blockIdx.x; !BITS && t < n_tiles; t += gridDim.x) {
         for (int dxi = 0; dxi < 3; dxi++, it++) {
           const int st = it % STAGES;
           const uint32_t ph = (it / STAGES) & 1;
           mbar_wait(&empty[st], ph ^ 1);
+          if (args.debug & 4) { mbar_arrive(&full[st]); continue; }
           mbar_expect_tx(&full[st], (uint32_t)stage_bytes);
           const long long row = row_begin + (long long)t * TILE_M - g.P + (dxi - 1);
           tma_load_2d(s_a + (size_t)st * stage_bytes, &map_act, &full[st], 0, (int)row);
         }
       }
+    }
+  } else if (BITS && warp >= 10) {
+    // ===== A-operand producers: conv1 (4->32, 3x3) + ReLU from bitboards, written as 3 swizzled stages =====
+    const int pt = threadIdx.x - CONV_THREADS;               // 0..255
+    for (int i = pt; i < 72 * 32 + 32; i += 256) s_w1[i] = i < 72 * 32 ? args.w1[i] : args.b1[i - 72 * 32];
+    int it = 0, tl = 0;
+    for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, tl++, it += 3) {
+      const long long R0 = row_begin + (long long)t * TILE_M;
+      const long long rlo = R0 - g.P - 1;                    // first padded row any of the three stages holds
+      const int rows_needed = args.stage_rows + 2;
+      int16_t* cb = s_cells + (tl & 1) * CODES;
+      // One code per padded position in [rlo - P, rlo + rows_needed + P): per input plane (0 = side to
+      // move's stones, 1 = opponent's, 2 = last move; games.py:86-129) the 3-bit pattern of columns
+      // c-1, c, c+1, plus bit 9 = "interior cell".  Halo positions get 0, so vertical neighbours are simply
+      // the codes at +-P and no bounds checks remain in the convolution below.
+      for (int i = pt; i < rows_needed + 2 * g.P; i += 256) {
+        const long long qrow = rlo - g.P + i;
+        int code = 0;
+        if (qrow >= 0) {
+          const int slot = (int)(qrow / g.stride), pos = (int)(qrow % g.stride);
+          const int y = pos / g.P, x = pos % g.P;
+          if (y >= 1 && x >= 1 && x <= g.B && slot < g.G) {
+            const int c = x - 1, a = (y - 1) * g.B + c;
+            const bool xm = args.ltm[slot] == 1;
+            const uint64_t* own = (xm ? args.lx : args.lo) + (size_t)slot * args.NW;
+            const uint64_t* opp = (xm ? args.lo : args.lx) + (size_t)slot * args.NW;
+            const int last = args.llast[slot];
+            code = 0x200;
+#pragma unroll
+            for (int kx = 0; kx < 3; kx++) {
+              const int cc = c + kx - 1, aa = a + kx - 1;
+              if (cc < 0 || cc >= g.B) continue;
+              const int b0 = (int)((own[aa >> 6] >> (aa & 63)) & 1), b1 = (int)((opp[aa >> 6] >> (aa & 63)) & 1);
+              code |= (b0 << kx) | (b1 << (3 + kx)) | ((aa == last ? 1 : 0) << (6 + kx));
+            }
+          }
+        }
+        cb[i] = (int16_t)code;
+      }
+      asm volatile("bar.sync 2, 256;" ::: "memory");         // codes (and, first time, the conv1 tables) visible
+      for (int dxi = 0; dxi < 3; dxi++) {
+        const int st = (it + dxi) % STAGES;
+        mbar_wait(&empty[st], (((it + dxi) / STAGES) & 1) ^ 1);
+      }
+      for (int idx = pt; idx < rows_needed; idx += 256) {
+        uint32_t packed[16];
+#pragma unroll
+        for (int j = 0; j < 16; j++) packed[j] = 0u;
+        const int16_t* cs = cb + idx;                        // cs[ky * P] = code of the cell one row above/at/below
+        if (cs[g.P] & 0x200) {
+          float acc[32];
+#pragma unroll
+          for (int j = 0; j < 32; j++) acc[j] = s_w1[72 * 32 + j];
+          // conv1 = bias + sum over (plane, kernel row) of a table row indexed by the 3-bit column pattern
+          // The two stone planes are added branch-free (pattern 0 selects an all-zero table row, and
+          // x + 0.0f == x), so all table loads of a position are in flight together; the last-move plane is
+          // non-zero for at most nine positions of a board and keeps its branch.
+          const int c0 = cs[0], c1 = cs[g.P], c2 = cs[2 * g.P];
+#pragma unroll
+          for (int pl = 0; pl < 3; pl++) {
+#pragma unroll
+            for (int ky = 0; ky < 3; ky++) {
+              const int pat = ((ky == 0 ? c0 : (ky == 1 ? c1 : c2)) >> (3 * pl)) & 7;
+              if (pl == 2 && !pat) continue;
+              const float4* tr = reinterpret_cast<const float4*>(s_w1 + ((pl * 3 + ky) * 8 + pat) * 32);
+#pragma unroll
+              for (int j = 0; j < 8; j++) {
+                const float4 w4 = tr[j];
+                acc[4 * j] += w4.x; acc[4 * j + 1] += w4.y; acc[4 * j + 2] += w4.z; acc[4 * j + 3] += w4.w;
+              }
+            }
+          }
+#pragma unroll
+          for (int j = 0; j < 16; j++) {
+            __nv_bfloat162 hh = __floats2bfloat162_rn(fmaxf(acc[2 * j], 0.f), fmaxf(acc[2 * j + 1], 0.f));
+            packed[j] = *reinterpret_cast<uint32_t*>(&hh);
+          }
+        }
+        // stage dxi holds padded rows starting at R0 - P + (dxi - 1): this row is its row idx - dxi
+#pragma unroll
+        for (int dxi = 0; dxi < 3; dxi++) {
+          const int j = idx - dxi;
+          if (j < 0 || j >= args.stage_rows) continue;
+          uint8_t* rowp = s_a + (size_t)((it + dxi) % STAGES) * stage_bytes + j * 64;
+          const int sw = (j >> 1) & 3;                       // SWIZZLE_64B: 16-byte chunk index ^= address bits [7,8]
+#pragma unroll
+          for (int c = 0; c < 4; c++)
+            *reinterpret_cast<uint4*>(rowp + ((c ^ sw) << 4)) =
+                make_uint4(packed[4 * c], packed[4 * c + 1], packed[4 * c + 2], packed[4 * c + 3]);
+        }
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to UMMA
+      __syncwarp();
+      if (lane == 0)
+        for (int dxi = 0; dxi < 3; dxi++) mbar_arrive(&full[(it + dxi) % STAGES]);
     }
   } else if (warp == 1) {
     // ===== MMA issuer =====
@@ -389,6 +510,7 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_umma_kernel(const __grid
             const uint32_t w_tap = w_base + (uint32_t)((dyi * 3 + dxi) * S::W_TAP_BYTES);
 #pragma unroll
             for (int k = 0; k < KSTEPS; k++) {
+              if (args.debug & 2) break;
               umma_bf16(d_tmem, umma_desc(a_tap + k * 32, ROWB), umma_desc(w_tap + k * 32, ROWB), idesc, accumulate);
               accumulate = 1;
             }
@@ -400,7 +522,7 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_umma_kernel(const __grid
       }
       if (HEADS && tl > 0) issue_head(tl - 1);
     }
-  } else {
+  } else if (warp >= 2 && warp < 10) {
     // ===== epilogue: warp (q, h) owns TMEM lanes 32q..32q+31 (tile rows) and channel half h =====
     const int q = warp & 3;
     const int h = (warp - 2) >> 2;
@@ -439,7 +561,11 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_umma_kernel(const __grid
       const int y = pos / g.P, x = pos % g.P;
       const bool interior = y >= 1 && x >= 1 && x <= g.B && slot < g.G;
       const uint32_t taddr = tmem_base + lane_addr + (uint32_t)(acc * COUT + h * HALF);
-      if (!HEADS) {
+      if (args.debug & 1) {
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) { mbar_arrive(&tempty[acc]); if (HEADS) mbar_arrive(act_full); }
+      } else if (!HEADS) {
         uint4* dst = reinterpret_cast<uint4*>(args.out + (size_t)R * COUT + h * HALF);
         const bool in_range = slot < g.G;
 #pragma unroll
@@ -711,9 +837,12 @@ int make_map(azp_engine* e, CUtensorMap* map, const void* base, uint64_t rows, i
   cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
   CUtensorMapSwizzle sw = box_cols * 2 == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
+  static int promo = -1;
+  if (promo < 0) { const char* v = getenv("AZP_TMA_PROMO"); promo = v ? atoi(v) : 2; }
+  const CUtensorMapL2promotion pr = promo == 0 ? CU_TENSOR_MAP_L2_PROMOTION_NONE
+                                  : promo == 1 ? CU_TENSOR_MAP_L2_PROMOTION_L2_128B : CU_TENSOR_MAP_L2_PROMOTION_L2_256B;
   CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, sw, pr, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) { e->set_error("cuTensorMapEncodeTiled failed: " + std::to_string((int)r)); return AZP_ERR_CUDA; }
   return AZP_OK;
 }
@@ -735,6 +864,7 @@ struct UmmaWeights {
   __nv_bfloat16* w3 = nullptr;        // [9][128][64]
   float* b1 = nullptr; float* b2 = nullptr; float* b3 = nullptr;
   float* w1_bits = nullptr;           // [tap][3][32]
+  float* w1_tab = nullptr;            // [plane(3)][ky][pattern(8)][32]: sum over set pattern bits kx of w1[co][plane][ky][kx]
   float* w1_planes = nullptr;         // [tap][4][32]
   __nv_bfloat16* head_w16 = nullptr;  // [16][128] 1x1 head conv weights (policy rows first, zero padded)
   float* head_b8 = nullptr;           // [8]
@@ -743,13 +873,13 @@ struct UmmaWeights {
   CUtensorMap map_w2, map_w3, map_hw, map_wp, map_wv;
 };
 
-constexpr int STAGES2 = 6, STAGES3 = 3;
+constexpr int STAGES2 = 12, STAGES3 = 3;
 
-template <int CIN, int COUT, int STAGES, bool HEADS>
+template <int CIN, int COUT, int STAGES, bool HEADS, bool BITS>
 int conv_smem_bytes(int stage_rows) {
   using S = ConvSmem<CIN, COUT, STAGES, HEADS>;
   return 1024 + S::W_BYTES + STAGES * stage_rows * S::ROWB + (HEADS ? (COUT / 64) * HEAD_N * 128 : 0) +
-         (2 * STAGES + 7) * 8 + 16 + (COUT + 8) * 4 + 64;
+         (2 * STAGES + 7) * 8 + 16 + (COUT + 8) * 4 + (BITS ? (72 * 32 + 32) * 4 + 2 * CODES * 2 : 0) + 64;
 }
 
 }  // namespace
@@ -788,11 +918,13 @@ int azp_umma_create(azp_engine* e) {
   cudaDeviceProp prop;
   AZP_CUDA(e, cudaGetDeviceProperties(&prop, e->cfg.device));
   ws->sms = prop.multiProcessorCount;
-  ws->smem2 = conv_smem_bytes<32, 64, STAGES2, false>(stage_rows);
-  ws->smem3 = conv_smem_bytes<64, 128, STAGES3, true>(stage_rows);
-  AZP_CUDA(e, cudaFuncSetAttribute(conv_umma_kernel<32, 64, STAGES2, false>,
+  ws->smem2 = conv_smem_bytes<32, 64, STAGES2, false, true>(stage_rows);
+  ws->smem3 = conv_smem_bytes<64, 128, STAGES3, true, false>(stage_rows);
+  AZP_CUDA(e, cudaFuncSetAttribute(conv_umma_kernel<32, 64, STAGES2, false, false>,
                                    cudaFuncAttributeMaxDynamicSharedMemorySize, ws->smem2));
-  AZP_CUDA(e, cudaFuncSetAttribute(conv_umma_kernel<64, 128, STAGES3, true>,
+  AZP_CUDA(e, cudaFuncSetAttribute(conv_umma_kernel<32, 64, STAGES2, false, true>,
+                                   cudaFuncAttributeMaxDynamicSharedMemorySize, ws->smem2));
+  AZP_CUDA(e, cudaFuncSetAttribute(conv_umma_kernel<64, 128, STAGES3, true, false>,
                                    cudaFuncAttributeMaxDynamicSharedMemorySize, ws->smem3));
   AZP_CUDA(e, cudaFuncSetAttribute(fc_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ws->fc_smem));
   return AZP_OK;
@@ -832,6 +964,19 @@ int azp_umma_build(azp_engine* e, const HostNet& net, NetWeights* W) {
         if (ci < 3) w1b[(t * 3 + ci) * 32 + co] = v;
       }
   if ((st = up(e, &U->w1_bits, w1b))) return st;
+  {
+    std::vector<float> tab(72 * 32, 0.f);
+    for (int pl = 0; pl < 3; pl++)
+      for (int ky = 0; ky < 3; ky++)
+        for (int pat = 0; pat < 8; pat++)
+          for (int co = 0; co < 32; co++) {
+            float t = 0.f;                                  // fixed order kx = 0,1,2 (matched by conv1_planes_kernel)
+            for (int kx = 0; kx < 3; kx++)
+              if (pat & (1 << kx)) t += c1.w[((size_t)co * 4 + pl) * 9 + ky * 3 + kx];
+            tab[((pl * 3 + ky) * 8 + pat) * 32 + co] = t;
+          }
+    if ((st = up(e, &U->w1_tab, tab))) return st;
+  }
   if ((st = up(e, &U->w1_planes, w1p))) return st;
   if ((st = up(e, &U->b1, c1.b))) return st;
   // conv2/conv3: bf16 [tap][cout][cin] (K-major rows of one tap = UMMA B operand)
@@ -882,7 +1027,7 @@ int azp_umma_build(azp_engine* e, const HostNet& net, NetWeights* W) {
 
 // conv2 + conv3(+heads) + FC on rows already holding act1
 static int run_trunk(azp_engine* e, NetWeights* W, const int32_t* count_dev, int count_host, int back,
-                     float* logits, float* policy, float* value, int out_by_index, cudaStream_t s) {
+                     float* logits, float* policy, float* value, int out_by_index, bool from_bits, cudaStream_t s) {
   UmmaWorkspace* ws = (UmmaWorkspace*)e->ws->umma;
   UmmaWeights* U = (UmmaWeights*)W->umma;
   const ConvGeom& g = ws->g;
@@ -893,14 +1038,20 @@ static int run_trunk(azp_engine* e, NetWeights* W, const int32_t* count_dev, int
   a2.g = g; a2.bias = U->b2; a2.out = ws->act2; a2.head_b = nullptr; a2.feat = nullptr; a2.NJ = 0;
   a2.PC = 0; a2.PKp = 0; a2.FK = 0;
   a2.count_dev = count_dev; a2.count_host = count_host; a2.back = back; a2.stage_rows = TILE_M + 2 * g.P;
-  conv_umma_kernel<32, 64, STAGES2, false><<<grid, CONV_THREADS, ws->smem2, s>>>(ws->map_act1, U->map_w2, U->map_w2, a2);
+  a2.lx = e->tv.leaf_x; a2.lo = e->tv.leaf_o; a2.ltm = e->tv.leaf_tm; a2.llast = e->tv.leaf_last; a2.NW = e->NW;
+  a2.w1 = U->w1_tab; a2.b1 = U->b1;
+  { static int dbg = -1; if (dbg < 0) { const char* v = getenv("AZP_DEBUG_CONV"); dbg = v ? atoi(v) : 0; } a2.debug = dbg; }
+  if (from_bits)
+    conv_umma_kernel<32, 64, STAGES2, false, true><<<grid, CONV_THREADS_BITS, ws->smem2, s>>>(ws->map_act1, U->map_w2, U->map_w2, a2);
+  else
+    conv_umma_kernel<32, 64, STAGES2, false, false><<<grid, CONV_THREADS, ws->smem2, s>>>(ws->map_act1, U->map_w2, U->map_w2, a2);
   azp_count_launch();
   ConvArgs a3 = a2;
   a3.bias = U->b3; a3.out = nullptr; a3.head_b = U->head_b8; a3.feat = ws->feat;
   a3.NJ = W->PC + W->VC; a3.PC = W->PC; a3.PKp = ws->PKp; a3.FK = ws->FK;
   e->prof_flops_per_board = 2.0 * 9.0 * 64 * 128 * g.A;
   azp_prof_begin(e, count_dev, count_host, s);
-  conv_umma_kernel<64, 128, STAGES3, true><<<grid, CONV_THREADS, ws->smem3, s>>>(ws->map_act2, U->map_w3, U->map_hw, a3);
+  conv_umma_kernel<64, 128, STAGES3, true, false><<<grid, CONV_THREADS, ws->smem3, s>>>(ws->map_act2, U->map_w3, U->map_hw, a3);
   azp_count_launch();
   azp_prof_end(e, s);
   FcArgs fa;
@@ -925,11 +1076,15 @@ int azp_umma_eval_leaves(azp_engine* e, NetWeights* W, const int32_t* count_dev,
   const ConvGeom& g = ws->g;
   const int zmax = count_dev ? g.G : count_host;
   if (zmax <= 0) return AZP_OK;
-  const int grid = zmax < 4 * ws->sms ? zmax : 4 * ws->sms;
-  AZP_DISPATCH_NW(e->NW, conv1_bits_kernel, grid, 256, 0, s, g, e->tv.leaf_x, e->tv.leaf_o, e->tv.leaf_tm,
-                  e->tv.leaf_last, U->w1_bits, U->b1, ws->act1, count_dev, count_host, back);
-  azp_count_launch();
-  return run_trunk(e, W, count_dev, count_host, back, nullptr, e->d_policy, e->d_value, 0, s);
+  static int fuse = -1;
+  if (fuse < 0) { const char* v = getenv("AZP_FUSE_CONV1"); fuse = v ? atoi(v) : 0; }
+  if (!fuse) {
+    const int grid = zmax < 4 * ws->sms ? zmax : 4 * ws->sms;
+    AZP_DISPATCH_NW(e->NW, conv1_bits_kernel, grid, 256, 0, s, g, e->tv.leaf_x, e->tv.leaf_o, e->tv.leaf_tm,
+                    e->tv.leaf_last, U->w1_bits, U->b1, ws->act1, count_dev, count_host, back);
+    azp_count_launch();
+  }
+  return run_trunk(e, W, count_dev, count_host, back, nullptr, e->d_policy, e->d_value, 0, /*from_bits=*/fuse != 0, s);
 }
 
 // diagnostics: intermediate activations of the last evaluation as dense float32
@@ -973,5 +1128,5 @@ int azp_umma_eval_planes(azp_engine* e, NetWeights* W, int n, const float* plane
   const int grid = n < 4 * ws->sms ? n : 4 * ws->sms;
   conv1_planes_kernel<<<grid, 256, 4 * g.A * sizeof(float), s>>>(g, n, planes, U->w1_planes, U->b1, ws->act1);
   azp_count_launch();
-  return run_trunk(e, W, nullptr, n, 0, logits, policy, value, 1, s);
+  return run_trunk(e, W, nullptr, n, 0, logits, policy, value, 1, /*from_bits=*/false, s);
 }
