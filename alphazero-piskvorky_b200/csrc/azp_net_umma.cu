@@ -93,10 +93,12 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
 
 // Shared-memory matrix descriptor, K-major operand with a hardware swizzle whose span is one row
 // (64 B rows -> SWIZZLE_64B, 128 B rows -> SWIZZLE_128B): 8-row atoms, stride between atoms = 8 rows.
-__device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr, uint32_t row_bytes) {
+__device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr, uint32_t row_bytes, int base_mode = 0) {
   const uint64_t layout = row_bytes == 128 ? 2ull : 4ull;        // SWIZZLE_128B : SWIZZLE_64B
   const uint64_t sbo = (8u * row_bytes) >> 4;
-  return (uint64_t)((smem_addr >> 4) & 0x3FFF) | (1ull << 16) | (sbo << 32) | (1ull << 46) | (layout << 61);
+  // "matrix base offset" (bits 49-51): position of the start address inside the repeating swizzle pattern
+  const uint64_t base = base_mode == 2 ? (uint64_t)((smem_addr >> 7) & (row_bytes == 128 ? 7u : 3u)) : 0ull;
+  return (uint64_t)((smem_addr >> 4) & 0x3FFF) | (1ull << 16) | (sbo << 32) | (1ull << 46) | (base << 49) | (layout << 61);
 }
 // instruction descriptor: D=f32, A=B=bf16, both K-major, M=128, N
 __device__ __forceinline__ uint32_t umma_idesc(uint32_t n) {
@@ -263,6 +265,10 @@ struct ConvArgs {
   const float* w1;                // [plane(3)][ky][pattern(8)][32] fp32 partial sums of conv1 weights
   const float* b1;                // [32]
   int debug;                      // bring-up switches (AZP_DEBUG_CONV): 1 skip epilogue math, 2 skip conv MMAs, 4 skip A loads
+  int single;                     // 0: three dx-shifted TMA loads per tile; 1/2: ONE load of 128+2P+2 rows, the nine taps are
+                                  // row-offset descriptors into it (2 = descriptors carry the swizzle base offset)
+  int stage_bytes;                // bytes of one ring stage
+  long long* clk;                 // bring-up: per-tile clock64 stamps of CTA 0 ([tile][16]) or null
 };
 
 __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&v)[16]) {
@@ -287,8 +293,8 @@ __device__ __forceinline__ void umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, u
       ::"r"(tmem_d), "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
 }
 
-constexpr int CONV_THREADS = 320;     // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue (2 per TMEM lane quarter)
-constexpr int CONV_THREADS_BITS = 576; // + warps 10..17: conv1-from-bitboards producers of the A operand
+constexpr int CONV_THREADS = 352;     // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue (2 per TMEM lane quarter), warp 10 head-GEMM issuer
+constexpr int CONV_THREADS_BITS = 608; // + warps 11..18: conv1-from-bitboards producers of the A operand
 constexpr int CODES = 256;            // >= 128 + 4P + 2 codes per tile (P <= 24)
 constexpr int HEAD_N = 16;            // fused 1x1 head convs: 6 (or 3) outputs padded to the UMMA minimum N
 
@@ -309,14 +315,20 @@ __global__ void __launch_bounds__(BITS ? CONV_THREADS_BITS : CONV_THREADS, 1) co
   constexpr int ROWB = S::ROWB;
   constexpr int KSTEPS = CIN / 16;
   constexpr int HW_BYTES = HEADS ? (COUT / 64) * HEAD_N * 128 : 0;     // head weights: K chunks of 64 x 16 rows
-  constexpr uint32_t COL_ACT = 2 * COUT;                    // bf16 copy of the activated tile (COUT/2 columns)
-  constexpr uint32_t COL_HEAD = COL_ACT + COUT / 2;         // head accumulator (HEAD_N columns)
-  constexpr uint32_t NEED = HEADS ? COL_HEAD + HEAD_N : 2 * COUT;
+  // TMEM columns: [0, 2*COUT) two conv accumulators; HEADS adds two bf16 copies of the activated tile
+  // (COUT/2 columns each) and two head accumulators (HEAD_N columns each), all double-buffered so the
+  // epilogue of tile t never waits for the head GEMM of tile t-1
+  constexpr uint32_t COL_ACT = 2 * COUT;
+  constexpr uint32_t COL_HEAD = COL_ACT + COUT;
+  // The head GEMM's K loop is split over HEAD_CHAINS independent accumulators (summed by the epilogue):
+  // back-to-back UMMAs into ONE narrow accumulator serialise on its ~64-cycle dependent-issue latency
+  constexpr int HEAD_CHAINS = 4;
+  constexpr uint32_t NEED = HEADS ? COL_HEAD + 2 * HEAD_CHAINS * HEAD_N : 2 * COUT;
   constexpr uint32_t TMEM_COLS = NEED <= 32 ? 32 : (NEED <= 64 ? 64 : (NEED <= 128 ? 128 : (NEED <= 256 ? 256 : 512)));
   constexpr int HALF = COUT / 2;                            // channels per epilogue warp
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // 1024-B aligned, still a shared pointer
-  const int stage_bytes = args.stage_rows * ROWB;          // multiple of 1024 (P multiple of 8)
+  const int stage_bytes = args.stage_bytes;                 // multiple of the swizzle pattern size
   uint8_t* s_w = smem;                                      // 9 taps x [COUT][CIN]
   uint8_t* s_a = s_w + S::W_BYTES;                          // STAGES x [stage_rows][CIN]
   uint8_t* s_hw = s_a + (size_t)STAGES * stage_bytes;       // HEADS: [COUT/64][16][64] bf16, 128B swizzle
@@ -326,9 +338,9 @@ __global__ void __launch_bounds__(BITS ? CONV_THREADS_BITS : CONV_THREADS, 1) co
   uint64_t* tfull = empty + STAGES;                         // [2]
   uint64_t* tempty = tfull + 2;                             // [2]
   uint64_t* wbar = tempty + 2;                              // [1]
-  uint64_t* act_full = wbar + 1;                            // [1] epilogue -> MMA: bf16 tile is in TMEM
-  uint64_t* head_full = act_full + 1;                       // [1] MMA -> epilogue: head accumulator ready
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(head_full + 1);
+  uint64_t* act_full = wbar + 1;                            // [2] epilogue -> MMA: bf16 tile b is in TMEM
+  uint64_t* head_full = act_full + 2;                       // [2] MMA -> epilogue: head accumulator b ready
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(head_full + 2);
   float* s_bias = reinterpret_cast<float*>(tmem_slot + 2);  // [COUT] (+ [8] head bias)
   float* s_w1 = s_bias + COUT + 8;                          // BITS: [3 planes][3 ky][8 patterns][32] conv1 tables + [32] bias
   int16_t* s_cells = reinterpret_cast<int16_t*>(s_w1 + 72 * 32 + 32); // BITS: [2][CODES] column-pattern codes
@@ -345,8 +357,7 @@ __global__ void __launch_bounds__(BITS ? CONV_THREADS_BITS : CONV_THREADS, 1) co
     for (int i = 0; i < STAGES; i++) { mbar_init(&full[i], BITS ? 8 : 1); mbar_init(&empty[i], 1); }
     for (int i = 0; i < 2; i++) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 8); }
     mbar_init(wbar, 1);
-    mbar_init(act_full, 8);
-    mbar_init(head_full, 1);
+    for (int i = 0; i < 2; i++) { mbar_init(&act_full[i], 8); mbar_init(&head_full[i], 1); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   for (int i = threadIdx.x; i < COUT; i += blockDim.x) s_bias[i] = args.bias[i];
@@ -365,7 +376,20 @@ __global__ void __launch_bounds__(BITS ? CONV_THREADS_BITS : CONV_THREADS, 1) co
       if (HEADS)
         for (int kc = 0; kc < COUT / 64; kc++) tma_load_2d(s_hw + kc * HEAD_N * 128, &map_hw, wbar, kc * 64, 0);
       int it = 0;
-      for (int t = blockIdx.x; !BITS && t < n_tiles; t += gridDim.x) {
+      if (!BITS && args.single) {
+        // one box of 128+2P+2 rows per tile, starting one row above/left of the dy=-1,dx=-1 window
+        const uint32_t bytes = (uint32_t)(args.stage_rows + 2) * ROWB;
+        for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, it++) {
+          const int st = it % STAGES;
+          if (args.clk && blockIdx.x == 0) args.clk[it * 16 + 0] = clock64();
+          mbar_wait(&empty[st], ((it / STAGES) & 1) ^ 1);
+          if (args.clk && blockIdx.x == 0) args.clk[it * 16 + 1] = clock64();
+          mbar_expect_tx(&full[st], bytes);
+          const long long row = row_begin + (long long)t * TILE_M - g.P - 1;
+          tma_load_2d(s_a + (size_t)st * stage_bytes, &map_act, &full[st], 0, (int)row);
+        }
+      }
+      for (int t = blockIdx.x; !BITS && !args.single && t < n_tiles; t += gridDim.x) {
         for (int dxi = 0; dxi < 3; dxi++, it++) {
           const int st = it % STAGES;
           const uint32_t ph = (it / STAGES) & 1;
@@ -377,14 +401,15 @@ __global__ void __launch_bounds__(BITS ? CONV_THREADS_BITS : CONV_THREADS, 1) co
         }
       }
     }
-  } else if (BITS && warp >= 10) {
-    // ===== A-operand producers: conv1 (4->32, 3x3) + ReLU from bitboards, written as 3 swizzled stages =====
+  } else if (BITS && warp >= 11) {
+    // ===== A-operand producers: conv1 (4->32, 3x3) + ReLU from bitboards, written as ONE swizzled stage of
+    //       128+2P+2 rows per tile (the nine taps are row-offset descriptors into it) =====
     const int pt = threadIdx.x - CONV_THREADS;               // 0..255
     for (int i = pt; i < 72 * 32 + 32; i += 256) s_w1[i] = i < 72 * 32 ? args.w1[i] : args.b1[i - 72 * 32];
     int it = 0, tl = 0;
-    for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, tl++, it += 3) {
+    for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, tl++, it++) {
       const long long R0 = row_begin + (long long)t * TILE_M;
-      const long long rlo = R0 - g.P - 1;                    // first padded row any of the three stages holds
+      const long long rlo = R0 - g.P - 1;                    // first padded row of the stage
       const int rows_needed = args.stage_rows + 2;
       int16_t* cb = s_cells + (tl & 1) * CODES;
       // One code per padded position in [rlo - P, rlo + rows_needed + P): per input plane (0 = side to
@@ -416,10 +441,10 @@ __global__ void __launch_bounds__(BITS ? CONV_THREADS_BITS : CONV_THREADS, 1) co
         cb[i] = (int16_t)code;
       }
       asm volatile("bar.sync 2, 256;" ::: "memory");         // codes (and, first time, the conv1 tables) visible
-      for (int dxi = 0; dxi < 3; dxi++) {
-        const int st = (it + dxi) % STAGES;
-        mbar_wait(&empty[st], (((it + dxi) / STAGES) & 1) ^ 1);
-      }
+      const int st = it % STAGES;
+      if (args.clk && blockIdx.x == 0 && pt == 0) args.clk[tl * 16 + 0] = clock64();
+      mbar_wait(&empty[st], ((it / STAGES) & 1) ^ 1);
+      if (args.clk && blockIdx.x == 0 && pt == 0) args.clk[tl * 16 + 1] = clock64();
       for (int idx = pt; idx < rows_needed; idx += 256) {
         uint32_t packed[16];
 #pragma unroll
@@ -454,51 +479,58 @@ __global__ void __launch_bounds__(BITS ? CONV_THREADS_BITS : CONV_THREADS, 1) co
             packed[j] = *reinterpret_cast<uint32_t*>(&hh);
           }
         }
-        // stage dxi holds padded rows starting at R0 - P + (dxi - 1): this row is its row idx - dxi
+        uint8_t* rowp = s_a + (size_t)st * stage_bytes + idx * 64;
+        const int sw = (idx >> 1) & 3;                       // SWIZZLE_64B: 16-byte chunk index ^= address bits [7,8]
 #pragma unroll
-        for (int dxi = 0; dxi < 3; dxi++) {
-          const int j = idx - dxi;
-          if (j < 0 || j >= args.stage_rows) continue;
-          uint8_t* rowp = s_a + (size_t)((it + dxi) % STAGES) * stage_bytes + j * 64;
-          const int sw = (j >> 1) & 3;                       // SWIZZLE_64B: 16-byte chunk index ^= address bits [7,8]
-#pragma unroll
-          for (int c = 0; c < 4; c++)
-            *reinterpret_cast<uint4*>(rowp + ((c ^ sw) << 4)) =
-                make_uint4(packed[4 * c], packed[4 * c + 1], packed[4 * c + 2], packed[4 * c + 3]);
-        }
+        for (int c = 0; c < 4; c++)
+          *reinterpret_cast<uint4*>(rowp + ((c ^ sw) << 4)) =
+              make_uint4(packed[4 * c], packed[4 * c + 1], packed[4 * c + 2], packed[4 * c + 3]);
       }
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to UMMA
       __syncwarp();
-      if (lane == 0)
-        for (int dxi = 0; dxi < 3; dxi++) mbar_arrive(&full[(it + dxi) % STAGES]);
+      if (lane == 0) mbar_arrive(&full[st]);
+      if (args.clk && blockIdx.x == 0 && pt == 0) args.clk[tl * 16 + 6] = clock64();
     }
   } else if (warp == 1) {
     // ===== MMA issuer =====
     if (lane == 0) {
       const uint32_t idesc = umma_idesc(COUT);
-      const uint32_t idesc_head = umma_idesc(HEAD_N);
-      const uint32_t a_base = smem_u32(s_a), w_base = smem_u32(s_w), hw_base = smem_u32(s_hw);
-      // 1x1 head GEMM of local tile j: [128 x COUT] (TMEM, bf16) x [COUT x 16] (smem) -> TMEM cols COL_HEAD..
-      auto issue_head = [&](int j) {
-        mbar_wait(act_full, (uint32_t)(j & 1));
-        tc_fence_after();
-#pragma unroll
-        for (int k = 0; k < COUT / 16; k++)
-          umma_bf16_ts(tmem_base + COL_HEAD, tmem_base + COL_ACT + k * 8,
-                       umma_desc(hw_base + (k / 4) * HEAD_N * 128 + (k % 4) * 32, 128), idesc_head, k > 0 ? 1u : 0u);
-        umma_commit(head_full);
-      };
+      const uint32_t a_base = smem_u32(s_a), w_base = smem_u32(s_w);
       mbar_wait(wbar, 0);
       tc_fence_after();
       int it = 0, tl = 0;
       for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, tl++) {
         const int acc = tl & 1;
         const uint32_t acc_ph = (tl >> 1) & 1;
+        if (args.clk && blockIdx.x == 0) args.clk[tl * 16 + 2] = clock64();
         mbar_wait(&tempty[acc], acc_ph ^ 1);              // epilogue has drained this accumulator
+        if (args.clk && blockIdx.x == 0) args.clk[tl * 16 + 3] = clock64();
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * COUT);
         uint32_t accumulate = 0;
-        for (int dxi = 0; dxi < 3; dxi++, it++) {
+        if (args.single) {
+          const int st = it % STAGES;
+          mbar_wait(&full[st], (it / STAGES) & 1);
+          if (args.clk && blockIdx.x == 0) args.clk[tl * 16 + 4] = clock64();
+          tc_fence_after();
+          const uint32_t a_stage = a_base + (uint32_t)st * (uint32_t)stage_bytes;
+#pragma unroll
+          for (int dxi = 0; dxi < 3; dxi++) {
+#pragma unroll
+            for (int dyi = 0; dyi < 3; dyi++) {
+              const uint32_t a_tap = a_stage + (uint32_t)((dyi * g.P + dxi) * ROWB);   // row offset dy*P + dx
+              const uint32_t w_tap = w_base + (uint32_t)((dyi * 3 + dxi) * S::W_TAP_BYTES);
+#pragma unroll
+              for (int k = 0; k < KSTEPS; k++) {
+                umma_bf16(d_tmem, umma_desc(a_tap + k * 32, ROWB, args.single), umma_desc(w_tap + k * 32, ROWB), idesc, accumulate);
+                accumulate = 1;
+              }
+            }
+          }
+          umma_commit(&empty[st]);
+          it++;
+        }
+        for (int dxi = 0; !args.single && dxi < 3; dxi++, it++) {
           const int st = it % STAGES;
           const uint32_t ph = (it / STAGES) & 1;
           mbar_wait(&full[st], ph);
@@ -518,9 +550,34 @@ __global__ void __launch_bounds__(BITS ? CONV_THREADS_BITS : CONV_THREADS, 1) co
           umma_commit(&empty[st]);                        // stage reusable once these MMAs retire
         }
         umma_commit(&tfull[acc]);                         // accumulator complete
-        if (HEADS && tl > 0) issue_head(tl - 1);          // queued behind this tile's conv MMAs
+        if (args.clk && blockIdx.x == 0) args.clk[tl * 16 + 5] = clock64();
       }
-      if (HEADS && tl > 0) issue_head(tl - 1);
+    }
+  } else if (HEADS && warp == 10) {
+    // ===== head-GEMM issuer: its own thread, so the conv issue loop never waits for the epilogue =====
+    if (lane == 0) {
+      const uint32_t idesc_head = umma_idesc(HEAD_N);
+      const uint32_t hw_base = smem_u32(s_hw);
+      // 1x1 head GEMM of local tile j: [128 x COUT] (TMEM, bf16) x [COUT x 16] (smem) -> TMEM cols COL_HEAD..
+      auto issue_head = [&](int j) {
+        const int b = j & 1;
+        mbar_wait(&act_full[b], (uint32_t)((j >> 1) & 1));
+        tc_fence_after();
+#pragma unroll
+        for (int k = 0; k < COUT / 16; k++)
+          umma_bf16_ts(tmem_base + COL_HEAD + (b * HEAD_CHAINS + (k % HEAD_CHAINS)) * HEAD_N,
+                       tmem_base + COL_ACT + b * (COUT / 2) + k * 8,
+                       umma_desc(hw_base + (k / 4) * HEAD_N * 128 + (k % 4) * 32, 128), idesc_head,
+                       k >= HEAD_CHAINS ? 1u : 0u);
+        umma_commit(&head_full[b]);
+      };
+      mbar_wait(wbar, 0);
+      tc_fence_after();
+      int tl = 0;
+      for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, tl++) {
+        issue_head(tl);
+        if (args.clk && blockIdx.x == 0) args.clk[tl * 16 + 6] = clock64();
+      }
     }
   } else if (warp >= 2 && warp < 10) {
     // ===== epilogue: warp (q, h) owns TMEM lanes 32q..32q+31 (tile rows) and channel half h =====
@@ -528,11 +585,20 @@ __global__ void __launch_bounds__(BITS ? CONV_THREADS_BITS : CONV_THREADS, 1) co
     const int h = (warp - 2) >> 2;
     const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
     // head outputs of local tile j (global tile tj): +bias, ReLU, scatter to feat[slot][j][pixel]
-    auto write_heads = [&](int tj) {
+    auto write_heads = [&](int tj, int j) {
+      mbar_wait(&head_full[j & 1], (uint32_t)((j >> 1) & 1));
+      tc_fence_after();
       uint32_t r[8];
-      tmem_ld8(tmem_base + lane_addr + COL_HEAD, r);
-      const long long R = row_begin + (long long)tj * TILE_M + q * 32 + lane;
-      const int slot = (int)(R / g.stride), pos = (int)(R % g.stride);
+      tmem_ld8(tmem_base + lane_addr + COL_HEAD + (j & 1) * HEAD_CHAINS * HEAD_N, r);
+#pragma unroll
+      for (int c = 1; c < HEAD_CHAINS; c++) {               // sum the partial accumulators of the K split
+        uint32_t r2[8];
+        tmem_ld8(tmem_base + lane_addr + COL_HEAD + ((j & 1) * HEAD_CHAINS + c) * HEAD_N, r2);
+#pragma unroll
+        for (int i = 0; i < 8; i++) r[i] = __float_as_uint(__uint_as_float(r[i]) + __uint_as_float(r2[i]));
+      }
+      const unsigned R = (unsigned)row_begin + (unsigned)tj * TILE_M + q * 32 + lane;
+      const int slot = (int)(R / (unsigned)g.stride), pos = (int)(R % (unsigned)g.stride);
       const int y = pos / g.P, x = pos % g.P;
       if (y >= 1 && x >= 1 && x <= g.B && slot < g.G) {
         __nv_bfloat16* f = args.feat + (size_t)slot * args.FK + (y - 1) * g.B + (x - 1);
@@ -547,24 +613,21 @@ __global__ void __launch_bounds__(BITS ? CONV_THREADS_BITS : CONV_THREADS, 1) co
     for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, tl++) {
       const int acc = tl & 1;
       const uint32_t acc_ph = (tl >> 1) & 1;
+      const bool stamp = args.clk && blockIdx.x == 0 && warp == 2 && lane == 0;
+      if (stamp) args.clk[tl * 16 + 8] = clock64();
       mbar_wait(&tfull[acc], acc_ph);
-      if (HEADS && tl > 0) {
-        // previous tile's head GEMM has retired: its TMEM input may be overwritten, its output read
-        mbar_wait(head_full, (uint32_t)((tl - 1) & 1));
-        tc_fence_after();
-        if (h == 0) write_heads(t_prev);
-      }
+      if (stamp) args.clk[tl * 16 + 9] = clock64();
       tc_fence_after();
-      const long long R = row_begin + (long long)t * TILE_M + q * 32 + lane;     // global padded row
-      const int slot = (int)(R / g.stride);
-      const int pos = (int)(R % g.stride);
+      const unsigned R = (unsigned)row_begin + (unsigned)t * TILE_M + q * 32 + lane;   // global padded row (< 2^31)
+      const int slot = (int)(R / (unsigned)g.stride);
+      const int pos = (int)(R % (unsigned)g.stride);
       const int y = pos / g.P, x = pos % g.P;
       const bool interior = y >= 1 && x >= 1 && x <= g.B && slot < g.G;
       const uint32_t taddr = tmem_base + lane_addr + (uint32_t)(acc * COUT + h * HALF);
       if (args.debug & 1) {
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) { mbar_arrive(&tempty[acc]); if (HEADS) mbar_arrive(act_full); }
+        if (lane == 0) { mbar_arrive(&tempty[acc]); if (HEADS) mbar_arrive(&act_full[tl & 1]); }
       } else if (!HEADS) {
         uint4* dst = reinterpret_cast<uint4*>(args.out + (size_t)R * COUT + h * HALF);
         const bool in_range = slot < g.G;
@@ -586,10 +649,16 @@ __global__ void __launch_bounds__(BITS ? CONV_THREADS_BITS : CONV_THREADS, 1) co
               dst[c0 / 8 + v] = make_uint4(packed[4 * v], packed[4 * v + 1], packed[4 * v + 2], packed[4 * v + 3]);
           }
         }
+        if (stamp) args.clk[tl * 16 + 10] = clock64();
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&tempty[acc]);
+        if (stamp) args.clk[tl * 16 + 11] = clock64();
       } else {
+        if (tl >= 2) {           // head GEMM of tile tl-2 (same TMEM buffers) has retired
+          mbar_wait(&head_full[tl & 1], (uint32_t)(((tl - 2) >> 1) & 1));
+          tc_fence_after();
+        }
 #pragma unroll
         for (int c0 = 0; c0 < HALF; c0 += 32) {
           uint32_t r[32];
@@ -602,20 +671,21 @@ __global__ void __launch_bounds__(BITS ? CONV_THREADS_BITS : CONV_THREADS, 1) co
             __nv_bfloat162 hh = __floats2bfloat162_rn(v0, v1);
             packed[j] = *reinterpret_cast<uint32_t*>(&hh);
           }
-          tmem_st16(tmem_base + lane_addr + COL_ACT + (uint32_t)((h * HALF + c0) / 2), packed);
+          tmem_st16(tmem_base + lane_addr + COL_ACT + (uint32_t)((tl & 1) * (COUT / 2) + (h * HALF + c0) / 2), packed);
         }
+        if (stamp) args.clk[tl * 16 + 10] = clock64();
         asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) { mbar_arrive(&tempty[acc]); mbar_arrive(act_full); }
+        if (lane == 0) { mbar_arrive(&tempty[acc]); mbar_arrive(&act_full[tl & 1]); }
+        if (stamp) args.clk[tl * 16 + 11] = clock64();
+        // the PREVIOUS tile's head GEMM was queued behind this tile's conv MMAs: it has retired by now
+        if (tl > 0 && h == 0) write_heads(t_prev, tl - 1);
+        if (stamp) args.clk[tl * 16 + 12] = clock64();
       }
       t_prev = t;
     }
-    if (HEADS && tl > 0) {
-      mbar_wait(head_full, (uint32_t)((tl - 1) & 1));
-      tc_fence_after();
-      if (h == 0) write_heads(t_prev);
-    }
+    if (HEADS && tl > 0 && h == 0) write_heads(t_prev, tl - 1);
   }
   tc_fence_before();
   __syncthreads();
@@ -855,6 +925,9 @@ struct UmmaWorkspace {
   int PKp = 0, VKp = 0, FK = 0;       // padded feature widths (multiples of 8 elements = 16 bytes)
   int fc_stages = 0, fc_b_rows = 0, fc_smem = 0;
   CUtensorMap map_act1, map_act2, map_feat;
+  CUtensorMap map_act1_s, map_act2_s;  // single-load boxes (128+2P+2 rows)
+  int single = 0;
+  long long* clk = nullptr;            // AZP_CLK=1: per-tile stamps of conv3's CTA 0
   size_t rows = 0;
   int sms = 148;
   int smem2 = 0, smem3 = 0;
@@ -873,13 +946,13 @@ struct UmmaWeights {
   CUtensorMap map_w2, map_w3, map_hw, map_wp, map_wv;
 };
 
-constexpr int STAGES2 = 12, STAGES3 = 3;
+constexpr int STAGES2 = 6, STAGES3 = 3;
 
 template <int CIN, int COUT, int STAGES, bool HEADS, bool BITS>
 int conv_smem_bytes(int stage_rows) {
   using S = ConvSmem<CIN, COUT, STAGES, HEADS>;
-  return 1024 + S::W_BYTES + STAGES * stage_rows * S::ROWB + (HEADS ? (COUT / 64) * HEAD_N * 128 : 0) +
-         (2 * STAGES + 7) * 8 + 16 + (COUT + 8) * 4 + (BITS ? (72 * 32 + 32) * 4 + 2 * CODES * 2 : 0) + 64;
+  return 1024 + S::W_BYTES + STAGES * ((stage_rows + 2 + 7) / 8 * 8) * S::ROWB + (HEADS ? (COUT / 64) * HEAD_N * 128 : 0) +
+         (2 * STAGES + 9) * 8 + 16 + (COUT + 8) * 4 + (BITS ? (72 * 32 + 32) * 4 + 2 * CODES * 2 : 0) + 64;
 }
 
 }  // namespace
@@ -915,6 +988,10 @@ int azp_umma_create(azp_engine* e) {
   const int stage_rows = TILE_M + 2 * g.P;
   if ((st = make_map(e, &ws->map_act1, ws->act1, ws->rows, 32, stage_rows))) return st;
   if ((st = make_map(e, &ws->map_act2, ws->act2, ws->rows, 64, stage_rows))) return st;
+  if ((st = make_map(e, &ws->map_act1_s, ws->act1, ws->rows, 32, stage_rows + 2))) return st;
+  if ((st = make_map(e, &ws->map_act2_s, ws->act2, ws->rows, 64, stage_rows + 2))) return st;
+  { const char* v = getenv("AZP_SINGLE_LOAD"); ws->single = v ? atoi(v) : 1; }
+  if (getenv("AZP_CLK")) { if ((st = e->alloc(&ws->clk, (size_t)64 * 16))) return st; AZP_CUDA(e, cudaMemset(ws->clk, 0, 64 * 16 * 8)); }
   cudaDeviceProp prop;
   AZP_CUDA(e, cudaGetDeviceProperties(&prop, e->cfg.device));
   ws->sms = prop.multiProcessorCount;
@@ -1038,20 +1115,28 @@ static int run_trunk(azp_engine* e, NetWeights* W, const int32_t* count_dev, int
   a2.g = g; a2.bias = U->b2; a2.out = ws->act2; a2.head_b = nullptr; a2.feat = nullptr; a2.NJ = 0;
   a2.PC = 0; a2.PKp = 0; a2.FK = 0;
   a2.count_dev = count_dev; a2.count_host = count_host; a2.back = back; a2.stage_rows = TILE_M + 2 * g.P;
+  a2.single = from_bits ? 1 : ws->single;
+  { const char* v = getenv("AZP_CLK"); a2.clk = (v && atoi(v) == 2) ? ws->clk : nullptr; }
+  a2.stage_bytes = (a2.single ? (a2.stage_rows + 2 + 7) / 8 * 8 : a2.stage_rows) * 64;
   a2.lx = e->tv.leaf_x; a2.lo = e->tv.leaf_o; a2.ltm = e->tv.leaf_tm; a2.llast = e->tv.leaf_last; a2.NW = e->NW;
   a2.w1 = U->w1_tab; a2.b1 = U->b1;
   { static int dbg = -1; if (dbg < 0) { const char* v = getenv("AZP_DEBUG_CONV"); dbg = v ? atoi(v) : 0; } a2.debug = dbg; }
   if (from_bits)
     conv_umma_kernel<32, 64, STAGES2, false, true><<<grid, CONV_THREADS_BITS, ws->smem2, s>>>(ws->map_act1, U->map_w2, U->map_w2, a2);
   else
-    conv_umma_kernel<32, 64, STAGES2, false, false><<<grid, CONV_THREADS, ws->smem2, s>>>(ws->map_act1, U->map_w2, U->map_w2, a2);
+    conv_umma_kernel<32, 64, STAGES2, false, false><<<grid, CONV_THREADS, ws->smem2, s>>>(
+        a2.single ? ws->map_act1_s : ws->map_act1, U->map_w2, U->map_w2, a2);
   azp_count_launch();
   ConvArgs a3 = a2;
   a3.bias = U->b3; a3.out = nullptr; a3.head_b = U->head_b8; a3.feat = ws->feat;
   a3.NJ = W->PC + W->VC; a3.PC = W->PC; a3.PKp = ws->PKp; a3.FK = ws->FK;
+  a3.single = ws->single;
+  { const char* v = getenv("AZP_CLK"); a3.clk = (v && atoi(v) == 1) ? ws->clk : nullptr; }
+  a3.stage_bytes = (a3.single ? (a3.stage_rows + 2 + 7) / 8 * 8 : a3.stage_rows) * 128;
   e->prof_flops_per_board = 2.0 * 9.0 * 64 * 128 * g.A;
   azp_prof_begin(e, count_dev, count_host, s);
-  conv_umma_kernel<64, 128, STAGES3, true, false><<<grid, CONV_THREADS, ws->smem3, s>>>(ws->map_act2, U->map_w3, U->map_hw, a3);
+  conv_umma_kernel<64, 128, STAGES3, true, false><<<grid, CONV_THREADS, ws->smem3, s>>>(
+      a3.single ? ws->map_act2_s : ws->map_act2, U->map_w3, U->map_hw, a3);
   azp_count_launch();
   azp_prof_end(e, s);
   FcArgs fa;
@@ -1104,6 +1189,11 @@ __global__ void unpack_feat_kernel(int A, int n, int PKp, int FK, const __nv_bfl
 int azp_umma_debug(azp_engine* e, int layer, int n, float* out, cudaStream_t s) {
   UmmaWorkspace* ws = (UmmaWorkspace*)e->ws->umma;
   const ConvGeom& g = ws->g;
+  if (layer == 9) {            // clock stamps of the last conv3 launch: [64][16] int64 reinterpreted, as floats of deltas
+    if (!ws->clk) return AZP_ERR_INVALID_ARG;
+    AZP_CUDA(e, cudaMemcpyAsync(out, ws->clk, 64 * 16 * 8, cudaMemcpyDeviceToDevice, s));
+    return AZP_OK;
+  }
   if (layer == 1 || layer == 2) {
     int C = layer == 1 ? 32 : 64;
     size_t total = (size_t)n * g.A * C;

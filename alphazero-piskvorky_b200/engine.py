@@ -114,6 +114,10 @@ class Engine:
     def debug_activations(self, layer, n):
         c = {1: 32, 2: 64}.get(layer)
         shape = (n, self.A, c) if c else (n, 6, self.A)
+        if layer == 9:                      # bring-up: conv3 clock stamps [64][16] int64
+            out = torch.zeros((64, 16), dtype=torch.int64, device=self.device)
+            check(self.lib.azp_debug_activations(self.h, 9, 1, ptr(out), stream_ptr()), self.h)
+            return out
         out = torch.empty(shape, device=self.device)
         check(self.lib.azp_debug_activations(self.h, layer, n, ptr(out), stream_ptr()), self.h)
         return out

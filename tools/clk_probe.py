@@ -1,0 +1,20 @@
+"""Per-tile clock stamps of conv3's CTA 0 (AZP_CLK=1): where do the cycles of a tile go?"""
+import sys, os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+os.environ["AZP_CLK"] = sys.argv[1] if len(sys.argv) > 1 else "1"
+import numpy as np, torch
+import alphazero_piskvorky_b200 as az
+from oracle import net as onet
+n = 2048
+eng = az.Engine(board=15, win_length=5, games=n, sims=2, net_dtype=az.DTYPE_BF16)
+eng.load_state_dict(onet.synthetic_stem_params(15, seed=1))
+x = torch.zeros((n, 4, 15, 15), device="cuda"); x[:, 0, 7, 7] = 1
+for _ in range(3): eng.net_forward(x)
+torch.cuda.synchronize()
+c = eng.debug_activations(9, 1).cpu().numpy()
+names = {0: "P:before empty", 1: "P:after empty", 2: "M:before tempty", 3: "M:after tempty", 4: "M:full landed", 5: "M:conv issued+commit",
+         6: "M:head issued", 8: "E:before tfull", 9: "E:after tfull", 10: "E:math+st issued", 11: "E:arrived", 12: "E:heads written"}
+t0 = c[0, 2]
+print("tile | " + " | ".join(f"{names[k]:>20s}" for k in sorted(names)))
+for tl in range(0, 28):
+    print(f"{tl:4d} | " + " | ".join(f"{int(c[tl, k] - t0):20d}" for k in sorted(names)))
