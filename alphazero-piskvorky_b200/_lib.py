@@ -26,7 +26,7 @@ class Config(C.Structure):
         ("net_kind", C.c_int32), ("net_dtype", C.c_int32), ("tower_blocks", C.c_int32),
         ("tower_channels", C.c_int32), ("augment_mode", C.c_int32), ("max_plies", C.c_int32),
         ("seed", C.c_uint64), ("rank", C.c_int32), ("world", C.c_int32), ("device", C.c_int32),
-        ("reserved", C.c_int32),
+        ("leaves_per_step", C.c_int32),
     ]
 
 

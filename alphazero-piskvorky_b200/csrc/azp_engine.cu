@@ -51,9 +51,12 @@ extern "C" const char* azp_last_error(const azp_engine* e) {
 static int create_impl(azp_engine* e) {
   const azp_config& c = e->cfg;
   const size_t G = c.games, A = e->A, NW = e->NW;
+  const size_t GK = (size_t)c.games * (c.leaves_per_step > 1 ? c.leaves_per_step : 1);
   TreeView& tv = e->tv;
-  tv.G = c.games; tv.A = e->A; tv.NW = e->NW; tv.S = c.sims;
-  tv.cap = c.sims + 2;
+  e->K = c.leaves_per_step > 1 ? c.leaves_per_step : 1;
+  e->slots = c.games * e->K;
+  tv.G = c.games; tv.A = e->A; tv.NW = e->NW; tv.S = c.sims; tv.K = e->K; tv.slots = e->slots;
+  tv.cap = c.sims + e->K + 2;
   const int empties = e->A;
   tv.maxd = (c.sims + 1 < empties ? c.sims + 1 : empties) + 1;
   int st;
@@ -73,22 +76,22 @@ static int create_impl(azp_engine* e) {
   if ((st = e->alloc(&tv.root_result, G))) return st;
   if ((st = e->alloc(&tv.active, G))) return st;
   if ((st = e->alloc(&tv.net_of_game, G))) return st;
-  if ((st = e->alloc(&tv.path, G * (size_t)tv.maxd))) return st;
-  if ((st = e->alloc(&tv.path_len, G))) return st;
-  if ((st = e->alloc(&tv.leaf_kind, G))) return st;
-  if ((st = e->alloc(&tv.leaf_tvalue, G))) return st;
-  if ((st = e->alloc(&tv.leaf_slot, G))) return st;
-  if ((st = e->alloc(&tv.slot_game, G))) return st;
-  if ((st = e->alloc(&tv.leaf_x, G * NW))) return st;
-  if ((st = e->alloc(&tv.leaf_o, G * NW))) return st;
-  if ((st = e->alloc(&tv.leaf_tm, G))) return st;
-  if ((st = e->alloc(&tv.leaf_last, G))) return st;
+  if ((st = e->alloc(&tv.path, GK * (size_t)tv.maxd))) return st;
+  if ((st = e->alloc(&tv.path_len, GK))) return st;
+  if ((st = e->alloc(&tv.leaf_kind, GK))) return st;
+  if ((st = e->alloc(&tv.leaf_tvalue, GK))) return st;
+  if ((st = e->alloc(&tv.leaf_slot, GK))) return st;
+  if ((st = e->alloc(&tv.slot_game, GK))) return st;
+  if ((st = e->alloc(&tv.leaf_x, GK * NW))) return st;
+  if ((st = e->alloc(&tv.leaf_o, GK * NW))) return st;
+  if ((st = e->alloc(&tv.leaf_tm, GK))) return st;
+  if ((st = e->alloc(&tv.leaf_last, GK))) return st;
   if ((st = e->alloc(&tv.n_leaves, 4))) return st;
   if ((st = e->alloc(&tv.error_flag, 1))) return st;
   if ((st = e->alloc(&tv.counters, (size_t)CNT_COUNT))) return st;
-  if ((st = e->alloc(&e->d_policy, G * A))) return st;
-  if ((st = e->alloc(&e->d_logits, G * A))) return st;
-  if ((st = e->alloc(&e->d_value, G))) return st;
+  if ((st = e->alloc(&e->d_policy, GK * A))) return st;
+  if ((st = e->alloc(&e->d_logits, GK * A))) return st;
+  if ((st = e->alloc(&e->d_value, GK))) return st;
   e->max_plies = (c.max_plies > 0 && c.max_plies < e->A) ? c.max_plies : e->A;
   const size_t MP = e->max_plies;
   if ((st = e->alloc(&e->d_temperature, MP + 2))) return st;
@@ -138,6 +141,8 @@ extern "C" int azp_create(const azp_config* cfg, azp_engine** out) {
     return bad("tower needs blocks >= 1 and channels a multiple of 32");
   if (cfg->augment_mode < 0 || cfg->augment_mode > 2) return bad("unknown augment_mode");
   if (cfg->world < 1 || cfg->rank < 0 || cfg->rank >= cfg->world) return bad("rank/world invalid");
+  if (cfg->leaves_per_step < 0 || cfg->leaves_per_step > 16 || (long long)cfg->games * (cfg->leaves_per_step > 1 ? cfg->leaves_per_step : 1) > 65535)
+    return bad("leaves_per_step must be in [0,16] and games*leaves_per_step <= 65535");
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
     azp_set_global_error("no CUDA device: this engine has no CPU fallback");
@@ -230,6 +235,7 @@ static int check_device_error(azp_engine* e, cudaStream_t s) {
 extern "C" int azp_search_begin(azp_engine* e, int n, const uint64_t* x, const uint64_t* o, const uint8_t* to_move,
                                 const int16_t* last, const int32_t* ply, const int64_t* game_id, void* stream) {
   if (!e || n < 1 || n > e->cfg.games || !x || !o || !to_move) return AZP_ERR_INVALID_ARG;
+  if (e->K != 1) { e->set_error("the step-by-step search API needs leaves_per_step == 1"); return AZP_ERR_UNSUPPORTED; }
   cudaStream_t s = (cudaStream_t)stream;
   set_roots_kernel<<<(e->cfg.games + 127) / 128, 128, 0, s>>>(e->tv, n, x, o, to_move, last, ply, game_id);
   azp_count_launch();
@@ -270,7 +276,8 @@ static int search_move(azp_engine* e, int n, int add_noise, int two_nets, cudaSt
   if ((st = azp_net_eval_leaves(e, 0, tv.n_leaves + e->parity * 2 + 0, 0, 0, s))) return st;
   if (two_nets && (st = azp_net_eval_leaves(e, 1, tv.n_leaves + e->parity * 2 + 1, 0, 1, s))) return st;
   if ((st = azp_tree_root_expand(e, n, e->d_policy, 1, add_noise, s))) return st;
-  for (int sim = 0; sim < e->cfg.sims; sim++) {
+  const int steps = (e->cfg.sims + e->K - 1) / e->K;      // K descents per game per step
+  for (int sim = 0; sim < steps; sim++) {
     e->parity ^= 1;
     if ((st = azp_tree_select(e, n, 1, e->parity, s))) return st;
     if ((st = azp_net_eval_leaves(e, 0, tv.n_leaves + e->parity * 2 + 0, 0, 0, s))) return st;

@@ -44,6 +44,7 @@ RulesParams azp_make_rules(int board, int win_length);
 // alphazero/mcts.py:25-48; the root's own N lives in root_n.
 struct TreeView {
   int G, A, NW, cap, maxd, S;
+  int K, slots;      // descents per game per step (virtual loss if > 1); leaf-batch rows = G*K
   int32_t* N;        // [G][cap][A] visit count of the child reached through the edge
   double* W;         // [G][cap][A] total value (float64, as the reference's Python floats)
   float* P;          // [G][cap][A] prior (float32 widened at use, mcts.py:63)
@@ -58,14 +59,15 @@ struct TreeView {
   uint8_t* active;                         // [G] 1 = this slot searches
   uint8_t* net_of_game;                    // [G] weight slot that evaluates this game's leaves
   // per-step leaf records
-  int32_t* path;         // [G][maxd] (node*A + cell) of every edge on the descent
-  int32_t* path_len;     // [G]
-  uint8_t* leaf_kind;    // [G] 0 = evaluate+expand, 1 = terminal, 2 = idle
-  float* leaf_tvalue;    // [G] value of a terminal leaf from its side to move's view
-  int32_t* leaf_slot;    // [G] row of the leaf in the contiguous evaluation batch (-1 if none)
-  int32_t* slot_game;    // [G] inverse
-  uint64_t* leaf_x; uint64_t* leaf_o;      // [G][NW] indexed by SLOT (contiguous batch)
-  uint8_t* leaf_tm; int16_t* leaf_last;    // [G]     indexed by SLOT
+  // per-step leaf records, one per (game, descent k): index g*K + k
+  int32_t* path;         // [G*K][maxd] (node*A + cell) of every edge on the descent
+  int32_t* path_len;     // [G*K]
+  uint8_t* leaf_kind;    // [G*K] 0 = evaluate+expand, 1 = terminal, 2 = idle
+  float* leaf_tvalue;    // [G*K] value of a terminal leaf from its side to move's view
+  int32_t* leaf_slot;    // [G*K] row of the leaf in the contiguous evaluation batch (-1 if none)
+  int32_t* slot_game;    // [slots] inverse
+  uint64_t* leaf_x; uint64_t* leaf_o;      // [slots][NW] indexed by SLOT (contiguous batch)
+  uint8_t* leaf_tm; int16_t* leaf_last;    // [slots]     indexed by SLOT
   int32_t* n_leaves;     // [4]: {front count, back count} x step parity
   int32_t* error_flag;   // [1] device-side error (capacity overflow, illegal move)
   unsigned long long* counters;  // azp_counters as 64-bit words
@@ -85,6 +87,7 @@ struct azp_engine {
   RulesParams rp;
   TreeView tv;
   int A, NW;
+  int K = 1, slots = 0;            // leaves per game per step; rows of the evaluation batch (games * K)
   std::string error;
   std::vector<void*> allocs;
   NetWeights* weights[2] = {nullptr, nullptr};

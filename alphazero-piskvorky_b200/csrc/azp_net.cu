@@ -325,7 +325,7 @@ static int build_f32(azp_engine* e, const HostNet& net, NetWeights* W) {
 int azp_net_create(azp_engine* e) {
   e->ws = new NetWorkspace();
   NetWorkspace* ws = e->ws;
-  const size_t G = e->cfg.games, A = e->A;
+  const size_t G = e->slots, A = e->A;
   int cmax = e->cfg.net_kind == AZP_NET_STEM ? 128 : e->cfg.tower_channels;
   ws->cmax = cmax;
   int st;
@@ -374,7 +374,7 @@ int azp_net_load(azp_engine* e, int slot, const float* blob, size_t n, bool on_d
 static int run_f32(azp_engine* e, NetWeights* W, const float* in4, const int32_t* count_dev, int count_host,
                    int back, float* logits, float* policy, float* value, int out_by_index, cudaStream_t s) {
   NetWorkspace* ws = e->ws;
-  const int B = e->cfg.board, A = e->A, G = e->cfg.games;
+  const int B = e->cfg.board, A = e->A, G = e->slots;
   const int zmax = count_dev ? G : count_host;
   if (zmax <= 0) return AZP_OK;
   // activation buffers rotate through ws->act[0..2]; a tower block needs three: x (skip), y, out
@@ -433,7 +433,7 @@ int azp_net_eval_leaves(azp_engine* e, int slot, const int32_t* count_dev, int c
   NetWeights* W = e->weights[slot];
   if (!W || !W->loaded) { e->set_error("no weights loaded in slot " + std::to_string(slot)); return AZP_ERR_NO_WEIGHTS; }
   if (e->cfg.net_dtype == AZP_DTYPE_BF16) return azp_umma_eval_leaves(e, W, count_dev, count_host, back, s);
-  const int A = e->A, G = e->cfg.games;
+  const int A = e->A, G = e->slots;
   const int zmax = count_dev ? G : count_host;
   if (zmax <= 0) return AZP_OK;
   leaves_to_nhwc_kernel<<<(int)(((size_t)zmax * A + 255) / 256), 256, 0, s>>>(
@@ -446,7 +446,7 @@ int azp_net_eval_planes(azp_engine* e, int slot, int n, const float* planes, flo
                         float* value, cudaStream_t s) {
   NetWeights* W = e->weights[slot];
   if (!W || !W->loaded) { e->set_error("no weights loaded in slot " + std::to_string(slot)); return AZP_ERR_NO_WEIGHTS; }
-  const int A = e->A, G = e->cfg.games;
+  const int A = e->A, G = e->slots;
   for (int done = 0; done < n; done += G) {
     int m = n - done < G ? n - done : G;
     const float* pin = planes + (size_t)done * 4 * A;

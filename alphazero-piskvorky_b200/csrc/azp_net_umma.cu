@@ -966,7 +966,7 @@ int azp_umma_create(azp_engine* e) {
   UmmaWorkspace* ws = new UmmaWorkspace();
   e->ws->umma = ws;
   ConvGeom& g = ws->g;
-  g.B = e->cfg.board; g.A = e->A; g.P = g.B <= 15 ? 16 : 24; g.stride = (g.B + 1) * g.P; g.G = e->cfg.games;
+  g.B = e->cfg.board; g.A = e->A; g.P = g.B <= 15 ? 16 : 24; g.stride = (g.B + 1) * g.P; g.G = e->slots;
   ws->rows = (size_t)g.G * g.stride + 2 * g.P + TILE_M;        // tail halo + a partial last tile
   int st;
   if ((st = e->alloc(&ws->act1, ws->rows * 32))) return st;

@@ -14,20 +14,21 @@ __device__ __forceinline__ void count(const TreeView& tv, int idx, unsigned long
 
 // Claim a row of the contiguous evaluation batch and store the position there.  Games evaluated
 // by weight slot 0 fill rows from the front, slot 1 (arena baseline) from the back.
+// `rec` = leaf record index (g*K + k).
 template <int NW>
-__device__ __forceinline__ int emit_leaf(const TreeView& tv, int g, const BB<NW>& x, const BB<NW>& o, int tm,
+__device__ __forceinline__ int emit_leaf(const TreeView& tv, int g, int rec, const BB<NW>& x, const BB<NW>& o, int tm,
                                          int last, int compact, int parity, int lane) {
-  int slot = g;
+  int slot = rec;
   if (compact) {
     if (lane == 0) {
       int side = tv.net_of_game[g];
       int idx = atomicAdd(&tv.n_leaves[parity * 2 + side], 1);
-      slot = side ? tv.G - 1 - idx : idx;
+      slot = side ? tv.slots - 1 - idx : idx;
     }
     slot = __shfl_sync(AZP_FULL, slot, 0);
   }
   if (lane == 0) {
-    tv.leaf_slot[g] = slot;
+    tv.leaf_slot[rec] = slot;
     tv.slot_game[slot] = g;
     bb_store<NW>(tv.leaf_x + (size_t)slot * NW, x);
     bb_store<NW>(tv.leaf_o + (size_t)slot * NW, o);
@@ -46,22 +47,23 @@ __global__ void begin_move_kernel(RulesParams rp, TreeView tv, int n, int emit, 
     tv.n_leaves[(parity ^ 1) * 2 + 1] = 0;
   }
   if (g >= n) return;
-  if (!tv.active[g]) {
-    if (lane == 0) { tv.leaf_kind[g] = 2; tv.leaf_slot[g] = -1; tv.path_len[g] = 0; }
-    return;
+  const int rec0 = g * tv.K;
+  if (lane < tv.K) {                      // every descent record of this game starts idle
+    tv.leaf_kind[rec0 + lane] = 2; tv.leaf_slot[rec0 + lane] = -1; tv.path_len[rec0 + lane] = 0;
   }
+  __syncwarp();
+  if (!tv.active[g]) return;
   BB<NW> x = bb_load<NW>(tv.root_x + (size_t)g * NW), o = bb_load<NW>(tv.root_o + (size_t)g * NW);
   int res = warp_result<NW>(rp, x, o, lane);
   if (lane == 0) {
     tv.node_count[g] = 1;
     tv.root_n[g] = 0;
     tv.root_result[g] = (uint8_t)res;
-    tv.leaf_kind[g] = 0;
-    tv.path_len[g] = 0;
+    tv.leaf_kind[rec0] = 0;
   }
   // the root is evaluated unconditionally (mcts.py:109), even when it is terminal
   if (emit) {
-    emit_leaf<NW>(tv, g, x, o, tv.root_tm[g], tv.root_last[g], compact, parity, lane);
+    emit_leaf<NW>(tv, g, rec0, x, o, tv.root_tm[g], tv.root_last[g], compact, parity, lane);
     if (lane == 0) count(tv, CNT_EVALS, 1);
   }
 }
@@ -77,7 +79,7 @@ __global__ void root_expand_kernel(RulesParams rp, TreeView tv, int n, const flo
   BB<NW> occ;
 #pragma unroll
   for (int k = 0; k < NW; k++) occ.w[k] = x.w[k] | o.w[k];
-  const float* prow = policy + (size_t)(by_slot ? tv.leaf_slot[g] : g) * A;
+  const float* prow = policy + (size_t)(by_slot ? tv.leaf_slot[g * tv.K] : g) * A;
   const size_t base = (size_t)g * tv.cap * A;   // node 0
   double gsum = 0.0;
   Philox rng = philox_for_game(seed, tv.game_id[g]);
@@ -108,7 +110,13 @@ __global__ void root_expand_kernel(RulesParams rp, TreeView tv, int n, const flo
   if (lane == 0) count(tv, CNT_EXPANSIONS, 1);
 }
 
-// ---- one PUCT descent per game (mcts.py:126-129 + 66-74) -------------------------------------
+#define CHILD_NONE (-1)
+#define CHILD_PENDING (-2)      // claimed by an earlier descent of this step (throughput mode only)
+
+// ---- K PUCT descents per game (mcts.py:126-129 + 66-74) ---------------------------------------
+// K == 1 is the exact mode: the tree is only read here.  K > 1 (throughput mode): after each descent its
+// path takes a VIRTUAL LOSS (N += 1, W -= 1, undone by expand_backup) so the next descent of the same step
+// goes elsewhere; an unexpanded edge reached twice in one step is a collision and the later descent idles.
 template <int NW>
 __global__ void select_kernel(RulesParams rp, TreeView tv, int n, double c_puct, int compact, int parity) {
   int g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
@@ -117,154 +125,200 @@ __global__ void select_kernel(RulesParams rp, TreeView tv, int n, double c_puct,
     tv.n_leaves[(parity ^ 1) * 2 + 1] = 0;
   }
   if (g >= n) return;
+  const int K = tv.K;
+  const int rec0 = g * K;
   if (!tv.active[g]) {
-    if (lane == 0) { tv.leaf_kind[g] = 2; tv.leaf_slot[g] = -1; tv.path_len[g] = 0; }
+    if (lane < K) { tv.leaf_kind[rec0 + lane] = 2; tv.leaf_slot[rec0 + lane] = -1; tv.path_len[rec0 + lane] = 0; }
     return;
   }
   const int A = rp.A;
-  BB<NW> x = bb_load<NW>(tv.root_x + (size_t)g * NW), o = bb_load<NW>(tv.root_o + (size_t)g * NW);
-  int tm = tv.root_tm[g], last = tv.root_last[g];
+  const BB<NW> rx = bb_load<NW>(tv.root_x + (size_t)g * NW), ro = bb_load<NW>(tv.root_o + (size_t)g * NW);
+  const int root_tm = tv.root_tm[g], root_last = tv.root_last[g];
   const size_t gbase = (size_t)g * tv.cap * A;
-  int32_t* path = tv.path + (size_t)g * tv.maxd;
-  int node = 0, nparent = tv.root_n[g], depth = 0;
-  int result = tv.root_result[g];
-  int kind;
-  float tvalue = 0.f;
-  unsigned long long scanned = 0;
-  while (true) {
-    if (result != 0) {   // terminal position: value from its side to move's view (mcts.py:132-134)
-      kind = 1;
-      tvalue = result == 3 ? 0.f : (result == tm ? 1.f : -1.f);
-      break;
+  const int root_result = tv.root_result[g];
+  int root_n = tv.root_n[g];
+  unsigned long long scanned = 0, path_total = 0, n_eval = 0, n_term = 0;
+  for (int kd = 0; kd < K; kd++) {
+    const int rec = rec0 + kd;
+    int32_t* path = tv.path + (size_t)rec * tv.maxd;
+    if (K > 1 && root_n >= tv.S) {       // this move's simulation budget is used up
+      if (lane == 0) { tv.leaf_kind[rec] = 2; tv.leaf_slot[rec] = -1; tv.path_len[rec] = 0; }
+      continue;
     }
-    const size_t nb = gbase + (size_t)node * A;
-    // score = Q + c_puct * P * sqrt(N_parent + 1e-8) / (1 + N_child), float64, left to right
-    const double sq = __dsqrt_rn(__dadd_rn((double)nparent, 1e-8));
-    double best = -1.0e308;
-    int besta = 0x7fffffff;
-    int stones = 0;
+    BB<NW> x = rx, o = ro;
+    int tm = root_tm, last = root_last;
+    int node = 0, nparent = root_n, depth = 0;
+    int result = root_result;
+    int kind;
+    float tvalue = 0.f;
+    while (true) {
+      if (result != 0) {   // terminal position: value from its side to move's view (mcts.py:132-134)
+        kind = 1;
+        tvalue = result == 3 ? 0.f : (result == tm ? 1.f : -1.f);
+        break;
+      }
+      const size_t nb = gbase + (size_t)node * A;
+      // score = Q + c_puct * P * sqrt(N_parent + 1e-8) / (1 + N_child), float64, left to right
+      const double sq = __dsqrt_rn(__dadd_rn((double)nparent, 1e-8));
+      double best = -1.0e308;
+      int besta = 0x7fffffff;
+      int stones = 0;
 #pragma unroll
-    for (int k = 0; k < NW; k++) stones += __popcll(x.w[k] | o.w[k]);
-    // all of a node's edge statistics are fetched before any arithmetic: one memory round trip per level
-    constexpr int MAXI = (AZP_MAX_BOARD * AZP_MAX_BOARD + 31) / 32;
-    int nn_[MAXI], ch_[MAXI];
-    double ww_[MAXI];
-    float pp_[MAXI];
+      for (int k = 0; k < NW; k++) stones += __popcll(x.w[k] | o.w[k]);
+      // all of a node's edge statistics are fetched before any arithmetic: one memory round trip per level
+      constexpr int MAXI = (AZP_MAX_BOARD * AZP_MAX_BOARD + 31) / 32;
+      int nn_[MAXI], ch_[MAXI];
+      double ww_[MAXI];
+      float pp_[MAXI];
 #pragma unroll
-    for (int i = 0; i < MAXI; i++) {
-      const int a = lane + 32 * i;
-      nn_[i] = 0; ww_[i] = 0.0; pp_[i] = 0.f; ch_[i] = -1;
-      if (a < A) { nn_[i] = tv.N[nb + a]; ww_[i] = tv.W[nb + a]; pp_[i] = tv.P[nb + a]; ch_[i] = tv.child[nb + a]; }
-    }
+      for (int i = 0; i < MAXI; i++) {
+        const int a = lane + 32 * i;
+        nn_[i] = 0; ww_[i] = 0.0; pp_[i] = 0.f; ch_[i] = CHILD_NONE;
+        if (a < A) { nn_[i] = tv.N[nb + a]; ww_[i] = tv.W[nb + a]; pp_[i] = tv.P[nb + a]; ch_[i] = tv.child[nb + a]; }
+      }
 #pragma unroll
-    for (int i = 0; i < MAXI; i++) {
-      const int a = lane + 32 * i;
-      const bool occupied = a >= A || bb_test<NW>(x, a) || bb_test<NW>(o, a);
-      if (occupied) continue;
-      const int nn = nn_[i];
-      double q = nn ? __ddiv_rn(ww_[i], (double)nn) : 0.0;
-      double u = __ddiv_rn(__dmul_rn(__dmul_rn(c_puct, (double)pp_[i]), sq), (double)(1 + nn));
-      double s = __dadd_rn(q, u);
-      if (s > best) { best = s; besta = a; }    // ascending a: the FIRST maximum is kept
-    }
+      for (int i = 0; i < MAXI; i++) {
+        const int a = lane + 32 * i;
+        const bool occupied = a >= A || bb_test<NW>(x, a) || bb_test<NW>(o, a);
+        if (occupied) continue;
+        const int nn = nn_[i];
+        double q = nn ? __ddiv_rn(ww_[i], (double)nn) : 0.0;
+        double u = __ddiv_rn(__dmul_rn(__dmul_rn(c_puct, (double)pp_[i]), sq), (double)(1 + nn));
+        double s = __dadd_rn(q, u);
+        if (s > best) { best = s; besta = a; }    // ascending a: the FIRST maximum is kept
+      }
 #pragma unroll
-    for (int off = 16; off; off >>= 1) {       // argmax with lowest-cell tie-break
-      double ob = __shfl_xor_sync(AZP_FULL, best, off);
-      int oa = __shfl_xor_sync(AZP_FULL, besta, off);
-      if (ob > best || (ob == best && oa < besta)) { best = ob; besta = oa; }
-    }
-    scanned += (unsigned long long)(A - stones);
-    const int a = besta;
-    if (a >= A) {          // cannot happen on a non-terminal position; never loop forever
-      if (lane == 0) atomicExch(tv.error_flag, AZP_ERR_CAPACITY);
-      kind = 2;
-      break;
-    }
-    // the winning edge's N / child pointer are already in the owning lane's registers
-    int cn = 0, ch = -1;
+      for (int off = 16; off; off >>= 1) {       // argmax with lowest-cell tie-break
+        double ob = __shfl_xor_sync(AZP_FULL, best, off);
+        int oa = __shfl_xor_sync(AZP_FULL, besta, off);
+        if (ob > best || (ob == best && oa < besta)) { best = ob; besta = oa; }
+      }
+      scanned += (unsigned long long)(A - stones);
+      const int a = besta;
+      if (a >= A || depth >= tv.maxd) {   // cannot happen on a non-terminal position; never loop forever
+        if (lane == 0) atomicExch(tv.error_flag, AZP_ERR_CAPACITY);
+        kind = 2;
+        break;
+      }
+      // the winning edge's N / child pointer are already in the owning lane's registers
+      int cn = 0, ch = CHILD_NONE;
 #pragma unroll
-    for (int i = 0; i < MAXI; i++) if (i == (a >> 5)) { cn = nn_[i]; ch = ch_[i]; }
-    cn = __shfl_sync(AZP_FULL, cn, a & 31);
-    ch = __shfl_sync(AZP_FULL, ch, a & 31);
-    if (depth >= tv.maxd) {
-      if (lane == 0) atomicExch(tv.error_flag, AZP_ERR_CAPACITY);
-      kind = 2;
-      break;
+      for (int i = 0; i < MAXI; i++) if (i == (a >> 5)) { cn = nn_[i]; ch = ch_[i]; }
+      cn = __shfl_sync(AZP_FULL, cn, a & 31);
+      ch = __shfl_sync(AZP_FULL, ch, a & 31);
+      if (lane == 0) path[depth] = node * A + a;
+      depth++;
+      if (tm == 1) bb_set<NW>(x, a); else bb_set<NW>(o, a);
+      tm = 3 - tm;
+      last = a;
+      result = warp_result<NW>(rp, x, o, lane);
+      if (result != 0) continue;
+      if (ch == CHILD_PENDING) { kind = 2; break; }          // collision with an earlier descent of this step
+      if (ch < 0) {                                          // reached a child that has not been expanded
+        kind = 0;
+        if (K > 1 && lane == 0) tv.child[nb + a] = CHILD_PENDING;
+        break;
+      }
+      node = ch;
+      nparent = cn;
     }
-    if (lane == 0) path[depth] = node * A + a;
-    depth++;
-    if (tm == 1) bb_set<NW>(x, a); else bb_set<NW>(o, a);
-    tm = 3 - tm;
-    last = a;
-    result = warp_result<NW>(rp, x, o, lane);
-    if (result != 0) continue;
-    if (ch < 0) { kind = 0; break; }     // reached a child that has not been expanded
-    node = ch;
-    nparent = cn;
+    if (kind == 0) emit_leaf<NW>(tv, g, rec, x, o, tm, last, compact, parity, lane);
+    if (lane == 0) {
+      tv.path_len[rec] = kind == 2 ? 0 : depth;
+      tv.leaf_kind[rec] = (uint8_t)kind;
+      tv.leaf_tvalue[rec] = tvalue;
+      if (kind != 0) tv.leaf_slot[rec] = -1;
+    }
+    if (kind != 2) {
+      path_total += (unsigned long long)depth;
+      n_eval += kind == 0;
+      n_term += kind == 1;
+      if (K > 1) {
+        // virtual loss along the path; visible to this warp's next descent after the __syncwarp
+        __syncwarp();
+        for (int i = lane; i < depth; i += 32) {
+          const size_t e = gbase + path[i];
+          tv.N[e] += 1;
+          tv.W[e] -= 1.0;
+        }
+        root_n++;
+        __syncwarp();
+      }
+    }
   }
-  if (kind == 0) emit_leaf<NW>(tv, g, x, o, tm, last, compact, parity, lane);
   if (lane == 0) {
-    tv.path_len[g] = depth;
-    tv.leaf_kind[g] = (uint8_t)kind;
-    tv.leaf_tvalue[g] = tvalue;
-    if (kind != 0) tv.leaf_slot[g] = -1;
+    if (K > 1) tv.root_n[g] = root_n;
     count(tv, CNT_SCANNED, scanned);
-    count(tv, CNT_PATH, (unsigned long long)depth);
-    if (kind == 0) count(tv, CNT_EVALS, 1);
-    if (kind == 1) count(tv, CNT_TERMINAL, 1);
+    count(tv, CNT_PATH, path_total);
+    count(tv, CNT_EVALS, n_eval);
+    count(tv, CNT_TERMINAL, n_term);
   }
 }
 
-// ---- expand the evaluated leaf and back the value up (mcts.py:136-141, 50-64, 76-82) --------
+// ---- expand the evaluated leaves and back the values up (mcts.py:136-141, 50-64, 76-82) --------
 template <int NW>
 __global__ void expand_backup_kernel(RulesParams rp, TreeView tv, int n, const float* __restrict__ policy,
                                      const float* __restrict__ value, int by_slot) {
   int g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (g >= n || !tv.active[g]) return;
-  const int kind = tv.leaf_kind[g];
-  if (kind == 2) return;
-  const int A = rp.A;
+  const int A = rp.A, K = tv.K;
   const size_t gbase = (size_t)g * tv.cap * A;
-  const int32_t* path = tv.path + (size_t)g * tv.maxd;
-  const int depth = tv.path_len[g];
-  float v;
-  if (kind == 0) {
-    const int slot = tv.leaf_slot[g];
-    const size_t row = (size_t)(by_slot ? slot : g);
-    v = value[row];
-    int nid = tv.node_count[g];
-    if (nid >= tv.cap) {
-      if (lane == 0) atomicExch(tv.error_flag, AZP_ERR_CAPACITY);
-      return;
+  unsigned long long n_exp = 0, n_sims = 0;
+  for (int kd = 0; kd < K; kd++) {
+    const int rec = g * K + kd;
+    const int kind = tv.leaf_kind[rec];
+    if (kind == 2) continue;
+    const int32_t* path = tv.path + (size_t)rec * tv.maxd;
+    const int depth = tv.path_len[rec];
+    float v;
+    if (kind == 0) {
+      const int slot = tv.leaf_slot[rec];
+      const size_t row = (size_t)(by_slot ? slot : rec);
+      v = value[row];
+      int nid = tv.node_count[g];
+      if (nid >= tv.cap) {
+        if (lane == 0) atomicExch(tv.error_flag, AZP_ERR_CAPACITY);
+        return;
+      }
+      BB<NW> lx = bb_load<NW>(tv.leaf_x + (size_t)slot * NW), lo = bb_load<NW>(tv.leaf_o + (size_t)slot * NW);
+      const size_t nb = gbase + (size_t)nid * A;
+      const float* prow = policy + row * A;
+      for (int a = lane; a < A; a += 32) {
+        bool legal = !(bb_test<NW>(lx, a) || bb_test<NW>(lo, a));
+        tv.P[nb + a] = legal ? prow[a] : 0.f;     // prior = policy[r,c], not renormalised (mcts.py:63)
+        tv.N[nb + a] = 0;
+        tv.W[nb + a] = 0.0;
+        tv.child[nb + a] = CHILD_NONE;
+      }
+      __syncwarp();
+      if (lane == 0) {
+        tv.node_count[g] = nid + 1;
+        if (depth > 0) tv.child[gbase + path[depth - 1]] = nid;
+      }
+      __syncwarp();
+      n_exp++;
+    } else {
+      v = tv.leaf_tvalue[rec];
     }
-    BB<NW> lx = bb_load<NW>(tv.leaf_x + (size_t)slot * NW), lo = bb_load<NW>(tv.leaf_o + (size_t)slot * NW);
-    const size_t nb = gbase + (size_t)nid * A;
-    const float* prow = policy + row * A;
-    for (int a = lane; a < A; a += 32) {
-      bool legal = !(bb_test<NW>(lx, a) || bb_test<NW>(lo, a));
-      tv.P[nb + a] = legal ? prow[a] : 0.f;     // prior = policy[r,c], not renormalised (mcts.py:63)
-      tv.N[nb + a] = 0;
-      tv.W[nb + a] = 0.0;
-      tv.child[nb + a] = -1;
+    // node.backup(-value): the leaf's own statistics (last edge) take -v, signs alternate upwards.
+    // Throughput mode: the edge already carries this descent's virtual visit (N+1, W-1): swap it for the value.
+    for (int i = lane; i < depth; i += 32) {
+      const size_t e = gbase + path[i];
+      const double val = ((depth - 1 - i) & 1) ? (double)v : -(double)v;
+      if (K == 1) {
+        tv.N[e] += 1;
+        tv.W[e] = __dadd_rn(tv.W[e], val);
+      } else {
+        tv.W[e] += 1.0 + val;
+      }
     }
-    if (lane == 0) {
-      tv.node_count[g] = nid + 1;
-      if (depth > 0) tv.child[gbase + path[depth - 1]] = nid;
-      count(tv, CNT_EXPANSIONS, 1);
-    }
-  } else {
-    v = tv.leaf_tvalue[g];
-  }
-  // node.backup(-value): the leaf's own statistics (last edge) take -v, signs alternate upwards
-  for (int i = lane; i < depth; i += 32) {
-    const size_t e = gbase + path[i];
-    const double val = ((depth - 1 - i) & 1) ? (double)v : -(double)v;
-    tv.N[e] += 1;
-    tv.W[e] = __dadd_rn(tv.W[e], val);
+    __syncwarp();
+    n_sims++;
   }
   if (lane == 0) {
-    tv.root_n[g] += 1;
-    count(tv, CNT_SIMS, 1);
+    if (K == 1) tv.root_n[g] += (int)n_sims;
+    count(tv, CNT_SIMS, n_sims);
+    count(tv, CNT_EXPANSIONS, n_exp);
   }
 }
 

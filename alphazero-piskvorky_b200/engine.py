@@ -53,7 +53,8 @@ class Engine:
 
     def __init__(self, board=5, win_length=4, games=256, sims=200, c_puct=2.0, dirichlet_alpha=0.3,
                  dirichlet_weight=0.25, net_kind=NET_STEM, net_dtype=DTYPE_F32, tower_blocks=10,
-                 tower_channels=128, augment=AUGMENT_D4, max_plies=0, seed=0, rank=0, world=1, device=None):
+                 tower_channels=128, augment=AUGMENT_D4, max_plies=0, seed=0, rank=0, world=1, device=None,
+                 leaves_per_step=1):
         self.lib = _lib.load()
         if not torch.cuda.is_available():
             raise RuntimeError("azp_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
@@ -65,7 +66,8 @@ class Engine:
                                dirichlet_alpha=dirichlet_alpha, dirichlet_weight=dirichlet_weight,
                                net_kind=net_kind, net_dtype=net_dtype, tower_blocks=tower_blocks,
                                tower_channels=tower_channels, augment_mode=augment, max_plies=max_plies,
-                               seed=seed, rank=rank, world=world, device=self.device.index, reserved=0)
+                               seed=seed, rank=rank, world=world, device=self.device.index,
+                               leaves_per_step=leaves_per_step)
         self.board, self.A, self.NW = board, board * board, words(board)
         self.games, self.sims = games, sims
         self.augment = augment

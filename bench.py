@@ -170,7 +170,8 @@ def run_engine_arm(args):
     engines, streams, outs = [], [], []
     for k in range(E):
         eng = az.Engine(board=BOARD, win_length=WIN, games=games // E, sims=args.sims, c_puct=C_PUCT, net_dtype=dtype,
-                        augment=az.AUGMENT_D4, seed=0, rank=rank * E + k, world=world * E, device=local)
+                        augment=az.AUGMENT_D4, seed=0, rank=rank * E + k, world=world * E, device=local,
+                        leaves_per_step=args.leaves_per_step)
         eng.load_blob(blob_host.numpy())
         engines.append(eng)
         streams.append(torch.cuda.Stream())
@@ -298,6 +299,9 @@ def run_engine_arm(args):
             "l2": "inputs larger than L2: node table working set is GBs per GPU (no flush needed)",
             "games_per_gpu": games, "sims_per_move": args.sims, "c_puct": C_PUCT, "augment": "d4",
             "engines_per_gpu": E,
+            "leaves_per_step": args.leaves_per_step,
+            "search_mode": "exact (visit counts identical to the reference)" if args.leaves_per_step <= 1
+                           else f"virtual loss, {args.leaves_per_step} leaves per game per step (throughput mode)",
         },
         "games_per_sec": games_done / (ms / 1e3),
         "games_per_sec_steady_state": (plies_done / (ms / 1e3)) / MEAN_GAME_PLIES,
@@ -335,6 +339,8 @@ def main():
     ap.add_argument("--engines", type=int, default=int(os.environ.get("AZP_BENCH_ENGINES", "1")),
                     help="engines per GPU, each with games/engines slots on its own CUDA stream (host thread each)")
     ap.add_argument("--sims", type=int, default=SIMS)
+    ap.add_argument("--leaves-per-step", type=int, default=int(os.environ.get("AZP_BENCH_LEAVES", "1")),
+                    help="1 = exact search (reference-identical visit counts); K > 1 = virtual-loss throughput mode")
     ap.add_argument("--cpu-budget", type=float, default=15.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

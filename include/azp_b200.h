@@ -69,7 +69,8 @@ typedef struct azp_config {
   uint64_t seed;            /* Philox key; streams are keyed by GLOBAL game id */
   int32_t rank, world;      /* game sharding: this engine plays global ids == rank (mod world) blocks */
   int32_t device;           /* CUDA device ordinal */
-  int32_t reserved;
+  int32_t leaves_per_step;  /* 0/1 = exact search (one leaf per game per step, visit counts == reference);
+                             * K > 1 = throughput mode: K descents per game per step kept apart by virtual loss */
 } azp_config;
 
 typedef struct azp_counters {

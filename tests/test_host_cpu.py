@@ -51,7 +51,7 @@ def test_engine_fails_loudly_without_gpu(az):
     lib = az._lib.load()
     cfg = az._lib.Config(board=5, win_length=4, games=4, sims=10, c_puct=2.0, dirichlet_alpha=0.3,
                          dirichlet_weight=0.25, net_kind=0, net_dtype=0, tower_blocks=0, tower_channels=0,
-                         augment_mode=1, max_plies=0, seed=0, rank=0, world=1, device=0, reserved=0)
+                         augment_mode=1, max_plies=0, seed=0, rank=0, world=1, device=0, leaves_per_step=1)
     h = C.c_void_p()
     st = lib.azp_create(C.byref(cfg), C.byref(h))
     assert st == az._lib.ERR_CUDA and not h.value
@@ -69,7 +69,7 @@ def test_create_rejects_bad_config(az):
                dict(world=2, rank=2), dict(net_dtype=7)):
         base = dict(board=5, win_length=4, games=4, sims=10, c_puct=2.0, dirichlet_alpha=0.3, dirichlet_weight=0.25,
                     net_kind=0, net_dtype=0, tower_blocks=0, tower_channels=0, augment_mode=1, max_plies=0, seed=0,
-                    rank=0, world=1, device=0, reserved=0)
+                    rank=0, world=1, device=0, leaves_per_step=1)
         base.update(kw)
         cfg = az._lib.Config(**base)
         assert lib.azp_create(C.byref(cfg), C.byref(h)) == az._lib.ERR_INVALID_ARG, kw
