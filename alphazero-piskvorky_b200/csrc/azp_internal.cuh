@@ -90,6 +90,7 @@ struct azp_engine {
   int K = 1, slots = 0;            // leaves per game per step; rows of the evaluation batch (games * K)
   std::string error;
   std::vector<void*> allocs;
+  std::vector<void*>* alloc_pool = nullptr;   // when set, alloc() charges this list (weights: freed on reload)
   NetWeights* weights[2] = {nullptr, nullptr};
   NetWorkspace* ws = nullptr;
   // evaluation outputs indexed by slot
@@ -123,7 +124,7 @@ struct azp_engine {
     void* q = nullptr;
     cudaError_t err = cudaMalloc(&q, count * sizeof(T) + 256);
     if (err != cudaSuccess) { set_error(std::string("cudaMalloc: ") + cudaGetErrorString(err)); return AZP_ERR_CUDA; }
-    allocs.push_back(q);
+    (alloc_pool ? *alloc_pool : allocs).push_back(q);
     *p = (T*)q;
     return AZP_OK;
   }

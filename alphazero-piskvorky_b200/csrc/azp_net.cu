@@ -360,11 +360,12 @@ int azp_net_load(azp_engine* e, int slot, const float* blob, size_t n, bool on_d
   int st = azp_net_parse(e, host.data(), n, net);
   if (st) { e->set_error("weight blob does not match the configured network"); return st; }
   AZP_CUDA(e, cudaDeviceSynchronize());      // no kernel may still read the weights being replaced
-  // (previous device copies stay allocated until the engine is destroyed; loads are rare)
-  delete e->weights[slot];
+  delete e->weights[slot];                   // frees the previous set's device buffers
   e->weights[slot] = new NetWeights();
+  e->alloc_pool = &e->weights[slot]->allocs;
   if (e->cfg.net_dtype == AZP_DTYPE_F32) st = build_f32(e, net, e->weights[slot]);
   else st = azp_umma_build(e, net, e->weights[slot]);
+  e->alloc_pool = nullptr;
   if (st) { delete e->weights[slot]; e->weights[slot] = nullptr; return st; }
   e->weights[slot]->loaded = true;
   return AZP_OK;

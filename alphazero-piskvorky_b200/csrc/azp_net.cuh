@@ -31,6 +31,12 @@ struct DevConv {
 
 struct NetWeights {
   bool loaded = false;
+  std::vector<void*> allocs;    // device buffers owned by this weight set
+  void (*umma_free)(void*) = nullptr;
+  ~NetWeights() {
+    for (void* q : allocs) cudaFree(q);
+    if (umma && umma_free) umma_free(umma);
+  }
   int C = 0, PC = 0, VC = 0;
   size_t dominant_layer = 0;    // index of the conv with the most FLOPs (profiled for the roofline)
   std::vector<DevConv> layers;

@@ -1009,8 +1009,7 @@ int azp_umma_create(azp_engine* e) {
 
 void azp_umma_destroy(azp_engine* e) {
   if (e->ws && e->ws->umma) { delete (UmmaWorkspace*)e->ws->umma; e->ws->umma = nullptr; }
-  for (int i = 0; i < 2; i++)
-    if (e->weights[i] && e->weights[i]->umma) { delete (UmmaWeights*)e->weights[i]->umma; e->weights[i]->umma = nullptr; }
+
 }
 
 template <typename T>
@@ -1029,6 +1028,7 @@ int azp_umma_build(azp_engine* e, const HostNet& net, NetWeights* W) {
   const int A = e->A;
   UmmaWeights* U = new UmmaWeights();
   W->umma = U;
+  W->umma_free = [](void* q) { delete (UmmaWeights*)q; };
   int st;
   // conv1: fp32 [tap][plane][32]
   const HostConv& c1 = net.convs[0];

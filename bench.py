@@ -30,6 +30,9 @@ BOARD, WIN, SIMS, GAMES_PER_GPU, C_PUCT = 15, 5, 800, 2048, 2.0
 METRIC = "mcts_simulations_per_sec"
 UNIT = "sims/s"
 MEAN_GAME_PLIES = 57.3             # measured at this config: profiles/r1_game_length_probe.txt
+# DRAM bytes (read + write) of ONE conv3 launch on 2048 leaves, from `ncu --set full` (cold caches):
+# profiles/r1_ncu_full_conv_umma_final.txt -> 67.31 MB + 1.55 MB; algorithmic = act2 read once (67.1 MB)
+CONV3_DRAM_TRAFFIC_PER_2048_LEAVES = 68.86e6
 FLOPS_PER_LEAF = 42.799e6          # 2*MAC of GomokuNet(15) per position
 
 
@@ -266,6 +269,26 @@ def run_engine_arm(args):
     ce1 = counters()
     e2e_sims = ce1["simulations"] - ce0["simulations"]
 
+    # ---- side measurement: virtual-loss throughput mode (K leaves per game per step), same workload ------
+    vl = None
+    if args.leaves_per_step <= 1 and args.vl_leaves > 1 and E == 1 and not args.no_vl:
+        for eng in engines:
+            eng.close()
+        engines.clear()
+        torch.cuda.empty_cache()
+        eng = az.Engine(board=BOARD, win_length=WIN, games=games, sims=args.sims, c_puct=C_PUCT, net_dtype=dtype,
+                        augment=az.AUGMENT_D4, seed=0, rank=rank, world=world, device=local,
+                        leaves_per_step=args.vl_leaves)
+        eng.load_blob(blob_host.numpy())
+        engines.append(eng)
+        first_flag[0] = True
+        run_all(3)
+        barrier()
+        v0 = eng.counters()["simulations"]
+        vms, _ = run_all(max(2, min(args.steps, 5)))
+        barrier()
+        vl = {"leaves_per_step": args.vl_leaves, "sims": eng.counters()["simulations"] - v0, "ms": vms}
+
     # ---- reduce over ranks: totals summed, time = max ----------------------------------------------
     stats = torch.tensor([ms, e2e_ms, float(sims_done), float(e2e_sims), float(games_done), float(plies_done),
                           float(launches), float(evals_done)], dtype=torch.float64, device="cuda")
@@ -274,6 +297,11 @@ def run_engine_arm(args):
         sm = stats.clone(); dist.all_reduce(sm, op=dist.ReduceOp.SUM)
         ms, e2e_ms = float(mx[0]), float(mx[1])
         sims_done, e2e_sims, games_done, plies_done, launches, evals_done = (float(v) for v in sm[2:8])
+    if vl is not None and world > 1:
+        t = torch.tensor([vl["sims"], vl["ms"]], dtype=torch.float64, device="cuda")
+        tsum = t.clone(); dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
+        tmax = t.clone(); dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        vl["sims"], vl["ms"] = float(tsum[0]), float(tmax[1])
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -315,12 +343,18 @@ def run_engine_arm(args):
         "roofline": {
             "kernel": "conv3 64->128 3x3 (dominant: 77.5% of net FLOPs)",
             "bound": "tensor", "achieved": achieved_tflops, "peak": peak_tf, "unit": "TFLOP/s",
-            "frac": achieved_tflops / peak_tf if peak_tf else None, "traffic": None,
+            "frac": achieved_tflops / peak_tf if peak_tf else None,
+            "traffic": CONV3_DRAM_TRAFFIC_PER_2048_LEAVES * (games / 2048.0) / max(1, E),
+            "traffic_note": "dram read+write bytes per launch from ncu --set full (profiles/r1_ncu_full_conv_umma_final.txt)",
             "peak_source": f"{peaks['source']} sustained bf16 (kernel timed inside a long step)",
             "kernel_ms_per_launch": kms / klaunches if klaunches else None, "kernel_launches": klaunches,
             "kernel_share_of_step": kms / ms / max(1, E) if ms else None,
             "net_tensor_frac_end_to_end": (evals_done / (ms / 1e3)) * FLOPS_PER_LEAF / 1e12 / world / peak_tf,
         },
+        "virtual_loss_mode": None if vl is None else {
+            "note": "same workload with K descents per game per step kept apart by virtual loss (throughput mode; "
+                    "visit counts are NOT reference-identical, the headline value above is the exact mode)",
+            "leaves_per_step": vl["leaves_per_step"], "value": vl["sims"] / (vl["ms"] / 1e3), "unit": UNIT},
         "cpu_baseline": cpu,
     }
     print(json.dumps(line), flush=True)
@@ -341,6 +375,8 @@ def main():
     ap.add_argument("--sims", type=int, default=SIMS)
     ap.add_argument("--leaves-per-step", type=int, default=int(os.environ.get("AZP_BENCH_LEAVES", "1")),
                     help="1 = exact search (reference-identical visit counts); K > 1 = virtual-loss throughput mode")
+    ap.add_argument("--vl-leaves", type=int, default=4, help="K of the virtual-loss side measurement")
+    ap.add_argument("--no-vl", action="store_true")
     ap.add_argument("--cpu-budget", type=float, default=15.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
