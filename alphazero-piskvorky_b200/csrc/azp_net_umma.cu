@@ -293,8 +293,9 @@ __device__ __forceinline__ void umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, u
       ::"r"(tmem_d), "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
 }
 
-constexpr int CONV_THREADS = 352;     // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue (2 per TMEM lane quarter), warp 10 head-GEMM issuer
-constexpr int CONV_THREADS_BITS = 608; // + warps 11..18: conv1-from-bitboards producers of the A operand
+constexpr int CONV_THREADS = 384;     // warp 0 TMA, warps 1 and 11 MMA issuers (even / odd tiles), warps 2..9 epilogue
+                                      // (2 per TMEM lane quarter), warp 10 head-GEMM issuer
+constexpr int CONV_THREADS_BITS = 640; // + warps 12..19: conv1-from-bitboards producers of the A operand
 constexpr int CODES = 256;            // >= 128 + 4P + 2 codes per tile (P <= 24)
 constexpr int HEAD_N = 16;            // fused 1x1 head convs: 6 (or 3) outputs padded to the UMMA minimum N
 
@@ -401,7 +402,7 @@ __global__ void __launch_bounds__(BITS ? CONV_THREADS_BITS : CONV_THREADS, 1) co
         }
       }
     }
-  } else if (BITS && warp >= 11) {
+  } else if (BITS && warp >= 12) {
     // ===== A-operand producers: conv1 (4->32, 3x3) + ReLU from bitboards, written as ONE swizzled stage of
     //       128+2P+2 rows per tile (the nine taps are row-offset descriptors into it) =====
     const int pt = threadIdx.x - CONV_THREADS;               // 0..255
@@ -491,15 +492,19 @@ __global__ void __launch_bounds__(BITS ? CONV_THREADS_BITS : CONV_THREADS, 1) co
       if (lane == 0) mbar_arrive(&full[st]);
       if (args.clk && blockIdx.x == 0 && pt == 0) args.clk[tl * 16 + 6] = clock64();
     }
-  } else if (warp == 1) {
-    // ===== MMA issuer =====
+  } else if (warp == 1 || warp == 11) {
+    // ===== MMA issuers: two threads, even / odd tiles.  A single thread alternates "wait for barriers" and
+    //       "issue" and leaves the tensor pipe idle ~10-30 % of a tile; with two, one waits while the other
+    //       issues (each owns one of the two TMEM accumulators) =====
     if (lane == 0) {
       const uint32_t idesc = umma_idesc(COUT);
       const uint32_t a_base = smem_u32(s_a), w_base = smem_u32(s_w);
+      const int my_parity = warp == 1 ? 0 : 1;
       mbar_wait(wbar, 0);
       tc_fence_after();
       int it = 0, tl = 0;
       for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, tl++) {
+        if ((tl & 1) != my_parity) { it += args.single ? 1 : 3; continue; }
         const int acc = tl & 1;
         const uint32_t acc_ph = (tl >> 1) & 1;
         if (args.clk && blockIdx.x == 0) args.clk[tl * 16 + 2] = clock64();
