@@ -111,15 +111,16 @@ def _cpu_worker(args):
     return runs, time.perf_counter() - t0
 
 
-def cpu_port_throughput(budget_s=15.0, procs=None):
+def cpu_port_throughput(budget_s=15.0, procs=None, board=BOARD, win=WIN, nsims=SIMS):
     import multiprocessing as mp
     cores = procs or os.cpu_count() or 1
     ctx = mp.get_context("spawn")
     with ctx.Pool(cores) as pool:
-        out = pool.map(_cpu_worker, [(1000 + i, budget_s, BOARD, WIN, SIMS) for i in range(cores)])
-    sims = sum(r for r, _ in out) * SIMS
+        out = pool.map(_cpu_worker, [(1000 + i, budget_s, board, win, nsims) for i in range(cores)])
+    sims = sum(r for r, _ in out) * nsims
     wall = max(t for _, t in out)
-    return sims / wall, cores, f"{cores} processes x {budget_s:.0f}s of MCTS.run on 15x15/800 sims, 1 torch thread each"
+    return sims / wall, cores, (f"{cores} processes x {budget_s:.0f}s of MCTS.run on {board}x{board}/{nsims} sims, "
+                                "1 torch thread each")
 
 
 def run_reference_arm(args):
@@ -161,6 +162,7 @@ def run_engine_arm(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     dtype = az.DTYPE_BF16 if args.dtype == "bf16" else az.DTYPE_F32
     games = args.games
+    BOARD, WIN = args.board, args.win          # default: config 3 (15x15 / 5)
     torch.manual_seed(0)
     net = az.GomokuNet(BOARD)
     blob_host = torch.from_numpy(az.flatten_state_dict(net.state_dict())).pin_memory()
@@ -308,21 +310,24 @@ def run_engine_arm(args):
         return
 
     peaks = load_peaks()
+    config3 = (BOARD, WIN, args.sims) == (15, 5, 800)
+    flops_per_leaf = {5: 4.72e6, 9: 15.314e6, 15: FLOPS_PER_LEAF, 19: 69.061e6}.get(BOARD, FLOPS_PER_LEAF)
     value = sims_done / (ms / 1e3)
     achieved_tflops = (kflops / 1e12) / (kms / 1e3) if kms > 0 else 0.0
     peak_tf = peaks["bf16_tflops_sustained"]
     mean_len = None
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
-        v, cores, sample = cpu_port_throughput(budget_s=args.cpu_budget)
+        v, cores, sample = cpu_port_throughput(budget_s=args.cpu_budget, board=BOARD, win=WIN, nsims=args.sims)
         cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": args.dtype, "data": "synthetic",
         "config": {
-            "workload": f"config 3: 15x15 Gomoku, WIN 5, {args.sims} sims/move, {games} concurrent games per GPU "
-                        f"({games * world} total), GomokuNet(15) random init seed 0, Dirichlet root noise on",
+            "workload": f"{'config 3: ' if (BOARD, WIN, args.sims, games) == (15, 5, 800, 2048) else ''}"
+                        f"{BOARD}x{BOARD} Gomoku, WIN {WIN}, {args.sims} sims/move, {games} concurrent games per GPU "
+                        f"({games * world} total), GomokuNet({BOARD}) random init seed 0, Dirichlet root noise on",
             "step": "one move step = every game searches and plays one move",
             "l2": "inputs larger than L2: node table working set is GBs per GPU (no flush needed)",
             "games_per_gpu": games, "sims_per_move": args.sims, "c_puct": C_PUCT, "augment": "d4",
@@ -332,8 +337,8 @@ def run_engine_arm(args):
                            else f"virtual loss, {args.leaves_per_step} leaves per game per step (throughput mode)",
         },
         "games_per_sec": games_done / (ms / 1e3),
-        "games_per_sec_steady_state": (plies_done / (ms / 1e3)) / MEAN_GAME_PLIES,
-        "mean_game_plies": MEAN_GAME_PLIES,
+        "games_per_sec_steady_state": (plies_done / (ms / 1e3)) / MEAN_GAME_PLIES if config3 else None,
+        "mean_game_plies": MEAN_GAME_PLIES if config3 else None,
         "plies_per_sec": plies_done / (ms / 1e3),
         "leaf_evals_per_sec": evals_done / (ms / 1e3),
         "clocks": clocks,
@@ -341,15 +346,15 @@ def run_engine_arm(args):
                 "h2d_bytes_per_step": int(blob_host.numel() * 4), "d2h_bytes_per_step": int(d2h / max(1, args.steps))},
         "gpu_launches": int(launches),
         "roofline": {
-            "kernel": "conv3 64->128 3x3 (dominant: 77.5% of net FLOPs)",
+            "kernel": "conv3 64->128 3x3 (dominant: ~77% of net FLOPs)",
             "bound": "tensor", "achieved": achieved_tflops, "peak": peak_tf, "unit": "TFLOP/s",
             "frac": achieved_tflops / peak_tf if peak_tf else None,
-            "traffic": CONV3_DRAM_TRAFFIC_PER_2048_LEAVES * (games / 2048.0) / max(1, E),
+            "traffic": CONV3_DRAM_TRAFFIC_PER_2048_LEAVES * (games / 2048.0) / max(1, E) if BOARD == 15 else None,
             "traffic_note": "dram read+write bytes per launch from ncu --set full (profiles/r1_ncu_full_conv_umma_final.txt)",
             "peak_source": f"{peaks['source']} sustained bf16 (kernel timed inside a long step)",
             "kernel_ms_per_launch": kms / klaunches if klaunches else None, "kernel_launches": klaunches,
             "kernel_share_of_step": kms / ms / max(1, E) if ms else None,
-            "net_tensor_frac_end_to_end": (evals_done / (ms / 1e3)) * FLOPS_PER_LEAF / 1e12 / world / peak_tf,
+            "net_tensor_frac_end_to_end": (evals_done / (ms / 1e3)) * flops_per_leaf / 1e12 / world / peak_tf,
         },
         "virtual_loss_mode": None if vl is None else {
             "note": "same workload with K descents per game per step kept apart by virtual loss (throughput mode; "
@@ -369,6 +374,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="engine", choices=["engine", "reference"])
     ap.add_argument("--dtype", default=os.environ.get("AZP_BENCH_DTYPE", "bf16"), choices=["bf16", "f32"])
+    ap.add_argument("--board", type=int, default=BOARD)
+    ap.add_argument("--win", type=int, default=WIN)
     ap.add_argument("--games", type=int, default=GAMES_PER_GPU)
     ap.add_argument("--engines", type=int, default=int(os.environ.get("AZP_BENCH_ENGINES", "1")),
                     help="engines per GPU, each with games/engines slots on its own CUDA stream (host thread each)")
