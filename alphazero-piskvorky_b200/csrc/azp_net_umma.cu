@@ -922,8 +922,14 @@ int make_map(azp_engine* e, CUtensorMap* map, const void* base, uint64_t rows, i
   return AZP_OK;
 }
 
+#include "azp_net_tower.cuh"
+
 struct UmmaWorkspace {
   ConvGeom g;
+  bool tower = false;                 // residual tower (config 4) instead of the conv stem
+  __nv_bfloat16* tact[3] = {nullptr, nullptr, nullptr};   // tower: rotating activation buffers [rows][128]
+  CUtensorMap map_tact[3];
+  int t_a_rows = 0, t_a_bytes = 0, smem_tower = 0;
   __nv_bfloat16* act1 = nullptr;      // [rows][32]
   __nv_bfloat16* act2 = nullptr;      // [rows][64]
   __nv_bfloat16* feat = nullptr;      // [G + 128][FK] bf16 head features (rows past G stay zero)
@@ -938,6 +944,13 @@ struct UmmaWorkspace {
   int smem2 = 0, smem3 = 0;
 };
 struct UmmaWeights {
+  // tower
+  std::vector<__nv_bfloat16*> tw;     // per 128->128 conv: [tap][k-chunk][cout][64]
+  std::vector<float*> tb;             // per conv: folded bias [128]
+  std::vector<CUtensorMap> map_tw;
+  std::vector<int> t_residual;        // per conv: add the block input before the ReLU
+  float* tf_bits = nullptr; float* tf_planes = nullptr; float* tf_b = nullptr;   // first conv [27|36][C], [C]
+  float* th_w = nullptr; float* th_b = nullptr;                                   // 1x1 heads [NJ][C], [NJ]
   __nv_bfloat16* w2 = nullptr;        // [9][64][32]
   __nv_bfloat16* w3 = nullptr;        // [9][128][64]
   float* b1 = nullptr; float* b2 = nullptr; float* b3 = nullptr;
@@ -963,20 +976,37 @@ int conv_smem_bytes(int stage_rows) {
 }  // namespace
 
 int azp_umma_create(azp_engine* e) {
-  if (e->cfg.net_kind != AZP_NET_STEM) {
-    e->set_error("bf16 tcgen05 path currently covers the conv-stem GomokuNet; the tower runs on the fp32 path");
+  const bool tower = e->cfg.net_kind == AZP_NET_TOWER;
+  if (tower && e->cfg.tower_channels != TW_C) {
+    e->set_error("the bf16 tcgen05 tower kernel is specialised for 128 channels (other widths: fp32 path)");
     return AZP_ERR_UNSUPPORTED;
   }
   if (e->cfg.board > 23) { e->set_error("board too large for the padded layout"); return AZP_ERR_UNSUPPORTED; }
   UmmaWorkspace* ws = new UmmaWorkspace();
   e->ws->umma = ws;
+  ws->tower = tower;
   ConvGeom& g = ws->g;
   g.B = e->cfg.board; g.A = e->A; g.P = g.B <= 15 ? 16 : 24; g.stride = (g.B + 1) * g.P; g.G = e->slots;
   ws->rows = (size_t)g.G * g.stride + 2 * g.P + TILE_M;        // tail halo + a partial last tile
   int st;
-  if ((st = e->alloc(&ws->act1, ws->rows * 32))) return st;
-  if ((st = e->alloc(&ws->act2, ws->rows * 64))) return st;
-  ws->PKp = (4 * g.A + 7) / 8 * 8; ws->VKp = (2 * g.A + 7) / 8 * 8; ws->FK = ws->PKp + ws->VKp;
+  const int PCh = tower ? 2 : 4, VCh = tower ? 1 : 2;          // head channels (policy, value)
+  if (!tower) {
+    if ((st = e->alloc(&ws->act1, ws->rows * 32))) return st;
+    if ((st = e->alloc(&ws->act2, ws->rows * 64))) return st;
+  } else {
+    ws->t_a_rows = TILE_M + 2 * g.P + 2;
+    ws->t_a_bytes = (ws->t_a_rows + 7) / 8 * 8 * 128;
+    for (int i = 0; i < 3; i++) {
+      if ((st = e->alloc(&ws->tact[i], ws->rows * TW_C))) return st;
+      AZP_CUDA(e, cudaMemset(ws->tact[i], 0, ws->rows * TW_C * sizeof(__nv_bfloat16)));
+      if ((st = make_map(e, &ws->map_tact[i], ws->tact[i], ws->rows, TW_C, ws->t_a_rows, 64))) return st;
+    }
+    ws->smem_tower = 1024 + 4 * ws->t_a_bytes + TW_WST * TW_C * 128 + 24 * 8 + 16 + TW_C * 4 + 64;
+    AZP_CUDA(e, cudaFuncSetAttribute(conv_tower_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ws->smem_tower));
+    AZP_CUDA(e, cudaFuncSetAttribute(tower_first_planes_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)((37 * TW_C + 4 * g.A) * sizeof(float))));
+  }
+  ws->PKp = (PCh * g.A + 7) / 8 * 8; ws->VKp = (VCh * g.A + 7) / 8 * 8; ws->FK = ws->PKp + ws->VKp;
   if ((st = e->alloc(&ws->feat, ((size_t)g.G + TILE_M) * ws->FK))) return st;
   AZP_CUDA(e, cudaMemset(ws->feat, 0, ((size_t)g.G + TILE_M) * ws->FK * sizeof(__nv_bfloat16)));
   if ((st = make_map(e, &ws->map_feat, ws->feat, (uint64_t)g.G + TILE_M, ws->FK, TILE_M, 64))) return st;
@@ -988,6 +1018,11 @@ int azp_umma_create(azp_engine* e) {
     ws->fc_smem = 1024 + ws->fc_stages * stage + 17 * 8 + 16 + (512 + 72 + 640) * 4 + 64;
     if (n_total > 448 || ws->fc_stages < 2) { e->set_error("board too large for the FC head kernel"); return AZP_ERR_UNSUPPORTED; }
   }
+  cudaDeviceProp prop0;
+  AZP_CUDA(e, cudaGetDeviceProperties(&prop0, e->cfg.device));
+  ws->sms = prop0.multiProcessorCount;
+  AZP_CUDA(e, cudaFuncSetAttribute(fc_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ws->fc_smem));
+  if (tower) return AZP_OK;
   AZP_CUDA(e, cudaMemset(ws->act1, 0, ws->rows * 32 * sizeof(__nv_bfloat16)));
   AZP_CUDA(e, cudaMemset(ws->act2, 0, ws->rows * 64 * sizeof(__nv_bfloat16)));
   const int stage_rows = TILE_M + 2 * g.P;
@@ -1025,7 +1060,53 @@ static int up(azp_engine* e, T** dst, const std::vector<T>& src) {
   return AZP_OK;
 }
 
+static int fc_weights_build(azp_engine* e, const HostNet& net, NetWeights* W, UmmaWeights* U);
+
+static int tower_build(azp_engine* e, const HostNet& net, NetWeights* W) {
+  UmmaWeights* U = new UmmaWeights();
+  W->umma = U;
+  W->umma_free = [](void* q) { delete (UmmaWeights*)q; };
+  const int C = TW_C;
+  int st;
+  if (net.convs.size() < 3 || net.convs[0].cin != 4 || net.convs[0].cout != C) {
+    e->set_error("bf16 tower expects a 4->128 first conv and 128->128 residual convs");
+    return AZP_ERR_UNSUPPORTED;
+  }
+  const HostConv& c0 = net.convs[0];
+  std::vector<float> wb(27 * C), wp(36 * C);
+  for (int co = 0; co < C; co++)
+    for (int ci = 0; ci < 4; ci++)
+      for (int t = 0; t < 9; t++) {
+        const float v = c0.w[((size_t)co * 4 + ci) * 9 + t];
+        wp[(t * 4 + ci) * C + co] = v;
+        if (ci < 3) wb[(t * 3 + ci) * C + co] = v;
+      }
+  if ((st = up(e, &U->tf_bits, wb))) return st;
+  if ((st = up(e, &U->tf_planes, wp))) return st;
+  if ((st = up(e, &U->tf_b, c0.b))) return st;
+  const size_t nconv = net.convs.size() - 1;
+  U->tw.resize(nconv); U->tb.resize(nconv); U->map_tw.resize(nconv); U->t_residual.resize(nconv);
+  for (size_t i = 0; i < nconv; i++) {
+    const HostConv& c = net.convs[i + 1];
+    if (c.cin != C || c.cout != C) { e->set_error("tower conv is not 128->128"); return AZP_ERR_UNSUPPORTED; }
+    std::vector<__nv_bfloat16> w((size_t)9 * 2 * C * 64);
+    for (int t = 0; t < 9; t++)
+      for (int kc = 0; kc < 2; kc++)
+        for (int co = 0; co < C; co++)
+          for (int k = 0; k < 64; k++)
+            w[(((size_t)t * 2 + kc) * C + co) * 64 + k] = __float2bfloat16(c.w[((size_t)co * C + kc * 64 + k) * 9 + t]);
+    if ((st = up(e, &U->tw[i], w))) return st;
+    if ((st = up(e, &U->tb[i], c.b))) return st;
+    if ((st = make_map(e, &U->map_tw[i], U->tw[i], (uint64_t)9 * 2 * C, 64, C))) return st;
+    U->t_residual[i] = c.residual;
+  }
+  if ((st = up(e, &U->th_w, net.head_w))) return st;
+  if ((st = up(e, &U->th_b, net.head_b))) return st;
+  return fc_weights_build(e, net, W, U);
+}
+
 int azp_umma_build(azp_engine* e, const HostNet& net, NetWeights* W) {
+  if (e->cfg.net_kind == AZP_NET_TOWER) return tower_build(e, net, W);
   if (net.convs.size() != 3 || net.convs[0].cout != 32 || net.convs[1].cout != 64 || net.convs[2].cout != 128) {
     e->set_error("bf16 path expects the 4->32->64->128 stem");
     return AZP_ERR_UNSUPPORTED;
@@ -1087,24 +1168,80 @@ int azp_umma_build(azp_engine* e, const HostNet& net, NetWeights* W) {
   if ((st = up(e, &U->head_w16, hw))) return st;
   if ((st = up(e, &U->head_b8, hb))) return st;
   if ((st = make_map(e, &U->map_hw, U->head_w16, HEAD_N, net.C, HEAD_N, 64))) return st;
-  {
-    UmmaWorkspace* ws = (UmmaWorkspace*)e->ws->umma;
-    const int PK = net.PC * A, VK = net.VC * A;
-    if (net.PC != 4 || net.VC != 2) { e->set_error("bf16 path expects 4 policy / 2 value head channels"); return AZP_ERR_UNSUPPORTED; }
-    std::vector<__nv_bfloat16> wp((size_t)A * ws->PKp, __float2bfloat16(0.f)), wv((size_t)64 * ws->VKp, __float2bfloat16(0.f));
-    for (int a = 0; a < A; a++) for (int k = 0; k < PK; k++) wp[(size_t)a * ws->PKp + k] = __float2bfloat16(net.pfc_w[(size_t)a * PK + k]);
-    for (int j = 0; j < 64; j++) for (int k = 0; k < VK; k++) wv[(size_t)j * ws->VKp + k] = __float2bfloat16(net.vfc1_w[(size_t)j * VK + k]);
-    if ((st = up(e, &U->wp16, wp))) return st;
-    if ((st = up(e, &U->wv16, wv))) return st;
-    if ((st = make_map(e, &U->map_wp, U->wp16, A, ws->PKp, 64, 64))) return st;
-    if ((st = make_map(e, &U->map_wv, U->wv16, 64, ws->VKp, 64, 64))) return st;
-  }
+  return fc_weights_build(e, net, W, U);
+}
+
+// policy_fc / value_fc1 as bf16 [out][K padded to 8] (B operands of fc_umma_kernel) + fp32 biases / tails
+static int fc_weights_build(azp_engine* e, const HostNet& net, NetWeights* W, UmmaWeights* U) {
+  UmmaWorkspace* ws = (UmmaWorkspace*)e->ws->umma;
+  const int A = e->A;
+  const int PK = net.PC * A, VK = net.VC * A;
+  int st;
+  if ((PK + 7) / 8 * 8 != ws->PKp || (VK + 7) / 8 * 8 != ws->VKp) { e->set_error("head channel counts do not match the configured net"); return AZP_ERR_UNSUPPORTED; }
+  std::vector<__nv_bfloat16> wp((size_t)A * ws->PKp, __float2bfloat16(0.f)), wv((size_t)64 * ws->VKp, __float2bfloat16(0.f));
+  for (int a = 0; a < A; a++) for (int k = 0; k < PK; k++) wp[(size_t)a * ws->PKp + k] = __float2bfloat16(net.pfc_w[(size_t)a * PK + k]);
+  for (int j = 0; j < 64; j++) for (int k = 0; k < VK; k++) wv[(size_t)j * ws->VKp + k] = __float2bfloat16(net.vfc1_w[(size_t)j * VK + k]);
+  if ((st = up(e, &U->wp16, wp))) return st;
+  if ((st = up(e, &U->wv16, wv))) return st;
+  if ((st = make_map(e, &U->map_wp, U->wp16, A, ws->PKp, 64, 64))) return st;
+  if ((st = make_map(e, &U->map_wv, U->wv16, 64, ws->VKp, 64, 64))) return st;
   if ((st = up(e, &W->pfc_b, net.pfc_b))) return st;
   if ((st = up(e, &W->vfc1_b, net.vfc1_b))) return st;
   if ((st = up(e, &W->vfc2_w, net.vfc2_w))) return st;
   if ((st = up(e, &W->vfc2_b, net.vfc2_b))) return st;
   W->C = net.C; W->PC = net.PC; W->VC = net.VC;
   return AZP_OK;
+}
+
+static int launch_fc(azp_engine* e, NetWeights* W, const int32_t* count_dev, int count_host, int back, float* logits,
+                     float* policy, float* value, int out_by_index, cudaStream_t s);
+
+// residual tower: first conv -> 2 convs per block (the second adds the block input) -> 1x1 heads -> FC
+static int run_tower(azp_engine* e, NetWeights* W, const int32_t* count_dev, int count_host, int back, int n_planes,
+                     const float* planes, float* logits, float* policy, float* value, int out_by_index, cudaStream_t s) {
+  UmmaWorkspace* ws = (UmmaWorkspace*)e->ws->umma;
+  UmmaWeights* U = (UmmaWeights*)W->umma;
+  const ConvGeom& g = ws->g;
+  const int zmax = count_dev ? g.G : count_host;
+  if (zmax <= 0) return AZP_OK;
+  const int C = TW_C;
+  const int grid1 = zmax < 4 * ws->sms ? zmax : 4 * ws->sms;
+  if (planes) {
+    tower_first_planes_kernel<<<grid1, 256, (37 * C + 4 * g.A) * sizeof(float), s>>>(g, C, n_planes, planes, U->tf_planes,
+                                                                                    U->tf_b, ws->tact[0]);
+  } else {
+    const size_t sm = (size_t)28 * C * sizeof(float);
+    AZP_DISPATCH_NW(e->NW, tower_first_bits_kernel, grid1, 256, sm, s, g, C, e->tv.leaf_x, e->tv.leaf_o, e->tv.leaf_tm,
+                    e->tv.leaf_last, U->tf_bits, U->tf_b, ws->tact[0], count_dev, count_host, back);
+  }
+  azp_count_launch();
+  const int max_tiles = (int)(((long long)zmax * g.stride + TILE_M - 1) / TILE_M);
+  const int max_pairs = (max_tiles + 1) / 2;
+  const int grid = max_pairs < ws->sms ? max_pairs : ws->sms;
+  int xi = 0;                               // buffer holding the current block input x; y = xi+1, block output = xi+2 (mod 3)
+  e->prof_flops_per_board = 2.0 * 9.0 * C * C * g.A;
+  for (size_t i = 0; i < U->tw.size(); i++) {
+    const bool second = U->t_residual[i] != 0;       // second conv of a block: relu(bn2(conv2(y)) + x)
+    TowerArgs ta;
+    ta.g = g; ta.bias = U->tb[i]; ta.count_dev = count_dev; ta.count_host = count_host; ta.back = back;
+    ta.a_rows = ws->t_a_rows; ta.a_bytes = ws->t_a_bytes;
+    const int in_i = second ? (xi + 1) % 3 : xi;
+    const int out_i = second ? (xi + 2) % 3 : (xi + 1) % 3;
+    ta.residual = second ? ws->tact[xi] : nullptr;
+    ta.out = ws->tact[out_i];
+    azp_prof_begin(e, count_dev, count_host, s);
+    conv_tower_kernel<<<grid, TW_THREADS, ws->smem_tower, s>>>(ws->map_tact[in_i], U->map_tw[i], ta);
+    azp_count_launch();
+    azp_prof_end(e, s);
+    if (second) xi = out_i;
+  }
+  const int NJ = W->PC + W->VC;
+  const long long total = (long long)zmax * g.A;
+  const int hgrid = (int)((total + 255) / 256 < 4096 ? (total + 255) / 256 : 4096);
+  tower_heads_kernel<<<hgrid, 256, (NJ * C + NJ) * sizeof(float), s>>>(g, C, NJ, W->PC, ws->PKp, ws->FK, ws->tact[xi], U->th_w,
+                                                                      U->th_b, ws->feat, count_dev, count_host, back);
+  azp_count_launch();
+  return launch_fc(e, W, count_dev, count_host, back, logits, policy, value, out_by_index, s);
 }
 
 // conv2 + conv3(+heads) + FC on rows already holding act1
@@ -1144,6 +1281,15 @@ static int run_trunk(azp_engine* e, NetWeights* W, const int32_t* count_dev, int
       a3.single ? ws->map_act2_s : ws->map_act2, U->map_w3, U->map_hw, a3);
   azp_count_launch();
   azp_prof_end(e, s);
+  return launch_fc(e, W, count_dev, count_host, back, logits, policy, value, out_by_index, s);
+}
+
+static int launch_fc(azp_engine* e, NetWeights* W, const int32_t* count_dev, int count_host, int back, float* logits,
+                     float* policy, float* value, int out_by_index, cudaStream_t s) {
+  UmmaWorkspace* ws = (UmmaWorkspace*)e->ws->umma;
+  UmmaWeights* U = (UmmaWeights*)W->umma;
+  const ConvGeom& g = ws->g;
+  const int zmax = count_dev ? g.G : count_host;
   FcArgs fa;
   const int n_total = (g.A + 15) / 16 * 16;
   fa.job[0].n_total = n_total; fa.job[0].n_first = n_total <= 256 ? n_total : 192; fa.job[0].n_valid = g.A;
@@ -1166,6 +1312,7 @@ int azp_umma_eval_leaves(azp_engine* e, NetWeights* W, const int32_t* count_dev,
   const ConvGeom& g = ws->g;
   const int zmax = count_dev ? g.G : count_host;
   if (zmax <= 0) return AZP_OK;
+  if (ws->tower) return run_tower(e, W, count_dev, count_host, back, 0, nullptr, nullptr, e->d_policy, e->d_value, 0, s);
   static int fuse = -1;
   if (fuse < 0) { const char* v = getenv("AZP_FUSE_CONV1"); fuse = v ? atoi(v) : 0; }
   if (!fuse) {
@@ -1220,6 +1367,7 @@ int azp_umma_eval_planes(azp_engine* e, NetWeights* W, int n, const float* plane
   UmmaWorkspace* ws = (UmmaWorkspace*)e->ws->umma;
   UmmaWeights* U = (UmmaWeights*)W->umma;
   const ConvGeom& g = ws->g;
+  if (ws->tower) return run_tower(e, W, nullptr, n, 0, n, planes, logits, policy, value, 1, s);
   const int grid = n < 4 * ws->sms ? n : 4 * ws->sms;
   conv1_planes_kernel<<<grid, 256, 4 * g.A * sizeof(float), s>>>(g, n, planes, U->w1_planes, U->b1, ws->act1);
   azp_count_launch();

@@ -164,8 +164,10 @@ def run_engine_arm(args):
     games = args.games
     BOARD, WIN = args.board, args.win          # default: config 3 (15x15 / 5)
     torch.manual_seed(0)
-    net = az.GomokuNet(BOARD)
-    blob_host = torch.from_numpy(az.flatten_state_dict(net.state_dict())).pin_memory()
+    tower = args.net == "tower"
+    net = az.GomokuTowerNet(BOARD, 128, 10) if tower else az.GomokuNet(BOARD)
+    net_kw = dict(net_kind=az.NET_TOWER, tower_blocks=10, tower_channels=128) if tower else {}
+    blob_host = torch.from_numpy(az.flatten_state_dict(net.state_dict(), az.NET_TOWER if tower else az.NET_STEM, 10)).pin_memory()
 
     import threading
     E = max(1, args.engines)
@@ -176,7 +178,7 @@ def run_engine_arm(args):
     for k in range(E):
         eng = az.Engine(board=BOARD, win_length=WIN, games=games // E, sims=args.sims, c_puct=C_PUCT, net_dtype=dtype,
                         augment=az.AUGMENT_D4, seed=0, rank=rank * E + k, world=world * E, device=local,
-                        leaves_per_step=args.leaves_per_step)
+                        leaves_per_step=args.leaves_per_step, **net_kw)
         eng.load_blob(blob_host.numpy())
         engines.append(eng)
         streams.append(torch.cuda.Stream())
@@ -280,7 +282,7 @@ def run_engine_arm(args):
         torch.cuda.empty_cache()
         eng = az.Engine(board=BOARD, win_length=WIN, games=games, sims=args.sims, c_puct=C_PUCT, net_dtype=dtype,
                         augment=az.AUGMENT_D4, seed=0, rank=rank, world=world, device=local,
-                        leaves_per_step=args.vl_leaves)
+                        leaves_per_step=args.vl_leaves, **net_kw)
         eng.load_blob(blob_host.numpy())
         engines.append(eng)
         first_flag[0] = True
@@ -312,6 +314,8 @@ def run_engine_arm(args):
     peaks = load_peaks()
     config3 = (BOARD, WIN, args.sims) == (15, 5, 800)
     flops_per_leaf = {5: 4.72e6, 9: 15.314e6, 15: FLOPS_PER_LEAF, 19: 69.061e6}.get(BOARD, FLOPS_PER_LEAF)
+    if tower:
+        flops_per_leaf = 1329.6e6 * (BOARD * BOARD / 225.0)      # 10x128 tower at 15x15
     value = sims_done / (ms / 1e3)
     achieved_tflops = (kflops / 1e12) / (kms / 1e3) if kms > 0 else 0.0
     peak_tf = peaks["bf16_tflops_sustained"]
@@ -327,7 +331,8 @@ def run_engine_arm(args):
         "config": {
             "workload": f"{'config 3: ' if (BOARD, WIN, args.sims, games) == (15, 5, 800, 2048) else ''}"
                         f"{BOARD}x{BOARD} Gomoku, WIN {WIN}, {args.sims} sims/move, {games} concurrent games per GPU "
-                        f"({games * world} total), GomokuNet({BOARD}) random init seed 0, Dirichlet root noise on",
+                        f"({games * world} total), {'residual tower 10x128' if tower else f'GomokuNet({BOARD})'} "
+                        f"random init seed 0, Dirichlet root noise on",
             "step": "one move step = every game searches and plays one move",
             "l2": "inputs larger than L2: node table working set is GBs per GPU (no flush needed)",
             "games_per_gpu": games, "sims_per_move": args.sims, "c_puct": C_PUCT, "augment": "d4",
@@ -346,10 +351,12 @@ def run_engine_arm(args):
                 "h2d_bytes_per_step": int(blob_host.numel() * 4), "d2h_bytes_per_step": int(d2h / max(1, args.steps))},
         "gpu_launches": int(launches),
         "roofline": {
-            "kernel": "conv3 64->128 3x3 (dominant: ~77% of net FLOPs)",
+            "kernel": ("tower conv 128->128 3x3, streamed weights (20 launches per eval, ~99% of net FLOPs)" if tower
+                       else "conv3 64->128 3x3 (dominant: ~77% of net FLOPs)"),
             "bound": "tensor", "achieved": achieved_tflops, "peak": peak_tf, "unit": "TFLOP/s",
             "frac": achieved_tflops / peak_tf if peak_tf else None,
-            "traffic": CONV3_DRAM_TRAFFIC_PER_2048_LEAVES * (games / 2048.0) / max(1, E) if BOARD == 15 else None,
+            "traffic": (CONV3_DRAM_TRAFFIC_PER_2048_LEAVES * (games / 2048.0) / max(1, E)
+                        if BOARD == 15 and not tower else None),
             "traffic_note": "dram read+write bytes per launch from ncu --set full (profiles/r1_ncu_full_conv_umma_final.txt)",
             "peak_source": f"{peaks['source']} sustained bf16 (kernel timed inside a long step)",
             "kernel_ms_per_launch": kms / klaunches if klaunches else None, "kernel_launches": klaunches,
@@ -374,6 +381,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="engine", choices=["engine", "reference"])
     ap.add_argument("--dtype", default=os.environ.get("AZP_BENCH_DTYPE", "bf16"), choices=["bf16", "f32"])
+    ap.add_argument("--net", default="stem", choices=["stem", "tower"], help="tower = BASELINE config 4 (10 blocks x 128)")
     ap.add_argument("--board", type=int, default=BOARD)
     ap.add_argument("--win", type=int, default=WIN)
     ap.add_argument("--games", type=int, default=GAMES_PER_GPU)

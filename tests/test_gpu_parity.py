@@ -219,6 +219,49 @@ def test_net_bf16_tcgen05_vs_reference_golden(az, golden, size):
     eng.close()
 
 
+def test_net_bf16_tower_tcgen05_vs_oracle(az):
+    """Config-4 residual tower on the streamed-weight tcgen05 kernel vs the oracle tower (fp32 torch; parity
+    unpinned by the reference beyond the key layout).  21 bf16 layers: tolerance 2e-2 on policy/value, logits
+    relative to their scale."""
+    size, C, NB, n = 15, 128, 4, 150
+    params = onet.synthetic_tower_params(size, seed=5, channels=C, blocks=NB)
+    eng = az.Engine(board=size, win_length=5, games=160, sims=2, net_kind=az.NET_TOWER, tower_blocks=NB,
+                    tower_channels=C, net_dtype=az.DTYPE_BF16)
+    eng.load_state_dict(params)
+    rs = np.random.RandomState(0)
+    occ = rs.random_sample((n, size, size))
+    x = np.zeros((n, 4, size, size), dtype=np.float32)
+    x[:, 0], x[:, 1] = occ < 0.2, (occ >= 0.2) & (occ < 0.4)
+    x[np.arange(n), 2, rs.randint(size, size=n), rs.randint(size, size=n)] = 1
+    logits, policy, value = eng.net_forward(torch.from_numpy(x).cuda())
+    ol, ov = onet.tower_forward(params, x, blocks=NB)
+    scale = max(1.0, float(ol.abs().max()))
+    assert float((logits.cpu() - ol).abs().max()) <= 3e-2 * scale
+    assert float((value.cpu() - ov.reshape(-1)).abs().max()) <= 2e-2
+    assert float((policy.cpu() - torch.softmax(ol, 1)).abs().max()) <= 2e-2
+    # leaf path (bitboards in) == planes path, so the search sees the same numbers
+    states = []
+    for i in range(8):
+        s0 = gomoku.State(size, 5)
+        for a in synth.random_playout(size, 5, plies=3 + 4 * i, seed=70 + i):
+            s0 = s0.play(a)
+        states.append(s0)
+    batch = _batch(az, [s0.board for s0 in states], [s0.to_move for s0 in states], [_last_index(s0) for s0 in states], 5)
+    eng2 = az.Engine(board=size, win_length=5, games=8, sims=16, net_kind=az.NET_TOWER, tower_blocks=NB,
+                     tower_channels=C, net_dtype=az.DTYPE_BF16)
+    eng2.load_state_dict(params)
+    visits = eng2.search(batch.x, batch.o, batch.to_move, batch.last).cpu().numpy()
+
+    def evaluator(state):
+        _, pol, val = eng2.net_forward(torch.from_numpy(state.planes()).unsqueeze(0).cuda())
+        return pol[0].cpu().numpy().reshape(size, size), float(val[0].item())
+
+    for i, s0 in enumerate(states[:4]):
+        ref = omcts.Search(evaluator, 16, 2.0).run(s0, 1.0, forced_action=s0.legal_actions()[0])
+        assert np.array_equal(visits[i].reshape(size, size), ref.visits), i
+    eng.close(); eng2.close()
+
+
 def test_net_bf16_large_batch_and_scaled_weights(az):
     """Many tiles per CTA, both accumulator stages, O(1) activations: relative error stays at bf16 level."""
     size, n = 15, 1500
