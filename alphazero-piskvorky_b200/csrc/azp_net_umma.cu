@@ -111,37 +111,47 @@ struct ConvGeom {
 };
 
 // ---- conv1 from bitboards (SIMT) ------------------------------------------------------------------------
-// One block per slot, one thread per padded position.  Inputs are 0/1 planes (games.py:86-129; plane 3
-// is all zero), so the convolution is a sum of at most 27 weight rows.  w: [tap][plane(3)][32] fp32.
+// One block per slot; work item = (padded position, 8 output channels).  Inputs are 0/1 planes
+// (games.py:86-129; plane 3 is all zero), so conv1 needs no multiplies: for every input plane and kernel row
+// the three column taps form a 3-bit pattern that indexes a table of pre-summed weight rows
+// (tab: [plane(3)][ky][pattern(8)][32] fp32).  Same association order as conv1_planes_kernel, so the leaf
+// path and the float-planes path agree bit for bit.
 template <int NWT>
 __global__ void __launch_bounds__(256) conv1_bits_kernel(ConvGeom g, const uint64_t* __restrict__ lx,
                                                          const uint64_t* __restrict__ lo,
                                                          const uint8_t* __restrict__ ltm,
                                                          const int16_t* __restrict__ llast,
-                                                         const float* __restrict__ w, const float* __restrict__ bias,
+                                                         const float* __restrict__ tab, const float* __restrict__ bias,
                                                          __nv_bfloat16* __restrict__ act1,
                                                          const int32_t* __restrict__ count_dev, int count_host,
                                                          int back) {
   const int count = count_dev ? *count_dev : count_host;
-  __shared__ float sw[27 * 32];
+  __shared__ __align__(16) float st[72 * 32];
   __shared__ float sb[32];
-  __shared__ int8_t cells[AZP_MAX_BOARD * AZP_MAX_BOARD + 3];
-  for (int i = threadIdx.x; i < 27 * 32; i += blockDim.x) sw[i] = w[i];
+  __shared__ int16_t codes[AZP_MAX_BOARD * AZP_MAX_BOARD + 3];
+  for (int i = threadIdx.x; i < 72 * 32; i += blockDim.x) st[i] = tab[i];
   if (threadIdx.x < 32) sb[threadIdx.x] = bias[threadIdx.x];
   for (int bi = blockIdx.x; bi < count; bi += gridDim.x) {
     const int slot = back ? g.G - 1 - bi : bi;
     __syncthreads();
     const bool xm = ltm[slot] == 1;
     const int last = llast[slot];
+    const uint64_t* own = (xm ? lx : lo) + (size_t)slot * NWT;
+    const uint64_t* opp = (xm ? lo : lx) + (size_t)slot * NWT;
     for (int a = threadIdx.x; a < g.A; a += blockDim.x) {
-      uint64_t wx = lx[(size_t)slot * NWT + (a >> 6)], wo = lo[(size_t)slot * NWT + (a >> 6)];
-      bool isx = (wx >> (a & 63)) & 1, iso = (wo >> (a & 63)) & 1;
-      int v = ((xm ? isx : iso) ? 1 : 0) | ((xm ? iso : isx) ? 2 : 0) | (a == last ? 4 : 0);
-      cells[a] = (int8_t)v;
+      const int c = a % g.B;
+      int code = 0;
+#pragma unroll
+      for (int kx = 0; kx < 3; kx++) {
+        const int cc = c + kx - 1, aa = a + kx - 1;
+        if (cc < 0 || cc >= g.B) continue;
+        const int b0 = (int)((own[aa >> 6] >> (aa & 63)) & 1), b1 = (int)((opp[aa >> 6] >> (aa & 63)) & 1);
+        code |= (b0 << kx) | (b1 << (3 + kx)) | ((aa == last ? 1 : 0) << (6 + kx));
+      }
+      codes[a] = (int16_t)code;
     }
     __syncthreads();
-    // 4 threads per padded position, 8 output channels each: one 16-byte store per thread, 64 contiguous
-    // bytes per position
+    // 4 threads per padded position, 8 output channels each: one 16-byte store per thread
     for (int item = threadIdx.x; item < g.stride * 4; item += blockDim.x) {
       const int pos = item >> 2, cg = item & 3;
       const int y = pos / g.P, x = pos % g.P;
@@ -154,18 +164,22 @@ __global__ void __launch_bounds__(256) conv1_bits_kernel(ConvGeom g, const uint6
       float acc[8];
 #pragma unroll
       for (int j = 0; j < 8; j++) acc[j] = sb[cg * 8 + j];
+      int code3[3];
 #pragma unroll
-      for (int tap = 0; tap < 9; tap++) {
-        const int rr = r + tap / 3 - 1, cc = c + tap % 3 - 1;
-        if (rr < 0 || rr >= g.B || cc < 0 || cc >= g.B) continue;
-        const int v = cells[rr * g.B + cc];
-        if (!v) continue;
+      for (int ky = 0; ky < 3; ky++) {
+        const int rr = r + ky - 1;
+        code3[ky] = (rr >= 0 && rr < g.B) ? codes[rr * g.B + c] : 0;
+      }
 #pragma unroll
-        for (int pl = 0; pl < 3; pl++) {
-          if (!(v & (1 << pl))) continue;
-          const float* wr = sw + (tap * 3 + pl) * 32 + cg * 8;
+      for (int pl = 0; pl < 3; pl++) {
 #pragma unroll
-          for (int j = 0; j < 8; j++) acc[j] += wr[j];
+        for (int ky = 0; ky < 3; ky++) {
+          const int pat = (code3[ky] >> (3 * pl)) & 7;
+          if (pl == 2 && !pat) continue;                // the last-move plane is almost always empty here
+          const float4* tr = reinterpret_cast<const float4*>(st + ((pl * 3 + ky) * 8 + pat) * 32 + cg * 8);
+          const float4 w0 = tr[0], w1 = tr[1];          // pattern 0 selects an all-zero row: x + 0.0f == x
+          acc[0] += w0.x; acc[1] += w0.y; acc[2] += w0.z; acc[3] += w0.w;
+          acc[4] += w1.x; acc[5] += w1.y; acc[6] += w1.z; acc[7] += w1.w;
         }
       }
       uint32_t packed[4];
@@ -1318,7 +1332,7 @@ int azp_umma_eval_leaves(azp_engine* e, NetWeights* W, const int32_t* count_dev,
   if (!fuse) {
     const int grid = zmax < 4 * ws->sms ? zmax : 4 * ws->sms;
     AZP_DISPATCH_NW(e->NW, conv1_bits_kernel, grid, 256, 0, s, g, e->tv.leaf_x, e->tv.leaf_o, e->tv.leaf_tm,
-                    e->tv.leaf_last, U->w1_bits, U->b1, ws->act1, count_dev, count_host, back);
+                    e->tv.leaf_last, U->w1_tab, U->b1, ws->act1, count_dev, count_host, back);
     azp_count_launch();
   }
   return run_trunk(e, W, count_dev, count_host, back, nullptr, e->d_policy, e->d_value, 0, /*from_bits=*/fuse != 0, s);

@@ -1,0 +1,67 @@
+"""Multi-GPU flow of SURVEY section 8(e) under torchrun (one process per GPU, NCCL over NVLink):
+   1. games sharded by global id, each rank self-plays its block (no collective in the simulation loop);
+   2. ragged all-gather of the generated example slabs into every rank's replay buffer;
+   3. arena new-vs-best sharded the same way, W/L/D all-reduced, promotion rule;
+   4. broadcast of the promoted weights as one flat fp32 blob and reload on every rank.
+Checks shard invariance against a single-rank run of the same global game ids on rank 0."""
+import os, sys, json, time
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np, torch, torch.distributed as dist
+import alphazero_piskvorky_b200 as az
+from alphazero_piskvorky_b200 import dist as azd
+
+rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+torch.cuda.set_device(local)
+dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+B, WIN, SIMS, GAMES = 9, 5, 64, 64
+torch.manual_seed(0); best = az.GomokuNet(B)
+torch.manual_seed(1); new = az.GomokuNet(B)
+
+eng = az.Engine(board=B, win_length=WIN, games=GAMES // world, sims=SIMS, net_dtype=az.DTYPE_BF16,
+                augment=az.AUGMENT_NONE, seed=3, rank=rank, world=world, device=local)
+eng.load_state_dict(best.state_dict())
+t0 = time.time()
+planes, pi, z = eng.selfplay_all(GAMES)                       # this rank's block of the 64 global games
+gp, gpi, gz = azd.all_gather_examples(planes, pi, z)          # every rank now holds all positions
+buf = az.ReplayBuffer(capacity=40_000)
+buf.extend_device(gp, gpi, gz)
+t_selfplay = time.time() - t0
+
+ok_invariance = None
+if rank == 0:                                                 # same global ids on ONE rank: identical multiset
+    solo = az.Engine(board=B, win_length=WIN, games=GAMES, sims=SIMS, net_dtype=az.DTYPE_BF16,
+                     augment=az.AUGMENT_NONE, seed=3, rank=0, world=1, device=local)
+    solo.load_state_dict(best.state_dict())
+    sp, spi, sz = solo.selfplay_all(GAMES)
+    key = lambda P, Q, Z: sorted((P[i].cpu().numpy().tobytes(), Q[i].cpu().numpy().tobytes(), int(Z[i])) for i in range(len(Z)))
+    ok_invariance = key(sp, spi, sz) == key(gp, gpi, gz)
+    solo.close()
+
+# arena: candidate (slot 0, X) vs best (slot 1, O), 32 games sharded over the ranks
+arena = az.Engine(board=B, win_length=WIN, games=max(1, 32 // world), sims=SIMS, net_dtype=az.DTYPE_BF16, seed=5,
+                  rank=rank, world=world, device=local)
+arena.load_state_dict(new.state_dict(), slot=0)
+arena.load_state_dict(best.state_dict(), slot=1)
+arena.set_temperature_table([0.3 * np.exp(-s / 4) for s in range(B * B + 1)])
+w, l, d = arena.arena(32)
+W, L, D = azd.all_reduce_wld(w, l, d)
+win_rate = (W + 0.5 * D) / (W + L + D)
+promote = az.should_promote(win_rate)
+
+# broadcast the winner's weights from rank 0 and reload them on the device everywhere
+winner = new if promote else best
+blob = torch.from_numpy(az.flatten_state_dict(winner.state_dict())).cuda() if rank == 0 else \
+    torch.zeros(eng.weight_count(), device="cuda")
+azd.broadcast_weights(blob, src=0)
+eng.load_blob(blob)
+x = torch.zeros((1, 4, B, B), device="cuda"); x[0, 0, 4, 4] = 1
+_, _, v = eng.net_forward(x)
+vs = [torch.zeros_like(v) for _ in range(world)]
+dist.all_gather(vs, v)
+same_value = all(torch.equal(vs[0], q) for q in vs)
+if rank == 0:
+    print(json.dumps({"world": world, "positions_total": int(gz.numel()), "positions_this_rank": int(z.numel()),
+                      "replay_len": buf.device_len(), "shard_invariant": ok_invariance, "arena_wld": [W, L, D],
+                      "win_rate": win_rate, "promote": bool(promote), "weights_identical_after_broadcast": bool(same_value),
+                      "selfplay_seconds": round(t_selfplay, 2)}))
+dist.destroy_process_group()
