@@ -8,11 +8,11 @@
 // Row group 0 and column 0 of every row group (and columns > B) are ZERO and double as the bottom /
 // right halo of the previous row group / board, so a 3x3 tap (dy,dx) is the constant row offset
 // dy*P + dx and the implicit-GEMM A operand of a tap is a plain [128 rows x C] window of that matrix.
-// P is a multiple of 8, so the three dy windows of one dx-shifted 160-row TMA load all start on a
-// swizzle-atom boundary: 3 TMA loads (not 9) feed the 9 taps of a 128-row output tile.
+// UMMA shared-memory descriptors may start at ANY row of a swizzled tile (the swizzle is a function of absolute
+// address bits), so ONE TMA box of 128+2P+2 rows per 128-row output tile feeds all nine taps.
 //
 // Pipeline per step (leaf batch of n positions):
-//   conv1_bits_kernel   bitboards -> act1 [rows][32]      SIMT (inputs are 0/1: K = 27 adds)
+//   conv1_bits_kernel   bitboards -> act1 [rows][32]      SIMT (inputs are 0/1: pattern-indexed tables of pre-summed weights)
 //   conv_umma<32,64>    act1 -> act2 [rows][64]           tcgen05, bias+ReLU+pad-zero epilogue
 //   conv_umma<64,128>   act2 -> head features [n][6][A]   tcgen05, epilogue = bias+ReLU + both 1x1 head
 //                                                         convs (act3 never leaves the SM)
