@@ -3,6 +3,7 @@
 #include <atomic>
 #include <mutex>
 #include <string.h>
+#include <stdlib.h>
 
 // ---- process-wide bookkeeping ------------------------------------------------------------------------
 static std::atomic<uint64_t> g_launches{0};
@@ -123,6 +124,7 @@ static int create_impl(azp_engine* e) {
   AZP_CUDA(e, cudaMemcpy(e->d_temperature, T.data(), T.size() * sizeof(double), cudaMemcpyHostToDevice));
   e->n_temperature = (int)T.size();
   if ((st = azp_net_create(e))) return st;
+  { const char* v = getenv("AZP_GRAPH"); e->use_graph = v ? atoi(v) != 0 : true; }
   AZP_CUDA(e, cudaDeviceSynchronize());
   return AZP_OK;
 }
@@ -170,6 +172,8 @@ extern "C" void azp_destroy(azp_engine* e) {
   cudaSetDevice(e->cfg.device);
   cudaDeviceSynchronize();
   for (cudaEvent_t ev : e->prof_events) cudaEventDestroy(ev);
+  if (e->graph_exec) cudaGraphExecDestroy(e->graph_exec);
+  for (cudaEvent_t ev : e->gprof_ev) if (ev) cudaEventDestroy(ev);
   if (e->cfg.net_dtype == AZP_DTYPE_BF16) azp_umma_destroy(e);
   azp_net_destroy(e);
   for (void* p : e->allocs) cudaFree(p);
@@ -268,22 +272,72 @@ extern "C" int azp_root_visits(azp_engine* e, int32_t* visits, void* stream) {
 
 // one move worth of search for the first n slots with the engine's own net(s):
 // root eval -> root expand (+noise) -> S x (select -> net -> expand+backup)
+// one simulation step for all games: K descents -> leaf batch -> net -> expand + backup
+static int sim_step(azp_engine* e, int n, int two_nets, int parity, cudaStream_t s) {
+  int st;
+  TreeView& tv = e->tv;
+  if ((st = azp_tree_select(e, n, 1, parity, s))) return st;
+  if ((st = azp_net_eval_leaves(e, 0, tv.n_leaves + parity * 2 + 0, 0, 0, s))) return st;
+  if (two_nets && (st = azp_net_eval_leaves(e, 1, tv.n_leaves + parity * 2 + 1, 0, 1, s))) return st;
+  return azp_tree_expand_backup(e, n, e->d_policy, e->d_value, 1, s);
+}
+
+// One move worth of search with the engine's own net(s):
+// root eval -> root expand (+noise) -> steps x (select -> net -> expand+backup).
+// The leaf counters are zeroed at the start of every move, so step i always uses counter pair i&1 and the
+// step sequence is identical from move to move: two consecutive steps are captured ONCE into a CUDA graph and
+// replayed steps/2 times (removes per-launch CPU cost and most launch gaps).  Per-launch profiling and the
+// first move after (re)loading weights use plain stream launches.
 static int search_move(azp_engine* e, int n, int add_noise, int two_nets, cudaStream_t s) {
   int st;
   TreeView& tv = e->tv;
-  e->parity ^= 1;
-  if ((st = azp_tree_begin_move(e, n, 1, 1, e->parity, s))) return st;
-  if ((st = azp_net_eval_leaves(e, 0, tv.n_leaves + e->parity * 2 + 0, 0, 0, s))) return st;
-  if (two_nets && (st = azp_net_eval_leaves(e, 1, tv.n_leaves + e->parity * 2 + 1, 0, 1, s))) return st;
+  AZP_CUDA(e, cudaMemsetAsync(tv.n_leaves, 0, 4 * sizeof(int32_t), s));
+  if ((st = azp_tree_begin_move(e, n, 1, 1, /*parity=*/1, s))) return st;
+  if ((st = azp_net_eval_leaves(e, 0, tv.n_leaves + 2, 0, 0, s))) return st;
+  if (two_nets && (st = azp_net_eval_leaves(e, 1, tv.n_leaves + 3, 0, 1, s))) return st;
   if ((st = azp_tree_root_expand(e, n, e->d_policy, 1, add_noise, s))) return st;
   const int steps = (e->cfg.sims + e->K - 1) / e->K;      // K descents per game per step
-  for (int sim = 0; sim < steps; sim++) {
-    e->parity ^= 1;
-    if ((st = azp_tree_select(e, n, 1, e->parity, s))) return st;
-    if ((st = azp_net_eval_leaves(e, 0, tv.n_leaves + e->parity * 2 + 0, 0, 0, s))) return st;
-    if (two_nets && (st = azp_net_eval_leaves(e, 1, tv.n_leaves + e->parity * 2 + 1, 0, 1, s))) return st;
-    if ((st = azp_tree_expand_backup(e, n, e->d_policy, e->d_value, 1, s))) return st;
+  int sim = 0;
+  const bool want_graph = e->use_graph && steps >= 4;
+  if (want_graph) {
+    const int key = (n * 2 + two_nets) * 2 + (e->profiling ? 1 : 0);
+    if (e->graph_exec && (e->graph_key != key || e->graph_epoch != e->weights_epoch)) {
+      cudaGraphExecDestroy(e->graph_exec);
+      e->graph_exec = nullptr;
+    }
+    if (!e->graph_exec) {
+      // capture is best effort: any failure falls back to plain stream launches for this engine
+      cudaGraph_t graph = nullptr;
+      const uint64_t launches_before = azp_launch_count();
+      cudaError_t ce = cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal);
+      if (ce == cudaSuccess) {
+        e->capturing = true;
+        e->gprof_n = 0;
+        st = sim_step(e, n, two_nets, 0, s);
+        if (!st) st = sim_step(e, n, two_nets, 1, s);
+        e->capturing = false;
+        ce = cudaStreamEndCapture(s, &graph);
+        if (!st && ce == cudaSuccess && graph) ce = cudaGraphInstantiate(&e->graph_exec, graph, 0);
+        if (graph) cudaGraphDestroy(graph);
+      }
+      if (st || ce != cudaSuccess || !e->graph_exec) {
+        if (getenv("AZP_GRAPH_DEBUG")) fprintf(stderr, "[azp] graph capture failed: st=%d cuda=%s\n", st, cudaGetErrorString(ce));
+        cudaGetLastError();                     // clear the sticky-free error state
+        e->graph_exec = nullptr;
+        e->use_graph = false;
+      } else {
+        e->graph_key = key;
+        e->graph_epoch = e->weights_epoch;
+        e->graph_launches_per_replay = (int)(azp_launch_count() - launches_before);   // kernels per replay
+      }
+    }
+    for (; e->graph_exec && sim + 2 <= steps; sim += 2) {
+      AZP_CUDA(e, cudaGraphLaunch(e->graph_exec, s));
+      azp_count_launch(e->graph_launches_per_replay);
+    }
   }
+  for (; sim < steps; sim++)
+    if ((st = sim_step(e, n, two_nets, sim & 1, s))) return st;
   return AZP_OK;
 }
 
@@ -367,6 +421,7 @@ static int episodes_run(azp_engine* e, long long first_game, long long n_games, 
     AZP_CUDA(e, cudaMemcpyAsync(rep.sched, e->d_sched, sizeof(rep.sched), cudaMemcpyDeviceToHost, s));
     AZP_CUDA(e, cudaMemcpyAsync(&rep.error, e->tv.error_flag, sizeof(int32_t), cudaMemcpyDeviceToHost, s));
     AZP_CUDA(e, cudaStreamSynchronize(s));
+    azp_prof_graph_sample(e);
     written = rep.sched[4];
     *host_written = written;
     if (rep.error) {
@@ -424,7 +479,18 @@ __global__ void prof_copy_count_kernel(const int32_t* src, int32_t* dst) { *dst 
 
 void azp_prof_begin(azp_engine* e, const int32_t* count_dev, int count_host, cudaStream_t s) {
   if (!e->profiling) return;
-  if (e->prof_used >= AZP_PROF_MAX) azp_prof_collect(e);
+  if (e->capturing) {
+    // inside the step graph: event-record NODES; every replay re-records them, the host samples the last
+    // replay of each move step after its sync (azp_prof_graph_sample)
+    if (e->gprof_n >= 2) return;
+    const int i = e->gprof_n;
+    for (int k = 0; k < 2; k++)
+      if (!e->gprof_ev[2 * i + k]) cudaEventCreate(&e->gprof_ev[2 * i + k]);
+    if (count_dev) { prof_copy_count_kernel<<<1, 1, 0, s>>>(count_dev, e->d_prof_counts + AZP_PROF_MAX - 2 + i); azp_count_launch(); }
+    cudaEventRecord(e->gprof_ev[2 * i], s);
+    return;
+  }
+  if (e->prof_used >= AZP_PROF_MAX - 2) azp_prof_collect(e);
   size_t i = e->prof_used;
   while (e->prof_events.size() < 2 * (i + 1)) {
     cudaEvent_t ev;
@@ -438,8 +504,28 @@ void azp_prof_begin(azp_engine* e, const int32_t* count_dev, int count_host, cud
 }
 void azp_prof_end(azp_engine* e, cudaStream_t s) {
   if (!e->profiling) return;
+  if (e->capturing) {
+    if (e->gprof_n >= 2) return;
+    cudaEventRecord(e->gprof_ev[2 * e->gprof_n + 1], s);
+    e->gprof_n++;
+    return;
+  }
   cudaEventRecord(e->prof_events[2 * e->prof_used + 1], s);
   e->prof_used++;
+}
+int azp_prof_graph_sample(azp_engine* e) {
+  if (!e->profiling || !e->graph_exec || e->gprof_n == 0) return AZP_OK;
+  int32_t counts[2] = {0, 0};
+  AZP_CUDA(e, cudaMemcpy(counts, e->d_prof_counts + AZP_PROF_MAX - 2, sizeof(counts), cudaMemcpyDeviceToHost));
+  for (int i = 0; i < e->gprof_n; i++) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, e->gprof_ev[2 * i], e->gprof_ev[2 * i + 1]) != cudaSuccess) { cudaGetLastError(); continue; }
+    if (counts[i] <= 0) continue;
+    e->prof_ms += ms;
+    e->prof_launches++;
+    e->prof_flops += e->prof_flops_per_board * counts[i];
+  }
+  return AZP_OK;
 }
 int azp_prof_collect(azp_engine* e) {
   if (e->prof_used == 0) return AZP_OK;

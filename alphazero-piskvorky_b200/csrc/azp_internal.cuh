@@ -91,6 +91,7 @@ struct azp_engine {
   std::string error;
   std::vector<void*> allocs;
   std::vector<void*>* alloc_pool = nullptr;   // when set, alloc() charges this list (weights: freed on reload)
+  bool alloc_reuse = false; size_t alloc_cursor = 0;   // reload: hand out the pool's existing buffers in order
   NetWeights* weights[2] = {nullptr, nullptr};
   NetWorkspace* ws = nullptr;
   // evaluation outputs indexed by slot
@@ -109,7 +110,15 @@ struct azp_engine {
   long long* d_sched = nullptr;    // [4]: next local game index, games to play, finished, (spare)
   int max_plies = 0;
   int search_n = 0;                // number of game slots in the current step-by-step search
-  int parity = 0;                  // which pair of leaf counters the current step uses
+  int parity = 0;                  // which pair of leaf counters the current step uses (step-by-step API)
+  // CUDA graph of two consecutive simulation steps (see search_move)
+  bool use_graph = true;
+  cudaGraphExec_t graph_exec = nullptr;
+  int graph_key = -1, graph_launches_per_replay = 0;
+  uint64_t weights_epoch = 0, graph_epoch = 0;
+  bool capturing = false;          // inside cudaStreamBeginCapture/EndCapture of the step graph
+  cudaEvent_t gprof_ev[4] = {nullptr, nullptr, nullptr, nullptr};   // event nodes around the dominant kernel in the graph
+  int gprof_n = 0;                 // dominant-kernel launches bracketed inside the captured graph (<= 2)
   // per-kernel profiling of the dominant kernel (roofline.achieved in bench.py)
   bool profiling = false;
   std::vector<cudaEvent_t> prof_events;      // pairs (start, stop), recycled after each collect
@@ -121,6 +130,7 @@ struct azp_engine {
   long long sp_first = 0, sp_total = 0;  // current self-play job
   void set_error(const std::string& m) { error = m; azp_set_global_error(m); }
   template <typename T> int alloc(T** p, size_t count) {
+    if (alloc_reuse && alloc_pool && alloc_cursor < alloc_pool->size()) { *p = (T*)(*alloc_pool)[alloc_cursor++]; return AZP_OK; }
     void* q = nullptr;
     cudaError_t err = cudaMalloc(&q, count * sizeof(T) + 256);
     if (err != cudaSuccess) { set_error(std::string("cudaMalloc: ") + cudaGetErrorString(err)); return AZP_ERR_CUDA; }
@@ -153,6 +163,7 @@ int azp_episode_drain(azp_engine* e, long long* out_written_dev, int mult, cudaS
 void azp_prof_begin(azp_engine* e, const int32_t* count_dev, int count_host, cudaStream_t s);
 void azp_prof_end(azp_engine* e, cudaStream_t s);
 int azp_prof_collect(azp_engine* e);
+int azp_prof_graph_sample(azp_engine* e);     // after a sync: read the event nodes of the last graph replay
 
 // azp_net.cu
 int azp_net_create(azp_engine* e);

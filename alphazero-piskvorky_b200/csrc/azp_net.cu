@@ -360,14 +360,23 @@ int azp_net_load(azp_engine* e, int slot, const float* blob, size_t n, bool on_d
   int st = azp_net_parse(e, host.data(), n, net);
   if (st) { e->set_error("weight blob does not match the configured network"); return st; }
   AZP_CUDA(e, cudaDeviceSynchronize());      // no kernel may still read the weights being replaced
-  delete e->weights[slot];                   // frees the previous set's device buffers
+  // A reload of the same network reuses the previous set's device buffers in allocation order: the kernels'
+  // pointer arguments (and with them the captured step graph and the TMA descriptors) stay valid.
+  std::vector<void*> old_allocs;
+  if (e->weights[slot]) { old_allocs.swap(e->weights[slot]->allocs); delete e->weights[slot]; }
   e->weights[slot] = new NetWeights();
+  e->weights[slot]->allocs.swap(old_allocs);
+  const size_t reused = e->weights[slot]->allocs.size();
   e->alloc_pool = &e->weights[slot]->allocs;
+  e->alloc_reuse = reused > 0; e->alloc_cursor = 0;
   if (e->cfg.net_dtype == AZP_DTYPE_F32) st = build_f32(e, net, e->weights[slot]);
   else st = azp_umma_build(e, net, e->weights[slot]);
-  e->alloc_pool = nullptr;
+  const bool same_layout = reused == 0 || (e->alloc_cursor == reused && e->weights[slot]->allocs.size() == reused);
+  e->alloc_pool = nullptr; e->alloc_reuse = false;
+  if (!same_layout) e->weights_epoch++;       // addresses changed: the captured graph must be rebuilt
   if (st) { delete e->weights[slot]; e->weights[slot] = nullptr; return st; }
   e->weights[slot]->loaded = true;
+  if (reused == 0) e->weights_epoch++;       // first load: (re)capture the simulation-step graph
   return AZP_OK;
 }
 

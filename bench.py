@@ -243,8 +243,9 @@ def run_engine_arm(args):
     run_all(max(args.warmup, 3))
 
     # ---- kernel-only arm: inputs resident in HBM --------------------------------------------------
+    profile_inline = os.environ.get("AZP_BENCH_NOPROF", "0") != "1"
     for eng in engines:
-        eng.set_profiling(True)
+        eng.set_profiling(profile_inline)
     c0 = counters()
     sampler = ClockSampler(local)
     if rank == 0:
@@ -360,7 +361,11 @@ def run_engine_arm(args):
             "traffic_note": "dram read+write bytes per launch from ncu --set full (profiles/r1_ncu_full_conv_umma_final.txt)",
             "peak_source": f"{peaks['source']} sustained bf16 (kernel timed inside a long step)",
             "kernel_ms_per_launch": kms / klaunches if klaunches else None, "kernel_launches": klaunches,
-            "kernel_share_of_step": kms / ms / max(1, E) if ms else None,
+            "kernel_share_of_step": ((kms / klaunches) * (-(-args.sims // max(1, args.leaves_per_step)) + 1) / (ms / args.steps)
+                                     if klaunches and ms else None),
+            "kernel_timing": "CUDA events around the kernel inside the timed region; launches replayed from the "
+                             "2-step CUDA graph are sampled once per move step per graph slot (event-record nodes), "
+                             "plain stream launches are all timed",
             "net_tensor_frac_end_to_end": (evals_done / (ms / 1e3)) * flops_per_leaf / 1e12 / world / peak_tf,
         },
         "virtual_loss_mode": None if vl is None else {

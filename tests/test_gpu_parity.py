@@ -302,7 +302,12 @@ def test_fused_search_matches_oracle_with_engine_net(az, size, win, sims, n, dty
         states.append(s)
     batch = _batch(az, [s.board for s in states], [s.to_move for s in states],
                    [_last_index(s) for s in states], win)
+    # on a side stream the simulation steps are replayed from a captured CUDA graph (capture is not possible
+    # on the legacy default stream, where the engine falls back to plain launches): both must give these counts
+    with torch.cuda.stream(torch.cuda.Stream()):
+        visits_graph = eng.search(batch.x, batch.o, batch.to_move, batch.last).cpu().numpy()
     visits = eng.search(batch.x, batch.o, batch.to_move, batch.last).cpu().numpy()
+    assert np.array_equal(visits, visits_graph)
     cache = {}
 
     def evaluator(state):
@@ -319,8 +324,8 @@ def test_fused_search_matches_oracle_with_engine_net(az, size, win, sims, n, dty
         assert np.array_equal(visits[i].reshape(size, size), ref.visits), i
         terminal += ref.stats["terminal_leaves"]
     c = eng.counters()
-    assert c["simulations"] == n * sims
-    assert c["terminal_leaves"] == terminal
+    assert c["simulations"] == 2 * n * sims
+    assert c["terminal_leaves"] == 2 * terminal
     eng.close()
 
 

@@ -5,7 +5,7 @@ out=$(timeout 300 python bench.py --dtype bf16 --steps 3 --warmup 3 --no-cpu-bas
 python - "$label" "$out" <<'PY'
 import sys, json
 try:
-    d = json.loads(sys.argv[2]); print(sys.argv[1], round(d["value"]), round(d["ms_per_step"], 1), round(d["roofline"]["kernel_ms_per_launch"] * 1000, 1), "us conv3")
+    d = json.loads(sys.argv[2]); k = d["roofline"]["kernel_ms_per_launch"]; print(sys.argv[1], round(d["value"]), round(d["ms_per_step"], 1), round(k * 1000, 1) if k else None, "us conv3", "e2e", round(d["e2e"]["value"]))
 except Exception as e:
     print(sys.argv[1], "FAILED", sys.argv[2][-300:])
 PY
