@@ -182,8 +182,13 @@ __global__ void select_kernel(RulesParams rp, TreeView tv, int n, double c_puct,
         const bool occupied = a >= A || bb_test<NW>(x, a) || bb_test<NW>(o, a);
         if (occupied) continue;
         const int nn = nn_[i];
-        double q = nn ? __ddiv_rn(ww_[i], (double)nn) : 0.0;
-        double u = __ddiv_rn(__dmul_rn(__dmul_rn(c_puct, (double)pp_[i]), sq), (double)(1 + nn));
+        // unvisited children (the vast majority of slots) need no fp64 division: Q = 0 and x / 1.0 == x exactly
+        const double num = __dmul_rn(__dmul_rn(c_puct, (double)pp_[i]), sq);
+        double q = 0.0, u = num;
+        if (nn) {
+          q = __ddiv_rn(ww_[i], (double)nn);
+          u = __ddiv_rn(num, (double)(1 + nn));
+        }
         double s = __dadd_rn(q, u);
         if (s > best) { best = s; besta = a; }    // ascending a: the FIRST maximum is kept
       }

@@ -74,6 +74,19 @@ class Engine:
         handle = C.c_void_p()
         check(self.lib.azp_create(C.byref(self.cfg), C.byref(handle)))
         self.h = handle
+        self._stream = None
+
+    def _driver_stream(self):
+        """The search / self-play / arena drivers replay a captured CUDA graph, which CUDA cannot capture on the
+        legacy default stream: when the caller is on the default stream, run the driver on a private stream
+        (ordered after the caller's pending work; the drivers are synchronous at return)."""
+        cur = torch.cuda.current_stream(self.device)
+        if cur.cuda_stream != 0:
+            return cur
+        if self._stream is None:
+            self._stream = torch.cuda.Stream(self.device)
+        self._stream.wait_stream(cur)
+        return self._stream
 
     def close(self):
         if getattr(self, "h", None):
@@ -161,8 +174,9 @@ class Engine:
         n = x.shape[0]
         self._n = n
         v = torch.empty((n, self.A), dtype=torch.int32, device=self.device)
-        check(self.lib.azp_search(self.h, 0, n, ptr(x), ptr(o), ptr(to_move), ptr(last), ptr(ply), ptr(game_id),
-                                  int(add_noise), ptr(v), stream_ptr()), self.h)
+        with torch.cuda.stream(self._driver_stream()):
+            check(self.lib.azp_search(self.h, 0, n, ptr(x), ptr(o), ptr(to_move), ptr(last), ptr(ply), ptr(game_id),
+                                      int(add_noise), ptr(v), stream_ptr()), self.h)
         return v
 
     # ---- drivers ------------------------------------------------------------------------------------
@@ -185,9 +199,10 @@ class Engine:
                    torch.empty((cap,), dtype=torch.int32, device=self.device))
         planes, pi, z = out
         written = C.c_int64(0)
-        st = check(self.lib.azp_selfplay_run(self.h, first_game, n_games, int(resume), max_move_steps, ptr(planes),
-                                             ptr(pi), ptr(z), planes.shape[0], C.byref(written), stream_ptr()),
-                   self.h)
+        with torch.cuda.stream(self._driver_stream()):
+            st = check(self.lib.azp_selfplay_run(self.h, first_game, n_games, int(resume), max_move_steps, ptr(planes),
+                                                 ptr(pi), ptr(z), planes.shape[0], C.byref(written), stream_ptr()),
+                       self.h)
         return st, planes, pi, z, int(written.value)
 
     def selfplay_all(self, n_games, first_game=0, capacity=None):
@@ -205,7 +220,8 @@ class Engine:
 
     def arena(self, n_games, first_game=0):
         wld = (C.c_int64 * 3)()
-        check(self.lib.azp_arena_run(self.h, first_game, n_games, wld, stream_ptr()), self.h)
+        with torch.cuda.stream(self._driver_stream()):
+            check(self.lib.azp_arena_run(self.h, first_game, n_games, wld, stream_ptr()), self.h)
         return int(wld[0]), int(wld[1]), int(wld[2])
 
     def counters(self) -> dict:

@@ -239,7 +239,10 @@ def run_engine_arm(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---- warm-up (also fast-forwards games so the timed region sees mid-game positions) ----------
+    # ---- untimed pre-roll to the steady state of the game population (games of every age, finished games
+    #      re-seated), then the W warm-up steps; without it every game would be at ply W..W+K and none could end
+    if args.preroll > 0:
+        run_all(args.preroll)
     run_all(max(args.warmup, 3))
 
     # ---- kernel-only arm: inputs resident in HBM --------------------------------------------------
@@ -337,7 +340,7 @@ def run_engine_arm(args):
             "step": "one move step = every game searches and plays one move",
             "l2": "inputs larger than L2: node table working set is GBs per GPU (no flush needed)",
             "games_per_gpu": games, "sims_per_move": args.sims, "c_puct": C_PUCT, "augment": "d4",
-            "engines_per_gpu": E,
+            "engines_per_gpu": E, "preroll_move_steps": args.preroll,
             "leaves_per_step": args.leaves_per_step,
             "search_mode": "exact (visit counts identical to the reference)" if args.leaves_per_step <= 1
                            else f"virtual loss, {args.leaves_per_step} leaves per game per step (throughput mode)",
@@ -397,6 +400,8 @@ def main():
                     help="1 = exact search (reference-identical visit counts); K > 1 = virtual-loss throughput mode")
     ap.add_argument("--vl-leaves", type=int, default=4, help="K of the virtual-loss side measurement")
     ap.add_argument("--no-vl", action="store_true")
+    ap.add_argument("--preroll", type=int, default=int(os.environ.get("AZP_BENCH_PREROLL", "64")),
+                    help="untimed move steps before warm-up: brings the 2048 games to their steady-state age mix")
     ap.add_argument("--cpu-budget", type=float, default=15.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
