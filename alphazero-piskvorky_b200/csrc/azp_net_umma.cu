@@ -310,6 +310,7 @@ __device__ __forceinline__ void umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, u
 constexpr int CONV_THREADS = 384;     // warp 0 TMA, warps 1 and 11 MMA issuers (even / odd tiles), warps 2..9 epilogue
                                       // (2 per TMEM lane quarter), warp 10 head-GEMM issuer
 constexpr int CONV_THREADS_BITS = 640; // + warps 12..19: conv1-from-bitboards producers of the A operand
+constexpr int CONV_THREADS_EPI2 = 640; // plain conv (no heads): warps 12..19 = a second epilogue group (odd tiles)
 constexpr int CODES = 256;            // >= 128 + 4P + 2 codes per tile (P <= 24)
 constexpr int HEAD_N = 16;            // fused 1x1 head convs: 6 (or 3) outputs padded to the UMMA minimum N
 
@@ -322,7 +323,7 @@ constexpr int HEAD_N = 16;            // fused 1x1 head convs: 6 (or 3) outputs 
 // three dx-shifted, 64B-swizzled A stages into shared memory themselves -- no act1 round trip through
 // HBM/L2 and no TMA loads for the activations.
 template <int CIN, int COUT, int STAGES, bool HEADS, bool BITS>
-__global__ void __launch_bounds__(BITS ? CONV_THREADS_BITS : CONV_THREADS, 1) conv_umma_kernel(const __grid_constant__ CUtensorMap map_act,
+__global__ void __launch_bounds__(BITS ? CONV_THREADS_BITS : (HEADS ? CONV_THREADS : CONV_THREADS_EPI2), 1) conv_umma_kernel(const __grid_constant__ CUtensorMap map_act,
                                                                     const __grid_constant__ CUtensorMap map_w,
                                                                     const __grid_constant__ CUtensorMap map_hw,
                                                                     const ConvArgs args) {
@@ -338,7 +339,11 @@ __global__ void __launch_bounds__(BITS ? CONV_THREADS_BITS : CONV_THREADS, 1) co
   // The head GEMM's K loop is split over HEAD_CHAINS independent accumulators (summed by the epilogue):
   // back-to-back UMMAs into ONE narrow accumulator serialise on its ~64-cycle dependent-issue latency
   constexpr int HEAD_CHAINS = 4;
-  constexpr uint32_t NEED = HEADS ? COL_HEAD + 2 * HEAD_CHAINS * HEAD_N : 2 * COUT;
+  // The plain conv (conv2) is epilogue-latency bound with one epilogue group: it gets FOUR accumulators and TWO
+  // epilogue groups (even / odd tiles) so two tiles are drained concurrently.
+  constexpr int NACC = (HEADS || BITS) ? 2 : 4;
+  constexpr int EGROUPS = (HEADS || BITS) ? 1 : 2;
+  constexpr uint32_t NEED = HEADS ? COL_HEAD + 2 * HEAD_CHAINS * HEAD_N : NACC * COUT;
   constexpr uint32_t TMEM_COLS = NEED <= 32 ? 32 : (NEED <= 64 ? 64 : (NEED <= 128 ? 128 : (NEED <= 256 ? 256 : 512)));
   constexpr int HALF = COUT / 2;                            // channels per epilogue warp
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -347,12 +352,13 @@ __global__ void __launch_bounds__(BITS ? CONV_THREADS_BITS : CONV_THREADS, 1) co
   uint8_t* s_w = smem;                                      // 9 taps x [COUT][CIN]
   uint8_t* s_a = s_w + S::W_BYTES;                          // STAGES x [stage_rows][CIN]
   uint8_t* s_hw = s_a + (size_t)STAGES * stage_bytes;       // HEADS: [COUT/64][16][64] bf16, 128B swizzle
-  uint8_t* s_tail = s_hw + HW_BYTES;
+  uint8_t* s_out = s_hw + HW_BYTES;                         // plain conv: EGROUPS x [128 rows][64 ch] bf16 output staging
+  uint8_t* s_tail = s_out + (HEADS ? 0 : EGROUPS * TILE_M * 128);
   uint64_t* full = reinterpret_cast<uint64_t*>(s_tail);     // [STAGES]
   uint64_t* empty = full + STAGES;                          // [STAGES]
-  uint64_t* tfull = empty + STAGES;                         // [2]
-  uint64_t* tempty = tfull + 2;                             // [2]
-  uint64_t* wbar = tempty + 2;                              // [1]
+  uint64_t* tfull = empty + STAGES;                         // [NACC <= 4]
+  uint64_t* tempty = tfull + 4;                             // [NACC <= 4]
+  uint64_t* wbar = tempty + 4;                              // [1]
   uint64_t* act_full = wbar + 1;                            // [2] epilogue -> MMA: bf16 tile b is in TMEM
   uint64_t* head_full = act_full + 2;                       // [2] MMA -> epilogue: head accumulator b ready
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(head_full + 2);
@@ -370,7 +376,7 @@ __global__ void __launch_bounds__(BITS ? CONV_THREADS_BITS : CONV_THREADS, 1) co
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < STAGES; i++) { mbar_init(&full[i], BITS ? 8 : 1); mbar_init(&empty[i], 1); }
-    for (int i = 0; i < 2; i++) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 8); }
+    for (int i = 0; i < NACC; i++) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 8); }
     mbar_init(wbar, 1);
     for (int i = 0; i < 2; i++) { mbar_init(&act_full[i], 8); mbar_init(&head_full[i], 1); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -519,8 +525,8 @@ __global__ void __launch_bounds__(BITS ? CONV_THREADS_BITS : CONV_THREADS, 1) co
       int it = 0, tl = 0;
       for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, tl++) {
         if ((tl & 1) != my_parity) { it += args.single ? 1 : 3; continue; }
-        const int acc = tl & 1;
-        const uint32_t acc_ph = (tl >> 1) & 1;
+        const int acc = tl % NACC;
+        const uint32_t acc_ph = (tl / NACC) & 1;
         if (args.clk && blockIdx.x == 0) args.clk[tl * 16 + 2] = clock64();
         mbar_wait(&tempty[acc], acc_ph ^ 1);              // epilogue has drained this accumulator
         if (args.clk && blockIdx.x == 0) args.clk[tl * 16 + 3] = clock64();
@@ -598,10 +604,12 @@ __global__ void __launch_bounds__(BITS ? CONV_THREADS_BITS : CONV_THREADS, 1) co
         if (args.clk && blockIdx.x == 0) args.clk[tl * 16 + 6] = clock64();
       }
     }
-  } else if (warp >= 2 && warp < 10) {
-    // ===== epilogue: warp (q, h) owns TMEM lanes 32q..32q+31 (tile rows) and channel half h =====
+  } else if ((warp >= 2 && warp < 10) || (EGROUPS == 2 && warp >= 12 && warp < 20)) {
+    // ===== epilogue: warp (q, h) owns TMEM lanes 32q..32q+31 (tile rows) and channel half h; with two groups,
+    //       group 0 (warps 2..9) drains even tiles and group 1 (warps 12..19) odd tiles =====
+    const int egroup = warp >= 12 ? 1 : 0;
     const int q = warp & 3;
-    const int h = (warp - 2) >> 2;
+    const int h = (warp - (egroup ? 12 : 2)) >> 2;
     const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
     // head outputs of local tile j (global tile tj): +bias, ReLU, scatter to feat[slot][j][pixel]
     auto write_heads = [&](int tj, int j) {
@@ -630,9 +638,10 @@ __global__ void __launch_bounds__(BITS ? CONV_THREADS_BITS : CONV_THREADS, 1) co
     };
     int tl = 0, t_prev = 0;
     for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, tl++) {
-      const int acc = tl & 1;
-      const uint32_t acc_ph = (tl >> 1) & 1;
-      const bool stamp = args.clk && blockIdx.x == 0 && warp == 2 && lane == 0;
+      if (EGROUPS == 2 && (tl & 1) != egroup) continue;
+      const int acc = tl % NACC;
+      const uint32_t acc_ph = (tl / NACC) & 1;
+      const bool stamp = args.clk && blockIdx.x == 0 && (warp == 2 || warp == 12) && lane == 0;
       if (stamp) args.clk[tl * 16 + 8] = clock64();
       mbar_wait(&tfull[acc], acc_ph);
       if (stamp) args.clk[tl * 16 + 9] = clock64();
@@ -648,30 +657,40 @@ __global__ void __launch_bounds__(BITS ? CONV_THREADS_BITS : CONV_THREADS, 1) co
         __syncwarp();
         if (lane == 0) { mbar_arrive(&tempty[acc]); if (HEADS) mbar_arrive(&act_full[tl & 1]); }
       } else if (!HEADS) {
-        uint4* dst = reinterpret_cast<uint4*>(args.out + (size_t)R * COUT + h * HALF);
-        const bool in_range = slot < g.G;
-#pragma unroll
-        for (int c0 = 0; c0 < HALF; c0 += 32) {
-          uint32_t r[32];
-          tmem_ld32(taddr + c0, r);
-          uint32_t packed[16];
-#pragma unroll
-          for (int j = 0; j < 16; j++) {
-            float v0 = interior ? fmaxf(__uint_as_float(r[2 * j]) + s_bias[h * HALF + c0 + 2 * j], 0.f) : 0.f;
-            float v1 = interior ? fmaxf(__uint_as_float(r[2 * j + 1]) + s_bias[h * HALF + c0 + 2 * j + 1], 0.f) : 0.f;
-            __nv_bfloat162 hh = __floats2bfloat162_rn(v0, v1);
-            packed[j] = *reinterpret_cast<uint32_t*>(&hh);
-          }
-          if (in_range) {
-#pragma unroll
-            for (int v = 0; v < 4; v++)
-              dst[c0 / 8 + v] = make_uint4(packed[4 * v], packed[4 * v + 1], packed[4 * v + 2], packed[4 * v + 3]);
-          }
-        }
-        if (stamp) args.clk[tl * 16 + 10] = clock64();
+        // bias + ReLU + halo zero in registers, the accumulator is released at once; the tile is then staged in
+        // shared memory (128B-swizzled rows) and leaves the SM as ONE TMA store -- per-thread row stores are
+        // uncoalesced (one 32-byte sector per lane and instruction) and bound this kernel before
+        static_assert(HEADS || HALF == 32, "plain-conv epilogue expects 64 output channels");
+        uint32_t r[32];
+        tmem_ld32(taddr, r);
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&tempty[acc]);
+        uint32_t packed[16];
+#pragma unroll
+        for (int j = 0; j < 16; j++) {
+          float v0 = interior ? fmaxf(__uint_as_float(r[2 * j]) + s_bias[h * HALF + 2 * j], 0.f) : 0.f;
+          float v1 = interior ? fmaxf(__uint_as_float(r[2 * j + 1]) + s_bias[h * HALF + 2 * j + 1], 0.f) : 0.f;
+          __nv_bfloat162 hh = __floats2bfloat162_rn(v0, v1);
+          packed[j] = *reinterpret_cast<uint32_t*>(&hh);
+        }
+        uint8_t* obuf = s_out + egroup * (TILE_M * 128);
+        const int m = q * 32 + lane;
+        // previous TMA store of this group has finished reading the buffer (its issuer waited before this barrier)
+        asm volatile("bar.sync %0, 256;" ::"r"(3 + egroup) : "memory");
+#pragma unroll
+        for (int v = 0; v < 4; v++)
+          *reinterpret_cast<uint4*>(obuf + m * 128 + (((h * 4 + v) ^ (m & 7)) << 4)) =
+              make_uint4(packed[4 * v], packed[4 * v + 1], packed[4 * v + 2], packed[4 * v + 3]);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        asm volatile("bar.sync %0, 256;" ::"r"(3 + egroup) : "memory");
+        if (h == 0 && q == 0 && lane == 0) {
+          const unsigned R0 = (unsigned)row_begin + (unsigned)t * TILE_M;
+          asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+                       ::"l"((uint64_t)&map_hw), "r"(smem_u32(obuf)), "r"(0), "r"((int)R0) : "memory");
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+          asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        }
         if (stamp) args.clk[tl * 16 + 11] = clock64();
       } else {
         if (tl >= 2) {           // head GEMM of tile tl-2 (same TMEM buffers) has retired
@@ -704,6 +723,7 @@ __global__ void __launch_bounds__(BITS ? CONV_THREADS_BITS : CONV_THREADS, 1) co
       }
       t_prev = t;
     }
+    if (!HEADS && h == 0 && q == 0 && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     if (HEADS && tl > 0 && h == 0) write_heads(t_prev, tl - 1);
   }
   tc_fence_before();
@@ -951,6 +971,7 @@ struct UmmaWorkspace {
   int fc_stages = 0, fc_b_rows = 0, fc_smem = 0;
   CUtensorMap map_act1, map_act2, map_feat;
   CUtensorMap map_act1_s, map_act2_s;  // single-load boxes (128+2P+2 rows)
+  CUtensorMap map_act2_out;            // conv2 epilogue: TMA store of one [128 rows][64 ch] tile
   int single = 0;
   long long* clk = nullptr;            // AZP_CLK=1: per-tile stamps of conv3's CTA 0
   size_t rows = 0;
@@ -984,7 +1005,7 @@ template <int CIN, int COUT, int STAGES, bool HEADS, bool BITS>
 int conv_smem_bytes(int stage_rows) {
   using S = ConvSmem<CIN, COUT, STAGES, HEADS>;
   return 1024 + S::W_BYTES + STAGES * ((stage_rows + 2 + 7) / 8 * 8) * S::ROWB + (HEADS ? (COUT / 64) * HEAD_N * 128 : 0) +
-         (2 * STAGES + 9) * 8 + 16 + (COUT + 8) * 4 + (BITS ? (72 * 32 + 32) * 4 + 2 * CODES * 2 : 0) + 64;
+         (HEADS ? 0 : 2 * TILE_M * 128) + (2 * STAGES + 13) * 8 + 16 + (COUT + 8) * 4 + (BITS ? (72 * 32 + 32) * 4 + 2 * CODES * 2 : 0) + 64;
 }
 
 }  // namespace
@@ -1044,6 +1065,7 @@ int azp_umma_create(azp_engine* e) {
   if ((st = make_map(e, &ws->map_act2, ws->act2, ws->rows, 64, stage_rows))) return st;
   if ((st = make_map(e, &ws->map_act1_s, ws->act1, ws->rows, 32, stage_rows + 2))) return st;
   if ((st = make_map(e, &ws->map_act2_s, ws->act2, ws->rows, 64, stage_rows + 2))) return st;
+  if ((st = make_map(e, &ws->map_act2_out, ws->act2, ws->rows, 64, TILE_M))) return st;
   { const char* v = getenv("AZP_SINGLE_LOAD"); ws->single = v ? atoi(v) : 1; }
   if (getenv("AZP_CLK")) { if ((st = e->alloc(&ws->clk, (size_t)64 * 16))) return st; AZP_CUDA(e, cudaMemset(ws->clk, 0, 64 * 16 * 8)); }
   cudaDeviceProp prop;
@@ -1278,10 +1300,10 @@ static int run_trunk(azp_engine* e, NetWeights* W, const int32_t* count_dev, int
   a2.w1 = U->w1_tab; a2.b1 = U->b1;
   { static int dbg = -1; if (dbg < 0) { const char* v = getenv("AZP_DEBUG_CONV"); dbg = v ? atoi(v) : 0; } a2.debug = dbg; }
   if (from_bits)
-    conv_umma_kernel<32, 64, STAGES2, false, true><<<grid, CONV_THREADS_BITS, ws->smem2, s>>>(ws->map_act1, U->map_w2, U->map_w2, a2);
+    conv_umma_kernel<32, 64, STAGES2, false, true><<<grid, CONV_THREADS_BITS, ws->smem2, s>>>(ws->map_act1, U->map_w2, ws->map_act2_out, a2);
   else
-    conv_umma_kernel<32, 64, STAGES2, false, false><<<grid, CONV_THREADS, ws->smem2, s>>>(
-        a2.single ? ws->map_act1_s : ws->map_act1, U->map_w2, U->map_w2, a2);
+    conv_umma_kernel<32, 64, STAGES2, false, false><<<grid, CONV_THREADS_EPI2, ws->smem2, s>>>(
+        a2.single ? ws->map_act1_s : ws->map_act1, U->map_w2, ws->map_act2_out, a2);
   azp_count_launch();
   ConvArgs a3 = a2;
   a3.bias = U->b3; a3.out = nullptr; a3.head_b = U->head_b8; a3.feat = ws->feat;
