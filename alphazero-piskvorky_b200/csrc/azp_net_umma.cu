@@ -175,9 +175,10 @@ __global__ void __launch_bounds__(256) conv1_bits_kernel(ConvGeom g, const uint6
 #pragma unroll
         for (int ky = 0; ky < 3; ky++) {
           const int pat = (code3[ky] >> (3 * pl)) & 7;
-          if (pl == 2 && !pat) continue;                // the last-move plane is almost always empty here
+          if (!pat) continue;       // empty pattern = all-zero table row (x + 0.0f == x): skip its shared-memory read,
+                                    // the table traffic is what bounds this kernel and most patterns are empty
           const float4* tr = reinterpret_cast<const float4*>(st + ((pl * 3 + ky) * 8 + pat) * 32 + cg * 8);
-          const float4 w0 = tr[0], w1 = tr[1];          // pattern 0 selects an all-zero row: x + 0.0f == x
+          const float4 w0 = tr[0], w1 = tr[1];
           acc[0] += w0.x; acc[1] += w0.y; acc[2] += w0.z; acc[3] += w0.w;
           acc[4] += w1.x; acc[5] += w1.y; acc[6] += w1.z; acc[7] += w1.w;
         }
