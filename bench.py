@@ -31,8 +31,8 @@ METRIC = "mcts_simulations_per_sec"
 UNIT = "sims/s"
 MEAN_GAME_PLIES = 57.3             # measured at this config: profiles/r1_game_length_probe.txt
 # DRAM bytes (read + write) of ONE conv3 launch on 2048 leaves, from `ncu --set full` (cold caches):
-# profiles/r1_ncu_full_conv_umma_final.txt -> 67.31 MB + 1.55 MB; algorithmic = act2 read once (67.1 MB)
-CONV3_DRAM_TRAFFIC_PER_2048_LEAVES = 68.86e6
+# profiles/r1_ncu_full_conv_umma_final.txt -> 67.32 MB + 1.62 MB; algorithmic = act2 read once (67.1 MB)
+CONV3_DRAM_TRAFFIC_PER_2048_LEAVES = 68.94e6
 FLOPS_PER_LEAF = 42.799e6          # 2*MAC of GomokuNet(15) per position
 
 
