@@ -23,6 +23,12 @@ int azp_check_launch() {
   return AZP_OK;
 }
 
+bool azp_pdl_enabled() {
+  static int v = -1;
+  if (v < 0) { const char* q = getenv("AZP_PDL"); v = q ? (atoi(q) != 0) : 1; }
+  return v != 0;
+}
+
 RulesParams azp_make_rules(int B, int WL) {
   RulesParams rp;
   memset(&rp, 0, sizeof(rp));
@@ -172,7 +178,7 @@ extern "C" void azp_destroy(azp_engine* e) {
   cudaSetDevice(e->cfg.device);
   cudaDeviceSynchronize();
   for (cudaEvent_t ev : e->prof_events) cudaEventDestroy(ev);
-  if (e->graph_exec) cudaGraphExecDestroy(e->graph_exec);
+  for (cudaGraphExec_t ge : e->graph_exec) if (ge) cudaGraphExecDestroy(ge);
   for (cudaEvent_t ev : e->gprof_ev) if (ev) cudaEventDestroy(ev);
   if (e->cfg.net_dtype == AZP_DTYPE_BF16) azp_umma_destroy(e);
   azp_net_destroy(e);
@@ -270,74 +276,82 @@ extern "C" int azp_root_visits(azp_engine* e, int32_t* visits, void* stream) {
   return azp_tree_root_visits(e, e->search_n, visits, (cudaStream_t)stream);
 }
 
-// one move worth of search for the first n slots with the engine's own net(s):
-// root eval -> root expand (+noise) -> S x (select -> net -> expand+backup)
-// one simulation step for all games: K descents -> leaf batch -> net -> expand + backup
-static int sim_step(azp_engine* e, int n, int two_nets, int parity, cudaStream_t s) {
+// evaluate the leaf batch of counter pair `parity` with the engine's own net(s)
+static int eval_step(azp_engine* e, int two_nets, int parity, cudaStream_t s) {
   int st;
   TreeView& tv = e->tv;
-  if ((st = azp_tree_select(e, n, 1, parity, s))) return st;
   if ((st = azp_net_eval_leaves(e, 0, tv.n_leaves + parity * 2 + 0, 0, 0, s))) return st;
   if (two_nets && (st = azp_net_eval_leaves(e, 1, tv.n_leaves + parity * 2 + 1, 0, 1, s))) return st;
-  return azp_tree_expand_backup(e, n, e->d_policy, e->d_value, 1, s);
+  return AZP_OK;
 }
 
 // One move worth of search with the engine's own net(s):
-// root eval -> root expand (+noise) -> steps x (select -> net -> expand+backup).
+//   root eval -> root expand (+noise) -> descent 0 -> steps x (net -> expand+backup [+ descent of the next step])
+// The expand+backup of step i and the descent of step i+1 are ONE launch (advance_kernel).
 // The leaf counters are zeroed at the start of every move, so step i always uses counter pair i&1 and the
-// step sequence is identical from move to move: two consecutive steps are captured ONCE into a CUDA graph and
-// replayed steps/2 times (removes per-launch CPU cost and most launch gaps).  Per-launch profiling and the
-// first move after (re)loading weights use plain stream launches.
+// sequence is identical from move to move: two consecutive iterations are captured ONCE into a CUDA graph and
+// replayed (removes per-launch CPU cost and most launch gaps).  The kernels of the chain are launched with
+// programmatic dependent launch, inside the graph too.
 static int search_move(azp_engine* e, int n, int add_noise, int two_nets, cudaStream_t s) {
   int st;
   TreeView& tv = e->tv;
   AZP_CUDA(e, cudaMemsetAsync(tv.n_leaves, 0, 4 * sizeof(int32_t), s));
   if ((st = azp_tree_begin_move(e, n, 1, 1, /*parity=*/1, s))) return st;
-  if ((st = azp_net_eval_leaves(e, 0, tv.n_leaves + 2, 0, 0, s))) return st;
-  if (two_nets && (st = azp_net_eval_leaves(e, 1, tv.n_leaves + 3, 0, 1, s))) return st;
+  if ((st = eval_step(e, two_nets, 1, s))) return st;
   if ((st = azp_tree_root_expand(e, n, e->d_policy, 1, add_noise, s))) return st;
   const int steps = (e->cfg.sims + e->K - 1) / e->K;      // K descents per game per step
+  if ((st = azp_tree_select(e, n, 1, 0, s))) return st;   // descent of step 0
+  // iteration i: net(pair i&1), then expand+backup(i) fused with the descent of step i+1 (pair (i+1)&1)
+  auto iteration = [&](int i, bool last) -> int {
+    int r = eval_step(e, two_nets, i & 1, s);
+    if (r) return r;
+    if (last) return azp_tree_expand_backup(e, n, e->d_policy, e->d_value, 1, s);
+    return azp_tree_advance(e, n, e->d_policy, e->d_value, 1, 1, (i + 1) & 1, s);
+  };
   int sim = 0;
-  const bool want_graph = e->use_graph && steps >= 4;
+  const bool want_graph = e->use_graph && steps >= 5;
   if (want_graph) {
     const int key = (n * 2 + two_nets) * 2 + (e->profiling ? 1 : 0);
-    if (e->graph_exec && (e->graph_key != key || e->graph_epoch != e->weights_epoch)) {
-      cudaGraphExecDestroy(e->graph_exec);
-      e->graph_exec = nullptr;
+    const int gi = e->profiling ? 1 : 0;                  // one cached executable per profiling state
+    if (e->graph_exec[gi] && (e->graph_key[gi] != key || e->graph_epoch[gi] != e->weights_epoch)) {
+      cudaGraphExecDestroy(e->graph_exec[gi]);
+      e->graph_exec[gi] = nullptr;
     }
-    if (!e->graph_exec) {
+    if (!e->graph_exec[gi]) {
       // capture is best effort: any failure falls back to plain stream launches for this engine
       cudaGraph_t graph = nullptr;
       const uint64_t launches_before = azp_launch_count();
       cudaError_t ce = cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal);
       if (ce == cudaSuccess) {
         e->capturing = true;
-        e->gprof_n = 0;
-        st = sim_step(e, n, two_nets, 0, s);
-        if (!st) st = sim_step(e, n, two_nets, 1, s);
+        if (gi == 1) e->gprof_n = 0;
+        st = iteration(0, false);
+        if (!st) st = iteration(1, false);
         e->capturing = false;
         ce = cudaStreamEndCapture(s, &graph);
-        if (!st && ce == cudaSuccess && graph) ce = cudaGraphInstantiate(&e->graph_exec, graph, 0);
+        if (!st && ce == cudaSuccess && graph) ce = cudaGraphInstantiate(&e->graph_exec[gi], graph, 0);
         if (graph) cudaGraphDestroy(graph);
       }
-      if (st || ce != cudaSuccess || !e->graph_exec) {
+      if (st || ce != cudaSuccess || !e->graph_exec[gi]) {
         if (getenv("AZP_GRAPH_DEBUG")) fprintf(stderr, "[azp] graph capture failed: st=%d cuda=%s\n", st, cudaGetErrorString(ce));
         cudaGetLastError();                     // clear the sticky-free error state
-        e->graph_exec = nullptr;
+        e->graph_exec[gi] = nullptr;
         e->use_graph = false;
       } else {
-        e->graph_key = key;
-        e->graph_epoch = e->weights_epoch;
-        e->graph_launches_per_replay = (int)(azp_launch_count() - launches_before);   // kernels per replay
+        e->graph_key[gi] = key;
+        e->graph_epoch[gi] = e->weights_epoch;
+        e->graph_launches_per_replay[gi] = (int)(azp_launch_count() - launches_before);   // kernels per replay
       }
     }
-    for (; e->graph_exec && sim + 2 <= steps; sim += 2) {
-      AZP_CUDA(e, cudaGraphLaunch(e->graph_exec, s));
-      azp_count_launch(e->graph_launches_per_replay);
+    e->graph_last = e->graph_exec[gi] ? gi : -1;
+    // the last iteration (no descent after it) always runs as plain launches
+    for (; e->graph_exec[gi] && sim + 2 <= steps - 1; sim += 2) {
+      AZP_CUDA(e, cudaGraphLaunch(e->graph_exec[gi], s));
+      azp_count_launch(e->graph_launches_per_replay[gi]);
     }
   }
   for (; sim < steps; sim++)
-    if ((st = sim_step(e, n, two_nets, sim & 1, s))) return st;
+    if ((st = iteration(sim, sim == steps - 1))) return st;
   return AZP_OK;
 }
 
@@ -514,7 +528,7 @@ void azp_prof_end(azp_engine* e, cudaStream_t s) {
   e->prof_used++;
 }
 int azp_prof_graph_sample(azp_engine* e) {
-  if (!e->profiling || !e->graph_exec || e->gprof_n == 0) return AZP_OK;
+  if (!e->profiling || e->graph_last != 1 || !e->graph_exec[1] || e->gprof_n == 0) return AZP_OK;
   int32_t counts[2] = {0, 0};
   AZP_CUDA(e, cudaMemcpy(counts, e->d_prof_counts + AZP_PROF_MAX - 2, sizeof(counts), cudaMemcpyDeviceToHost));
   for (int i = 0; i < e->gprof_n; i++) {

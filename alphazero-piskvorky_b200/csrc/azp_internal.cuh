@@ -5,6 +5,8 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <string>
+#include <string.h>
+#include <utility>
 #include <vector>
 #include "azp_common.cuh"
 
@@ -25,6 +27,44 @@ RulesParams azp_make_rules(int board, int win_length);
       case 4: kernel<4><<<grid, block, smem, stream>>>(__VA_ARGS__); break;                 \
       case 5: kernel<5><<<grid, block, smem, stream>>>(__VA_ARGS__); break;                 \
       default: kernel<6><<<grid, block, smem, stream>>>(__VA_ARGS__); break;                \
+    }                                                                                       \
+  } while (0)
+
+// ---- programmatic dependent launch (PDL) -------------------------------------------------------------
+// The kernels of a simulation step form a strict chain (select -> conv1 -> conv2 -> conv3 -> fc ->
+// expand/backup -> select ...).  Launched with the programmatic-stream-serialization attribute, kernel
+// N+1 may become resident and run its prologue (barrier init, TMEM allocation, weight loads into shared
+// memory -- nothing that kernel N writes) while kernel N drains; `pdl_wait()` then blocks until kernel N
+// has completed and its writes are visible.  Every kernel launched through azp_launch(..., pdl=true) MUST
+// call pdl_wait() before its first access to data produced on the stream.  Both instructions are no-ops
+// in a launch without the attribute.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+bool azp_pdl_enabled();                        // AZP_PDL (default 1)
+
+template <typename... P, typename... A>
+inline cudaError_t azp_launch(void (*kernel)(P...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, bool pdl,
+                              A&&... args) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = (pdl && azp_pdl_enabled()) ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, std::forward<A>(args)...);
+}
+
+#define AZP_DISPATCH_NW_PDL(nw, kernel, grid, block, smem, stream, ...)                     \
+  do {                                                                                      \
+    switch (nw) {                                                                           \
+      case 1: azp_launch(kernel<1>, grid, block, smem, stream, true, __VA_ARGS__); break;   \
+      case 2: azp_launch(kernel<2>, grid, block, smem, stream, true, __VA_ARGS__); break;   \
+      case 3: azp_launch(kernel<3>, grid, block, smem, stream, true, __VA_ARGS__); break;   \
+      case 4: azp_launch(kernel<4>, grid, block, smem, stream, true, __VA_ARGS__); break;   \
+      case 5: azp_launch(kernel<5>, grid, block, smem, stream, true, __VA_ARGS__); break;   \
+      default: azp_launch(kernel<6>, grid, block, smem, stream, true, __VA_ARGS__); break;  \
     }                                                                                       \
   } while (0)
 
@@ -113,9 +153,10 @@ struct azp_engine {
   int parity = 0;                  // which pair of leaf counters the current step uses (step-by-step API)
   // CUDA graph of two consecutive simulation steps (see search_move)
   bool use_graph = true;
-  cudaGraphExec_t graph_exec = nullptr;
-  int graph_key = -1, graph_launches_per_replay = 0;
-  uint64_t weights_epoch = 0, graph_epoch = 0;
+  cudaGraphExec_t graph_exec[2] = {nullptr, nullptr};     // [profiling off / on]
+  int graph_key[2] = {-1, -1}, graph_launches_per_replay[2] = {0, 0};
+  int graph_last = -1;                                    // executable used by the last search_move (-1: none)
+  uint64_t weights_epoch = 0, graph_epoch[2] = {0, 0};
   bool capturing = false;          // inside cudaStreamBeginCapture/EndCapture of the step graph
   cudaEvent_t gprof_ev[4] = {nullptr, nullptr, nullptr, nullptr};   // event nodes around the dominant kernel in the graph
   int gprof_n = 0;                 // dominant-kernel launches bracketed inside the captured graph (<= 2)
@@ -151,6 +192,9 @@ int azp_tree_begin_move(azp_engine* e, int n, int emit, int compact, int parity,
 int azp_tree_root_expand(azp_engine* e, int n, const float* policy, int by_slot, int add_noise, cudaStream_t s);
 int azp_tree_select(azp_engine* e, int n, int compact, int parity, cudaStream_t s);
 int azp_tree_expand_backup(azp_engine* e, int n, const float* policy, const float* value, int by_slot, cudaStream_t s);
+// expand+backup of the step just evaluated, then the descent of the next step (counter pair `parity`), one launch
+int azp_tree_advance(azp_engine* e, int n, const float* policy, const float* value, int by_slot, int compact, int parity,
+                     cudaStream_t s);
 int azp_tree_root_visits(azp_engine* e, int n, int32_t* visits, cudaStream_t s);
 int azp_tree_leaf_states(azp_engine* e, int n, uint64_t* x, uint64_t* o, uint8_t* tm, int16_t* last, uint8_t* kind, cudaStream_t s);
 int azp_episode_seat(azp_engine* e, int n, int arena, cudaStream_t s);

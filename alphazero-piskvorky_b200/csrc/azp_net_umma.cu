@@ -53,6 +53,16 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     if (clock64() - t0 > 4000000000ll) __trap();
   }
 }
+// Same, for waits that are expected to be long and sit next to issue-bound warps (conv1 producers): back off with
+// nanosleep so the spinning warp does not eat the issue slots of the warps it is waiting for.
+__device__ __forceinline__ void mbar_wait_sleep(uint64_t* bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    __nanosleep(64);
+    if (clock64() - t0 > 4000000000ll) __trap();
+  }
+}
 __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c_inner, int c_row) {
   asm volatile(
       "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
@@ -293,6 +303,13 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&v)[16
       ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]),
         "r"(v[8]), "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]) : "memory");
 }
+__device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                 "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+               : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&r)[8]) {
   asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
@@ -369,18 +386,19 @@ __global__ void __launch_bounds__(BITS ? CONV_THREADS_BITS : (HEADS ? CONV_THREA
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const ConvGeom g = args.g;
-  const int count = args.count_dev ? *args.count_dev : args.count_host;
-  const int slot0 = args.back ? g.G - count : 0;
-  const long long row_begin = (long long)slot0 * g.stride;
-  const long long rows_total = (long long)count * g.stride;
-  const int n_tiles = (int)((rows_total + TILE_M - 1) / TILE_M);
 
+  // ---- prologue: touches nothing the previous kernel of the stream writes, so under programmatic dependent
+  //      launch it overlaps that kernel's tail (barriers, TMEM, bias and the resident weights) ----
   if (threadIdx.x == 0) {
     for (int i = 0; i < STAGES; i++) { mbar_init(&full[i], BITS ? 8 : 1); mbar_init(&empty[i], 1); }
     for (int i = 0; i < NACC; i++) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 8); }
     mbar_init(wbar, 1);
     for (int i = 0; i < 2; i++) { mbar_init(&act_full[i], 8); mbar_init(&head_full[i], 1); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    mbar_expect_tx(wbar, S::W_BYTES + HW_BYTES);
+    for (int tap = 0; tap < 9; tap++) tma_load_2d(s_w + tap * S::W_TAP_BYTES, &map_w, wbar, 0, tap * COUT);
+    if (HEADS)
+      for (int kc = 0; kc < COUT / 64; kc++) tma_load_2d(s_hw + kc * HEAD_N * 128, &map_hw, wbar, kc * 64, 0);
   }
   for (int i = threadIdx.x; i < COUT; i += blockDim.x) s_bias[i] = args.bias[i];
   if (HEADS && threadIdx.x < 8) s_bias[COUT + threadIdx.x] = args.head_b[threadIdx.x];
@@ -390,13 +408,17 @@ __global__ void __launch_bounds__(BITS ? CONV_THREADS_BITS : (HEADS ? CONV_THREA
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
+  pdl_wait();                      // the leaf count and the input activations are the previous kernels' outputs
+  pdl_launch_dependents();
+  const int count = args.count_dev ? *args.count_dev : args.count_host;
+  const int slot0 = args.back ? g.G - count : 0;
+  const long long row_begin = (long long)slot0 * g.stride;
+  const long long rows_total = (long long)count * g.stride;
+  const int n_tiles = (int)((rows_total + TILE_M - 1) / TILE_M);
+
   if (warp == 0) {
     // ===== TMA producer =====
     if (lane == 0) {
-      mbar_expect_tx(wbar, S::W_BYTES + HW_BYTES);
-      for (int tap = 0; tap < 9; tap++) tma_load_2d(s_w + tap * S::W_TAP_BYTES, &map_w, wbar, 0, tap * COUT);
-      if (HEADS)
-        for (int kc = 0; kc < COUT / 64; kc++) tma_load_2d(s_hw + kc * HEAD_N * 128, &map_hw, wbar, kc * 64, 0);
       int it = 0;
       if (!BITS && args.single) {
         // one box of 128+2P+2 rows per tile, starting one row above/left of the dy=-1,dx=-1 window
@@ -732,6 +754,345 @@ __global__ void __launch_bounds__(BITS ? CONV_THREADS_BITS : (HEADS ? CONV_THREA
   if (warp == 1) tmem_dealloc(tmem_base, TMEM_COLS);
 }
 
+// ---- conv1 (4 -> 32, 3x3) on the tensor core ------------------------------------------------------------------
+// The first conv sees 0/1 planes (games.py:86-129), so its implicit-GEMM A operand is just the 27 neighbourhood BITS
+// of a position (3 kernel rows x 3 stone/last-move planes x 3 columns; plane 3 is all zero) expanded to bf16, plus a
+// constant-one column that carries the bias:  act1[row][co] = relu( sum_k A[row][k] * W[co][k] ),
+//     k = ky*9 + plane*3 + kx  (k < 27),  k = 27: bias,  k = 28..31: zero.
+// Halo rows get an all-zero A row, so their output is exactly 0 and the epilogue is a bare ReLU + pack.
+// W is split into bf16 hi + lo parts (two UMMA passes over the same A) so the products with the exact 0/1 inputs
+// reproduce the fp32 weights to ~2^-17 relative: conv1 stays fp32-accurate like the SIMT kernel it replaces.
+// PLANES = true reads arbitrary float planes [n][4][A] instead (azp_net_forward): same K layout for planes 0..2 and
+// a second 16-wide K chunk for plane 3, issued AFTER the shared chunks -- on 0/1 inputs with an empty plane 3 it adds
+// exact zeros, so both variants agree bit for bit and the search sees the numbers net_forward reports.
+// Persistent, warp-specialised: warp 0 = TMEM owner + MMA issuer, warps 1..8 = two producer groups (even / odd
+// tiles) that build the swizzled A tile in shared memory, warps 9..16 = two epilogue groups (TMEM -> ReLU -> bf16 ->
+// swizzled staging tile -> one TMA store).
+constexpr int C1_NPG = 2;                    // producer groups per CTA (tile tl is built by group tl % C1_NPG); TWO CTAs per SM
+constexpr int C1_THREADS = 32 * (1 + 4 * C1_NPG + 8);
+constexpr int C1_STAGES = 4;                 // A stages == TMEM accumulators (tile tl uses stage/accumulator tl % 4)
+constexpr int C1_A_BYTES = TILE_M * 64;      // one A tile: 128 rows x 32 bf16
+constexpr int C1_W_BYTES = 32 * 64;          // one weight matrix: 32 cout x 32 k bf16
+constexpr int C1_TAB = 4 * 3 * 24;            // per tile: <= 4 boards x 3 planes x (B+2 <= 24) row-bit words (uint32)
+
+struct Conv1Args {
+  ConvGeom g;
+  const __nv_bfloat16* w;          // [4][32][32] bf16: hi, lo (planes 0..2 + bias), plane-3 hi, plane-3 lo
+  const int32_t* count_dev; int count_host; int back;
+  const uint64_t* lx; const uint64_t* lo; const uint8_t* ltm; const int16_t* llast; int NW;   // leaf batch (bitboards)
+  const float* planes;             // PLANES: [count][4][A] float32
+  long long* clk;                  // bring-up (AZP_CLK=3): per-tile clock64 stamps of CTA 0 ([tile][16]) or null
+};
+#define C1_STAMP(cond, k) do { if (args.clk && blockIdx.x == 0 && tl < 64 && (cond)) args.clk[tl * 16 + (k)] = clock64(); } while (0)
+
+constexpr int C1_BB_ITEMS = 32;              // staged leaf inputs of the <= 2 boards a tile touches: 2 x (2*NW words + tm + last)
+constexpr int conv1_smem_bytes(bool planes) {
+  return 1024 + 4 * C1_W_BYTES + (planes ? 2 : 1) * C1_STAGES * C1_A_BYTES + 4 * C1_A_BYTES + 256 * 16 + C1_NPG * 2 * C1_TAB * 4 +
+         C1_NPG * 2 * C1_BB_ITEMS * 8 + 4 * C1_STAGES * 8 + 64;
+}
+
+template <bool PLANES>
+__global__ void __launch_bounds__(C1_THREADS, 2) conv1_umma_kernel(const __grid_constant__ CUtensorMap map_out,
+                                                                   const Conv1Args args) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint8_t* s_w = smem;                                         // 4 x [32][32] bf16, 64B-swizzled rows
+  uint8_t* s_a = s_w + 4 * C1_W_BYTES;                         // C1_STAGES x [128][32] (planes 0..2 + bias)
+  uint8_t* s_a3 = s_a + C1_STAGES * C1_A_BYTES;                // C1_STAGES x [128][32] (plane 3; PLANES only)
+  uint8_t* s_out = s_a3 + (PLANES ? C1_STAGES * C1_A_BYTES : 0);   // 2 epilogue groups x 2 x [128][32] bf16 staging
+  uint4* s_lut = reinterpret_cast<uint4*>(s_out + 4 * C1_A_BYTES);            // [256]: 8 input bits -> 8 bf16 (0.0 / 1.0)
+  uint32_t* s_tab = reinterpret_cast<uint32_t*>(s_lut + 256);                 // [C1_NPG groups][2][C1_TAB] row-bit tables
+  uint64_t* s_bb = reinterpret_cast<uint64_t*>(s_tab + C1_NPG * 2 * C1_TAB);  // [C1_NPG groups][2][C1_BB_ITEMS]
+  uint64_t* full = s_bb + C1_NPG * 2 * C1_BB_ITEMS;
+  uint64_t* done = full + C1_STAGES;                           // MMAs of the stage retired: A stage free AND accumulator ready
+  uint64_t* tempty = done + C1_STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + C1_STAGES);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const ConvGeom g = args.g;
+
+  // ---- prologue (independent of the previous kernel: overlaps its tail under programmatic dependent launch) ----
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < C1_STAGES; i++) {
+      mbar_init(&full[i], 4); mbar_init(&done[i], 1); mbar_init(&tempty[i], 4);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (threadIdx.x < 512) {                                     // weights -> shared memory in the UMMA 64B-swizzle layout
+    const int mat = threadIdx.x >> 7, co = (threadIdx.x >> 2) & 31, c = threadIdx.x & 3;
+    const uint4 v = reinterpret_cast<const uint4*>(args.w)[threadIdx.x];
+    *reinterpret_cast<uint4*>(s_w + mat * C1_W_BYTES + co * 64 + ((c ^ ((co >> 1) & 3)) << 4)) = v;
+  }
+  if (threadIdx.x < 256) {
+    const uint32_t e8 = threadIdx.x;
+    uint32_t wd[4];
+#pragma unroll
+    for (int j = 0; j < 4; j++) wd[j] = (((e8 >> (2 * j)) & 1u) ? 0x3F80u : 0u) | (((e8 >> (2 * j + 1)) & 1u) ? 0x3F800000u : 0u);
+    s_lut[e8] = make_uint4(wd[0], wd[1], wd[2], wd[3]);
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  if (warp == 0) tmem_alloc(tmem_slot, 64 * C1_STAGES);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  pdl_wait();                      // leaf batch / leaf count are written by the descent kernel before us
+  pdl_launch_dependents();
+  const int count = args.count_dev ? *args.count_dev : args.count_host;
+  const int slot0 = args.back ? g.G - count : 0;
+  const long long row_begin = (long long)slot0 * g.stride;
+  const long long rows_total = (long long)count * g.stride;
+  const int n_tiles = (int)((rows_total + TILE_M - 1) / TILE_M);
+
+  if (warp == 0) {
+    // ===== MMA issuer =====
+    if (lane == 0) {
+      // hi and lo weight parts are the two halves of ONE N = 64 B operand (rows 0..31 / 32..63 of the same swizzled
+      // array): two UMMAs per tile instead of four; the epilogue adds the two 32-column halves
+      const uint32_t idesc = umma_idesc(64);
+      const uint32_t w_base = smem_u32(s_w), a_base = smem_u32(s_a), a3_base = smem_u32(s_a3);
+      int tl = 0;
+      for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, tl++) {
+        const int st = tl % C1_STAGES;
+        const uint32_t ph = (tl / C1_STAGES) & 1;
+        mbar_wait_sleep(&tempty[st], ph ^ 1);
+        C1_STAMP(true, 5);
+        mbar_wait_sleep(&full[st], ph);
+        C1_STAMP(true, 6);
+        tc_fence_after();
+        const uint32_t d = tmem_base + (uint32_t)(st * 64);
+        const uint32_t a = a_base + (uint32_t)(st * C1_A_BYTES);
+        umma_bf16(d, umma_desc(a, 64), umma_desc(w_base, 64), idesc, 0u);
+        umma_bf16(d, umma_desc(a + 32, 64), umma_desc(w_base + 32, 64), idesc, 1u);
+        if (PLANES) {
+          const uint32_t a3 = a3_base + (uint32_t)(st * C1_A_BYTES);
+          umma_bf16(d, umma_desc(a3, 64), umma_desc(w_base + 2 * C1_W_BYTES, 64), idesc, 1u);
+        }
+        umma_commit(&done[st]);
+        C1_STAMP(true, 7);
+      }
+    }
+  } else if (warp <= 4 * C1_NPG) {
+    // ===== A-operand producers: group pg builds the tiles with tl % C1_NPG == pg, one row per thread =====
+    const int pg = (warp - 1) >> 2;
+    const int pt = threadIdx.x - 32 - pg * 128;              // 0..127
+    // the 128 rows of a tile touch at most `nb` boards: 2 for B >= 9, up to 4 for the smallest boards
+    const int nb = min((TILE_M + g.stride - 2) / g.stride + 1, 4);
+    const int per_board = 2 * args.NW + 2;
+    const int n_items = min(nb * per_board, C1_BB_ITEMS);
+    // Leaf inputs of tile t, item = board * per_board + j (j < NW: x word, j < 2NW: o word, then the aligned 32-bit
+    // words holding the board's to-move byte / last-move int16).  They are fetched with cp.async one tile ahead:
+    // plain loads would be drained by the group's next bar.sync (a barrier waits for the warp's outstanding loads),
+    // exposing the full global latency on every tile.
+    const unsigned stride_rcp = (unsigned)(0x100000000ull / (unsigned)g.stride);
+    const int ib = (pt >= per_board) + (pt >= 2 * per_board) + (pt >= 3 * per_board), ij = pt - ib * per_board;
+    auto request = [&](int t, int buf) {
+      if (pt < n_items && t < n_tiles) {
+        const unsigned R0t = (unsigned)(row_begin + (long long)t * TILE_M);
+        unsigned q = __umulhi(R0t, stride_rcp);               // floor(2^32 / stride) underestimates by < 1
+        if (R0t - q * (unsigned)g.stride >= (unsigned)g.stride) q++;
+        const int slot = (int)q + ib;
+        if (slot < g.G) {
+          const uint32_t dst = smem_u32(s_bb + (pg * 2 + buf) * C1_BB_ITEMS + pt);
+          if (ij < 2 * args.NW) {
+            const uint64_t* src = (ij < args.NW ? args.lx : args.lo) + (size_t)slot * args.NW + (ij < args.NW ? ij : ij - args.NW);
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(src) : "memory");
+          } else {
+            const char* src = ij == 2 * args.NW ? reinterpret_cast<const char*>(args.ltm) + (slot & ~3)
+                                                : reinterpret_cast<const char*>(args.llast) + ((2 * slot) & ~3);
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src) : "memory");
+          }
+        }
+      }
+      asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    if (!PLANES) {
+      request((int)blockIdx.x + pg * (int)gridDim.x, 0);
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+    }
+    const int TR = g.B + 2;                                  // table rows per (board, plane): rr = -1 .. B
+    const unsigned tr_rcp = (65536u + (unsigned)TR - 1u) / (unsigned)TR;      // e / TR == (e * tr_rcp) >> 16 for e < 128
+    int tl = 0;
+    for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, tl++) {
+      if ((tl % C1_NPG) != pg) continue;
+      const int st = tl % C1_STAGES;
+      const uint32_t ph = (tl / C1_STAGES) & 1;
+      const long long R0 = row_begin + (long long)t * TILE_M;
+      uint32_t words[16], words3[16];
+#pragma unroll
+      for (int j = 0; j < 16; j++) { words[j] = 0u; words3[j] = 0u; }
+      if (!PLANES) {
+        const int buf = (tl / C1_NPG) & 1;
+        const uint64_t* bb = s_bb + (pg * 2 + buf) * C1_BB_ITEMS;
+        C1_STAMP(pt == 0, 0);
+        request(t + C1_NPG * (int)gridDim.x, buf ^ 1);
+        asm volatile("bar.sync %0, 128;" ::"r"(1 + pg) : "memory");        // bb[buf] (landed last iteration) is visible
+        C1_STAMP(pt == 0, 1);
+        // Row-bit table: tab[board][plane][rr + 1] = (the B cells of board row rr in that plane) << 1, zero for
+        // rr = -1 / B.  The 3-bit column pattern (c-1, c, c+1) of cell (rr, c) is then (tab >> c) & 7 with the
+        // board edges handled by the zero bits at both ends.  Planes: side to move's stones, opponent's, last move.
+        uint32_t* tab = s_tab + (pg * 2 + buf) * C1_TAB;
+        unsigned sA = __umulhi((unsigned)R0, stride_rcp);
+        if ((unsigned)R0 - sA * (unsigned)g.stride >= (unsigned)g.stride) sA++;
+        for (int e = pt; e < nb * 3 * TR; e += 128) {        // one pass for every supported board (<= 126 entries)
+          const int combo = (int)(((unsigned)e * tr_rcp) >> 16), ri = e - combo * TR, rr = ri - 1;
+          const int b = combo / 3, pl = combo - 3 * b;
+          const int slot = (int)sA + b;
+          uint32_t v = 0;
+          if (rr >= 0 && rr < g.B && slot < g.G) {
+            const uint64_t* sx = bb + b * per_board;
+            if (pl == 2) {
+              const int last = (int)(int16_t)((uint32_t)sx[2 * args.NW + 1] >> (16 * (slot & 1)));     // -1 if none
+              const int rel = last - rr * g.B;
+              if (last >= 0 && rel >= 0 && rel < g.B) v = 2u << rel;
+            } else {
+              const bool xm = (((uint32_t)sx[2 * args.NW] >> (8 * (slot & 3))) & 0xFFu) == 1u;
+              const uint64_t* wsrc = ((pl == 0) == xm) ? sx : sx + args.NW;
+              const int bit = rr * g.B, wi = bit >> 6, sh = bit & 63;
+              uint64_t w = wsrc[wi] >> sh;
+              if (sh && wi + 1 < args.NW) w |= wsrc[wi + 1] << (64 - sh);
+              v = ((uint32_t)w & ((1u << g.B) - 1u)) << 1;
+            }
+          }
+          tab[e] = v;
+        }
+        asm volatile("bar.sync %0, 128;" ::"r"(1 + pg) : "memory");
+        C1_STAMP(pt == 0, 2);
+        unsigned pos = (unsigned)R0 + (unsigned)pt - sA * (unsigned)g.stride;
+        int b = 0;
+        while (pos >= (unsigned)g.stride) { pos -= (unsigned)g.stride; b++; }
+        int y, x;
+        if (g.P == 16) { y = (int)(pos >> 4); x = (int)(pos & 15u); } else { y = (int)(pos / 24u); x = (int)pos - y * 24; }
+        if (y >= 1 && x >= 1 && x <= g.B && (int)sA + b < g.G) {
+          const uint32_t* tb = tab + b * 3 * TR + (y - 1);
+          uint32_t bits = 1u << 27;
+#pragma unroll
+          for (int ky = 0; ky < 3; ky++)
+#pragma unroll
+            for (int pl = 0; pl < 3; pl++) bits |= ((tb[pl * TR + ky] >> (x - 1)) & 7u) << (ky * 9 + pl * 3);
+#pragma unroll
+          for (int c = 0; c < 4; c++) {
+            const uint4 v = s_lut[(bits >> (8 * c)) & 0xFFu];
+            words[4 * c] = v.x; words[4 * c + 1] = v.y; words[4 * c + 2] = v.z; words[4 * c + 3] = v.w;
+          }
+        }
+      } else {
+        const long long R = R0 + pt;
+        const int slot = (int)(R / g.stride), pos = (int)(R % g.stride);
+        const int y = pos / g.P, x = pos % g.P;
+        if (y >= 1 && x >= 1 && x <= g.B && slot - slot0 < count && slot < g.G) {
+          const float* pb = args.planes + (size_t)(slot - slot0) * 4 * g.A;
+          __nv_bfloat16 vals[32], vals3[16];
+#pragma unroll
+          for (int k = 0; k < 32; k++) vals[k] = __float2bfloat16(k == 27 ? 1.f : 0.f);
+#pragma unroll
+          for (int k = 0; k < 16; k++) vals3[k] = __float2bfloat16(0.f);
+#pragma unroll
+          for (int ky = 0; ky < 3; ky++) {
+            const int rr = y - 1 + ky - 1;
+            if (rr < 0 || rr >= g.B) continue;
+#pragma unroll
+            for (int kx = 0; kx < 3; kx++) {
+              const int cc = x - 1 + kx - 1;
+              if (cc < 0 || cc >= g.B) continue;
+#pragma unroll
+              for (int pl = 0; pl < 3; pl++) vals[ky * 9 + pl * 3 + kx] = __float2bfloat16(pb[pl * g.A + rr * g.B + cc]);
+              vals3[ky * 3 + kx] = __float2bfloat16(pb[3 * g.A + rr * g.B + cc]);
+            }
+          }
+#pragma unroll
+          for (int j = 0; j < 16; j++) {
+            __nv_bfloat162 h2; h2.x = vals[2 * j]; h2.y = vals[2 * j + 1];
+            words[j] = *reinterpret_cast<uint32_t*>(&h2);
+          }
+#pragma unroll
+          for (int j = 0; j < 8; j++) {
+            __nv_bfloat162 h2; h2.x = vals3[2 * j]; h2.y = vals3[2 * j + 1];
+            words3[j] = *reinterpret_cast<uint32_t*>(&h2);
+          }
+        }
+      }
+      C1_STAMP(pt == 0, 3);
+      mbar_wait(&done[st], ph ^ 1);
+      C1_STAMP(pt == 0, 4);
+      const int sw = (pt >> 1) & 3;                          // SWIZZLE_64B: 16-byte chunk index ^= address bits [7,8]
+      uint8_t* rowp = s_a + (size_t)st * C1_A_BYTES + pt * 64;
+#pragma unroll
+      for (int c = 0; c < 4; c++)
+        *reinterpret_cast<uint4*>(rowp + ((c ^ sw) << 4)) = make_uint4(words[4 * c], words[4 * c + 1], words[4 * c + 2], words[4 * c + 3]);
+      if (PLANES) {
+        uint8_t* rowp3 = s_a3 + (size_t)st * C1_A_BYTES + pt * 64;
+#pragma unroll
+        for (int c = 0; c < 4; c++)
+          *reinterpret_cast<uint4*>(rowp3 + ((c ^ sw) << 4)) = make_uint4(words3[4 * c], words3[4 * c + 1], words3[4 * c + 2], words3[4 * c + 3]);
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to UMMA
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&full[st]);
+      if (!PLANES) asm volatile("cp.async.wait_group 0;" ::: "memory");   // next tile's leaf inputs have landed
+    }
+  } else {
+    // ===== epilogue: group eg drains the tiles with (tl & 1) == eg; warp q owns TMEM lanes 32q..32q+31 =====
+    const int eg = (warp - 1 - 4 * C1_NPG) >> 2;
+    const int q = warp & 3;
+    const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
+    const int m = q * 32 + lane;
+    const bool issuer = ((warp - 1 - 4 * C1_NPG) & 3) == 0 && lane == 0;
+    int tl = 0;
+    for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, tl++) {
+      if ((tl & 1) != eg) continue;
+      const int st = tl % C1_STAGES;
+      const uint32_t ph = (tl / C1_STAGES) & 1;
+      C1_STAMP(issuer, 8);
+      mbar_wait_sleep(&done[st], ph);
+      C1_STAMP(issuer, 9);
+      tc_fence_after();
+      uint32_t packed[16];
+#pragma unroll
+      for (int hf = 0; hf < 2; hf++) {                         // 16 channels at a time: hi-part + lo-part products
+        uint32_t r[16], r2[16];
+        tmem_ld16_nowait(tmem_base + lane_addr + (uint32_t)(st * 64 + hf * 16), r);
+        tmem_ld16_nowait(tmem_base + lane_addr + (uint32_t)(st * 64 + 32 + hf * 16), r2);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+          __nv_bfloat162 hh = __floats2bfloat162_rn(fmaxf(__uint_as_float(r[2 * j]) + __uint_as_float(r2[2 * j]), 0.f),
+                                                    fmaxf(__uint_as_float(r[2 * j + 1]) + __uint_as_float(r2[2 * j + 1]), 0.f));
+          packed[hf * 8 + j] = *reinterpret_cast<uint32_t*>(&hh);
+        }
+      }
+      C1_STAMP(issuer, 10);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty[st]);
+      // two staging buffers per group: the TMA store issued two tiles ago (same buffer) has finished reading it --
+      // its issuer waited for that (wait_group.read 1) before arriving at this barrier
+      uint8_t* obuf = s_out + (eg * 2 + ((tl >> 1) & 1)) * C1_A_BYTES;
+      asm volatile("bar.sync %0, 128;" ::"r"(1 + C1_NPG + eg) : "memory");
+      C1_STAMP(issuer, 11);
+#pragma unroll
+      for (int c = 0; c < 4; c++)
+        *reinterpret_cast<uint4*>(obuf + m * 64 + ((c ^ ((m >> 1) & 3)) << 4)) =
+            make_uint4(packed[4 * c], packed[4 * c + 1], packed[4 * c + 2], packed[4 * c + 3]);
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      asm volatile("bar.sync %0, 128;" ::"r"(1 + C1_NPG + eg) : "memory");
+      C1_STAMP(issuer, 12);
+      if (issuer) {
+        const unsigned R0 = (unsigned)row_begin + (unsigned)t * TILE_M;
+        asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+                     ::"l"((uint64_t)&map_out), "r"(smem_u32(obuf)), "r"(0), "r"((int)R0) : "memory");
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+      }
+      C1_STAMP(issuer, 13);
+    }
+    if (issuer) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem_base, 64 * C1_STAGES);
+}
+
 // ---- FC heads as tensor-core GEMMs -------------------------------------------------------------------------
 // job 0 (blockIdx.y == 0): policy_fc  logits[b][a] = feat[b][0:PK] . Wp[a][:] + bp[a]  then softmax over ALL cells
 // job 1 (blockIdx.y == 1): value_fc1 (+ReLU), value_fc2, tanh                          (net.py:64-70)
@@ -761,9 +1122,7 @@ __global__ void __launch_bounds__(FC_THREADS, 1) fc_umma_kernel(const __grid_con
                                                                 const __grid_constant__ CUtensorMap map_wp,
                                                                 const __grid_constant__ CUtensorMap map_wv,
                                                                 const FcArgs args) {
-  const int count = args.count_dev ? *args.count_dev : args.count_host;
   const int tile = blockIdx.x;
-  if (tile * TILE_M >= count) return;
   const FcJob job = args.job[blockIdx.y];
   const CUtensorMap* map_w = blockIdx.y == 0 ? &map_wp : &map_wv;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -778,7 +1137,6 @@ __global__ void __launch_bounds__(FC_THREADS, 1) fc_umma_kernel(const __grid_con
   float* s_w2 = s_bias + 512;                                       // [64] + [1] (+pad)
   float* s_part = s_w2 + 72;                                        // [4][128] per-row partial max / sum, [128] 1/sum
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int row0 = (args.back ? args.G - count : 0) + tile * TILE_M;
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < args.stages; i++) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
@@ -792,6 +1150,15 @@ __global__ void __launch_bounds__(FC_THREADS, 1) fc_umma_kernel(const __grid_con
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+
+  pdl_wait();                      // leaf count + head features come from the previous kernels of the stream
+  pdl_launch_dependents();
+  const int count = args.count_dev ? *args.count_dev : args.count_host;
+  const int row0 = (args.back ? args.G - count : 0) + tile * TILE_M;
+  if (tile * TILE_M >= count) {    // nothing to do for this tile: release TMEM and leave (uniform per CTA)
+    if (warp == 1) tmem_dealloc(tmem_base, 512);
+    return;
+  }
 
   if (warp == 0) {
     if (lane == 0) {
@@ -973,6 +1340,8 @@ struct UmmaWorkspace {
   CUtensorMap map_act1, map_act2, map_feat;
   CUtensorMap map_act1_s, map_act2_s;  // single-load boxes (128+2P+2 rows)
   CUtensorMap map_act2_out;            // conv2 epilogue: TMA store of one [128 rows][64 ch] tile
+  CUtensorMap map_act1_out;            // conv1 (tensor core) epilogue: TMA store of one [128 rows][32 ch] tile
+  int conv1_mode = 1;                  // 1: conv1_umma_kernel, 0: SIMT table kernel (AZP_CONV1=simt)
   int single = 0;
   long long* clk = nullptr;            // AZP_CLK=1: per-tile stamps of conv3's CTA 0
   size_t rows = 0;
@@ -993,6 +1362,7 @@ struct UmmaWeights {
   float* w1_bits = nullptr;           // [tap][3][32]
   float* w1_tab = nullptr;            // [plane(3)][ky][pattern(8)][32]: sum over set pattern bits kx of w1[co][plane][ky][kx]
   float* w1_planes = nullptr;         // [tap][4][32]
+  __nv_bfloat16* w1_umma = nullptr;   // [4][32][32]: hi, lo (k = ky*9+plane*3+kx, k=27 bias), plane-3 hi, lo (k = ky*3+kx)
   __nv_bfloat16* head_w16 = nullptr;  // [16][128] 1x1 head conv weights (policy rows first, zero padded)
   float* head_b8 = nullptr;           // [8]
   __nv_bfloat16* wp16 = nullptr;      // [A][PKp] policy_fc weights, K contiguous, zero padded
@@ -1067,6 +1437,10 @@ int azp_umma_create(azp_engine* e) {
   if ((st = make_map(e, &ws->map_act1_s, ws->act1, ws->rows, 32, stage_rows + 2))) return st;
   if ((st = make_map(e, &ws->map_act2_s, ws->act2, ws->rows, 64, stage_rows + 2))) return st;
   if ((st = make_map(e, &ws->map_act2_out, ws->act2, ws->rows, 64, TILE_M))) return st;
+  if ((st = make_map(e, &ws->map_act1_out, ws->act1, ws->rows, 32, TILE_M))) return st;
+  { const char* v = getenv("AZP_CONV1"); ws->conv1_mode = (v && !strcmp(v, "simt")) ? 0 : 1; }
+  AZP_CUDA(e, cudaFuncSetAttribute(conv1_umma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, conv1_smem_bytes(false)));
+  AZP_CUDA(e, cudaFuncSetAttribute(conv1_umma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, conv1_smem_bytes(true)));
   { const char* v = getenv("AZP_SINGLE_LOAD"); ws->single = v ? atoi(v) : 1; }
   if (getenv("AZP_CLK")) { if ((st = e->alloc(&ws->clk, (size_t)64 * 16))) return st; AZP_CUDA(e, cudaMemset(ws->clk, 0, 64 * 16 * 8)); }
   cudaDeviceProp prop;
@@ -1179,6 +1553,24 @@ int azp_umma_build(azp_engine* e, const HostNet& net, NetWeights* W) {
   }
   if ((st = up(e, &U->w1_planes, w1p))) return st;
   if ((st = up(e, &U->b1, c1.b))) return st;
+  {
+    // tensor-core conv1: B operands [32 cout][32 k] bf16, value split v = hi + lo
+    std::vector<__nv_bfloat16> wu((size_t)4 * 32 * 32, __float2bfloat16(0.f));
+    auto put = [&](int mat, int co, int k, float v) {
+      const __nv_bfloat16 hi = __float2bfloat16(v);
+      wu[((size_t)mat * 32 + co) * 32 + k] = hi;
+      wu[((size_t)(mat + 1) * 32 + co) * 32 + k] = __float2bfloat16(v - __bfloat162float(hi));
+    };
+    for (int co = 0; co < 32; co++) {
+      for (int ky = 0; ky < 3; ky++)
+        for (int kx = 0; kx < 3; kx++) {
+          for (int pl = 0; pl < 3; pl++) put(0, co, ky * 9 + pl * 3 + kx, c1.w[((size_t)co * 4 + pl) * 9 + ky * 3 + kx]);
+          put(2, co, ky * 3 + kx, c1.w[((size_t)co * 4 + 3) * 9 + ky * 3 + kx]);
+        }
+      put(0, co, 27, c1.b[co]);
+    }
+    if ((st = up(e, &U->w1_umma, wu))) return st;
+  }
   // conv2/conv3: bf16 [tap][cout][cin] (K-major rows of one tap = UMMA B operand)
   auto pack = [&](const HostConv& c, __nv_bfloat16** dst) {
     std::vector<__nv_bfloat16> w((size_t)9 * c.cout * c.cin);
@@ -1301,10 +1693,11 @@ static int run_trunk(azp_engine* e, NetWeights* W, const int32_t* count_dev, int
   a2.w1 = U->w1_tab; a2.b1 = U->b1;
   { static int dbg = -1; if (dbg < 0) { const char* v = getenv("AZP_DEBUG_CONV"); dbg = v ? atoi(v) : 0; } a2.debug = dbg; }
   if (from_bits)
-    conv_umma_kernel<32, 64, STAGES2, false, true><<<grid, CONV_THREADS_BITS, ws->smem2, s>>>(ws->map_act1, U->map_w2, ws->map_act2_out, a2);
+    azp_launch(conv_umma_kernel<32, 64, STAGES2, false, true>, grid, CONV_THREADS_BITS, ws->smem2, s, true, ws->map_act1,
+               U->map_w2, ws->map_act2_out, a2);
   else
-    conv_umma_kernel<32, 64, STAGES2, false, false><<<grid, CONV_THREADS_EPI2, ws->smem2, s>>>(
-        a2.single ? ws->map_act1_s : ws->map_act1, U->map_w2, ws->map_act2_out, a2);
+    azp_launch(conv_umma_kernel<32, 64, STAGES2, false, false>, grid, CONV_THREADS_EPI2, ws->smem2, s, true,
+               a2.single ? ws->map_act1_s : ws->map_act1, U->map_w2, ws->map_act2_out, a2);
   azp_count_launch();
   ConvArgs a3 = a2;
   a3.bias = U->b3; a3.out = nullptr; a3.head_b = U->head_b8; a3.feat = ws->feat;
@@ -1314,8 +1707,8 @@ static int run_trunk(azp_engine* e, NetWeights* W, const int32_t* count_dev, int
   a3.stage_bytes = (a3.single ? (a3.stage_rows + 2 + 7) / 8 * 8 : a3.stage_rows) * 128;
   e->prof_flops_per_board = 2.0 * 9.0 * 64 * 128 * g.A;
   azp_prof_begin(e, count_dev, count_host, s);
-  conv_umma_kernel<64, 128, STAGES3, true, false><<<grid, CONV_THREADS, ws->smem3, s>>>(
-      a3.single ? ws->map_act2_s : ws->map_act2, U->map_w3, U->map_hw, a3);
+  azp_launch(conv_umma_kernel<64, 128, STAGES3, true, false>, grid, CONV_THREADS, ws->smem3, s, true,
+             a3.single ? ws->map_act2_s : ws->map_act2, U->map_w3, U->map_hw, a3);
   azp_count_launch();
   azp_prof_end(e, s);
   return launch_fc(e, W, count_dev, count_host, back, logits, policy, value, out_by_index, s);
@@ -1337,7 +1730,26 @@ static int launch_fc(azp_engine* e, NetWeights* W, const int32_t* count_dev, int
   fa.vfc2_w = W->vfc2_w; fa.vfc2_b = W->vfc2_b; fa.logits = logits; fa.policy = policy; fa.value = value;
   fa.count_dev = count_dev; fa.count_host = count_host; fa.back = back; fa.out_by_index = out_by_index;
   dim3 fc_grid((zmax + TILE_M - 1) / TILE_M, 2);
-  fc_umma_kernel<<<fc_grid, FC_THREADS, ws->fc_smem, s>>>(ws->map_feat, U->map_wp, U->map_wv, fa);
+  azp_launch(fc_umma_kernel, fc_grid, FC_THREADS, ws->fc_smem, s, true, ws->map_feat, U->map_wp, U->map_wv, fa);
+  azp_count_launch();
+  return azp_check_launch();
+}
+
+// conv1 on the tensor core: leaf bitboards (planes == null) or float planes -> act1
+static int launch_conv1_umma(azp_engine* e, UmmaWeights* U, const int32_t* count_dev, int count_host, int back,
+                             const float* planes, cudaStream_t s) {
+  UmmaWorkspace* ws = (UmmaWorkspace*)e->ws->umma;
+  const ConvGeom& g = ws->g;
+  const int zmax = count_dev ? g.G : count_host;
+  const int max_tiles = (int)(((long long)zmax * g.stride + TILE_M - 1) / TILE_M);
+  const int grid = max_tiles < 2 * ws->sms ? max_tiles : 2 * ws->sms;       // two CTAs per SM
+  Conv1Args a;
+  a.g = g; a.w = U->w1_umma; a.count_dev = count_dev; a.count_host = count_host; a.back = back;
+  a.lx = e->tv.leaf_x; a.lo = e->tv.leaf_o; a.ltm = e->tv.leaf_tm; a.llast = e->tv.leaf_last; a.NW = e->NW;
+  a.planes = planes;
+  { const char* v = getenv("AZP_CLK"); a.clk = (v && atoi(v) == 3) ? ws->clk : nullptr; }
+  if (planes) azp_launch(conv1_umma_kernel<true>, grid, C1_THREADS, conv1_smem_bytes(true), s, true, ws->map_act1_out, a);
+  else azp_launch(conv1_umma_kernel<false>, grid, C1_THREADS, conv1_smem_bytes(false), s, true, ws->map_act1_out, a);
   azp_count_launch();
   return azp_check_launch();
 }
@@ -1352,7 +1764,10 @@ int azp_umma_eval_leaves(azp_engine* e, NetWeights* W, const int32_t* count_dev,
   if (ws->tower) return run_tower(e, W, count_dev, count_host, back, 0, nullptr, nullptr, e->d_policy, e->d_value, 0, s);
   static int fuse = -1;
   if (fuse < 0) { const char* v = getenv("AZP_FUSE_CONV1"); fuse = v ? atoi(v) : 0; }
-  if (!fuse) {
+  if (!fuse && ws->conv1_mode == 1) {
+    int st = launch_conv1_umma(e, U, count_dev, count_host, back, nullptr, s);
+    if (st) return st;
+  } else if (!fuse) {
     const int grid = zmax < 4 * ws->sms ? zmax : 4 * ws->sms;
     AZP_DISPATCH_NW(e->NW, conv1_bits_kernel, grid, 256, 0, s, g, e->tv.leaf_x, e->tv.leaf_o, e->tv.leaf_tm,
                     e->tv.leaf_last, U->w1_tab, U->b1, ws->act1, count_dev, count_host, back);
@@ -1405,8 +1820,13 @@ int azp_umma_eval_planes(azp_engine* e, NetWeights* W, int n, const float* plane
   UmmaWeights* U = (UmmaWeights*)W->umma;
   const ConvGeom& g = ws->g;
   if (ws->tower) return run_tower(e, W, nullptr, n, 0, n, planes, logits, policy, value, 1, s);
-  const int grid = n < 4 * ws->sms ? n : 4 * ws->sms;
-  conv1_planes_kernel<<<grid, 256, 4 * g.A * sizeof(float), s>>>(g, n, planes, U->w1_planes, U->b1, ws->act1);
-  azp_count_launch();
+  if (ws->conv1_mode == 1) {
+    int st = launch_conv1_umma(e, U, nullptr, n, 0, planes, s);
+    if (st) return st;
+  } else {
+    const int grid = n < 4 * ws->sms ? n : 4 * ws->sms;
+    conv1_planes_kernel<<<grid, 256, 4 * g.A * sizeof(float), s>>>(g, n, planes, U->w1_planes, U->b1, ws->act1);
+    azp_count_launch();
+  }
   return run_trunk(e, W, nullptr, n, 0, logits, policy, value, 1, /*from_bits=*/false, s);
 }

@@ -118,13 +118,8 @@ __global__ void root_expand_kernel(RulesParams rp, TreeView tv, int n, const flo
 // path takes a VIRTUAL LOSS (N += 1, W -= 1, undone by expand_backup) so the next descent of the same step
 // goes elsewhere; an unexpanded edge reached twice in one step is a collision and the later descent idles.
 template <int NW>
-__global__ void select_kernel(RulesParams rp, TreeView tv, int n, double c_puct, int compact, int parity) {
-  int g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-  if (blockIdx.x == 0 && threadIdx.x == 0) {
-    tv.n_leaves[(parity ^ 1) * 2 + 0] = 0;
-    tv.n_leaves[(parity ^ 1) * 2 + 1] = 0;
-  }
-  if (g >= n) return;
+__device__ __forceinline__ void select_body(const RulesParams& rp, const TreeView& tv, int g, int lane, double c_puct,
+                                            int compact, int parity) {
   const int K = tv.K;
   const int rec0 = g * K;
   if (!tv.active[g]) {
@@ -166,7 +161,8 @@ __global__ void select_kernel(RulesParams rp, TreeView tv, int n, double c_puct,
 #pragma unroll
       for (int k = 0; k < NW; k++) stones += __popcll(x.w[k] | o.w[k]);
       // all of a node's edge statistics are fetched before any arithmetic: one memory round trip per level
-      constexpr int MAXI = (AZP_MAX_BOARD * AZP_MAX_BOARD + 31) / 32;
+      constexpr int MAXI = (2 * NW < (AZP_MAX_BOARD * AZP_MAX_BOARD + 31) / 32) ? 2 * NW   // A <= 64*NW cells = 2*NW per lane
+                                                                             : (AZP_MAX_BOARD * AZP_MAX_BOARD + 31) / 32;
       int nn_[MAXI], ch_[MAXI];
       double ww_[MAXI];
       float pp_[MAXI];
@@ -261,11 +257,12 @@ __global__ void select_kernel(RulesParams rp, TreeView tv, int n, double c_puct,
 }
 
 // ---- expand the evaluated leaves and back the values up (mcts.py:136-141, 50-64, 76-82) --------
+// returns false on a capacity overflow (error flag set)
 template <int NW>
-__global__ void expand_backup_kernel(RulesParams rp, TreeView tv, int n, const float* __restrict__ policy,
-                                     const float* __restrict__ value, int by_slot) {
-  int g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-  if (g >= n || !tv.active[g]) return;
+__device__ __forceinline__ bool expand_backup_body(const RulesParams& rp, const TreeView& tv, int g, int lane,
+                                                   const float* __restrict__ policy, const float* __restrict__ value,
+                                                   int by_slot) {
+  if (!tv.active[g]) return true;
   const int A = rp.A, K = tv.K;
   const size_t gbase = (size_t)g * tv.cap * A;
   unsigned long long n_exp = 0, n_sims = 0;
@@ -283,7 +280,7 @@ __global__ void expand_backup_kernel(RulesParams rp, TreeView tv, int n, const f
       int nid = tv.node_count[g];
       if (nid >= tv.cap) {
         if (lane == 0) atomicExch(tv.error_flag, AZP_ERR_CAPACITY);
-        return;
+        return false;
       }
       BB<NW> lx = bb_load<NW>(tv.leaf_x + (size_t)slot * NW), lo = bb_load<NW>(tv.leaf_o + (size_t)slot * NW);
       const size_t nb = gbase + (size_t)nid * A;
@@ -325,6 +322,52 @@ __global__ void expand_backup_kernel(RulesParams rp, TreeView tv, int n, const f
     count(tv, CNT_SIMS, n_sims);
     count(tv, CNT_EXPANSIONS, n_exp);
   }
+  return true;
+}
+
+// ---- kernels: the two halves alone (step-by-step API) and fused ------------------------------------------------
+// 2048 games = 512 CTAs of four warps: at >128 registers only 3 CTAs fit an SM (444 per wave) and the latency-bound
+// descent ran as TWO waves; capped so that one wave holds them all (4 CTAs x 148 SMs = 592)
+template <int NW>
+__global__ void __launch_bounds__(128, 4) select_kernel(RulesParams rp, TreeView tv, int n, double c_puct, int compact, int parity) {
+  pdl_wait();
+  pdl_launch_dependents();
+  int g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    tv.n_leaves[(parity ^ 1) * 2 + 0] = 0;
+    tv.n_leaves[(parity ^ 1) * 2 + 1] = 0;
+  }
+  if (g >= n) return;
+  select_body<NW>(rp, tv, g, lane, c_puct, compact, parity);
+}
+
+template <int NW>
+__global__ void expand_backup_kernel(RulesParams rp, TreeView tv, int n, const float* __restrict__ policy,
+                                     const float* __restrict__ value, int by_slot) {
+  pdl_wait();
+  pdl_launch_dependents();
+  int g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (g >= n) return;
+  expand_backup_body<NW>(rp, tv, g, lane, policy, value, by_slot);
+}
+
+// expand+backup of simulation step i followed at once by the descent of step i+1: the same warp owns the game in
+// both halves, so the two launches of the lockstep loop collapse into one (the tree lines just written are still
+// in L1/L2 when the descent re-reads them)
+template <int NW>
+__global__ void __launch_bounds__(128, 4) advance_kernel(RulesParams rp, TreeView tv, int n, const float* __restrict__ policy,
+                               const float* __restrict__ value, int by_slot, double c_puct, int compact, int parity) {
+  pdl_wait();
+  pdl_launch_dependents();
+  int g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    tv.n_leaves[(parity ^ 1) * 2 + 0] = 0;
+    tv.n_leaves[(parity ^ 1) * 2 + 1] = 0;
+  }
+  if (g >= n) return;
+  if (!expand_backup_body<NW>(rp, tv, g, lane, policy, value, by_slot)) return;
+  __syncwarp();               // the descent's lanes read edges other lanes of this warp have just written
+  select_body<NW>(rp, tv, g, lane, c_puct, compact, parity);
 }
 
 // ---- root visit counts (mcts.py:144) -----------------------------------------------------------
@@ -567,12 +610,19 @@ int azp_tree_root_expand(azp_engine* e, int n, const float* policy, int by_slot,
   return azp_check_launch();
 }
 int azp_tree_select(azp_engine* e, int n, int compact, int parity, cudaStream_t s) {
-  AZP_DISPATCH_NW(e->NW, select_kernel, warp_grid(n), 128, 0, s, e->rp, e->tv, n, e->cfg.c_puct, compact, parity);
+  AZP_DISPATCH_NW_PDL(e->NW, select_kernel, warp_grid(n), 128, 0, s, e->rp, e->tv, n, e->cfg.c_puct, compact, parity);
   azp_count_launch();
   return azp_check_launch();
 }
 int azp_tree_expand_backup(azp_engine* e, int n, const float* policy, const float* value, int by_slot, cudaStream_t s) {
-  AZP_DISPATCH_NW(e->NW, expand_backup_kernel, warp_grid(n), 128, 0, s, e->rp, e->tv, n, policy, value, by_slot);
+  AZP_DISPATCH_NW_PDL(e->NW, expand_backup_kernel, warp_grid(n), 128, 0, s, e->rp, e->tv, n, policy, value, by_slot);
+  azp_count_launch();
+  return azp_check_launch();
+}
+int azp_tree_advance(azp_engine* e, int n, const float* policy, const float* value, int by_slot, int compact, int parity,
+                     cudaStream_t s) {
+  AZP_DISPATCH_NW_PDL(e->NW, advance_kernel, warp_grid(n), 128, 0, s, e->rp, e->tv, n, policy, value, by_slot,
+                      e->cfg.c_puct, compact, parity);
   azp_count_launch();
   return azp_check_launch();
 }
