@@ -85,6 +85,30 @@ __device__ __forceinline__ double warp_sum_d(double v) {
   for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(AZP_FULL, v, o);
   return v;
 }
+__device__ __forceinline__ float warp_sum_f(float v) {
+#pragma unroll
+  for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(AZP_FULL, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max_f(float v) {
+#pragma unroll
+  for (int o = 16; o; o >>= 1) v = fmaxf(v, __shfl_xor_sync(AZP_FULL, v, o));
+  return v;
+}
+// softmax over ALL A cells of one row of raw logits (controller.py:49), evaluated by one warp:
+// p[a] = __expf(row[a] - m) * inv.  Every consumer of the bf16 net's raw logits (root expansion, leaf expansion,
+// azp_net_forward's policy output) goes through this one function with the same lane assignment (a = lane + 32k),
+// so they all see bit-identical probabilities.
+__device__ __forceinline__ void warp_softmax_stats(const float* __restrict__ row, int A, int lane, float& m, float& inv) {
+  float mx = -INFINITY;
+  for (int a = lane; a < A; a += 32) mx = fmaxf(mx, row[a]);
+  mx = warp_max_f(mx);
+  float z = 0.f;
+  for (int a = lane; a < A; a += 32) z += __expf(row[a] - mx);
+  z = warp_sum_f(z);
+  m = mx;
+  inv = 1.f / z;
+}
 __device__ __forceinline__ double warp_max_d(double v) {
 #pragma unroll
   for (int o = 16; o; o >>= 1) v = fmax(v, __shfl_xor_sync(AZP_FULL, v, o));

@@ -163,6 +163,7 @@ extern "C" int azp_create(const azp_config* cfg, azp_engine** out) {
   e->A = cfg->board * cfg->board;
   e->NW = AZP_WORDS(cfg->board);
   e->rp = azp_make_rules(cfg->board, cfg->win_length);
+  e->policy_logits = cfg->net_dtype == AZP_DTYPE_BF16 ? 1 : 0;
   int st = create_impl(e);
   if (st) {
     azp_set_global_error(e->error.empty() ? "engine creation failed" : e->error);
@@ -255,7 +256,7 @@ extern "C" int azp_search_begin(azp_engine* e, int n, const uint64_t* x, const u
 }
 extern "C" int azp_root_expand(azp_engine* e, const float* policy, int add_noise, void* stream) {
   if (!e || !policy || e->search_n < 1) return AZP_ERR_INVALID_ARG;
-  return azp_tree_root_expand(e, e->search_n, policy, /*by_slot=*/0, add_noise, (cudaStream_t)stream);
+  return azp_tree_root_expand(e, e->search_n, policy, /*by_slot=*/0, add_noise, /*logits=*/0, (cudaStream_t)stream);
 }
 extern "C" int azp_select(azp_engine* e, void* stream) {
   if (!e || e->search_n < 1) return AZP_ERR_INVALID_ARG;
@@ -269,7 +270,7 @@ extern "C" int azp_leaf_states(azp_engine* e, uint64_t* x, uint64_t* o, uint8_t*
 }
 extern "C" int azp_expand_backup(azp_engine* e, const float* policy, const float* value, void* stream) {
   if (!e || e->search_n < 1 || !policy || !value) return AZP_ERR_INVALID_ARG;
-  return azp_tree_expand_backup(e, e->search_n, policy, value, /*by_slot=*/0, (cudaStream_t)stream);
+  return azp_tree_expand_backup(e, e->search_n, policy, value, /*by_slot=*/0, /*logits=*/0, (cudaStream_t)stream);
 }
 extern "C" int azp_root_visits(azp_engine* e, int32_t* visits, void* stream) {
   if (!e || e->search_n < 1 || !visits) return AZP_ERR_INVALID_ARG;
@@ -298,15 +299,15 @@ static int search_move(azp_engine* e, int n, int add_noise, int two_nets, cudaSt
   AZP_CUDA(e, cudaMemsetAsync(tv.n_leaves, 0, 4 * sizeof(int32_t), s));
   if ((st = azp_tree_begin_move(e, n, 1, 1, /*parity=*/1, s))) return st;
   if ((st = eval_step(e, two_nets, 1, s))) return st;
-  if ((st = azp_tree_root_expand(e, n, e->d_policy, 1, add_noise, s))) return st;
+  if ((st = azp_tree_root_expand(e, n, e->d_policy, 1, add_noise, e->policy_logits, s))) return st;
   const int steps = (e->cfg.sims + e->K - 1) / e->K;      // K descents per game per step
   if ((st = azp_tree_select(e, n, 1, 0, s))) return st;   // descent of step 0
   // iteration i: net(pair i&1), then expand+backup(i) fused with the descent of step i+1 (pair (i+1)&1)
   auto iteration = [&](int i, bool last) -> int {
     int r = eval_step(e, two_nets, i & 1, s);
     if (r) return r;
-    if (last) return azp_tree_expand_backup(e, n, e->d_policy, e->d_value, 1, s);
-    return azp_tree_advance(e, n, e->d_policy, e->d_value, 1, 1, (i + 1) & 1, s);
+    if (last) return azp_tree_expand_backup(e, n, e->d_policy, e->d_value, 1, e->policy_logits, s);
+    return azp_tree_advance(e, n, e->d_policy, e->d_value, 1, e->policy_logits, 1, (i + 1) & 1, s);
   };
   int sim = 0;
   const bool want_graph = e->use_graph && steps >= 5;

@@ -135,7 +135,8 @@ struct azp_engine {
   NetWeights* weights[2] = {nullptr, nullptr};
   NetWorkspace* ws = nullptr;
   // evaluation outputs indexed by slot
-  float* d_policy = nullptr;   // [G][A]
+  float* d_policy = nullptr;   // [G][A]  fp32 net: probabilities; bf16 net: RAW LOGITS (policy_logits = 1), softmax in the consumer
+  int policy_logits = 0;
   float* d_logits = nullptr;   // [G][A]
   float* d_value = nullptr;    // [G]
   // self-play state
@@ -189,12 +190,15 @@ int azp_augment_launch(int board, int mode, int n_max, const int* n_dev, const f
 
 // azp_tree.cu
 int azp_tree_begin_move(azp_engine* e, int n, int emit, int compact, int parity, cudaStream_t s);  // reset trees, root result, roots -> eval batch
-int azp_tree_root_expand(azp_engine* e, int n, const float* policy, int by_slot, int add_noise, cudaStream_t s);
+// `logits` != 0: `policy` holds raw logits and the softmax over all cells happens in the consumer (bf16 net path)
+int azp_tree_root_expand(azp_engine* e, int n, const float* policy, int by_slot, int add_noise, int logits, cudaStream_t s);
 int azp_tree_select(azp_engine* e, int n, int compact, int parity, cudaStream_t s);
-int azp_tree_expand_backup(azp_engine* e, int n, const float* policy, const float* value, int by_slot, cudaStream_t s);
+int azp_tree_expand_backup(azp_engine* e, int n, const float* policy, const float* value, int by_slot, int logits,
+                           cudaStream_t s);
+int azp_softmax_rows(int n, int A, const float* logits, float* policy, cudaStream_t s);
 // expand+backup of the step just evaluated, then the descent of the next step (counter pair `parity`), one launch
-int azp_tree_advance(azp_engine* e, int n, const float* policy, const float* value, int by_slot, int compact, int parity,
-                     cudaStream_t s);
+int azp_tree_advance(azp_engine* e, int n, const float* policy, const float* value, int by_slot, int logits, int compact,
+                     int parity, cudaStream_t s);
 int azp_tree_root_visits(azp_engine* e, int n, int32_t* visits, cudaStream_t s);
 int azp_tree_leaf_states(azp_engine* e, int n, uint64_t* x, uint64_t* o, uint8_t* tm, int16_t* last, uint8_t* kind, cudaStream_t s);
 int azp_episode_seat(azp_engine* e, int n, int arena, cudaStream_t s);

@@ -1094,58 +1094,65 @@ __global__ void __launch_bounds__(C1_THREADS, 2) conv1_umma_kernel(const __grid_
 }
 
 // ---- FC heads as tensor-core GEMMs -------------------------------------------------------------------------
-// job 0 (blockIdx.y == 0): policy_fc  logits[b][a] = feat[b][0:PK] . Wp[a][:] + bp[a]  then softmax over ALL cells
-// job 1 (blockIdx.y == 1): value_fc1 (+ReLU), value_fc2, tanh                          (net.py:64-70)
-// One CTA = 128 boards (UMMA M).  A = bf16 feature rows, B = bf16 weight rows (both K-major, TMA, 128B
-// swizzle, K chunks of 64), fp32 accumulators in TMEM; every epilogue thread owns one board's whole row, so
-// softmax / the value tail need no cross-thread reduction.
-struct FcJob {
-  int n_total;                    // accumulator columns (multiple of 16)
-  int n_first;                    // N of the first UMMA (the second covers n_total - n_first, 0 if none)
-  int n_valid;                    // real outputs
-  int k_chunks;                   // ceil(K / 64)
-  int k_off;                      // first feature column of this job
-  const float* bias;              // [n_valid]
-};
+// blockIdx.y <  n_slices: policy_fc, one 64-column slice of the outputs:  logits[b][a] = feat[b][0:PK] . Wp[a][:] + bp[a]
+// blockIdx.y == n_slices: value_fc1 (+ReLU), value_fc2, tanh                                   (net.py:64-70)
+// One CTA = 128 boards (UMMA M) x 64 outputs (UMMA N).  A = bf16 feature rows, B = bf16 weight rows (both K-major,
+// TMA, 128B swizzle, K chunks of 64), fp32 accumulators in TMEM.  The kernel is bound by its operand loads
+// (latency, few CTAs), so the outputs are split over 4-6 CTAs per board tile and the policy job stops at the RAW
+// LOGITS: the softmax over all cells (controller.py:49) is done by the consumer -- one warp per board in the
+// expansion kernels / softmax_rows_kernel -- where it costs two warp reductions; no cross-CTA reduction here.
 struct FcArgs {
-  FcJob job[2];
-  int A, G, stages, b_rows;       // b_rows = rows of B staged per K chunk (multiple of 64)
+  int A, G, stages;
+  int n_slices;                   // policy output slices of 64 columns
+  int pk_chunks, vk_chunks;       // ceil(K / 64) of the policy / value job
+  int v_off;                      // first feature column of the value job
+  const float* pbias;             // [A]
+  const float* vbias;             // [64]
   const float* vfc2_w; const float* vfc2_b;
-  float* logits; float* policy; float* value;
+  float* logits; float* value;
   const int32_t* count_dev; int count_host; int back; int out_by_index;
 };
 
-constexpr int FC_EPI_WARPS = 16;                       // 4 per TMEM lane quarter, 64 accumulator columns each
+constexpr int FC_N = 64;
+constexpr int FC_EPI_WARPS = 8;                        // warp (q, h): TMEM lanes 32q..32q+31 (boards), columns 32h..32h+31
 constexpr int FC_THREADS = 64 + 32 * FC_EPI_WARPS;
+constexpr int FC_STAGE_BYTES = TILE_M * 128 + FC_N * 128;
+constexpr int FC_PITCH = FC_N + 1;                     // odd pitch: conflict-free row-per-thread staging writes
 
 __global__ void __launch_bounds__(FC_THREADS, 1) fc_umma_kernel(const __grid_constant__ CUtensorMap map_feat,
                                                                 const __grid_constant__ CUtensorMap map_wp,
                                                                 const __grid_constant__ CUtensorMap map_wv,
                                                                 const FcArgs args) {
   const int tile = blockIdx.x;
-  const FcJob job = args.job[blockIdx.y];
-  const CUtensorMap* map_w = blockIdx.y == 0 ? &map_wp : &map_wv;
+  const bool is_value = (int)blockIdx.y == args.n_slices;
+  const int slice = is_value ? 0 : (int)blockIdx.y;
+  const int k_chunks = is_value ? args.vk_chunks : args.pk_chunks;
+  const int k_off = is_value ? args.v_off : 0;
+  const CUtensorMap* map_w = is_value ? &map_wv : &map_wp;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  const int stage_bytes = TILE_M * 128 + args.b_rows * 128;
-  uint8_t* s_tail = smem + (size_t)args.stages * stage_bytes;
+  uint8_t* s_tail = smem + (size_t)args.stages * FC_STAGE_BYTES;
   uint64_t* full = reinterpret_cast<uint64_t*>(s_tail);
   uint64_t* empty = full + 8;
   uint64_t* tfull = empty + 8;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tfull + 1);
-  float* s_bias = reinterpret_cast<float*>(tmem_slot + 2);          // [512]
-  float* s_w2 = s_bias + 512;                                       // [64] + [1] (+pad)
-  float* s_part = s_w2 + 72;                                        // [4][128] per-row partial max / sum, [128] 1/sum
+  float* s_bias = reinterpret_cast<float*>(tmem_slot + 2);          // [64]
+  float* s_w2 = s_bias + 64;                                        // [64] + [1] (+pad)
+  float* s_part = s_w2 + 72;                                        // [2][128] value partial sums
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
+  // ---- prologue: constants only (overlaps the previous kernel's tail under programmatic dependent launch) ----
   if (threadIdx.x == 0) {
     for (int i = 0; i < args.stages; i++) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
     mbar_init(tfull, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  for (int i = threadIdx.x; i < 512; i += blockDim.x) s_bias[i] = i < job.n_valid ? job.bias[i] : 0.f;
+  if (threadIdx.x < 64) {
+    const int c = slice * FC_N + threadIdx.x;
+    s_bias[threadIdx.x] = is_value ? args.vbias[threadIdx.x] : (c < args.A ? args.pbias[c] : 0.f);
+  }
   if (threadIdx.x < 65) s_w2[threadIdx.x] = threadIdx.x < 64 ? args.vfc2_w[threadIdx.x] : args.vfc2_b[0];
-  if (warp == 1) tmem_alloc(tmem_slot, 512);
+  if (warp == 1) tmem_alloc(tmem_slot, FC_N);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -1156,40 +1163,36 @@ __global__ void __launch_bounds__(FC_THREADS, 1) fc_umma_kernel(const __grid_con
   const int count = args.count_dev ? *args.count_dev : args.count_host;
   const int row0 = (args.back ? args.G - count : 0) + tile * TILE_M;
   if (tile * TILE_M >= count) {    // nothing to do for this tile: release TMEM and leave (uniform per CTA)
-    if (warp == 1) tmem_dealloc(tmem_base, 512);
+    if (warp == 1) tmem_dealloc(tmem_base, FC_N);
     return;
   }
 
   if (warp == 0) {
     if (lane == 0) {
-      for (int kc = 0; kc < job.k_chunks; kc++) {
+      for (int kc = 0; kc < k_chunks; kc++) {
         const int st = kc % args.stages;
         const uint32_t ph = (kc / args.stages) & 1;
         mbar_wait(&empty[st], ph ^ 1);
-        mbar_expect_tx(&full[st], (uint32_t)stage_bytes);
-        uint8_t* sa = smem + (size_t)st * stage_bytes;
-        tma_load_2d(sa, &map_feat, &full[st], job.k_off + kc * 64, row0);
-        for (int r = 0; r < args.b_rows; r += 64) tma_load_2d(sa + TILE_M * 128 + r * 128, map_w, &full[st], kc * 64, r);
+        mbar_expect_tx(&full[st], (uint32_t)FC_STAGE_BYTES);
+        uint8_t* sa = smem + (size_t)st * FC_STAGE_BYTES;
+        tma_load_2d(sa, &map_feat, &full[st], k_off + kc * 64, row0);
+        tma_load_2d(sa + TILE_M * 128, map_w, &full[st], kc * 64, slice * FC_N);      // rows past the matrix: zero fill
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      const uint32_t idesc1 = umma_idesc(job.n_first);
-      const uint32_t idesc2 = umma_idesc(job.n_total - job.n_first);
+      const uint32_t idesc = umma_idesc(FC_N);
       uint32_t accumulate = 0;
-      for (int kc = 0; kc < job.k_chunks; kc++) {
+      for (int kc = 0; kc < k_chunks; kc++) {
         const int st = kc % args.stages;
         const uint32_t ph = (kc / args.stages) & 1;
         mbar_wait(&full[st], ph);
         tc_fence_after();
-        const uint32_t a_addr = smem_u32(smem + (size_t)st * stage_bytes);
+        const uint32_t a_addr = smem_u32(smem + (size_t)st * FC_STAGE_BYTES);
         const uint32_t b_addr = a_addr + TILE_M * 128;
 #pragma unroll
         for (int k = 0; k < 4; k++) {
-          umma_bf16(tmem_base, umma_desc(a_addr + k * 32, 128), umma_desc(b_addr + k * 32, 128), idesc1, accumulate);
-          if (job.n_total > job.n_first)
-            umma_bf16(tmem_base + job.n_first, umma_desc(a_addr + k * 32, 128),
-                      umma_desc(b_addr + job.n_first * 128 + k * 32, 128), idesc2, accumulate);
+          umma_bf16(tmem_base, umma_desc(a_addr + k * 32, 128), umma_desc(b_addr + k * 32, 128), idesc, accumulate);
           accumulate = 1;
         }
         umma_commit(&empty[st]);
@@ -1197,93 +1200,49 @@ __global__ void __launch_bounds__(FC_THREADS, 1) fc_umma_kernel(const __grid_con
       umma_commit(tfull);
     }
   } else {
-    // ===== epilogue: warp (q, p) owns rows 32q..32q+31 and accumulator columns 64p..64p+63 =====
-    const int q = warp & 3, p = (warp - 2) >> 2;
-    const int ew = warp - 2;                                   // 0..15
-    mbar_wait(tfull, 0);
+    // ===== epilogue =====
+    const int q = warp & 3, h = (warp - 2) >> 2;
+    const int ew = warp - 2;                                   // 0..7
+    mbar_wait_sleep(tfull, 0);
     tc_fence_after();
     const int trow = q * 32 + lane;
     const int bi = tile * TILE_M + trow;                       // index within the evaluated batch
     const bool valid = bi < count;
-    const int row = args.back ? args.G - count + bi : bi;
-    const int orow = args.out_by_index ? bi : row;
-    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(p * 64);
-    if (blockIdx.y == 0) {
-      const int A = args.A;
-      float m = -INFINITY;
-      // column blocks of 64: this warp takes blocks p, p+4 (the second only exists for boards > 16x16)
-      for (int c_begin = p * 64; c_begin < job.n_total; c_begin += 256) {      // pass 1: row maximum (+ raw logits)
-#pragma unroll
-        for (int h = 0; h < 2; h++) {
-          uint32_t r[32];
-          tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c_begin + h * 32), r);
-#pragma unroll
-          for (int i = 0; i < 32; i++) {
-            const int c = c_begin + h * 32 + i;
-            const float l = __uint_as_float(r[i]) + s_bias[c];
-            if (c < A) {
-              m = fmaxf(m, l);
-              if (valid && args.logits) args.logits[(size_t)orow * A + c] = l;
-            }
-          }
-        }
-      }
-      s_part[p * 128 + trow] = m;
-      asm volatile("bar.sync 1, 512;" ::: "memory");
-      m = fmaxf(fmaxf(s_part[trow], s_part[128 + trow]), fmaxf(s_part[256 + trow], s_part[384 + trow]));
-      asm volatile("bar.sync 1, 512;" ::: "memory");           // everyone has read the maxima
-      // pass 2: exp(l - max) staged unnormalised in the (now idle) pipeline buffers; TMEM is re-read, which
-      // is cheaper than keeping 64 values per thread in registers
+    uint32_t r[32];
+    tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(h * 32), r);
+    if (!is_value) {
+      // logits + bias staged in the (now idle) pipeline buffers, then written out coalesced: 256 contiguous bytes
+      // per board row and slice
       float* stage = reinterpret_cast<float*>(smem);
-      const int pitch = A | 1;                                 // odd pitch: conflict-free row-per-thread writes
-      float z = 0.f;
-      for (int c_begin = p * 64; c_begin < job.n_total; c_begin += 256) {
-        float* srow = stage + (size_t)trow * pitch;
 #pragma unroll
-        for (int h = 0; h < 2; h++) {
-          uint32_t r[32];
-          tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c_begin + h * 32), r);
-#pragma unroll
-          for (int i = 0; i < 32; i++) {
-            const int c = c_begin + h * 32 + i;
-            if (c < A) {
-              const float ex = __expf(__uint_as_float(r[i]) + s_bias[c] - m);
-              z += ex;
-              srow[c] = ex;
-            }
-          }
-        }
-      }
-      s_part[p * 128 + trow] = z;
-      asm volatile("bar.sync 1, 512;" ::: "memory");
-      if (p == 0)                                              // softmax over ALL cells (controller.py:49)
-        s_part[512 + trow] = 1.f / ((s_part[trow] + s_part[128 + trow]) + (s_part[256 + trow] + s_part[384 + trow]));
-      asm volatile("bar.sync 1, 512;" ::: "memory");
-      if (args.policy) {                                       // coalesced copy-out, 8 rows per warp
+      for (int i = 0; i < 32; i++) stage[trow * FC_PITCH + h * 32 + i] = __uint_as_float(r[i]) + s_bias[h * 32 + i];
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      if (args.logits) {
+        const int A = args.A;
         const int nrows = min(TILE_M, count - tile * TILE_M);
         const int orow0 = args.out_by_index ? tile * TILE_M : (args.back ? args.G - count + tile * TILE_M : tile * TILE_M);
-        float* out = args.policy + (size_t)orow0 * A;
+        float* out = args.logits + (size_t)orow0 * A + slice * FC_N;
+        const int ncols = min(FC_N, A - slice * FC_N);
         for (int rr = ew; rr < nrows; rr += FC_EPI_WARPS) {
-          const float* src = stage + (size_t)rr * pitch;
-          const float inv = s_part[512 + rr];
-          for (int a = lane; a < A; a += 32) out[(size_t)rr * A + a] = src[a] * inv;
+          const float* src = stage + rr * FC_PITCH;
+          for (int c = lane; c < ncols; c += 32) out[(size_t)rr * A + c] = src[c];
         }
       }
-    } else if (p == 0) {
-      float s = s_w2[64];
+    } else {
+      float sp = 0.f;
 #pragma unroll
-      for (int c0 = 0; c0 < 64; c0 += 32) {
-        uint32_t r[32];
-        tmem_ld32(taddr + c0, r);
-#pragma unroll
-        for (int i = 0; i < 32; i++) s = fmaf(fmaxf(__uint_as_float(r[i]) + s_bias[c0 + i], 0.f), s_w2[c0 + i], s);
+      for (int i = 0; i < 32; i++) sp = fmaf(fmaxf(__uint_as_float(r[i]) + s_bias[h * 32 + i], 0.f), s_w2[h * 32 + i], sp);
+      s_part[h * 128 + trow] = sp;
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      if (h == 0 && valid && args.value) {
+        const int row = args.back ? args.G - count + bi : bi;
+        args.value[args.out_by_index ? bi : row] = tanhf((s_part[trow] + s_part[128 + trow]) + s_w2[64]);
       }
-      if (valid && args.value) args.value[orow] = tanhf(s);
     }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem_base, 512);
+  if (warp == 1) tmem_dealloc(tmem_base, FC_N);
 }
 
 // ---- host side -----------------------------------------------------------------------------------------------
@@ -1417,12 +1376,8 @@ int azp_umma_create(azp_engine* e) {
   AZP_CUDA(e, cudaMemset(ws->feat, 0, ((size_t)g.G + TILE_M) * ws->FK * sizeof(__nv_bfloat16)));
   if ((st = make_map(e, &ws->map_feat, ws->feat, (uint64_t)g.G + TILE_M, ws->FK, TILE_M, 64))) return st;
   {
-    const int n_total = (g.A + 15) / 16 * 16;
-    ws->fc_b_rows = (n_total + 63) / 64 * 64;
-    const int stage = TILE_M * 128 + ws->fc_b_rows * 128;
-    ws->fc_stages = (200 * 1024) / stage; if (ws->fc_stages > 6) ws->fc_stages = 6;
-    ws->fc_smem = 1024 + ws->fc_stages * stage + 17 * 8 + 16 + (512 + 72 + 640) * 4 + 64;
-    if (n_total > 448 || ws->fc_stages < 2) { e->set_error("board too large for the FC head kernel"); return AZP_ERR_UNSUPPORTED; }
+    ws->fc_stages = 6;                         // 6 x 24 KB operand stages; the first two double as the logits staging tile
+    ws->fc_smem = 1024 + ws->fc_stages * FC_STAGE_BYTES + 17 * 8 + 16 + (64 + 72 + 256) * 4 + 64;
   }
   cudaDeviceProp prop0;
   AZP_CUDA(e, cudaGetDeviceProperties(&prop0, e->cfg.device));
@@ -1720,19 +1675,25 @@ static int launch_fc(azp_engine* e, NetWeights* W, const int32_t* count_dev, int
   UmmaWeights* U = (UmmaWeights*)W->umma;
   const ConvGeom& g = ws->g;
   const int zmax = count_dev ? g.G : count_host;
+  // The kernel writes RAW LOGITS.  Leaf path: `policy` is the engine's d_policy, consumed as logits by the expansion
+  // kernels (policy_logits = 1).  azp_net_forward: logits go to the caller's buffer (or the engine's scratch) and a
+  // one-warp-per-row softmax with the consumers' arithmetic produces `policy`.
+  const bool want_softmax = out_by_index != 0;
+  float* logits_out = want_softmax ? (logits ? logits : e->d_logits) : policy;
   FcArgs fa;
-  const int n_total = (g.A + 15) / 16 * 16;
-  fa.job[0].n_total = n_total; fa.job[0].n_first = n_total <= 256 ? n_total : 192; fa.job[0].n_valid = g.A;
-  fa.job[0].k_chunks = (ws->PKp + 63) / 64; fa.job[0].k_off = 0; fa.job[0].bias = W->pfc_b;
-  fa.job[1].n_total = 64; fa.job[1].n_first = 64; fa.job[1].n_valid = 64;
-  fa.job[1].k_chunks = (ws->VKp + 63) / 64; fa.job[1].k_off = ws->PKp; fa.job[1].bias = W->vfc1_b;
-  fa.A = g.A; fa.G = g.G; fa.stages = ws->fc_stages; fa.b_rows = ws->fc_b_rows;
-  fa.vfc2_w = W->vfc2_w; fa.vfc2_b = W->vfc2_b; fa.logits = logits; fa.policy = policy; fa.value = value;
+  fa.A = g.A; fa.G = g.G; fa.stages = ws->fc_stages;
+  fa.n_slices = (g.A + FC_N - 1) / FC_N;
+  fa.pk_chunks = (ws->PKp + 63) / 64; fa.vk_chunks = (ws->VKp + 63) / 64; fa.v_off = ws->PKp;
+  fa.pbias = W->pfc_b; fa.vbias = W->vfc1_b;
+  fa.vfc2_w = W->vfc2_w; fa.vfc2_b = W->vfc2_b; fa.logits = logits_out; fa.value = value;
   fa.count_dev = count_dev; fa.count_host = count_host; fa.back = back; fa.out_by_index = out_by_index;
-  dim3 fc_grid((zmax + TILE_M - 1) / TILE_M, 2);
+  dim3 fc_grid((zmax + TILE_M - 1) / TILE_M, fa.n_slices + 1);
   azp_launch(fc_umma_kernel, fc_grid, FC_THREADS, ws->fc_smem, s, true, ws->map_feat, U->map_wp, U->map_wv, fa);
   azp_count_launch();
-  return azp_check_launch();
+  int st = azp_check_launch();
+  if (st) return st;
+  if (want_softmax && policy) return azp_softmax_rows(count_host, g.A, logits_out, policy, s);
+  return AZP_OK;
 }
 
 // conv1 on the tensor core: leaf bitboards (planes == null) or float planes -> act1

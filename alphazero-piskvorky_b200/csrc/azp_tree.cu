@@ -71,7 +71,7 @@ __global__ void begin_move_kernel(RulesParams rp, TreeView tv, int n, int emit, 
 // ---- root priors (+ Dirichlet noise), mcts.py:109-120 ---------------------------------------
 template <int NW>
 __global__ void root_expand_kernel(RulesParams rp, TreeView tv, int n, const float* __restrict__ policy,
-                                   int by_slot, int add_noise, double alpha, double weight, uint64_t seed) {
+                                   int by_slot, int add_noise, double alpha, double weight, uint64_t seed, int logits) {
   int g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (g >= n || !tv.active[g]) return;
   const int A = rp.A;
@@ -80,6 +80,8 @@ __global__ void root_expand_kernel(RulesParams rp, TreeView tv, int n, const flo
 #pragma unroll
   for (int k = 0; k < NW; k++) occ.w[k] = x.w[k] | o.w[k];
   const float* prow = policy + (size_t)(by_slot ? tv.leaf_slot[g * tv.K] : g) * A;
+  float sm_m = 0.f, sm_inv = 1.f;               // `logits`: the row holds raw logits, softmax happens here
+  if (logits) warp_softmax_stats(prow, A, lane, sm_m, sm_inv);
   const size_t base = (size_t)g * tv.cap * A;   // node 0
   double gsum = 0.0;
   Philox rng = philox_for_game(seed, tv.game_id[g]);
@@ -93,7 +95,7 @@ __global__ void root_expand_kernel(RulesParams rp, TreeView tv, int n, const flo
     bool legal = !bb_test<NW>(occ, a);
     float p = 0.f;
     if (legal) {
-      p = prow[a];
+      p = logits ? __expf(prow[a] - sm_m) * sm_inv : prow[a];
       if (add_noise) {
         // policy[r,c] = (1-w)*policy[r,c] + w*eta with a float32 policy array (mcts.py:116):
         // float32 product, float64 sum, rounded back to float32 on store
@@ -261,7 +263,7 @@ __device__ __forceinline__ void select_body(const RulesParams& rp, const TreeVie
 template <int NW>
 __device__ __forceinline__ bool expand_backup_body(const RulesParams& rp, const TreeView& tv, int g, int lane,
                                                    const float* __restrict__ policy, const float* __restrict__ value,
-                                                   int by_slot) {
+                                                   int by_slot, int logits) {
   if (!tv.active[g]) return true;
   const int A = rp.A, K = tv.K;
   const size_t gbase = (size_t)g * tv.cap * A;
@@ -285,9 +287,12 @@ __device__ __forceinline__ bool expand_backup_body(const RulesParams& rp, const 
       BB<NW> lx = bb_load<NW>(tv.leaf_x + (size_t)slot * NW), lo = bb_load<NW>(tv.leaf_o + (size_t)slot * NW);
       const size_t nb = gbase + (size_t)nid * A;
       const float* prow = policy + row * A;
+      float sm_m = 0.f, sm_inv = 1.f;             // `logits`: raw logits in, softmax over all cells here (controller.py:49)
+      if (logits) warp_softmax_stats(prow, A, lane, sm_m, sm_inv);
       for (int a = lane; a < A; a += 32) {
         bool legal = !(bb_test<NW>(lx, a) || bb_test<NW>(lo, a));
-        tv.P[nb + a] = legal ? prow[a] : 0.f;     // prior = policy[r,c], not renormalised (mcts.py:63)
+        const float pa = logits ? __expf(prow[a] - sm_m) * sm_inv : prow[a];
+        tv.P[nb + a] = legal ? pa : 0.f;          // prior = policy[r,c], not renormalised (mcts.py:63)
         tv.N[nb + a] = 0;
         tv.W[nb + a] = 0.0;
         tv.child[nb + a] = CHILD_NONE;
@@ -343,12 +348,12 @@ __global__ void __launch_bounds__(128, 4) select_kernel(RulesParams rp, TreeView
 
 template <int NW>
 __global__ void expand_backup_kernel(RulesParams rp, TreeView tv, int n, const float* __restrict__ policy,
-                                     const float* __restrict__ value, int by_slot) {
+                                     const float* __restrict__ value, int by_slot, int logits) {
   pdl_wait();
   pdl_launch_dependents();
   int g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (g >= n) return;
-  expand_backup_body<NW>(rp, tv, g, lane, policy, value, by_slot);
+  expand_backup_body<NW>(rp, tv, g, lane, policy, value, by_slot, logits);
 }
 
 // expand+backup of simulation step i followed at once by the descent of step i+1: the same warp owns the game in
@@ -356,7 +361,8 @@ __global__ void expand_backup_kernel(RulesParams rp, TreeView tv, int n, const f
 // in L1/L2 when the descent re-reads them)
 template <int NW>
 __global__ void __launch_bounds__(128, 4) advance_kernel(RulesParams rp, TreeView tv, int n, const float* __restrict__ policy,
-                               const float* __restrict__ value, int by_slot, double c_puct, int compact, int parity) {
+                               const float* __restrict__ value, int by_slot, int logits, double c_puct, int compact,
+                               int parity) {
   pdl_wait();
   pdl_launch_dependents();
   int g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
@@ -365,7 +371,7 @@ __global__ void __launch_bounds__(128, 4) advance_kernel(RulesParams rp, TreeVie
     tv.n_leaves[(parity ^ 1) * 2 + 1] = 0;
   }
   if (g >= n) return;
-  if (!expand_backup_body<NW>(rp, tv, g, lane, policy, value, by_slot)) return;
+  if (!expand_backup_body<NW>(rp, tv, g, lane, policy, value, by_slot, logits)) return;
   __syncwarp();               // the descent's lanes read edges other lanes of this warp have just written
   select_body<NW>(rp, tv, g, lane, c_puct, compact, parity);
 }
@@ -579,8 +585,24 @@ __global__ void drain_raw_kernel(int32_t* raw_count, long long* out_written, int
   *raw_count = 0;
 }
 
+// rows of raw logits -> probabilities (azp_net_forward on the bf16 path); one warp per row, same arithmetic as the
+// consumers inside the search
+__global__ void softmax_rows_kernel(int n, int A, const float* __restrict__ logits, float* __restrict__ policy) {
+  int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (r >= n) return;
+  const float* row = logits + (size_t)r * A;
+  float m, inv;
+  warp_softmax_stats(row, A, lane, m, inv);
+  for (int a = lane; a < A; a += 32) policy[(size_t)r * A + a] = __expf(row[a] - m) * inv;
+}
+
 // ================= host side ====================================================================
 static inline int warp_grid(int n) { return (n * 32 + 127) / 128; }
+int azp_softmax_rows(int n, int A, const float* logits, float* policy, cudaStream_t s) {
+  softmax_rows_kernel<<<warp_grid(n), 128, 0, s>>>(n, A, logits, policy);
+  azp_count_launch();
+  return azp_check_launch();
+}
 
 static EpisodeView episode_view(azp_engine* e) {
   EpisodeView ev;
@@ -603,9 +625,9 @@ int azp_tree_begin_move(azp_engine* e, int n, int emit, int compact, int parity,
   azp_count_launch();
   return azp_check_launch();
 }
-int azp_tree_root_expand(azp_engine* e, int n, const float* policy, int by_slot, int add_noise, cudaStream_t s) {
+int azp_tree_root_expand(azp_engine* e, int n, const float* policy, int by_slot, int add_noise, int logits, cudaStream_t s) {
   AZP_DISPATCH_NW(e->NW, root_expand_kernel, warp_grid(n), 128, 0, s, e->rp, e->tv, n, policy, by_slot, add_noise,
-                  e->cfg.dirichlet_alpha, e->cfg.dirichlet_weight, e->cfg.seed);
+                  e->cfg.dirichlet_alpha, e->cfg.dirichlet_weight, e->cfg.seed, logits);
   azp_count_launch();
   return azp_check_launch();
 }
@@ -614,14 +636,15 @@ int azp_tree_select(azp_engine* e, int n, int compact, int parity, cudaStream_t 
   azp_count_launch();
   return azp_check_launch();
 }
-int azp_tree_expand_backup(azp_engine* e, int n, const float* policy, const float* value, int by_slot, cudaStream_t s) {
-  AZP_DISPATCH_NW_PDL(e->NW, expand_backup_kernel, warp_grid(n), 128, 0, s, e->rp, e->tv, n, policy, value, by_slot);
+int azp_tree_expand_backup(azp_engine* e, int n, const float* policy, const float* value, int by_slot, int logits,
+                           cudaStream_t s) {
+  AZP_DISPATCH_NW_PDL(e->NW, expand_backup_kernel, warp_grid(n), 128, 0, s, e->rp, e->tv, n, policy, value, by_slot, logits);
   azp_count_launch();
   return azp_check_launch();
 }
-int azp_tree_advance(azp_engine* e, int n, const float* policy, const float* value, int by_slot, int compact, int parity,
-                     cudaStream_t s) {
-  AZP_DISPATCH_NW_PDL(e->NW, advance_kernel, warp_grid(n), 128, 0, s, e->rp, e->tv, n, policy, value, by_slot,
+int azp_tree_advance(azp_engine* e, int n, const float* policy, const float* value, int by_slot, int logits, int compact,
+                     int parity, cudaStream_t s) {
+  AZP_DISPATCH_NW_PDL(e->NW, advance_kernel, warp_grid(n), 128, 0, s, e->rp, e->tv, n, policy, value, by_slot, logits,
                       e->cfg.c_puct, compact, parity);
   azp_count_launch();
   return azp_check_launch();
