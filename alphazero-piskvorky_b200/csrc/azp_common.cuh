@@ -147,6 +147,30 @@ __device__ __forceinline__ int warp_result(const RulesParams& rp, const BB<NW>& 
   return stones == rp.A ? 3 : 0;
 }
 
+// Result of a position reached by playing cell `a` from a NON-TERMINAL position: only the mover can own a line and
+// every such line passes through `a`, so instead of the full-board scan lane (d, k) tests the one WL-run that starts
+// k steps before `a` along direction d (32 lanes = 4 directions x up to 8 offsets; WL <= 8).  Same answer as
+// warp_result on every position reachable in play (games.py:133-166).  `mine` = the mover's stones including `a`.
+template <int NW>
+__device__ __forceinline__ bool warp_line_through(const RulesParams& rp, const BB<NW>& mine, int a, int lane) {
+  const int WL = rp.WL, B = rp.B;
+  const int d = lane >> 3, k = lane & 7;
+  bool hit = false;
+  if (k < WL) {
+    const int r = a / B, c = a - r * B;
+    const int dr = d == 0 ? 0 : 1, dc = d == 0 ? 1 : (d == 1 ? 0 : (d == 2 ? 1 : -1));
+    const int r0 = r - k * dr, c0 = c - k * dc;
+    const int r1 = r0 + (WL - 1) * dr, c1 = c0 + (WL - 1) * dc;
+    if (r0 >= 0 && r1 < B && c0 >= 0 && c0 < B && c1 >= 0 && c1 < B) {
+      hit = true;
+      int idx = r0 * B + c0;
+      const int step = dr * B + dc;
+      for (int j = 0; j < WL; j++, idx += step) hit = hit && bb_test<NW>(mine, idx);
+    }
+  }
+  return __ballot_sync(AZP_FULL, hit) != 0u;
+}
+
 // ---- Philox4x32-10 counter-based RNG ------------------------------------------------
 struct Philox {
   uint32_t key[2];

@@ -160,8 +160,9 @@ __device__ __forceinline__ void select_body(const RulesParams& rp, const TreeVie
       double best = -1.0e308;
       int besta = 0x7fffffff;
       int stones = 0;
+      uint64_t occw[NW];                         // occupancy: cell a = lane + 32i is bit lane + 32(i&1) of word i>>1
 #pragma unroll
-      for (int k = 0; k < NW; k++) stones += __popcll(x.w[k] | o.w[k]);
+      for (int k = 0; k < NW; k++) { occw[k] = x.w[k] | o.w[k]; stones += __popcll(occw[k]); }
       // all of a node's edge statistics are fetched before any arithmetic: one memory round trip per level
       constexpr int MAXI = (2 * NW < (AZP_MAX_BOARD * AZP_MAX_BOARD + 31) / 32) ? 2 * NW   // A <= 64*NW cells = 2*NW per lane
                                                                              : (AZP_MAX_BOARD * AZP_MAX_BOARD + 31) / 32;
@@ -177,7 +178,7 @@ __device__ __forceinline__ void select_body(const RulesParams& rp, const TreeVie
 #pragma unroll
       for (int i = 0; i < MAXI; i++) {
         const int a = lane + 32 * i;
-        const bool occupied = a >= A || bb_test<NW>(x, a) || bb_test<NW>(o, a);
+        const bool occupied = a >= A || ((occw[i >> 1] >> (lane + 32 * (i & 1))) & 1ull);
         if (occupied) continue;
         const int nn = nn_[i];
         // unvisited children (the vast majority of slots) need no fp64 division: Q = 0 and x / 1.0 == x exactly
@@ -187,7 +188,7 @@ __device__ __forceinline__ void select_body(const RulesParams& rp, const TreeVie
           q = __ddiv_rn(ww_[i], (double)nn);
           u = __ddiv_rn(num, (double)(1 + nn));
         }
-        double s = __dadd_rn(q, u);
+        const double s = nn ? __dadd_rn(q, u) : u;   // 0.0 + u == u exactly (u >= 0)
         if (s > best) { best = s; besta = a; }    // ascending a: the FIRST maximum is kept
       }
 #pragma unroll
@@ -212,9 +213,15 @@ __device__ __forceinline__ void select_body(const RulesParams& rp, const TreeVie
       if (lane == 0) path[depth] = node * A + a;
       depth++;
       if (tm == 1) bb_set<NW>(x, a); else bb_set<NW>(o, a);
+      if (rp.WL <= 8) {
+        // the parent was not terminal: only the mover can have completed a line, and only through `a`
+        const bool won = tm == 1 ? warp_line_through<NW>(rp, x, a, lane) : warp_line_through<NW>(rp, o, a, lane);
+        result = won ? tm : (stones + 1 == A ? 3 : 0);
+      } else {
+        result = warp_result<NW>(rp, x, o, lane);
+      }
       tm = 3 - tm;
       last = a;
-      result = warp_result<NW>(rp, x, o, lane);
       if (result != 0) continue;
       if (ch == CHILD_PENDING) { kind = 2; break; }          // collision with an earlier descent of this step
       if (ch < 0) {                                          // reached a child that has not been expanded
@@ -289,13 +296,17 @@ __device__ __forceinline__ bool expand_backup_body(const RulesParams& rp, const 
       const float* prow = policy + row * A;
       float sm_m = 0.f, sm_inv = 1.f;             // `logits`: raw logits in, softmax over all cells here (controller.py:49)
       if (logits) warp_softmax_stats(prow, A, lane, sm_m, sm_inv);
-      for (int a = lane; a < A; a += 32) {
-        bool legal = !(bb_test<NW>(lx, a) || bb_test<NW>(lo, a));
-        const float pa = logits ? __expf(prow[a] - sm_m) * sm_inv : prow[a];
-        tv.P[nb + a] = legal ? pa : 0.f;          // prior = policy[r,c], not renormalised (mcts.py:63)
-        tv.N[nb + a] = 0;
-        tv.W[nb + a] = 0.0;
-        tv.child[nb + a] = CHILD_NONE;
+#pragma unroll
+      for (int i = 0; i < 2 * NW; i++) {          // cell a = lane + 32i is bit lane + 32(i&1) of word i>>1
+        const int a = lane + 32 * i;
+        if (a < A) {
+          const bool legal = !(((lx.w[i >> 1] | lo.w[i >> 1]) >> (lane + 32 * (i & 1))) & 1ull);
+          const float pa = logits ? __expf(prow[a] - sm_m) * sm_inv : prow[a];
+          tv.P[nb + a] = legal ? pa : 0.f;        // prior = policy[r,c], not renormalised (mcts.py:63)
+          tv.N[nb + a] = 0;
+          tv.W[nb + a] = 0.0;
+          tv.child[nb + a] = CHILD_NONE;
+        }
       }
       __syncwarp();
       if (lane == 0) {

@@ -191,13 +191,17 @@ def run_engine_arm(args):
     total_games = 1 << 40                    # endless stream of games: finished slots are re-seated
     first_flag = [True] * E
 
-    def move_steps(k, n, start_event, done_events, e2e, d2h_acc):
+    def move_steps(k, n, start_event, done_events, e2e, d2h_acc, profile_last=False):
         """n move steps of engine k on its stream (runs in its own host thread)."""
         torch.cuda.set_device(local)
         with torch.cuda.stream(streams[k]):
             if start_event is not None:
                 streams[k].wait_event(start_event)
-            for _ in range(n):
+            for i in range(n):
+                if profile_last and i == n - 1:
+                    # the dominant kernel is bracketed with CUDA events on the LAST timed step only: the event nodes
+                    # cut the programmatic-dependent-launch edges around it, so the other steps run unperturbed
+                    engines[k].set_profiling(True)
                 if e2e:
                     engines[k].load_blob(blob_host.numpy())            # weights: host -> device, every step
                 st, _, _, _, w = engines[k].selfplay(total_games, first_game=0, out=outs[k],
@@ -209,13 +213,13 @@ def run_engine_arm(args):
                     d2h_acc[k] += w * (5 * BOARD * BOARD + 1) * 4
             done_events[k].record(streams[k])
 
-    def run_all(n, e2e=False):
+    def run_all(n, e2e=False, profile_last=False):
         """All engines advance n move steps concurrently; returns device milliseconds (start -> all done)."""
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         done = [torch.cuda.Event() for _ in range(E)]
         d2h_acc = [0] * E
         ev0.record()
-        threads = [threading.Thread(target=move_steps, args=(k, n, ev0, done, e2e, d2h_acc)) for k in range(E)]
+        threads = [threading.Thread(target=move_steps, args=(k, n, ev0, done, e2e, d2h_acc, profile_last)) for k in range(E)]
         for t in threads:
             t.start()
         for t in threads:
@@ -247,14 +251,19 @@ def run_engine_arm(args):
 
     # ---- kernel-only arm: inputs resident in HBM --------------------------------------------------
     profile_inline = os.environ.get("AZP_BENCH_NOPROF", "0") != "1"
-    for eng in engines:
-        eng.set_profiling(profile_inline)
+    if profile_inline:               # instantiate the profiled step graph outside the timed region
+        for eng in engines:
+            eng.set_profiling(True)
+        run_all(1)
+        for eng in engines:
+            eng.get_profile()
+            eng.set_profiling(False)
     c0 = counters()
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
     barrier()
-    ms, _ = run_all(args.steps)
+    ms, _ = run_all(args.steps, profile_last=profile_inline)
     barrier()
     clocks = sampler.stop() if rank == 0 else None
     c1 = counters()
@@ -366,9 +375,9 @@ def run_engine_arm(args):
             "kernel_ms_per_launch": kms / klaunches if klaunches else None, "kernel_launches": klaunches,
             "kernel_share_of_step": ((kms / klaunches) * (-(-args.sims // max(1, args.leaves_per_step)) + 1) / (ms / args.steps)
                                      if klaunches and ms else None),
-            "kernel_timing": "CUDA events around the kernel inside the timed region; launches replayed from the "
-                             "2-step CUDA graph are sampled once per move step per graph slot (event-record nodes), "
-                             "plain stream launches are all timed",
+            "kernel_timing": "CUDA events around the kernel on the last step of the timed region (event-record nodes in "
+                             "the replayed 2-step CUDA graph, sampled once per graph slot, plus the plain launches of that "
+                             "step); the other timed steps run without the event nodes",
             "net_tensor_frac_end_to_end": (evals_done / (ms / 1e3)) * flops_per_leaf / 1e12 / world / peak_tf,
         },
         "virtual_loss_mode": None if vl is None else {
