@@ -16,9 +16,10 @@ from .mcts import MCTS
 from .net import GomokuNet, GomokuTowerNet
 from .replay_buffer import ReplayBuffer
 from .self_play import SelfPlayManager, default_temperature_schedule
+from .trainer import Trainer, adamw_step
 
 __all__ = [
     "Engine", "EngineError", "Gomoku", "GomokuBatch", "MCTS", "GomokuNet", "GomokuTowerNet", "SelfPlayManager",
     "ReplayBuffer", "ModelEvaluator", "NeuralNetworkController", "make_policy_value_fn",
-    "default_temperature_schedule", "flatten_state_dict", "should_promote", "X", "O", "DRAW",
+    "default_temperature_schedule", "flatten_state_dict", "should_promote", "Trainer", "adamw_step", "X", "O", "DRAW",
 ]

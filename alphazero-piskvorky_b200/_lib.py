@@ -74,6 +74,13 @@ SIGNATURES = {
     "azp_reset_counters": (C.c_int, [P]),
     "azp_set_profiling": (C.c_int, [P, C.c_int]),
     "azp_get_profile": (C.c_int, [P, C.POINTER(C.c_double), C.POINTER(C.c_uint64), C.POINTER(C.c_double)]),
+    "azp_trainer_create": (C.c_int, [C.c_int, C.c_int, C.c_int, C.POINTER(P)]),
+    "azp_trainer_destroy": (None, [P]),
+    "azp_trainer_last_error": (C.c_char_p, [P]),
+    "azp_trainer_weight_count": (C.c_size_t, [P]),
+    "azp_train_loss_grad": (C.c_int, [P, C.c_int, P, P, P, P, P, P, P]),
+    "azp_adamw_step": (C.c_int, [C.c_size_t, P, P, P, P, C.c_int, C.c_double, C.c_double, C.c_double, C.c_double,
+                                 C.c_double, P]),
 }
 
 _lib = None

@@ -3,7 +3,8 @@
 The self-play path has NO collective inside the simulation loop.
 torch.distributed (NCCL over NVLink on the box, gloo in CPU tests) is used for exactly three
 things: all-gather of generated example slabs into every rank's replay buffer, broadcast of
-promoted weights from rank 0, and a 3-integer all-reduce of the arena tally."""
+promoted weights from rank 0, and a 3-integer all-reduce of the arena tally.  The training step
+ adds one more: the all-reduce of the flat gradient blob."""
 
 from __future__ import annotations
 
@@ -53,3 +54,11 @@ def all_reduce_wld(wins: int, losses: int, draws: int, group=None, device=None):
     t = torch.tensor([wins, losses, draws], dtype=torch.int64, device=device)
     dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
     return int(t[0]), int(t[1]), int(t[2])
+
+
+def all_reduce_mean(blob: torch.Tensor, group=None):
+    """Data-parallel training: average the flat gradient blob over ranks in place (equal local batch sizes
+    make this the gradient of the global batch mean)."""
+    dist.all_reduce(blob, op=dist.ReduceOp.SUM, group=group)
+    blob.div_(dist.get_world_size(group))
+    return blob

@@ -186,6 +186,29 @@ int azp_set_profiling(azp_engine* e, int enabled);
 int azp_get_profile(azp_engine* e, double* host_ms, uint64_t* host_launches, double* host_flops);
 int azp_reset_counters(azp_engine* e);
 
+/* ---- training step (the immediate consumer of the examples) ----------- */
+/* Stem net only (AZP_NET_STEM).  The trainer object owns activation / im2col / split-K workspaces for
+ * batches of up to max_batch positions; parameters, gradients and optimizer moments are caller-owned
+ * float32 device blobs in the azp_load_weights layout (reference state_dict order, PyTorch layouts). */
+typedef struct azp_trainer azp_trainer;
+int azp_trainer_create(int board, int max_batch, int device, azp_trainer** out);
+void azp_trainer_destroy(azp_trainer* t);
+const char* azp_trainer_last_error(const azp_trainer* t);     /* t may be NULL */
+size_t azp_trainer_weight_count(const azp_trainer* t);
+/* NeuralNetworkController.train_step up to loss.backward(), controller.py:117-124: forward of
+ * GomokuNet (net.py:55-72) on planes float32 [n][4][B][B], policy loss = F.cross_entropy(logits, pi)
+ * with probability targets pi float32 [n][B*B], value loss = F.mse_loss(value, z) with z float32 [n],
+ * gradients of (policy + value loss) w.r.t. every parameter -> grads (same layout as params; batch-mean
+ * reduced, deterministic).  losses float32 [4] on the device = {policy loss, value loss, mean entropy of
+ * the predicted policy, policy + value}.  grads may be NULL (forward + losses only). */
+int azp_train_loss_grad(azp_trainer* t, int n, const float* params, const float* planes, const float* pi,
+                        const float* z, float* grads, float* losses, void* stream);
+/* torch.optim.AdamW.step() (controller.py:75-79, 114-115, 125) on flat blobs, stateless: `step` is the
+ * 1-based step count of the bias corrections; the reference uses betas (0.9, 0.999), eps 1e-8,
+ * weight_decay 1e-4 and sets lr before every step.  In place on params / exp_avg / exp_avg_sq. */
+int azp_adamw_step(size_t n, float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int step,
+                   double lr, double beta1, double beta2, double eps, double weight_decay, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

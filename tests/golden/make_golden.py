@@ -42,6 +42,7 @@ with contextlib.redirect_stdout(io.StringIO()):
 
 import synth                             # noqa: E402
 from oracle import net as onet           # noqa: E402  (only for the synthetic weight generator)
+from oracle import train as otrain       # noqa: E402  (only for the synthetic batch generator)
 
 CODE = {None: 0, "X": 1, "O": 2, "D": 3}
 SIZES = ((5, 4), (9, 5), (15, 5), (19, 5))
@@ -480,12 +481,53 @@ def make_replay():
     np.savez_compressed(os.path.join(HERE, "replay.npz"), **out)
 
 
+TRAIN_CASES = ((5, 24, 3, 1e-3), (9, 16, 2, 5e-5))     # board, batch, steps, lr
+TRAIN_STRIDE = 4
+
+
+def train_sample(a: np.ndarray) -> np.ndarray:
+    """Fixture size control: big tensors are stored as every TRAIN_STRIDE-th element."""
+    a = np.asarray(a, dtype=np.float32).reshape(-1)
+    return a if a.size <= 4096 else a[::TRAIN_STRIDE].copy()
+
+
+def make_train():
+    """NeuralNetworkController.train_step (controller.py:82-131) of the UNMODIFIED reference on
+    seeded weights and batches: total loss per step, gradients left in ``param.grad`` by the first
+    step, parameters after the last step (AdamW, weight_decay 1e-4)."""
+    out = {}
+    for size, n, steps, lr in TRAIN_CASES:
+        params = onet.synthetic_stem_params(size, seed=100 + size)
+        model = ref_net.GomokuNet(board_size=size)
+        model.load_state_dict({k: torch.from_numpy(v) for k, v in params.items()})
+        with quiet():
+            ctrl = ref_controller.NeuralNetworkController(model, device="cpu")
+        planes, pi, z = otrain.synthetic_batch(size, n, seed=300 + size)
+        losses = []
+        for step in range(steps):
+            with quiet():
+                loss, _ = ctrl.train_step(torch.from_numpy(planes), torch.from_numpy(pi), torch.from_numpy(z), lr)
+            losses.append(loss)
+            if step == 0:
+                for k, p in ctrl.net.named_parameters():
+                    out[f"grad1_{size}_{k}"] = train_sample(p.grad.detach().numpy())
+        for k, p in ctrl.net.named_parameters():
+            out[f"final_{size}_{k}"] = train_sample(p.detach().numpy())
+        out[f"planes_{size}"] = planes.astype(np.uint8)
+        out[f"pi_{size}"] = pi
+        out[f"z_{size}"] = z
+        out[f"losses_{size}"] = np.array(losses, dtype=np.float64)
+        out[f"lr_{size}"] = np.array(lr)
+    np.savez_compressed(os.path.join(HERE, "train.npz"), **out)
+    print("train: losses", {s: out[f"losses_{s}"].tolist() for s, *_ in TRAIN_CASES})
+
+
 if __name__ == "__main__":
     torch.set_num_threads(1)
     only = set(sys.argv[1:])
     for name, fn in (("rules", make_rules), ("net", make_net), ("mcts", make_mcts),
                      ("mcts_ckpt", make_mcts_ckpt), ("selfplay", make_selfplay),
-                     ("arena", make_arena), ("replay", make_replay)):
+                     ("arena", make_arena), ("replay", make_replay), ("train", make_train)):
         if not only or name in only:
             fn()
     sizes = {f: os.path.getsize(os.path.join(HERE, f)) for f in sorted(os.listdir(HERE)) if f.endswith(".npz")}

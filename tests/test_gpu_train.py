@@ -1,0 +1,189 @@
+"""GPU parity tests of the training step: the CUDA kernels, called
+through the C ABI (azp_train_loss_grad / azp_adamw_step), against the oracle (PyTorch CPU autograd,
+as the reference's own arithmetic) and the fixture produced by the reference controller.
+
+Tolerances (fp32 arithmetic on both sides, different summation orders): losses 1e-5 relative;
+gradients 2e-5 of the tensor's largest gradient (measured against a float64 oracle, next to the
+error PyTorch's own fp32 CPU path makes); AdamW element-wise 2e-7."""
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import net as onet, train as otrain
+
+pytestmark = pytest.mark.gpu
+
+TRAIN_GOLDEN = ((5, 3), (9, 2))
+
+
+@pytest.fixture(scope="module")
+def az():
+    import alphazero_piskvorky_b200 as az
+    return az
+
+
+def flat_of(az, params):
+    return torch.from_numpy(az.flatten_state_dict(params)).cuda()
+
+
+def split_flat(flat, board):
+    out, off = {}, 0
+    shapes = onet.stem_shapes(board)
+    for k in otrain.PARAM_KEYS:
+        n = int(np.prod(shapes[k]))
+        out[k] = flat[off:off + n].reshape(shapes[k])
+        off += n
+    assert off == flat.size
+    return out
+
+
+def sample(a):
+    a = np.asarray(a, dtype=np.float32).reshape(-1)
+    return a if a.size <= 4096 else a[::4]
+
+
+@pytest.mark.parametrize("size,n", [(5, 24), (5, 1), (9, 16), (15, 7), (19, 3)])
+def test_loss_and_gradients_vs_oracle(az, size, n):
+    params = onet.synthetic_stem_params(size, seed=100 + size)
+    planes, pi, z = otrain.synthetic_batch(size, n, seed=300 + size)
+    tr = az.Trainer(size, max(n, 8))
+    assert tr.weight_count() == sum(int(np.prod(s)) for s in onet.stem_shapes(size).values())
+    losses, grads = tr.loss_grad(flat_of(az, params), torch.from_numpy(planes), torch.from_numpy(pi), torch.from_numpy(z))
+    losses = losses.cpu().numpy()
+    g = split_flat(grads.cpu().numpy(), size)
+    ref_l, ref_g = otrain.loss_and_grads(params, planes, pi, z, dtype=torch.float64)
+    _, f32_g = otrain.loss_and_grads(params, planes, pi, z, dtype=torch.float32)
+    for i, k in enumerate(("policy", "value", "entropy", "total")):
+        assert abs(losses[i] - ref_l[k]) <= 1e-5 * max(1.0, abs(ref_l[k])), k
+    for k in otrain.PARAM_KEYS:
+        scale = max(np.abs(ref_g[k]).max(), 1e-12)
+        err = np.abs(g[k] - ref_g[k]).max() / scale
+        torch_err = np.abs(f32_g[k] - ref_g[k]).max() / scale
+        assert err <= 2e-5, (k, err, torch_err)
+        assert g[k].shape == ref_g[k].shape
+    # channel 3 of the input is all zeros (games.py:86-129) => exactly zero gradient, as in the reference
+    assert not g["conv1.weight"][:, 3].any()
+    tr.close()
+
+
+@pytest.mark.parametrize("size,steps", TRAIN_GOLDEN)
+def test_first_step_gradients_vs_reference_golden(az, golden, size, steps):
+    g = golden("train.npz")
+    params = onet.synthetic_stem_params(size, seed=100 + size)
+    planes = torch.from_numpy(g[f"planes_{size}"].astype(np.float32))
+    tr = az.Trainer(size, planes.shape[0])
+    _, grads = tr.loss_grad(flat_of(az, params), planes, torch.from_numpy(g[f"pi_{size}"]), torch.from_numpy(g[f"z_{size}"]))
+    got = split_flat(grads.cpu().numpy(), size)
+    for k in otrain.PARAM_KEYS:
+        ref = g[f"grad1_{size}_{k}"]
+        assert np.abs(sample(got[k]) - ref).max() <= 2e-5 * max(np.abs(ref).max(), 1e-12), k
+
+
+def test_adamw_kernel_vs_torch(az):
+    rs = np.random.RandomState(5)
+    n = 100_003
+    p0 = rs.randn(n).astype(np.float32)
+    tp = torch.nn.Parameter(torch.from_numpy(p0.copy()))
+    opt = torch.optim.AdamW([tp], weight_decay=1e-4)
+    p = torch.from_numpy(p0.copy()).cuda()
+    m, v = torch.zeros_like(p), torch.zeros_like(p)
+    for step in range(1, 7):
+        gnp = (rs.randn(n) * 10.0 ** rs.randint(-6, 1, size=n)).astype(np.float32)
+        gnp[::17] = 0.0
+        lr = [1e-3, 5e-5, 2e-4, 1e-3, 1e-2, 5e-5][step - 1]
+        opt.param_groups[0]["lr"] = lr
+        tp.grad = torch.from_numpy(gnp.copy())
+        opt.step()
+        az.adamw_step(p, torch.from_numpy(gnp).cuda(), m, v, step, lr)
+        assert float((p.cpu() - tp.detach()).abs().max()) <= 2e-7, step
+        st = opt.state[tp]
+        assert float((m.cpu() - st["exp_avg"]).abs().max()) <= 1e-7 * max(1.0, float(st["exp_avg"].abs().max()))
+        assert float(((v.cpu() - st["exp_avg_sq"]).abs() / (st["exp_avg_sq"].abs() + 1e-30)).max()) <= 1e-5
+    with pytest.raises(ValueError):
+        az.adamw_step(p.cpu(), p, m, v, 1, 1e-3)
+
+
+@pytest.mark.parametrize("size,steps", TRAIN_GOLDEN)
+def test_train_steps_vs_reference_golden(az, golden, size, steps):
+    """NeuralNetworkController.train_step through the facade vs the reference controller's own run."""
+    g = golden("train.npz")
+    net = az.GomokuNet(board_size=size)
+    net.load_state_dict({k: torch.from_numpy(v) for k, v in onet.synthetic_stem_params(size, seed=100 + size).items()})
+    ctrl = az.NeuralNetworkController(net, device="cuda", batch_size=8)
+    planes = torch.from_numpy(g[f"planes_{size}"].astype(np.float32))
+    pi, z, lr = torch.from_numpy(g[f"pi_{size}"]), torch.from_numpy(g[f"z_{size}"]), float(g[f"lr_{size}"])
+    for step in range(steps):
+        loss, entropy = ctrl.train_step(planes, pi, z, lr)
+        assert abs(loss - g[f"losses_{size}"][step]) <= 1e-5 * g[f"losses_{size}"][step], step
+        assert 0.0 < entropy <= np.log(size * size) + 1e-4
+    sd = ctrl.net.state_dict()
+    for k in otrain.PARAM_KEYS:
+        # AdamW's first steps move every weight by ~lr whatever |grad|: a rounding difference in a near-zero gradient can
+        # flip a +-lr step, so the bulk must agree tightly and every element within 2*lr*steps (same rule as the oracle test)
+        d = np.abs(sample(sd[k].cpu().numpy()) - g[f"final_{size}_{k}"])
+        assert np.quantile(d, 0.995) <= 2e-6 and d.max() <= 2 * lr * steps + 1e-7, (k, np.quantile(d, 0.995), d.max())
+    # the module's parameters are views of the flat blob the kernels update
+    assert ctrl._bound() and next(ctrl.net.parameters()).is_cuda
+
+
+def test_full_batch_is_deterministic_and_linear(az):
+    """BASELINE-size batch (1024 positions of 15x15, constants.py:22): two runs are bit-identical (no atomics),
+    the batch gradient is the mean of the gradients of its halves, and a strided sample agrees with the oracle."""
+    size, n = 15, 1024
+    params = onet.synthetic_stem_params(size, seed=7)
+    planes, pi, z = otrain.synthetic_batch(size, n, seed=11)
+    P, X, PI, Z = flat_of(az, params), torch.from_numpy(planes).cuda(), torch.from_numpy(pi).cuda(), torch.from_numpy(z).cuda()
+    tr = az.Trainer(size, n)
+    l1, g1 = tr.loss_grad(P, X, PI, Z)
+    g1 = g1.clone()
+    l2, g2 = tr.loss_grad(P, X, PI, Z)
+    assert torch.equal(g1, g2) and torch.equal(l1, l2)
+    _, ga = tr.loss_grad(P, X[:512], PI[:512], Z[:512])
+    ga = ga.clone()
+    _, gb = tr.loss_grad(P, X[512:], PI[512:], Z[512:])
+    half = 0.5 * (ga + gb)
+    assert float((half - g1).abs().max()) <= 2e-5 * float(g1.abs().max())
+    ref_l, ref_g = otrain.loss_and_grads(params, planes, pi, z, dtype=torch.float32)
+    got = split_flat(g1.cpu().numpy(), size)
+    assert abs(float(l1[3]) - ref_l["total"]) <= 1e-5 * ref_l["total"]
+    for k in otrain.PARAM_KEYS:
+        scale = max(np.abs(ref_g[k]).max(), 1e-12)
+        assert np.abs(got[k] - ref_g[k]).max() / scale <= 1e-4, k      # both sides fp32 over 230400-term sums
+    with pytest.raises(az.EngineError):
+        tr.loss_grad(P, torch.zeros(n + 1, 4, size, size), torch.zeros(n + 1, size * size), torch.zeros(n + 1))
+    tr.close()
+
+
+def test_controller_train_loop_feeds_selfplay(az):
+    """self-play -> ReplayBuffer -> controller.train (controller.py:134-187) -> the next self-play reads the trained
+    weights (train.py:89-104): the closed loop on one device."""
+    net = az.GomokuNet(board_size=5)
+    ctrl = az.NeuralNetworkController(net, device="cuda", batch_size=64)
+    mgr = az.SelfPlayManager(ctrl, device="cuda", mcts_params={"num_simulations": 16, "c_puct": 2.0},
+                             concurrent_games=16, augment="d4")
+    data = mgr.generate_self_play(num_games=16)
+    buf = az.ReplayBuffer(capacity=4000)
+    buf.extend(data)
+    before = {k: v.detach().clone() for k, v in ctrl.net.state_dict().items()}
+    examples = buf.sample_batch(256)
+    first = ctrl.evaluate_losses(torch.stack([e[0] for e in examples]),
+                                 torch.stack([torch.from_numpy(e[1]) for e in examples]),
+                                 torch.tensor([float(e[2]) for e in examples]))
+    ctrl.train(examples, epochs=6, lr=1e-3)
+    assert len(ctrl.training_history) == 6
+    assert ctrl.training_history[-1]["policy"] + ctrl.training_history[-1]["value"] < first[0] + first[1]
+    after = ctrl.net.state_dict()
+    assert all(not torch.equal(before[k], after[k]) for k in before)
+    with pytest.raises(ValueError, match="does not match expected"):
+        ctrl.train([(torch.zeros(4, 6, 6), np.zeros((6, 6), np.float32), 0)], epochs=1)
+    # the engine now evaluates with the trained weights: its forward equals the module's forward
+    x = torch.stack([e[0] for e in examples[:8]]).cuda()
+    eng = mgr.engine(16)
+    eng.load_state_dict(ctrl.net.state_dict())
+    logits, _, value = eng.net_forward(x)
+    with torch.no_grad():
+        tl, tv = ctrl.net(x)
+    assert float((logits - tl).abs().max()) <= 1e-4 and float((value - tv.view(-1)).abs().max()) <= 1e-4
+    data2 = mgr.generate_self_play(num_games=4)
+    assert len(data2) >= 4 * 7 * 8

@@ -62,6 +62,23 @@ def test_engine_fails_loudly_without_gpu(az):
         az.Gomoku(5, 4).get_legal_actions()
 
 
+def test_trainer_fails_loudly_without_gpu(az):
+    """The training step has no CPU fallback either: the C ABI reports the missing device, the facade raises."""
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    import ctypes as C
+    lib = az._lib.load()
+    h = C.c_void_p()
+    assert lib.azp_trainer_create(5, 8, 0, C.byref(h)) == az._lib.ERR_CUDA
+    assert b"no CPU fallback" in lib.azp_trainer_last_error(None)
+    assert lib.azp_trainer_create(2, 8, 0, C.byref(h)) == az._lib.ERR_INVALID_ARG
+    ctrl = az.NeuralNetworkController(az.GomokuNet(5), device="cuda")
+    with pytest.raises(RuntimeError, match="no CPU"):
+        ctrl.train_step(torch.zeros(2, 4, 5, 5), torch.zeros(2, 5, 5), torch.zeros(2), 1e-3)
+    with pytest.raises(RuntimeError, match="no CPU"):
+        az.Trainer(5, 8)
+
+
 def test_create_rejects_bad_config(az):
     lib = az._lib.load()
     h = C.c_void_p()
@@ -150,7 +167,8 @@ def _gloo_worker(rank, world, port, q):
     blob = torch.arange(10, dtype=torch.float32) if rank == 0 else torch.zeros(10)
     d.broadcast_weights(blob, src=0)
     wld = d.all_reduce_wld(rank + 1, 2, 0, device="cpu")
-    q.put((rank, gz.tolist(), gp[:, 0, 0, 0].tolist(), gpi.shape, blob.tolist(), wld))
+    grads = d.all_reduce_mean(torch.full((6,), float(rank + 1)))       # data-parallel training: mean of the rank gradients
+    q.put((rank, gz.tolist(), gp[:, 0, 0, 0].tolist(), gpi.shape, blob.tolist(), wld, grads.tolist()))
     dist.destroy_process_group()
 
 
@@ -166,7 +184,8 @@ def test_multi_gpu_plumbing_on_gloo_world2():
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
-    for rank, gz, gp0, pishape, blob, wld in results:
+    for rank, gz, gp0, pishape, blob, wld, grads in results:
+        assert grads == [1.5] * 6
         assert gz == [0, 0, 0, 1, 1, 1, 1, 1]              # rank order, trimmed to the true counts
         assert gp0 == [0.0] * 3 + [1.0] * 5 and tuple(pishape) == (8, 3, 3)
         assert blob == [float(i) for i in range(10)]

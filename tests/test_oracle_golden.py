@@ -265,3 +265,55 @@ def test_replay_fifo(golden):
     small.extend([1, 2, 3])
     assert list(small.sample_batch(5)) == list(g["undersized_sample"])
     assert len(set(buf.sample_batch(4))) == 4
+
+
+# ---- training step -------------------------------------
+TRAIN_CASES = ((5, 3), (9, 2))     # board, steps -- as tests/golden/make_golden.py TRAIN_CASES
+
+
+def train_sample(a):
+    a = np.asarray(a, dtype=np.float32).reshape(-1)
+    return a if a.size <= 4096 else a[::4]
+
+
+@pytest.mark.parametrize("size,steps", TRAIN_CASES)
+def test_train_step_matches_reference_controller(golden, size, steps):
+    """oracle.train vs NeuralNetworkController.train_step of the reference (controller.py:82-131):
+    losses, first-step gradients, parameters after AdamW."""
+    from oracle import train as otrain
+    g = golden("train.npz")
+    planes, pi, z = otrain.synthetic_batch(size, len(g[f"z_{size}"]), seed=300 + size)
+    assert np.array_equal(planes.astype(np.uint8), g[f"planes_{size}"])        # the fixture's inputs
+    assert np.array_equal(pi, g[f"pi_{size}"]) and np.array_equal(z, g[f"z_{size}"])
+    st = otrain.TrainerState(net.synthetic_stem_params(size, seed=100 + size))
+    lr = float(g[f"lr_{size}"])
+    for step in range(steps):
+        losses = st.train_step(planes, pi, z, lr)
+        assert abs(losses["total"] - g[f"losses_{size}"][step]) <= 2e-6 * abs(g[f"losses_{size}"][step])
+        if step == 0:
+            for k in otrain.PARAM_KEYS:
+                ref = g[f"grad1_{size}_{k}"]
+                assert np.abs(train_sample(st.last_grads[k]) - ref).max() <= 1e-6 * max(1.0, np.abs(ref).max()), k
+    for k in otrain.PARAM_KEYS:
+        # AdamW's first steps move every weight by ~lr regardless of |grad|: an fp32 rounding difference in a
+        # near-zero gradient can flip a +-lr step, so the bulk must agree tightly and every element within 2*lr*steps
+        d = np.abs(train_sample(st.params[k]) - g[f"final_{size}_{k}"])
+        assert np.quantile(d, 0.999) <= 1e-6 and d.max() <= 2 * lr * steps + 1e-7, (k, d.max())
+
+
+def test_adamw_update_matches_torch():
+    import torch
+    from oracle import train as otrain
+    rs = np.random.RandomState(5)
+    p0 = rs.randn(4097).astype(np.float32)
+    tp = torch.nn.Parameter(torch.from_numpy(p0.copy()))
+    opt = torch.optim.AdamW([tp], weight_decay=otrain.WEIGHT_DECAY)
+    p, m, v = p0.copy(), np.zeros_like(p0), np.zeros_like(p0)
+    for step in range(1, 6):
+        gnp = (rs.randn(4097) * 10.0 ** rs.randint(-6, 1)).astype(np.float32)
+        lr = [1e-3, 5e-5, 2e-4, 1e-3, 1e-2][step - 1]
+        opt.param_groups[0]["lr"] = lr
+        tp.grad = torch.from_numpy(gnp.copy())
+        opt.step()
+        otrain.adamw_update(p, gnp, m, v, step, lr)
+        assert np.abs(p - tp.detach().numpy()).max() <= 2e-7
