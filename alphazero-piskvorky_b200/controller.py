@@ -31,6 +31,7 @@ class NeuralNetworkController:
         self._flat = self._exp_avg = self._exp_avg_sq = self._grads = None
         self._step = 0
         self._trainer = None
+        self.version = 0                        # bumped whenever the weights change (train_step / load): cached engines reload
 
     # ---- flat parameter blob ------------------------------------------------------------------------
     def _cuda_device(self):
@@ -100,6 +101,7 @@ class NeuralNetworkController:
         losses, grads = self.loss_and_grads(state_batch, mcts_probs, winner_batch)
         self._step += 1
         adamw_step(self._flat, grads, self._exp_avg, self._exp_avg_sq, self._step, lr, BETAS, EPS, self.weight_decay)
+        self.version += 1
         host = losses.cpu()
         return float(host[3]), float(host[2])
 
@@ -148,6 +150,7 @@ class NeuralNetworkController:
 
     def load(self, path):
         self.net.load_state_dict(torch.load(path, map_location="cpu", weights_only=True))
+        self.version += 1
 
     def eval(self):
         self.net.eval()
@@ -174,7 +177,10 @@ def make_policy_value_fn(controller, dtype=DTYPE_F32):
             if isinstance(net, GomokuTowerNet):
                 kw = dict(net_kind=NET_TOWER, tower_blocks=net.blocks, tower_channels=net.channels)
             eng = cache[b] = _e.Engine(board=b, win_length=state.win_length, games=1, sims=1, net_dtype=dtype, **kw)
+            eng.weights_version = None
+        if eng.weights_version != getattr(controller, "version", 0):      # the reference reads controller.net live
             eng.load_state_dict(net.state_dict())
+            eng.weights_version = getattr(controller, "version", 0)
         planes = state.encode().unsqueeze(0)
         _, policy, value = eng.net_forward(planes)
         return policy[0].cpu().numpy().reshape(b, b), float(value[0].item())

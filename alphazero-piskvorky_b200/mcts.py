@@ -60,9 +60,12 @@ class MCTS:
             eng = _e.Engine(board=board, win_length=win, games=n, sims=self.num_simulations, c_puct=self.c_puct,
                             dirichlet_alpha=self.dirichlet_alpha, dirichlet_weight=self.dirichlet_weight,
                             seed=self.seed, net_dtype=self.net_dtype, **kw)
-            if ctrl is not None:
-                eng.load_state_dict(ctrl.net.state_dict())
+            eng.weights_version = None
             self._engines[key] = eng
+        ctrl = getattr(self.policy_value_fn, "controller", None)
+        if ctrl is not None and eng.weights_version != getattr(ctrl, "version", 0):
+            eng.load_state_dict(ctrl.net.state_dict())        # the reference reads controller.net at every evaluation
+            eng.weights_version = getattr(ctrl, "version", 0)
         return eng
 
     # ---- batched search ------------------------------------------------------------------------------

@@ -38,6 +38,18 @@ def split_flat(flat, board):
     return out
 
 
+def torch_cuda_grads(params, planes, pi, z):
+    """The reference's arithmetic as it would run with DEVICE = "cuda": PyTorch autograd on cuDNN / cuBLAS, TF32 off."""
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    pc = {k: torch.from_numpy(params[k]).cuda().requires_grad_(True) for k in otrain.PARAM_KEYS}
+    logits, v = otrain.forward_train(pc, torch.from_numpy(planes).cuda())
+    loss = torch.nn.functional.cross_entropy(logits, torch.from_numpy(pi).cuda().flatten(1, -1)) + \
+        torch.nn.functional.mse_loss(v.view(-1), torch.from_numpy(z).cuda())
+    loss.backward()
+    return {k: pc[k].grad.cpu().numpy() for k in otrain.PARAM_KEYS}
+
+
 def sample(a):
     a = np.asarray(a, dtype=np.float32).reshape(-1)
     return a if a.size <= 4096 else a[::4]
@@ -96,7 +108,8 @@ def test_adamw_kernel_vs_torch(az):
         tp.grad = torch.from_numpy(gnp.copy())
         opt.step()
         az.adamw_step(p, torch.from_numpy(gnp).cuda(), m, v, step, lr)
-        assert float((p.cpu() - tp.detach()).abs().max()) <= 2e-7, step
+        ref = tp.detach()
+        assert float(((p.cpu() - ref).abs() / ref.abs().clamp(min=1.0)).max()) <= 2e-7, step     # one fp32 ulp
         st = opt.state[tp]
         assert float((m.cpu() - st["exp_avg"]).abs().max()) <= 1e-7 * max(1.0, float(st["exp_avg"].abs().max()))
         assert float(((v.cpu() - st["exp_avg_sq"]).abs() / (st["exp_avg_sq"].abs() + 1e-30)).max()) <= 1e-5
@@ -144,12 +157,19 @@ def test_full_batch_is_deterministic_and_linear(az):
     _, gb = tr.loss_grad(P, X[512:], PI[512:], Z[512:])
     half = 0.5 * (ga + gb)
     assert float((half - g1).abs().max()) <= 2e-5 * float(g1.abs().max())
-    ref_l, ref_g = otrain.loss_and_grads(params, planes, pi, z, dtype=torch.float32)
+    ref_l, ref_g = otrain.loss_and_grads(params, planes, pi, z, dtype=torch.float64)
+    cuda_g = torch_cuda_grads(params, planes, pi, z)
     got = split_flat(g1.cpu().numpy(), size)
     assert abs(float(l1[3]) - ref_l["total"]) <= 1e-5 * ref_l["total"]
     for k in otrain.PARAM_KEYS:
+        # 29.5 M ReLU units: a handful have a pre-activation within fp32 rounding of zero, and an fp32 forward that
+        # lands on the other side than float64 switches that unit's gradient on/off (measured: 3.9e-4 of conv1.weight's
+        # largest gradient, IDENTICAL for these kernels and for PyTorch's cuDNN path; 2e-5 on batches without such a
+        # unit).  The yardstick is therefore PyTorch's own fp32 CUDA error against float64 on the same batch.
         scale = max(np.abs(ref_g[k]).max(), 1e-12)
-        assert np.abs(got[k] - ref_g[k]).max() / scale <= 1e-4, k      # both sides fp32 over 230400-term sums
+        err = np.abs(got[k] - ref_g[k]).max() / scale
+        torch_err = np.abs(cuda_g[k] - ref_g[k]).max() / scale
+        assert err <= max(2e-5, 1.5 * torch_err), (k, err, torch_err)
     with pytest.raises(az.EngineError):
         tr.loss_grad(P, torch.zeros(n + 1, 4, size, size), torch.zeros(n + 1, size * size), torch.zeros(n + 1))
     tr.close()
@@ -165,7 +185,7 @@ def test_controller_train_loop_feeds_selfplay(az):
     data = mgr.generate_self_play(num_games=16)
     buf = az.ReplayBuffer(capacity=4000)
     buf.extend(data)
-    before = {k: v.detach().clone() for k, v in ctrl.net.state_dict().items()}
+    before = {k: v.detach().cpu().clone() for k, v in ctrl.net.state_dict().items()}
     examples = buf.sample_batch(256)
     first = ctrl.evaluate_losses(torch.stack([e[0] for e in examples]),
                                  torch.stack([torch.from_numpy(e[1]) for e in examples]),
@@ -174,7 +194,7 @@ def test_controller_train_loop_feeds_selfplay(az):
     assert len(ctrl.training_history) == 6
     assert ctrl.training_history[-1]["policy"] + ctrl.training_history[-1]["value"] < first[0] + first[1]
     after = ctrl.net.state_dict()
-    assert all(not torch.equal(before[k], after[k]) for k in before)
+    assert all(not torch.equal(before[k], after[k].cpu()) for k in before)
     with pytest.raises(ValueError, match="does not match expected"):
         ctrl.train([(torch.zeros(4, 6, 6), np.zeros((6, 6), np.float32), 0)], epochs=1)
     # the engine now evaluates with the trained weights: its forward equals the module's forward
@@ -187,3 +207,47 @@ def test_controller_train_loop_feeds_selfplay(az):
     assert float((logits - tl).abs().max()) <= 1e-4 and float((value - tv.view(-1)).abs().max()) <= 1e-4
     data2 = mgr.generate_self_play(num_games=4)
     assert len(data2) >= 4 * 7 * 8
+
+
+def test_training_loop_on_the_facade(az, tmp_path):
+    """train.py:39-131 end to end on the GPU at a tiny size: self-play -> buffer -> train -> arena -> promotion files,
+    reference on-disk formats (state_dict .pt, buffer.pkl = pickled deque of (Tensor, ndarray, int))."""
+    import os
+    import pickle
+    from collections import deque
+    from alphazero_piskvorky_b200.train import run_training
+    model_dir, buf = str(tmp_path / "models"), str(tmp_path / "buffer.pkl")
+    out = run_training(num_episodes=2, board_size=5, win_length=4, device="cuda", model_dir=model_dir, buffer_path=buf,
+                       num_games=12, num_simulations=12, batch_size=64, batches_per_episode=2, num_epochs=2,
+                       learning_rate=1e-3, evaluation_games=6, eval_simulations=8, concurrent_games=16)
+    assert len(out) == 2 and all(o["examples"] > 0 and 0.0 <= o["win_rate"] <= 1.0 for o in out)
+    assert out[1]["buffer"] > out[0]["buffer"]
+    pts = [f for f in os.listdir(model_dir) if f.endswith(".pt")]
+    assert len(pts) == 1 + sum(o["promoted"] for o in out)
+    sd = torch.load(os.path.join(model_dir, pts[0]), map_location="cpu", weights_only=True)
+    assert list(sd) == [f"{k}.{f}" for k in onet.STEM_KEYS for f in ("weight", "bias")]
+    with open(buf, "rb") as f:
+        d = pickle.load(f)
+    assert isinstance(d, deque) and len(d) == out[1]["buffer"]
+    s, p, zz = d[0]
+    assert isinstance(s, torch.Tensor) and s.shape == (4, 5, 5) and isinstance(p, np.ndarray) and isinstance(zz, int)
+
+
+def test_human_vs_ai_scripted(az):
+    """main.py:26-85 with scripted input: the model answers through MCTS.run(temperature=0) on the GPU."""
+    from alphazero_piskvorky_b200.main import human_vs_ai
+    log = []
+    state = {"game": None}
+
+    def out(x):
+        log.append(x)
+        if isinstance(x, az.Gomoku):
+            state["game"] = x
+
+    def scripted(_prompt):
+        r, c = state["game"].get_legal_actions()[0]
+        return f"{r} {c}"
+
+    winner = human_vs_ai(model=az.GomokuNet(board_size=5), board_size=5, win_length=4, num_simulations=24,
+                         input_fn=scripted, output_fn=out)
+    assert winner in ("X", "O", "D") and any(isinstance(x, str) and x.startswith("AI plays") for x in log)

@@ -190,3 +190,39 @@ def test_multi_gpu_plumbing_on_gloo_world2():
         assert gp0 == [0.0] * 3 + [1.0] * 5 and tuple(pishape) == (8, 3, 3)
         assert blob == [float(i) for i in range(10)]
         assert wld == (3, 4, 0)
+
+
+def test_checkpoint_and_buffer_formats(az, tmp_path, golden):
+    """reference-format files.  A reference ``state_dict`` (.pt, key names of net.py:37-53)
+    loads into the facade net unchanged; ModelLoader picks the newest file or creates a random-init one;
+    ``buffer.pkl`` is a pickled deque of (Tensor (4,B,B), ndarray (B,B), int) (replay_buffer.py:50-71)."""
+    import pickle
+    from collections import deque
+    from alphazero_piskvorky_b200.model_loader import ModelLoader
+    ck = golden("ref_ckpt_5x5.npz")                                       # tensors of the reference's shipped checkpoint
+    path = tmp_path / "models" / "5x5.pt"
+    os.makedirs(path.parent)
+    torch.save({k: torch.from_numpy(ck[k]) for k in ck.files}, path)
+    ctrl = az.NeuralNetworkController(az.GomokuNet(board_size=5), device="cuda")
+    v0 = ctrl.version
+    ctrl.load(str(path))
+    assert ctrl.version == v0 + 1
+    assert all(np.array_equal(ctrl.net.state_dict()[k].numpy(), ck[k]) for k in ck.files)
+    ctrl.save(str(tmp_path / "out.pt"))
+    again = torch.load(tmp_path / "out.pt", weights_only=True)
+    assert list(again) == list(ck.files) and all(np.array_equal(again[k].numpy(), ck[k]) for k in ck.files)
+    loader = ModelLoader(str(path.parent), board_size=5)
+    assert loader.best_path == str(path)
+    assert np.array_equal(loader.get_best_model().state_dict()["conv1.weight"].numpy(), ck["conv1.weight"])
+    fresh = ModelLoader(str(tmp_path / "empty"), board_size=5)
+    assert fresh.best_path is None and fresh.get_best_model().board_size == 5
+    assert len(os.listdir(tmp_path / "empty")) == 1                       # the random-init net was saved (model_loader.py:33-37)
+    buf = az.ReplayBuffer(capacity=5)
+    buf.extend([(torch.full((4, 5, 5), float(i)), np.full((5, 5), i, np.float32), i % 3 - 1) for i in range(7)])
+    buf.save(str(tmp_path / "buffer.pkl"))
+    with open(tmp_path / "buffer.pkl", "rb") as f:
+        raw = pickle.load(f)
+    assert isinstance(raw, deque) and len(raw) == 5 and float(raw[0][0][0, 0, 0]) == 2.0
+    other = az.ReplayBuffer(capacity=4)
+    other.load(str(tmp_path / "buffer.pkl"))
+    assert len(other) == 4 and float(other.all()[0][0][0, 0, 0]) == 3.0  # deque(maxlen) keeps the newest
