@@ -754,6 +754,314 @@ __global__ void __launch_bounds__(BITS ? CONV_THREADS_BITS : (HEADS ? CONV_THREA
   if (warp == 1) tmem_dealloc(tmem_base, TMEM_COLS);
 }
 
+// ---- conv3 + 1x1 heads on a CTA PAIR (tcgen05 cta_group::2) ------------------------------------------------------
+// The single-CTA conv3 above is bound by the shared-memory port: an SS-mode M128 N128 K16 UMMA reads 4 KB of A and
+// 4 KB of B per 64 tensor cycles = the whole 128 B/cycle.  Here two CTAs of a cluster (the two SMs of a TPC) execute
+// ONE M256 N128 K16 UMMA: each SM supplies the A rows of ITS 128-row tile and only HALF of B (64 of the 128 output
+// channels' weight rows), so a tile costs 4 + 2 KB per 64 cycles (96 B/cycle) and the resident weights shrink to
+// 72 KB per SM (two more activation stages).  Protocol (CUTLASS's 2-SM scheme):
+//   * both CTAs run a TMA producer for their own tile; the loads complete on the LEADER's full barrier (mapa), the
+//     leader's producer posts the expected bytes of both;
+//   * the leader's two issuer threads (even / odd tile pairs) issue every UMMA; tcgen05.commit multicasts the
+//     "stage free" / "accumulator ready" / "head accumulator ready" arrivals to the same barrier in both CTAs;
+//   * the epilogue warps of BOTH CTAs arrive on the LEADER's "accumulator drained" / "bf16 tile written" barriers
+//     (mbarrier.arrive on the mapa address), since only the leader issues;
+//   * the head GEMM is a TS-mode cta_group::2 UMMA: A = each CTA's activated tile in ITS tensor memory, B = 8 of the 16
+//     (padded) head-weight rows per CTA.
+constexpr int C3P_STAGES = 5;
+constexpr int C3P_CIN = 64, C3P_COUT = 128;
+constexpr int C3P_W_TAP_BYTES = (C3P_COUT / 2) * C3P_CIN * 2;          // 64 rows x 128 B
+constexpr int C3P_W_BYTES = 9 * C3P_W_TAP_BYTES;
+constexpr int C3P_HW_BYTES = (C3P_COUT / 64) * (HEAD_N / 2) * 128;     // 2 K chunks x 8 rows x 128 B
+
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ uint32_t cluster_id_x() { uint32_t r; asm volatile("mov.u32 %0, %%clusterid.x;" : "=r"(r)); return r; }
+__device__ __forceinline__ uint32_t cluster_count_x() { uint32_t r; asm volatile("mov.u32 %0, %%nclusterid.x;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cluster address of `p` (a shared variable of this CTA) in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t mapa_u32(const void* p, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_u32(p)), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// TMA load into THIS CTA's shared memory whose bytes are counted on a barrier of the pair's leader CTA
+__device__ __forceinline__ void tma_load_2d_pair(void* dst, const CUtensorMap* map, uint32_t leader_bar, int c_inner, int c_row) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(dst)), "l"((uint64_t)map), "r"(leader_bar), "r"(c_inner), "r"(c_row) : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_pair(uint32_t* dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols));
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;");
+}
+__device__ __forceinline__ void tmem_dealloc_pair(uint32_t addr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(ncols));
+}
+// arrive (once the issuing thread's earlier UMMAs retire) on the barrier at this offset in BOTH CTAs of the pair
+__device__ __forceinline__ void umma_commit_pair(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(smem_u32(bar)), "h"((uint16_t)3) : "memory");
+}
+__device__ __forceinline__ void umma_bf16_pair(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_bf16_ts_pair(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+}
+// instruction descriptor of the pair UMMA: D=f32, A=B=bf16, K-major, M=256 (128 rows per CTA), N
+__device__ __forceinline__ uint32_t umma_idesc_pair(uint32_t n) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((n >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+}
+
+__device__ __forceinline__ bool tp_limit_ok(int n_pairs, int ncl) { return (n_pairs + ncl - 1) / ncl <= 64; }
+
+__global__ void __launch_bounds__(CONV_THREADS, 1) conv3_pair_kernel(const __grid_constant__ CUtensorMap map_act,
+                                                                     const __grid_constant__ CUtensorMap map_w,
+                                                                     const __grid_constant__ CUtensorMap map_hw,
+                                                                     const ConvArgs args) {
+  constexpr int CIN = C3P_CIN, COUT = C3P_COUT, STAGES = C3P_STAGES;
+  constexpr int ROWB = CIN * 2;
+  constexpr int KSTEPS = CIN / 16;
+  constexpr uint32_t COL_ACT = 2 * COUT;
+  constexpr uint32_t COL_HEAD = COL_ACT + COUT;
+  constexpr int HEAD_CHAINS = 4;
+  constexpr uint32_t TMEM_COLS = 512;                       // 256 (two accumulators) + 128 (two bf16 tiles) + 128 (head partials)
+  constexpr int HALF = COUT / 2;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  const int stage_bytes = args.stage_bytes;
+  uint8_t* s_w = smem;                                      // 9 taps x [64 of the 128 couts][CIN]
+  uint8_t* s_a = s_w + C3P_W_BYTES;                         // STAGES x [stage_rows + 2][CIN]
+  uint8_t* s_hw = s_a + (size_t)STAGES * stage_bytes;       // [2 K chunks][8 of the 16 head rows][64] bf16, 128B swizzle
+  uint8_t* s_tail = s_hw + C3P_HW_BYTES;
+  uint64_t* full = reinterpret_cast<uint64_t*>(s_tail);     // [STAGES]  (the leader's are used)
+  uint64_t* empty = full + STAGES;                          // [STAGES]  per CTA, multicast commit
+  uint64_t* tfull = empty + STAGES;                         // [2]       per CTA, multicast commit
+  uint64_t* tempty = tfull + 2;                             // [2]       leader's: 16 arrivals (8 epilogue warps x 2 CTAs)
+  uint64_t* wbar = tempty + 2;                              // [1]       leader's: weights of both CTAs resident
+  uint64_t* act_full = wbar + 1;                            // [2]       leader's: 16 arrivals
+  uint64_t* head_full = act_full + 2;                       // [2]       per CTA, multicast commit
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(head_full + 2);
+  float* s_bias = reinterpret_cast<float*>(tmem_slot + 2);  // [COUT] + [8] head bias
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const ConvGeom g = args.g;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+
+  // ---- prologue (independent of the previous kernel's outputs) ----
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < STAGES; i++) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+    for (int i = 0; i < 2; i++) {
+      mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 16);
+      mbar_init(&act_full[i], 16); mbar_init(&head_full[i], 1);
+    }
+    mbar_init(wbar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  for (int i = threadIdx.x; i < COUT; i += blockDim.x) s_bias[i] = args.bias[i];
+  if (threadIdx.x < 8) s_bias[COUT + threadIdx.x] = args.head_b[threadIdx.x];
+  __syncthreads();
+  cluster_sync_all();                                       // both CTAs' barriers exist before anything signals across
+  if (threadIdx.x == 0) {
+    if (leader) mbar_expect_tx(wbar, 2 * (C3P_W_BYTES + C3P_HW_BYTES));
+    const uint32_t lw = mapa_u32(wbar, 0);
+    for (int tap = 0; tap < 9; tap++)
+      tma_load_2d_pair(s_w + tap * C3P_W_TAP_BYTES, &map_w, lw, 0, tap * COUT + (int)rank * (COUT / 2));
+    for (int kc = 0; kc < COUT / 64; kc++)
+      tma_load_2d_pair(s_hw + kc * (HEAD_N / 2) * 128, &map_hw, lw, kc * 64, (int)rank * (HEAD_N / 2));
+  }
+  if (warp == 1) tmem_alloc_pair(tmem_slot, TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  pdl_wait();
+  pdl_launch_dependents();
+  const int count = args.count_dev ? *args.count_dev : args.count_host;
+  const int slot0 = args.back ? g.G - count : 0;
+  const long long row_begin = (long long)slot0 * g.stride;
+  const long long rows_total = (long long)count * g.stride;
+  const int n_tiles = (int)((rows_total + TILE_M - 1) / TILE_M);
+  const int n_pairs = (n_tiles + 1) / 2;
+  const int cid = (int)cluster_id_x(), ncl = (int)cluster_count_x();
+  const bool stampc = args.clk && cid == 0 && leader && tp_limit_ok(n_pairs, ncl);
+  // this CTA's tile of pair tp is 2*tp + rank (a phantom tile past the end loads zero-filled rows and is discarded)
+
+  if (warp == 0) {
+    // ===== TMA producer (both CTAs): one box of 128+2P+2 rows per tile into the own stage =====
+    if (lane == 0) {
+      const uint32_t bytes = (uint32_t)(args.stage_rows + 2) * ROWB;
+      int it = 0;
+      for (int tp = cid; tp < n_pairs; tp += ncl, it++) {
+        const int st = it % STAGES;
+        if (stampc) args.clk[it * 16 + 0] = clock64();
+        mbar_wait(&empty[st], ((it / STAGES) & 1) ^ 1);
+        if (stampc) args.clk[it * 16 + 1] = clock64();
+        if (leader) mbar_expect_tx(&full[st], 2 * bytes);
+        const long long row = row_begin + (long long)(2 * tp + (int)rank) * TILE_M - g.P - 1;
+        tma_load_2d_pair(s_a + (size_t)st * stage_bytes, &map_act, mapa_u32(&full[st], 0), 0, (int)row);
+      }
+    }
+  } else if (warp == 1 || warp == 11) {
+    // ===== UMMA issuers (leader CTA only): even / odd tile pairs, one TMEM accumulator each =====
+    if (leader && lane == 0) {
+      const uint32_t idesc = umma_idesc_pair(COUT);
+      const uint32_t a_base = smem_u32(s_a), w_base = smem_u32(s_w);
+      const int my_parity = warp == 1 ? 0 : 1;
+      mbar_wait(wbar, 0);
+      tc_fence_after();
+      int tl = 0;
+      for (int tp = cid; tp < n_pairs; tp += ncl, tl++) {
+        if ((tl & 1) != my_parity) continue;
+        const int acc = tl & 1;
+        if (stampc) args.clk[tl * 16 + 2] = clock64();
+        mbar_wait(&tempty[acc], ((tl >> 1) & 1) ^ 1);          // both CTAs' epilogues have drained this accumulator
+        if (stampc) args.clk[tl * 16 + 3] = clock64();
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * COUT);
+        const int st = tl % STAGES;
+        mbar_wait(&full[st], (tl / STAGES) & 1);               // both CTAs' boxes have landed
+        if (stampc) args.clk[tl * 16 + 4] = clock64();
+        tc_fence_after();
+        const uint32_t a_stage = a_base + (uint32_t)st * (uint32_t)stage_bytes;
+        uint32_t accumulate = 0;
+#pragma unroll
+        for (int dxi = 0; dxi < 3; dxi++) {
+#pragma unroll
+          for (int dyi = 0; dyi < 3; dyi++) {
+            const uint32_t a_tap = a_stage + (uint32_t)((dyi * g.P + dxi) * ROWB);
+            const uint32_t w_tap = w_base + (uint32_t)((dyi * 3 + dxi) * C3P_W_TAP_BYTES);
+#pragma unroll
+            for (int k = 0; k < KSTEPS; k++) {
+              umma_bf16_pair(d_tmem, umma_desc(a_tap + k * 32, ROWB, args.single), umma_desc(w_tap + k * 32, ROWB), idesc, accumulate);
+              accumulate = 1;
+            }
+          }
+        }
+        umma_commit_pair(&empty[st]);
+        umma_commit_pair(&tfull[acc]);
+        if (stampc) args.clk[tl * 16 + 5] = clock64();
+      }
+    }
+  } else if (warp == 10) {
+    // ===== head-GEMM issuer (leader CTA only) =====
+    if (leader && lane == 0) {
+      const uint32_t idesc_head = umma_idesc_pair(HEAD_N);
+      const uint32_t hw_base = smem_u32(s_hw);
+      mbar_wait(wbar, 0);
+      tc_fence_after();
+      int tl = 0;
+      for (int tp = cid; tp < n_pairs; tp += ncl, tl++) {
+        const int b = tl & 1;
+        mbar_wait(&act_full[b], (uint32_t)((tl >> 1) & 1));
+        tc_fence_after();
+#pragma unroll
+        for (int k = 0; k < COUT / 16; k++)
+          umma_bf16_ts_pair(tmem_base + COL_HEAD + (b * HEAD_CHAINS + (k % HEAD_CHAINS)) * HEAD_N,
+                            tmem_base + COL_ACT + b * (COUT / 2) + k * 8,
+                            umma_desc(hw_base + (k / 4) * (HEAD_N / 2) * 128 + (k % 4) * 32, 128), idesc_head,
+                            k >= HEAD_CHAINS ? 1u : 0u);
+        umma_commit_pair(&head_full[b]);
+        if (stampc) args.clk[tl * 16 + 6] = clock64();
+      }
+    }
+  } else if (warp >= 2 && warp < 10) {
+    // ===== epilogue (both CTAs, own tile): warp (q, h) owns TMEM lanes 32q..32q+31 and channel half h =====
+    const int q = warp & 3;
+    const int h = (warp - 2) >> 2;
+    const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
+    auto write_heads = [&](int tj, int j) {
+      mbar_wait(&head_full[j & 1], (uint32_t)((j >> 1) & 1));
+      tc_fence_after();
+      uint32_t r[8];
+      tmem_ld8(tmem_base + lane_addr + COL_HEAD + (j & 1) * HEAD_CHAINS * HEAD_N, r);
+#pragma unroll
+      for (int c = 1; c < HEAD_CHAINS; c++) {
+        uint32_t r2[8];
+        tmem_ld8(tmem_base + lane_addr + COL_HEAD + ((j & 1) * HEAD_CHAINS + c) * HEAD_N, r2);
+#pragma unroll
+        for (int i = 0; i < 8; i++) r[i] = __float_as_uint(__uint_as_float(r[i]) + __uint_as_float(r2[i]));
+      }
+      if (tj >= n_tiles) return;                            // phantom tile of an odd tile count
+      const unsigned R = (unsigned)row_begin + (unsigned)tj * TILE_M + q * 32 + lane;
+      const int slot = (int)(R / (unsigned)g.stride), pos = (int)(R % (unsigned)g.stride);
+      const int y = pos / g.P, x = pos % g.P;
+      if (y >= 1 && x >= 1 && x <= g.B && slot < g.G) {
+        __nv_bfloat16* f = args.feat + (size_t)slot * args.FK + (y - 1) * g.B + (x - 1);
+#pragma unroll
+        for (int j2 = 0; j2 < 8; j2++)
+          if (j2 < args.NJ)
+            f[j2 < args.PC ? j2 * g.A : args.PKp + (j2 - args.PC) * g.A] =
+                __float2bfloat16(fmaxf(__uint_as_float(r[j2]) + s_bias[COUT + j2], 0.f));
+      }
+    };
+    const uint32_t l_tempty0 = mapa_u32(&tempty[0], 0), l_tempty1 = mapa_u32(&tempty[1], 0);
+    const uint32_t l_act0 = mapa_u32(&act_full[0], 0), l_act1 = mapa_u32(&act_full[1], 0);
+    int tl = 0, t_prev = 0;
+    for (int tp = cid; tp < n_pairs; tp += ncl, tl++) {
+      const int t = 2 * tp + (int)rank;
+      const int acc = tl & 1;
+      const bool stamp = stampc && warp == 2 && lane == 0;
+      if (stamp) args.clk[tl * 16 + 8] = clock64();
+      mbar_wait(&tfull[acc], (tl >> 1) & 1);
+      if (stamp) args.clk[tl * 16 + 9] = clock64();
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + lane_addr + (uint32_t)(acc * COUT + h * HALF);
+      if (tl >= 2) {             // head GEMM of tile tl-2 (same TMEM buffers) has retired
+        mbar_wait(&head_full[tl & 1], (uint32_t)(((tl - 2) >> 1) & 1));
+        tc_fence_after();
+      }
+#pragma unroll
+      for (int c0 = 0; c0 < HALF; c0 += 32) {
+        uint32_t r[32];
+        tmem_ld32(taddr + c0, r);
+        uint32_t packed[16];
+#pragma unroll
+        for (int j = 0; j < 16; j++) {
+          float v0 = fmaxf(__uint_as_float(r[2 * j]) + s_bias[h * HALF + c0 + 2 * j], 0.f);
+          float v1 = fmaxf(__uint_as_float(r[2 * j + 1]) + s_bias[h * HALF + c0 + 2 * j + 1], 0.f);
+          __nv_bfloat162 hh = __floats2bfloat162_rn(v0, v1);
+          packed[j] = *reinterpret_cast<uint32_t*>(&hh);
+        }
+        tmem_st16(tmem_base + lane_addr + COL_ACT + (uint32_t)((tl & 1) * (COUT / 2) + (h * HALF + c0) / 2), packed);
+      }
+      if (stamp) args.clk[tl * 16 + 10] = clock64();
+      asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        mbar_arrive_cluster(acc ? l_tempty1 : l_tempty0);
+        mbar_arrive_cluster((tl & 1) ? l_act1 : l_act0);
+      }
+      if (stamp) args.clk[tl * 16 + 11] = clock64();
+      if (tl > 0 && h == 0) write_heads(t_prev, tl - 1);
+      if (stamp) args.clk[tl * 16 + 12] = clock64();
+      t_prev = t;
+    }
+    if (tl > 0 && h == 0) write_heads(t_prev, tl - 1);
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();            // the leader's UMMAs read the peer's shared and tensor memory: leave together
+  if (warp == 1) tmem_dealloc_pair(tmem_base, TMEM_COLS);
+}
+
 // ---- conv1 (4 -> 32, 3x3) on the tensor core ------------------------------------------------------------------
 // The first conv sees 0/1 planes (games.py:86-129), so its implicit-GEMM A operand is just the 27 neighbourhood BITS
 // of a position (3 kernel rows x 3 stone/last-move planes x 3 columns; plane 3 is all zero) expanded to bf16, plus a
@@ -1306,6 +1614,7 @@ struct UmmaWorkspace {
   size_t rows = 0;
   int sms = 148;
   int smem2 = 0, smem3 = 0;
+  int pair = 0, smem3p = 0, pair_clusters = 0;   // conv3 on CTA pairs (cta_group::2): AZP_CONV3_PAIR=1 (default 0)
 };
 struct UmmaWeights {
   // tower
@@ -1327,6 +1636,7 @@ struct UmmaWeights {
   __nv_bfloat16* wp16 = nullptr;      // [A][PKp] policy_fc weights, K contiguous, zero padded
   __nv_bfloat16* wv16 = nullptr;      // [64][VKp] value_fc1 weights
   CUtensorMap map_w2, map_w3, map_hw, map_wp, map_wv;
+  CUtensorMap map_w3h, map_hwh;       // pair kernel: boxes of HALF the output channels / head rows
 };
 
 constexpr int STAGES2 = 6, STAGES3 = 3;
@@ -1410,6 +1720,32 @@ int azp_umma_create(azp_engine* e) {
   AZP_CUDA(e, cudaFuncSetAttribute(conv_umma_kernel<64, 128, STAGES3, true, false>,
                                    cudaFuncAttributeMaxDynamicSharedMemorySize, ws->smem3));
   AZP_CUDA(e, cudaFuncSetAttribute(fc_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ws->fc_smem));
+  {
+    // conv3 on CTA pairs: persistent grid = 2 x (clusters that can be co-resident; a GPC with an odd SM count strands one SM)
+    const char* v = getenv("AZP_CONV3_PAIR");
+    ws->pair = v ? atoi(v) : 0;      // measured 4 % SLOWER than the single-CTA kernel: opt-in
+    ws->smem3p = 1024 + C3P_W_BYTES + C3P_STAGES * ((stage_rows + 2 + 7) / 8 * 8) * 128 + C3P_HW_BYTES +
+                 (2 * C3P_STAGES + 9) * 8 + 16 + (C3P_COUT + 8) * 4 + 64;
+    if (ws->pair && ws->single != 1) ws->pair = 0;
+    if (ws->pair) {
+      AZP_CUDA(e, cudaFuncSetAttribute(conv3_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ws->smem3p));
+      cudaLaunchConfig_t cfg;
+      memset(&cfg, 0, sizeof(cfg));
+      cfg.gridDim = dim3(ws->sms / 2 * 2); cfg.blockDim = dim3(CONV_THREADS); cfg.dynamicSmemBytes = ws->smem3p;
+      cudaLaunchAttribute at[1];
+      at[0].id = cudaLaunchAttributeClusterDimension;
+      at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+      cfg.attrs = at; cfg.numAttrs = 1;
+      int ncl = 0;
+      if (cudaOccupancyMaxActiveClusters(&ncl, conv3_pair_kernel, &cfg) != cudaSuccess || ncl < 1) {
+        cudaGetLastError();
+        ws->pair = 0;
+      } else {
+        ws->pair_clusters = ncl < ws->sms / 2 ? ncl : ws->sms / 2;
+      }
+      if (getenv("AZP_VERBOSE")) fprintf(stderr, "[azp] conv3 pair mode %d, co-resident clusters %d (using %d), smem %d\n", ws->pair, ncl, ws->pair_clusters, ws->smem3p);
+    }
+  }
   return AZP_OK;
 }
 
@@ -1552,6 +1888,8 @@ int azp_umma_build(azp_engine* e, const HostNet& net, NetWeights* W) {
   if ((st = up(e, &U->head_w16, hw))) return st;
   if ((st = up(e, &U->head_b8, hb))) return st;
   if ((st = make_map(e, &U->map_hw, U->head_w16, HEAD_N, net.C, HEAD_N, 64))) return st;
+  if ((st = make_map(e, &U->map_w3h, U->w3, 9 * 128, 64, 64))) return st;
+  if ((st = make_map(e, &U->map_hwh, U->head_w16, HEAD_N, net.C, HEAD_N / 2, 64))) return st;
   return fc_weights_build(e, net, W, U);
 }
 
@@ -1662,8 +2000,23 @@ static int run_trunk(azp_engine* e, NetWeights* W, const int32_t* count_dev, int
   a3.stage_bytes = (a3.single ? (a3.stage_rows + 2 + 7) / 8 * 8 : a3.stage_rows) * 128;
   e->prof_flops_per_board = 2.0 * 9.0 * 64 * 128 * g.A;
   azp_prof_begin(e, count_dev, count_host, s);
-  azp_launch(conv_umma_kernel<64, 128, STAGES3, true, false>, grid, CONV_THREADS, ws->smem3, s, true,
-             a3.single ? ws->map_act2_s : ws->map_act2, U->map_w3, U->map_hw, a3);
+  if (ws->pair) {
+    const int max_pairs = (max_tiles + 1) / 2;
+    const int ncl = max_pairs < ws->pair_clusters ? max_pairs : ws->pair_clusters;
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(2 * ncl); cfg.blockDim = dim3(CONV_THREADS); cfg.dynamicSmemBytes = ws->smem3p; cfg.stream = s;
+    cudaLaunchAttribute at[2];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[1].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = azp_pdl_enabled() ? 2 : 1;
+    cudaLaunchKernelEx(&cfg, conv3_pair_kernel, ws->map_act2_s, U->map_w3h, U->map_hwh, a3);
+  } else {
+    azp_launch(conv_umma_kernel<64, 128, STAGES3, true, false>, grid, CONV_THREADS, ws->smem3, s, true,
+               a3.single ? ws->map_act2_s : ws->map_act2, U->map_w3, U->map_hw, a3);
+  }
   azp_count_launch();
   azp_prof_end(e, s);
   return launch_fc(e, W, count_dev, count_host, back, logits, policy, value, out_by_index, s);

@@ -282,6 +282,28 @@ def test_net_bf16_large_batch_and_scaled_weights(az):
     eng.close()
 
 
+def test_conv3_cta_pair_kernel_matches_single_cta(az, monkeypatch):
+    """AZP_CONV3_PAIR=1: conv3 + heads as cta_group::2 UMMAs on CTA pairs (two SMs share one M256 instruction, each
+    holding half of the weights).  Same products in the same K order => the logits must agree with the default
+    single-CTA kernel to fp32 rounding, on a batch with an odd tile count (phantom tile) and a full one."""
+    params = onet.synthetic_stem_params(15, seed=3)
+    rs = np.random.RandomState(0)
+    for n in (37, 512):
+        x = torch.from_numpy((rs.random_sample((n, 4, 15, 15)) < 0.2).astype(np.float32)).cuda()
+        outs = []
+        for flag in ("0", "1"):
+            monkeypatch.setenv("AZP_CONV3_PAIR", flag)
+            eng = az.Engine(board=15, win_length=5, games=n, sims=2, net_dtype=az.DTYPE_BF16)
+            eng.load_state_dict(params)
+            logits, _, value = eng.net_forward(x)
+            outs.append((logits.clone(), value.clone()))
+            eng.close()
+        assert float((outs[0][0] - outs[1][0]).abs().max()) <= 1e-5
+        assert float((outs[0][1] - outs[1][1]).abs().max()) <= 1e-5
+        ol, ov = onet.stem_forward(params, x.cpu())
+        assert float((outs[1][0].cpu() - ol).abs().max()) <= 2e-2       # north-star bf16 tolerance
+
+
 @pytest.mark.parametrize("size,win,sims,n,dtype", [(5, 4, 120, 24, "f32"), (9, 5, 200, 16, "f32"),
                                                    (15, 5, 160, 8, "f32"), (9, 5, 150, 16, "bf16"),
                                                    (15, 5, 200, 40, "bf16")])
