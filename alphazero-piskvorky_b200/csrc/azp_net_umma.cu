@@ -352,16 +352,20 @@ __global__ void __launch_bounds__(BITS ? CONV_THREADS_BITS : (HEADS ? CONV_THREA
   // TMEM columns: [0, 2*COUT) two conv accumulators; HEADS adds two bf16 copies of the activated tile
   // (COUT/2 columns each) and two head accumulators (HEAD_N columns each), all double-buffered so the
   // epilogue of tile t never waits for the head GEMM of tile t-1
-  constexpr uint32_t COL_ACT = 2 * COUT;
-  constexpr uint32_t COL_HEAD = COL_ACT + COUT;
   // The head GEMM's K loop is split over HEAD_CHAINS independent accumulators (summed by the epilogue):
   // back-to-back UMMAs into ONE narrow accumulator serialise on its ~64-cycle dependent-issue latency
   constexpr int HEAD_CHAINS = 4;
   // The plain conv (conv2) is epilogue-latency bound with one epilogue group: it gets FOUR accumulators and TWO
   // epilogue groups (even / odd tiles) so two tiles are drained concurrently.
-  constexpr int NACC = (HEADS || BITS) ? 2 : 4;
+  // HEADS: FOUR accumulators of COUT columns and nothing else -- the bf16 copy of the activated tile (A operand of the
+  // head GEMM) and the head GEMM's partial accumulators ALIAS the accumulator being drained: channel half h keeps its
+  // 32 packed columns at [h*64, h*64+32) (written over fp32 columns that are already in registers), the four head
+  // chains live in the freed columns [32,64) and [96,128).  An accumulator is released only after its head outputs
+  // were read, but with four in rotation the issuers never wait for an epilogue (they did with two: 9 us per launch).
+  constexpr int NACC = BITS ? 2 : 4;
   constexpr int EGROUPS = (HEADS || BITS) ? 1 : 2;
-  constexpr uint32_t NEED = HEADS ? COL_HEAD + 2 * HEAD_CHAINS * HEAD_N : NACC * COUT;
+  static_assert(!HEADS || (COUT == 128 && HEAD_CHAINS * HEAD_N == 64), "aliased head layout assumes 128 output channels");
+  constexpr uint32_t NEED = NACC * COUT;
   constexpr uint32_t TMEM_COLS = NEED <= 32 ? 32 : (NEED <= 64 ? 64 : (NEED <= 128 ? 128 : (NEED <= 256 ? 256 : 512)));
   constexpr int HALF = COUT / 2;                            // channels per epilogue warp
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -377,9 +381,9 @@ __global__ void __launch_bounds__(BITS ? CONV_THREADS_BITS : (HEADS ? CONV_THREA
   uint64_t* tfull = empty + STAGES;                         // [NACC <= 4]
   uint64_t* tempty = tfull + 4;                             // [NACC <= 4]
   uint64_t* wbar = tempty + 4;                              // [1]
-  uint64_t* act_full = wbar + 1;                            // [2] epilogue -> MMA: bf16 tile b is in TMEM
-  uint64_t* head_full = act_full + 2;                       // [2] MMA -> epilogue: head accumulator b ready
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(head_full + 2);
+  uint64_t* act_full = wbar + 1;                            // [4] epilogue -> MMA: bf16 tile of accumulator a is in TMEM
+  uint64_t* head_full = act_full + 4;                       // [4] MMA -> epilogue: head outputs of accumulator a ready
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(head_full + 4);
   float* s_bias = reinterpret_cast<float*>(tmem_slot + 2);  // [COUT] (+ [8] head bias)
   float* s_w1 = s_bias + COUT + 8;                          // BITS: [3 planes][3 ky][8 patterns][32] conv1 tables + [32] bias
   int16_t* s_cells = reinterpret_cast<int16_t*>(s_w1 + 72 * 32 + 32); // BITS: [2][CODES] column-pattern codes
@@ -391,9 +395,10 @@ __global__ void __launch_bounds__(BITS ? CONV_THREADS_BITS : (HEADS ? CONV_THREA
   //      launch it overlaps that kernel's tail (barriers, TMEM, bias and the resident weights) ----
   if (threadIdx.x == 0) {
     for (int i = 0; i < STAGES; i++) { mbar_init(&full[i], BITS ? 8 : 1); mbar_init(&empty[i], 1); }
-    for (int i = 0; i < NACC; i++) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 8); }
+    // HEADS: an accumulator is released by the four warps that read its head outputs; otherwise by all eight
+    for (int i = 0; i < NACC; i++) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], HEADS ? 4 : 8); }
     mbar_init(wbar, 1);
-    for (int i = 0; i < 2; i++) { mbar_init(&act_full[i], 8); mbar_init(&head_full[i], 1); }
+    for (int i = 0; i < 4; i++) { mbar_init(&act_full[i], 8); mbar_init(&head_full[i], 1); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     mbar_expect_tx(wbar, S::W_BYTES + HW_BYTES);
     for (int tap = 0; tap < 9; tap++) tma_load_2d(s_w + tap * S::W_TAP_BYTES, &map_w, wbar, 0, tap * COUT);
@@ -598,7 +603,12 @@ __global__ void __launch_bounds__(BITS ? CONV_THREADS_BITS : (HEADS ? CONV_THREA
           umma_commit(&empty[st]);                        // stage reusable once these MMAs retire
         }
         umma_commit(&tfull[acc]);                         // accumulator complete
-        if (args.clk && blockIdx.x == 0) args.clk[tl * 16 + 5] = clock64();
+        if (args.clk && blockIdx.x == 0) {
+          args.clk[tl * 16 + 5] = clock64();
+          unsigned long long gt;
+          asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+          args.clk[tl * 16 + 13] = (long long)gt;          // wall-clock ns next to the cycle stamp: SM clock under load
+        }
       }
     }
   } else if (HEADS && warp == 10) {
@@ -608,15 +618,18 @@ __global__ void __launch_bounds__(BITS ? CONV_THREADS_BITS : (HEADS ? CONV_THREA
       const uint32_t hw_base = smem_u32(s_hw);
       // 1x1 head GEMM of local tile j: [128 x COUT] (TMEM, bf16) x [COUT x 16] (smem) -> TMEM cols COL_HEAD..
       auto issue_head = [&](int j) {
-        const int b = j & 1;
-        mbar_wait(&act_full[b], (uint32_t)((j >> 1) & 1));
+        const int b = j % NACC;
+        mbar_wait(&act_full[b], (uint32_t)((j / NACC) & 1));
         tc_fence_after();
+        const uint32_t acc_base = tmem_base + (uint32_t)(b * COUT);
 #pragma unroll
-        for (int k = 0; k < COUT / 16; k++)
-          umma_bf16_ts(tmem_base + COL_HEAD + (b * HEAD_CHAINS + (k % HEAD_CHAINS)) * HEAD_N,
-                       tmem_base + COL_ACT + b * (COUT / 2) + k * 8,
+        for (int k = 0; k < COUT / 16; k++) {
+          const int c = k % HEAD_CHAINS;                    // chain c accumulates K steps c, c+4
+          umma_bf16_ts(acc_base + (c < 2 ? 32 + c * HEAD_N : 96 + (c - 2) * HEAD_N),
+                       acc_base + (k / 4) * 64 + (k % 4) * 8,
                        umma_desc(hw_base + (k / 4) * HEAD_N * 128 + (k % 4) * 32, 128), idesc_head,
                        k >= HEAD_CHAINS ? 1u : 0u);
+        }
         umma_commit(&head_full[b]);
       };
       mbar_wait(wbar, 0);
@@ -636,17 +649,22 @@ __global__ void __launch_bounds__(BITS ? CONV_THREADS_BITS : (HEADS ? CONV_THREA
     const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
     // head outputs of local tile j (global tile tj): +bias, ReLU, scatter to feat[slot][j][pixel]
     auto write_heads = [&](int tj, int j) {
-      mbar_wait(&head_full[j & 1], (uint32_t)((j >> 1) & 1));
+      const int b = j % NACC;
+      mbar_wait(&head_full[b], (uint32_t)((j / NACC) & 1));
       tc_fence_after();
+      const uint32_t acc_base = tmem_base + lane_addr + (uint32_t)(b * COUT);
       uint32_t r[8];
-      tmem_ld8(tmem_base + lane_addr + COL_HEAD + (j & 1) * HEAD_CHAINS * HEAD_N, r);
+      tmem_ld8(acc_base + 32, r);
 #pragma unroll
       for (int c = 1; c < HEAD_CHAINS; c++) {               // sum the partial accumulators of the K split
         uint32_t r2[8];
-        tmem_ld8(tmem_base + lane_addr + COL_HEAD + ((j & 1) * HEAD_CHAINS + c) * HEAD_N, r2);
+        tmem_ld8(acc_base + (c < 2 ? 32 + c * HEAD_N : 96 + (c - 2) * HEAD_N), r2);
 #pragma unroll
         for (int i = 0; i < 8; i++) r[i] = __float_as_uint(__uint_as_float(r[i]) + __uint_as_float(r2[i]));
       }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty[b]);               // head outputs are in registers: the accumulator is free
       const unsigned R = (unsigned)row_begin + (unsigned)tj * TILE_M + q * 32 + lane;
       const int slot = (int)(R / (unsigned)g.stride), pos = (int)(R % (unsigned)g.stride);
       const int y = pos / g.P, x = pos % g.P;
@@ -678,7 +696,8 @@ __global__ void __launch_bounds__(BITS ? CONV_THREADS_BITS : (HEADS ? CONV_THREA
       if (args.debug & 1) {
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) { mbar_arrive(&tempty[acc]); if (HEADS) mbar_arrive(&act_full[tl & 1]); }
+        if (lane == 0) { if (HEADS) mbar_arrive(&act_full[acc]); else mbar_arrive(&tempty[acc]); }
+        if (HEADS && tl > 0 && h == 0) write_heads(t_prev, tl - 1);
       } else if (!HEADS) {
         // bias + ReLU + halo zero in registers, the accumulator is released at once; the tile is then staged in
         // shared memory (128B-swizzled rows) and leaves the SM as ONE TMA store -- per-thread row stores are
@@ -716,10 +735,6 @@ __global__ void __launch_bounds__(BITS ? CONV_THREADS_BITS : (HEADS ? CONV_THREA
         }
         if (stamp) args.clk[tl * 16 + 11] = clock64();
       } else {
-        if (tl >= 2) {           // head GEMM of tile tl-2 (same TMEM buffers) has retired
-          mbar_wait(&head_full[tl & 1], (uint32_t)(((tl - 2) >> 1) & 1));
-          tc_fence_after();
-        }
 #pragma unroll
         for (int c0 = 0; c0 < HALF; c0 += 32) {
           uint32_t r[32];
@@ -732,13 +747,14 @@ __global__ void __launch_bounds__(BITS ? CONV_THREADS_BITS : (HEADS ? CONV_THREA
             __nv_bfloat162 hh = __floats2bfloat162_rn(v0, v1);
             packed[j] = *reinterpret_cast<uint32_t*>(&hh);
           }
-          tmem_st16(tmem_base + lane_addr + COL_ACT + (uint32_t)((tl & 1) * (COUT / 2) + (h * HALF + c0) / 2), packed);
+          // in place: the 16 packed columns of this chunk overwrite fp32 columns this warp already holds in registers
+          tmem_st16(tmem_base + lane_addr + (uint32_t)(acc * COUT + h * HALF + c0 / 2), packed);
         }
         if (stamp) args.clk[tl * 16 + 10] = clock64();
         asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) { mbar_arrive(&tempty[acc]); mbar_arrive(&act_full[tl & 1]); }
+        if (lane == 0) mbar_arrive(&act_full[acc]);
         if (stamp) args.clk[tl * 16 + 11] = clock64();
         // the PREVIOUS tile's head GEMM was queued behind this tile's conv MMAs: it has retired by now
         if (tl > 0 && h == 0) write_heads(t_prev, tl - 1);
@@ -1645,7 +1661,7 @@ template <int CIN, int COUT, int STAGES, bool HEADS, bool BITS>
 int conv_smem_bytes(int stage_rows) {
   using S = ConvSmem<CIN, COUT, STAGES, HEADS>;
   return 1024 + S::W_BYTES + STAGES * ((stage_rows + 2 + 7) / 8 * 8) * S::ROWB + (HEADS ? (COUT / 64) * HEAD_N * 128 : 0) +
-         (HEADS ? 0 : 2 * TILE_M * 128) + (2 * STAGES + 13) * 8 + 16 + (COUT + 8) * 4 + (BITS ? (72 * 32 + 32) * 4 + 2 * CODES * 2 : 0) + 64;
+         (HEADS ? 0 : 2 * TILE_M * 128) + (2 * STAGES + 17) * 8 + 16 + (COUT + 8) * 4 + (BITS ? (72 * 32 + 32) * 4 + 2 * CODES * 2 : 0) + 64;
 }
 
 }  // namespace

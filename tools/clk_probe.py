@@ -18,3 +18,5 @@ t0 = c[0, 2]
 print("tile | " + " | ".join(f"{names[k]:>20s}" for k in sorted(names)))
 for tl in range(0, 28):
     print(f"{tl:4d} | " + " | ".join(f"{int(c[tl, k] - t0):20d}" for k in sorted(names)))
+ns = float(c[27, 13] - c[1, 13]); cyc = float(c[27, 5] - c[1, 5])
+print(f"SM clock during the launch: {cyc / ns * 1e3:.0f} MHz ({cyc:.0f} cycles in {ns:.0f} ns)")
