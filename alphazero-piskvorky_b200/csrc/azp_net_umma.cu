@@ -390,6 +390,8 @@ __global__ void __launch_bounds__(BITS ? CONV_THREADS_BITS : (HEADS ? CONV_THREA
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const ConvGeom g = args.g;
+  auto wall_ns = [] { unsigned long long gt; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt)); return (long long)gt; };
+  if (args.clk && blockIdx.x == 0 && threadIdx.x == 0) args.clk[0 * 16 + 14] = wall_ns();      // kernel entry
 
   // ---- prologue: touches nothing the previous kernel of the stream writes, so under programmatic dependent
   //      launch it overlaps that kernel's tail (barriers, TMEM, bias and the resident weights) ----
@@ -413,8 +415,10 @@ __global__ void __launch_bounds__(BITS ? CONV_THREADS_BITS : (HEADS ? CONV_THREA
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
+  if (args.clk && blockIdx.x == 0 && threadIdx.x == 0) args.clk[1 * 16 + 14] = wall_ns();      // barriers + TMEM ready
   pdl_wait();                      // the leaf count and the input activations are the previous kernels' outputs
   pdl_launch_dependents();
+  if (args.clk && blockIdx.x == 0 && threadIdx.x == 0) args.clk[2 * 16 + 14] = wall_ns();      // predecessor finished
   const int count = args.count_dev ? *args.count_dev : args.count_host;
   const int slot0 = args.back ? g.G - count : 0;
   const long long row_begin = (long long)slot0 * g.stride;
@@ -549,6 +553,7 @@ __global__ void __launch_bounds__(BITS ? CONV_THREADS_BITS : (HEADS ? CONV_THREA
       const uint32_t a_base = smem_u32(s_a), w_base = smem_u32(s_w);
       const int my_parity = warp == 1 ? 0 : 1;
       mbar_wait(wbar, 0);
+      if (args.clk && blockIdx.x == 0 && warp == 1) args.clk[3 * 16 + 14] = wall_ns();           // weights resident
       tc_fence_after();
       int it = 0, tl = 0;
       for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, tl++) {
@@ -767,6 +772,7 @@ __global__ void __launch_bounds__(BITS ? CONV_THREADS_BITS : (HEADS ? CONV_THREA
   }
   tc_fence_before();
   __syncthreads();
+  if (args.clk && blockIdx.x == 0 && threadIdx.x == 0) args.clk[4 * 16 + 14] = wall_ns();      // all roles done
   if (warp == 1) tmem_dealloc(tmem_base, TMEM_COLS);
 }
 

@@ -20,3 +20,6 @@ for tl in range(0, 28):
     print(f"{tl:4d} | " + " | ".join(f"{int(c[tl, k] - t0):20d}" for k in sorted(names)))
 ns = float(c[27, 13] - c[1, 13]); cyc = float(c[27, 5] - c[1, 5])
 print(f"SM clock during the launch: {cyc / ns * 1e3:.0f} MHz ({cyc:.0f} cycles in {ns:.0f} ns)")
+w = [int(c[i, 14] - c[0, 14]) for i in range(5)]
+print(f"wall ns from kernel entry (CTA 0): barriers+TMEM {w[1]}, predecessor done {w[2]}, weights resident {w[3]}, all roles done {w[4]};"
+      f" first/last issue complete at {int(c[0, 13] - c[0, 14])} / {int(c[27, 13] - c[0, 14])}")
