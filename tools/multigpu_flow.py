@@ -2,7 +2,10 @@
    1. games sharded by global id, each rank self-plays its block (no collective in the simulation loop);
    2. ragged all-gather of the generated example slabs into every rank's replay buffer;
    3. arena new-vs-best sharded the same way, W/L/D all-reduced, promotion rule;
-   4. broadcast of the promoted weights as one flat fp32 blob and reload on every rank.
+   4. broadcast of the promoted weights as one flat fp32 blob and reload on every rank;
+   5. data-parallel training steps: every rank takes its shard of one global batch drawn from the
+      gathered replay ring, gradients are all-reduced (NCCL) as ONE flat blob, AdamW runs on every rank; rank 0 also
+      trains on the whole batch alone -- the weights must agree.
 Checks shard invariance against a single-rank run of the same global game ids on rank 0."""
 import os, sys, json, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -59,8 +62,36 @@ _, _, v = eng.net_forward(x)
 vs = [torch.zeros_like(v) for _ in range(world)]
 dist.all_gather(vs, v)
 same_value = all(torch.equal(vs[0], q) for q in vs)
+# ---- data-parallel training on the gathered examples ----
+torch.manual_seed(2)
+GB, STEPS, LR = 256, 3, 1e-3
+P, PI, Z = buf.device_all()
+sel = torch.randperm(P.shape[0], generator=torch.Generator().manual_seed(7))[:GB].cuda()     # same global batch on every rank
+gP, gPI, gZ = P[sel], PI[sel], Z[sel].float()
+lo, n_loc = azd.rank_block(0, GB, rank, world)
+init = {k: v.clone() for k, v in best.state_dict().items()}
+net_dp = az.GomokuNet(B); net_dp.load_state_dict(init)
+ctrl = az.NeuralNetworkController(net_dp, device=f"cuda:{local}", batch_size=GB, rank=rank, world=world)
+t1 = time.time()
+dp_losses = [ctrl.train_step(gP[lo:lo + n_loc], gPI[lo:lo + n_loc], gZ[lo:lo + n_loc], LR)[0] for _ in range(STEPS)]
+torch.cuda.synchronize()
+t_train = time.time() - t1
+flat = ctrl.flat_parameters()
+flats = [torch.zeros_like(flat) for _ in range(world)]
+dist.all_gather(flats, flat)
+dp_identical = all(torch.equal(flats[0], f) for f in flats)
+dp_vs_single = None
 if rank == 0:
-    print(json.dumps({"world": world, "positions_total": int(gz.numel()), "positions_this_rank": int(z.numel()),
+    net_1 = az.GomokuNet(B); net_1.load_state_dict(init)
+    solo_ctrl = az.NeuralNetworkController(net_1, device=f"cuda:{local}", batch_size=GB)
+    for _ in range(STEPS):
+        solo_ctrl.train_step(gP, gPI, gZ, LR)
+    d = (solo_ctrl.flat_parameters() - flat).abs()
+    dp_vs_single = {"quantile_999": float(torch.quantile(d[::7], 0.999)), "max": float(d.max())}
+if rank == 0:
+    print(json.dumps({"world": world, "dp_train": {"global_batch": GB, "steps": STEPS, "local_losses": dp_losses,
+                      "weights_identical_across_ranks": bool(dp_identical), "abs_diff_vs_single_rank_full_batch": dp_vs_single,
+                      "seconds": round(t_train, 3)}, "positions_total": int(gz.numel()), "positions_this_rank": int(z.numel()),
                       "replay_len": buf.device_len(), "shard_invariant": ok_invariance, "arena_wld": [W, L, D],
                       "win_rate": win_rate, "promote": bool(promote), "weights_identical_after_broadcast": bool(same_value),
                       "selfplay_seconds": round(t_selfplay, 2)}))
