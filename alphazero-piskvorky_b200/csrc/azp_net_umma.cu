@@ -704,9 +704,11 @@ __global__ void __launch_bounds__(BITS ? CONV_THREADS_BITS : (HEADS ? CONV_THREA
         if (lane == 0) { if (HEADS) mbar_arrive(&act_full[acc]); else mbar_arrive(&tempty[acc]); }
         if (HEADS && tl > 0 && h == 0) write_heads(t_prev, tl - 1);
       } else if (!HEADS) {
-        // bias + ReLU + halo zero in registers, the accumulator is released at once; the tile is then staged in
-        // shared memory (128B-swizzled rows) and leaves the SM as ONE TMA store -- per-thread row stores are
-        // uncoalesced (one 32-byte sector per lane and instruction) and bound this kernel before
+        // bias + ReLU + halo zero in registers, the accumulator is released at once.  Each lane then owns 64 contiguous
+        // bytes of its output row and writes them as two 256-bit stores (st.global.v8: full 32-byte sectors).  16-byte
+        // row stores (one half-used sector per lane and instruction) bound this kernel once, and the shared-memory
+        // staging + TMA store that replaced them costs 32 KB of shared-memory port time per tile in a kernel that is
+        // bound by exactly that port
         static_assert(HEADS || HALF == 32, "plain-conv epilogue expects 64 output channels");
         uint32_t r[32];
         tmem_ld32(taddr, r);
@@ -720,6 +722,20 @@ __global__ void __launch_bounds__(BITS ? CONV_THREADS_BITS : (HEADS ? CONV_THREA
           float v1 = interior ? fmaxf(__uint_as_float(r[2 * j + 1]) + s_bias[h * HALF + 2 * j + 1], 0.f) : 0.f;
           __nv_bfloat162 hh = __floats2bfloat162_rn(v0, v1);
           packed[j] = *reinterpret_cast<uint32_t*>(&hh);
+        }
+        if (!(args.debug & 16)) {
+          // direct path (default; AZP_DEBUG_CONV=16 selects the staged TMA-store path, 0.9 % slower end to end): each lane owns 64 contiguous bytes of its output row -> two 256-bit stores (full 32 B sectors),
+          // no shared-memory round trip (the staged path costs 32 KB of shared-memory port time per tile)
+          uint8_t* gp = reinterpret_cast<uint8_t*>(args.out) + (size_t)R * 128 + h * 64;
+#pragma unroll
+          for (int v = 0; v < 2; v++)
+            asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+                         ::"l"(gp + v * 32), "r"(packed[8 * v]), "r"(packed[8 * v + 1]), "r"(packed[8 * v + 2]),
+                           "r"(packed[8 * v + 3]), "r"(packed[8 * v + 4]), "r"(packed[8 * v + 5]), "r"(packed[8 * v + 6]),
+                           "r"(packed[8 * v + 7]) : "memory");
+          if (stamp) args.clk[tl * 16 + 11] = clock64();
+          t_prev = t;
+          continue;
         }
         uint8_t* obuf = s_out + egroup * (TILE_M * 128);
         const int m = q * 32 + lane;
@@ -1708,7 +1724,7 @@ int azp_umma_create(azp_engine* e) {
   AZP_CUDA(e, cudaMemset(ws->feat, 0, ((size_t)g.G + TILE_M) * ws->FK * sizeof(__nv_bfloat16)));
   if ((st = make_map(e, &ws->map_feat, ws->feat, (uint64_t)g.G + TILE_M, ws->FK, TILE_M, 64))) return st;
   {
-    ws->fc_stages = 6;                         // 6 x 24 KB operand stages; the first two double as the logits staging tile
+    { const char* v = getenv("AZP_FC_STAGES"); ws->fc_stages = v ? atoi(v) : 6; }   // x 24 KB operand stages; the first two double as the logits staging tile
     ws->fc_smem = 1024 + ws->fc_stages * FC_STAGE_BYTES + 17 * 8 + 16 + (64 + 72 + 256) * 4 + 64;
   }
   cudaDeviceProp prop0;

@@ -183,11 +183,13 @@ def run_engine_arm(args):
         engines.append(eng)
         streams.append(torch.cuda.Stream())
         cap = eng.example_capacity_floor() * 2
-        outs.append((torch.empty((cap, 4, BOARD, BOARD), device="cuda"), torch.empty((cap, BOARD, BOARD), device="cuda"),
-                     torch.empty((cap,), dtype=torch.int32, device="cuda")))
-    cap = outs[0][0].shape[0]
-    host_out = (torch.empty((cap, 4, BOARD, BOARD)).pin_memory(), torch.empty((cap, BOARD, BOARD)).pin_memory(),
-                torch.empty((cap,), dtype=torch.int32).pin_memory())
+        # two output slabs per engine: step i+1 fills one while step i's examples drain to the host from the other
+        outs.append([(torch.empty((cap, 4, BOARD, BOARD), device="cuda"), torch.empty((cap, BOARD, BOARD), device="cuda"),
+                      torch.empty((cap,), dtype=torch.int32, device="cuda")) for _ in range(2)])
+    cap = outs[0][0][0].shape[0]
+    host_out = [(torch.empty((cap, 4, BOARD, BOARD)).pin_memory(), torch.empty((cap, BOARD, BOARD)).pin_memory(),
+                 torch.empty((cap,), dtype=torch.int32).pin_memory()) for _ in range(2)]
+    copy_streams = [torch.cuda.Stream() for _ in range(E)]
     total_games = 1 << 40                    # endless stream of games: finished slots are re-seated
     first_flag = [True] * E
 
@@ -197,20 +199,35 @@ def run_engine_arm(args):
         with torch.cuda.stream(streams[k]):
             if start_event is not None:
                 streams[k].wait_event(start_event)
+            drained = [None, None]                                     # per slab: event "its examples are on the host"
             for i in range(n):
+                slab = i & 1
+                if drained[slab] is not None:
+                    streams[k].wait_event(drained[slab])               # never overwrite a slab that is still draining
                 if profile_last and i == n - 1:
                     # the dominant kernel is bracketed with CUDA events on the LAST timed step only: the event nodes
                     # cut the programmatic-dependent-launch edges around it, so the other steps run unperturbed
                     engines[k].set_profiling(True)
                 if e2e:
                     engines[k].load_blob(blob_host.numpy())            # weights: host -> device, every step
-                st, _, _, _, w = engines[k].selfplay(total_games, first_game=0, out=outs[k],
+                st, _, _, _, w = engines[k].selfplay(total_games, first_game=0, out=outs[k][slab],
                                                      resume=not first_flag[k], max_move_steps=1)
                 first_flag[k] = False
-                if e2e and w:                                          # examples: device -> pinned host
-                    for src, dst in zip(outs[k], host_out):
-                        dst[:w].copy_(src[:w], non_blocking=True)
+                if e2e and w:
+                    # examples: device -> pinned host on a copy stream, overlapping the next move step (the driver is
+                    # synchronous at return, so the slab is complete); everything drains inside the timed region
+                    ready = torch.cuda.Event()
+                    ready.record(streams[k])
+                    copy_streams[k].wait_event(ready)
+                    with torch.cuda.stream(copy_streams[k]):
+                        for src, dst in zip(outs[k][slab], host_out[slab]):
+                            dst[:w].copy_(src[:w], non_blocking=True)
+                        drained[slab] = torch.cuda.Event()
+                        drained[slab].record(copy_streams[k])
                     d2h_acc[k] += w * (5 * BOARD * BOARD + 1) * 4
+            for ev in drained:
+                if ev is not None:
+                    streams[k].wait_event(ev)
             done_events[k].record(streams[k])
 
     def run_all(n, e2e=False, profile_last=False):
