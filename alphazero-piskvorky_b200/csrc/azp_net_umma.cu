@@ -1127,6 +1127,8 @@ struct Conv1Args {
   const int32_t* count_dev; int count_host; int back;
   const uint64_t* lx; const uint64_t* lo; const uint8_t* ltm; const int16_t* llast; int NW;   // leaf batch (bitboards)
   const float* planes;             // PLANES: [count][4][A] float32
+  __nv_bfloat16* out;              // act1 [rows][32] (direct-store epilogue)
+  int staged;                      // 1: swizzled smem staging + TMA store (AZP_CONV1_STORE=tma), 0: 256-bit stores from registers
   long long* clk;                  // bring-up (AZP_CLK=3): per-tile clock64 stamps of CTA 0 ([tile][16]) or null
 };
 #define C1_STAMP(cond, k) do { if (args.clk && blockIdx.x == 0 && tl < 64 && (cond)) args.clk[tl * 16 + (k)] = clock64(); } while (0)
@@ -1411,6 +1413,19 @@ __global__ void __launch_bounds__(C1_THREADS, 2) conv1_umma_kernel(const __grid_
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty[st]);
+      if (!args.staged) {
+        // each lane owns the 64 contiguous bytes of its output row: two 256-bit stores (full 32-byte sectors), no
+        // shared-memory round trip and no group barriers
+        uint8_t* gp = reinterpret_cast<uint8_t*>(args.out) + ((size_t)row_begin + (size_t)t * TILE_M + m) * 64;
+#pragma unroll
+        for (int v = 0; v < 2; v++)
+          asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+                       ::"l"(gp + v * 32), "r"(packed[8 * v]), "r"(packed[8 * v + 1]), "r"(packed[8 * v + 2]),
+                         "r"(packed[8 * v + 3]), "r"(packed[8 * v + 4]), "r"(packed[8 * v + 5]), "r"(packed[8 * v + 6]),
+                         "r"(packed[8 * v + 7]) : "memory");
+        C1_STAMP(issuer, 13);
+        continue;
+      }
       // two staging buffers per group: the TMA store issued two tiles ago (same buffer) has finished reading it --
       // its issuer waited for that (wait_group.read 1) before arriving at this barrier
       uint8_t* obuf = s_out + (eg * 2 + ((tl >> 1) & 1)) * C1_A_BYTES;
@@ -2098,7 +2113,8 @@ static int launch_conv1_umma(azp_engine* e, UmmaWeights* U, const int32_t* count
   Conv1Args a;
   a.g = g; a.w = U->w1_umma; a.count_dev = count_dev; a.count_host = count_host; a.back = back;
   a.lx = e->tv.leaf_x; a.lo = e->tv.leaf_o; a.ltm = e->tv.leaf_tm; a.llast = e->tv.leaf_last; a.NW = e->NW;
-  a.planes = planes;
+  a.planes = planes; a.out = ws->act1;
+  { static int staged = -1; if (staged < 0) { const char* v = getenv("AZP_CONV1_STORE"); staged = (v && !strcmp(v, "tma")) ? 1 : 0; } a.staged = staged; }
   { const char* v = getenv("AZP_CLK"); a.clk = (v && atoi(v) == 3) ? ws->clk : nullptr; }
   if (planes) azp_launch(conv1_umma_kernel<true>, grid, C1_THREADS, conv1_smem_bytes(true), s, true, ws->map_act1_out, a);
   else azp_launch(conv1_umma_kernel<false>, grid, C1_THREADS, conv1_smem_bytes(false), s, true, ws->map_act1_out, a);
