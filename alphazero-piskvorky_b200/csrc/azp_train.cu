@@ -398,7 +398,9 @@ void gemm(cudaStream_t s, bool a_kc, bool b_nc, const float* A, long long sAi, l
           long long sBk, long long sBj, float* C, int M, int N, int K, int epi = 0, const float* bias = nullptr,
           const float* mask = nullptr) {
   GemmArgs g{A, B, C, M, N, K, sAi, sAk, sBk, sBj, K, epi, bias, mask};
-  if (N <= 32) launch_gemm_shape<128, 32, 4, 4>(g, a_kc, b_nc, 1, s);
+  // the FC layers have few output tiles (policy_fc forward: 8 x 2 of 128 x 128): the narrow tile gives 4x the CTAs
+  const long long wide_tiles = (long long)((M + 127) / 128) * ((N + 127) / 128);
+  if (N <= 32 || wide_tiles < 74) launch_gemm_shape<128, 32, 4, 4>(g, a_kc, b_nc, 1, s);
   else launch_gemm_shape<128, 128, 8, 8>(g, a_kc, b_nc, 1, s);
 }
 
@@ -571,7 +573,7 @@ extern "C" int azp_train_loss_grad(azp_trainer* t, int n, const float* params, c
   // ---- backward ----
   float* G = grads;
   // value_fc2
-  gemm(s, false, true, t->dv2, 1, 1, t->v1, 64, 1, G + t->o_v2w, 1, 64, n);                       // dW = dv2^T v1
+  if ((st = gemm_splitk(t, s, false, true, t->dv2, 1, 1, t->v1, 64, 1, G + t->o_v2w, 1, 64, n))) return st;   // dW = dv2^T v1
   colsum(t, s, t->dv2, n, 1, G + t->o_v2b);
   gemm(s, true, true, t->dv2, 1, 1, P + t->o_v2w, 64, 1, t->dv1, n, 64, 1, 3, nullptr, t->v1);     // dv1 = dv2 W2 .* (v1>0)
   // value_fc1
