@@ -401,6 +401,7 @@ void gemm(cudaStream_t s, bool a_kc, bool b_nc, const float* A, long long sAi, l
   // the FC layers have few output tiles (policy_fc forward: 8 x 2 of 128 x 128): the narrow tile gives 4x the CTAs
   const long long wide_tiles = (long long)((M + 127) / 128) * ((N + 127) / 128);
   if (N <= 32 || wide_tiles < 74) launch_gemm_shape<128, 32, 4, 4>(g, a_kc, b_nc, 1, s);
+  else if (N <= 64) launch_gemm_shape<128, 64, 8, 4>(g, a_kc, b_nc, 1, s);      // a 128-wide tile would waste half its FMAs
   else launch_gemm_shape<128, 128, 8, 8>(g, a_kc, b_nc, 1, s);
 }
 
@@ -409,8 +410,9 @@ void gemm(cudaStream_t s, bool a_kc, bool b_nc, const float* A, long long sAi, l
 int gemm_splitk(azp_trainer* t, cudaStream_t s, bool a_kc, bool b_nc, const float* A, long long sAi, long long sAk,
                 const float* B, long long sBk, long long sBj, float* out, int M, int N, int K, int conv_cin = 0,
                 int conv_cout = 0) {
-  const bool narrow = N <= 32;
-  const int tiles = ((N + (narrow ? 31 : 127)) / (narrow ? 32 : 128)) * ((M + 127) / 128);
+  const bool narrow = N <= 32, mid = !narrow && N <= 64;
+  const int bn = narrow ? 32 : (mid ? 64 : 128);
+  const int tiles = ((N + bn - 1) / bn) * ((M + 127) / 128);
   int splits = (SM_TARGET_CTAS + tiles - 1) / tiles;
   const int max_splits = (K + 63) / 64;            // at least four k-tiles per slice
   if (splits > max_splits) splits = max_splits;
@@ -421,6 +423,7 @@ int gemm_splitk(azp_trainer* t, cudaStream_t s, bool a_kc, bool b_nc, const floa
   if ((size_t)splits * M * N > t->partial_floats) { t->set_error("split-K workspace too small"); return AZP_ERR_CAPACITY; }
   GemmArgs g{A, B, t->partial, M, N, K, sAi, sAk, sBk, sBj, chunk, 0, nullptr, nullptr};
   if (narrow) launch_gemm_shape<128, 32, 4, 4>(g, a_kc, b_nc, splits, s);
+  else if (mid) launch_gemm_shape<128, 64, 8, 4>(g, a_kc, b_nc, splits, s);
   else launch_gemm_shape<128, 128, 8, 8>(g, a_kc, b_nc, splits, s);
   const int n = M * N;
   reduce_splits_kernel<<<(n + 255) / 256, 256, 0, s>>>(out, t->partial, n, (long long)M * N, splits, conv_cin, conv_cout);
