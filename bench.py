@@ -323,6 +323,33 @@ def run_engine_arm(args):
         barrier()
         vl = {"leaves_per_step": args.vl_leaves, "sims": eng.counters()["simulations"] - v0, "ms": vms}
 
+    # ---- side measurement (rank 0, N = 1, stem net): the consumer of the examples -- one training step of
+    #      NeuralNetworkController.train_step on BATCH_SIZE = 1024 positions, device resident
+    train = None
+    if world == 1 and not tower and not args.no_train:
+        for eng in engines:
+            eng.close()
+        engines.clear()
+        torch.cuda.empty_cache()
+        tb = 1024
+        ctrl = az.NeuralNetworkController(az.GomokuNet(BOARD), device=f"cuda:{local}", batch_size=tb)
+        gen = torch.Generator(device="cuda").manual_seed(0)
+        X = (torch.rand((tb, 4, BOARD, BOARD), device="cuda", generator=gen) < 0.15).float()
+        PI = torch.softmax(torch.randn((tb, BOARD * BOARD), device="cuda", generator=gen), dim=1)
+        Z = torch.randint(-1, 2, (tb,), device="cuda", generator=gen).float()
+        for _ in range(3):
+            ctrl.train_step(X, PI, Z, 5e-5)
+        t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0.record()
+        for _ in range(10):
+            ctrl.train_step(X, PI, Z, 5e-5)
+        t1.record()
+        torch.cuda.synchronize()
+        tms = t0.elapsed_time(t1) / 10
+        train = {"what": "NeuralNetworkController.train_step (fp32 forward + loss + backward + AdamW, hand-written CUDA), "
+                         "1024 positions resident in HBM, loss read back every step",
+                 "ms_per_step": tms, "positions_per_sec": tb / tms * 1e3, "batch": tb, "dtype": "f32"}
+
     # ---- reduce over ranks: totals summed, time = max ----------------------------------------------
     stats = torch.tensor([ms, e2e_ms, float(sims_done), float(e2e_sims), float(games_done), float(plies_done),
                           float(launches), float(evals_done)], dtype=torch.float64, device="cuda")
@@ -402,6 +429,7 @@ def run_engine_arm(args):
                     "visit counts are NOT reference-identical, the headline value above is the exact mode)",
             "leaves_per_step": vl["leaves_per_step"], "value": vl["sims"] / (vl["ms"] / 1e3), "unit": UNIT},
         "cpu_baseline": cpu,
+        "train_step": train,
     }
     print(json.dumps(line), flush=True)
     if world > 1:
@@ -426,6 +454,7 @@ def main():
                     help="1 = exact search (reference-identical visit counts); K > 1 = virtual-loss throughput mode")
     ap.add_argument("--vl-leaves", type=int, default=4, help="K of the virtual-loss side measurement")
     ap.add_argument("--no-vl", action="store_true")
+    ap.add_argument("--no-train", action="store_true", help="skip the training-step side measurement")
     ap.add_argument("--preroll", type=int, default=int(os.environ.get("AZP_BENCH_PREROLL", "64")),
                     help="untimed move steps before warm-up: brings the 2048 games to their steady-state age mix")
     ap.add_argument("--cpu-budget", type=float, default=15.0)

@@ -226,3 +226,33 @@ def test_checkpoint_and_buffer_formats(az, tmp_path, golden):
     other = az.ReplayBuffer(capacity=4)
     other.load(str(tmp_path / "buffer.pkl"))
     assert len(other) == 4 and float(other.all()[0][0][0, 0, 0]) == 3.0  # deque(maxlen) keeps the newest
+
+
+def test_promoter_rule_and_files_with_stub_evaluator(az, tmp_path):
+    """promoter.py:27-62 host logic: the candidate is saved as a new reference-format checkpoint iff win_rate > threshold
+    (strictly), the baseline is the newest file of the model directory (created random-init when empty)."""
+    from alphazero_piskvorky_b200.promoter import ModelPromoter
+
+    class StubEvaluator:
+        def __init__(self, rate):
+            self.rate, self.calls = rate, []
+
+        def evaluate(self, candidate, baseline, num_games=20, debug=False):
+            self.calls.append((candidate, baseline, num_games))
+            return self.rate, {"win_rate": self.rate, "total": num_games}
+
+    cand = az.NeuralNetworkController(az.GomokuNet(board_size=5), device="cuda")
+    model_dir = str(tmp_path / "models")
+    for rate, promoted in ((0.55, False), (0.5501, True), (0.2, False)):
+        ev = StubEvaluator(rate)
+        before = set(os.listdir(model_dir)) if os.path.isdir(model_dir) else set()
+        pr = ModelPromoter(model_dir, ev, az.GomokuNet, device="cuda")
+        wr, metrics, was = pr.evaluate_and_maybe_promote(cand, num_games=7, metadata={"episode": 1})
+        assert (wr, was) == (rate, promoted) and metrics["total"] == 7
+        assert ev.calls[0][1].net.board_size == 5 and ev.calls[0][2] == 7      # baseline = loaded best model, same board
+        new = set(os.listdir(model_dir)) - before
+        assert len(new) == (1 if not before else 0) + (1 if promoted else 0)    # first call also creates the random-init best
+        if promoted:
+            sd = torch.load(pr.best_path, weights_only=True)
+            assert all(torch.equal(sd[k], v.cpu()) for k, v in cand.net.state_dict().items())
+    assert az.should_promote(0.55) is False and az.should_promote(0.56) is True

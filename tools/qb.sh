@@ -1,7 +1,7 @@
 #!/bin/bash
 # quick bench: prints "<label> sims/s ms_per_step conv3_ms" ; usage: tools/qb.sh label [bench args...]
 label=$1; shift
-out=$(timeout 300 python bench.py --dtype bf16 --steps 3 --warmup 3 --no-cpu-baseline --no-vl --preroll 0 "$@" 2>&1 | tail -1)
+out=$(timeout 300 python bench.py --dtype bf16 --steps 3 --warmup 3 --no-cpu-baseline --no-vl --no-train --preroll 0 "$@" 2>&1 | tail -1)
 python - "$label" "$out" <<'PY'
 import sys, json
 try:
