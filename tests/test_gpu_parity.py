@@ -351,6 +351,44 @@ def test_fused_search_matches_oracle_with_engine_net(az, size, win, sims, n, dty
     eng.close()
 
 
+def test_config3_full_size_search_properties_and_spot_parity(az):
+    """BASELINE config 3 at its full per-GPU size: 2048 concurrent 15x15 games, 800 simulations per move, bf16 tcgen05
+    net.  Size-independent properties on every game (root child visits sum to the budget -- root.N == S, mcts.py:123-141;
+    no visits on occupied cells; counters add up) and exact visit-count parity against the oracle on a sample of roots
+    fed with the engine's own network outputs."""
+    size, win, sims, n = 15, 5, 800, 2048
+    params = onet.synthetic_stem_params(size, seed=42, scale=2.0)
+    eng = az.Engine(board=size, win_length=win, games=n, sims=sims, c_puct=2.0, net_dtype=az.DTYPE_BF16)
+    eng.load_state_dict(params)
+    states = []
+    for i in range(n):
+        s = gomoku.State(size, win)
+        for a in synth.random_playout(size, win, plies=(i * 7) % 90, seed=1000 + i):
+            if s.play(a).is_terminal():
+                break
+            s = s.play(a)
+        states.append(s)
+    batch = _batch(az, [s.board for s in states], [s.to_move for s in states], [_last_index(s) for s in states], win)
+    with torch.cuda.stream(torch.cuda.Stream()):
+        visits = eng.search(batch.x, batch.o, batch.to_move, batch.last).cpu().numpy()
+    boards = np.stack([s.board for s in states]).reshape(n, -1)
+    assert (visits.sum(axis=1) == sims).all()                         # every simulation passes through one root child
+    assert not visits[boards != 0].any()                              # occupied cells are never children
+    c = eng.counters()
+    assert c["simulations"] == n * sims
+    assert c["leaf_evals"] + c["terminal_leaves"] == n * sims + n      # + the root evaluations (mcts.py:109)
+    assert c["path_length"] >= c["simulations"]                       # at least the root edge per simulation
+
+    def evaluator(state):
+        _, pol, val = eng.net_forward(torch.from_numpy(state.planes()).unsqueeze(0).cuda())
+        return pol[0].cpu().numpy().reshape(size, size), float(val[0].item())
+
+    for i in (0, 777, 2047):
+        ref = omcts.Search(evaluator, sims, 2.0).run(states[i], 1.0, forced_action=states[i].legal_actions()[0])
+        assert np.array_equal(visits[i].reshape(size, size), ref.visits), i
+    eng.close()
+
+
 # ---- pi extraction, augmentation ---------------------------------------------------------------
 def test_extract_policy_vs_oracle(az):
     rs = np.random.RandomState(1)
