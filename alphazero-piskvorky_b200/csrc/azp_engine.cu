@@ -346,6 +346,7 @@ static int search_move(azp_engine* e, int n, int add_noise, int two_nets, cudaSt
     }
     e->graph_last = e->graph_exec[gi] ? gi : -1;
     // the last iteration (no descent after it) always runs as plain launches
+    e->note_stream(s);
     for (; e->graph_exec[gi] && sim + 2 <= steps - 1; sim += 2) {
       AZP_CUDA(e, cudaGraphLaunch(e->graph_exec[gi], s));
       azp_count_launch(e->graph_launches_per_replay[gi]);

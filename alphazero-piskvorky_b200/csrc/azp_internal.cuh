@@ -170,6 +170,13 @@ struct azp_engine {
   double prof_flops_per_board = 0.0;
   int32_t* d_prof_counts = nullptr;          // [PROF_MAX] leaf counts copied at launch time
   long long sp_first = 0, sp_total = 0;  // current self-play job
+  // streams this engine has launched network kernels on: a weight reload waits for THESE (not for the whole device,
+  // which would also wait for a caller's copy stream draining examples to the host and serialise it with the search)
+  std::vector<cudaStream_t> net_streams;
+  void note_stream(cudaStream_t s) {
+    for (cudaStream_t q : net_streams) if (q == s) return;
+    net_streams.push_back(s);
+  }
   void set_error(const std::string& m) { error = m; azp_set_global_error(m); }
   template <typename T> int alloc(T** p, size_t count) {
     if (alloc_reuse && alloc_pool && alloc_cursor < alloc_pool->size()) { *p = (T*)(*alloc_pool)[alloc_cursor++]; return AZP_OK; }

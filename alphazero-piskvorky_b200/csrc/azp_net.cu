@@ -359,7 +359,10 @@ int azp_net_load(azp_engine* e, int slot, const float* blob, size_t n, bool on_d
   HostNet net;
   int st = azp_net_parse(e, host.data(), n, net);
   if (st) { e->set_error("weight blob does not match the configured network"); return st; }
-  AZP_CUDA(e, cudaDeviceSynchronize());      // no kernel may still read the weights being replaced
+  // no kernel may still read the weights being replaced: wait for every stream network kernels were launched on
+  for (cudaStream_t q : e->net_streams)
+    if (cudaStreamSynchronize(q) != cudaSuccess) cudaGetLastError();          // a stream destroyed by its owner has no work left
+  AZP_CUDA(e, cudaStreamSynchronize(s));
   // A reload of the same network reuses the previous set's device buffers in allocation order: the kernels'
   // pointer arguments (and with them the captured step graph and the TMA descriptors) stay valid.
   std::vector<void*> old_allocs;
@@ -440,6 +443,7 @@ static int run_f32(azp_engine* e, NetWeights* W, const float* in4, const int32_t
 }
 
 int azp_net_eval_leaves(azp_engine* e, int slot, const int32_t* count_dev, int count_host, int back, cudaStream_t s) {
+  e->note_stream(s);
   NetWeights* W = e->weights[slot];
   if (!W || !W->loaded) { e->set_error("no weights loaded in slot " + std::to_string(slot)); return AZP_ERR_NO_WEIGHTS; }
   if (e->cfg.net_dtype == AZP_DTYPE_BF16) return azp_umma_eval_leaves(e, W, count_dev, count_host, back, s);
@@ -454,6 +458,7 @@ int azp_net_eval_leaves(azp_engine* e, int slot, const int32_t* count_dev, int c
 
 int azp_net_eval_planes(azp_engine* e, int slot, int n, const float* planes, float* logits, float* policy,
                         float* value, cudaStream_t s) {
+  e->note_stream(s);
   NetWeights* W = e->weights[slot];
   if (!W || !W->loaded) { e->set_error("no weights loaded in slot " + std::to_string(slot)); return AZP_ERR_NO_WEIGHTS; }
   const int A = e->A, G = e->slots;
