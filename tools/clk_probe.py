@@ -9,6 +9,9 @@ n = 2048
 eng = az.Engine(board=15, win_length=5, games=n, sims=2, net_dtype=az.DTYPE_BF16)
 eng.load_state_dict(onet.synthetic_stem_params(15, seed=1))
 x = torch.zeros((n, 4, 15, 15), device="cuda"); x[:, 0, 7, 7] = 1
+if os.environ.get("AZP_PROBE_RANDOM"):          # mid-game-like random positions instead of 2048 copies of one board
+    r = torch.rand((n, 15, 15), device="cuda", generator=torch.Generator(device="cuda").manual_seed(0))
+    x = torch.stack([(r < 0.15).float(), ((r >= 0.15) & (r < 0.3)).float(), torch.zeros_like(r), torch.zeros_like(r)], dim=1)
 for _ in range(3): eng.net_forward(x)
 torch.cuda.synchronize()
 c = eng.debug_activations(9, 1).cpu().numpy()
