@@ -1,5 +1,6 @@
+"""Host time of one weight reload (azp_load_weights: host repack + uploads) on a config-3 engine."""
 import sys, os, time
-sys.path.insert(0, "/root/repo")
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
 import alphazero_piskvorky_b200 as az
 net = az.GomokuNet(15)

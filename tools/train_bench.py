@@ -46,13 +46,10 @@ def main():
     net.load_state_dict({k: torch.from_numpy(v) for k, v in params.items()})
     ctrl = az.NeuralNetworkController(net, device="cuda", batch_size=args.batch)
     X, PI, Z = (torch.from_numpy(t).cuda() for t in (planes, pi, z))
-    lib = az._lib.load()
     for _ in range(args.warmup):
         ctrl.train_step(X, PI, Z, 5e-5)
     torch.cuda.synchronize()
-    c0 = az.Engine.counters if False else None
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
-    launches0 = None
     ev[0].record()
     for _ in range(args.steps):
         losses, grads = ctrl.loss_and_grads(X, PI, Z)
