@@ -383,7 +383,7 @@ def test_config3_full_size_search_properties_and_spot_parity(az):
         _, pol, val = eng.net_forward(torch.from_numpy(state.planes()).unsqueeze(0).cuda())
         return pol[0].cpu().numpy().reshape(size, size), float(val[0].item())
 
-    for i in (0, 777, 2047):
+    for i in (0, 311, 777, 1290, 1801, 2047):
         ref = omcts.Search(evaluator, sims, 2.0).run(states[i], 1.0, forced_action=states[i].legal_actions()[0])
         assert np.array_equal(visits[i].reshape(size, size), ref.visits), i
     eng.close()

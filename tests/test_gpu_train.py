@@ -55,10 +55,14 @@ def sample(a):
     return a if a.size <= 4096 else a[::4]
 
 
-@pytest.mark.parametrize("size,n", [(5, 24), (5, 1), (9, 16), (15, 7), (19, 3)])
-def test_loss_and_gradients_vs_oracle(az, size, n):
+@pytest.mark.parametrize("size,n,pi_scale", [(5, 24, 1.0), (5, 1, 1.0), (9, 16, 1.0), (15, 7, 1.0), (19, 3, 1.0), (9, 5, 0.7)])
+def test_loss_and_gradients_vs_oracle(az, size, n, pi_scale):
     params = onet.synthetic_stem_params(size, seed=100 + size)
     planes, pi, z = otrain.synthetic_batch(size, n, seed=300 + size)
+    # the reference never checks that mcts_probs sum to 1 (its ValueError is constructed, not raised: controller.py:99-100);
+    # F.cross_entropy with unnormalised targets has gradient softmax * sum(pi) - pi, which the kernel must reproduce
+    pi = (pi * np.float32(pi_scale)).astype(np.float32)
+    z = (z * np.float32(0.5 + 0.5 * pi_scale)).astype(np.float32)
     tr = az.Trainer(size, max(n, 8))
     assert tr.weight_count() == sum(int(np.prod(s)) for s in onet.stem_shapes(size).values())
     losses, grads = tr.loss_grad(flat_of(az, params), torch.from_numpy(planes), torch.from_numpy(pi), torch.from_numpy(z))
