@@ -5,7 +5,9 @@ algorithms (numpy for the board / integer work, torch-CPU functional ops for
 the network arithmetic, which in the reference also lives in PyTorch).  It is
 the checker the CUDA engine is compared against.  Only ``tests/``,
 ``__graft_entry__.smoke()`` and the ``cpu_baseline`` / ``--impl reference``
-legs of ``bench.py`` may import it; the product package
+legs of ``bench.py`` may import it (plus the bring-up diagnostics under
+``tools/``, which borrow its seeded synthetic weights / batches and time it as
+the CPU baseline of the training step); the product package
 (``alphazero-piskvorky_b200/``) never does and has no CPU fallback.
 
 Parity pin: every module here is checked against outputs of the UNMODIFIED
@@ -18,4 +20,4 @@ table) is restated in ``tests/test_oracle_golden.py``.
 All ``file:line`` citations are relative to ``/root/reference/``.
 """
 
-from . import gomoku, mcts, net, selfplay, replay, arena  # noqa: F401
+from . import gomoku, mcts, net, selfplay, replay, arena, train  # noqa: F401
