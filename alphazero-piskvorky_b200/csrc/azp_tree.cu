@@ -382,6 +382,25 @@ __global__ void __launch_bounds__(128, 4) advance_kernel(RulesParams rp, TreeVie
     tv.n_leaves[(parity ^ 1) * 2 + 1] = 0;
   }
   if (g >= n) return;
+  const bool root_prefetch = (compact >> 4) & 1;           // bit 4 of `compact`: AZP_ROOT_PREFETCH (default on)
+  compact &= 15;
+  if (tv.K == 1 && root_prefetch) {
+    // The descent below starts with the ROOT's edge arrays (20 B x A, evicted from L2 by ~100 MB of activations per
+    // step): ask L2 for them now, so that they arrive while this warp expands and backs up the previous leaf.
+    const size_t gb = (size_t)g * tv.cap * rp.A;
+    const char* pn = reinterpret_cast<const char*>(tv.N + gb);
+    const char* pw = reinterpret_cast<const char*>(tv.W + gb);
+    const char* pp = reinterpret_cast<const char*>(tv.P + gb);
+    const char* pc = reinterpret_cast<const char*>(tv.child + gb);
+    for (int o = lane * 128; o < rp.A * 8; o += 32 * 128) {
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(pw + o));
+      if (o < rp.A * 4) {
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(pn + o));
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(pp + o));
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(pc + o));
+      }
+    }
+  }
   if (!expand_backup_body<NW>(rp, tv, g, lane, policy, value, by_slot, logits)) return;
   __syncwarp();               // the descent's lanes read edges other lanes of this warp have just written
   select_body<NW>(rp, tv, g, lane, c_puct, compact, parity);
@@ -655,8 +674,10 @@ int azp_tree_expand_backup(azp_engine* e, int n, const float* policy, const floa
 }
 int azp_tree_advance(azp_engine* e, int n, const float* policy, const float* value, int by_slot, int logits, int compact,
                      int parity, cudaStream_t s) {
+  static int prefetch = -1;
+  if (prefetch < 0) { const char* v = getenv("AZP_ROOT_PREFETCH"); prefetch = v ? atoi(v) != 0 : 1; }
   AZP_DISPATCH_NW_PDL(e->NW, advance_kernel, warp_grid(n), 128, 0, s, e->rp, e->tv, n, policy, value, by_slot, logits,
-                      e->cfg.c_puct, compact, parity);
+                      e->cfg.c_puct, compact | (prefetch << 4), parity);
   azp_count_launch();
   return azp_check_launch();
 }
