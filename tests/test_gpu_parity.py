@@ -617,3 +617,29 @@ def test_reference_facade_end_to_end(az):
     fn = az.make_policy_value_fn(ctrl)
     pi, action = az.MCTS(fn, 30, 2.0).run(az.Gomoku(5, 4), temperature=1.0, add_root_noise=True)
     assert pi.shape == (5, 5) and abs(pi.sum() - 1) < 1e-5 and action is not None
+
+
+def test_bench_line_contract(az):
+    """bench.py prints ONE JSON line with the contract's keys (tiny workload; the numbers are not judged here)."""
+    import json
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--board", "9", "--games", "64", "--sims", "16",
+                          "--steps", "2", "--warmup", "3", "--preroll", "0", "--no-cpu-baseline", "--no-vl"],
+                         capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+              "vs_baseline", "dtype", "data", "config", "clocks", "e2e", "gpu_launches", "roofline", "cpu_baseline"):
+        assert k in d, k
+    assert d["metric"] == "mcts_simulations_per_sec" and d["unit"] == "sims/s" and d["n_gpus"] == 1 and d["steps"] == 2
+    assert d["value"] > 0 and d["higher_is_better"] is True and d["scaling"] == "weak" and d["vs_baseline"] is None
+    assert "workload" in d["config"] and "model" not in d["config"]
+    assert d["e2e"]["value"] > 0 and d["e2e"]["h2d_bytes_per_step"] > 0 and d["gpu_launches"] > 0
+    r = d["roofline"]
+    assert r["bound"] == "tensor" and r["unit"] == "TFLOP/s" and r["peak"] > 0 and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9
+    assert d["train_step"]["ms_per_step"] > 0

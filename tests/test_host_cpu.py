@@ -256,3 +256,12 @@ def test_promoter_rule_and_files_with_stub_evaluator(az, tmp_path):
             sd = torch.load(pr.best_path, weights_only=True)
             assert all(torch.equal(sd[k], v.cpu()) for k, v in cand.net.state_dict().items())
     assert az.should_promote(0.55) is False and az.should_promote(0.56) is True
+
+
+def test_bench_reference_arm_sampler_runs_on_cpu():
+    """bench.py's CPU leg (the oracle port of the reference's per-process inner loop, timed as the baseline): a tiny
+    bounded sample on two processes returns a positive simulations/s figure and says what the sample was."""
+    sys.path.insert(0, ROOT)
+    import bench
+    v, cores, sample = bench.cpu_port_throughput(budget_s=1.0, procs=2, board=5, win=4, nsims=20)
+    assert v > 0 and cores == 2 and "2 processes" in sample and "5x5/20 sims" in sample
