@@ -31,8 +31,8 @@ METRIC = "mcts_simulations_per_sec"
 UNIT = "sims/s"
 MEAN_GAME_PLIES = 57.3             # measured at this config: profiles/r1_game_length_probe.txt
 # DRAM bytes (read + write) of ONE conv3 launch on 2048 leaves, from `ncu --set full` (cold caches):
-# profiles/r1_ncu_full_conv_umma_final.txt -> 67.32 MB + 1.62 MB; algorithmic = act2 read once (67.1 MB)
-CONV3_DRAM_TRAFFIC_PER_2048_LEAVES = 68.94e6
+# profiles/r1c_ncu_full_step_kernels.txt -> 67.32 MB + 1.09 MB; algorithmic = act2 read once (67.1 MB)
+CONV3_DRAM_TRAFFIC_PER_2048_LEAVES = 68.41e6
 FLOPS_PER_LEAF = 42.799e6          # 2*MAC of GomokuNet(15) per position
 
 
@@ -418,7 +418,7 @@ def run_engine_arm(args):
             "frac": achieved_tflops / peak_tf if peak_tf else None,
             "traffic": (CONV3_DRAM_TRAFFIC_PER_2048_LEAVES * (games / 2048.0) / max(1, E)
                         if BOARD == 15 and not tower else None),
-            "traffic_note": "dram read+write bytes per launch from ncu --set full (profiles/r1_ncu_full_conv_umma_final.txt)",
+            "traffic_note": "dram read+write bytes per launch from ncu --set full (profiles/r1c_ncu_full_step_kernels.txt)",
             "peak_source": f"{peaks['source']} sustained bf16 (kernel timed inside a long step)",
             "kernel_ms_per_launch": kms / klaunches if klaunches else None, "kernel_launches": klaunches,
             "kernel_share_of_step": ((kms / klaunches) * (-(-args.sims // max(1, args.leaves_per_step)) + 1) / (ms / args.steps)
