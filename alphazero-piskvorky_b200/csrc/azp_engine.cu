@@ -179,6 +179,7 @@ extern "C" void azp_destroy(azp_engine* e) {
   cudaSetDevice(e->cfg.device);
   cudaDeviceSynchronize();
   for (cudaEvent_t ev : e->prof_events) cudaEventDestroy(ev);
+  if (e->reload_ev) cudaEventDestroy(e->reload_ev);
   for (cudaGraphExec_t ge : e->graph_exec) if (ge) cudaGraphExecDestroy(ge);
   for (cudaEvent_t ev : e->gprof_ev) if (ev) cudaEventDestroy(ev);
   if (e->cfg.net_dtype == AZP_DTYPE_BF16) azp_umma_destroy(e);

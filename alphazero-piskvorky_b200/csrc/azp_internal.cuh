@@ -173,7 +173,10 @@ struct azp_engine {
   // streams this engine has launched network kernels on: a weight reload waits for THESE (not for the whole device,
   // which would also wait for a caller's copy stream draining examples to the host and serialise it with the search)
   std::vector<cudaStream_t> net_streams;
+  cudaEvent_t reload_ev = nullptr; cudaStream_t reload_stream = nullptr;   // last device-side weight refresh (see azp_net_load)
+  // called wherever network kernels are about to be launched on `s`
   void note_stream(cudaStream_t s) {
+    if (reload_ev && s != reload_stream) cudaStreamWaitEvent(s, reload_ev, 0);   // the refresh ran on another stream
     for (cudaStream_t q : net_streams) if (q == s) return;
     net_streams.push_back(s);
   }

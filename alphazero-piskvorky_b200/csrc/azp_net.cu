@@ -349,6 +349,30 @@ int azp_net_load(azp_engine* e, int slot, const float* blob, size_t n, bool on_d
     e->set_error("weight blob has " + std::to_string(n) + " floats, expected " + std::to_string(azp_net_weight_count(e)));
     return AZP_ERR_INVALID_ARG;
   }
+  if (on_device && e->cfg.net_dtype == AZP_DTYPE_BF16 && e->weights[slot] && e->weights[slot]->loaded) {
+    // refresh in place on the device: order the repack after every stream that may still run kernels on the old
+    // weights (events, no host wait), then enqueue it on `s`
+    for (cudaStream_t q : e->net_streams) {
+      if (q == s) continue;
+      cudaEvent_t ev;
+      if (cudaEventCreateWithFlags(&ev, cudaEventDisableTiming) != cudaSuccess) { cudaGetLastError(); continue; }
+      if (cudaEventRecord(ev, q) == cudaSuccess) cudaStreamWaitEvent(s, ev, 0); else cudaGetLastError();
+      cudaEventDestroy(ev);
+    }
+    const int rst = azp_umma_reload_device(e, e->weights[slot], blob, s);
+    if (rst == AZP_OK) {
+      if (!e->reload_ev && cudaEventCreateWithFlags(&e->reload_ev, cudaEventDisableTiming) != cudaSuccess) {
+        cudaGetLastError(); e->reload_ev = nullptr;
+        AZP_CUDA(e, cudaStreamSynchronize(s));          // no event to order other streams with: finish the refresh now
+      } else {
+        AZP_CUDA(e, cudaEventRecord(e->reload_ev, s));
+      }
+      e->reload_stream = s;
+      e->note_stream(s);
+      return AZP_OK;
+    }
+    if (rst != AZP_ERR_UNSUPPORTED) return rst;
+  }
   std::vector<float> host(n);
   if (on_device) {
     AZP_CUDA(e, cudaStreamSynchronize(s));

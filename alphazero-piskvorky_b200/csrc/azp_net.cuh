@@ -61,6 +61,7 @@ int azp_net_parse(const azp_engine* e, const float* blob, size_t n, HostNet& net
 int azp_umma_create(azp_engine* e);
 void azp_umma_destroy(azp_engine* e);
 int azp_umma_build(azp_engine* e, const HostNet& net, NetWeights* W);
+int azp_umma_reload_device(azp_engine* e, NetWeights* W, const float* dev_blob, cudaStream_t s);
 int azp_umma_eval_leaves(azp_engine* e, NetWeights* W, const int32_t* count_dev, int count_host, int back,
                          cudaStream_t s);
 int azp_umma_debug(azp_engine* e, int layer, int n, float* out, cudaStream_t s);

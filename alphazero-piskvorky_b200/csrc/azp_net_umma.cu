@@ -1946,6 +1946,84 @@ int azp_umma_build(azp_engine* e, const HostNet& net, NetWeights* W) {
   return fc_weights_build(e, net, W, U);
 }
 
+// ---- device-side repack (azp_load_weights_device on an already loaded bf16 stem) ---------------------------------
+// Rebuilds every derived weight buffer of the stem straight from the flat state_dict blob ON THE DEVICE, with the
+// arithmetic of the host builders above (same bf16 roundings, same summation order), into the buffers the kernels,
+// tensor maps and the captured step graph already point to.  No host round trip, no synchronisation: a promotion
+// broadcast or a per-step weight refresh is just one more kernel on the stream.
+struct StemRepack {
+  const float* blob; int A, PKp, VKp;
+  size_t o_c1w, o_c1b, o_c2w, o_c2b, o_c3w, o_c3b, o_pcw, o_pcb, o_pfw, o_pfb, o_vcw, o_vcb, o_v1w, o_v1b, o_v2w, o_v2b;
+  float *w1_bits, *w1_tab, *w1_planes, *b1, *b2, *b3, *head_b8, *pfc_b, *vfc1_b, *vfc2_w, *vfc2_b;
+  __nv_bfloat16 *w1_umma, *w2, *w3, *head_w16, *wp16, *wv16;
+};
+
+__global__ void stem_repack_kernel(StemRepack r) {
+  const float* c1w = r.blob + r.o_c1w; const float* c1b = r.blob + r.o_c1b;
+  const int A = r.A, PK = 4 * A, VK = 2 * A;
+  // segment sizes, in the order they are walked
+  const long long n[12] = {27 * 32, 36 * 32, 72 * 32, 4 * 32 * 32, 9 * 64 * 32, 9 * 128 * 64, HEAD_N * 128,
+                           (long long)A * r.PKp, 64LL * r.VKp, 32 + 64 + 128 + 8, A + 64 + 64 + 1, 0};
+  long long total = 0;
+  for (int i = 0; i < 11; i++) total += n[i];
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    long long i = idx;
+    int seg = 0;
+    while (i >= n[seg]) { i -= n[seg]; seg++; }
+    const int k = (int)i;
+    if (seg == 0) {                                   // w1_bits [tap][3][32]
+      const int co = k % 32, ci = (k / 32) % 3, t = k / 96;
+      r.w1_bits[k] = c1w[(co * 4 + ci) * 9 + t];
+    } else if (seg == 1) {                            // w1_planes [tap][4][32]
+      const int co = k % 32, ci = (k / 32) % 4, t = k / 128;
+      r.w1_planes[k] = c1w[(co * 4 + ci) * 9 + t];
+    } else if (seg == 2) {                            // w1_tab [plane(3)][ky][pattern(8)][32], kx summed in order 0,1,2
+      const int co = k % 32, pat = (k / 32) % 8, ky = (k / 256) % 3, pl = k / 768;
+      float t = 0.f;
+      for (int kx = 0; kx < 3; kx++)
+        if (pat & (1 << kx)) t = __fadd_rn(t, c1w[(co * 4 + pl) * 9 + ky * 3 + kx]);
+      r.w1_tab[k] = t;
+    } else if (seg == 3) {                            // w1_umma [4][32][32]: hi, lo (planes 0..2 + bias), plane-3 hi, lo
+      const int kk = k % 32, co = (k / 32) % 32, mat = k / 1024;
+      float v = 0.f;
+      if (mat < 2) {
+        if (kk < 27) { const int ky = kk / 9, rem = kk % 9, pl = rem / 3, kx = rem % 3; v = c1w[(co * 4 + pl) * 9 + ky * 3 + kx]; }
+        else if (kk == 27) v = c1b[co];
+      } else if (kk < 9) {
+        v = c1w[(co * 4 + 3) * 9 + kk];
+      }
+      const __nv_bfloat16 hi = __float2bfloat16(v);
+      r.w1_umma[k] = (mat & 1) ? __float2bfloat16(__fsub_rn(v, __bfloat162float(hi))) : hi;
+    } else if (seg == 4) {                            // w2 [tap][64][32]
+      const int ci = k % 32, co = (k / 32) % 64, t = k / 2048;
+      r.w2[k] = __float2bfloat16(r.blob[r.o_c2w + ((size_t)co * 32 + ci) * 9 + t]);
+    } else if (seg == 5) {                            // w3 [tap][128][64]
+      const int ci = k % 64, co = (k / 64) % 128, t = k / 8192;
+      r.w3[k] = __float2bfloat16(r.blob[r.o_c3w + ((size_t)co * 64 + ci) * 9 + t]);
+    } else if (seg == 6) {                            // head_w16 [16][128]: policy rows, value rows, zero padding
+      const int c = k % 128, j = k / 128;
+      const float v = j < 4 ? r.blob[r.o_pcw + j * 128 + c] : (j < 6 ? r.blob[r.o_vcw + (j - 4) * 128 + c] : 0.f);
+      r.head_w16[k] = __float2bfloat16(v);
+    } else if (seg == 7) {                            // wp16 [A][PKp]
+      const int kk = k % r.PKp, a = k / r.PKp;
+      r.wp16[k] = __float2bfloat16(kk < PK ? r.blob[r.o_pfw + (size_t)a * PK + kk] : 0.f);
+    } else if (seg == 8) {                            // wv16 [64][VKp]
+      const int kk = k % r.VKp, j = k / r.VKp;
+      r.wv16[k] = __float2bfloat16(kk < VK ? r.blob[r.o_v1w + (size_t)j * VK + kk] : 0.f);
+    } else if (seg == 9) {                            // conv biases + head bias
+      if (k < 32) r.b1[k] = c1b[k];
+      else if (k < 96) r.b2[k - 32] = r.blob[r.o_c2b + k - 32];
+      else if (k < 224) r.b3[k - 96] = r.blob[r.o_c3b + k - 96];
+      else { const int j = k - 224; r.head_b8[j] = j < 4 ? r.blob[r.o_pcb + j] : (j < 6 ? r.blob[r.o_vcb + j - 4] : 0.f); }
+    } else {                                          // FC biases and the value tail
+      if (k < A) r.pfc_b[k] = r.blob[r.o_pfb + k];
+      else if (k < A + 64) r.vfc1_b[k - A] = r.blob[r.o_v1b + k - A];
+      else if (k < A + 128) r.vfc2_w[k - A - 64] = r.blob[r.o_v2w + k - A - 64];
+      else r.vfc2_b[0] = r.blob[r.o_v2b];
+    }
+  }
+}
+
 // policy_fc / value_fc1 as bf16 [out][K padded to 8] (B operands of fc_umma_kernel) + fp32 biases / tails
 static int fc_weights_build(azp_engine* e, const HostNet& net, NetWeights* W, UmmaWeights* U) {
   UmmaWorkspace* ws = (UmmaWorkspace*)e->ws->umma;
@@ -1970,6 +2048,32 @@ static int fc_weights_build(azp_engine* e, const HostNet& net, NetWeights* W, Um
 
 static int launch_fc(azp_engine* e, NetWeights* W, const int32_t* count_dev, int count_host, int back, float* logits,
                      float* policy, float* value, int out_by_index, cudaStream_t s);
+
+// Returns AZP_OK after enqueueing the repack on `s`, AZP_ERR_UNSUPPORTED when this weight set cannot be refreshed in
+// place (tower, first load): the caller then takes the host path.
+int azp_umma_reload_device(azp_engine* e, NetWeights* W, const float* dev_blob, cudaStream_t s) {
+  if (e->cfg.net_kind != AZP_NET_STEM || !W || !W->loaded || !W->umma) return AZP_ERR_UNSUPPORTED;
+  UmmaWorkspace* ws = (UmmaWorkspace*)e->ws->umma;
+  UmmaWeights* U = (UmmaWeights*)W->umma;
+  const size_t A = e->A;
+  StemRepack r;
+  r.blob = dev_blob; r.A = (int)A; r.PKp = ws->PKp; r.VKp = ws->VKp;
+  size_t o = 0;
+  auto take = [&](size_t& off, size_t cnt) { off = o; o += cnt; };
+  take(r.o_c1w, 32 * 4 * 9); take(r.o_c1b, 32); take(r.o_c2w, 64 * 32 * 9); take(r.o_c2b, 64);
+  take(r.o_c3w, 128 * 64 * 9); take(r.o_c3b, 128); take(r.o_pcw, 4 * 128); take(r.o_pcb, 4);
+  take(r.o_pfw, A * 4 * A); take(r.o_pfb, A); take(r.o_vcw, 2 * 128); take(r.o_vcb, 2);
+  take(r.o_v1w, 64 * 2 * A); take(r.o_v1b, 64); take(r.o_v2w, 64); take(r.o_v2b, 1);
+  r.w1_bits = U->w1_bits; r.w1_tab = U->w1_tab; r.w1_planes = U->w1_planes; r.b1 = U->b1; r.b2 = U->b2; r.b3 = U->b3;
+  r.head_b8 = U->head_b8; r.pfc_b = W->pfc_b; r.vfc1_b = W->vfc1_b; r.vfc2_w = W->vfc2_w; r.vfc2_b = W->vfc2_b;
+  r.w1_umma = U->w1_umma; r.w2 = U->w2; r.w3 = U->w3; r.head_w16 = U->head_w16; r.wp16 = U->wp16; r.wv16 = U->wv16;
+  if (!r.w1_bits || !r.w1_tab || !r.w1_planes || !r.b1 || !r.b2 || !r.b3 || !r.head_b8 || !r.pfc_b || !r.vfc1_b ||
+      !r.vfc2_w || !r.vfc2_b || !r.w1_umma || !r.w2 || !r.w3 || !r.head_w16 || !r.wp16 || !r.wv16)
+    return AZP_ERR_UNSUPPORTED;
+  stem_repack_kernel<<<148 * 2, 256, 0, s>>>(r);
+  azp_count_launch();
+  return azp_check_launch();
+}
 
 // residual tower: first conv -> 2 convs per block (the second adds the block input) -> 1x1 heads -> FC
 static int run_tower(azp_engine* e, NetWeights* W, const int32_t* count_dev, int count_host, int back, int n_planes,

@@ -190,6 +190,13 @@ def run_engine_arm(args):
     host_out = [(torch.empty((cap, 4, BOARD, BOARD)).pin_memory(), torch.empty((cap, BOARD, BOARD)).pin_memory(),
                  torch.empty((cap,), dtype=torch.int32).pin_memory()) for _ in range(2)]
     copy_streams = [torch.cuda.Stream() for _ in range(E)]
+    blob_dev = torch.empty(blob_host.numel(), device="cuda")
+
+    def upload_weights(k):
+        """e2e arm: the step's weights travel pinned host -> device on the engine's stream and are repacked there
+        (azp_load_weights_device: in place, no host synchronisation)."""
+        blob_dev.copy_(blob_host, non_blocking=True)
+        engines[k].load_blob(blob_dev)
     total_games = 1 << 40                    # endless stream of games: finished slots are re-seated
     first_flag = [True] * E
 
@@ -208,15 +215,11 @@ def run_engine_arm(args):
                     # the dominant kernel is bracketed with CUDA events on the LAST timed step only: the event nodes
                     # cut the programmatic-dependent-launch edges around it, so the other steps run unperturbed
                     engines[k].set_profiling(True)
-                if e2e and i == 0 and os.environ.get("AZP_E2E_SKIP", "") != "h2d":
-                    engines[k].load_blob(blob_host.numpy())            # weights: host -> device, once per step (see below)
+                if e2e and os.environ.get("AZP_E2E_SKIP", "") != "h2d":
+                    upload_weights(k)                                  # weights: host -> device, every step
                 st, _, _, _, w = engines[k].selfplay(total_games, first_game=0, out=outs[k][slab],
                                                      resume=not first_flag[k], max_move_steps=1)
                 first_flag[k] = False
-                if e2e and i + 1 < n and os.environ.get("AZP_E2E_SKIP", "") != "h2d":
-                    # the NEXT step's weights go up before this step's examples start draining: the reload's blocking
-                    # cudaMemcpy calls otherwise queue behind the 97 MB device->host transfer (3 ms per step)
-                    engines[k].load_blob(blob_host.numpy())
                 if e2e and w and os.environ.get("AZP_E2E_SKIP", "") != "d2h":
                     # examples: device -> pinned host on a copy stream, overlapping the next move step (the driver is
                     # synchronous at return, so the slab is complete); everything drains inside the timed region

@@ -619,6 +619,41 @@ def test_reference_facade_end_to_end(az):
     assert pi.shape == (5, 5) and abs(pi.sum() - 1) < 1e-5 and action is not None
 
 
+def test_device_side_weight_refresh_is_bit_identical(az):
+    """azp_load_weights_device on an already loaded bf16 stem repacks every derived buffer ON the device (no host round
+    trip, no synchronisation).  The result must be bit-identical to a fresh engine loaded through the host builders:
+    planes path (net_forward) and leaf path (whole searches, conv1 from bitboards)."""
+    size, win, n, sims = 15, 5, 64, 40
+    pa, pb = onet.synthetic_stem_params(size, seed=1), onet.synthetic_stem_params(size, seed=2, scale=2.0)
+    rs = np.random.RandomState(3)
+    x = torch.from_numpy((rs.random_sample((n, 4, size, size)) < 0.2).astype(np.float32)).cuda()
+    states = []
+    for i in range(n):
+        s = gomoku.State(size, win)
+        for a in synth.random_playout(size, win, plies=(i * 5) % 60, seed=70 + i):
+            if s.play(a).is_terminal():
+                break
+            s = s.play(a)
+        states.append(s)
+    batch = _batch(az, [s.board for s in states], [s.to_move for s in states], [_last_index(s) for s in states], win)
+    e1 = az.Engine(board=size, win_length=win, games=n, sims=sims, net_dtype=az.DTYPE_BF16)
+    e1.load_state_dict(pa)
+    with torch.cuda.stream(torch.cuda.Stream()):
+        before = e1.search(batch.x, batch.o, batch.to_move, batch.last).clone()      # graph captured on the OLD weights
+        e1.load_blob(torch.from_numpy(az.flatten_state_dict(pb)).cuda())             # in place, on this stream
+        v1 = e1.search(batch.x, batch.o, batch.to_move, batch.last).clone()
+        l1, _, val1 = e1.net_forward(x)
+    e2 = az.Engine(board=size, win_length=win, games=n, sims=sims, net_dtype=az.DTYPE_BF16)
+    e2.load_state_dict(pb)                                                           # host builders
+    with torch.cuda.stream(torch.cuda.Stream()):
+        v2 = e2.search(batch.x, batch.o, batch.to_move, batch.last).clone()
+        l2, _, val2 = e2.net_forward(x)
+    torch.cuda.synchronize()
+    assert torch.equal(l1, l2) and torch.equal(val1, val2)
+    assert torch.equal(v1, v2) and not torch.equal(before, v1)
+    e1.close(); e2.close()
+
+
 def test_bench_line_contract(az):
     """bench.py prints ONE JSON line with the contract's keys (tiny workload; the numbers are not judged here)."""
     import json
