@@ -125,7 +125,10 @@ int azp_augment_write(int board, int mode, int n, const float* planes, const flo
  * value_conv.*, value_fc1.*, value_fc2.*; net.py:37-53), PyTorch layouts.  slot 0 = the
  * self-play / candidate net, slot 1 = the arena baseline.  Synchronous. */
 int azp_load_weights(azp_engine* e, int slot, const float* host_blob, size_t n_floats);
-/* same, blob already on this device (after an NCCL broadcast of promoted weights) */
+/* same, blob already on this device (after an NCCL broadcast of promoted weights, or a per-step refresh).  On an
+ * already loaded bf16 stem the derived buffers are rebuilt IN PLACE by one kernel on `stream` (bit-identical to the host
+ * builders; asynchronous, ordered after the engine's earlier work on any stream); first loads, the fp32 path and the
+ * tower go through the host and are synchronous. */
 int azp_load_weights_device(azp_engine* e, int slot, const float* dev_blob, size_t n_floats, void* stream);
 size_t azp_weight_count(const azp_engine* e);
 /* GomokuNet.forward + controller.py:33-55: planes float32 [n][4][B][B] ->
