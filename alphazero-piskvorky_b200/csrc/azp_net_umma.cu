@@ -1472,7 +1472,9 @@ struct FcArgs {
   const float* vfc2_w; const float* vfc2_b;
   float* logits; float* value;
   const int32_t* count_dev; int count_host; int back; int out_by_index;
+  long long* clk;                 // bring-up (AZP_CLK=4): wall-clock ns stamps of CTA (0,0) or null
 };
+#define FC_STAMP(cond, k) do { if (args.clk && blockIdx.x == 0 && blockIdx.y == 0 && (cond)) { unsigned long long gt_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt_)); args.clk[k] = (long long)gt_; } } while (0)
 
 constexpr int FC_N = 64;
 constexpr int FC_EPI_WARPS = 8;                        // warp (q, h): TMEM lanes 32q..32q+31 (boards), columns 32h..32h+31
@@ -1501,6 +1503,7 @@ __global__ void __launch_bounds__(FC_THREADS, 1) fc_umma_kernel(const __grid_con
   float* s_w2 = s_bias + 64;                                        // [64] + [1] (+pad)
   float* s_part = s_w2 + 72;                                        // [2][128] value partial sums
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  FC_STAMP(threadIdx.x == 0, 0);
 
   // ---- prologue: constants only (overlaps the previous kernel's tail under programmatic dependent launch) ----
   if (threadIdx.x == 0) {
@@ -1519,8 +1522,10 @@ __global__ void __launch_bounds__(FC_THREADS, 1) fc_umma_kernel(const __grid_con
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
+  FC_STAMP(threadIdx.x == 0, 1);
   pdl_wait();                      // leaf count + head features come from the previous kernels of the stream
   pdl_launch_dependents();
+  FC_STAMP(threadIdx.x == 0, 2);
   const int count = args.count_dev ? *args.count_dev : args.count_host;
   const int row0 = (args.back ? args.G - count : 0) + tile * TILE_M;
   if (tile * TILE_M >= count) {    // nothing to do for this tile: release TMEM and leave (uniform per CTA)
@@ -1548,6 +1553,7 @@ __global__ void __launch_bounds__(FC_THREADS, 1) fc_umma_kernel(const __grid_con
         const int st = kc % args.stages;
         const uint32_t ph = (kc / args.stages) & 1;
         mbar_wait(&full[st], ph);
+        if (kc == 0) FC_STAMP(true, 3);
         tc_fence_after();
         const uint32_t a_addr = smem_u32(smem + (size_t)st * FC_STAGE_BYTES);
         const uint32_t b_addr = a_addr + TILE_M * 128;
@@ -1559,12 +1565,14 @@ __global__ void __launch_bounds__(FC_THREADS, 1) fc_umma_kernel(const __grid_con
         umma_commit(&empty[st]);
       }
       umma_commit(tfull);
+      FC_STAMP(true, 4);
     }
   } else {
     // ===== epilogue =====
     const int q = warp & 3, h = (warp - 2) >> 2;
     const int ew = warp - 2;                                   // 0..7
     mbar_wait_sleep(tfull, 0);
+    FC_STAMP(warp == 2 && lane == 0, 5);
     tc_fence_after();
     const int trow = q * 32 + lane;
     const int bi = tile * TILE_M + trow;                       // index within the evaluated batch
@@ -1603,6 +1611,7 @@ __global__ void __launch_bounds__(FC_THREADS, 1) fc_umma_kernel(const __grid_con
   }
   tc_fence_before();
   __syncthreads();
+  FC_STAMP(threadIdx.x == 0, 6);
   if (warp == 1) tmem_dealloc(tmem_base, FC_N);
 }
 
@@ -2197,6 +2206,7 @@ static int launch_fc(azp_engine* e, NetWeights* W, const int32_t* count_dev, int
   fa.pbias = W->pfc_b; fa.vbias = W->vfc1_b;
   fa.vfc2_w = W->vfc2_w; fa.vfc2_b = W->vfc2_b; fa.logits = logits_out; fa.value = value;
   fa.count_dev = count_dev; fa.count_host = count_host; fa.back = back; fa.out_by_index = out_by_index;
+  { const char* v = getenv("AZP_CLK"); fa.clk = (v && atoi(v) == 4) ? ws->clk : nullptr; }
   dim3 fc_grid((zmax + TILE_M - 1) / TILE_M, fa.n_slices + 1);
   azp_launch(fc_umma_kernel, fc_grid, FC_THREADS, ws->fc_smem, s, true, ws->map_feat, U->map_wp, U->map_wv, fa);
   azp_count_launch();

@@ -17,6 +17,11 @@ torch.cuda.synchronize()
 c = eng.debug_activations(9, 1).cpu().numpy()
 names = {0: "P:before empty", 1: "P:after empty", 2: "M:before tempty", 3: "M:after tempty", 4: "M:full landed", 5: "M:conv issued+commit",
          6: "M:head issued", 8: "E:before tfull", 9: "E:after tfull", 10: "E:math+st issued", 11: "E:arrived", 12: "E:heads written"}
+if os.environ["AZP_CLK"] == "4":        # FC kernel: wall-clock ns of CTA (0,0) from kernel entry
+    f = c.reshape(-1)
+    print("fc wall ns from entry: prologue done %d, predecessor done %d, first chunk landed %d, all MMAs issued %d, accumulator ready %d, CTA done %d"
+          % tuple(int(f[i] - f[0]) for i in range(1, 7)))
+    sys.exit(0)
 t0 = c[0, 2]
 print("tile | " + " | ".join(f"{names[k]:>20s}" for k in sorted(names)))
 for tl in range(0, 28):
