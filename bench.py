@@ -215,12 +215,12 @@ def run_engine_arm(args):
                     # the dominant kernel is bracketed with CUDA events on the LAST timed step only: the event nodes
                     # cut the programmatic-dependent-launch edges around it, so the other steps run unperturbed
                     engines[k].set_profiling(True)
-                if e2e and os.environ.get("AZP_E2E_SKIP", "") != "h2d":
+                if e2e:
                     upload_weights(k)                                  # weights: host -> device, every step
                 st, _, _, _, w = engines[k].selfplay(total_games, first_game=0, out=outs[k][slab],
                                                      resume=not first_flag[k], max_move_steps=1)
                 first_flag[k] = False
-                if e2e and w and os.environ.get("AZP_E2E_SKIP", "") != "d2h":
+                if e2e and w:
                     # examples: device -> pinned host on a copy stream, overlapping the next move step (the driver is
                     # synchronous at return, so the slab is complete); everything drains inside the timed region
                     ready = torch.cuda.Event()
