@@ -86,9 +86,24 @@ class NeuralNetworkController:
         """Forward + loss + backward on the device; returns (losses float32[4] CUDA tensor = policy, value,
         entropy, total; flat gradient blob).  With world > 1 the gradients are averaged over ranks (NCCL)."""
         flat = self.flat_parameters()
-        tr = self._get_trainer(int(state_batch.shape[0]))
+        n = int(state_batch.shape[0])
+        chunk = max(self.batch_size, 1)
         with torch.cuda.device(flat.device):
-            losses, grads = tr.loss_grad(flat, state_batch, mcts_probs, winner_batch, self._grads)
+            if n <= chunk:
+                tr = self._get_trainer(n)
+                losses, grads = tr.loss_grad(flat, state_batch, mcts_probs, winner_batch, self._grads)
+            else:
+                # a batch larger than the workspace (the im2col buffer alone is 9*128*4 bytes per board cell) is
+                # processed in chunks of batch_size; batch means combine with the weights n_i / n
+                tr = self._get_trainer(chunk)
+                part = torch.empty_like(self._grads)
+                grads, losses = self._grads.zero_(), torch.zeros(4, device=flat.device)
+                pi2 = torch.as_tensor(mcts_probs).reshape(n, -1)
+                for i in range(0, n, chunk):
+                    j = min(n, i + chunk)
+                    l, g = tr.loss_grad(flat, state_batch[i:j], pi2[i:j], torch.as_tensor(winner_batch)[i:j], part)
+                    grads.add_(g, alpha=(j - i) / n)
+                    losses.add_(l, alpha=(j - i) / n)
             if self.world > 1:
                 from .dist import all_reduce_mean
                 all_reduce_mean(grads)
@@ -108,10 +123,17 @@ class NeuralNetworkController:
     def evaluate_losses(self, state_batch, mcts_probs, winner_batch):
         """(policy loss, value loss) of the current weights, forward only."""
         flat = self.flat_parameters()
-        tr = self._get_trainer(int(state_batch.shape[0]))
+        n = int(state_batch.shape[0])
+        chunk = max(self.batch_size, 1)
+        tr = self._get_trainer(min(n, chunk))
+        pi2 = torch.as_tensor(mcts_probs).reshape(n, -1)
+        total = torch.zeros(4, device=flat.device)
         with torch.cuda.device(flat.device):
-            losses, _ = tr.loss_grad(flat, state_batch, mcts_probs, winner_batch, want_grads=False)
-        host = losses.cpu()
+            for i in range(0, n, chunk):
+                j = min(n, i + chunk)
+                l, _ = tr.loss_grad(flat, state_batch[i:j], pi2[i:j], torch.as_tensor(winner_batch)[i:j], want_grads=False)
+                total.add_(l, alpha=(j - i) / n)
+        host = total.cpu()
         return float(host[0]), float(host[1])
 
     def train(self, examples, epochs=10, lr=LEARNING_RATE, generator=None):

@@ -142,6 +142,7 @@ def test_train_steps_vs_reference_golden(az, golden, size, steps):
         assert np.quantile(d, 0.995) <= 2e-6 and d.max() <= 2 * lr * steps + 1e-7, (k, np.quantile(d, 0.995), d.max())
     # the module's parameters are views of the flat blob the kernels update
     assert ctrl._bound() and next(ctrl.net.parameters()).is_cuda
+    # (batch_size = 8 here, so every step above ran as chunks of 8 whose batch means were recombined with weights n_i / n)
 
 
 def test_full_batch_is_deterministic_and_linear(az):
