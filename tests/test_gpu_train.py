@@ -256,3 +256,25 @@ def test_human_vs_ai_scripted(az):
     winner = human_vs_ai(model=az.GomokuNet(board_size=5), board_size=5, win_length=4, num_simulations=24,
                          input_fn=scripted, output_fn=out)
     assert winner in ("X", "O", "D") and any(isinstance(x, str) and x.startswith("AI plays") for x in log)
+
+
+def test_device_resident_replay_to_training(az):
+    """SURVEY 8f row 1 as titled: the training step on the GPU-RESIDENT replay buffer -- self-play slabs go into the device
+    ring (ReplayBuffer.extend_device), uniform sampling without replacement (sample_device), train_tensors; nothing
+    touches the host except the per-step loss read-back."""
+    net = az.GomokuNet(board_size=9)
+    ctrl = az.NeuralNetworkController(net, device="cuda", batch_size=256)
+    mgr = az.SelfPlayManager(ctrl, device="cuda", mcts_params={"num_simulations": 24, "c_puct": 2.0}, win_length=5,
+                             concurrent_games=32, augment="d4", net_dtype=az.DTYPE_BF16)
+    buf = az.ReplayBuffer(capacity=6000)
+    for planes, pi, z in mgr.generate_device(32):
+        assert planes.is_cuda and pi.is_cuda and z.is_cuda
+        buf.extend_device(planes, pi, z)
+    assert buf.device_len() == min(6000, buf._head) and buf.device_len() > 32 * 9 * 8
+    g = torch.Generator(device="cuda").manual_seed(0)
+    P, PI, Z = buf.sample_device(1024, generator=g)
+    assert P.shape == (1024, 4, 9, 9) and PI.shape == (1024, 9, 9) and Z.shape == (1024,)
+    assert torch.allclose(PI.reshape(1024, -1).sum(dim=1), torch.ones(1024, device="cuda"), atol=1e-4)
+    before = ctrl.evaluate_losses(P, PI, Z)
+    last = ctrl.train_tensors(P, PI, Z, epochs=4, lr=1e-3)
+    assert len(ctrl.training_history) == 4 and last["policy"] + last["value"] < before[0] + before[1]
