@@ -351,19 +351,24 @@ def test_fused_search_matches_oracle_with_engine_net(az, size, win, sims, n, dty
     eng.close()
 
 
-def test_config3_full_size_search_properties_and_spot_parity(az):
-    """BASELINE config 3 at its full per-GPU size: 2048 concurrent 15x15 games, 800 simulations per move, bf16 tcgen05
-    net.  Size-independent properties on every game (root child visits sum to the budget -- root.N == S, mcts.py:123-141;
-    no visits on occupied cells; counters add up) and exact visit-count parity against the oracle on a sample of roots
-    fed with the engine's own network outputs."""
-    size, win, sims, n = 15, 5, 800, 2048
+@pytest.mark.parametrize("size,win,sims,n,spots", [
+    (15, 5, 800, 2048, (0, 311, 777, 1290, 1801, 2047)),       # config 3, one GPU's share
+    (9, 5, 400, 4096, (0, 613, 1777, 2890, 3501, 4095)),       # config 2
+    (19, 5, 1600, 50, (0, 23, 49)),                            # config 5's search shape (one GPU's 50 arena games)
+], ids=["config3", "config2", "config5"])
+def test_full_size_search_properties_and_spot_parity(az, size, win, sims, n, spots):
+    """BASELINE configs at their full per-GPU sizes (config 3: 2048 concurrent 15x15 games x 800 simulations; config 2:
+    4096 9x9 games x 400; config 5: 50 19x19 games x 1600), bf16 tcgen05 net.  Size-independent properties on every
+    game (root child visits sum to the budget -- root.N == S, mcts.py:123-141; no visits on occupied cells; counters
+    add up) and exact visit-count parity against the oracle on a sample of roots fed with the engine's own network
+    outputs."""
     params = onet.synthetic_stem_params(size, seed=42, scale=2.0)
     eng = az.Engine(board=size, win_length=win, games=n, sims=sims, c_puct=2.0, net_dtype=az.DTYPE_BF16)
     eng.load_state_dict(params)
     states = []
     for i in range(n):
         s = gomoku.State(size, win)
-        for a in synth.random_playout(size, win, plies=(i * 7) % 90, seed=1000 + i):
+        for a in synth.random_playout(size, win, plies=(i * 7) % (2 * size * size // 5), seed=1000 + i):
             if s.play(a).is_terminal():
                 break
             s = s.play(a)
@@ -383,7 +388,7 @@ def test_config3_full_size_search_properties_and_spot_parity(az):
         _, pol, val = eng.net_forward(torch.from_numpy(state.planes()).unsqueeze(0).cuda())
         return pol[0].cpu().numpy().reshape(size, size), float(val[0].item())
 
-    for i in (0, 311, 777, 1290, 1801, 2047):
+    for i in spots:
         ref = omcts.Search(evaluator, sims, 2.0).run(states[i], 1.0, forced_action=states[i].legal_actions()[0])
         assert np.array_equal(visits[i].reshape(size, size), ref.visits), i
     eng.close()
