@@ -65,6 +65,7 @@ SIGNATURES = {
     "azp_leaf_states": (C.c_int, [P, P, P, P, P, P, P]),
     "azp_expand_backup": (C.c_int, [P, P, P, P]),
     "azp_root_visits": (C.c_int, [P, P, P]),
+    "azp_root_priors": (C.c_int, [P, P, P]),
     "azp_search": (C.c_int, [P, C.c_int, C.c_int, P, P, P, P, P, P, C.c_int, P, P]),
     "azp_set_temperature_table": (C.c_int, [P, P, C.c_int]),
     "azp_selfplay_run": (C.c_int, [P, C.c_int64, C.c_int64, C.c_int, C.c_int, P, P, P, C.c_int64,

@@ -277,6 +277,10 @@ extern "C" int azp_root_visits(azp_engine* e, int32_t* visits, void* stream) {
   if (!e || e->search_n < 1 || !visits) return AZP_ERR_INVALID_ARG;
   return azp_tree_root_visits(e, e->search_n, visits, (cudaStream_t)stream);
 }
+extern "C" int azp_root_priors(azp_engine* e, float* priors, void* stream) {
+  if (!e || e->search_n < 1 || !priors) return AZP_ERR_INVALID_ARG;
+  return azp_tree_root_priors(e, e->search_n, priors, (cudaStream_t)stream);
+}
 
 // evaluate the leaf batch of counter pair `parity` with the engine's own net(s)
 static int eval_step(azp_engine* e, int two_nets, int parity, cudaStream_t s) {

@@ -210,6 +210,7 @@ int azp_softmax_rows(int n, int A, const float* logits, float* policy, cudaStrea
 int azp_tree_advance(azp_engine* e, int n, const float* policy, const float* value, int by_slot, int logits, int compact,
                      int parity, cudaStream_t s);
 int azp_tree_root_visits(azp_engine* e, int n, int32_t* visits, cudaStream_t s);
+int azp_tree_root_priors(azp_engine* e, int n, float* priors, cudaStream_t s);
 int azp_tree_leaf_states(azp_engine* e, int n, uint64_t* x, uint64_t* o, uint8_t* tm, int16_t* last, uint8_t* kind, cudaStream_t s);
 int azp_episode_seat(azp_engine* e, int n, int arena, cudaStream_t s);
 int azp_episode_end_move(azp_engine* e, int n, int arena, cudaStream_t s);

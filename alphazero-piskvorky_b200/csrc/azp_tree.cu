@@ -416,6 +416,14 @@ __global__ void root_visits_kernel(TreeView tv, int n, int32_t* __restrict__ vis
   visits[i] = legal ? tv.N[(size_t)g * tv.cap * tv.A + a] : 0;
 }
 
+// root priors as stored by root_expand (after the Dirichlet mix of mcts.py:114-116); 0 on occupied cells
+__global__ void root_priors_kernel(TreeView tv, int n, float* __restrict__ priors) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (size_t)n * tv.A) return;
+  int g = i / tv.A, a = i % tv.A;
+  priors[i] = tv.P[(size_t)g * tv.cap * tv.A + a];
+}
+
 __global__ void leaf_states_kernel(TreeView tv, int n, uint64_t* x, uint64_t* o, uint8_t* tm, int16_t* last,
                                    uint8_t* kind) {
   int g = blockIdx.x * blockDim.x + threadIdx.x;
@@ -683,6 +691,11 @@ int azp_tree_advance(azp_engine* e, int n, const float* policy, const float* val
 }
 int azp_tree_root_visits(azp_engine* e, int n, int32_t* visits, cudaStream_t s) {
   root_visits_kernel<<<(int)(((size_t)n * e->A + 255) / 256), 256, 0, s>>>(e->tv, n, visits);
+  azp_count_launch();
+  return azp_check_launch();
+}
+int azp_tree_root_priors(azp_engine* e, int n, float* priors, cudaStream_t s) {
+  root_priors_kernel<<<(int)(((size_t)n * e->A + 255) / 256), 256, 0, s>>>(e->tv, n, priors);
   azp_count_launch();
   return azp_check_launch();
 }

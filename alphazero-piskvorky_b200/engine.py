@@ -169,6 +169,12 @@ class Engine:
         check(self.lib.azp_root_visits(self.h, ptr(v), stream_ptr()), self.h)
         return v
 
+    def root_priors(self):
+        """Priors of the root's children [n,A] after root_expand (mcts.py:109-120); 0 on occupied cells."""
+        p = torch.empty((self._n, self.A), dtype=torch.float32, device=self.device)
+        check(self.lib.azp_root_priors(self.h, ptr(p), stream_ptr()), self.h)
+        return p
+
     def search(self, x, o, to_move, last, ply=None, game_id=None, add_noise=False):
         """Full search of n roots with the engine's own net; returns root visit counts [n,A]."""
         n = x.shape[0]

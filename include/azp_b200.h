@@ -159,6 +159,10 @@ int azp_leaf_states(azp_engine* e, uint64_t* x, uint64_t* o, uint8_t* to_move, i
 int azp_expand_backup(azp_engine* e, const float* policy, const float* value, void* stream);
 /* root child visit counts int32 [n][B*B] (the reference computes them at mcts.py:144) */
 int azp_root_visits(azp_engine* e, int32_t* visits, void* stream);
+/* root priors float32 [n][B*B] as the search holds them after azp_root_expand: policy[r,c] on legal cells,
+ * (1-w)*policy + w*Dirichlet(alpha) if add_noise was set (mcts.py:109-120, Node.expand mcts.py:50-64); 0 on
+ * occupied cells */
+int azp_root_priors(azp_engine* e, float* priors, void* stream);
 /* whole search with the engine's own net: begin + root eval + S x (select, net, expand_backup) */
 int azp_search(azp_engine* e, int slot, int n, const uint64_t* x, const uint64_t* o,
                const uint8_t* to_move, const int16_t* last, const int32_t* ply,

@@ -591,6 +591,67 @@ def test_selfplay_noise_and_sampling_are_distributionally_sane(az):
     eng.close()
 
 
+def test_root_noise_is_dirichlet_and_mixed_like_the_reference(az):
+    """mcts.py:109-120 in isolation, through azp_root_expand / azp_root_priors.  Without noise the root priors are the
+    policy on legal cells (not renormalised, mcts.py:50-64) and 0 elsewhere, bit-exact.  With noise:
+    p' = (1-w)*p + w*eta on legal cells only, eta ~ Dirichlet(0.3 * 1_k) over the k legal cells -- each row sums to 1,
+    every marginal is Beta(alpha, (k-1)*alpha) (KS test against scipy and against numpy's own Dirichlet sampler, the
+    call the reference makes), streams depend on (seed, global game id, ply) and on nothing else."""
+    from scipy import stats
+    size, win, n = 9, 5, 8192
+    A = size * size
+    alpha, w = 0.3, 0.25
+    rs = np.random.RandomState(11)
+    cells = np.zeros((size, size), dtype=np.int8)
+    occ = rs.choice(A, 20, replace=False)
+    cells.reshape(-1)[occ[:10]] = 1
+    cells.reshape(-1)[occ[10:]] = 2
+    legal = cells.reshape(-1) == 0
+    k = int(legal.sum())
+    batch = _batch(az, np.broadcast_to(cells, (n, size, size)).copy(), None, None, win)
+    gid = torch.arange(n, dtype=torch.int64).cuda()
+    ply = torch.full((n,), 20, dtype=torch.int32).cuda()
+    eng = az.Engine(board=size, win_length=win, games=n, sims=1, seed=7, dirichlet_alpha=alpha, dirichlet_weight=w)
+
+    def priors(policy, noise, game_id=gid, ply_=ply, b=batch):
+        eng.search_begin(b.x, b.o, b.to_move, b.last, ply=ply_, game_id=game_id)
+        eng.root_expand(policy, add_noise=noise)
+        return eng.root_priors().cpu().numpy()
+
+    logits = rs.standard_normal((n, A)).astype(np.float32)
+    pol = np.exp(logits) / np.exp(logits).sum(1, keepdims=True)
+    pol = pol.astype(np.float32)
+    plain = priors(torch.from_numpy(pol).cuda(), False)
+    assert np.array_equal(plain[:, legal], pol[:, legal]) and not plain[:, ~legal].any()
+
+    # zero policy => p' = w * eta exactly (to float32 rounding): the noise itself
+    eta = priors(torch.zeros((n, A)).cuda(), True).astype(np.float64) / w
+    assert not eta[:, ~legal].any() and (eta[:, legal] > 0).all()
+    assert np.abs(eta.sum(1) - 1.0).max() <= 1e-6
+    assert np.abs(eta[:, legal].mean(0) - 1.0 / k).max() <= 5 * np.sqrt((1 / k) * (1 - 1 / k) / (k * alpha + 1) / n)
+    ref = np.random.default_rng(0).dirichlet([alpha] * k, n)       # the reference's sampler (mcts.py:114)
+    for j, cell in enumerate(np.flatnonzero(legal)[[0, 7, 30, k - 1]]):
+        assert stats.kstest(eta[:, cell], stats.beta(alpha, (k - 1) * alpha).cdf).pvalue > 1e-3, cell
+        assert stats.ks_2samp(eta[:, cell], ref[:, j]).pvalue > 1e-3, cell
+    # pairs of cells are negatively correlated as in a Dirichlet: corr = -1/(k-1)
+    c0, c1 = np.flatnonzero(legal)[[3, 40]]
+    assert abs(np.corrcoef(eta[:, c0], eta[:, c1])[0, 1] + 1.0 / (k - 1)) < 0.05
+
+    # the mix with a real policy: float32 product, float64 sum, float32 store (mcts.py:116)
+    mixed = priors(torch.from_numpy(pol).cuda(), True)
+    expect = (np.float32(1 - w) * pol).astype(np.float64) + w * eta
+    assert np.abs(mixed[:, legal] - expect[:, legal]).max() <= 1e-7 and not mixed[:, ~legal].any()
+
+    # streams: keyed by (seed, global game id, ply) -- independent of the row a game sits in, fresh per ply and per game
+    perm = torch.from_numpy(rs.permutation(n)).cuda()
+    again = priors(torch.zeros((n, A)).cuda(), True, game_id=gid[perm]).astype(np.float64) / w
+    assert np.array_equal(again, eta[perm.cpu().numpy()])
+    other_ply = priors(torch.zeros((n, A)).cuda(), True, ply_=ply + 1).astype(np.float64) / w
+    assert not np.isclose(other_ply[:, legal], eta[:, legal]).all(axis=1).any()
+    assert len({row.tobytes() for row in eta[:, legal]}) == n
+    eng.close()
+
+
 def test_arena_runs_and_tallies(az):
     size, win = 5, 4
     eng = az.Engine(board=size, win_length=win, games=16, sims=30, seed=5)
