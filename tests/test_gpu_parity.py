@@ -591,6 +591,38 @@ def test_selfplay_noise_and_sampling_are_distributionally_sane(az):
     eng.close()
 
 
+def test_selfplay_moves_are_sampled_from_pi(az):
+    """mcts.py:177: the move is ALWAYS drawn from pi (np.random.choice(k, p=probs)), never the arg-max.  On 5x5 / WIN 4 no
+    game can end before ply 7, so the moves made at plies 0..5 are all observable (the next recorded position shows the new
+    stone) and unbiased: per cell, the count of moves played there minus the summed pi mass must be within 5 sigma."""
+    size, win, sims, ngames = 5, 4, 30, 768
+    A = size * size
+    eng = az.Engine(board=size, win_length=win, games=256, sims=sims, augment=az.AUGMENT_NONE, seed=21)
+    eng.load_state_dict(onet.synthetic_stem_params(size, seed=4, scale=2.0))
+    planes, pi, z = (t.cpu().numpy() for t in eng.selfplay_all(ngames))
+    stones = planes[:, 0].sum((1, 2)) + planes[:, 1].sum((1, 2))          # = ply of the position
+    played = np.zeros(A)
+    mass = np.zeros(A)
+    var = np.zeros(A)
+    argmax_hits, argmax_mass, samples = 0, 0.0, 0
+    for i in np.flatnonzero(stones <= 5):
+        assert stones[i + 1] == stones[i] + 1                             # same game, next ply
+        a = int(np.flatnonzero((planes[i + 1][2] > 0).reshape(-1))[0])    # last-move plane of the next position
+        p = pi[i].reshape(-1).astype(np.float64)
+        assert p[a] > 0
+        played[a] += 1
+        mass += p
+        var += p * (1 - p)
+        argmax_hits += int(a == int(p.argmax()))
+        argmax_mass += p.max()
+        samples += 1
+    assert samples == 6 * ngames
+    assert (np.abs(played - mass) <= 5 * np.sqrt(var) + 1e-9).all()
+    assert abs(argmax_hits - argmax_mass) <= 5 * np.sqrt(samples * 0.25)
+    assert argmax_hits < 0.9 * samples                                    # sampling, not arg-max
+    eng.close()
+
+
 def test_root_noise_is_dirichlet_and_mixed_like_the_reference(az):
     """mcts.py:109-120 in isolation, through azp_root_expand / azp_root_priors.  Without noise the root priors are the
     policy on legal cells (not renormalised, mcts.py:50-64) and 0 elsewhere, bit-exact.  With noise:
