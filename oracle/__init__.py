@@ -5,9 +5,9 @@ algorithms (numpy for the board / integer work, torch-CPU functional ops for
 the network arithmetic, which in the reference also lives in PyTorch).  It is
 the checker the CUDA engine is compared against.  Only ``tests/``,
 ``__graft_entry__.smoke()`` and the ``cpu_baseline`` / ``--impl reference``
-legs of ``bench.py`` may import it (plus the bring-up diagnostics under
-``tools/``, which borrow its seeded synthetic weights / batches and time it as
-the CPU baseline of the training step); the product package
+legs of ``bench.py`` may import it (plus three bring-up diagnostics under
+``tools/`` -- ``debug_umma.py``, ``train_diag.py``, ``train_bench.py`` -- which use it
+the same way: as the checker, or timed as the CPU baseline of the training step); the product package
 (``alphazero-piskvorky_b200/``) never does and has no CPU fallback.
 
 Parity pin: every module here is checked against outputs of the UNMODIFIED

@@ -4,10 +4,9 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 os.environ["AZP_CLK"] = sys.argv[1] if len(sys.argv) > 1 else "1"
 import numpy as np, torch
 import alphazero_piskvorky_b200 as az
-from oracle import net as onet
 n = 2048
 eng = az.Engine(board=15, win_length=5, games=n, sims=2, net_dtype=az.DTYPE_BF16)
-eng.load_state_dict(onet.synthetic_stem_params(15, seed=1))
+torch.manual_seed(1); eng.load_state_dict(az.GomokuNet(15).state_dict())
 x = torch.zeros((n, 4, 15, 15), device="cuda"); x[:, 0, 7, 7] = 1
 if os.environ.get("AZP_PROBE_RANDOM"):          # mid-game-like random positions instead of 2048 copies of one board
     r = torch.rand((n, 15, 15), device="cuda", generator=torch.Generator(device="cuda").manual_seed(0))

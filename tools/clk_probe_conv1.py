@@ -4,10 +4,9 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 os.environ["AZP_CLK"] = "3"
 import numpy as np, torch
 import alphazero_piskvorky_b200 as az
-from oracle import net as onet
 n = 2048
 eng = az.Engine(board=15, win_length=5, games=n, sims=6, net_dtype=az.DTYPE_BF16)
-eng.load_state_dict(onet.synthetic_stem_params(15, seed=1))
+torch.manual_seed(1); eng.load_state_dict(az.GomokuNet(15).state_dict())
 cells = np.zeros((n, 15, 15), dtype=np.int8)
 cells[:, 7, 7] = 1
 batch = az.GomokuBatch.from_cells(cells, to_move=[2] * n, last=[7 * 15 + 7] * n, win_length=5)

@@ -3,10 +3,9 @@ import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
 import alphazero_piskvorky_b200 as az
-from oracle import net as onet
 n = 2048
 eng = az.Engine(board=15, win_length=5, games=n, sims=2, net_dtype=az.DTYPE_BF16)
-eng.load_state_dict(onet.synthetic_stem_params(15, seed=1))
+torch.manual_seed(1); eng.load_state_dict(az.GomokuNet(15).state_dict())
 x = torch.zeros((n, 4, 15, 15), device="cuda"); x[:, 0, 7, 7] = 1
 for _ in range(5): eng.net_forward(x)
 torch.cuda.synchronize()
