@@ -40,6 +40,47 @@ def test_library_exports_every_header_symbol(az):
     assert lib.azp_version() >= 100
 
 
+def _header_text():
+    text = open(os.path.join(ROOT, "include", "azp_b200.h")).read()
+    return re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+
+
+def _header_struct(name):
+    """[(ctype, field)] of a struct in include/azp_b200.h, in declaration order."""
+    body = re.search(r"typedef struct %s \{(.*?)\} %s;" % (name, name), _header_text(), flags=re.S).group(1)
+    fields = []
+    for decl in body.split(";"):
+        decl = decl.strip()
+        if decl:
+            ctype, names = decl.split(None, 1)
+            fields += [(ctype, n.strip()) for n in names.split(",")]
+    return fields
+
+
+def test_ctypes_structs_match_the_header(az):
+    """ABI drift guard: field order and types of azp_config / azp_counters in the header == the ctypes structures the
+    facade passes == the stub INTEGRATION.md tells a maintainer to write."""
+    ctype_of = {"int32_t": C.c_int32, "uint64_t": C.c_uint64, "double": C.c_double}
+    for cname, struct in (("azp_config", az._lib.Config), ("azp_counters", az._lib.Counters)):
+        want = [(n, ctype_of[t]) for t, n in _header_struct(cname)]
+        assert [(n, t) for n, t in struct._fields_] == want, cname
+    assert C.sizeof(az._lib.Config) == 88 and C.sizeof(az._lib.Counters) == 14 * 8
+    doc = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    stub = re.search(r"class Config\(C\.Structure\):.*?_fields_ = \[(.*?)\]\n", doc, flags=re.S).group(1)
+    stub_fields = re.findall(r'\("([a-z_]+)", C\.(c_[a-z0-9]+)\)', stub)
+    assert [(n, getattr(C, t)) for n, t in stub_fields] == list(az._lib.Config._fields_)
+
+
+def test_ctypes_argument_counts_match_the_header(az):
+    """Every prototype in the header has as many parameters as the ctypes argtypes list that binds it."""
+    protos = re.findall(r"\b(azp_[a-z_0-9]+)\s*\(([^)]*)\)\s*;", _header_text())
+    assert len(protos) == len(az._lib.SIGNATURES)
+    for name, params in protos:
+        params = params.strip()
+        n = 0 if params in ("", "void") else len(params.split(","))
+        assert n == len(az._lib.SIGNATURES[name][1]), name
+
+
 def test_library_is_sm100a_native(az):
     """The shipped cubin targets sm_100a (no PTX-JIT fallback for other archs is relied on)."""
     out = subprocess.run(["cuobjdump", "-lelf", az._lib.LIB_PATH], capture_output=True, text=True).stdout
