@@ -27,6 +27,7 @@ import torch
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
 REF = "/root/reference/alphazero"
+OUT = os.environ.get("AZP_GOLDEN_OUT", HERE)     # tests regenerate into a scratch dir and compare
 sys.path.insert(0, REF)
 sys.path.insert(1, ROOT)
 sys.path.insert(2, os.path.join(ROOT, "tests"))
@@ -117,7 +118,7 @@ def make_rules():
             g = game_from_cells(fuzz[i], win)
             fuzz_result[i] = CODE[g.get_game_result()]
             fuzz_legal_count[i] = len(g.get_legal_actions())
-        np.savez_compressed(os.path.join(HERE, f"rules_{size}x{size}_w{win}.npz"),
+        np.savez_compressed(os.path.join(OUT, f"rules_{size}x{size}_w{win}.npz"),
                             size=size, win=win, moves=moves, lens=lens, boards=boards,
                             to_move=to_move, legal=legal, result=result, planes=planes,
                             term_ply=term_ply, fuzz=fuzz, fuzz_result=fuzz_result,
@@ -154,7 +155,7 @@ def make_net():
     """GomokuNet.forward and policy_value_fn on synthetic weights (all sizes) and
     on the shipped 5x5 checkpoint."""
     sd = torch.load(os.path.join(REF, "models/saved/5x5_4_in_a_row.pt"), weights_only=True)
-    np.savez_compressed(os.path.join(HERE, "ref_ckpt_5x5.npz"),
+    np.savez_compressed(os.path.join(OUT, "ref_ckpt_5x5.npz"),
                         **{k: v.numpy().astype(np.float32) for k, v in sd.items()})
 
     out = {}
@@ -188,7 +189,7 @@ def make_net():
     out["x_ckpt"] = x.numpy().astype(np.uint8)
     out["logits_ckpt"] = logits.numpy()
     out["value_ckpt"] = value.numpy()
-    np.savez_compressed(os.path.join(HERE, "net_stem.npz"), **out)
+    np.savez_compressed(os.path.join(OUT, "net_stem.npz"), **out)
     print("net: wrote", sorted(out))
 
 
@@ -320,7 +321,7 @@ def make_mcts():
     pi, action = ref_mcts.MCTS(synth.reference_evaluator(1), 5, 2.0).run(g, 1.0)
     assert action is None
     out["edge_full_pi"] = np.asarray(pi, dtype=np.float32)
-    np.savez_compressed(os.path.join(HERE, "mcts.npz"), **out)
+    np.savez_compressed(os.path.join(OUT, "mcts.npz"), **out)
     print(f"mcts: {len(cases)} deterministic cases, {len(ncases)} noise cases")
 
 
@@ -373,7 +374,7 @@ def make_mcts_ckpt():
         out[f"rec_policy_{j}"] = np.stack(rec_p).astype(np.float32)
         out[f"rec_value_{j}"] = np.array(rec_v, dtype=np.float64)
     out["count"] = np.array(len(roots))
-    np.savez_compressed(os.path.join(HERE, "mcts_ckpt5.npz"), **out)
+    np.savez_compressed(os.path.join(OUT, "mcts_ckpt5.npz"), **out)
     print(f"mcts_ckpt5: {len(roots)} roots, {term_total} terminal-leaf simulations")
 
 
@@ -424,7 +425,7 @@ def make_selfplay():
     out["ep_count"] = np.array(len(games))
     out["ep_seed"] = np.array(2024)
     out["numpy_version"] = np.array(np.__version__)
-    np.savez_compressed(os.path.join(HERE, "selfplay.npz"), **out)
+    np.savez_compressed(os.path.join(OUT, "selfplay.npz"), **out)
     print("selfplay: episodes of length", [len(g) for g in games])
 
 
@@ -466,7 +467,7 @@ def make_arena():
     out["steps"] = np.array(steps)
     out["seed"] = np.array(31337)
     out["sims"] = np.array(40)
-    np.savez_compressed(os.path.join(HERE, "arena.npz"), **out)
+    np.savez_compressed(os.path.join(OUT, "arena.npz"), **out)
     print("arena:", metrics, "temperature steps:", len(steps))
 
 
@@ -478,7 +479,7 @@ def make_replay():
     small = ref_replay.ReplayBuffer(capacity=10)
     small.extend([1, 2, 3])
     out["undersized_sample"] = np.array(list(small.sample_batch(5)))
-    np.savez_compressed(os.path.join(HERE, "replay.npz"), **out)
+    np.savez_compressed(os.path.join(OUT, "replay.npz"), **out)
 
 
 TRAIN_CASES = ((5, 24, 3, 1e-3), (9, 16, 2, 5e-5))     # board, batch, steps, lr
@@ -518,7 +519,7 @@ def make_train():
         out[f"z_{size}"] = z
         out[f"losses_{size}"] = np.array(losses, dtype=np.float64)
         out[f"lr_{size}"] = np.array(lr)
-    np.savez_compressed(os.path.join(HERE, "train.npz"), **out)
+    np.savez_compressed(os.path.join(OUT, "train.npz"), **out)
     print("train: losses", {s: out[f"losses_{s}"].tolist() for s, *_ in TRAIN_CASES})
 
 

@@ -1,6 +1,10 @@
 """The oracle pinned against outputs of the unmodified reference
 (tests/golden/*.npz, produced by tests/golden/make_golden.py)."""
 
+import os
+import subprocess
+import sys
+
 import numpy as np
 import pytest
 
@@ -317,3 +321,31 @@ def test_adamw_update_matches_torch():
         opt.step()
         otrain.adamw_update(p, gnp, m, v, step, lr)
         assert np.abs(p - tp.detach().numpy()).max() <= 2e-7
+
+
+# ---- the fixtures themselves: reproducible from the unmodified reference ----------------------------
+REFERENCE = "/root/reference/alphazero"
+
+
+@pytest.mark.skipif(not os.path.isdir(REFERENCE), reason="the reference tree only exists in the build container")
+@pytest.mark.parametrize("parts", ["rules net replay arena mcts_ckpt selfplay train", "mcts"], ids=["all-but-mcts", "mcts"])
+def test_golden_fixtures_regenerate_bit_identically_from_the_reference(tmp_path, parts):
+    """Provenance of tests/golden/*.npz: run tests/golden/make_golden.py (which imports and executes the UNMODIFIED
+    reference) into a scratch directory and compare every array with the committed fixture -- bit for bit, floats
+    included.  So the pins the oracle and the CUDA path are tested against ARE the reference's outputs in this
+    container (torch / numpy versions as SURVEY.md section 8c records), not hand-edited numbers."""
+    if parts == "mcts" and not os.environ.get("AZP_GOLDEN_FULL"):
+        pytest.skip("~2.5 min of the reference's own MCTS (48 searches up to 19x19): set AZP_GOLDEN_FULL=1")
+    env = dict(os.environ, AZP_GOLDEN_OUT=str(tmp_path), OMP_NUM_THREADS="1")
+    script = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "make_golden.py")
+    r = subprocess.run([sys.executable, script] + parts.split(), env=env, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stderr[-2000:]
+    made = sorted(f for f in os.listdir(tmp_path) if f.endswith(".npz"))
+    assert made
+    for f in made:
+        new = np.load(os.path.join(tmp_path, f), allow_pickle=False)
+        old = np.load(os.path.join(os.path.dirname(script), f), allow_pickle=False)
+        assert sorted(new.files) == sorted(old.files), f
+        for k in old.files:
+            assert new[k].dtype == old[k].dtype and new[k].shape == old[k].shape, (f, k)
+            assert np.array_equal(new[k], old[k]), (f, k)
