@@ -71,7 +71,7 @@ def test_rules_fuzz_boards_bit_exact(az, golden, size, win):
     assert np.array_equal(batch.cells().cpu().numpy(), g["fuzz"])          # pack/unpack round trip
 
 
-@pytest.mark.parametrize("size,win", SIZES)
+@pytest.mark.parametrize("size,win", SIZES + ((3, 3), (7, 4), (11, 5), (13, 6)))
 def test_rules_random_boards_vs_oracle_large(az, size, win):
     """Size-independent property at scale: 20k random boards, terminal status == vectorised oracle."""
     rs = np.random.RandomState(size)
@@ -282,6 +282,28 @@ def test_net_bf16_large_batch_and_scaled_weights(az):
     eng.close()
 
 
+@pytest.mark.parametrize("size", [3, 7, 11, 13, 17])
+def test_net_other_board_sizes_vs_oracle(az, size):
+    """Board sizes that no fixture and no BASELINE config uses (other padded widths, tile counts and FC shapes):
+    fp32 path <= 1e-5, bf16 tcgen05 path <= 2e-2 against the oracle forward (net.py:55-72)."""
+    n = 45
+    params = onet.synthetic_stem_params(size, seed=60 + size)
+    rs = np.random.RandomState(size)
+    occ = rs.random_sample((n, size, size))
+    x = np.zeros((n, 4, size, size), dtype=np.float32)
+    x[:, 0], x[:, 1] = occ < 0.25, (occ >= 0.25) & (occ < 0.5)
+    x[np.arange(1, n), 2, rs.randint(size, size=n - 1), rs.randint(size, size=n - 1)] = 1      # row 0: no last move
+    ol, ov = onet.stem_forward(params, x)
+    for dtype, tol in ((az.DTYPE_F32, 1e-5), (az.DTYPE_BF16, 2e-2)):
+        eng = az.Engine(board=size, win_length=3, games=64, sims=2, net_dtype=dtype)
+        eng.load_state_dict(params)
+        logits, policy, value = eng.net_forward(torch.from_numpy(x).cuda())
+        assert float((logits.cpu() - ol).abs().max()) <= tol, dtype
+        assert float((value.cpu() - ov.reshape(-1)).abs().max()) <= tol, dtype
+        assert float((policy.cpu() - torch.softmax(ol, 1)).abs().max()) <= tol, dtype
+        eng.close()
+
+
 def test_conv3_cta_pair_kernel_matches_single_cta(az, monkeypatch):
     """AZP_CONV3_PAIR=1: conv3 + heads as cta_group::2 UMMAs on CTA pairs (two SMs share one M256 instruction, each
     holding half of the weights).  Same products in the same K order => the logits must agree with the default
@@ -306,7 +328,10 @@ def test_conv3_cta_pair_kernel_matches_single_cta(az, monkeypatch):
 
 @pytest.mark.parametrize("size,win,sims,n,dtype", [(5, 4, 120, 24, "f32"), (9, 5, 200, 16, "f32"),
                                                    (15, 5, 160, 8, "f32"), (9, 5, 150, 16, "bf16"),
-                                                   (15, 5, 200, 40, "bf16")])
+                                                   (15, 5, 200, 40, "bf16"),
+                                                   # board sizes no fixture and no BASELINE config uses
+                                                   (7, 4, 120, 8, "f32"), (11, 5, 120, 8, "bf16"),
+                                                   (13, 5, 120, 8, "bf16")])
 def test_fused_search_matches_oracle_with_engine_net(az, size, win, sims, n, dtype):
     """Whole search on the device (compacted leaf batch + the engine's net kernels, fp32 SIMT or bf16
     tcgen05) vs the oracle search fed with the SAME network numbers: visit counts must be identical."""
