@@ -5,7 +5,7 @@ The directory name is fixed by the build contract and is not a valid Python iden
 import it as ``alphazero_piskvorky_b200`` (a one-file alias package at the repo root)."""
 
 from . import _lib
-from ._lib import (AUGMENT_D4, AUGMENT_NONE, AUGMENT_REFERENCE, DTYPE_BF16, DTYPE_F32, NET_STEM, NET_TOWER,
+from ._lib import (AUGMENT_D4, AUGMENT_NONE, AUGMENT_REFERENCE, DTYPE_BF16, DTYPE_F32, MORE, NET_STEM, NET_TOWER,
                    EngineError)
 from .constants import DRAW, O, X
 from .controller import NeuralNetworkController, make_policy_value_fn

@@ -17,6 +17,7 @@ NET_STEM, NET_TOWER = 0, 1
 DTYPE_F32, DTYPE_BF16 = 0, 1
 AUGMENT_REFERENCE, AUGMENT_D4, AUGMENT_NONE = 0, 1, 2
 AUGMENT_MULT = {AUGMENT_REFERENCE: 4, AUGMENT_D4: 8, AUGMENT_NONE: 1}
+PROF_KINDS = ("dominant", "advance", "conv1", "conv2", "fc", "root_expand", "end_move", "finish", "augment")
 
 
 class Config(C.Structure):
@@ -54,6 +55,7 @@ SIGNATURES = {
     "azp_encode": (C.c_int, [C.c_int, C.c_int, P, P, P, P, P, P]),
     "azp_extract_policy": (C.c_int, [C.c_int, C.c_int, P, P, P, P, P]),
     "azp_augment_write": (C.c_int, [C.c_int, C.c_int, C.c_int, P, P, P, P, P, P, P]),
+    "azp_augment_write_ring": (C.c_int, [C.c_int, C.c_int, C.c_int, P, P, P, P, P, P, P, P, C.c_int64, P]),
     "azp_load_weights": (C.c_int, [P, C.c_int, P, C.c_size_t]),
     "azp_load_weights_device": (C.c_int, [P, C.c_int, P, C.c_size_t, P]),
     "azp_weight_count": (C.c_size_t, [P]),
@@ -64,17 +66,23 @@ SIGNATURES = {
     "azp_select": (C.c_int, [P, P]),
     "azp_leaf_states": (C.c_int, [P, P, P, P, P, P, P]),
     "azp_expand_backup": (C.c_int, [P, P, P, P]),
+    "azp_expand_backup_f64": (C.c_int, [P, P, P, P]),
     "azp_root_visits": (C.c_int, [P, P, P]),
     "azp_root_priors": (C.c_int, [P, P, P]),
     "azp_search": (C.c_int, [P, C.c_int, C.c_int, P, P, P, P, P, P, C.c_int, P, P]),
     "azp_set_temperature_table": (C.c_int, [P, P, C.c_int]),
+    "azp_set_augment_mode": (C.c_int, [P, C.c_int]),
     "azp_selfplay_run": (C.c_int, [P, C.c_int64, C.c_int64, C.c_int, C.c_int, P, P, P, C.c_int64,
                                    C.POINTER(C.c_int64), P]),
     "azp_arena_run": (C.c_int, [P, C.c_int64, C.c_int64, C.POINTER(C.c_int64), P]),
+    "azp_arena_run_steps": (C.c_int, [P, C.c_int64, C.c_int64, C.c_int, C.c_int, C.POINTER(C.c_int64), P]),
+    "azp_episode_snapshot": (C.c_int, [P, P, P, P, P, P, P]),
     "azp_get_counters": (C.c_int, [P, C.POINTER(Counters)]),
     "azp_reset_counters": (C.c_int, [P]),
     "azp_set_profiling": (C.c_int, [P, C.c_int]),
     "azp_get_profile": (C.c_int, [P, C.POINTER(C.c_double), C.POINTER(C.c_uint64), C.POINTER(C.c_double)]),
+    "azp_get_profile_kernel": (C.c_int, [P, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_uint64),
+                                         C.POINTER(C.c_double)]),
     "azp_trainer_create": (C.c_int, [C.c_int, C.c_int, C.c_int, C.POINTER(P)]),
     "azp_trainer_destroy": (None, [P]),
     "azp_trainer_last_error": (C.c_char_p, [P]),
@@ -121,9 +129,10 @@ def check(status: int, engine=None):
     raise EngineError(status, text)
 
 
-def stream_ptr():
+def stream_ptr(device=None):
+    """torch's current stream ON ``device`` (default: the current device) as a cudaStream_t."""
     import torch
-    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
 
 
 def ptr(t):

@@ -185,24 +185,41 @@ def net_kind_of(net):
     return NET_TOWER if isinstance(net, GomokuTowerNet) else NET_STEM
 
 
+def weights_fingerprint(controller):
+    """Cheap identity of the weights ``controller.net`` holds RIGHT NOW.  The reference evaluates ``controller.net``
+    live on every call (controller.py:39-53), so an engine that caches uploaded weights must notice every way they can
+    change: the library's raw-pointer AdamW kernels and ``load`` (``controller.version``), ``net.load_state_dict`` /
+    a torch optimizer / any in-place op (tensor version counters), re-pointed ``.data`` (data pointers) and a
+    reassigned ``controller.net`` (object identity)."""
+    net = controller.net
+    tensors = list(net.parameters()) + list(net.buffers())
+    return (id(net), getattr(controller, "version", 0), sum(t._version for t in tensors),
+            sum(t.data_ptr() for t in tensors))
+
+
 def make_policy_value_fn(controller, dtype=DTYPE_F32):
     """``policy_value_fn(state) -> (policy (B,B) float32 summing to 1 over ALL cells, value float)``
     -- batch of one through the engine's CUDA net (controller.py:39-53)."""
-    net = controller.net
     cache = {}
 
     def policy_value_fn(state):
+        net = controller.net                                   # read at call time, as the reference does
         b = state.board_size
-        eng = cache.get(b)
+        key = (b, type(net), getattr(net, "blocks", 0), getattr(net, "channels", 0))
+        eng = cache.get(key)
         if eng is None:
+            for old in cache.values():                         # another architecture / size: one engine at a time
+                old.close()
+            cache.clear()
             kw = {}
             if isinstance(net, GomokuTowerNet):
                 kw = dict(net_kind=NET_TOWER, tower_blocks=net.blocks, tower_channels=net.channels)
-            eng = cache[b] = _e.Engine(board=b, win_length=state.win_length, games=1, sims=1, net_dtype=dtype, **kw)
+            eng = cache[key] = _e.Engine(board=b, win_length=state.win_length, games=1, sims=1, net_dtype=dtype, **kw)
             eng.weights_version = None
-        if eng.weights_version != getattr(controller, "version", 0):      # the reference reads controller.net live
+        fp = weights_fingerprint(controller)
+        if eng.weights_version != fp:
             eng.load_state_dict(net.state_dict())
-            eng.weights_version = getattr(controller, "version", 0)
+            eng.weights_version = fp
         planes = state.encode().unsqueeze(0)
         _, policy, value = eng.net_forward(planes)
         return policy[0].cpu().numpy().reshape(b, b), float(value[0].item())

@@ -157,7 +157,8 @@ extern "C" int azp_create(const azp_config* cfg, azp_engine** out) {
     return AZP_ERR_CUDA;
   }
   if (cfg->device < 0 || cfg->device >= ndev) return bad("device ordinal out of range");
-  if (cudaSetDevice(cfg->device) != cudaSuccess) { azp_set_global_error("cudaSetDevice failed"); return AZP_ERR_CUDA; }
+  AzpDeviceGuard dev_guard(cfg->device);
+  { int cur = -1; if (cudaGetDevice(&cur) != cudaSuccess || cur != cfg->device) { azp_set_global_error("cudaSetDevice failed"); return AZP_ERR_CUDA; } }
   azp_engine* e = new azp_engine();
   e->cfg = *cfg;
   e->A = cfg->board * cfg->board;
@@ -176,12 +177,12 @@ extern "C" int azp_create(const azp_config* cfg, azp_engine** out) {
 
 extern "C" void azp_destroy(azp_engine* e) {
   if (!e) return;
+  AzpDeviceGuard dev_guard(e->cfg.device);
   cudaSetDevice(e->cfg.device);
   cudaDeviceSynchronize();
   for (cudaEvent_t ev : e->prof_events) cudaEventDestroy(ev);
   if (e->reload_ev) cudaEventDestroy(e->reload_ev);
-  for (cudaGraphExec_t ge : e->graph_exec) if (ge) cudaGraphExecDestroy(ge);
-  for (cudaEvent_t ev : e->gprof_ev) if (ev) cudaEventDestroy(ev);
+  if (e->graph_exec) cudaGraphExecDestroy(e->graph_exec);
   if (e->cfg.net_dtype == AZP_DTYPE_BF16) azp_umma_destroy(e);
   azp_net_destroy(e);
   for (void* p : e->allocs) cudaFree(p);
@@ -192,21 +193,25 @@ extern "C" void azp_destroy(azp_engine* e) {
 extern "C" size_t azp_weight_count(const azp_engine* e) { return e ? azp_net_weight_count(e) : 0; }
 extern "C" int azp_load_weights(azp_engine* e, int slot, const float* host_blob, size_t n) {
   if (!e || !host_blob) return AZP_ERR_INVALID_ARG;
+  AzpDeviceGuard dev_guard(e->cfg.device);
   return azp_net_load(e, slot, host_blob, n, false, 0);
 }
 extern "C" int azp_load_weights_device(azp_engine* e, int slot, const float* dev_blob, size_t n, void* stream) {
   if (!e || !dev_blob) return AZP_ERR_INVALID_ARG;
+  AzpDeviceGuard dev_guard(e->cfg.device);
   return azp_net_load(e, slot, dev_blob, n, true, (cudaStream_t)stream);
 }
 extern "C" int azp_net_forward(azp_engine* e, int slot, int n, const float* planes, float* logits, float* policy,
                                float* value, void* stream) {
   if (!e || !planes || n < 0 || slot < 0 || slot > 1) return AZP_ERR_INVALID_ARG;
+  AzpDeviceGuard dev_guard(e->cfg.device);
   if (n == 0) return AZP_OK;
   return azp_net_eval_planes(e, slot, n, planes, logits, policy, value, (cudaStream_t)stream);
 }
 
 extern "C" int azp_debug_activations(azp_engine* e, int layer, int n, float* out, void* stream) {
   if (!e || !out || n < 1 || n > e->cfg.games) return AZP_ERR_INVALID_ARG;
+  AzpDeviceGuard dev_guard(e->cfg.device);
   if (e->cfg.net_dtype != AZP_DTYPE_BF16) { e->set_error("debug activations exist on the bf16 path only"); return AZP_ERR_UNSUPPORTED; }
   return azp_umma_debug(e, layer, n, out, (cudaStream_t)stream);
 }
@@ -247,6 +252,7 @@ static int check_device_error(azp_engine* e, cudaStream_t s) {
 extern "C" int azp_search_begin(azp_engine* e, int n, const uint64_t* x, const uint64_t* o, const uint8_t* to_move,
                                 const int16_t* last, const int32_t* ply, const int64_t* game_id, void* stream) {
   if (!e || n < 1 || n > e->cfg.games || !x || !o || !to_move) return AZP_ERR_INVALID_ARG;
+  AzpDeviceGuard dev_guard(e->cfg.device);
   if (e->K != 1) { e->set_error("the step-by-step search API needs leaves_per_step == 1"); return AZP_ERR_UNSUPPORTED; }
   cudaStream_t s = (cudaStream_t)stream;
   set_roots_kernel<<<(e->cfg.games + 127) / 128, 128, 0, s>>>(e->tv, n, x, o, to_move, last, ply, game_id);
@@ -257,28 +263,41 @@ extern "C" int azp_search_begin(azp_engine* e, int n, const uint64_t* x, const u
 }
 extern "C" int azp_root_expand(azp_engine* e, const float* policy, int add_noise, void* stream) {
   if (!e || !policy || e->search_n < 1) return AZP_ERR_INVALID_ARG;
+  AzpDeviceGuard dev_guard(e->cfg.device);
   return azp_tree_root_expand(e, e->search_n, policy, /*by_slot=*/0, add_noise, /*logits=*/0, (cudaStream_t)stream);
 }
 extern "C" int azp_select(azp_engine* e, void* stream) {
   if (!e || e->search_n < 1) return AZP_ERR_INVALID_ARG;
+  AzpDeviceGuard dev_guard(e->cfg.device);
   e->parity ^= 1;
   return azp_tree_select(e, e->search_n, /*compact=*/0, e->parity, (cudaStream_t)stream);
 }
 extern "C" int azp_leaf_states(azp_engine* e, uint64_t* x, uint64_t* o, uint8_t* to_move, int16_t* last, uint8_t* kind,
                                void* stream) {
   if (!e || e->search_n < 1 || !x || !o || !to_move || !last || !kind) return AZP_ERR_INVALID_ARG;
+  AzpDeviceGuard dev_guard(e->cfg.device);
   return azp_tree_leaf_states(e, e->search_n, x, o, to_move, last, kind, (cudaStream_t)stream);
 }
 extern "C" int azp_expand_backup(azp_engine* e, const float* policy, const float* value, void* stream) {
   if (!e || e->search_n < 1 || !policy || !value) return AZP_ERR_INVALID_ARG;
-  return azp_tree_expand_backup(e, e->search_n, policy, value, /*by_slot=*/0, /*logits=*/0, (cudaStream_t)stream);
+  AzpDeviceGuard dev_guard(e->cfg.device);
+  return azp_tree_expand_backup(e, e->search_n, policy, value, /*by_slot=*/0, /*logits=*/0, /*value_f64=*/0,
+                                (cudaStream_t)stream);
+}
+extern "C" int azp_expand_backup_f64(azp_engine* e, const float* policy, const double* value, void* stream) {
+  if (!e || e->search_n < 1 || !policy || !value) return AZP_ERR_INVALID_ARG;
+  AzpDeviceGuard dev_guard(e->cfg.device);
+  return azp_tree_expand_backup(e, e->search_n, policy, value, /*by_slot=*/0, /*logits=*/0, /*value_f64=*/1,
+                                (cudaStream_t)stream);
 }
 extern "C" int azp_root_visits(azp_engine* e, int32_t* visits, void* stream) {
   if (!e || e->search_n < 1 || !visits) return AZP_ERR_INVALID_ARG;
+  AzpDeviceGuard dev_guard(e->cfg.device);
   return azp_tree_root_visits(e, e->search_n, visits, (cudaStream_t)stream);
 }
 extern "C" int azp_root_priors(azp_engine* e, float* priors, void* stream) {
   if (!e || e->search_n < 1 || !priors) return AZP_ERR_INVALID_ARG;
+  AzpDeviceGuard dev_guard(e->cfg.device);
   return azp_tree_root_priors(e, e->search_n, priors, (cudaStream_t)stream);
 }
 
@@ -311,50 +330,51 @@ static int search_move(azp_engine* e, int n, int add_noise, int two_nets, cudaSt
   auto iteration = [&](int i, bool last) -> int {
     int r = eval_step(e, two_nets, i & 1, s);
     if (r) return r;
-    if (last) return azp_tree_expand_backup(e, n, e->d_policy, e->d_value, 1, e->policy_logits, s);
+    if (last) return azp_tree_expand_backup(e, n, e->d_policy, e->d_value, 1, e->policy_logits, 0, s);
     return azp_tree_advance(e, n, e->d_policy, e->d_value, 1, e->policy_logits, 1, (i + 1) & 1, s);
   };
   int sim = 0;
   const bool want_graph = e->use_graph && steps >= 5;
+  // Profiling (azp_set_profiling): CUDA event records cannot bracket kernels inside a replayed graph one launch at a time,
+  // so the last AZP_PROF_TAIL iterations of the move run as plain launches, each profiled kernel between its own pair of
+  // events; the iterations before them (and every move step with profiling off) replay the captured graph.
+  const int plain_tail = e->profiling ? (steps < AZP_PROF_TAIL ? steps : AZP_PROF_TAIL) : 1;
   if (want_graph) {
-    const int key = (n * 2 + two_nets) * 2 + (e->profiling ? 1 : 0);
-    const int gi = e->profiling ? 1 : 0;                  // one cached executable per profiling state
-    if (e->graph_exec[gi] && (e->graph_key[gi] != key || e->graph_epoch[gi] != e->weights_epoch)) {
-      cudaGraphExecDestroy(e->graph_exec[gi]);
-      e->graph_exec[gi] = nullptr;
+    const int key = n * 2 + two_nets;
+    if (e->graph_exec && (e->graph_key != key || e->graph_epoch != e->weights_epoch)) {
+      cudaGraphExecDestroy(e->graph_exec);
+      e->graph_exec = nullptr;
     }
-    if (!e->graph_exec[gi]) {
+    if (!e->graph_exec) {
       // capture is best effort: any failure falls back to plain stream launches for this engine
       cudaGraph_t graph = nullptr;
       const uint64_t launches_before = azp_launch_count();
       cudaError_t ce = cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal);
       if (ce == cudaSuccess) {
         e->capturing = true;
-        if (gi == 1) e->gprof_n = 0;
         st = iteration(0, false);
         if (!st) st = iteration(1, false);
         e->capturing = false;
         ce = cudaStreamEndCapture(s, &graph);
-        if (!st && ce == cudaSuccess && graph) ce = cudaGraphInstantiate(&e->graph_exec[gi], graph, 0);
+        if (!st && ce == cudaSuccess && graph) ce = cudaGraphInstantiate(&e->graph_exec, graph, 0);
         if (graph) cudaGraphDestroy(graph);
       }
-      if (st || ce != cudaSuccess || !e->graph_exec[gi]) {
+      if (st || ce != cudaSuccess || !e->graph_exec) {
         if (getenv("AZP_GRAPH_DEBUG")) fprintf(stderr, "[azp] graph capture failed: st=%d cuda=%s\n", st, cudaGetErrorString(ce));
         cudaGetLastError();                     // clear the sticky-free error state
-        e->graph_exec[gi] = nullptr;
+        e->graph_exec = nullptr;
         e->use_graph = false;
       } else {
-        e->graph_key[gi] = key;
-        e->graph_epoch[gi] = e->weights_epoch;
-        e->graph_launches_per_replay[gi] = (int)(azp_launch_count() - launches_before);   // kernels per replay
+        e->graph_key = key;
+        e->graph_epoch = e->weights_epoch;
+        e->graph_launches_per_replay = (int)(azp_launch_count() - launches_before);   // kernels per replay
       }
     }
-    e->graph_last = e->graph_exec[gi] ? gi : -1;
     // the last iteration (no descent after it) always runs as plain launches
     e->note_stream(s);
-    for (; e->graph_exec[gi] && sim + 2 <= steps - 1; sim += 2) {
-      AZP_CUDA(e, cudaGraphLaunch(e->graph_exec[gi], s));
-      azp_count_launch(e->graph_launches_per_replay[gi]);
+    for (; e->graph_exec && sim + 2 <= steps - plain_tail; sim += 2) {
+      AZP_CUDA(e, cudaGraphLaunch(e->graph_exec, s));
+      azp_count_launch(e->graph_launches_per_replay);
     }
   }
   for (; sim < steps; sim++)
@@ -366,6 +386,7 @@ extern "C" int azp_search(azp_engine* e, int slot, int n, const uint64_t* x, con
                           const int16_t* last, const int32_t* ply, const int64_t* game_id, int add_noise,
                           int32_t* visits, void* stream) {
   if (!e || n < 1 || n > e->cfg.games || !x || !o || !to_move || slot != 0) return AZP_ERR_INVALID_ARG;
+  AzpDeviceGuard dev_guard(e->cfg.device);
   cudaStream_t s = (cudaStream_t)stream;
   set_roots_kernel<<<(e->cfg.games + 127) / 128, 128, 0, s>>>(e->tv, n, x, o, to_move, last, ply, game_id);
   azp_count_launch();
@@ -377,8 +398,14 @@ extern "C" int azp_search(azp_engine* e, int slot, int n, const uint64_t* x, con
 }
 
 // ---- drivers ------------------------------------------------------------------------------------------------
+extern "C" int azp_set_augment_mode(azp_engine* e, int mode) {
+  if (!e || mode < 0 || mode > 2) return AZP_ERR_INVALID_ARG;
+  e->cfg.augment_mode = mode;          // read by the self-play driver at every call
+  return AZP_OK;
+}
 extern "C" int azp_set_temperature_table(azp_engine* e, const double* host_table, int n) {
   if (!e || !host_table || n < 1) return AZP_ERR_INVALID_ARG;
+  AzpDeviceGuard dev_guard(e->cfg.device);
   if (n > e->max_plies + 1) n = e->max_plies + 1;
   AZP_CUDA(e, cudaDeviceSynchronize());
   AZP_CUDA(e, cudaMemcpy(e->d_temperature, host_table, (size_t)n * sizeof(double), cudaMemcpyHostToDevice));
@@ -425,6 +452,7 @@ static int episodes_run(azp_engine* e, long long first_game, long long n_games, 
   }
   long long written = 0;
   *host_written = 0;
+  e->search_n = G;                  // azp_root_visits / azp_root_priors read the trees of the last move step
   if (e->sp_total == 0) return AZP_OK;
   for (int step = 0; max_move_steps <= 0 || step < max_move_steps; step++) {
     if (!arena && capacity - written < e->raw_capacity * mult) { *host_written = written; return AZP_MORE; }
@@ -432,9 +460,11 @@ static int episodes_run(azp_engine* e, long long first_game, long long n_games, 
     if ((st = azp_episode_end_move(e, G, arena, s))) return st;
     if ((st = azp_episode_finish(e, G, arena, s))) return st;
     if (!arena) {
+      azp_prof_begin(e, AZP_PROF_AUGMENT, e->d_raw_count, 0, s);        // units = raw positions of this move step
       if ((st = azp_augment_launch(e->cfg.board, mode, (int)e->raw_capacity, e->d_raw_count, e->d_raw_planes,
                                    e->d_raw_pi, e->d_raw_z, out_planes, out_pi, out_z, 0, d_out_written, capacity, s)))
         return st;
+      azp_prof_end(e, AZP_PROF_AUGMENT, s);
       if ((st = azp_episode_drain(e, d_out_written, mult, s))) return st;
     }
     // one small read-back per move step (a move step is `sims` network evaluations long)
@@ -442,7 +472,6 @@ static int episodes_run(azp_engine* e, long long first_game, long long n_games, 
     AZP_CUDA(e, cudaMemcpyAsync(rep.sched, e->d_sched, sizeof(rep.sched), cudaMemcpyDeviceToHost, s));
     AZP_CUDA(e, cudaMemcpyAsync(&rep.error, e->tv.error_flag, sizeof(int32_t), cudaMemcpyDeviceToHost, s));
     AZP_CUDA(e, cudaStreamSynchronize(s));
-    azp_prof_graph_sample(e);
     written = rep.sched[4];
     *host_written = written;
     if (rep.error) {
@@ -459,6 +488,7 @@ extern "C" int azp_selfplay_run(azp_engine* e, int64_t first_game, int64_t n_gam
                                 float* out_planes, float* out_pi, int32_t* out_z, int64_t capacity,
                                 int64_t* host_written, void* stream) {
   if (!e || n_games < 0 || !out_planes || !out_pi || !out_z || !host_written) return AZP_ERR_INVALID_ARG;
+  AzpDeviceGuard dev_guard(e->cfg.device);
   long long w = 0;
   int st = episodes_run(e, first_game, n_games, resume, max_move_steps, 0, out_planes, out_pi, out_z, capacity, &w,
                         (cudaStream_t)stream);
@@ -466,25 +496,49 @@ extern "C" int azp_selfplay_run(azp_engine* e, int64_t first_game, int64_t n_gam
   return st;
 }
 
-extern "C" int azp_arena_run(azp_engine* e, int64_t first_game, int64_t n_games, int64_t* host_wld, void* stream) {
+extern "C" int azp_arena_run_steps(azp_engine* e, int64_t first_game, int64_t n_games, int resume, int max_move_steps,
+                                   int64_t* host_wld, void* stream) {
   if (!e || n_games < 0 || !host_wld) return AZP_ERR_INVALID_ARG;
+  AzpDeviceGuard dev_guard(e->cfg.device);
   cudaStream_t s = (cudaStream_t)stream;
-  unsigned long long before[CNT_COUNT], after[CNT_COUNT];
-  AZP_CUDA(e, cudaMemcpyAsync(before, e->tv.counters, sizeof(before), cudaMemcpyDeviceToHost, s));
-  AZP_CUDA(e, cudaStreamSynchronize(s));
+  unsigned long long after[CNT_COUNT];
+  if (!resume) {       // the tally is the counters' growth since the match started
+    AZP_CUDA(e, cudaMemcpyAsync(e->arena_before, e->tv.counters, sizeof(e->arena_before), cudaMemcpyDeviceToHost, s));
+    AZP_CUDA(e, cudaStreamSynchronize(s));
+  }
   long long w = 0;
-  int st = episodes_run(e, first_game, n_games, 0, 0, 1, nullptr, nullptr, nullptr, 0, &w, s);
-  if (st) return st;
+  int st = episodes_run(e, first_game, n_games, resume, max_move_steps, 1, nullptr, nullptr, nullptr, 0, &w, s);
+  if (st != AZP_OK && st != AZP_MORE) return st;
   AZP_CUDA(e, cudaMemcpyAsync(after, e->tv.counters, sizeof(after), cudaMemcpyDeviceToHost, s));
   AZP_CUDA(e, cudaStreamSynchronize(s));
-  host_wld[0] = (int64_t)(after[CNT_XWINS] - before[CNT_XWINS]);     // candidate plays X
-  host_wld[1] = (int64_t)(after[CNT_OWINS] - before[CNT_OWINS]);
-  host_wld[2] = (int64_t)(after[CNT_DRAWS] - before[CNT_DRAWS]);
+  host_wld[0] = (int64_t)(after[CNT_XWINS] - e->arena_before[CNT_XWINS]);     // candidate plays X
+  host_wld[1] = (int64_t)(after[CNT_OWINS] - e->arena_before[CNT_OWINS]);
+  host_wld[2] = (int64_t)(after[CNT_DRAWS] - e->arena_before[CNT_DRAWS]);
+  return st;
+}
+extern "C" int azp_arena_run(azp_engine* e, int64_t first_game, int64_t n_games, int64_t* host_wld, void* stream) {
+  AzpDeviceGuard dev_guard(e->cfg.device);
+  return azp_arena_run_steps(e, first_game, n_games, 0, 0, host_wld, stream);
+}
+
+// Episode state of every slot as the drivers hold it (plain device-to-device copies; any pointer may be null).
+extern "C" int azp_episode_snapshot(azp_engine* e, int32_t* ply, int64_t* game_id, uint8_t* status, uint16_t* moves,
+                                    float* pi_hist, void* stream) {
+  if (!e) return AZP_ERR_INVALID_ARG;
+  AzpDeviceGuard dev_guard(e->cfg.device);
+  cudaStream_t s = (cudaStream_t)stream;
+  const size_t G = e->cfg.games, MP = e->max_plies, A = e->A;
+  if (ply) AZP_CUDA(e, cudaMemcpyAsync(ply, e->tv.ply, G * sizeof(int32_t), cudaMemcpyDeviceToDevice, s));
+  if (game_id) AZP_CUDA(e, cudaMemcpyAsync(game_id, e->tv.game_id, G * sizeof(int64_t), cudaMemcpyDeviceToDevice, s));
+  if (status) AZP_CUDA(e, cudaMemcpyAsync(status, e->d_status, G, cudaMemcpyDeviceToDevice, s));
+  if (moves) AZP_CUDA(e, cudaMemcpyAsync(moves, e->d_moves, G * MP * sizeof(uint16_t), cudaMemcpyDeviceToDevice, s));
+  if (pi_hist) AZP_CUDA(e, cudaMemcpyAsync(pi_hist, e->d_pi_hist, G * MP * A * sizeof(float), cudaMemcpyDeviceToDevice, s));
   return AZP_OK;
 }
 
 extern "C" int azp_get_counters(azp_engine* e, azp_counters* out) {
   if (!e || !out) return AZP_ERR_INVALID_ARG;
+  AzpDeviceGuard dev_guard(e->cfg.device);
   unsigned long long c[CNT_COUNT];
   AZP_CUDA(e, cudaDeviceSynchronize());
   AZP_CUDA(e, cudaMemcpy(c, e->tv.counters, sizeof(c), cudaMemcpyDeviceToHost));
@@ -496,57 +550,31 @@ extern "C" int azp_get_counters(azp_engine* e, azp_counters* out) {
   return AZP_OK;
 }
 // ---- per-kernel profiling ---------------------------------------------------------------------------------
+// Every launch of a profiled kernel class (AZP_PROF_*) is bracketed by its own pair of CUDA events on the launching
+// stream while profiling is on (never inside a graph capture).  `units` = what the launch processed (leaves for the net
+// kernels, game slots for the tree / episode kernels), read on the device at launch time when it is only known there.
 __global__ void prof_copy_count_kernel(const int32_t* src, int32_t* dst) { *dst = *src; }
 
-void azp_prof_begin(azp_engine* e, const int32_t* count_dev, int count_host, cudaStream_t s) {
-  if (!e->profiling) return;
-  if (e->capturing) {
-    // inside the step graph: event-record NODES; every replay re-records them, the host samples the last
-    // replay of each move step after its sync (azp_prof_graph_sample)
-    if (e->gprof_n >= 2) return;
-    const int i = e->gprof_n;
-    for (int k = 0; k < 2; k++)
-      if (!e->gprof_ev[2 * i + k]) cudaEventCreate(&e->gprof_ev[2 * i + k]);
-    if (count_dev) { prof_copy_count_kernel<<<1, 1, 0, s>>>(count_dev, e->d_prof_counts + AZP_PROF_MAX - 2 + i); azp_count_launch(); }
-    cudaEventRecord(e->gprof_ev[2 * i], s);
-    return;
-  }
+void azp_prof_begin(azp_engine* e, int kind, const int32_t* count_dev, int count_host, cudaStream_t s) {
+  if (!e->profiling || e->capturing) return;
   if (e->prof_used >= AZP_PROF_MAX - 2) azp_prof_collect(e);
-  size_t i = e->prof_used;
+  const size_t i = e->prof_used;
   while (e->prof_events.size() < 2 * (i + 1)) {
     cudaEvent_t ev;
     cudaEventCreate(&ev);
     e->prof_events.push_back(ev);
   }
   if (count_dev) { prof_copy_count_kernel<<<1, 1, 0, s>>>(count_dev, e->d_prof_counts + i); azp_count_launch(); }
+  e->prof_kind.push_back(kind);
   e->prof_count_dev.push_back(count_dev ? e->d_prof_counts + i : nullptr);
   e->prof_count_host.push_back(count_host);
   cudaEventRecord(e->prof_events[2 * i], s);
 }
-void azp_prof_end(azp_engine* e, cudaStream_t s) {
-  if (!e->profiling) return;
-  if (e->capturing) {
-    if (e->gprof_n >= 2) return;
-    cudaEventRecord(e->gprof_ev[2 * e->gprof_n + 1], s);
-    e->gprof_n++;
-    return;
-  }
+void azp_prof_end(azp_engine* e, int kind, cudaStream_t s) {
+  (void)kind;
+  if (!e->profiling || e->capturing) return;
   cudaEventRecord(e->prof_events[2 * e->prof_used + 1], s);
   e->prof_used++;
-}
-int azp_prof_graph_sample(azp_engine* e) {
-  if (!e->profiling || e->graph_last != 1 || !e->graph_exec[1] || e->gprof_n == 0) return AZP_OK;
-  int32_t counts[2] = {0, 0};
-  AZP_CUDA(e, cudaMemcpy(counts, e->d_prof_counts + AZP_PROF_MAX - 2, sizeof(counts), cudaMemcpyDeviceToHost));
-  for (int i = 0; i < e->gprof_n; i++) {
-    float ms = 0.f;
-    if (cudaEventElapsedTime(&ms, e->gprof_ev[2 * i], e->gprof_ev[2 * i + 1]) != cudaSuccess) { cudaGetLastError(); continue; }
-    if (counts[i] <= 0) continue;
-    e->prof_ms += ms;
-    e->prof_launches++;
-    e->prof_flops += e->prof_flops_per_board * counts[i];
-  }
-  return AZP_OK;
 }
 int azp_prof_collect(azp_engine* e) {
   if (e->prof_used == 0) return AZP_OK;
@@ -555,34 +583,45 @@ int azp_prof_collect(azp_engine* e) {
   AZP_CUDA(e, cudaMemcpy(counts.data(), e->d_prof_counts, AZP_PROF_MAX * sizeof(int32_t), cudaMemcpyDeviceToHost));
   for (size_t i = 0; i < e->prof_used; i++) {
     float ms = 0.f;
-    cudaEventElapsedTime(&ms, e->prof_events[2 * i], e->prof_events[2 * i + 1]);
-    int boards = e->prof_count_dev[i] ? counts[i] : e->prof_count_host[i];
-    if (boards <= 0) continue;
-    e->prof_ms += ms;
-    e->prof_launches++;
-    e->prof_flops += e->prof_flops_per_board * boards;
+    if (cudaEventElapsedTime(&ms, e->prof_events[2 * i], e->prof_events[2 * i + 1]) != cudaSuccess) { cudaGetLastError(); continue; }
+    const int units = e->prof_count_dev[i] ? counts[i] : e->prof_count_host[i];
+    if (units <= 0) continue;
+    const int k = e->prof_kind[i];
+    e->prof_ms[k] += ms;
+    e->prof_launches[k]++;
+    e->prof_units[k] += units;
   }
   e->prof_used = 0;
+  e->prof_kind.clear();
   e->prof_count_dev.clear();
   e->prof_count_host.clear();
   return AZP_OK;
 }
 extern "C" int azp_set_profiling(azp_engine* e, int enabled) {
   if (!e) return AZP_ERR_INVALID_ARG;
+  AzpDeviceGuard dev_guard(e->cfg.device);
   int st = azp_prof_collect(e);
   e->profiling = enabled != 0;
   return st;
 }
-extern "C" int azp_get_profile(azp_engine* e, double* ms, uint64_t* launches, double* flops) {
-  if (!e || !ms || !launches || !flops) return AZP_ERR_INVALID_ARG;
+extern "C" int azp_get_profile_kernel(azp_engine* e, int kind, double* ms, uint64_t* launches, double* units) {
+  if (!e || !ms || !launches || !units || kind < 0 || kind >= AZP_PROF_KINDS) return AZP_ERR_INVALID_ARG;
+  AzpDeviceGuard dev_guard(e->cfg.device);
   int st = azp_prof_collect(e);
-  *ms = e->prof_ms; *launches = e->prof_launches; *flops = e->prof_flops;
-  e->prof_ms = 0.0; e->prof_flops = 0.0; e->prof_launches = 0;
+  *ms = e->prof_ms[kind]; *launches = e->prof_launches[kind]; *units = e->prof_units[kind];
+  e->prof_ms[kind] = 0.0; e->prof_units[kind] = 0.0; e->prof_launches[kind] = 0;
+  return st;
+}
+extern "C" int azp_get_profile(azp_engine* e, double* ms, uint64_t* launches, double* flops) {
+  double units = 0.0;
+  int st = azp_get_profile_kernel(e, AZP_PROF_DOMINANT, ms, launches, &units);
+  if (st == AZP_OK && flops) *flops = units * e->prof_flops_per_board;
   return st;
 }
 
 extern "C" int azp_reset_counters(azp_engine* e) {
   if (!e) return AZP_ERR_INVALID_ARG;
+  AzpDeviceGuard dev_guard(e->cfg.device);
   AZP_CUDA(e, cudaDeviceSynchronize());
   AZP_CUDA(e, cudaMemset(e->tv.counters, 0, CNT_COUNT * sizeof(unsigned long long)));
   return AZP_OK;

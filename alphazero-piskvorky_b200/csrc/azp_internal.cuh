@@ -77,6 +77,19 @@ inline cudaError_t azp_launch(void (*kernel)(P...), dim3 grid, dim3 block, size_
     }                                                                                       \
   } while (0)
 
+// ---- device selection -------------------------------------------------------------------------------------------
+// Every entry point that takes an engine / trainer runs on THAT object's device whatever the caller's current device
+// is, and leaves the caller's current device as it found it (a process may hold engines on several GPUs).
+struct AzpDeviceGuard {
+  int prev = -1; bool changed = false;
+  explicit AzpDeviceGuard(int dev) {
+    if (cudaGetDevice(&prev) == cudaSuccess && prev != dev) changed = cudaSetDevice(dev) == cudaSuccess;
+  }
+  ~AzpDeviceGuard() { if (changed) cudaSetDevice(prev); }
+  AzpDeviceGuard(const AzpDeviceGuard&) = delete;
+  AzpDeviceGuard& operator=(const AzpDeviceGuard&) = delete;
+};
+
 // ---- device-side views ------------------------------------------------------------------
 // Structure-of-arrays node table.  Node `nd` of game `g` owns A edge slots, one per CELL
 // (slot index == r*B+c, so the reference's row-major child order is the slot order and
@@ -118,6 +131,9 @@ enum CounterIndex {
   CNT_POSITIONS, CNT_EXAMPLES, CNT_LAUNCHES, CNT_XWINS, CNT_OWINS, CNT_DRAWS, CNT_COUNT
 };
 
+#define AZP_PROF_MAX 4096      // bracketed launches buffered between two collects
+#define AZP_PROF_TAIL 40       // iterations of a move step that run as plain (bracketable) launches while profiling
+
 // ---- network ------------------------------------------------------------------------------
 struct NetWeights;       // defined in azp_net.cu
 struct NetWorkspace;
@@ -154,22 +170,20 @@ struct azp_engine {
   int parity = 0;                  // which pair of leaf counters the current step uses (step-by-step API)
   // CUDA graph of two consecutive simulation steps (see search_move)
   bool use_graph = true;
-  cudaGraphExec_t graph_exec[2] = {nullptr, nullptr};     // [profiling off / on]
-  int graph_key[2] = {-1, -1}, graph_launches_per_replay[2] = {0, 0};
-  int graph_last = -1;                                    // executable used by the last search_move (-1: none)
-  uint64_t weights_epoch = 0, graph_epoch[2] = {0, 0};
+  cudaGraphExec_t graph_exec = nullptr;
+  int graph_key = -1, graph_launches_per_replay = 0;
+  uint64_t weights_epoch = 0, graph_epoch = 0;
   bool capturing = false;          // inside cudaStreamBeginCapture/EndCapture of the step graph
-  cudaEvent_t gprof_ev[4] = {nullptr, nullptr, nullptr, nullptr};   // event nodes around the dominant kernel in the graph
-  int gprof_n = 0;                 // dominant-kernel launches bracketed inside the captured graph (<= 2)
   // per-kernel profiling of the dominant kernel (roofline.achieved in bench.py)
   bool profiling = false;
   std::vector<cudaEvent_t> prof_events;      // pairs (start, stop), recycled after each collect
-  std::vector<const int32_t*> prof_count_dev; std::vector<int> prof_count_host;
+  std::vector<const int32_t*> prof_count_dev; std::vector<int> prof_count_host, prof_kind;
   size_t prof_used = 0;
-  double prof_ms = 0.0, prof_flops = 0.0; uint64_t prof_launches = 0;
-  double prof_flops_per_board = 0.0;
+  double prof_ms[AZP_PROF_KINDS] = {0}, prof_units[AZP_PROF_KINDS] = {0}; uint64_t prof_launches[AZP_PROF_KINDS] = {0};
+  double prof_flops_per_board = 0.0;    // algorithmic FLOPs of the dominant kernel per leaf
   int32_t* d_prof_counts = nullptr;          // [PROF_MAX] leaf counts copied at launch time
   long long sp_first = 0, sp_total = 0;  // current self-play job
+  unsigned long long arena_before[CNT_COUNT] = {0};   // counters when the current arena match started
   // streams this engine has launched network kernels on: a weight reload waits for THESE (not for the whole device,
   // which would also wait for a caller's copy stream draining examples to the host and serialise it with the search)
   std::vector<cudaStream_t> net_streams;
@@ -203,8 +217,9 @@ int azp_tree_begin_move(azp_engine* e, int n, int emit, int compact, int parity,
 // `logits` != 0: `policy` holds raw logits and the softmax over all cells happens in the consumer (bf16 net path)
 int azp_tree_root_expand(azp_engine* e, int n, const float* policy, int by_slot, int add_noise, int logits, cudaStream_t s);
 int azp_tree_select(azp_engine* e, int n, int compact, int parity, cudaStream_t s);
-int azp_tree_expand_backup(azp_engine* e, int n, const float* policy, const float* value, int by_slot, int logits,
-                           cudaStream_t s);
+// `value`: float32 [n] or, with value_f64 != 0, float64 [n] (a host evaluator's Python float, mcts.py:137-141)
+int azp_tree_expand_backup(azp_engine* e, int n, const float* policy, const void* value, int by_slot, int logits,
+                           int value_f64, cudaStream_t s);
 int azp_softmax_rows(int n, int A, const float* logits, float* policy, cudaStream_t s);
 // expand+backup of the step just evaluated, then the descent of the next step (counter pair `parity`), one launch
 int azp_tree_advance(azp_engine* e, int n, const float* policy, const float* value, int by_slot, int logits, int compact,
@@ -218,11 +233,9 @@ int azp_episode_finish(azp_engine* e, int n, int arena, cudaStream_t s);
 int azp_episode_drain(azp_engine* e, long long* out_written_dev, int mult, cudaStream_t s);
 
 // profiling helpers (azp_engine.cu)
-#define AZP_PROF_MAX 4096
-void azp_prof_begin(azp_engine* e, const int32_t* count_dev, int count_host, cudaStream_t s);
-void azp_prof_end(azp_engine* e, cudaStream_t s);
+void azp_prof_begin(azp_engine* e, int kind, const int32_t* count_dev, int count_host, cudaStream_t s);
+void azp_prof_end(azp_engine* e, int kind, cudaStream_t s);
 int azp_prof_collect(azp_engine* e);
-int azp_prof_graph_sample(azp_engine* e);     // after a sync: read the event nodes of the last graph replay
 
 // azp_net.cu
 int azp_net_create(azp_engine* e);

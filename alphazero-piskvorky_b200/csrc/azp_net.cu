@@ -431,7 +431,7 @@ static int run_f32(azp_engine* e, NetWeights* W, const float* in4, const int32_t
     const bool dominant = li == W->dominant_layer;
     if (dominant) {
       e->prof_flops_per_board = 2.0 * 9.0 * L.cin * L.cout * A;
-      azp_prof_begin(e, count_dev, count_host, s);
+      azp_prof_begin(e, AZP_PROF_DOMINANT, count_dev, count_host, s);
     }
     if (L.cin % 16 == 0 && L.cout % 64 == 0) {
       grid.y = L.cout / 64;
@@ -454,7 +454,7 @@ static int run_f32(azp_engine* e, NetWeights* W, const float* in4, const int32_t
       return AZP_ERR_UNSUPPORTED;
     }
     azp_count_launch();
-    if (dominant) azp_prof_end(e, s);
+    if (dominant) azp_prof_end(e, AZP_PROF_DOMINANT, s);
     if (!tower_block || second) { xi = out_idx; cur = out; }
   }
   const int NJ = W->PC + W->VC;

@@ -21,6 +21,18 @@
 #include <cuda.h>
 #include <stdlib.h>
 
+// Bring-up instrumentation is COMPILED OUT of the default build: the per-tile clock stamps (AZP_CLK) and the
+// timing-experiment switches (AZP_DEBUG_CONV, which skip work and therefore produce wrong results by design) exist only
+// in a `make BRINGUP=1` build (-DAZP_BRINGUP); otherwise the pointers / bits below are compile-time constants and every
+// stamp store and debug branch is dead code.  A stray environment variable cannot touch the product kernels.
+#ifdef AZP_BRINGUP
+#define AZP_CLKPTR(p) (p)
+#define AZP_DBGBITS(x) (x)
+#else
+#define AZP_CLKPTR(p) (static_cast<long long*>(nullptr))
+#define AZP_DBGBITS(x) 0
+#endif
+
 namespace {
 
 constexpr int TILE_M = 128;
@@ -391,7 +403,7 @@ __global__ void __launch_bounds__(BITS ? CONV_THREADS_BITS : (HEADS ? CONV_THREA
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const ConvGeom g = args.g;
   auto wall_ns = [] { unsigned long long gt; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt)); return (long long)gt; };
-  if (args.clk && blockIdx.x == 0 && threadIdx.x == 0) args.clk[0 * 16 + 14] = wall_ns();      // kernel entry
+  if (AZP_CLKPTR(args.clk) && blockIdx.x == 0 && threadIdx.x == 0) AZP_CLKPTR(args.clk)[0 * 16 + 14] = wall_ns();      // kernel entry
 
   // ---- prologue: touches nothing the previous kernel of the stream writes, so under programmatic dependent
   //      launch it overlaps that kernel's tail (barriers, TMEM, bias and the resident weights) ----
@@ -415,10 +427,10 @@ __global__ void __launch_bounds__(BITS ? CONV_THREADS_BITS : (HEADS ? CONV_THREA
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (args.clk && blockIdx.x == 0 && threadIdx.x == 0) args.clk[1 * 16 + 14] = wall_ns();      // barriers + TMEM ready
+  if (AZP_CLKPTR(args.clk) && blockIdx.x == 0 && threadIdx.x == 0) AZP_CLKPTR(args.clk)[1 * 16 + 14] = wall_ns();      // barriers + TMEM ready
   pdl_wait();                      // the leaf count and the input activations are the previous kernels' outputs
   pdl_launch_dependents();
-  if (args.clk && blockIdx.x == 0 && threadIdx.x == 0) args.clk[2 * 16 + 14] = wall_ns();      // predecessor finished
+  if (AZP_CLKPTR(args.clk) && blockIdx.x == 0 && threadIdx.x == 0) AZP_CLKPTR(args.clk)[2 * 16 + 14] = wall_ns();      // predecessor finished
   const int count = args.count_dev ? *args.count_dev : args.count_host;
   const int slot0 = args.back ? g.G - count : 0;
   const long long row_begin = (long long)slot0 * g.stride;
@@ -434,9 +446,9 @@ __global__ void __launch_bounds__(BITS ? CONV_THREADS_BITS : (HEADS ? CONV_THREA
         const uint32_t bytes = (uint32_t)(args.stage_rows + 2) * ROWB;
         for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, it++) {
           const int st = it % STAGES;
-          if (args.clk && blockIdx.x == 0) args.clk[it * 16 + 0] = clock64();
+          if (AZP_CLKPTR(args.clk) && blockIdx.x == 0) AZP_CLKPTR(args.clk)[it * 16 + 0] = clock64();
           mbar_wait(&empty[st], ((it / STAGES) & 1) ^ 1);
-          if (args.clk && blockIdx.x == 0) args.clk[it * 16 + 1] = clock64();
+          if (AZP_CLKPTR(args.clk) && blockIdx.x == 0) AZP_CLKPTR(args.clk)[it * 16 + 1] = clock64();
           mbar_expect_tx(&full[st], bytes);
           const long long row = row_begin + (long long)t * TILE_M - g.P - 1;
           tma_load_2d(s_a + (size_t)st * stage_bytes, &map_act, &full[st], 0, (int)row);
@@ -447,7 +459,7 @@ __global__ void __launch_bounds__(BITS ? CONV_THREADS_BITS : (HEADS ? CONV_THREA
           const int st = it % STAGES;
           const uint32_t ph = (it / STAGES) & 1;
           mbar_wait(&empty[st], ph ^ 1);
-          if (args.debug & 4) { mbar_arrive(&full[st]); continue; }
+          if (AZP_DBGBITS(args.debug) & 4) { mbar_arrive(&full[st]); continue; }
           mbar_expect_tx(&full[st], (uint32_t)stage_bytes);
           const long long row = row_begin + (long long)t * TILE_M - g.P + (dxi - 1);
           tma_load_2d(s_a + (size_t)st * stage_bytes, &map_act, &full[st], 0, (int)row);
@@ -495,9 +507,9 @@ __global__ void __launch_bounds__(BITS ? CONV_THREADS_BITS : (HEADS ? CONV_THREA
       }
       asm volatile("bar.sync 2, 256;" ::: "memory");         // codes (and, first time, the conv1 tables) visible
       const int st = it % STAGES;
-      if (args.clk && blockIdx.x == 0 && pt == 0) args.clk[tl * 16 + 0] = clock64();
+      if (AZP_CLKPTR(args.clk) && blockIdx.x == 0 && pt == 0) AZP_CLKPTR(args.clk)[tl * 16 + 0] = clock64();
       mbar_wait(&empty[st], ((it / STAGES) & 1) ^ 1);
-      if (args.clk && blockIdx.x == 0 && pt == 0) args.clk[tl * 16 + 1] = clock64();
+      if (AZP_CLKPTR(args.clk) && blockIdx.x == 0 && pt == 0) AZP_CLKPTR(args.clk)[tl * 16 + 1] = clock64();
       for (int idx = pt; idx < rows_needed; idx += 256) {
         uint32_t packed[16];
 #pragma unroll
@@ -542,7 +554,7 @@ __global__ void __launch_bounds__(BITS ? CONV_THREADS_BITS : (HEADS ? CONV_THREA
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to UMMA
       __syncwarp();
       if (lane == 0) mbar_arrive(&full[st]);
-      if (args.clk && blockIdx.x == 0 && pt == 0) args.clk[tl * 16 + 6] = clock64();
+      if (AZP_CLKPTR(args.clk) && blockIdx.x == 0 && pt == 0) AZP_CLKPTR(args.clk)[tl * 16 + 6] = clock64();
     }
   } else if (warp == 1 || warp == 11) {
     // ===== MMA issuers: two threads, even / odd tiles.  A single thread alternates "wait for barriers" and
@@ -553,23 +565,23 @@ __global__ void __launch_bounds__(BITS ? CONV_THREADS_BITS : (HEADS ? CONV_THREA
       const uint32_t a_base = smem_u32(s_a), w_base = smem_u32(s_w);
       const int my_parity = warp == 1 ? 0 : 1;
       mbar_wait(wbar, 0);
-      if (args.clk && blockIdx.x == 0 && warp == 1) args.clk[3 * 16 + 14] = wall_ns();           // weights resident
+      if (AZP_CLKPTR(args.clk) && blockIdx.x == 0 && warp == 1) AZP_CLKPTR(args.clk)[3 * 16 + 14] = wall_ns();           // weights resident
       tc_fence_after();
       int it = 0, tl = 0;
       for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, tl++) {
         if ((tl & 1) != my_parity) { it += args.single ? 1 : 3; continue; }
         const int acc = tl % NACC;
         const uint32_t acc_ph = (tl / NACC) & 1;
-        if (args.clk && blockIdx.x == 0) args.clk[tl * 16 + 2] = clock64();
+        if (AZP_CLKPTR(args.clk) && blockIdx.x == 0) AZP_CLKPTR(args.clk)[tl * 16 + 2] = clock64();
         mbar_wait(&tempty[acc], acc_ph ^ 1);              // epilogue has drained this accumulator
-        if (args.clk && blockIdx.x == 0) args.clk[tl * 16 + 3] = clock64();
+        if (AZP_CLKPTR(args.clk) && blockIdx.x == 0) AZP_CLKPTR(args.clk)[tl * 16 + 3] = clock64();
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * COUT);
         uint32_t accumulate = 0;
         if (args.single) {
           const int st = it % STAGES;
           mbar_wait(&full[st], (it / STAGES) & 1);
-          if (args.clk && blockIdx.x == 0) args.clk[tl * 16 + 4] = clock64();
+          if (AZP_CLKPTR(args.clk) && blockIdx.x == 0) AZP_CLKPTR(args.clk)[tl * 16 + 4] = clock64();
           tc_fence_after();
           const uint32_t a_stage = a_base + (uint32_t)st * (uint32_t)stage_bytes;
 #pragma unroll
@@ -600,7 +612,7 @@ __global__ void __launch_bounds__(BITS ? CONV_THREADS_BITS : (HEADS ? CONV_THREA
             const uint32_t w_tap = w_base + (uint32_t)((dyi * 3 + dxi) * S::W_TAP_BYTES);
 #pragma unroll
             for (int k = 0; k < KSTEPS; k++) {
-              if (args.debug & 2) break;
+              if (AZP_DBGBITS(args.debug) & 2) break;
               umma_bf16(d_tmem, umma_desc(a_tap + k * 32, ROWB), umma_desc(w_tap + k * 32, ROWB), idesc, accumulate);
               accumulate = 1;
             }
@@ -608,11 +620,11 @@ __global__ void __launch_bounds__(BITS ? CONV_THREADS_BITS : (HEADS ? CONV_THREA
           umma_commit(&empty[st]);                        // stage reusable once these MMAs retire
         }
         umma_commit(&tfull[acc]);                         // accumulator complete
-        if (args.clk && blockIdx.x == 0) {
-          args.clk[tl * 16 + 5] = clock64();
+        if (AZP_CLKPTR(args.clk) && blockIdx.x == 0) {
+          AZP_CLKPTR(args.clk)[tl * 16 + 5] = clock64();
           unsigned long long gt;
           asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
-          args.clk[tl * 16 + 13] = (long long)gt;          // wall-clock ns next to the cycle stamp: SM clock under load
+          AZP_CLKPTR(args.clk)[tl * 16 + 13] = (long long)gt;          // wall-clock ns next to the cycle stamp: SM clock under load
         }
       }
     }
@@ -642,7 +654,7 @@ __global__ void __launch_bounds__(BITS ? CONV_THREADS_BITS : (HEADS ? CONV_THREA
       int tl = 0;
       for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, tl++) {
         issue_head(tl);
-        if (args.clk && blockIdx.x == 0) args.clk[tl * 16 + 6] = clock64();
+        if (AZP_CLKPTR(args.clk) && blockIdx.x == 0) AZP_CLKPTR(args.clk)[tl * 16 + 6] = clock64();
       }
     }
   } else if ((warp >= 2 && warp < 10) || (EGROUPS == 2 && warp >= 12 && warp < 20)) {
@@ -687,10 +699,10 @@ __global__ void __launch_bounds__(BITS ? CONV_THREADS_BITS : (HEADS ? CONV_THREA
       if (EGROUPS == 2 && (tl & 1) != egroup) continue;
       const int acc = tl % NACC;
       const uint32_t acc_ph = (tl / NACC) & 1;
-      const bool stamp = args.clk && blockIdx.x == 0 && (warp == 2 || warp == 12) && lane == 0;
-      if (stamp) args.clk[tl * 16 + 8] = clock64();
+      const bool stamp = AZP_CLKPTR(args.clk) && blockIdx.x == 0 && (warp == 2 || warp == 12) && lane == 0;
+      if (stamp) AZP_CLKPTR(args.clk)[tl * 16 + 8] = clock64();
       mbar_wait(&tfull[acc], acc_ph);
-      if (stamp) args.clk[tl * 16 + 9] = clock64();
+      if (stamp) AZP_CLKPTR(args.clk)[tl * 16 + 9] = clock64();
       tc_fence_after();
       const unsigned R = (unsigned)row_begin + (unsigned)t * TILE_M + q * 32 + lane;   // global padded row (< 2^31)
       const int slot = (int)(R / (unsigned)g.stride);
@@ -698,7 +710,7 @@ __global__ void __launch_bounds__(BITS ? CONV_THREADS_BITS : (HEADS ? CONV_THREA
       const int y = pos / g.P, x = pos % g.P;
       const bool interior = y >= 1 && x >= 1 && x <= g.B && slot < g.G;
       const uint32_t taddr = tmem_base + lane_addr + (uint32_t)(acc * COUT + h * HALF);
-      if (args.debug & 1) {
+      if (AZP_DBGBITS(args.debug) & 1) {
         tc_fence_before();
         __syncwarp();
         if (lane == 0) { if (HEADS) mbar_arrive(&act_full[acc]); else mbar_arrive(&tempty[acc]); }
@@ -723,7 +735,7 @@ __global__ void __launch_bounds__(BITS ? CONV_THREADS_BITS : (HEADS ? CONV_THREA
           __nv_bfloat162 hh = __floats2bfloat162_rn(v0, v1);
           packed[j] = *reinterpret_cast<uint32_t*>(&hh);
         }
-        if (!(args.debug & 16)) {
+        if (!(AZP_DBGBITS(args.debug) & 16)) {
           // direct path (default; AZP_DEBUG_CONV=16 selects the staged TMA-store path, 0.9 % slower end to end): each lane owns 64 contiguous bytes of its output row -> two 256-bit stores (full 32 B sectors),
           // no shared-memory round trip (the staged path costs 32 KB of shared-memory port time per tile)
           uint8_t* gp = reinterpret_cast<uint8_t*>(args.out) + (size_t)R * 128 + h * 64;
@@ -733,7 +745,7 @@ __global__ void __launch_bounds__(BITS ? CONV_THREADS_BITS : (HEADS ? CONV_THREA
                          ::"l"(gp + v * 32), "r"(packed[8 * v]), "r"(packed[8 * v + 1]), "r"(packed[8 * v + 2]),
                            "r"(packed[8 * v + 3]), "r"(packed[8 * v + 4]), "r"(packed[8 * v + 5]), "r"(packed[8 * v + 6]),
                            "r"(packed[8 * v + 7]) : "memory");
-          if (stamp) args.clk[tl * 16 + 11] = clock64();
+          if (stamp) AZP_CLKPTR(args.clk)[tl * 16 + 11] = clock64();
           t_prev = t;
           continue;
         }
@@ -754,7 +766,7 @@ __global__ void __launch_bounds__(BITS ? CONV_THREADS_BITS : (HEADS ? CONV_THREA
           asm volatile("cp.async.bulk.commit_group;" ::: "memory");
           asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
         }
-        if (stamp) args.clk[tl * 16 + 11] = clock64();
+        if (stamp) AZP_CLKPTR(args.clk)[tl * 16 + 11] = clock64();
       } else {
 #pragma unroll
         for (int c0 = 0; c0 < HALF; c0 += 32) {
@@ -771,15 +783,15 @@ __global__ void __launch_bounds__(BITS ? CONV_THREADS_BITS : (HEADS ? CONV_THREA
           // in place: the 16 packed columns of this chunk overwrite fp32 columns this warp already holds in registers
           tmem_st16(tmem_base + lane_addr + (uint32_t)(acc * COUT + h * HALF + c0 / 2), packed);
         }
-        if (stamp) args.clk[tl * 16 + 10] = clock64();
+        if (stamp) AZP_CLKPTR(args.clk)[tl * 16 + 10] = clock64();
         asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&act_full[acc]);
-        if (stamp) args.clk[tl * 16 + 11] = clock64();
+        if (stamp) AZP_CLKPTR(args.clk)[tl * 16 + 11] = clock64();
         // the PREVIOUS tile's head GEMM was queued behind this tile's conv MMAs: it has retired by now
         if (tl > 0 && h == 0) write_heads(t_prev, tl - 1);
-        if (stamp) args.clk[tl * 16 + 12] = clock64();
+        if (stamp) AZP_CLKPTR(args.clk)[tl * 16 + 12] = clock64();
       }
       t_prev = t;
     }
@@ -788,7 +800,7 @@ __global__ void __launch_bounds__(BITS ? CONV_THREADS_BITS : (HEADS ? CONV_THREA
   }
   tc_fence_before();
   __syncthreads();
-  if (args.clk && blockIdx.x == 0 && threadIdx.x == 0) args.clk[4 * 16 + 14] = wall_ns();      // all roles done
+  if (AZP_CLKPTR(args.clk) && blockIdx.x == 0 && threadIdx.x == 0) AZP_CLKPTR(args.clk)[4 * 16 + 14] = wall_ns();      // all roles done
   if (warp == 1) tmem_dealloc(tmem_base, TMEM_COLS);
 }
 
@@ -938,7 +950,7 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv3_pair_kernel(const __gri
   const int n_tiles = (int)((rows_total + TILE_M - 1) / TILE_M);
   const int n_pairs = (n_tiles + 1) / 2;
   const int cid = (int)cluster_id_x(), ncl = (int)cluster_count_x();
-  const bool stampc = args.clk && cid == 0 && leader && tp_limit_ok(n_pairs, ncl);
+  const bool stampc = AZP_CLKPTR(args.clk) && cid == 0 && leader && tp_limit_ok(n_pairs, ncl);
   // this CTA's tile of pair tp is 2*tp + rank (a phantom tile past the end loads zero-filled rows and is discarded)
 
   if (warp == 0) {
@@ -948,9 +960,9 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv3_pair_kernel(const __gri
       int it = 0;
       for (int tp = cid; tp < n_pairs; tp += ncl, it++) {
         const int st = it % STAGES;
-        if (stampc) args.clk[it * 16 + 0] = clock64();
+        if (stampc) AZP_CLKPTR(args.clk)[it * 16 + 0] = clock64();
         mbar_wait(&empty[st], ((it / STAGES) & 1) ^ 1);
-        if (stampc) args.clk[it * 16 + 1] = clock64();
+        if (stampc) AZP_CLKPTR(args.clk)[it * 16 + 1] = clock64();
         if (leader) mbar_expect_tx(&full[st], 2 * bytes);
         const long long row = row_begin + (long long)(2 * tp + (int)rank) * TILE_M - g.P - 1;
         tma_load_2d_pair(s_a + (size_t)st * stage_bytes, &map_act, mapa_u32(&full[st], 0), 0, (int)row);
@@ -968,14 +980,14 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv3_pair_kernel(const __gri
       for (int tp = cid; tp < n_pairs; tp += ncl, tl++) {
         if ((tl & 1) != my_parity) continue;
         const int acc = tl & 1;
-        if (stampc) args.clk[tl * 16 + 2] = clock64();
+        if (stampc) AZP_CLKPTR(args.clk)[tl * 16 + 2] = clock64();
         mbar_wait(&tempty[acc], ((tl >> 1) & 1) ^ 1);          // both CTAs' epilogues have drained this accumulator
-        if (stampc) args.clk[tl * 16 + 3] = clock64();
+        if (stampc) AZP_CLKPTR(args.clk)[tl * 16 + 3] = clock64();
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * COUT);
         const int st = tl % STAGES;
         mbar_wait(&full[st], (tl / STAGES) & 1);               // both CTAs' boxes have landed
-        if (stampc) args.clk[tl * 16 + 4] = clock64();
+        if (stampc) AZP_CLKPTR(args.clk)[tl * 16 + 4] = clock64();
         tc_fence_after();
         const uint32_t a_stage = a_base + (uint32_t)st * (uint32_t)stage_bytes;
         uint32_t accumulate = 0;
@@ -994,7 +1006,7 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv3_pair_kernel(const __gri
         }
         umma_commit_pair(&empty[st]);
         umma_commit_pair(&tfull[acc]);
-        if (stampc) args.clk[tl * 16 + 5] = clock64();
+        if (stampc) AZP_CLKPTR(args.clk)[tl * 16 + 5] = clock64();
       }
     }
   } else if (warp == 10) {
@@ -1016,7 +1028,7 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv3_pair_kernel(const __gri
                             umma_desc(hw_base + (k / 4) * (HEAD_N / 2) * 128 + (k % 4) * 32, 128), idesc_head,
                             k >= HEAD_CHAINS ? 1u : 0u);
         umma_commit_pair(&head_full[b]);
-        if (stampc) args.clk[tl * 16 + 6] = clock64();
+        if (stampc) AZP_CLKPTR(args.clk)[tl * 16 + 6] = clock64();
       }
     }
   } else if (warp >= 2 && warp < 10) {
@@ -1056,9 +1068,9 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv3_pair_kernel(const __gri
       const int t = 2 * tp + (int)rank;
       const int acc = tl & 1;
       const bool stamp = stampc && warp == 2 && lane == 0;
-      if (stamp) args.clk[tl * 16 + 8] = clock64();
+      if (stamp) AZP_CLKPTR(args.clk)[tl * 16 + 8] = clock64();
       mbar_wait(&tfull[acc], (tl >> 1) & 1);
-      if (stamp) args.clk[tl * 16 + 9] = clock64();
+      if (stamp) AZP_CLKPTR(args.clk)[tl * 16 + 9] = clock64();
       tc_fence_after();
       const uint32_t taddr = tmem_base + lane_addr + (uint32_t)(acc * COUT + h * HALF);
       if (tl >= 2) {             // head GEMM of tile tl-2 (same TMEM buffers) has retired
@@ -1079,7 +1091,7 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv3_pair_kernel(const __gri
         }
         tmem_st16(tmem_base + lane_addr + COL_ACT + (uint32_t)((tl & 1) * (COUT / 2) + (h * HALF + c0) / 2), packed);
       }
-      if (stamp) args.clk[tl * 16 + 10] = clock64();
+      if (stamp) AZP_CLKPTR(args.clk)[tl * 16 + 10] = clock64();
       asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
       tc_fence_before();
       __syncwarp();
@@ -1087,9 +1099,9 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv3_pair_kernel(const __gri
         mbar_arrive_cluster(acc ? l_tempty1 : l_tempty0);
         mbar_arrive_cluster((tl & 1) ? l_act1 : l_act0);
       }
-      if (stamp) args.clk[tl * 16 + 11] = clock64();
+      if (stamp) AZP_CLKPTR(args.clk)[tl * 16 + 11] = clock64();
       if (tl > 0 && h == 0) write_heads(t_prev, tl - 1);
-      if (stamp) args.clk[tl * 16 + 12] = clock64();
+      if (stamp) AZP_CLKPTR(args.clk)[tl * 16 + 12] = clock64();
       t_prev = t;
     }
     if (tl > 0 && h == 0) write_heads(t_prev, tl - 1);
@@ -1131,7 +1143,7 @@ struct Conv1Args {
   int staged;                      // 1: swizzled smem staging + TMA store (AZP_CONV1_STORE=tma), 0: 256-bit stores from registers
   long long* clk;                  // bring-up (AZP_CLK=3): per-tile clock64 stamps of CTA 0 ([tile][16]) or null
 };
-#define C1_STAMP(cond, k) do { if (args.clk && blockIdx.x == 0 && tl < 64 && (cond)) args.clk[tl * 16 + (k)] = clock64(); } while (0)
+#define C1_STAMP(cond, k) do { if (AZP_CLKPTR(args.clk) && blockIdx.x == 0 && tl < 64 && (cond)) AZP_CLKPTR(args.clk)[tl * 16 + (k)] = clock64(); } while (0)
 
 constexpr int C1_BB_ITEMS = 32;              // staged leaf inputs of the <= 2 boards a tile touches: 2 x (2*NW words + tm + last)
 constexpr int conv1_smem_bytes(bool planes) {
@@ -1474,7 +1486,7 @@ struct FcArgs {
   const int32_t* count_dev; int count_host; int back; int out_by_index;
   long long* clk;                 // bring-up (AZP_CLK=4): wall-clock ns stamps of CTA (0,0) or null
 };
-#define FC_STAMP(cond, k) do { if (args.clk && blockIdx.x == 0 && blockIdx.y == 0 && (cond)) { unsigned long long gt_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt_)); args.clk[k] = (long long)gt_; } } while (0)
+#define FC_STAMP(cond, k) do { if (AZP_CLKPTR(args.clk) && blockIdx.x == 0 && blockIdx.y == 0 && (cond)) { unsigned long long gt_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt_)); AZP_CLKPTR(args.clk)[k] = (long long)gt_; } } while (0)
 
 constexpr int FC_N = 64;
 constexpr int FC_EPI_WARPS = 8;                        // warp (q, h): TMEM lanes 32q..32q+31 (boards), columns 32h..32h+31
@@ -1703,6 +1715,27 @@ struct UmmaWeights {
 
 constexpr int STAGES2 = 6, STAGES3 = 3;
 
+// bring-up builds only (make BRINGUP=1): which kernel stamps its tiles (AZP_CLK=1 conv3, 2 conv2, 3 conv1, 4 FC) and the
+// AZP_DEBUG_CONV experiment bits; constants in the default build
+inline long long* bringup_clk(const UmmaWorkspace* ws, int which) {
+#ifdef AZP_BRINGUP
+  const char* v = getenv("AZP_CLK");
+  return (v && atoi(v) == which) ? ws->clk : nullptr;
+#else
+  (void)ws; (void)which;
+  return nullptr;
+#endif
+}
+inline int bringup_debug_bits() {
+#ifdef AZP_BRINGUP
+  static int dbg = -1;
+  if (dbg < 0) { const char* v = getenv("AZP_DEBUG_CONV"); dbg = v ? atoi(v) : 0; }
+  return dbg;
+#else
+  return 0;
+#endif
+}
+
 template <int CIN, int COUT, int STAGES, bool HEADS, bool BITS>
 int conv_smem_bytes(int stage_rows) {
   using S = ConvSmem<CIN, COUT, STAGES, HEADS>;
@@ -1769,7 +1802,9 @@ int azp_umma_create(azp_engine* e) {
   AZP_CUDA(e, cudaFuncSetAttribute(conv1_umma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, conv1_smem_bytes(false)));
   AZP_CUDA(e, cudaFuncSetAttribute(conv1_umma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, conv1_smem_bytes(true)));
   { const char* v = getenv("AZP_SINGLE_LOAD"); ws->single = v ? atoi(v) : 1; }
+#ifdef AZP_BRINGUP
   if (getenv("AZP_CLK")) { if ((st = e->alloc(&ws->clk, (size_t)64 * 16))) return st; AZP_CUDA(e, cudaMemset(ws->clk, 0, 64 * 16 * 8)); }
+#endif
   cudaDeviceProp prop;
   AZP_CUDA(e, cudaGetDeviceProperties(&prop, e->cfg.device));
   ws->sms = prop.multiProcessorCount;
@@ -2117,10 +2152,10 @@ static int run_tower(azp_engine* e, NetWeights* W, const int32_t* count_dev, int
     const int out_i = second ? (xi + 2) % 3 : (xi + 1) % 3;
     ta.residual = second ? ws->tact[xi] : nullptr;
     ta.out = ws->tact[out_i];
-    azp_prof_begin(e, count_dev, count_host, s);
+    azp_prof_begin(e, AZP_PROF_DOMINANT, count_dev, count_host, s);
     conv_tower_kernel<<<grid, TW_THREADS, ws->smem_tower, s>>>(ws->map_tact[in_i], U->map_tw[i], ta);
     azp_count_launch();
-    azp_prof_end(e, s);
+    azp_prof_end(e, AZP_PROF_DOMINANT, s);
     if (second) xi = out_i;
   }
   const int NJ = W->PC + W->VC;
@@ -2146,11 +2181,12 @@ static int run_trunk(azp_engine* e, NetWeights* W, const int32_t* count_dev, int
   a2.PC = 0; a2.PKp = 0; a2.FK = 0;
   a2.count_dev = count_dev; a2.count_host = count_host; a2.back = back; a2.stage_rows = TILE_M + 2 * g.P;
   a2.single = from_bits ? 1 : ws->single;
-  { const char* v = getenv("AZP_CLK"); a2.clk = (v && atoi(v) == 2) ? ws->clk : nullptr; }
+  a2.clk = bringup_clk(ws, 2);
   a2.stage_bytes = (a2.single ? (a2.stage_rows + 2 + 7) / 8 * 8 : a2.stage_rows) * 64;
   a2.lx = e->tv.leaf_x; a2.lo = e->tv.leaf_o; a2.ltm = e->tv.leaf_tm; a2.llast = e->tv.leaf_last; a2.NW = e->NW;
   a2.w1 = U->w1_tab; a2.b1 = U->b1;
-  { static int dbg = -1; if (dbg < 0) { const char* v = getenv("AZP_DEBUG_CONV"); dbg = v ? atoi(v) : 0; } a2.debug = dbg; }
+  a2.debug = bringup_debug_bits();
+  azp_prof_begin(e, AZP_PROF_CONV2, count_dev, count_host, s);
   if (from_bits)
     azp_launch(conv_umma_kernel<32, 64, STAGES2, false, true>, grid, CONV_THREADS_BITS, ws->smem2, s, true, ws->map_act1,
                U->map_w2, ws->map_act2_out, a2);
@@ -2158,14 +2194,15 @@ static int run_trunk(azp_engine* e, NetWeights* W, const int32_t* count_dev, int
     azp_launch(conv_umma_kernel<32, 64, STAGES2, false, false>, grid, CONV_THREADS_EPI2, ws->smem2, s, true,
                a2.single ? ws->map_act1_s : ws->map_act1, U->map_w2, ws->map_act2_out, a2);
   azp_count_launch();
+  azp_prof_end(e, AZP_PROF_CONV2, s);
   ConvArgs a3 = a2;
   a3.bias = U->b3; a3.out = nullptr; a3.head_b = U->head_b8; a3.feat = ws->feat;
   a3.NJ = W->PC + W->VC; a3.PC = W->PC; a3.PKp = ws->PKp; a3.FK = ws->FK;
   a3.single = ws->single;
-  { const char* v = getenv("AZP_CLK"); a3.clk = (v && atoi(v) == 1) ? ws->clk : nullptr; }
+  a3.clk = bringup_clk(ws, 1);
   a3.stage_bytes = (a3.single ? (a3.stage_rows + 2 + 7) / 8 * 8 : a3.stage_rows) * 128;
   e->prof_flops_per_board = 2.0 * 9.0 * 64 * 128 * g.A;
-  azp_prof_begin(e, count_dev, count_host, s);
+  azp_prof_begin(e, AZP_PROF_DOMINANT, count_dev, count_host, s);
   if (ws->pair) {
     const int max_pairs = (max_tiles + 1) / 2;
     const int ncl = max_pairs < ws->pair_clusters ? max_pairs : ws->pair_clusters;
@@ -2184,7 +2221,7 @@ static int run_trunk(azp_engine* e, NetWeights* W, const int32_t* count_dev, int
                a3.single ? ws->map_act2_s : ws->map_act2, U->map_w3, U->map_hw, a3);
   }
   azp_count_launch();
-  azp_prof_end(e, s);
+  azp_prof_end(e, AZP_PROF_DOMINANT, s);
   return launch_fc(e, W, count_dev, count_host, back, logits, policy, value, out_by_index, s);
 }
 
@@ -2206,10 +2243,12 @@ static int launch_fc(azp_engine* e, NetWeights* W, const int32_t* count_dev, int
   fa.pbias = W->pfc_b; fa.vbias = W->vfc1_b;
   fa.vfc2_w = W->vfc2_w; fa.vfc2_b = W->vfc2_b; fa.logits = logits_out; fa.value = value;
   fa.count_dev = count_dev; fa.count_host = count_host; fa.back = back; fa.out_by_index = out_by_index;
-  { const char* v = getenv("AZP_CLK"); fa.clk = (v && atoi(v) == 4) ? ws->clk : nullptr; }
+  fa.clk = bringup_clk(ws, 4);
   dim3 fc_grid((zmax + TILE_M - 1) / TILE_M, fa.n_slices + 1);
+  azp_prof_begin(e, AZP_PROF_FC, count_dev, count_host, s);
   azp_launch(fc_umma_kernel, fc_grid, FC_THREADS, ws->fc_smem, s, true, ws->map_feat, U->map_wp, U->map_wv, fa);
   azp_count_launch();
+  azp_prof_end(e, AZP_PROF_FC, s);
   int st = azp_check_launch();
   if (st) return st;
   if (want_softmax && policy) return azp_softmax_rows(count_host, g.A, logits_out, policy, s);
@@ -2229,10 +2268,12 @@ static int launch_conv1_umma(azp_engine* e, UmmaWeights* U, const int32_t* count
   a.lx = e->tv.leaf_x; a.lo = e->tv.leaf_o; a.ltm = e->tv.leaf_tm; a.llast = e->tv.leaf_last; a.NW = e->NW;
   a.planes = planes; a.out = ws->act1;
   { static int staged = -1; if (staged < 0) { const char* v = getenv("AZP_CONV1_STORE"); staged = (v && !strcmp(v, "tma")) ? 1 : 0; } a.staged = staged; }
-  { const char* v = getenv("AZP_CLK"); a.clk = (v && atoi(v) == 3) ? ws->clk : nullptr; }
+  a.clk = bringup_clk(ws, 3);
+  azp_prof_begin(e, AZP_PROF_CONV1, count_dev, count_host, s);
   if (planes) azp_launch(conv1_umma_kernel<true>, grid, C1_THREADS, conv1_smem_bytes(true), s, true, ws->map_act1_out, a);
   else azp_launch(conv1_umma_kernel<false>, grid, C1_THREADS, conv1_smem_bytes(false), s, true, ws->map_act1_out, a);
   azp_count_launch();
+  azp_prof_end(e, AZP_PROF_CONV1, s);
   return azp_check_launch();
 }
 

@@ -140,8 +140,12 @@ __global__ void augment_write_kernel(int B, int mode, int n, const float* __rest
   const int mult = mode == AZP_AUGMENT_D4 ? 8 : (mode == AZP_AUGMENT_REFERENCE ? 4 : 1);
   if (n_dev) n = *n_dev;
   if (out_offset_dev) out_offset += *out_offset_dev;
+  // more examples than the ring holds: only the newest out_capacity survive (deque(maxlen) semantics), the others are
+  // not written at all, so no two blocks of this launch ever target the same slot
+  const long long skip = (long long)n * mult > out_capacity ? (long long)n * mult - out_capacity : 0;
   int pos = blockIdx.x / mult, s = blockIdx.x % mult;
   for (; pos < n; pos += gridDim.x / mult) {
+    if ((long long)pos * mult + s < skip) continue;
     // state symmetry: k quarter turns (+flip for s>=4 in D4); pi symmetry: the SAME element in
     // D4/NONE mode, but ALWAYS one quarter turn in reference mode (self_play.py:104-105 as written)
     int ks = s & 3, fs = (mode == AZP_AUGMENT_D4) ? (s >> 2) : 0;
@@ -241,4 +245,24 @@ extern "C" int azp_augment_write(int board, int mode, int n, const float* planes
   int mult = mode == AZP_AUGMENT_D4 ? 8 : (mode == AZP_AUGMENT_REFERENCE ? 4 : 1);
   return azp_augment_launch(board, mode, n, nullptr, planes, pi, z, out_planes, out_pi, out_z, 0, nullptr,
                             (long long)n * mult + 1, (cudaStream_t)stream);
+}
+
+// ---- replay ring writer (ReplayBuffer.extend on the device, replay_buffer.py:27-29; + _augment_symmetries) --------
+__global__ void ring_advance_kernel(long long* head, const int* n_dev, int n_host, int mult) {
+  *head += (long long)(n_dev ? *n_dev : n_host) * mult;
+}
+extern "C" int azp_augment_write_ring(int board, int mode, int n_max, const int32_t* n_dev, const float* planes,
+                                      const float* pi, const int32_t* z, float* ring_planes, float* ring_pi,
+                                      int32_t* ring_z, int64_t* ring_head_dev, int64_t ring_capacity, void* stream) {
+  if (board < 1 || board > AZP_MAX_BOARD || n_max < 0 || mode < 0 || mode > 2 || !ring_head_dev || ring_capacity < 1)
+    return AZP_ERR_INVALID_ARG;
+  if (n_max == 0) return AZP_OK;
+  const int mult = mode == AZP_AUGMENT_D4 ? 8 : (mode == AZP_AUGMENT_REFERENCE ? 4 : 1);
+  cudaStream_t s = (cudaStream_t)stream;
+  int st = azp_augment_launch(board, mode, n_max, n_dev, planes, pi, z, ring_planes, ring_pi, ring_z, 0,
+                              reinterpret_cast<const long long*>(ring_head_dev), (long long)ring_capacity, s);
+  if (st) return st;
+  ring_advance_kernel<<<1, 1, 0, s>>>(reinterpret_cast<long long*>(ring_head_dev), n_dev, n_max, mult);
+  azp_count_launch();
+  return azp_check_launch();
 }

@@ -471,10 +471,11 @@ extern "C" int azp_trainer_create(int board, int max_batch, int device, azp_trai
     azp_set_global_error("no CUDA device: the trainer has no CPU fallback");
     return AZP_ERR_CUDA;
   }
-  if (device < 0 || device >= ndev || cudaSetDevice(device) != cudaSuccess) {
+  if (device < 0 || device >= ndev) {
     azp_set_global_error("azp_trainer_create: bad device ordinal");
     return AZP_ERR_INVALID_ARG;
   }
+  AzpDeviceGuard dev_guard(device);
   azp_trainer* t = new azp_trainer();
   t->board = board; t->A = board * board; t->max_batch = max_batch; t->device = device;
   const size_t A = t->A, nb = max_batch, M = nb * A;
@@ -518,7 +519,7 @@ extern "C" int azp_trainer_create(int board, int max_batch, int device, azp_trai
 
 extern "C" void azp_trainer_destroy(azp_trainer* t) {
   if (!t) return;
-  cudaSetDevice(t->device);
+  AzpDeviceGuard dev_guard(t->device);
   for (void* p : t->allocs) cudaFree(p);
   delete t;
 }
@@ -533,6 +534,7 @@ extern "C" size_t azp_trainer_weight_count(const azp_trainer* t) { return t ? t-
 extern "C" int azp_train_loss_grad(azp_trainer* t, int n, const float* params, const float* planes, const float* pi,
                                    const float* z, float* grads, float* losses, void* stream) {
   if (!t) return AZP_ERR_INVALID_ARG;
+  AzpDeviceGuard dev_guard(t->device);
   if (n < 1 || n > t->max_batch || !params || !planes || !pi || !z || !losses) {
     t->set_error("azp_train_loss_grad: n must be 1..max_batch and params/planes/pi/z/losses non-null");
     return AZP_ERR_INVALID_ARG;

@@ -269,8 +269,8 @@ __device__ __forceinline__ void select_body(const RulesParams& rp, const TreeVie
 // returns false on a capacity overflow (error flag set)
 template <int NW>
 __device__ __forceinline__ bool expand_backup_body(const RulesParams& rp, const TreeView& tv, int g, int lane,
-                                                   const float* __restrict__ policy, const float* __restrict__ value,
-                                                   int by_slot, int logits) {
+                                                   const float* __restrict__ policy, const void* __restrict__ value,
+                                                   int by_slot, int logits, int value_f64 = 0) {
   if (!tv.active[g]) return true;
   const int A = rp.A, K = tv.K;
   const size_t gbase = (size_t)g * tv.cap * A;
@@ -281,11 +281,11 @@ __device__ __forceinline__ bool expand_backup_body(const RulesParams& rp, const 
     if (kind == 2) continue;
     const int32_t* path = tv.path + (size_t)rec * tv.maxd;
     const int depth = tv.path_len[rec];
-    float v;
+    double v;                                     // the reference backs up a Python float (float64), mcts.py:137-141
     if (kind == 0) {
       const int slot = tv.leaf_slot[rec];
       const size_t row = (size_t)(by_slot ? slot : rec);
-      v = value[row];
+      v = value_f64 ? static_cast<const double*>(value)[row] : (double)static_cast<const float*>(value)[row];
       int nid = tv.node_count[g];
       if (nid >= tv.cap) {
         if (lane == 0) atomicExch(tv.error_flag, AZP_ERR_CAPACITY);
@@ -316,13 +316,13 @@ __device__ __forceinline__ bool expand_backup_body(const RulesParams& rp, const 
       __syncwarp();
       n_exp++;
     } else {
-      v = tv.leaf_tvalue[rec];
+      v = (double)tv.leaf_tvalue[rec];
     }
     // node.backup(-value): the leaf's own statistics (last edge) take -v, signs alternate upwards.
     // Throughput mode: the edge already carries this descent's virtual visit (N+1, W-1): swap it for the value.
     for (int i = lane; i < depth; i += 32) {
       const size_t e = gbase + path[i];
-      const double val = ((depth - 1 - i) & 1) ? (double)v : -(double)v;
+      const double val = ((depth - 1 - i) & 1) ? v : -v;
       if (K == 1) {
         tv.N[e] += 1;
         tv.W[e] = __dadd_rn(tv.W[e], val);
@@ -359,12 +359,12 @@ __global__ void __launch_bounds__(128, 4) select_kernel(RulesParams rp, TreeView
 
 template <int NW>
 __global__ void expand_backup_kernel(RulesParams rp, TreeView tv, int n, const float* __restrict__ policy,
-                                     const float* __restrict__ value, int by_slot, int logits) {
+                                     const void* __restrict__ value, int by_slot, int logits, int value_f64) {
   pdl_wait();
   pdl_launch_dependents();
   int g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (g >= n) return;
-  expand_backup_body<NW>(rp, tv, g, lane, policy, value, by_slot, logits);
+  expand_backup_body<NW>(rp, tv, g, lane, policy, value, by_slot, logits, value_f64);
 }
 
 // expand+backup of simulation step i followed at once by the descent of step i+1: the same warp owns the game in
@@ -411,9 +411,9 @@ __global__ void root_visits_kernel(TreeView tv, int n, int32_t* __restrict__ vis
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (size_t)n * tv.A) return;
   int g = i / tv.A, a = i % tv.A;
-  uint64_t occ = tv.root_x[(size_t)g * tv.NW + (a >> 6)] | tv.root_o[(size_t)g * tv.NW + (a >> 6)];
-  bool legal = !((occ >> (a & 63)) & 1);
-  visits[i] = legal ? tv.N[(size_t)g * tv.cap * tv.A + a] : 0;
+  // occupied cells were given N = 0 by root_expand and are never selected; no occupancy mask here, so the counts of a
+  // search stay readable after the episode driver has played its move into the root position
+  visits[i] = tv.N[(size_t)g * tv.cap * tv.A + a];
 }
 
 // root priors as stored by root_expand (after the Dirichlet mix of mcts.py:114-116); 0 on occupied cells
@@ -527,7 +527,7 @@ __global__ void end_move_kernel(RulesParams rp, TreeView tv, EpisodeView ev, int
     bool legal = a < A && !(bb_test<NW>(x, a) || bb_test<NW>(o, a));
     double p = 0.0;
     if (legal) p = uniform ? 1.0 / k : exp((double)logf((float)Nroot[a] + 1e-8f) / T - mx) / sum;
-    if (!arena && a < A) pi[a] = (float)p;
+    if (a < A) pi[a] = (float)p;          // the arena keeps it for azp_episode_snapshot only (no examples are emitted)
     double c = p;            // inclusive scan inside the chunk
 #pragma unroll
     for (int off = 1; off < 32; off <<= 1) {
@@ -664,9 +664,11 @@ int azp_tree_begin_move(azp_engine* e, int n, int emit, int compact, int parity,
   return azp_check_launch();
 }
 int azp_tree_root_expand(azp_engine* e, int n, const float* policy, int by_slot, int add_noise, int logits, cudaStream_t s) {
+  azp_prof_begin(e, AZP_PROF_ROOT_EXPAND, nullptr, n, s);
   AZP_DISPATCH_NW(e->NW, root_expand_kernel, warp_grid(n), 128, 0, s, e->rp, e->tv, n, policy, by_slot, add_noise,
                   e->cfg.dirichlet_alpha, e->cfg.dirichlet_weight, e->cfg.seed, logits);
   azp_count_launch();
+  azp_prof_end(e, AZP_PROF_ROOT_EXPAND, s);
   return azp_check_launch();
 }
 int azp_tree_select(azp_engine* e, int n, int compact, int parity, cudaStream_t s) {
@@ -674,9 +676,10 @@ int azp_tree_select(azp_engine* e, int n, int compact, int parity, cudaStream_t 
   azp_count_launch();
   return azp_check_launch();
 }
-int azp_tree_expand_backup(azp_engine* e, int n, const float* policy, const float* value, int by_slot, int logits,
-                           cudaStream_t s) {
-  AZP_DISPATCH_NW_PDL(e->NW, expand_backup_kernel, warp_grid(n), 128, 0, s, e->rp, e->tv, n, policy, value, by_slot, logits);
+int azp_tree_expand_backup(azp_engine* e, int n, const float* policy, const void* value, int by_slot, int logits,
+                           int value_f64, cudaStream_t s) {
+  AZP_DISPATCH_NW_PDL(e->NW, expand_backup_kernel, warp_grid(n), 128, 0, s, e->rp, e->tv, n, policy, value, by_slot, logits,
+                      value_f64);
   azp_count_launch();
   return azp_check_launch();
 }
@@ -684,9 +687,11 @@ int azp_tree_advance(azp_engine* e, int n, const float* policy, const float* val
                      int parity, cudaStream_t s) {
   static int prefetch = -1;
   if (prefetch < 0) { const char* v = getenv("AZP_ROOT_PREFETCH"); prefetch = v ? atoi(v) != 0 : 1; }
+  azp_prof_begin(e, AZP_PROF_ADVANCE, nullptr, n, s);
   AZP_DISPATCH_NW_PDL(e->NW, advance_kernel, warp_grid(n), 128, 0, s, e->rp, e->tv, n, policy, value, by_slot, logits,
                       e->cfg.c_puct, compact | (prefetch << 4), parity);
   azp_count_launch();
+  azp_prof_end(e, AZP_PROF_ADVANCE, s);
   return azp_check_launch();
 }
 int azp_tree_root_visits(azp_engine* e, int n, int32_t* visits, cudaStream_t s) {
@@ -712,14 +717,18 @@ int azp_episode_seat(azp_engine* e, int n, int arena, cudaStream_t s) {
 }
 int azp_episode_end_move(azp_engine* e, int n, int arena, cudaStream_t s) {
   EpisodeView ev = episode_view(e);
+  azp_prof_begin(e, AZP_PROF_END_MOVE, nullptr, n, s);
   AZP_DISPATCH_NW(e->NW, end_move_kernel, warp_grid(n), 128, 0, s, e->rp, e->tv, ev, n, arena);
   azp_count_launch();
+  azp_prof_end(e, AZP_PROF_END_MOVE, s);
   return azp_check_launch();
 }
 int azp_episode_finish(azp_engine* e, int n, int arena, cudaStream_t s) {
   EpisodeView ev = episode_view(e);
+  azp_prof_begin(e, AZP_PROF_FINISH, nullptr, n, s);
   AZP_DISPATCH_NW(e->NW, finish_games_kernel, warp_grid(n), 128, 0, s, e->rp, e->tv, ev, n, arena);
   azp_count_launch();
+  azp_prof_end(e, AZP_PROF_FINISH, s);
   return azp_check_launch();
 }
 int azp_episode_drain(azp_engine* e, long long* out_written_dev, int mult, cudaStream_t s) {

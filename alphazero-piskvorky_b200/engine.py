@@ -61,7 +61,6 @@ class Engine:
         if device is None:
             device = torch.cuda.current_device()
         self.device = torch.device("cuda", device if isinstance(device, int) else torch.device(device).index or 0)
-        torch.cuda.set_device(self.device)
         self.cfg = _lib.Config(board=board, win_length=win_length, games=games, sims=sims, c_puct=c_puct,
                                dirichlet_alpha=dirichlet_alpha, dirichlet_weight=dirichlet_weight,
                                net_kind=net_kind, net_dtype=net_dtype, tower_blocks=tower_blocks,
@@ -88,6 +87,10 @@ class Engine:
         self._stream.wait_stream(cur)
         return self._stream
 
+    def _sp(self):
+        """cudaStream_t of torch's current stream on THIS engine's device (the C side selects the device itself)."""
+        return stream_ptr(self.device)
+
     def close(self):
         if getattr(self, "h", None):
             self.lib.azp_destroy(self.h)
@@ -110,7 +113,7 @@ class Engine:
     def load_blob(self, blob, slot=0):
         if isinstance(blob, torch.Tensor) and blob.is_cuda:
             blob = blob.contiguous().float()
-            check(self.lib.azp_load_weights_device(self.h, slot, ptr(blob), blob.numel(), stream_ptr()), self.h)
+            check(self.lib.azp_load_weights_device(self.h, slot, ptr(blob), blob.numel(), self._sp()), self.h)
         else:
             blob = np.ascontiguousarray(blob, dtype=np.float32)
             check(self.lib.azp_load_weights(self.h, slot, blob.ctypes.data_as(C.c_void_p), blob.size), self.h)
@@ -123,7 +126,7 @@ class Engine:
         policy = torch.empty((n, self.A), device=self.device)
         value = torch.empty((n,), device=self.device)
         check(self.lib.azp_net_forward(self.h, slot, n, ptr(planes), ptr(logits), ptr(policy), ptr(value),
-                                       stream_ptr()), self.h)
+                                       self._sp()), self.h)
         return logits, policy, value
 
     def debug_activations(self, layer, n):
@@ -131,10 +134,10 @@ class Engine:
         shape = (n, self.A, c) if c else (n, 6, self.A)
         if layer == 9:                      # bring-up: conv3 clock stamps [64][16] int64
             out = torch.zeros((64, 16), dtype=torch.int64, device=self.device)
-            check(self.lib.azp_debug_activations(self.h, 9, 1, ptr(out), stream_ptr()), self.h)
+            check(self.lib.azp_debug_activations(self.h, 9, 1, ptr(out), self._sp()), self.h)
             return out
         out = torch.empty(shape, device=self.device)
-        check(self.lib.azp_debug_activations(self.h, layer, n, ptr(out), stream_ptr()), self.h)
+        check(self.lib.azp_debug_activations(self.h, layer, n, ptr(out), self._sp()), self.h)
         return out
 
     # ---- step-by-step search (host evaluator hook) ------------------------------------------------
@@ -142,13 +145,13 @@ class Engine:
         n = x.shape[0]
         self._n = n
         check(self.lib.azp_search_begin(self.h, n, ptr(x), ptr(o), ptr(to_move), ptr(last), ptr(ply),
-                                        ptr(game_id), stream_ptr()), self.h)
+                                        ptr(game_id), self._sp()), self.h)
 
     def root_expand(self, policy, add_noise=False):
-        check(self.lib.azp_root_expand(self.h, ptr(policy), int(add_noise), stream_ptr()), self.h)
+        check(self.lib.azp_root_expand(self.h, ptr(policy), int(add_noise), self._sp()), self.h)
 
     def select(self):
-        check(self.lib.azp_select(self.h, stream_ptr()), self.h)
+        check(self.lib.azp_select(self.h, self._sp()), self.h)
 
     def leaf_states(self):
         n = self._n
@@ -158,21 +161,28 @@ class Engine:
         tm = torch.empty((n,), dtype=torch.uint8, device=dev)
         last = torch.empty((n,), dtype=torch.int16, device=dev)
         kind = torch.empty((n,), dtype=torch.uint8, device=dev)
-        check(self.lib.azp_leaf_states(self.h, ptr(x), ptr(o), ptr(tm), ptr(last), ptr(kind), stream_ptr()), self.h)
+        check(self.lib.azp_leaf_states(self.h, ptr(x), ptr(o), ptr(tm), ptr(last), ptr(kind), self._sp()), self.h)
         return x, o, tm, last, kind
 
     def expand_backup(self, policy, value):
-        check(self.lib.azp_expand_backup(self.h, ptr(policy), ptr(value), stream_ptr()), self.h)
+        """value float32 [n], or float64 [n]: a host evaluator's Python floats are backed up unrounded (mcts.py:137-141)."""
+        if value.dtype == torch.float64:
+            check(self.lib.azp_expand_backup_f64(self.h, ptr(policy), ptr(value), self._sp()), self.h)
+        else:
+            check(self.lib.azp_expand_backup(self.h, ptr(policy), ptr(value), self._sp()), self.h)
 
-    def root_visits(self):
+    def root_visits(self, n=None):
+        """Root child visit counts [n,A]; after selfplay()/arena_steps() pass n=self.games: the last move step's searches."""
+        if n is not None:
+            self._n = n
         v = torch.empty((self._n, self.A), dtype=torch.int32, device=self.device)
-        check(self.lib.azp_root_visits(self.h, ptr(v), stream_ptr()), self.h)
+        check(self.lib.azp_root_visits(self.h, ptr(v), self._sp()), self.h)
         return v
 
     def root_priors(self):
         """Priors of the root's children [n,A] after root_expand (mcts.py:109-120); 0 on occupied cells."""
         p = torch.empty((self._n, self.A), dtype=torch.float32, device=self.device)
-        check(self.lib.azp_root_priors(self.h, ptr(p), stream_ptr()), self.h)
+        check(self.lib.azp_root_priors(self.h, ptr(p), self._sp()), self.h)
         return p
 
     def search(self, x, o, to_move, last, ply=None, game_id=None, add_noise=False):
@@ -182,13 +192,18 @@ class Engine:
         v = torch.empty((n, self.A), dtype=torch.int32, device=self.device)
         with torch.cuda.stream(self._driver_stream()):
             check(self.lib.azp_search(self.h, 0, n, ptr(x), ptr(o), ptr(to_move), ptr(last), ptr(ply), ptr(game_id),
-                                      int(add_noise), ptr(v), stream_ptr()), self.h)
+                                      int(add_noise), ptr(v), self._sp()), self.h)
         return v
 
     # ---- drivers ------------------------------------------------------------------------------------
     def set_temperature_table(self, table):
         t = np.ascontiguousarray(table, dtype=np.float64)
         check(self.lib.azp_set_temperature_table(self.h, t.ctypes.data_as(C.c_void_p), t.size), self.h)
+
+    def set_augment(self, mode):
+        """Augmentation of the next selfplay() calls (AUGMENT_NONE = raw positions, for the cross-rank exchange)."""
+        check(self.lib.azp_set_augment_mode(self.h, int(mode)), self.h)
+        self.augment = mode
 
     def example_capacity_floor(self) -> int:
         """Smallest output capacity (examples) azp_selfplay_run accepts."""
@@ -207,7 +222,7 @@ class Engine:
         written = C.c_int64(0)
         with torch.cuda.stream(self._driver_stream()):
             st = check(self.lib.azp_selfplay_run(self.h, first_game, n_games, int(resume), max_move_steps, ptr(planes),
-                                                 ptr(pi), ptr(z), planes.shape[0], C.byref(written), stream_ptr()),
+                                                 ptr(pi), ptr(z), planes.shape[0], C.byref(written), self._sp()),
                        self.h)
         return st, planes, pi, z, int(written.value)
 
@@ -227,8 +242,30 @@ class Engine:
     def arena(self, n_games, first_game=0):
         wld = (C.c_int64 * 3)()
         with torch.cuda.stream(self._driver_stream()):
-            check(self.lib.azp_arena_run(self.h, first_game, n_games, wld, stream_ptr()), self.h)
+            check(self.lib.azp_arena_run(self.h, first_game, n_games, wld, self._sp()), self.h)
         return int(wld[0]), int(wld[1]), int(wld[2])
+
+    def arena_steps(self, n_games, first_game=0, max_move_steps=1, resume=False):
+        """The match in slices of lockstep moves: (status, (wins, losses, draws) so far); status MORE while games remain."""
+        wld = (C.c_int64 * 3)()
+        with torch.cuda.stream(self._driver_stream()):
+            st = check(self.lib.azp_arena_run_steps(self.h, first_game, n_games, int(resume), max_move_steps, wld,
+                                                    self._sp()), self.h)
+        return st, (int(wld[0]), int(wld[1]), int(wld[2]))
+
+    def episode_snapshot(self, history=True):
+        """Per-slot episode state: dict(ply [G], game_id [G], status [G], moves [G,max_plies], pi [G,max_plies,A])."""
+        g, dev = self.games, self.device
+        mp = self.cfg.max_plies if 0 < self.cfg.max_plies < self.A else self.A
+        out = dict(ply=torch.empty((g,), dtype=torch.int32, device=dev),
+                   game_id=torch.empty((g,), dtype=torch.int64, device=dev),
+                   status=torch.empty((g,), dtype=torch.uint8, device=dev))
+        if history:
+            out["moves"] = torch.empty((g, mp), dtype=torch.int16, device=dev)       # uint16 payload
+            out["pi"] = torch.empty((g, mp, self.A), dtype=torch.float32, device=dev)
+        check(self.lib.azp_episode_snapshot(self.h, ptr(out["ply"]), ptr(out["game_id"]), ptr(out["status"]),
+                                            ptr(out.get("moves")), ptr(out.get("pi")), self._sp()), self.h)
+        return out
 
     def counters(self) -> dict:
         c = _lib.Counters()
@@ -243,6 +280,15 @@ class Engine:
         ms, n, fl = C.c_double(0), C.c_uint64(0), C.c_double(0)
         check(self.lib.azp_get_profile(self.h, C.byref(ms), C.byref(n), C.byref(fl)), self.h)
         return float(ms.value), int(n.value), float(fl.value)
+
+    def get_profile_kernels(self) -> dict:
+        """{kernel class: (ms, launches, units)} of every bracketed kernel class since the last call (azp_b200.h AZP_PROF_*)."""
+        out = {}
+        for kind, name in enumerate(_lib.PROF_KINDS):
+            ms, n, u = C.c_double(0), C.c_uint64(0), C.c_double(0)
+            check(self.lib.azp_get_profile_kernel(self.h, kind, C.byref(ms), C.byref(n), C.byref(u)), self.h)
+            out[name] = (float(ms.value), int(n.value), float(u.value))
+        return out
 
     def reset_counters(self):
         check(self.lib.azp_reset_counters(self.h), self.h)

@@ -32,18 +32,32 @@ class ModelEvaluator:
         self.num_simulations, self.c_puct = num_simulations, c_puct
         self.win_length = win_length
         self.net_dtype, self.seed, self.rank, self.world = net_dtype, seed, rank, world
+        self._first_game = 0                # global game ids already played: every match gets fresh Philox streams
 
     def evaluate(self, candidate_controller, baseline_controller, num_games=20, debug=False):
         board = candidate_controller.net.board_size
         win = self.win_length if self.win_length is not None else (WIN_LENGTH if board < 9 else 5)
         local = -(-num_games // self.world)
+        from .controller import net_kind_of
+        from .net import GomokuTowerNet
+        cand, base = candidate_controller.net, baseline_controller.net
+        kw = {}
+        if isinstance(cand, GomokuTowerNet) or isinstance(base, GomokuTowerNet):
+            if type(cand) is not type(base) or (cand.blocks, cand.channels) != (base.blocks, base.channels):
+                raise ValueError("candidate and baseline must share one architecture (two weight slots of one engine)")
+            kw = dict(net_kind=net_kind_of(cand), tower_blocks=cand.blocks, tower_channels=cand.channels)
+        if base.board_size != board:
+            raise ValueError("candidate and baseline play on different board sizes")
         eng = _e.Engine(board=board, win_length=win, games=max(1, local), sims=self.num_simulations,
                         c_puct=self.c_puct, net_dtype=self.net_dtype, seed=self.seed, rank=self.rank,
-                        world=self.world)
-        eng.load_state_dict(candidate_controller.net.state_dict(), slot=0)
-        eng.load_state_dict(baseline_controller.net.state_dict(), slot=1)
+                        world=self.world, **kw)
+        eng.load_state_dict(cand.state_dict(), slot=0)
+        eng.load_state_dict(base.state_dict(), slot=1)
         eng.set_temperature_table([float(temperature_schedule(s)) for s in range(board * board + 1)])
-        wins, losses, draws = eng.arena(num_games)
+        # game parity decides the first mover (evaluator.py:64-69): keep first_game even so game i of this match
+        # starts like game i of the reference's loop
+        wins, losses, draws = eng.arena(num_games, first_game=self._first_game)
+        self._first_game += num_games + (num_games & 1)
         eng.close()
         if self.world > 1:
             from .dist import all_reduce_wld

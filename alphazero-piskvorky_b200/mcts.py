@@ -34,39 +34,51 @@ def _state_from_cells(cells, to_move, last, board, win):
 
 class MCTS:
     def __init__(self, policy_value_fn, num_simulations, c_puct, dirichlet_alpha=0.3, dirichlet_weight=0.25,
-                 seed=0, net_dtype=DTYPE_F32):
+                 seed=None, net_dtype=DTYPE_F32, max_cached_engines=4):
         self.policy_value_fn = policy_value_fn
         self.num_simulations = num_simulations
         self.c_puct = c_puct
         self.dirichlet_alpha = dirichlet_alpha
         self.dirichlet_weight = dirichlet_weight
-        self.seed = seed
+        # the reference draws its noise / moves from the global NumPy RNG (mcts.py:114, 177): without an explicit seed
+        # the Philox key comes from that RNG, so every MCTS object gets its own stream and np.random.seed() reproduces it
+        self.seed = int(np.random.randint(0, 2 ** 31 - 1)) if seed is None else seed
         self.net_dtype = net_dtype
-        self._engines = {}
+        self._engines = {}                  # (board, win, n, architecture) -> Engine, least recently used first
+        self._max_engines = max(1, max_cached_engines)
         self._calls = 0
 
     def _engine(self, board, win, n):
-        key = (board, win, n)
-        eng = self._engines.get(key)
+        ctrl = getattr(self.policy_value_fn, "controller", None)
+        net = ctrl.net if ctrl is not None else None           # read at call time
+        kw = {}
+        if net is not None:
+            from .controller import net_kind_of
+            from .net import GomokuTowerNet
+            if isinstance(net, GomokuTowerNet):
+                kw = dict(net_kind=net_kind_of(net), tower_blocks=net.blocks, tower_channels=net.channels)
+        key = (board, win, n, tuple(sorted(kw.items())))
+        eng = self._engines.pop(key, None)
         if eng is None:
-            kw = {}
-            ctrl = getattr(self.policy_value_fn, "controller", None)
-            if ctrl is not None:
-                from .controller import net_kind_of
-                from .net import GomokuTowerNet
-                if isinstance(ctrl.net, GomokuTowerNet):
-                    kw = dict(net_kind=net_kind_of(ctrl.net), tower_blocks=ctrl.net.blocks,
-                              tower_channels=ctrl.net.channels)
+            while len(self._engines) >= self._max_engines:     # each engine owns a node table: close the stalest
+                self._engines.pop(next(iter(self._engines))).close()
             eng = _e.Engine(board=board, win_length=win, games=n, sims=self.num_simulations, c_puct=self.c_puct,
                             dirichlet_alpha=self.dirichlet_alpha, dirichlet_weight=self.dirichlet_weight,
                             seed=self.seed, net_dtype=self.net_dtype, **kw)
             eng.weights_version = None
-            self._engines[key] = eng
-        ctrl = getattr(self.policy_value_fn, "controller", None)
-        if ctrl is not None and eng.weights_version != getattr(ctrl, "version", 0):
-            eng.load_state_dict(ctrl.net.state_dict())        # the reference reads controller.net at every evaluation
-            eng.weights_version = getattr(ctrl, "version", 0)
+        self._engines[key] = eng                               # most recently used last
+        if ctrl is not None:
+            from .controller import weights_fingerprint
+            fp = weights_fingerprint(ctrl)                     # the reference reads controller.net at every evaluation
+            if eng.weights_version != fp:
+                eng.load_state_dict(net.state_dict())
+                eng.weights_version = fp
         return eng
+
+    def close(self):
+        for eng in self._engines.values():
+            eng.close()
+        self._engines.clear()
 
     # ---- batched search ------------------------------------------------------------------------------
     def run_batch(self, states, temperature, add_root_noise=False, sample=True):
@@ -110,7 +122,7 @@ class MCTS:
         dev = eng.device
         eng.search_begin(batch.x, batch.o, batch.to_move, batch.last, ply=ply)
         pol = np.zeros((n, A), dtype=np.float32)
-        val = np.zeros((n,), dtype=np.float32)
+        val = np.zeros((n,), dtype=np.float64)                  # Python floats stay float64 (mcts.py:137-141)
         for i, s in enumerate(states):                          # root evaluation (value discarded)
             p, _ = self.policy_value_fn(s)
             pol[i] = np.asarray(p, dtype=np.float32).reshape(-1)

@@ -20,12 +20,12 @@ class ModelLoader:
 
     def get_best_model(self):
         if self.best_path is None:
-            print("[Model Loader] Choosen a randomly initialized model.")
+            print(f"[ModelLoader] {self.model_dir} holds no checkpoint: saving a random init as the first best")
             random_net = GomokuNet(board_size=self.board_size)
             timestamp = datetime.now().strftime("%Y%m%d_%H%M%S")
             torch.save(random_net.state_dict(), os.path.join(self.model_dir, f"model_{timestamp}.pt"))
             return random_net.float()
-        print(f"[Model Loader] Choosen {self.best_path} for evaluation.")
+        print(f"[ModelLoader] best = {self.best_path}")
         model = GomokuNet(board_size=self.board_size)
         model.load_state_dict(torch.load(self.best_path, map_location="cpu", weights_only=True))
         return model.float()

@@ -23,8 +23,11 @@ def run_training(num_episodes=K.NUM_EPISODES, board_size=K.BOARD_SIZE, win_lengt
                  num_simulations=K.NUM_SELF_PLAY_SIMULATIONS, c_puct=K.SELF_PLAY_EXPLORATION_CONSTANT,
                  buffer_capacity=K.BUFFER_CAPACITY, batch_size=K.BATCH_SIZE, batches_per_episode=K.BATCHES_PER_EPISODE,
                  num_epochs=K.NUM_EPOCHS, learning_rate=K.LEARNING_RATE, evaluation_games=K.EVALUATION_GAMES,
-                 eval_simulations=K.NUM_EVAL_SIMULATIONS, augment="reference", concurrent_games=2048):
-    """Returns a list of per-episode summaries ``{"examples", "buffer", "loss", "win_rate", "promoted"}``."""
+                 eval_simulations=K.NUM_EVAL_SIMULATIONS, augment="d4", concurrent_games=2048):
+    """Returns a list of per-episode summaries ``{"examples", "buffer", "loss", "win_rate", "promoted"}``.
+    ``augment="d4"`` (default) emits 8 consistent examples per position; ``"reference"`` reproduces the 4 pairs of
+    self_play.py:94-108 as written, three of which pair a rotated state with a mis-rotated pi -- kept for
+    parity tests, not for training."""
     print(f"[Main] Using {device}")
     net = ModelLoader(model_dir, board_size).get_best_model()
     evaluator = ModelEvaluator(Gomoku, print_games=False, device=device, num_simulations=eval_simulations,

@@ -119,6 +119,16 @@ int azp_extract_policy(int board, int n, const int32_t* visits, const uint8_t* l
 int azp_augment_write(int board, int mode, int n, const float* planes, const float* pi,
                       const int32_t* z, float* out_planes, float* out_pi, int32_t* out_z, void* stream);
 
+/* ReplayBuffer.extend on the device (replay_buffer.py:27-29: append in order, evict the oldest) fused with the
+ * augmentation: up to n_max positions (the count is read on the device from *n_dev when n_dev != NULL -- e.g. the
+ * header of a slab received by an all-gather -- else it is n_max) are expanded by `mode` and written into a ring of
+ * ring_capacity examples at slot (*ring_head_dev + i) % ring_capacity; *ring_head_dev (int64 on the device = examples
+ * ever written) advances by count * mult.  A slab larger than the ring keeps its newest ring_capacity examples
+ * (deque(maxlen) semantics).  No host synchronisation. */
+int azp_augment_write_ring(int board, int mode, int n_max, const int32_t* n_dev, const float* planes, const float* pi,
+                           const int32_t* z, float* ring_planes, float* ring_pi, int32_t* ring_z,
+                           int64_t* ring_head_dev, int64_t ring_capacity, void* stream);
+
 /* ---- network ------------------------------------------------------------------ */
 /* weights: float32 blob on the HOST holding the reference state_dict tensors concatenated in
  * key order (stem: conv1.weight, conv1.bias, conv2.*, conv3.*, policy_conv.*, policy_fc.*,
@@ -157,7 +167,11 @@ int azp_leaf_states(azp_engine* e, uint64_t* x, uint64_t* o, uint8_t* to_move, i
 /* mcts.py:131-141: expand the evaluated leaves with policy float32 [n][B*B] / value float32 [n]
  * (indexed by game), terminal leaves use their game result; back up along each path */
 int azp_expand_backup(azp_engine* e, const float* policy, const float* value, void* stream);
-/* root child visit counts int32 [n][B*B] (the reference computes them at mcts.py:144) */
+/* same with value float64 [n]: a host evaluator returns a Python float and the reference backs up exactly that
+ * double (value = float(v.item()), controller.py:50; node.backup(-value), mcts.py:137-141) */
+int azp_expand_backup_f64(azp_engine* e, const float* policy, const double* value, void* stream);
+/* root child visit counts int32 [n][B*B] (the reference computes them at mcts.py:144); after a driver call
+ * (azp_selfplay_run / azp_arena_run_steps) these are the counts of the LAST move step's searches, one row per slot */
 int azp_root_visits(azp_engine* e, int32_t* visits, void* stream);
 /* root priors float32 [n][B*B] as the search holds them after azp_root_expand: policy[r,c] on legal cells,
  * (1-w)*policy + w*Dirichlet(alpha) if add_noise was set (mcts.py:109-120, Node.expand mcts.py:50-64); 0 on
@@ -172,6 +186,10 @@ int azp_search(azp_engine* e, int slot, int n, const uint64_t* x, const uint64_t
 /* temperature per ply, host doubles (default_temperature_schedule, self_play.py:24-26, is
  * evaluated by the facade so user-supplied schedules keep working) */
 int azp_set_temperature_table(azp_engine* e, const double* host_table, int n);
+/* augmentation applied by the next azp_selfplay_run calls (AZP_AUGMENT_*; initial value: azp_config.augment_mode).
+ * AZP_AUGMENT_NONE emits raw positions -- the form that is all-gathered across ranks, the receiving side augments
+ * (self_play.py:94-108 runs in the parent process in the reference too). */
+int azp_set_augment_mode(azp_engine* e, int mode);
 /* SelfPlayManager.generate_self_play, self_play.py:110-159 + _worker, :29-77.
  * Plays global game ids [first_game, first_game + n_games) that belong to this rank, S sims per
  * move with root noise, writes augmented examples to out_* (capacity in examples).  Returns
@@ -184,6 +202,18 @@ int azp_selfplay_run(azp_engine* e, int64_t first_game, int64_t n_games, int res
  * plays O); game i has X to move first iff i is even; no root noise; T = table[step].
  * host_wld = {candidate wins, baseline wins, draws} for this rank's games. */
 int azp_arena_run(azp_engine* e, int64_t first_game, int64_t n_games, int64_t* host_wld, void* stream);
+/* the same match in slices of at most max_move_steps lockstep moves (0 = run to the end): returns AZP_MORE while games
+ * remain (call again with resume != 0); host_wld is the tally since the match started.  Lets a caller watch the loop
+ * of evaluator.py:64-90 move by move (azp_root_visits + azp_episode_snapshot between slices). */
+int azp_arena_run_steps(azp_engine* e, int64_t first_game, int64_t n_games, int resume, int max_move_steps,
+                        int64_t* host_wld, void* stream);
+/* Episode state of every slot as the drivers hold it (self_play.py:47-58 / evaluator.py:64-90 bookkeeping), copied
+ * device-to-device; any pointer may be NULL.  ply int32 [games] = moves played in the slot's current game; game_id
+ * int64 [games]; status uint8 [games] (0 idle / 1 playing / 2 finished, not yet emitted); moves uint16 [games][max_plies]
+ * and pi_hist float32 [games][max_plies][B*B] = the move played and the pi it was drawn from at every ply of the slot's
+ * game (rows of a finished game stay readable until the slot's next game overwrites them). */
+int azp_episode_snapshot(azp_engine* e, int32_t* ply, int64_t* game_id, uint8_t* status, uint16_t* moves,
+                         float* pi_hist, void* stream);
 int azp_get_counters(azp_engine* e, azp_counters* host_out);
 /* Per-kernel timing for the roofline: when enabled, every launch of the DOMINANT kernel (the
  * largest convolution of the net) is bracketed by CUDA events on its own stream.
@@ -191,6 +221,22 @@ int azp_get_counters(azp_engine* e, azp_counters* host_out);
  * algorithmic FLOPs those launches performed, and resets the accumulators. */
 int azp_set_profiling(azp_engine* e, int enabled);
 int azp_get_profile(azp_engine* e, double* host_ms, uint64_t* host_launches, double* host_flops);
+/* The other kernels of the path, for the HBM side of the roofline.  While profiling is on, the
+ * last 40 simulation steps of every move run as plain launches with each kernel between its own pair of CUDA events
+ * (the steps before them still replay the captured graph, unbracketed).  Returns and resets, per kernel class: summed
+ * duration (ms), bracketed launches, and the units those launches processed (leaves of the evaluated batch for the net
+ * kernels, game slots for the tree / episode kernels). */
+#define AZP_PROF_DOMINANT 0     /* largest convolution of the net (conv3 / a tower conv): GomokuNet.forward, net.py:57-59 */
+#define AZP_PROF_ADVANCE 1      /* expand + backup + next descent: Node.expand/backup/select, mcts.py:50-82, 126-141 */
+#define AZP_PROF_CONV1 2        /* leaf gather + encode + first conv: Gomoku.encode, games.py:86-129; net.py:57 */
+#define AZP_PROF_CONV2 3        /* second convolution, net.py:58 */
+#define AZP_PROF_FC 4           /* policy_fc / value_fc1 / value_fc2, net.py:64-70 */
+#define AZP_PROF_ROOT_EXPAND 5  /* root priors + Dirichlet noise, mcts.py:109-120 */
+#define AZP_PROF_END_MOVE 6     /* pi from visits, move sampling, apply: mcts.py:143-183, self_play.py:53-58 */
+#define AZP_PROF_FINISH 7       /* labelled raw positions of finished games: self_play.py:60-72 */
+#define AZP_PROF_AUGMENT 8      /* symmetry augmentation + example writer: self_play.py:94-108 */
+#define AZP_PROF_KINDS 9
+int azp_get_profile_kernel(azp_engine* e, int kind, double* host_ms, uint64_t* host_launches, double* host_units);
 int azp_reset_counters(azp_engine* e);
 
 /* ---- training step (the immediate consumer of the examples) ----------- */

@@ -1,0 +1,314 @@
+"""GPU parity tests of the DRIVER-level semantics: what the episode loops of the reference do between searches.
+
+* self-play (alphazero/self_play.py:47-58): the pi a worker records at ply p is ``MCTS.run(state, T(p))`` -- the root
+  visit counts of THAT search pushed through mcts.py:143-170 at the temperature of THAT ply;
+* arena (alphazero/evaluator.py:64-90): X (candidate) moves first in even games, O in odd games; the side to move
+  searches with ITS OWN net, without root noise, at ``T = table[step]`` where ``step`` is that side's own counter
+  (0,1,2,.. for the first mover, 1,2,3,.. for the second); the tally counts X wins as candidate wins;
+* the evaluator hook keeps the value a host callable returns as a Python float (float64), mcts.py:137-141.
+
+The drivers run in slices of ONE lockstep move (``max_move_steps=1``); between slices the tests read the visit counts
+of the searches that have just ended (azp_root_visits) and the episode bookkeeping (azp_episode_snapshot), and replay
+everything with the oracle."""
+
+import numpy as np
+import pytest
+import torch
+
+import synth
+from oracle import arena as oarena, gomoku, mcts as omcts, net as onet, selfplay as oselfplay
+
+pytestmark = pytest.mark.gpu
+
+PLAYING = 1
+
+
+@pytest.fixture(scope="module")
+def az():
+    import alphazero_piskvorky_b200 as az
+    return az
+
+
+def _pi_reference(visits_row, legal, T):
+    """mcts.py:143-170 on the root's children in row-major order; T arrives as np.float64 from the schedules."""
+    idx = np.flatnonzero(legal)
+    return idx, omcts.policy_from_visits(visits_row[idx].astype(np.float32), np.float64(T))
+
+
+class _Tracker:
+    """Host-side mirror of one slot: the oracle position of the game the slot is playing."""
+
+    def __init__(self, size, win):
+        self.size, self.win = size, win
+        self.gid, self.state, self.moves, self.pis = None, None, [], []
+
+    def seat(self, gid, first=gomoku.X):
+        self.gid = int(gid)
+        self.state = gomoku.State(self.size, self.win)
+        self.state.to_move = first
+        self.moves, self.pis = [], []
+
+
+@pytest.mark.parametrize("size,win,sims,slots,ngames,steps,dtype", [
+    (15, 8, 12, 6, 6, 130, "bf16"),      # WIN 8: nobody wins early, so plies 0, 1, 10, 100 are all reached
+    (5, 4, 40, 8, 20, 100, "f32"),        # short games: slots are re-seated many times, every game ends inside the run
+])
+def test_selfplay_pi_is_the_searchs_visit_counts_at_the_plys_temperature(az, size, win, sims, slots, ngames, steps, dtype):
+    A = size * size
+    eng = az.Engine(board=size, win_length=win, games=slots, sims=sims, augment=az.AUGMENT_NONE, seed=13,
+                    net_dtype=az.DTYPE_BF16 if dtype == "bf16" else az.DTYPE_F32)
+    eng.load_state_dict(onet.synthetic_stem_params(size, seed=5, scale=2.0))
+    # the reference's own schedule (self_play.py:24-26): every ply has a different temperature
+    table = np.array([oselfplay.default_temperature_schedule(m) for m in range(A + 1)], dtype=np.float64)
+    eng.set_temperature_table(table)
+    trackers = [_Tracker(size, win) for _ in range(slots)]
+    finished = {}                         # tuple(moves) -> [pi rows] of every finished game
+    emitted = []
+    plies_checked = set()
+    out, status_before = None, None
+    for step in range(steps):
+        st, planes, pi, z, written = eng.selfplay(ngames, max_move_steps=1, out=out, resume=step > 0)
+        out = (planes, pi, z)
+        if written:
+            emitted.append((planes[:written].cpu().numpy(), pi[:written].cpu().numpy(), z[:written].cpu().numpy()))
+        visits = eng.root_visits(slots).cpu().numpy()
+        snap = {k: v.cpu().numpy() for k, v in eng.episode_snapshot().items()}
+        for g, tr in enumerate(trackers):
+            if step == 0:
+                # every slot got a game (ngames >= slots) and has played exactly one move of it
+                assert snap["ply"][g] == 1 and snap["status"][g] == PLAYING
+                tr.seat(snap["game_id"][g])
+            elif status_before[g] != PLAYING:                      # parked slot: no search happened here
+                if snap["status"][g] == PLAYING:                   # (a game waiting for slab space got flushed)
+                    assert snap["ply"][g] == 0
+                    tr.seat(snap["game_id"][g])
+                continue
+            p = len(tr.moves)                                      # the ply this step's search was run at
+            board_flat = tr.state.board.reshape(-1)
+            legal = board_flat == 0
+            row_pi = snap["pi"][g, p]
+            move = int(snap["moves"][g, p].astype(np.uint16))
+            assert visits[g].sum() == sims and not visits[g][~legal].any()          # root.N == S (mcts.py:123-141)
+            idx, ref = _pi_reference(visits[g], legal, table[p])                     # T(ply), self_play.py:53
+            assert np.abs(row_pi[idx] - ref).max() <= 1e-6, (step, g, p)            # a12 tolerance
+            assert not row_pi[~legal].any()
+            assert legal[move] and row_pi[move] > 0                                 # a draw from pi (mcts.py:177)
+            plies_checked.add(p)
+            tr.pis.append(row_pi.copy())
+            tr.moves.append(move)
+            tr.state = tr.state.play((move // size, move % size))
+            if tr.state.is_terminal():
+                finished[tuple(tr.moves)] = (tr.pis, tr.state.result())
+                # the slot was flushed and handed its next game (or parked) inside the same driver call
+                assert snap["game_id"][g] != tr.gid or snap["status"][g] != PLAYING
+                if snap["status"][g] == PLAYING:
+                    assert snap["ply"][g] == 0
+                    tr.seat(snap["game_id"][g])
+            else:
+                assert snap["game_id"][g] == tr.gid and snap["ply"][g] == p + 1 and snap["status"][g] == PLAYING
+        status_before = snap["status"].copy()
+        if st != az.MORE:
+            break
+    if size == 15:
+        assert {0, 1, 10, 100} <= plies_checked
+    else:
+        assert st != az.MORE and len(finished) >= ngames - 2       # (two games sharing every move would collide)
+    # the examples the writer emitted are exactly the recorded rows: game-major, pi bit-identical, z from the result
+    n_rows = 0
+    for planes, pi, z in emitted:
+        i = 0
+        while i < len(z):
+            assert planes[i].sum() == 0                            # a game starts on the empty board
+            j = i + 1
+            while j < len(z) and planes[j].sum() != 0:
+                j += 1
+            moves = []
+            for k in range(i, j - 1):                              # move k = the last-move plane of position k+1
+                moves.append(int(np.flatnonzero(planes[k + 1][2].reshape(-1))[0]))
+            match = [m for m in finished if len(m) == j - i and list(m[:-1]) == moves]
+            assert match, "emitted game not among the tracked finished games"
+            pis, result = finished[match[0]]
+            for k in range(i, j):
+                assert np.array_equal(pi[k].reshape(-1), pis[k - i])
+                player = gomoku.X if (k - i) % 2 == 0 else gomoku.O
+                assert z[k] == oselfplay.label(result, player)     # self_play.py:71
+            n_rows += j - i
+            i = j
+    assert n_rows == sum(len(m) for m in finished) or size == 15   # 15x15: games still running when the test stops
+
+
+@pytest.mark.parametrize("table_kind", ["reference", "index_revealing"])
+def test_arena_first_mover_step_counters_nets_and_tally_match_the_oracle(az, table_kind):
+    size, win, sims, slots, ngames = 5, 4, 30, 6, 14
+    A = size * size
+    params = [onet.synthetic_stem_params(size, seed=1, scale=2.0), onet.synthetic_stem_params(size, seed=2, scale=2.0)]
+    eng = az.Engine(board=size, win_length=win, games=slots, sims=sims, c_puct=1.5, seed=5)
+    eng.load_state_dict(params[0], slot=0)              # candidate, plays X
+    eng.load_state_dict(params[1], slot=1)              # baseline, plays O
+    if table_kind == "reference":
+        table = np.array([oarena.eval_temperature(s) for s in range(A + 1)], dtype=np.float64)   # evaluator.py:14-19
+    else:
+        table = np.array([0.5 + 0.13 * s for s in range(A + 1)], dtype=np.float64)     # every index gives another pi
+    eng.set_temperature_table(table)
+
+    def evaluator(slot):
+        cache = {}
+
+        def fn(state):
+            key = (state.board.tobytes(), state.to_move, state.last)
+            if key not in cache:
+                _, pol, val = eng.net_forward(torch.from_numpy(state.planes()).unsqueeze(0).cuda(), slot=slot)
+                cache[key] = (pol[0].cpu().numpy().reshape(size, size), float(val[0].item()))
+            p, v = cache[key]
+            return p.copy(), v
+        return fn
+
+    evals = [evaluator(0), evaluator(1)]
+    trackers = [_Tracker(size, win) for _ in range(slots)]
+    tally = {gomoku.X: 0, gomoku.O: 0, gomoku.DRAW: 0}
+    seen_first = set()
+    status_before, done, step = None, 0, 0
+    while True:
+        st, wld = eng.arena_steps(ngames, max_move_steps=1, resume=step > 0)
+        visits = eng.root_visits(slots).cpu().numpy()
+        snap = {k: v.cpu().numpy() for k, v in eng.episode_snapshot().items()}
+        for g, tr in enumerate(trackers):
+            if step == 0:
+                assert snap["ply"][g] == 1 and snap["status"][g] == PLAYING
+                gid = int(snap["game_id"][g])
+                tr.seat(gid, gomoku.X if gid % 2 == 0 else gomoku.O)      # evaluator.py:64-69
+            elif status_before[g] != PLAYING:
+                continue
+            p = len(tr.moves)
+            side = tr.state.to_move
+            first = gomoku.X if tr.gid % 2 == 0 else gomoku.O
+            assert side == (first if p % 2 == 0 else gomoku.other(first))
+            seen_first.add(first)
+            # the side to move searches with its own net (evaluator.py:71-84): candidate = X = slot 0
+            ref = omcts.Search(evals[0 if side == gomoku.X else 1], sims, 1.5).run(
+                tr.state, 1.0, add_root_noise=False, forced_action=tr.state.legal_actions()[0])
+            assert np.array_equal(visits[g].reshape(size, size), ref.visits), (step, g, p)
+            # ... at the temperature of ITS OWN step counter (evaluator.py:87-90)
+            tidx = oarena.step_counters(first == gomoku.X, p)
+            assert tidx == (p // 2 if p % 2 == 0 else p // 2 + 1)
+            legal = tr.state.board.reshape(-1) == 0
+            idx, want = _pi_reference(visits[g], legal, table[tidx])
+            row_pi = snap["pi"][g, p]
+            assert np.abs(row_pi[idx] - want).max() <= 1e-6, (step, g, p, tidx)
+            if table_kind == "index_revealing" and p >= 1 and visits[g].max() < sims:
+                # the neighbouring indices (the ply itself, the other side's counter) give a measurably different pi
+                for wrong in {p, tidx - 1, tidx + 1} - {tidx}:
+                    if 0 <= wrong <= A:
+                        _, other = _pi_reference(visits[g], legal, table[wrong])
+                        assert np.abs(row_pi[idx] - other).max() > 1e-5
+            move = int(snap["moves"][g, p].astype(np.uint16))
+            assert legal[move] and row_pi[move] > 0
+            tr.moves.append(move)
+            tr.state = tr.state.play((move // size, move % size))
+            if tr.state.is_terminal():
+                tally[tr.state.result()] += 1
+                done += 1
+                if snap["status"][g] == PLAYING:
+                    assert snap["ply"][g] == 0 and snap["game_id"][g] != tr.gid
+                    gid = int(snap["game_id"][g])
+                    tr.seat(gid, gomoku.X if gid % 2 == 0 else gomoku.O)
+            else:
+                assert snap["game_id"][g] == tr.gid and snap["ply"][g] == p + 1
+        status_before = snap["status"].copy()
+        step += 1
+        assert wld == (tally[gomoku.X], tally[gomoku.O], tally[gomoku.DRAW])       # candidate wins == X wins
+        if st != az.MORE:
+            break
+        assert step < 40 * ngames
+    assert done == ngames and seen_first == {gomoku.X, gomoku.O}
+    win_rate = (wld[0] + 0.5 * wld[2]) / ngames                                    # evaluator.py:103-105
+    assert oarena.should_promote(win_rate) == az.should_promote(win_rate)
+    eng.close()
+
+
+def test_arena_run_equals_its_sliced_form(az):
+    """azp_arena_run == azp_arena_run_steps run to the end: same Philox streams, same tally."""
+    size, win = 5, 4
+    out = []
+    for sliced in (False, True):
+        eng = az.Engine(board=size, win_length=win, games=8, sims=24, seed=9)
+        eng.load_state_dict(onet.synthetic_stem_params(size, seed=1, scale=2.0), slot=0)
+        eng.load_state_dict(onet.synthetic_stem_params(size, seed=2, scale=2.0), slot=1)
+        eng.set_temperature_table([oarena.eval_temperature(s) for s in range(26)])
+        if not sliced:
+            out.append(eng.arena(20))
+        else:
+            st, wld, k = az.MORE, None, 0
+            while st == az.MORE:
+                st, wld = eng.arena_steps(20, max_move_steps=3, resume=k > 0)
+                k += 1
+            out.append(wld)
+        eng.close()
+    assert out[0] == out[1] and sum(out[0]) == 20
+
+
+def test_hook_backs_up_the_evaluators_python_float_unrounded(az):
+    """mcts.py:137-141: ``value`` is a Python float (float64) and is backed up as such.  With uniform priors every PUCT
+    comparison is decided by Q, so rounding the evaluator's value to float32 changes visit counts: the float64 entry
+    point must reproduce the oracle fed with the doubles, the float32 one the oracle fed with the rounded values."""
+    from alphazero_piskvorky_b200 import engine as _e
+    size, win, sims, n = 5, 4, 300, 12
+    A = size * size
+
+    def make_eval(rounded):
+        def fn(state):
+            key = synth.board_key(state.board, state.to_move, 3)
+            v = ((key % 13) - 6) * 0.05                                    # decimals: sums tie in float64, not after float32 rounding
+            if rounded:
+                v = float(np.float32(v))
+            return np.full((size, size), 1.0 / A, dtype=np.float32), v
+        return fn
+
+    states = []
+    for i in range(n):
+        s = gomoku.State(size, win)
+        for a in synth.random_playout(size, win, plies=i % 6, seed=300 + i):
+            s = s.play(a)
+        states.append(s)
+    batch = az.GomokuBatch.from_cells(np.stack([s.board for s in states]), to_move=[s.to_move for s in states],
+                                      last=[-1 if s.last is None else s.last[0] * size + s.last[1] for s in states],
+                                      win_length=win)
+    eng = az.Engine(board=size, win_length=win, games=n, sims=sims, c_puct=2.0)
+    results = {}
+    for rounded, dt in ((False, torch.float64), (True, torch.float32)):
+        fn = make_eval(rounded)
+        eng.search_begin(batch.x, batch.o, batch.to_move, batch.last)
+        pol = torch.full((n, A), 1.0 / A, device="cuda")
+        eng.root_expand(pol)
+        for _ in range(sims):
+            eng.select()
+            x, o, tm, last, kind = eng.leaf_states()
+            cells = _e.unpack_boards(x, o, size).view(n, size, size).cpu().numpy()
+            tm_h, last_h, kind_h = tm.cpu().numpy(), last.cpu().numpy(), kind.cpu().numpy()
+            val = np.zeros(n, dtype=np.float64)
+            for i in np.flatnonzero(kind_h == 0):
+                la = None if last_h[i] < 0 else (int(last_h[i]) // size, int(last_h[i]) % size)
+                val[i] = fn(gomoku.State.from_board(cells[i], int(tm_h[i]), win, la))[1]
+            eng.expand_backup(pol, torch.from_numpy(val).to("cuda", dt))
+        got = eng.root_visits().cpu().numpy()
+        for i, s in enumerate(states):
+            ref = omcts.Search(fn, sims, 2.0).run(s, 1.0, forced_action=s.legal_actions()[0])
+            assert np.array_equal(got[i].reshape(size, size), ref.visits), (rounded, i)
+        results[rounded] = got
+    assert not np.array_equal(results[False], results[True])       # the test is sensitive to the rounding
+    # and the facade's hook path takes the float64 route
+    sym = {0: None, 1: "X", 2: "O"}
+    gs = []
+    for s in states:
+        g = az.Gomoku(size, win)
+        g.board = [[sym[int(v)] for v in row] for row in s.board]
+        g.current_player = sym[s.to_move]
+        g.last_action = s.last
+        gs.append(g)
+
+    def ref_fn(game):
+        b, tm = synth._cells_of_reference(game)
+        return make_eval(False)(gomoku.State.from_board(b, tm, win))
+    _, _, visits = az.MCTS(ref_fn, sims, 2.0).run_batch(gs, 1.0)
+    assert np.array_equal(visits, results[False])
+    eng.close()

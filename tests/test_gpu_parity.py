@@ -377,9 +377,9 @@ def test_fused_search_matches_oracle_with_engine_net(az, size, win, sims, n, dty
 
 
 @pytest.mark.parametrize("size,win,sims,n,spots", [
-    (15, 5, 800, 2048, (0, 311, 777, 1290, 1801, 2047)),       # config 3, one GPU's share
-    (9, 5, 400, 4096, (0, 613, 1777, 2890, 3501, 4095)),       # config 2
-    (19, 5, 1600, 50, (0, 23, 49)),                            # config 5's search shape (one GPU's 50 arena games)
+    (15, 5, 800, 2048, tuple(range(0, 2048, 32))),              # config 3, one GPU's share: 64 roots
+    (9, 5, 400, 4096, tuple(range(0, 4096, 64))),               # config 2: 64 roots
+    (19, 5, 1600, 50, tuple(range(0, 50, 3))),                  # config 5's search shape (one GPU's 50 arena games): 17 roots
 ], ids=["config3", "config2", "config5"])
 def test_full_size_search_properties_and_spot_parity(az, size, win, sims, n, spots):
     """BASELINE configs at their full per-GPU sizes (config 3: 2048 concurrent 15x15 games x 800 simulations; config 2:
@@ -410,8 +410,9 @@ def test_full_size_search_properties_and_spot_parity(az, size, win, sims, n, spo
     assert c["path_length"] >= c["simulations"]                       # at least the root edge per simulation
 
     def evaluator(state):
-        _, pol, val = eng.net_forward(torch.from_numpy(state.planes()).unsqueeze(0).cuda())
-        return pol[0].cpu().numpy().reshape(size, size), float(val[0].item())
+        out = torch.cat([t.reshape(-1) for t in eng.net_forward(torch.from_numpy(state.planes()).unsqueeze(0).cuda())[1:]])
+        out = out.cpu().numpy()                                       # one device-to-host copy per leaf
+        return out[:-1].reshape(size, size), float(out[-1])
 
     for i in spots:
         ref = omcts.Search(evaluator, sims, 2.0).run(states[i], 1.0, forced_action=states[i].legal_actions()[0])
@@ -532,9 +533,12 @@ def test_selfplay_games_are_legal_and_labelled(az):
 
 def test_virtual_loss_throughput_mode(az):
     """leaves_per_step = K > 1 (virtual loss) is a THROUGHPUT mode, not a parity mode: it must keep the
-    simulation budget, build a consistent tree and stay close to the exact search's visit distribution."""
-    size, win, sims, n = 15, 5, 400, 32
-    params = onet.synthetic_stem_params(size, seed=100 + size, scale=2.0)
+    simulation budget, build a consistent tree and stay close to the exact search's visit distribution.  The net is made
+    peaked (weight scale 4: the exact search puts 44 % of its visits on one move on average) so that "close" is a real
+    statement -- measured on B200 (tools/vl_probe.py): mean L1 distance of the visit shares 0.13, same most-visited move
+    on 92 % of the roots; a broken virtual loss (e.g. paths not restored) lands far outside the bounds below."""
+    size, win, sims, n = 15, 5, 400, 64
+    params = onet.synthetic_stem_params(size, seed=100 + size, scale=4.0)
     states = []
     for i in range(n):
         s = gomoku.State(size, win)
@@ -553,12 +557,13 @@ def test_virtual_loss_throughput_mode(az):
         c = eng.counters()
         assert c["simulations"] == out[K].sum()
         eng.close()
+    boards = np.stack([s.board for s in states]).reshape(n, -1)
     assert (out[1].sum(1) == sims).all()
     assert (out[4].sum(1) <= sims).all() and out[4].sum() >= 0.97 * n * sims      # collisions idle a descent
+    assert not out[4][boards != 0].any()
     p1, p4 = out[1] / out[1].sum(1, keepdims=True), out[4] / out[4].sum(1, keepdims=True)
-    # sanity only: with a near-uniform random-init evaluator most visits are tie-breaks, so the two modes
-    # legitimately spread them differently; the shares must still overlap substantially
-    assert np.abs(p1 - p4).sum(1).mean() < 0.8                                     # mean L1 distance of visit shares
+    assert np.abs(p1 - p4).sum(1).mean() < 0.25                                   # mean L1 distance of visit shares
+    assert (p1.argmax(1) == p4.argmax(1)).mean() > 0.8                            # same most-visited move
 
 
 def test_virtual_loss_selfplay_games_are_legal(az):

@@ -233,6 +233,62 @@ def test_multi_gpu_plumbing_on_gloo_world2():
         assert wld == (3, 4, 0)
 
 
+def _gloo_exchange_worker(rank, world, port, q):
+    import torch.distributed as dist
+    sys.path.insert(0, ROOT)
+    import alphazero_piskvorky_b200 as az
+    from alphazero_piskvorky_b200 import dist as d
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    board, cap = 3, 6
+    ex = d.ExampleExchange(board, cap, "cpu")
+    ring = az.ReplayBuffer(capacity=12)
+    log = []
+    for step in range(3):
+        k = step & 1
+        ex.wait_slab(k)
+        planes, pi, z = ex.out_views(k)                     # the engine writes its raw positions straight into the slab
+        n = (2 + rank + step) % (cap + 1)                   # ragged counts, different on every rank and step
+        planes[:n] = 100.0 * step + 10.0 * rank + torch.arange(n, dtype=torch.float32).view(n, 1, 1, 1)
+        pi[:n] = 0.5 + planes[:n, 0]
+        z[:n] = rank - step
+        ex.exchange(k, n, ring=ring)
+        log.append(ex.counts(k))
+    got = ring.device_all()
+    q.put((rank, log, got[0][:, 0, 0, 0].tolist(), got[1][:, 1, 1].tolist(), got[2].tolist(), ex.bytes_per_step))
+    dist.destroy_process_group()
+
+
+def test_example_exchange_slabs_on_gloo_world2():
+    """fixed-capacity slabs of RAW positions with the count in the header, all-gathered every move step,
+    appended to every rank's ring in rank order -- identical rings everywhere, deque eviction order."""
+    import torch.multiprocessing as mp
+    from oracle import replay
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_gloo_exchange_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    results = [q.get(timeout=180) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    ref = replay.Fifo(12)
+    counts = []
+    for step in range(3):
+        row = []
+        for rank in range(2):
+            n = (2 + rank + step) % 7
+            row.append(n)
+            ref.extend([(100.0 * step + 10.0 * rank + i, rank - step) for i in range(n)])
+        counts.append(row)
+    for rank, log, p0, pi11, z, nbytes in results:
+        assert log == counts
+        assert p0 == [v for v, _ in ref.all()] and z == [zz for _, zz in ref.all()]
+        assert pi11 == [v + 0.5 for v, _ in ref.all()]
+        assert nbytes == 2 * 4 * (4 + 6 * (5 * 9 + 1))
+
+
 def test_checkpoint_and_buffer_formats(az, tmp_path, golden):
     """reference-format files.  A reference ``state_dict`` (.pt, key names of net.py:37-53)
     loads into the facade net unchanged; ModelLoader picks the newest file or creates a random-init one;
@@ -305,4 +361,8 @@ def test_bench_reference_arm_sampler_runs_on_cpu():
     sys.path.insert(0, ROOT)
     import bench
     v, cores, sample = bench.cpu_port_throughput(budget_s=1.0, procs=2, board=5, win=4, nsims=20)
-    assert v > 0 and cores == 2 and "2 processes" in sample and "5x5/20 sims" in sample
+    assert v > 0 and cores == 2 and "2 persistent processes" in sample and "5x5/20 sims" in sample
+    if bench.reference_available():            # the unmodified reference, staged by __graft_entry__.build()
+        rv, rcores, rsample = bench.cpu_throughput("reference", budget_s=1.0, procs=2, board=5, win=4, nsims=20)
+        assert rv > 0 and rcores == 2 and "UNMODIFIED reference" in rsample
+        assert v > rv                          # the port does not clone a board per legal child
