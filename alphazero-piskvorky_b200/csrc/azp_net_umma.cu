@@ -3,7 +3,8 @@
 // shared memory, tcgen05.mma (UMMA) implicit GEMM with fp32 accumulators in TMEM, fused epilogues.
 //
 // Activation layout in HBM ("padded NHWC", bf16): one row of C channels per padded board position;
-// a board occupies (B+1) row groups of P positions (P = 16 for B <= 15, 24 for B <= 23):
+// a board occupies (B+1) row groups of P positions (P = B+1 for B >= 7 -- one halo column per row group and nothing else;
+// 16 for the smallest boards, so that a 128-row tile never spans more than three boards):
 //     row(slot, r, c) = slot*(B+1)*P + (r+1)*P + (c+1)
 // Row group 0 and column 0 of every row group (and columns > B) are ZERO and double as the bottom /
 // right halo of the previous row group / board, so a 3x3 tap (dy,dx) is the constant row offset
@@ -1322,7 +1323,7 @@ __global__ void __launch_bounds__(C1_THREADS, 2) conv1_umma_kernel(const __grid_
         int b = 0;
         while (pos >= (unsigned)g.stride) { pos -= (unsigned)g.stride; b++; }
         int y, x;
-        if (g.P == 16) { y = (int)(pos >> 4); x = (int)(pos & 15u); } else { y = (int)(pos / 24u); x = (int)pos - y * 24; }
+        if (g.P == 16) { y = (int)(pos >> 4); x = (int)(pos & 15u); } else { y = (int)(pos / (unsigned)g.P); x = (int)pos - y * g.P; }
         if (y >= 1 && x >= 1 && x <= g.B && (int)sA + b < g.G) {
           const uint32_t* tb = tab + b * 3 * TR + (y - 1);
           uint32_t bits = 1u << 27;
@@ -1756,7 +1757,12 @@ int azp_umma_create(azp_engine* e) {
   e->ws->umma = ws;
   ws->tower = tower;
   ConvGeom& g = ws->g;
-  g.B = e->cfg.board; g.A = e->A; g.P = g.B <= 15 ? 16 : 24; g.stride = (g.B + 1) * g.P; g.G = e->slots;
+  // Row pitch: the halo column x = 0 of a row group is also the right-hand halo of the row group before it, so B+1
+  // positions per row group are enough: (B+1)^2 rows per board (100 at 9x9, 256 at 15x15, 400 at 19x19) instead of the
+  // 16 / 24-wide groups of the first layout (160 / 256 / 480): the tensor work wasted on halo rows falls from 49 % to
+  // 19 % at 9x9 and from 25 % to 10 % at 19x19.  UMMA descriptors and TMA boxes take any row offset, so nothing else
+  // depends on the pitch.  Boards below 7x7 keep a pitch of 16 (the conv1 producers stage at most 4 boards per tile).
+  g.B = e->cfg.board; g.A = e->A; g.P = g.B >= 7 ? g.B + 1 : 16; g.stride = (g.B + 1) * g.P; g.G = e->slots;
   ws->rows = (size_t)g.G * g.stride + 2 * g.P + TILE_M;        // tail halo + a partial last tile
   int st;
   const int PCh = tower ? 2 : 4, VCh = tower ? 1 : 2;          // head channels (policy, value)
