@@ -307,7 +307,25 @@ struct ConvArgs {
                                   // row-offset descriptors into it (2 = descriptors carry the swizzle base offset)
   int stage_bytes;                // bytes of one ring stage
   long long* clk;                 // bring-up: per-tile clock64 stamps of CTA 0 ([tile][16]) or null
+  // HEADS only: the FC layers (policy_fc, value_fc1 + ReLU + value_fc2 + tanh; net.py:64-70) run INSIDE this kernel as
+  // extra items of the accumulator rotation -- job = (board tile of 128 boards, 64-column slice of the policy outputs or
+  // the value head) -- once the head features of the board tile have been written by every CTA's epilogue
+  int fc_fused;                   // 0: the FC layers are a separate launch (fc_umma_kernel)
+  int fc_slices, fc_pk_chunks, fc_vk_chunks, fc_v_off, fc_A;
+  const float* fc_pbias; const float* fc_vbias; const float* fc_vw2; const float* fc_vb2;
+  float* fc_logits; float* fc_value;
+  unsigned int* feat_done;        // [board tiles] epilogue -> FC producer: one count per (conv tile touching it, lane quarter)
+  unsigned int* fc_done;          // [board tiles] FC epilogue -> consumers of the logits / values: one count per (job, lane quarter)
 };
+
+constexpr int FC_FUSED_STAGE_BYTES = TILE_M * 128 + 64 * 128;      // A: 128 boards x 64 K, B: 64 outputs x 64 K (bf16)
+constexpr int FC_MAX_BOARD_TILES = 512;                            // 65535 leaf rows / 128
+
+__device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
 
 __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&v)[16]) {
   asm volatile(
@@ -357,6 +375,9 @@ template <int CIN, int COUT, int STAGES, bool HEADS, bool BITS>
 __global__ void __launch_bounds__(BITS ? CONV_THREADS_BITS : (HEADS ? CONV_THREADS : CONV_THREADS_EPI2), 1) conv_umma_kernel(const __grid_constant__ CUtensorMap map_act,
                                                                     const __grid_constant__ CUtensorMap map_w,
                                                                     const __grid_constant__ CUtensorMap map_hw,
+                                                                    const __grid_constant__ CUtensorMap map_feat,
+                                                                    const __grid_constant__ CUtensorMap map_wp,
+                                                                    const __grid_constant__ CUtensorMap map_wv,
                                                                     const ConvArgs args) {
   using S = ConvSmem<CIN, COUT, STAGES, HEADS>;
   constexpr int ROWB = S::ROWB;
@@ -437,6 +458,29 @@ __global__ void __launch_bounds__(BITS ? CONV_THREADS_BITS : (HEADS ? CONV_THREA
   const long long row_begin = (long long)slot0 * g.stride;
   const long long rows_total = (long long)count * g.stride;
   const int n_tiles = (int)((rows_total + TILE_M - 1) / TILE_M);
+  // ---- work list of this CTA: its conv tiles (t = blockIdx.x + k * gridDim.x) and then, with the FC layers fused in, its
+  //      share of the FC jobs j = (board tile, slice); the jobs go to the CTAs with the FEWEST conv tiles first
+  const int n_cta = (int)gridDim.x, cta = (int)blockIdx.x;
+  const int n_conv = cta < n_tiles ? (n_tiles - 1 - cta) / n_cta + 1 : 0;
+  const bool fc_on = HEADS && !BITS && args.fc_fused != 0;
+  const int fc_per_bt = args.fc_slices + 1;                       // policy slices + the value job
+  const int fc_jobs = fc_on ? ((count + TILE_M - 1) / TILE_M) * fc_per_bt : 0;
+  const int fc_first = n_cta - 1 - cta;
+  const int n_fc = fc_first < fc_jobs ? (fc_jobs - 1 - fc_first) / n_cta + 1 : 0;
+  const int n_items = n_conv + n_fc;
+  if (!BITS && !HEADS && blockIdx.x == 0 && args.feat_done) {
+    // conv2 runs between two conv3 launches: it resets the counters of the fused FC jobs (every consumer of the previous
+    // evaluation has finished -- this kernel is past its griddepcontrol.wait)
+    for (int i = threadIdx.x; i < FC_MAX_BOARD_TILES; i += blockDim.x) { args.feat_done[i] = 0u; args.fc_done[i] = 0u; }
+  }
+  // item tl of the work list: conv tile (returns true, sets t) or FC job (false, sets bt / sl; sl == fc_slices: value head)
+  auto item_is_conv = [&](int tl, int& t, int& bt, int& sl) -> bool {
+    if (tl < n_conv) { t = cta + tl * n_cta; return true; }
+    const int j = fc_first + (tl - n_conv) * n_cta;
+    bt = j / fc_per_bt; sl = j - bt * fc_per_bt; t = 0;
+    return false;
+  };
+  auto fc_chunks = [&](int sl) -> int { return sl == args.fc_slices ? args.fc_vk_chunks : args.fc_pk_chunks; };
 
   if (warp == 0) {
     // ===== TMA producer =====
@@ -445,14 +489,44 @@ __global__ void __launch_bounds__(BITS ? CONV_THREADS_BITS : (HEADS ? CONV_THREA
       if (!BITS && args.single) {
         // one box of 128+2P+2 rows per tile, starting one row above/left of the dy=-1,dx=-1 window
         const uint32_t bytes = (uint32_t)(args.stage_rows + 2) * ROWB;
-        for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, it++) {
-          const int st = it % STAGES;
-          if (AZP_CLKPTR(args.clk) && blockIdx.x == 0) AZP_CLKPTR(args.clk)[it * 16 + 0] = clock64();
-          mbar_wait(&empty[st], ((it / STAGES) & 1) ^ 1);
-          if (AZP_CLKPTR(args.clk) && blockIdx.x == 0) AZP_CLKPTR(args.clk)[it * 16 + 1] = clock64();
-          mbar_expect_tx(&full[st], bytes);
-          const long long row = row_begin + (long long)t * TILE_M - g.P - 1;
-          tma_load_2d(s_a + (size_t)st * stage_bytes, &map_act, &full[st], 0, (int)row);
+        for (int tl = 0; tl < n_items; tl++) {
+          int t, bt, sl;
+          if (item_is_conv(tl, t, bt, sl)) {
+            const int st = it % STAGES;
+            if (AZP_CLKPTR(args.clk) && blockIdx.x == 0) AZP_CLKPTR(args.clk)[it * 16 + 0] = clock64();
+            mbar_wait(&empty[st], ((it / STAGES) & 1) ^ 1);
+            if (AZP_CLKPTR(args.clk) && blockIdx.x == 0) AZP_CLKPTR(args.clk)[it * 16 + 1] = clock64();
+            mbar_expect_tx(&full[st], bytes);
+            const long long row = row_begin + (long long)t * TILE_M - g.P - 1;
+            tma_load_2d(s_a + (size_t)st * stage_bytes, &map_act, &full[st], 0, (int)row);
+            it++;
+            continue;
+          }
+          // FC job: its A operand = the head features of boards [128 bt, 128 bt + 128), written by the epilogues of every
+          // CTA whose conv tiles touch those boards -- 4 counts (lane quarters) per such tile
+          const int nb = min(TILE_M, count - bt * TILE_M);
+          const long long lo = (long long)bt * TILE_M * g.stride, hi = ((long long)bt * TILE_M + nb) * g.stride - 1;
+          const int t_lo = (int)(lo / TILE_M), t_hi = min(n_tiles - 1, (int)(hi / TILE_M));
+          const unsigned target = 4u * (unsigned)(t_hi - t_lo + 1);
+          {
+            const long long t0 = clock64();
+            while (ld_acquire_u32(args.feat_done + bt) < target) {
+              __nanosleep(64);
+              if (clock64() - t0 > 4000000000ll) __trap();
+            }
+          }
+          asm volatile("fence.proxy.async;" ::: "memory");         // generic-proxy stores (acquired above) -> TMA reads
+          const bool is_value = sl == args.fc_slices;
+          const CUtensorMap* mw = is_value ? &map_wv : &map_wp;
+          const int k_off = is_value ? args.fc_v_off : 0, kcs = fc_chunks(sl);
+          for (int kc = 0; kc < kcs; kc++, it++) {
+            const int st = it % STAGES;
+            mbar_wait(&empty[st], ((it / STAGES) & 1) ^ 1);
+            mbar_expect_tx(&full[st], (uint32_t)FC_FUSED_STAGE_BYTES);
+            uint8_t* sa = s_a + (size_t)st * stage_bytes;
+            tma_load_2d(sa, &map_feat, &full[st], k_off + kc * 64, bt * TILE_M);
+            tma_load_2d(sa + TILE_M * 128, mw, &full[st], kc * 64, is_value ? 0 : sl * 64);     // rows past the matrix: zero fill
+          }
         }
       }
       for (int t = blockIdx.x; !BITS && !args.single && t < n_tiles; t += gridDim.x) {
@@ -568,9 +642,11 @@ __global__ void __launch_bounds__(BITS ? CONV_THREADS_BITS : (HEADS ? CONV_THREA
       mbar_wait(wbar, 0);
       if (AZP_CLKPTR(args.clk) && blockIdx.x == 0 && warp == 1) AZP_CLKPTR(args.clk)[3 * 16 + 14] = wall_ns();           // weights resident
       tc_fence_after();
-      int it = 0, tl = 0;
-      for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, tl++) {
-        if ((tl & 1) != my_parity) { it += args.single ? 1 : 3; continue; }
+      int it = 0;
+      for (int tl = 0; tl < n_items; tl++) {
+        int t, bt, sl;
+        const bool is_conv = item_is_conv(tl, t, bt, sl);
+        if ((tl & 1) != my_parity) { it += is_conv ? (args.single ? 1 : 3) : fc_chunks(sl); continue; }
         const int acc = tl % NACC;
         const uint32_t acc_ph = (tl / NACC) & 1;
         if (AZP_CLKPTR(args.clk) && blockIdx.x == 0) AZP_CLKPTR(args.clk)[tl * 16 + 2] = clock64();
@@ -579,6 +655,26 @@ __global__ void __launch_bounds__(BITS ? CONV_THREADS_BITS : (HEADS ? CONV_THREA
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * COUT);
         uint32_t accumulate = 0;
+        if (!is_conv) {
+          // FC job: [128 boards x 64 K] x [64 outputs x 64 K]^T per chunk into the first 64 columns of the accumulator --
+          // the instruction sequence of fc_umma_kernel, so both give bit-identical logits / values
+          const uint32_t idesc_fc = umma_idesc(64);
+          const int kcs = fc_chunks(sl);
+          for (int kc = 0; kc < kcs; kc++, it++) {
+            const int st = it % STAGES;
+            mbar_wait(&full[st], (it / STAGES) & 1);
+            tc_fence_after();
+            const uint32_t a_addr = a_base + (uint32_t)st * (uint32_t)stage_bytes, b_addr = a_addr + TILE_M * 128;
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+              umma_bf16(d_tmem, umma_desc(a_addr + k * 32, 128), umma_desc(b_addr + k * 32, 128), idesc_fc, accumulate);
+              accumulate = 1;
+            }
+            umma_commit(&empty[st]);
+          }
+          umma_commit(&tfull[acc]);
+          continue;
+        }
         if (args.single) {
           const int st = it % STAGES;
           mbar_wait(&full[st], (it / STAGES) & 1);
@@ -652,9 +748,16 @@ __global__ void __launch_bounds__(BITS ? CONV_THREADS_BITS : (HEADS ? CONV_THREA
       };
       mbar_wait(wbar, 0);
       tc_fence_after();
-      int tl = 0;
-      for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, tl++) {
-        issue_head(tl);
+      for (int tl = 0; tl < n_items; tl++) {
+        if (tl < n_conv) {
+          issue_head(tl);
+        } else {
+          // FC job: no head GEMM, but the barrier pair keeps its one-phase-per-item rhythm (the epilogue has read the
+          // job's outputs out of the accumulator when its eight warps have arrived)
+          const int b = tl % NACC;
+          mbar_wait(&act_full[b], (uint32_t)((tl / NACC) & 1));
+          mbar_arrive(&head_full[b]);
+        }
         if (AZP_CLKPTR(args.clk) && blockIdx.x == 0) AZP_CLKPTR(args.clk)[tl * 16 + 6] = clock64();
       }
     }
@@ -665,11 +768,19 @@ __global__ void __launch_bounds__(BITS ? CONV_THREADS_BITS : (HEADS ? CONV_THREA
     const int q = warp & 3;
     const int h = (warp - (egroup ? 12 : 2)) >> 2;
     const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
-    // head outputs of local tile j (global tile tj): +bias, ReLU, scatter to feat[slot][j][pixel]
-    auto write_heads = [&](int tj, int j) {
+    // head outputs of item j of the work list (conv tile tj): +bias, ReLU, scatter to feat[slot][j][pixel]; an FC job has
+    // no head outputs -- its accumulator is simply handed back
+    auto write_heads = [&](int j) {
       const int b = j % NACC;
       mbar_wait(&head_full[b], (uint32_t)((j / NACC) & 1));
       tc_fence_after();
+      if (j >= n_conv) {
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tempty[b]);
+        return;
+      }
+      const int tj = cta + j * n_cta;
       const uint32_t acc_base = tmem_base + lane_addr + (uint32_t)(b * COUT);
       uint32_t r[8];
       tmem_ld8(acc_base + 32, r);
@@ -694,13 +805,75 @@ __global__ void __launch_bounds__(BITS ? CONV_THREADS_BITS : (HEADS ? CONV_THREA
             f[j < args.PC ? j * g.A : args.PKp + (j - args.PC) * g.A] =
                 __float2bfloat16(fmaxf(__uint_as_float(r[j]) + s_bias[COUT + j], 0.f));
       }
+      if (fc_on) {
+        // release: this lane quarter's features of the tile are written -> one count for every board tile the conv tile
+        // touches (the FC jobs' producers acquire the sum)
+        __threadfence();
+        __syncwarp();
+        if (lane == 0) {
+          const unsigned R0 = (unsigned)row_begin + (unsigned)tj * TILE_M;
+          const int s_first = (int)(R0 / (unsigned)g.stride);
+          const int s_last = min(count - 1, (int)((R0 + TILE_M - 1) / (unsigned)g.stride));
+          atomicAdd(args.feat_done + (s_first >> 7), 1u);
+          if ((s_last >> 7) != (s_first >> 7)) atomicAdd(args.feat_done + (s_last >> 7), 1u);
+        }
+      }
     };
-    int tl = 0, t_prev = 0;
-    for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, tl++) {
+    bool heads_pending = false;           // write_heads(tl - 1) still to be done when item tl starts
+    for (int tl = 0; tl < n_items; tl++) {
       if (EGROUPS == 2 && (tl & 1) != egroup) continue;
+      int t, fbt, fsl;
+      const bool is_conv = item_is_conv(tl, t, fbt, fsl);
       const int acc = tl % NACC;
       const uint32_t acc_ph = (tl / NACC) & 1;
       const bool stamp = AZP_CLKPTR(args.clk) && blockIdx.x == 0 && (warp == 2 || warp == 12) && lane == 0;
+      if (HEADS && !is_conv) {
+        // ---- FC job.  The features it waits for may be the ones THIS warp still has to write (the previous item's
+        //      heads), so they go out first -- waiting for the job's accumulator before that could never end.
+        if (heads_pending && h == 0) write_heads(tl - 1);
+        heads_pending = false;
+        mbar_wait(&tfull[acc], acc_ph);
+        tc_fence_after();
+        if (h == 0) {
+          const bool is_value = fsl == args.fc_slices;
+          const int row = fbt * TILE_M + q * 32 + lane;            // board = row of the evaluated batch
+          const uint32_t fc_addr = tmem_base + lane_addr + (uint32_t)(acc * COUT);
+          float sp[2] = {0.f, 0.f};
+#pragma unroll
+          for (int hf = 0; hf < 2; hf++) {
+            uint32_t r[32];
+            tmem_ld32(fc_addr + hf * 32, r);
+            if (!is_value) {
+              // raw logits (+bias); the softmax over all cells happens in the consumer (controller.py:49)
+              if (row < count) {
+                float* out = args.fc_logits + (size_t)row * args.fc_A;
+#pragma unroll
+                for (int i = 0; i < 32; i++) {
+                  const int c = fsl * 64 + hf * 32 + i;
+                  if (c < args.fc_A) out[c] = __uint_as_float(r[i]) + __ldg(args.fc_pbias + c);
+                }
+              }
+            } else {
+              // value_fc1 + ReLU, value_fc2: the same two 32-column partial sums, in the same order, as fc_umma_kernel
+#pragma unroll
+              for (int i = 0; i < 32; i++)
+                sp[hf] = fmaf(fmaxf(__uint_as_float(r[i]) + __ldg(args.fc_vbias + hf * 32 + i), 0.f),
+                              __ldg(args.fc_vw2 + hf * 32 + i), sp[hf]);
+            }
+          }
+          if (is_value && row < count) args.fc_value[row] = tanhf((sp[0] + sp[1]) + __ldg(args.fc_vb2));
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&act_full[acc]);
+        if (h == 0) {
+          __threadfence();                                         // release: this lane quarter's outputs of the job
+          __syncwarp();
+          if (lane == 0) atomicAdd(args.fc_done + fbt, 1u);
+        }
+        heads_pending = true;
+        continue;
+      }
       if (stamp) AZP_CLKPTR(args.clk)[tl * 16 + 8] = clock64();
       mbar_wait(&tfull[acc], acc_ph);
       if (stamp) AZP_CLKPTR(args.clk)[tl * 16 + 9] = clock64();
@@ -715,7 +888,8 @@ __global__ void __launch_bounds__(BITS ? CONV_THREADS_BITS : (HEADS ? CONV_THREA
         tc_fence_before();
         __syncwarp();
         if (lane == 0) { if (HEADS) mbar_arrive(&act_full[acc]); else mbar_arrive(&tempty[acc]); }
-        if (HEADS && tl > 0 && h == 0) write_heads(t_prev, tl - 1);
+        if (HEADS && heads_pending && h == 0) write_heads(tl - 1);
+        heads_pending = true;
       } else if (!HEADS) {
         // bias + ReLU + halo zero in registers, the accumulator is released at once.  Each lane then owns 64 contiguous
         // bytes of its output row and writes them as two 256-bit stores (st.global.v8: full 32-byte sectors).  16-byte
@@ -747,7 +921,6 @@ __global__ void __launch_bounds__(BITS ? CONV_THREADS_BITS : (HEADS ? CONV_THREA
                            "r"(packed[8 * v + 3]), "r"(packed[8 * v + 4]), "r"(packed[8 * v + 5]), "r"(packed[8 * v + 6]),
                            "r"(packed[8 * v + 7]) : "memory");
           if (stamp) AZP_CLKPTR(args.clk)[tl * 16 + 11] = clock64();
-          t_prev = t;
           continue;
         }
         uint8_t* obuf = s_out + egroup * (TILE_M * 128);
@@ -791,13 +964,13 @@ __global__ void __launch_bounds__(BITS ? CONV_THREADS_BITS : (HEADS ? CONV_THREA
         if (lane == 0) mbar_arrive(&act_full[acc]);
         if (stamp) AZP_CLKPTR(args.clk)[tl * 16 + 11] = clock64();
         // the PREVIOUS tile's head GEMM was queued behind this tile's conv MMAs: it has retired by now
-        if (tl > 0 && h == 0) write_heads(t_prev, tl - 1);
+        if (heads_pending && h == 0) write_heads(tl - 1);
+        heads_pending = true;
         if (stamp) AZP_CLKPTR(args.clk)[tl * 16 + 12] = clock64();
       }
-      t_prev = t;
     }
     if (!HEADS && h == 0 && q == 0 && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
-    if (HEADS && tl > 0 && h == 0) write_heads(t_prev, tl - 1);
+    if (HEADS && heads_pending && h == 0) write_heads(n_items - 1);
   }
   tc_fence_before();
   __syncthreads();
@@ -1690,6 +1863,9 @@ struct UmmaWorkspace {
   int sms = 148;
   int smem2 = 0, smem3 = 0;
   int pair = 0, smem3p = 0, pair_clusters = 0;   // conv3 on CTA pairs (cta_group::2): AZP_CONV3_PAIR=1 (default 0)
+  int fuse_fc = 1;                     // FC layers inside the conv3 kernel (AZP_FUSE_FC=0: separate fc_umma_kernel launch)
+  unsigned int* feat_done = nullptr;   // [FC_MAX_BOARD_TILES] see ConvArgs
+  unsigned int* fc_done = nullptr;     // [FC_MAX_BOARD_TILES]
 };
 struct UmmaWeights {
   // tower
@@ -1737,10 +1913,16 @@ inline int bringup_debug_bits() {
 #endif
 }
 
+// bytes of one activation stage: the TMA box of a conv tile, or (conv3 with the FC layers fused in) an FC operand pair
+inline int conv_stage_bytes(int stage_rows, int rowb, bool fc_fused) {
+  const int conv = (stage_rows + 2 + 7) / 8 * 8 * rowb;
+  return fc_fused && conv < FC_FUSED_STAGE_BYTES ? FC_FUSED_STAGE_BYTES : conv;
+}
+
 template <int CIN, int COUT, int STAGES, bool HEADS, bool BITS>
-int conv_smem_bytes(int stage_rows) {
+int conv_smem_bytes(int stage_rows, bool fc_fused = false) {
   using S = ConvSmem<CIN, COUT, STAGES, HEADS>;
-  return 1024 + S::W_BYTES + STAGES * ((stage_rows + 2 + 7) / 8 * 8) * S::ROWB + (HEADS ? (COUT / 64) * HEAD_N * 128 : 0) +
+  return 1024 + S::W_BYTES + STAGES * conv_stage_bytes(stage_rows, S::ROWB, fc_fused) + (HEADS ? (COUT / 64) * HEAD_N * 128 : 0) +
          (HEADS ? 0 : 2 * TILE_M * 128) + (2 * STAGES + 17) * 8 + 16 + (COUT + 8) * 4 + (BITS ? (72 * 32 + 32) * 4 + 2 * CODES * 2 : 0) + 64;
 }
 
@@ -1814,8 +1996,18 @@ int azp_umma_create(azp_engine* e) {
   cudaDeviceProp prop;
   AZP_CUDA(e, cudaGetDeviceProperties(&prop, e->cfg.device));
   ws->sms = prop.multiProcessorCount;
+  { const char* v = getenv("AZP_FUSE_FC"); ws->fuse_fc = v ? atoi(v) : 1; }
+  if (ws->single != 1) ws->fuse_fc = 0;
+  if ((st = e->alloc(&ws->feat_done, (size_t)FC_MAX_BOARD_TILES))) return st;
+  if ((st = e->alloc(&ws->fc_done, (size_t)FC_MAX_BOARD_TILES))) return st;
+  AZP_CUDA(e, cudaMemset(ws->feat_done, 0, FC_MAX_BOARD_TILES * sizeof(unsigned int)));
+  AZP_CUDA(e, cudaMemset(ws->fc_done, 0, FC_MAX_BOARD_TILES * sizeof(unsigned int)));
   ws->smem2 = conv_smem_bytes<32, 64, STAGES2, false, true>(stage_rows);
-  ws->smem3 = conv_smem_bytes<64, 128, STAGES3, true, false>(stage_rows);
+  ws->smem3 = conv_smem_bytes<64, 128, STAGES3, true, false>(stage_rows, ws->fuse_fc != 0);
+  if (ws->smem3 > (int)prop.sharedMemPerBlockOptin) {       // cannot happen for boards <= 23; never launch an oversized kernel
+    ws->fuse_fc = 0;
+    ws->smem3 = conv_smem_bytes<64, 128, STAGES3, true, false>(stage_rows, false);
+  }
   AZP_CUDA(e, cudaFuncSetAttribute(conv_umma_kernel<32, 64, STAGES2, false, false>,
                                    cudaFuncAttributeMaxDynamicSharedMemorySize, ws->smem2));
   AZP_CUDA(e, cudaFuncSetAttribute(conv_umma_kernel<32, 64, STAGES2, false, true>,
@@ -2191,14 +2383,17 @@ static int run_trunk(azp_engine* e, NetWeights* W, const int32_t* count_dev, int
   a2.stage_bytes = (a2.single ? (a2.stage_rows + 2 + 7) / 8 * 8 : a2.stage_rows) * 64;
   a2.lx = e->tv.leaf_x; a2.lo = e->tv.leaf_o; a2.ltm = e->tv.leaf_tm; a2.llast = e->tv.leaf_last; a2.NW = e->NW;
   a2.w1 = U->w1_tab; a2.b1 = U->b1;
+  a2.fc_fused = 0; a2.fc_slices = 0; a2.fc_pk_chunks = 0; a2.fc_vk_chunks = 0; a2.fc_v_off = 0; a2.fc_A = g.A;
+  a2.fc_pbias = nullptr; a2.fc_vbias = nullptr; a2.fc_vw2 = nullptr; a2.fc_vb2 = nullptr; a2.fc_logits = nullptr; a2.fc_value = nullptr;
+  a2.feat_done = ws->feat_done; a2.fc_done = ws->fc_done;       // conv2 resets them for the conv3 launch that follows
   a2.debug = bringup_debug_bits();
   azp_prof_begin(e, AZP_PROF_CONV2, count_dev, count_host, s);
   if (from_bits)
     azp_launch(conv_umma_kernel<32, 64, STAGES2, false, true>, grid, CONV_THREADS_BITS, ws->smem2, s, true, ws->map_act1,
-               U->map_w2, ws->map_act2_out, a2);
+               U->map_w2, ws->map_act2_out, ws->map_feat, U->map_wp, U->map_wv, a2);
   else
     azp_launch(conv_umma_kernel<32, 64, STAGES2, false, false>, grid, CONV_THREADS_EPI2, ws->smem2, s, true,
-               a2.single ? ws->map_act1_s : ws->map_act1, U->map_w2, ws->map_act2_out, a2);
+               a2.single ? ws->map_act1_s : ws->map_act1, U->map_w2, ws->map_act2_out, ws->map_feat, U->map_wp, U->map_wv, a2);
   azp_count_launch();
   azp_prof_end(e, AZP_PROF_CONV2, s);
   ConvArgs a3 = a2;
@@ -2206,7 +2401,18 @@ static int run_trunk(azp_engine* e, NetWeights* W, const int32_t* count_dev, int
   a3.NJ = W->PC + W->VC; a3.PC = W->PC; a3.PKp = ws->PKp; a3.FK = ws->FK;
   a3.single = ws->single;
   a3.clk = bringup_clk(ws, 1);
-  a3.stage_bytes = (a3.single ? (a3.stage_rows + 2 + 7) / 8 * 8 : a3.stage_rows) * 128;
+  // The FC layers ride inside conv3 for the leaf batches the search evaluates from the front (raw logits into the engine's
+  // policy buffer); azp_net_forward (softmax wanted, caller's buffers), the arena's back-filled batch and the CTA-pair
+  // variant keep the separate FC launch.  Both run the same UMMA sequence: bit-identical outputs.
+  const bool fused = ws->fuse_fc && !ws->pair && a3.single == 1 && !out_by_index && !back && policy && value;
+  a3.stage_bytes = a3.single ? conv_stage_bytes(a3.stage_rows, 128, ws->fuse_fc != 0) : a3.stage_rows * 128;
+  if (fused) {
+    a3.fc_fused = 1;
+    a3.fc_slices = (g.A + FC_N - 1) / FC_N; a3.fc_pk_chunks = (ws->PKp + 63) / 64; a3.fc_vk_chunks = (ws->VKp + 63) / 64;
+    a3.fc_v_off = ws->PKp; a3.fc_A = g.A;
+    a3.fc_pbias = W->pfc_b; a3.fc_vbias = W->vfc1_b; a3.fc_vw2 = W->vfc2_w; a3.fc_vb2 = W->vfc2_b;
+    a3.fc_logits = policy; a3.fc_value = value;
+  }
   e->prof_flops_per_board = 2.0 * 9.0 * 64 * 128 * g.A;
   azp_prof_begin(e, AZP_PROF_DOMINANT, count_dev, count_host, s);
   if (ws->pair) {
@@ -2224,10 +2430,11 @@ static int run_trunk(azp_engine* e, NetWeights* W, const int32_t* count_dev, int
     cudaLaunchKernelEx(&cfg, conv3_pair_kernel, ws->map_act2_s, U->map_w3h, U->map_hwh, a3);
   } else {
     azp_launch(conv_umma_kernel<64, 128, STAGES3, true, false>, grid, CONV_THREADS, ws->smem3, s, true,
-               a3.single ? ws->map_act2_s : ws->map_act2, U->map_w3, U->map_hw, a3);
+               a3.single ? ws->map_act2_s : ws->map_act2, U->map_w3, U->map_hw, ws->map_feat, U->map_wp, U->map_wv, a3);
   }
   azp_count_launch();
   azp_prof_end(e, AZP_PROF_DOMINANT, s);
+  if (fused) return azp_check_launch();
   return launch_fc(e, W, count_dev, count_host, back, logits, policy, value, out_by_index, s);
 }
 
