@@ -9,7 +9,8 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libazp_b200.so")
+# AZP_B200_LIB selects another build of the same library (the bring-up build with clock stamps: make BRINGUP=1 OUT=...)
+LIB_PATH = os.environ.get("AZP_B200_LIB") or os.path.join(HERE, "libazp_b200.so")
 
 OK, ERR_INVALID_ARG, ERR_CUDA, ERR_INVALID_MOVE, ERR_CAPACITY, ERR_UNSUPPORTED, ERR_NO_WEIGHTS = range(7)
 MORE = 100

@@ -277,6 +277,189 @@ __global__ void __launch_bounds__(256) conv1_planes_kernel(ConvGeom g, int n, co
   }
 }
 
+
+// ---- conv1 from bitboards, merged-table SIMT kernel (AZP_CONV1=table) ---------------------------------------------------------
+// Inputs are 0/1 planes (games.py:86-129) and plane 3 is all zero, so for a position (r, c) and a kernel row ky the
+// contribution of BOTH stone planes is a function of six bits -- the side to move's and the opponent's stones in columns
+// c-1, c, c+1 of board row r+ky-1 -- and is read from a table:
+//     tab2[ky][own3 | opp3 << 3][32]  =  (sum of w[co][0][ky][kx] over the set own bits, kx ascending)
+//                                      + (the same for plane 1)                                   (24 KB of fp32)
+//     act1[r, c][co] = relu( ((b[co] + tab2[0][.]) + tab2[1][.]) + tab2[2][.]  (+ w[co][2][ky][kx] of the last move, if it
+//                            lies in the 3x3 window: at most nine positions of a board) )
+// Three 128-byte table rows per position instead of the nine pattern rows of the first SIMT kernel (which was bound by
+// exactly that shared-memory traffic), no multiplies, fp32 exact up to the summation order; conv1_table_planes_kernel adds
+// the same terms in the same order, so the leaf path and azp_net_forward agree bit for bit on 0/1 planes.
+// Work item = (interior position, 8 output channels): four threads per position.  Two neighbouring positions read
+// different 64-byte halves of their table rows in each of the two 128-bit loads (thread (p, cg) takes 16-byte chunk
+// cg + 4*((p+k)&1) in load k), so the eight threads of a quarter warp always cover all 32 banks; each thread ends up with
+// channels [4cg, 4cg+4) and [16+4cg, 16+4cg+4) and writes two 8-byte halves of the position's 64-byte bf16 row.
+// Halo rows are never written: they were zeroed when the buffer was allocated and nothing else touches them.
+constexpr int C1T_TAB_FLOATS = 3 * 64 * 32;
+
+constexpr int C1T_WARPS = 8;
+constexpr int C1T_CODES = (AZP_MAX_BOARD + 2) * AZP_MAX_BOARD;      // per warp: [row r+1][c], rows 0 and B+1 stay zero
+
+// One WARP per board (a CTA-per-board version spent its time in the per-board chain global load -> barrier -> codes ->
+// barrier -> items with only four boards in flight per SM; here every warp runs that chain on its own, 32 boards per SM).
+template <int NWT>
+__global__ void __launch_bounds__(32 * C1T_WARPS, 4) conv1_table_kernel(ConvGeom g, const uint64_t* __restrict__ lx,
+                                                          const uint64_t* __restrict__ lo,
+                                                          const uint8_t* __restrict__ ltm,
+                                                          const int16_t* __restrict__ llast,
+                                                          const float* __restrict__ tab2 /*[3][64][32]*/,
+                                                          const float* __restrict__ lm /*[ky][kx][32]: plane 2*/,
+                                                          const float* __restrict__ bias,
+                                                          __nv_bfloat16* __restrict__ act1,
+                                                          const int32_t* __restrict__ count_dev, int count_host,
+                                                          int back) {
+  __shared__ __align__(16) float st[C1T_TAB_FLOATS];
+  __shared__ __align__(16) float slm[9 * 32];
+  __shared__ __align__(16) float sb[32];
+  __shared__ int16_t codes_all[C1T_WARPS][C1T_CODES];
+  __shared__ int16_t out_row[AZP_MAX_BOARD * AZP_MAX_BOARD];        // cell -> padded row (r+1)*P + (c+1): no division per item
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int a = threadIdx.x; a < g.A; a += blockDim.x) out_row[a] = (int16_t)((a / g.B + 1) * g.P + (a % g.B + 1));
+  for (int i = threadIdx.x; i < C1T_TAB_FLOATS / 4; i += blockDim.x)
+    reinterpret_cast<float4*>(st)[i] = reinterpret_cast<const float4*>(tab2)[i];
+  for (int i = threadIdx.x; i < 9 * 32; i += blockDim.x) slm[i] = lm[i];
+  if (threadIdx.x < 32) sb[threadIdx.x] = bias[threadIdx.x];
+  int16_t* codes = codes_all[warp];
+  for (int i = lane; i < g.B; i += 32) { codes[i] = 0; codes[(g.B + 1) * g.B + i] = 0; }
+  __syncthreads();
+  pdl_wait();                      // leaf batch / leaf count are written by the descent kernel before us
+  pdl_launch_dependents();
+  const int count = count_dev ? *count_dev : count_host;
+  const int cg = lane & 3;
+  // TWO warps per board (each builds the codes, each writes half of the positions): 32 resident warps per SM hide the
+  // dependent shared-memory loads of an item.  Board bi -> CTA bi % grid, warp pair (bi / grid) % 4.
+  const int half = warp & 1;
+  for (int bi = (warp >> 1) * gridDim.x + blockIdx.x; bi < count; bi += gridDim.x * (C1T_WARPS / 2)) {
+    const int slot = back ? g.G - 1 - bi : bi;
+    const bool xm = ltm[slot] == 1;
+    const int last = llast[slot];
+    // lanes 0..NW-1 hold the side to move's words, lanes NW..2NW-1 the opponent's: one coalesced load each
+    uint64_t word = 0;
+    if (lane < NWT) word = (xm ? lx : lo)[(size_t)slot * NWT + lane];
+    else if (lane < 2 * NWT) word = (xm ? lo : lx)[(size_t)slot * NWT + lane - NWT];
+    __syncwarp();                                            // the previous board's codes have been consumed
+    for (int a0 = 0; a0 < g.A; a0 += 32) {
+      const int a = a0 + lane;
+      const int c = a % g.B;
+      int code = 0;
+#pragma unroll
+      for (int kx = 0; kx < 3; kx++) {
+        const int aa = min(max(a + kx - 1, 0), g.A - 1);     // clamped: every lane takes part in the shuffles
+        const uint64_t wo = __shfl_sync(AZP_FULL, word, aa >> 6), wp = __shfl_sync(AZP_FULL, word, NWT + (aa >> 6));
+        const int cc = c + kx - 1;
+        if (a < g.A && cc >= 0 && cc < g.B) {
+          const int b0 = (int)((wo >> (aa & 63)) & 1), b1 = (int)((wp >> (aa & 63)) & 1);
+          code |= (b0 << kx) | (b1 << (3 + kx)) | ((aa == last ? 1 : 0) << (6 + kx));
+        }
+      }
+      if (a < g.A) codes[g.B + a] = (int16_t)code;
+    }
+    __syncwarp();
+    __nv_bfloat16* base = act1 + (size_t)slot * g.stride * 32;
+    const int a_half = (g.A + 1) / 2 & ~7;                   // warp 0 of the pair: cells [0, a_half), warp 1: the rest
+    const int a_lo = half ? a_half : 0, a_hi = half ? g.A : a_half;
+#pragma unroll 2
+    for (int item = a_lo * 4 + lane; item < a_hi * 4; item += 32) {
+      const int a = item >> 2;
+      const int p = a & 1;                                   // neighbouring positions take opposite chunk halves per load
+      const int ch0 = cg + 4 * p, ch1 = cg + 4 * (p ^ 1);    // 16-byte chunks = channels [4 ch, 4 ch + 4)
+      const int16_t* cs = codes + a;                         // codes of board rows r-1, r, r+1 (zero border rows)
+      const int c0 = cs[0], c1 = cs[g.B], c2 = cs[2 * g.B];
+      float4 u = reinterpret_cast<const float4*>(sb)[ch0], v = reinterpret_cast<const float4*>(sb)[ch1];
+#pragma unroll
+      for (int ky = 0; ky < 3; ky++) {
+        const int code = ky == 0 ? c0 : (ky == 1 ? c1 : c2);
+        const float4* row = reinterpret_cast<const float4*>(st + (ky * 64 + (code & 63)) * 32);
+        const float4 t0 = row[ch0], t1 = row[ch1];
+        u.x += t0.x; u.y += t0.y; u.z += t0.z; u.w += t0.w;
+        v.x += t1.x; v.y += t1.y; v.z += t1.z; v.w += t1.w;
+      }
+      if ((c0 | c1 | c2) >> 6) {                             // the last move lies in this position's 3x3 window
+#pragma unroll
+        for (int ky = 0; ky < 3; ky++) {
+          const int pat = (ky == 0 ? c0 : (ky == 1 ? c1 : c2)) >> 6;
+          if (!pat) continue;
+          const int kx = pat == 1 ? 0 : (pat == 2 ? 1 : 2);
+          const float4* row = reinterpret_cast<const float4*>(slm + (ky * 3 + kx) * 32);
+          const float4 t0 = row[ch0], t1 = row[ch1];
+          u.x += t0.x; u.y += t0.y; u.z += t0.z; u.w += t0.w;
+          v.x += t1.x; v.y += t1.y; v.z += t1.z; v.w += t1.w;
+        }
+      }
+      __nv_bfloat162 a0 = __floats2bfloat162_rn(fmaxf(u.x, 0.f), fmaxf(u.y, 0.f)), a1 = __floats2bfloat162_rn(fmaxf(u.z, 0.f), fmaxf(u.w, 0.f));
+      __nv_bfloat162 b0 = __floats2bfloat162_rn(fmaxf(v.x, 0.f), fmaxf(v.y, 0.f)), b1 = __floats2bfloat162_rn(fmaxf(v.z, 0.f), fmaxf(v.w, 0.f));
+      uint8_t* rowp = reinterpret_cast<uint8_t*>(base + (size_t)out_row[a] * 32);
+      *reinterpret_cast<uint2*>(rowp + ch0 * 8) = make_uint2(*reinterpret_cast<uint32_t*>(&a0), *reinterpret_cast<uint32_t*>(&a1));
+      *reinterpret_cast<uint2*>(rowp + ch1 * 8) = make_uint2(*reinterpret_cast<uint32_t*>(&b0), *reinterpret_cast<uint32_t*>(&b1));
+    }
+  }
+}
+
+// general float32 planes [n][4][A] -> act1, SAME summation order as conv1_table_kernel: per kernel row the two stone
+// planes' column sums are added first (= the table entry), then the rows to the bias; the last-move plane and plane 3
+// follow.  On 0/1 planes with an empty plane 3 every extra term is an exact zero, so both kernels agree bit for bit.
+__global__ void __launch_bounds__(256) conv1_table_planes_kernel(ConvGeom g, int n, const float* __restrict__ planes,
+                                                                 const float* __restrict__ w4 /*[tap][4][32]*/,
+                                                                 const float* __restrict__ bias,
+                                                                 __nv_bfloat16* __restrict__ act1) {
+  __shared__ float sw[36 * 32];
+  __shared__ float sb[32];
+  extern __shared__ float sp[];          // [4][A]
+  for (int i = threadIdx.x; i < 36 * 32; i += blockDim.x) sw[i] = w4[i];
+  if (threadIdx.x < 32) sb[threadIdx.x] = bias[threadIdx.x];
+  for (int slot = blockIdx.x; slot < n; slot += gridDim.x) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < 4 * g.A; i += blockDim.x) sp[i] = planes[(size_t)slot * 4 * g.A + i];
+    __syncthreads();
+    for (int item = threadIdx.x; item < g.A * 4; item += blockDim.x) {
+      const int a = item >> 2, cgp = item & 3;               // 8 channels per thread: [8 cgp, 8 cgp + 8)
+      const int r = a / g.B, c = a - r * g.B;
+      float acc[8];
+#pragma unroll
+      for (int j = 0; j < 8; j++) acc[j] = sb[cgp * 8 + j];
+      auto column_sum = [&](int pl, int ky, float (&part)[8]) {
+#pragma unroll
+        for (int j = 0; j < 8; j++) part[j] = 0.f;
+        const int rr = r + ky - 1;
+        if (rr < 0 || rr >= g.B) return;
+        for (int kx = 0; kx < 3; kx++) {
+          const int cc = c + kx - 1;
+          if (cc < 0 || cc >= g.B) continue;
+          const float v = sp[pl * g.A + rr * g.B + cc];
+          const float* wr = sw + ((ky * 3 + kx) * 4 + pl) * 32 + cgp * 8;
+#pragma unroll
+          for (int j = 0; j < 8; j++) part[j] = fmaf(v, wr[j], part[j]);
+        }
+      };
+      float p0[8], p1[8];
+      for (int ky = 0; ky < 3; ky++) {                       // stone planes: (own + opp) per kernel row, rows in order
+        column_sum(0, ky, p0);
+        column_sum(1, ky, p1);
+#pragma unroll
+        for (int j = 0; j < 8; j++) acc[j] += p0[j] + p1[j];
+      }
+      for (int pl = 2; pl < 4; pl++)                         // last-move plane, then plane 3
+        for (int ky = 0; ky < 3; ky++) {
+          column_sum(pl, ky, p0);
+#pragma unroll
+          for (int j = 0; j < 8; j++) acc[j] += p0[j];
+        }
+      uint32_t packed[4];
+#pragma unroll
+      for (int j = 0; j < 4; j++) {
+        __nv_bfloat162 hh = __floats2bfloat162_rn(fmaxf(acc[2 * j], 0.f), fmaxf(acc[2 * j + 1], 0.f));
+        packed[j] = *reinterpret_cast<uint32_t*>(&hh);
+      }
+      *reinterpret_cast<uint4*>(act1 + ((size_t)slot * g.stride + (size_t)(r + 1) * g.P + (c + 1)) * 32 + cgp * 8) =
+          make_uint4(packed[0], packed[1], packed[2], packed[3]);
+    }
+  }
+}
+
 // ---- tcgen05 implicit-GEMM 3x3 convolution ---------------------------------------------------------------
 // Persistent, warp-specialised: warp 0 = TMA producer, warp 1 = TMEM owner + MMA issuer, warps 2..5 =
 // epilogue (warp w owns TMEM lanes 32*(w%4)..+31 == tile rows).
@@ -306,7 +489,8 @@ struct ConvArgs {
   int single;                     // 0: three dx-shifted TMA loads per tile; 1/2: ONE load of 128+2P+2 rows, the nine taps are
                                   // row-offset descriptors into it (2 = descriptors carry the swizzle base offset)
   int stage_bytes;                // bytes of one ring stage
-  long long* clk;                 // bring-up: per-tile clock64 stamps of CTA 0 ([tile][16]) or null
+  long long* clk;                 // bring-up: per-tile clock64 stamps of CTA clk_cta ([tile][16]) or null
+  int clk_cta;                    // bring-up: which CTA stamps (AZP_CLK_CTA, default 0)
   // HEADS only: the FC layers (policy_fc, value_fc1 + ReLU + value_fc2 + tanh; net.py:64-70) run INSIDE this kernel as
   // extra items of the accumulator rotation -- job = (board tile of 128 boards, 64-column slice of the policy outputs or
   // the value head) -- once the head features of the board tile have been written by every CTA's epilogue
@@ -314,7 +498,7 @@ struct ConvArgs {
   int fc_slices, fc_pk_chunks, fc_vk_chunks, fc_v_off, fc_A;
   const float* fc_pbias; const float* fc_vbias; const float* fc_vw2; const float* fc_vb2;
   float* fc_logits; float* fc_value;
-  unsigned int* feat_done;        // [board tiles] epilogue -> FC producer: one count per (conv tile touching it, lane quarter)
+  unsigned int* feat_done;        // [board tiles] -> FC producer: one count per conv tile touching the board tile, features stored
   unsigned int* fc_done;          // [board tiles] FC epilogue -> consumers of the logits / values: one count per (job, lane quarter)
 };
 
@@ -417,7 +601,8 @@ __global__ void __launch_bounds__(BITS ? CONV_THREADS_BITS : (HEADS ? CONV_THREA
   uint64_t* wbar = tempty + 4;                              // [1]
   uint64_t* act_full = wbar + 1;                            // [4] epilogue -> MMA: bf16 tile of accumulator a is in TMEM
   uint64_t* head_full = act_full + 4;                       // [4] MMA -> epilogue: head outputs of accumulator a ready
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(head_full + 4);
+  uint64_t* hw_done = head_full + 4;                        // [4] epilogue -> signaller: head features of the item are stored
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(hw_done + 4);
   float* s_bias = reinterpret_cast<float*>(tmem_slot + 2);  // [COUT] (+ [8] head bias)
   float* s_w1 = s_bias + COUT + 8;                          // BITS: [3 planes][3 ky][8 patterns][32] conv1 tables + [32] bias
   int16_t* s_cells = reinterpret_cast<int16_t*>(s_w1 + 72 * 32 + 32); // BITS: [2][CODES] column-pattern codes
@@ -425,7 +610,7 @@ __global__ void __launch_bounds__(BITS ? CONV_THREADS_BITS : (HEADS ? CONV_THREA
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const ConvGeom g = args.g;
   auto wall_ns = [] { unsigned long long gt; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt)); return (long long)gt; };
-  if (AZP_CLKPTR(args.clk) && blockIdx.x == 0 && threadIdx.x == 0) AZP_CLKPTR(args.clk)[0 * 16 + 14] = wall_ns();      // kernel entry
+  if (AZP_CLKPTR(args.clk) && (int)blockIdx.x == args.clk_cta && threadIdx.x == 0) AZP_CLKPTR(args.clk)[0 * 16 + 14] = wall_ns();      // kernel entry
 
   // ---- prologue: touches nothing the previous kernel of the stream writes, so under programmatic dependent
   //      launch it overlaps that kernel's tail (barriers, TMEM, bias and the resident weights) ----
@@ -434,7 +619,7 @@ __global__ void __launch_bounds__(BITS ? CONV_THREADS_BITS : (HEADS ? CONV_THREA
     // HEADS: an accumulator is released by the four warps that read its head outputs; otherwise by all eight
     for (int i = 0; i < NACC; i++) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], HEADS ? 4 : 8); }
     mbar_init(wbar, 1);
-    for (int i = 0; i < 4; i++) { mbar_init(&act_full[i], 8); mbar_init(&head_full[i], 1); }
+    for (int i = 0; i < 4; i++) { mbar_init(&act_full[i], 8); mbar_init(&head_full[i], 1); mbar_init(&hw_done[i], 4); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     mbar_expect_tx(wbar, S::W_BYTES + HW_BYTES);
     for (int tap = 0; tap < 9; tap++) tma_load_2d(s_w + tap * S::W_TAP_BYTES, &map_w, wbar, 0, tap * COUT);
@@ -449,10 +634,10 @@ __global__ void __launch_bounds__(BITS ? CONV_THREADS_BITS : (HEADS ? CONV_THREA
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (AZP_CLKPTR(args.clk) && blockIdx.x == 0 && threadIdx.x == 0) AZP_CLKPTR(args.clk)[1 * 16 + 14] = wall_ns();      // barriers + TMEM ready
+  if (AZP_CLKPTR(args.clk) && (int)blockIdx.x == args.clk_cta && threadIdx.x == 0) AZP_CLKPTR(args.clk)[1 * 16 + 14] = wall_ns();      // barriers + TMEM ready
   pdl_wait();                      // the leaf count and the input activations are the previous kernels' outputs
   pdl_launch_dependents();
-  if (AZP_CLKPTR(args.clk) && blockIdx.x == 0 && threadIdx.x == 0) AZP_CLKPTR(args.clk)[2 * 16 + 14] = wall_ns();      // predecessor finished
+  if (AZP_CLKPTR(args.clk) && (int)blockIdx.x == args.clk_cta && threadIdx.x == 0) AZP_CLKPTR(args.clk)[2 * 16 + 14] = wall_ns();      // predecessor finished
   const int count = args.count_dev ? *args.count_dev : args.count_host;
   const int slot0 = args.back ? g.G - count : 0;
   const long long row_begin = (long long)slot0 * g.stride;
@@ -481,6 +666,10 @@ __global__ void __launch_bounds__(BITS ? CONV_THREADS_BITS : (HEADS ? CONV_THREA
     return false;
   };
   auto fc_chunks = [&](int sl) -> int { return sl == args.fc_slices ? args.fc_vk_chunks : args.fc_pk_chunks; };
+  // bring-up: wall-clock stamps of the first FC job of the LAST CTA (row 48 of the stamp buffer)
+  auto fc_stamp = [&](int k) {
+    if (AZP_CLKPTR(args.clk) && blockIdx.x == gridDim.x - 1) AZP_CLKPTR(args.clk)[48 * 16 + k] = wall_ns();
+  };
 
   if (warp == 0) {
     // ===== TMA producer =====
@@ -493,9 +682,9 @@ __global__ void __launch_bounds__(BITS ? CONV_THREADS_BITS : (HEADS ? CONV_THREA
           int t, bt, sl;
           if (item_is_conv(tl, t, bt, sl)) {
             const int st = it % STAGES;
-            if (AZP_CLKPTR(args.clk) && blockIdx.x == 0) AZP_CLKPTR(args.clk)[it * 16 + 0] = clock64();
+            if (AZP_CLKPTR(args.clk) && (int)blockIdx.x == args.clk_cta) AZP_CLKPTR(args.clk)[it * 16 + 0] = clock64();
             mbar_wait(&empty[st], ((it / STAGES) & 1) ^ 1);
-            if (AZP_CLKPTR(args.clk) && blockIdx.x == 0) AZP_CLKPTR(args.clk)[it * 16 + 1] = clock64();
+            if (AZP_CLKPTR(args.clk) && (int)blockIdx.x == args.clk_cta) AZP_CLKPTR(args.clk)[it * 16 + 1] = clock64();
             mbar_expect_tx(&full[st], bytes);
             const long long row = row_begin + (long long)t * TILE_M - g.P - 1;
             tma_load_2d(s_a + (size_t)st * stage_bytes, &map_act, &full[st], 0, (int)row);
@@ -503,11 +692,12 @@ __global__ void __launch_bounds__(BITS ? CONV_THREADS_BITS : (HEADS ? CONV_THREA
             continue;
           }
           // FC job: its A operand = the head features of boards [128 bt, 128 bt + 128), written by the epilogues of every
-          // CTA whose conv tiles touch those boards -- 4 counts (lane quarters) per such tile
+          // CTA whose conv tiles touch those boards -- one count per such tile
           const int nb = min(TILE_M, count - bt * TILE_M);
           const long long lo = (long long)bt * TILE_M * g.stride, hi = ((long long)bt * TILE_M + nb) * g.stride - 1;
           const int t_lo = (int)(lo / TILE_M), t_hi = min(n_tiles - 1, (int)(hi / TILE_M));
-          const unsigned target = 4u * (unsigned)(t_hi - t_lo + 1);
+          const unsigned target = (unsigned)(t_hi - t_lo + 1);
+          if (tl == n_conv) fc_stamp(0);
           {
             const long long t0 = clock64();
             while (ld_acquire_u32(args.feat_done + bt) < target) {
@@ -516,6 +706,7 @@ __global__ void __launch_bounds__(BITS ? CONV_THREADS_BITS : (HEADS ? CONV_THREA
             }
           }
           asm volatile("fence.proxy.async;" ::: "memory");         // generic-proxy stores (acquired above) -> TMA reads
+          if (tl == n_conv) fc_stamp(1);
           const bool is_value = sl == args.fc_slices;
           const CUtensorMap* mw = is_value ? &map_wv : &map_wp;
           const int k_off = is_value ? args.fc_v_off : 0, kcs = fc_chunks(sl);
@@ -527,6 +718,7 @@ __global__ void __launch_bounds__(BITS ? CONV_THREADS_BITS : (HEADS ? CONV_THREA
             tma_load_2d(sa, &map_feat, &full[st], k_off + kc * 64, bt * TILE_M);
             tma_load_2d(sa + TILE_M * 128, mw, &full[st], kc * 64, is_value ? 0 : sl * 64);     // rows past the matrix: zero fill
           }
+          if (tl == n_conv) fc_stamp(2);
         }
       }
       for (int t = blockIdx.x; !BITS && !args.single && t < n_tiles; t += gridDim.x) {
@@ -582,9 +774,9 @@ __global__ void __launch_bounds__(BITS ? CONV_THREADS_BITS : (HEADS ? CONV_THREA
       }
       asm volatile("bar.sync 2, 256;" ::: "memory");         // codes (and, first time, the conv1 tables) visible
       const int st = it % STAGES;
-      if (AZP_CLKPTR(args.clk) && blockIdx.x == 0 && pt == 0) AZP_CLKPTR(args.clk)[tl * 16 + 0] = clock64();
+      if (AZP_CLKPTR(args.clk) && (int)blockIdx.x == args.clk_cta && pt == 0) AZP_CLKPTR(args.clk)[tl * 16 + 0] = clock64();
       mbar_wait(&empty[st], ((it / STAGES) & 1) ^ 1);
-      if (AZP_CLKPTR(args.clk) && blockIdx.x == 0 && pt == 0) AZP_CLKPTR(args.clk)[tl * 16 + 1] = clock64();
+      if (AZP_CLKPTR(args.clk) && (int)blockIdx.x == args.clk_cta && pt == 0) AZP_CLKPTR(args.clk)[tl * 16 + 1] = clock64();
       for (int idx = pt; idx < rows_needed; idx += 256) {
         uint32_t packed[16];
 #pragma unroll
@@ -629,7 +821,7 @@ __global__ void __launch_bounds__(BITS ? CONV_THREADS_BITS : (HEADS ? CONV_THREA
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to UMMA
       __syncwarp();
       if (lane == 0) mbar_arrive(&full[st]);
-      if (AZP_CLKPTR(args.clk) && blockIdx.x == 0 && pt == 0) AZP_CLKPTR(args.clk)[tl * 16 + 6] = clock64();
+      if (AZP_CLKPTR(args.clk) && (int)blockIdx.x == args.clk_cta && pt == 0) AZP_CLKPTR(args.clk)[tl * 16 + 6] = clock64();
     }
   } else if (warp == 1 || warp == 11) {
     // ===== MMA issuers: two threads, even / odd tiles.  A single thread alternates "wait for barriers" and
@@ -640,7 +832,7 @@ __global__ void __launch_bounds__(BITS ? CONV_THREADS_BITS : (HEADS ? CONV_THREA
       const uint32_t a_base = smem_u32(s_a), w_base = smem_u32(s_w);
       const int my_parity = warp == 1 ? 0 : 1;
       mbar_wait(wbar, 0);
-      if (AZP_CLKPTR(args.clk) && blockIdx.x == 0 && warp == 1) AZP_CLKPTR(args.clk)[3 * 16 + 14] = wall_ns();           // weights resident
+      if (AZP_CLKPTR(args.clk) && (int)blockIdx.x == args.clk_cta && warp == 1) AZP_CLKPTR(args.clk)[3 * 16 + 14] = wall_ns();           // weights resident
       tc_fence_after();
       int it = 0;
       for (int tl = 0; tl < n_items; tl++) {
@@ -649,9 +841,9 @@ __global__ void __launch_bounds__(BITS ? CONV_THREADS_BITS : (HEADS ? CONV_THREA
         if ((tl & 1) != my_parity) { it += is_conv ? (args.single ? 1 : 3) : fc_chunks(sl); continue; }
         const int acc = tl % NACC;
         const uint32_t acc_ph = (tl / NACC) & 1;
-        if (AZP_CLKPTR(args.clk) && blockIdx.x == 0) AZP_CLKPTR(args.clk)[tl * 16 + 2] = clock64();
+        if (AZP_CLKPTR(args.clk) && (int)blockIdx.x == args.clk_cta) AZP_CLKPTR(args.clk)[tl * 16 + 2] = clock64();
         mbar_wait(&tempty[acc], acc_ph ^ 1);              // epilogue has drained this accumulator
-        if (AZP_CLKPTR(args.clk) && blockIdx.x == 0) AZP_CLKPTR(args.clk)[tl * 16 + 3] = clock64();
+        if (AZP_CLKPTR(args.clk) && (int)blockIdx.x == args.clk_cta) AZP_CLKPTR(args.clk)[tl * 16 + 3] = clock64();
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * COUT);
         uint32_t accumulate = 0;
@@ -663,6 +855,7 @@ __global__ void __launch_bounds__(BITS ? CONV_THREADS_BITS : (HEADS ? CONV_THREA
           for (int kc = 0; kc < kcs; kc++, it++) {
             const int st = it % STAGES;
             mbar_wait(&full[st], (it / STAGES) & 1);
+            if (tl == n_conv && kc == 0) fc_stamp(3);
             tc_fence_after();
             const uint32_t a_addr = a_base + (uint32_t)st * (uint32_t)stage_bytes, b_addr = a_addr + TILE_M * 128;
 #pragma unroll
@@ -673,12 +866,13 @@ __global__ void __launch_bounds__(BITS ? CONV_THREADS_BITS : (HEADS ? CONV_THREA
             umma_commit(&empty[st]);
           }
           umma_commit(&tfull[acc]);
+          if (tl == n_conv) fc_stamp(4);
           continue;
         }
         if (args.single) {
           const int st = it % STAGES;
           mbar_wait(&full[st], (it / STAGES) & 1);
-          if (AZP_CLKPTR(args.clk) && blockIdx.x == 0) AZP_CLKPTR(args.clk)[tl * 16 + 4] = clock64();
+          if (AZP_CLKPTR(args.clk) && (int)blockIdx.x == args.clk_cta) AZP_CLKPTR(args.clk)[tl * 16 + 4] = clock64();
           tc_fence_after();
           const uint32_t a_stage = a_base + (uint32_t)st * (uint32_t)stage_bytes;
 #pragma unroll
@@ -717,7 +911,7 @@ __global__ void __launch_bounds__(BITS ? CONV_THREADS_BITS : (HEADS ? CONV_THREA
           umma_commit(&empty[st]);                        // stage reusable once these MMAs retire
         }
         umma_commit(&tfull[acc]);                         // accumulator complete
-        if (AZP_CLKPTR(args.clk) && blockIdx.x == 0) {
+        if (AZP_CLKPTR(args.clk) && (int)blockIdx.x == args.clk_cta) {
           AZP_CLKPTR(args.clk)[tl * 16 + 5] = clock64();
           unsigned long long gt;
           asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
@@ -746,20 +940,38 @@ __global__ void __launch_bounds__(BITS ? CONV_THREADS_BITS : (HEADS ? CONV_THREA
         }
         umma_commit(&head_full[b]);
       };
+      // This thread is also the SIGNALLER of the fused FC jobs: the four epilogue warps that store an item's head features
+      // arrive on hw_done (release / acquire at CTA scope), then this otherwise idle thread makes the stores visible
+      // device-wide with ONE fence and counts the tile in for every board tile it touches (the FC producers acquire the
+      // sum).  A fence in the epilogue warps themselves cost 17 % of conv3: they are the busiest threads of the kernel.
+      auto signal_item = [&](int j) {
+        mbar_wait(&hw_done[j % NACC], (uint32_t)((j / NACC) & 1));
+        if (!fc_on || j >= n_conv) return;
+        __threadfence();
+        const unsigned R0 = (unsigned)row_begin + (unsigned)(cta + j * n_cta) * TILE_M;
+        const int s_first = (int)(R0 / (unsigned)g.stride);
+        const int s_last = min(count - 1, (int)((R0 + TILE_M - 1) / (unsigned)g.stride));
+        atomicAdd(args.feat_done + (s_first >> 7), 1u);
+        if ((s_last >> 7) != (s_first >> 7)) atomicAdd(args.feat_done + (s_last >> 7), 1u);
+      };
       mbar_wait(wbar, 0);
       tc_fence_after();
       for (int tl = 0; tl < n_items; tl++) {
         if (tl < n_conv) {
           issue_head(tl);
+          if (tl > 0) signal_item(tl - 1);          // the epilogue writes the heads of tile tl-1 right after the math of tile tl
         } else {
           // FC job: no head GEMM, but the barrier pair keeps its one-phase-per-item rhythm (the epilogue has read the
-          // job's outputs out of the accumulator when its eight warps have arrived)
+          // job's outputs out of the accumulator when its eight warps have arrived).  The previous item's features go
+          // out FIRST: this very job may be waiting for them.
+          if (tl > 0) signal_item(tl - 1);
           const int b = tl % NACC;
           mbar_wait(&act_full[b], (uint32_t)((tl / NACC) & 1));
           mbar_arrive(&head_full[b]);
         }
-        if (AZP_CLKPTR(args.clk) && blockIdx.x == 0) AZP_CLKPTR(args.clk)[tl * 16 + 6] = clock64();
+        if (AZP_CLKPTR(args.clk) && (int)blockIdx.x == args.clk_cta) AZP_CLKPTR(args.clk)[tl * 16 + 6] = clock64();
       }
+      if (n_items > 0) signal_item(n_items - 1);
     }
   } else if ((warp >= 2 && warp < 10) || (EGROUPS == 2 && warp >= 12 && warp < 20)) {
     // ===== epilogue: warp (q, h) owns TMEM lanes 32q..32q+31 (tile rows) and channel half h; with two groups,
@@ -777,7 +989,7 @@ __global__ void __launch_bounds__(BITS ? CONV_THREADS_BITS : (HEADS ? CONV_THREA
       if (j >= n_conv) {
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&tempty[b]);
+        if (lane == 0) { mbar_arrive(&tempty[b]); mbar_arrive(&hw_done[b]); }
         return;
       }
       const int tj = cta + j * n_cta;
@@ -805,19 +1017,8 @@ __global__ void __launch_bounds__(BITS ? CONV_THREADS_BITS : (HEADS ? CONV_THREA
             f[j < args.PC ? j * g.A : args.PKp + (j - args.PC) * g.A] =
                 __float2bfloat16(fmaxf(__uint_as_float(r[j]) + s_bias[COUT + j], 0.f));
       }
-      if (fc_on) {
-        // release: this lane quarter's features of the tile are written -> one count for every board tile the conv tile
-        // touches (the FC jobs' producers acquire the sum)
-        __threadfence();
-        __syncwarp();
-        if (lane == 0) {
-          const unsigned R0 = (unsigned)row_begin + (unsigned)tj * TILE_M;
-          const int s_first = (int)(R0 / (unsigned)g.stride);
-          const int s_last = min(count - 1, (int)((R0 + TILE_M - 1) / (unsigned)g.stride));
-          atomicAdd(args.feat_done + (s_first >> 7), 1u);
-          if ((s_last >> 7) != (s_first >> 7)) atomicAdd(args.feat_done + (s_last >> 7), 1u);
-        }
-      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&hw_done[b]);              // -> signaller (the head issuer's thread): fence + count
     };
     bool heads_pending = false;           // write_heads(tl - 1) still to be done when item tl starts
     for (int tl = 0; tl < n_items; tl++) {
@@ -826,33 +1027,35 @@ __global__ void __launch_bounds__(BITS ? CONV_THREADS_BITS : (HEADS ? CONV_THREA
       const bool is_conv = item_is_conv(tl, t, fbt, fsl);
       const int acc = tl % NACC;
       const uint32_t acc_ph = (tl / NACC) & 1;
-      const bool stamp = AZP_CLKPTR(args.clk) && blockIdx.x == 0 && (warp == 2 || warp == 12) && lane == 0;
+      const bool stamp = AZP_CLKPTR(args.clk) && (int)blockIdx.x == args.clk_cta && (warp == 2 || warp == 12) && lane == 0;
       if (HEADS && !is_conv) {
         // ---- FC job.  The features it waits for may be the ones THIS warp still has to write (the previous item's
         //      heads), so they go out first -- waiting for the job's accumulator before that could never end.
+        const bool fstamp = tl == n_conv && warp == 2 && lane == 0;
+        if (fstamp) fc_stamp(5);
         if (heads_pending && h == 0) write_heads(tl - 1);
         heads_pending = false;
+        if (fstamp) fc_stamp(6);
         mbar_wait(&tfull[acc], acc_ph);
+        if (fstamp) fc_stamp(7);
         tc_fence_after();
         if (h == 0) {
           const bool is_value = fsl == args.fc_slices;
-          const int row = fbt * TILE_M + q * 32 + lane;            // board = row of the evaluated batch
+          const int trow = q * 32 + lane;
+          const int row = fbt * TILE_M + trow;                     // board = row of the evaluated batch
           const uint32_t fc_addr = tmem_base + lane_addr + (uint32_t)(acc * COUT);
+          // every conv item of this CTA precedes its FC jobs and this warp group has drained them all: the resident conv
+          // weights are dead, their shared memory stages the logits tile for a coalesced write-out
+          float* stage = reinterpret_cast<float*>(s_w);
+          constexpr int PITCH = 65;                                // odd pitch: conflict-free row-per-lane writes
           float sp[2] = {0.f, 0.f};
 #pragma unroll
           for (int hf = 0; hf < 2; hf++) {
             uint32_t r[32];
             tmem_ld32(fc_addr + hf * 32, r);
             if (!is_value) {
-              // raw logits (+bias); the softmax over all cells happens in the consumer (controller.py:49)
-              if (row < count) {
-                float* out = args.fc_logits + (size_t)row * args.fc_A;
 #pragma unroll
-                for (int i = 0; i < 32; i++) {
-                  const int c = fsl * 64 + hf * 32 + i;
-                  if (c < args.fc_A) out[c] = __uint_as_float(r[i]) + __ldg(args.fc_pbias + c);
-                }
-              }
+              for (int i = 0; i < 32; i++) stage[trow * PITCH + hf * 32 + i] = __uint_as_float(r[i]);
             } else {
               // value_fc1 + ReLU, value_fc2: the same two 32-column partial sums, in the same order, as fc_umma_kernel
 #pragma unroll
@@ -861,8 +1064,24 @@ __global__ void __launch_bounds__(BITS ? CONV_THREADS_BITS : (HEADS ? CONV_THREA
                               __ldg(args.fc_vw2 + hf * 32 + i), sp[hf]);
             }
           }
-          if (is_value && row < count) args.fc_value[row] = tanhf((sp[0] + sp[1]) + __ldg(args.fc_vb2));
+          if (is_value) {
+            if (row < count) args.fc_value[row] = tanhf((sp[0] + sp[1]) + __ldg(args.fc_vb2));
+          } else {
+            // raw logits (+bias); the softmax over all cells happens in the consumer (controller.py:49).  Warp w of the
+            // group writes rows w, w+4, ..: 64 consecutive floats per row, two per lane
+            asm volatile("bar.sync 5, 128;" ::: "memory");
+            const int nrows = min(TILE_M, count - fbt * TILE_M);
+            const int c0 = fsl * 64 + lane, c1 = c0 + 32;
+            const float b0 = c0 < args.fc_A ? __ldg(args.fc_pbias + c0) : 0.f, b1 = c1 < args.fc_A ? __ldg(args.fc_pbias + c1) : 0.f;
+            for (int rr = q; rr < nrows; rr += 4) {
+              float* out = args.fc_logits + (size_t)(fbt * TILE_M + rr) * args.fc_A;
+              if (c0 < args.fc_A) out[c0] = stage[rr * PITCH + lane] + b0;
+              if (c1 < args.fc_A) out[c1] = stage[rr * PITCH + 32 + lane] + b1;
+            }
+            asm volatile("bar.sync 5, 128;" ::: "memory");         // the staging tile may be refilled by the next job
+          }
         }
+        if (fstamp) fc_stamp(8);
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&act_full[acc]);
@@ -974,7 +1193,8 @@ __global__ void __launch_bounds__(BITS ? CONV_THREADS_BITS : (HEADS ? CONV_THREA
   }
   tc_fence_before();
   __syncthreads();
-  if (AZP_CLKPTR(args.clk) && blockIdx.x == 0 && threadIdx.x == 0) AZP_CLKPTR(args.clk)[4 * 16 + 14] = wall_ns();      // all roles done
+  if (AZP_CLKPTR(args.clk) && (int)blockIdx.x == args.clk_cta && threadIdx.x == 0) AZP_CLKPTR(args.clk)[4 * 16 + 14] = wall_ns();      // all roles done
+  if (threadIdx.x == 0) fc_stamp(9);
   if (warp == 1) tmem_dealloc(tmem_base, TMEM_COLS);
 }
 
@@ -1856,14 +2076,14 @@ struct UmmaWorkspace {
   CUtensorMap map_act1_s, map_act2_s;  // single-load boxes (128+2P+2 rows)
   CUtensorMap map_act2_out;            // conv2 epilogue: TMA store of one [128 rows][64 ch] tile
   CUtensorMap map_act1_out;            // conv1 (tensor core) epilogue: TMA store of one [128 rows][32 ch] tile
-  int conv1_mode = 1;                  // 1: conv1_umma_kernel, 0: SIMT table kernel (AZP_CONV1=simt)
+  int conv1_mode = 1;                  // 1: conv1_umma_kernel, 2: conv1_table_kernel, 0: conv1_bits_kernel (see azp_umma_create)
   int single = 0;
   long long* clk = nullptr;            // AZP_CLK=1: per-tile stamps of conv3's CTA 0
   size_t rows = 0;
   int sms = 148;
   int smem2 = 0, smem3 = 0;
   int pair = 0, smem3p = 0, pair_clusters = 0;   // conv3 on CTA pairs (cta_group::2): AZP_CONV3_PAIR=1 (default 0)
-  int fuse_fc = 1;                     // FC layers inside the conv3 kernel (AZP_FUSE_FC=0: separate fc_umma_kernel launch)
+  int fuse_fc = 0;                     // AZP_FUSE_FC=1: FC layers inside the conv3 kernel instead of the fc_umma_kernel launch
   unsigned int* feat_done = nullptr;   // [FC_MAX_BOARD_TILES] see ConvArgs
   unsigned int* fc_done = nullptr;     // [FC_MAX_BOARD_TILES]
 };
@@ -1881,6 +2101,8 @@ struct UmmaWeights {
   float* w1_bits = nullptr;           // [tap][3][32]
   float* w1_tab = nullptr;            // [plane(3)][ky][pattern(8)][32]: sum over set pattern bits kx of w1[co][plane][ky][kx]
   float* w1_planes = nullptr;         // [tap][4][32]
+  float* w1_tab2 = nullptr;           // [ky][own3 | opp3 << 3][32]: both stone planes' column sums of one kernel row (conv1_table_kernel)
+  float* w1_lm = nullptr;             // [ky][kx][32]: the last-move plane's weights
   __nv_bfloat16* w1_umma = nullptr;   // [4][32][32]: hi, lo (k = ky*9+plane*3+kx, k=27 bias), plane-3 hi, lo (k = ky*3+kx)
   __nv_bfloat16* head_w16 = nullptr;  // [16][128] 1x1 head conv weights (policy rows first, zero padded)
   float* head_b8 = nullptr;           // [8]
@@ -1923,7 +2145,7 @@ template <int CIN, int COUT, int STAGES, bool HEADS, bool BITS>
 int conv_smem_bytes(int stage_rows, bool fc_fused = false) {
   using S = ConvSmem<CIN, COUT, STAGES, HEADS>;
   return 1024 + S::W_BYTES + STAGES * conv_stage_bytes(stage_rows, S::ROWB, fc_fused) + (HEADS ? (COUT / 64) * HEAD_N * 128 : 0) +
-         (HEADS ? 0 : 2 * TILE_M * 128) + (2 * STAGES + 17) * 8 + 16 + (COUT + 8) * 4 + (BITS ? (72 * 32 + 32) * 4 + 2 * CODES * 2 : 0) + 64;
+         (HEADS ? 0 : 2 * TILE_M * 128) + (2 * STAGES + 21) * 8 + 16 + (COUT + 8) * 4 + (BITS ? (72 * 32 + 32) * 4 + 2 * CODES * 2 : 0) + 64;
 }
 
 }  // namespace
@@ -1986,7 +2208,11 @@ int azp_umma_create(azp_engine* e) {
   if ((st = make_map(e, &ws->map_act2_s, ws->act2, ws->rows, 64, stage_rows + 2))) return st;
   if ((st = make_map(e, &ws->map_act2_out, ws->act2, ws->rows, 64, TILE_M))) return st;
   if ((st = make_map(e, &ws->map_act1_out, ws->act1, ws->rows, 32, TILE_M))) return st;
-  { const char* v = getenv("AZP_CONV1"); ws->conv1_mode = (v && !strcmp(v, "simt")) ? 0 : 1; }
+  // conv1 of the leaf batch: 1 = tensor-core kernel (default), 2 = merged-table SIMT kernel (AZP_CONV1=table: three table rows
+  // per position; parity-green, but 11.3 M warp instructions per launch make it issue-bound at 23.9 us against the tensor
+  // kernel's 18-20 us, profiles/r2c_ncu_conv1_table_kernel.txt), 0 = the first SIMT kernel with nine pattern rows per
+  // position (AZP_CONV1=simt); each has a float-planes twin that agrees with it bit for bit
+  { const char* v = getenv("AZP_CONV1"); ws->conv1_mode = !v ? 1 : (!strcmp(v, "simt") ? 0 : (!strcmp(v, "table") ? 2 : 1)); }
   AZP_CUDA(e, cudaFuncSetAttribute(conv1_umma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, conv1_smem_bytes(false)));
   AZP_CUDA(e, cudaFuncSetAttribute(conv1_umma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, conv1_smem_bytes(true)));
   { const char* v = getenv("AZP_SINGLE_LOAD"); ws->single = v ? atoi(v) : 1; }
@@ -1996,7 +2222,10 @@ int azp_umma_create(azp_engine* e) {
   cudaDeviceProp prop;
   AZP_CUDA(e, cudaGetDeviceProperties(&prop, e->cfg.device));
   ws->sms = prop.multiProcessorCount;
-  { const char* v = getenv("AZP_FUSE_FC"); ws->fuse_fc = v ? atoi(v) : 1; }
+  // measured (profiles/r2c_fc_fused_timeline.txt): with the jobs at the tail of every CTA's work list the fused kernel costs
+  // what conv3 + the separately launched FC kernel cost under programmatic dependent launch (-6 us bracketed, +1 % end to
+  // end): off by default
+  { const char* v = getenv("AZP_FUSE_FC"); ws->fuse_fc = v ? atoi(v) : 0; }
   if (ws->single != 1) ws->fuse_fc = 0;
   if ((st = e->alloc(&ws->feat_done, (size_t)FC_MAX_BOARD_TILES))) return st;
   if ((st = e->alloc(&ws->fc_done, (size_t)FC_MAX_BOARD_TILES))) return st;
@@ -2138,6 +2367,23 @@ int azp_umma_build(azp_engine* e, const HostNet& net, NetWeights* W) {
     if ((st = up(e, &U->w1_tab, tab))) return st;
   }
   if ((st = up(e, &U->w1_planes, w1p))) return st;
+  {
+    std::vector<float> tab2((size_t)C1T_TAB_FLOATS, 0.f), lmw(9 * 32, 0.f);
+    for (int ky = 0; ky < 3; ky++)
+      for (int pat = 0; pat < 64; pat++)
+        for (int co = 0; co < 32; co++) {
+          float p0 = 0.f, p1 = 0.f;                        // fixed order kx = 0,1,2 per plane, then own + opp
+          for (int kx = 0; kx < 3; kx++) {
+            if (pat & (1 << kx)) p0 += c1.w[((size_t)co * 4 + 0) * 9 + ky * 3 + kx];
+            if (pat & (8 << kx)) p1 += c1.w[((size_t)co * 4 + 1) * 9 + ky * 3 + kx];
+          }
+          tab2[((size_t)ky * 64 + pat) * 32 + co] = p0 + p1;
+        }
+    for (int t = 0; t < 9; t++)
+      for (int co = 0; co < 32; co++) lmw[t * 32 + co] = c1.w[((size_t)co * 4 + 2) * 9 + t];
+    if ((st = up(e, &U->w1_tab2, tab2))) return st;
+    if ((st = up(e, &U->w1_lm, lmw))) return st;
+  }
   if ((st = up(e, &U->b1, c1.b))) return st;
   {
     // tensor-core conv1: B operands [32 cout][32 k] bf16, value split v = hi + lo
@@ -2196,7 +2442,7 @@ int azp_umma_build(azp_engine* e, const HostNet& net, NetWeights* W) {
 struct StemRepack {
   const float* blob; int A, PKp, VKp;
   size_t o_c1w, o_c1b, o_c2w, o_c2b, o_c3w, o_c3b, o_pcw, o_pcb, o_pfw, o_pfb, o_vcw, o_vcb, o_v1w, o_v1b, o_v2w, o_v2b;
-  float *w1_bits, *w1_tab, *w1_planes, *b1, *b2, *b3, *head_b8, *pfc_b, *vfc1_b, *vfc2_w, *vfc2_b;
+  float *w1_bits, *w1_tab, *w1_planes, *w1_tab2, *w1_lm, *b1, *b2, *b3, *head_b8, *pfc_b, *vfc1_b, *vfc2_w, *vfc2_b;
   __nv_bfloat16 *w1_umma, *w2, *w3, *head_w16, *wp16, *wv16;
 };
 
@@ -2204,10 +2450,10 @@ __global__ void stem_repack_kernel(StemRepack r) {
   const float* c1w = r.blob + r.o_c1w; const float* c1b = r.blob + r.o_c1b;
   const int A = r.A, PK = 4 * A, VK = 2 * A;
   // segment sizes, in the order they are walked
-  const long long n[12] = {27 * 32, 36 * 32, 72 * 32, 4 * 32 * 32, 9 * 64 * 32, 9 * 128 * 64, HEAD_N * 128,
-                           (long long)A * r.PKp, 64LL * r.VKp, 32 + 64 + 128 + 8, A + 64 + 64 + 1, 0};
+  const long long n[14] = {27 * 32, 36 * 32, 72 * 32, 4 * 32 * 32, 9 * 64 * 32, 9 * 128 * 64, HEAD_N * 128,
+                           (long long)A * r.PKp, 64LL * r.VKp, 32 + 64 + 128 + 8, A + 64 + 64 + 1, C1T_TAB_FLOATS, 9 * 32, 0};
   long long total = 0;
-  for (int i = 0; i < 11; i++) total += n[i];
+  for (int i = 0; i < 13; i++) total += n[i];
   for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
     long long i = idx;
     int seg = 0;
@@ -2257,11 +2503,22 @@ __global__ void stem_repack_kernel(StemRepack r) {
       else if (k < 96) r.b2[k - 32] = r.blob[r.o_c2b + k - 32];
       else if (k < 224) r.b3[k - 96] = r.blob[r.o_c3b + k - 96];
       else { const int j = k - 224; r.head_b8[j] = j < 4 ? r.blob[r.o_pcb + j] : (j < 6 ? r.blob[r.o_vcb + j - 4] : 0.f); }
-    } else {                                          // FC biases and the value tail
+    } else if (seg == 10) {                           // FC biases and the value tail
       if (k < A) r.pfc_b[k] = r.blob[r.o_pfb + k];
       else if (k < A + 64) r.vfc1_b[k - A] = r.blob[r.o_v1b + k - A];
       else if (k < A + 128) r.vfc2_w[k - A - 64] = r.blob[r.o_v2w + k - A - 64];
       else r.vfc2_b[0] = r.blob[r.o_v2b];
+    } else if (seg == 11) {                           // w1_tab2 [ky][own3 | opp3 << 3][32]: kx ascending per plane, then own + opp
+      const int co = k % 32, pat = (k / 32) % 64, ky = k / 2048;
+      float p0 = 0.f, p1 = 0.f;
+      for (int kx = 0; kx < 3; kx++) {
+        if (pat & (1 << kx)) p0 = __fadd_rn(p0, c1w[(co * 4 + 0) * 9 + ky * 3 + kx]);
+        if (pat & (8 << kx)) p1 = __fadd_rn(p1, c1w[(co * 4 + 1) * 9 + ky * 3 + kx]);
+      }
+      r.w1_tab2[k] = __fadd_rn(p0, p1);
+    } else {                                          // w1_lm [ky][kx][32]
+      const int co = k % 32, t = k / 32;
+      r.w1_lm[k] = c1w[(co * 4 + 2) * 9 + t];
     }
   }
 }
@@ -2307,9 +2564,10 @@ int azp_umma_reload_device(azp_engine* e, NetWeights* W, const float* dev_blob, 
   take(r.o_pfw, A * 4 * A); take(r.o_pfb, A); take(r.o_vcw, 2 * 128); take(r.o_vcb, 2);
   take(r.o_v1w, 64 * 2 * A); take(r.o_v1b, 64); take(r.o_v2w, 64); take(r.o_v2b, 1);
   r.w1_bits = U->w1_bits; r.w1_tab = U->w1_tab; r.w1_planes = U->w1_planes; r.b1 = U->b1; r.b2 = U->b2; r.b3 = U->b3;
+  r.w1_tab2 = U->w1_tab2; r.w1_lm = U->w1_lm;
   r.head_b8 = U->head_b8; r.pfc_b = W->pfc_b; r.vfc1_b = W->vfc1_b; r.vfc2_w = W->vfc2_w; r.vfc2_b = W->vfc2_b;
   r.w1_umma = U->w1_umma; r.w2 = U->w2; r.w3 = U->w3; r.head_w16 = U->head_w16; r.wp16 = U->wp16; r.wv16 = U->wv16;
-  if (!r.w1_bits || !r.w1_tab || !r.w1_planes || !r.b1 || !r.b2 || !r.b3 || !r.head_b8 || !r.pfc_b || !r.vfc1_b ||
+  if (!r.w1_tab2 || !r.w1_lm || !r.w1_bits || !r.w1_tab || !r.w1_planes || !r.b1 || !r.b2 || !r.b3 || !r.head_b8 || !r.pfc_b || !r.vfc1_b ||
       !r.vfc2_w || !r.vfc2_b || !r.w1_umma || !r.w2 || !r.w3 || !r.head_w16 || !r.wp16 || !r.wv16)
     return AZP_ERR_UNSUPPORTED;
   stem_repack_kernel<<<148 * 2, 256, 0, s>>>(r);
@@ -2387,6 +2645,7 @@ static int run_trunk(azp_engine* e, NetWeights* W, const int32_t* count_dev, int
   a2.fc_pbias = nullptr; a2.fc_vbias = nullptr; a2.fc_vw2 = nullptr; a2.fc_vb2 = nullptr; a2.fc_logits = nullptr; a2.fc_value = nullptr;
   a2.feat_done = ws->feat_done; a2.fc_done = ws->fc_done;       // conv2 resets them for the conv3 launch that follows
   a2.debug = bringup_debug_bits();
+  { const char* v = getenv("AZP_CLK_CTA"); a2.clk_cta = v ? atoi(v) : 0; }
   azp_prof_begin(e, AZP_PROF_CONV2, count_dev, count_host, s);
   if (from_bits)
     azp_launch(conv_umma_kernel<32, 64, STAGES2, false, true>, grid, CONV_THREADS_BITS, ws->smem2, s, true, ws->map_act1,
@@ -2401,6 +2660,7 @@ static int run_trunk(azp_engine* e, NetWeights* W, const int32_t* count_dev, int
   a3.NJ = W->PC + W->VC; a3.PC = W->PC; a3.PKp = ws->PKp; a3.FK = ws->FK;
   a3.single = ws->single;
   a3.clk = bringup_clk(ws, 1);
+  if (!a3.clk) a3.clk = bringup_clk(ws, 5);            // 5: stamps of the fused FC items (tools/fc_fused_probe.py)
   // The FC layers ride inside conv3 for the leaf batches the search evaluates from the front (raw logits into the engine's
   // policy buffer); azp_net_forward (softmax wanted, caller's buffers), the arena's back-filled batch and the CTA-pair
   // variant keep the separate FC launch.  Both run the same UMMA sequence: bit-identical outputs.
@@ -2503,6 +2763,14 @@ int azp_umma_eval_leaves(azp_engine* e, NetWeights* W, const int32_t* count_dev,
   if (!fuse && ws->conv1_mode == 1) {
     int st = launch_conv1_umma(e, U, count_dev, count_host, back, nullptr, s);
     if (st) return st;
+  } else if (!fuse && ws->conv1_mode == 2) {
+    // two warps per board, four boards per CTA, four CTAs per SM (boards are dealt to the CTAs round robin)
+    const int grid = zmax < 4 * ws->sms ? zmax : 4 * ws->sms;
+    azp_prof_begin(e, AZP_PROF_CONV1, count_dev, count_host, s);
+    AZP_DISPATCH_NW_PDL(e->NW, conv1_table_kernel, grid, 256, 0, s, g, e->tv.leaf_x, e->tv.leaf_o, e->tv.leaf_tm,
+                        e->tv.leaf_last, U->w1_tab2, U->w1_lm, U->b1, ws->act1, count_dev, count_host, back);
+    azp_count_launch();
+    azp_prof_end(e, AZP_PROF_CONV1, s);
   } else if (!fuse) {
     const int grid = zmax < 4 * ws->sms ? zmax : 4 * ws->sms;
     AZP_DISPATCH_NW(e->NW, conv1_bits_kernel, grid, 256, 0, s, g, e->tv.leaf_x, e->tv.leaf_o, e->tv.leaf_tm,
@@ -2559,6 +2827,10 @@ int azp_umma_eval_planes(azp_engine* e, NetWeights* W, int n, const float* plane
   if (ws->conv1_mode == 1) {
     int st = launch_conv1_umma(e, U, nullptr, n, 0, planes, s);
     if (st) return st;
+  } else if (ws->conv1_mode == 2) {
+    const int grid = n < 4 * ws->sms ? n : 4 * ws->sms;
+    conv1_table_planes_kernel<<<grid, 256, 4 * g.A * sizeof(float), s>>>(g, n, planes, U->w1_planes, U->b1, ws->act1);
+    azp_count_launch();
   } else {
     const int grid = n < 4 * ws->sms ? n : 4 * ws->sms;
     conv1_planes_kernel<<<grid, 256, 4 * g.A * sizeof(float), s>>>(g, n, planes, U->w1_planes, U->b1, ws->act1);
