@@ -312,3 +312,95 @@ def test_hook_backs_up_the_evaluators_python_float_unrounded(az):
     _, _, visits = az.MCTS(ref_fn, sims, 2.0).run_batch(gs, 1.0)
     assert np.array_equal(visits, results[False])
     eng.close()
+
+
+# ---- replay ring writer, raw-slab exchange, per-kernel profiling ---------------------------------------------------------
+def test_ring_writer_kernel_has_deque_semantics_and_augments(az):
+    """azp_augment_write_ring == ReplayBuffer.extend (replay_buffer.py:27-29: append in order, evict the oldest) fused with
+    the augmentation; the position count may live on the device (slab header)."""
+    from alphazero_piskvorky_b200 import engine as e
+    from oracle import replay
+    size, A = 5, 25
+    rs = np.random.RandomState(4)
+    ring, ref = az.ReplayBuffer(capacity=40), replay.Fifo(40)
+    k = 0
+    for n in (7, 9, 30, 55, 3):                                   # 55 > capacity: only the newest 40 survive
+        planes = torch.from_numpy(rs.random_sample((n, 4, size, size)).astype(np.float32)).cuda()
+        planes[:, 0, 0, 0] = torch.arange(k, k + n, dtype=torch.float32)
+        pi = torch.from_numpy(rs.random_sample((n, size, size)).astype(np.float32)).cuda()
+        z = torch.arange(k, k + n, dtype=torch.int32).cuda()
+        ring.extend_device(planes, pi, z)                         # CUDA tensors: the kernel path
+        ref.extend(list(range(k, k + n)))
+        k += n
+        got = ring.device_all()
+        assert got[2].cpu().tolist() == ref.all()
+        assert got[0][:, 0, 0, 0].cpu().tolist() == [float(v) for v in ref.all()]
+    # device-side count + D4 augmentation on the way in: equals azp_augment_write of the first `cnt` positions
+    cap, cnt = 12, 5
+    planes = torch.from_numpy((rs.random_sample((cap, 4, size, size)) < 0.3).astype(np.float32)).cuda()
+    pi = torch.from_numpy(rs.random_sample((cap, size, size)).astype(np.float32)).cuda()
+    z = torch.from_numpy(rs.randint(-1, 2, size=cap).astype(np.int32)).cuda()
+    n_dev = torch.tensor([cnt], dtype=torch.int32).cuda()
+    ring2 = az.ReplayBuffer(capacity=64)
+    ring2.write_slab(planes, pi, z, n_max=cap, n_dev=n_dev, augment=az.AUGMENT_D4)
+    assert ring2.sync_head() == cnt * 8
+    op, opi, oz = e.augment_write(planes[:cnt], pi[:cnt], z[:cnt], size, az.AUGMENT_D4)
+    got = ring2.device_all()
+    assert torch.equal(got[0], op) and torch.equal(got[1], opi) and torch.equal(got[2], oz)
+
+
+def test_example_exchange_on_one_gpu_matches_engine_side_augmentation(az):
+    """The multi-GPU example path at world size 1: raw positions -> slab -> (all-gather) -> D4 augmentation into the ring
+    on the receiving side == the engine's own D4 writer on the same games (same Philox streams)."""
+    from alphazero_piskvorky_b200 import dist as azd
+    size, win, sims, slots, ngames = 5, 4, 24, 8, 12
+    params = onet.synthetic_stem_params(size, seed=3, scale=2.0)
+    out = {}
+    for mode in ("exchange", "engine"):
+        eng = az.Engine(board=size, win_length=win, games=slots, sims=sims, seed=17,
+                        augment=az.AUGMENT_NONE if mode == "exchange" else az.AUGMENT_D4)
+        eng.load_state_dict(params)
+        if mode == "exchange":
+            ex = azd.ExampleExchange(size, eng.example_capacity_floor(), torch.device("cuda", 0))
+            ring = az.ReplayBuffer(capacity=8 * 25 * ngames)
+            step, st = 0, az.MORE
+            with torch.cuda.stream(torch.cuda.Stream()):
+                while st == az.MORE:
+                    k = step & 1
+                    ex.wait_slab(k)
+                    st, _, _, _, w = eng.selfplay(ngames, max_move_steps=1, out=ex.out_views(k), resume=step > 0)
+                    ex.exchange(k, w, ring=ring, augment=az.AUGMENT_D4)
+                    step += 1
+                ex.wait()
+            torch.cuda.synchronize()
+            assert ring.sync_head() == eng.counters()["positions"] * 8
+            out[mode] = tuple(t.cpu() for t in ring.device_all())
+        else:
+            out[mode] = tuple(t.cpu() for t in eng.selfplay_all(ngames))
+        eng.close()
+    # games that finish in the same move step reach the slab in the order of an atomic counter: compare as multisets
+    def keyed(t):
+        P, Q, Z = (x.numpy() for x in t)
+        return sorted((P[i].tobytes(), Q[i].tobytes(), int(Z[i])) for i in range(len(Z)))
+    assert keyed(out["exchange"]) == keyed(out["engine"]) and len(out["engine"][2]) > 0
+
+
+def test_per_kernel_profiling_brackets_every_step_kernel(az):
+    """azp_get_profile_kernel: with profiling on, the last simulation steps of a move run as plain launches, each kernel
+    between its own CUDA events; units = leaves (net kernels) / game slots (tree kernels)."""
+    size, win, sims, n = 9, 5, 64, 32
+    eng = az.Engine(board=size, win_length=win, games=n, sims=sims, net_dtype=az.DTYPE_BF16, augment=az.AUGMENT_NONE)
+    eng.load_state_dict(onet.synthetic_stem_params(size, seed=1, scale=2.0))
+    with torch.cuda.stream(torch.cuda.Stream()):
+        ref = eng.selfplay(n, max_move_steps=2)[4]
+        eng.set_profiling(True)
+        eng.selfplay(n, max_move_steps=1, resume=True)
+        prof = eng.get_profile_kernels()
+        eng.set_profiling(False)
+    for name in ("dominant", "advance", "conv1", "conv2", "fc"):
+        ms, launches, units = prof[name]
+        assert launches >= 39 and ms > 0, name                     # AZP_PROF_TAIL = 40 plain steps (advance: 39 + root)
+        assert units <= launches * n and units > 0
+    assert prof["end_move"][1] == 1 and prof["root_expand"][1] == 1 and prof["end_move"][2] == n
+    assert all(v == (0.0, 0, 0.0) for v in eng.get_profile_kernels().values())      # read-and-reset
+    eng.close()
