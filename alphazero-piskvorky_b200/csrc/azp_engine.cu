@@ -131,6 +131,7 @@ static int create_impl(azp_engine* e) {
   e->n_temperature = (int)T.size();
   if ((st = azp_net_create(e))) return st;
   { const char* v = getenv("AZP_GRAPH"); e->use_graph = v ? atoi(v) != 0 : true; }
+  { const char* v = getenv("AZP_ARENA_ALIGNED"); e->arena_aligned = v ? atoi(v) != 0 : 1; }
   AZP_CUDA(e, cudaDeviceSynchronize());
   return AZP_OK;
 }
@@ -182,7 +183,7 @@ extern "C" void azp_destroy(azp_engine* e) {
   cudaDeviceSynchronize();
   for (cudaEvent_t ev : e->prof_events) cudaEventDestroy(ev);
   if (e->reload_ev) cudaEventDestroy(e->reload_ev);
-  if (e->graph_exec) cudaGraphExecDestroy(e->graph_exec);
+  for (cudaGraphExec_t ge : e->graph_exec) if (ge) cudaGraphExecDestroy(ge);
   if (e->cfg.net_dtype == AZP_DTYPE_BF16) azp_umma_destroy(e);
   azp_net_destroy(e);
   for (void* p : e->allocs) cudaFree(p);
@@ -302,10 +303,10 @@ extern "C" int azp_root_priors(azp_engine* e, float* priors, void* stream) {
 }
 
 // evaluate the leaf batch of counter pair `parity` with the engine's own net(s)
-static int eval_step(azp_engine* e, int two_nets, int parity, cudaStream_t s) {
+static int eval_step(azp_engine* e, int two_nets, int net_slot, int parity, cudaStream_t s) {
   int st;
   TreeView& tv = e->tv;
-  if ((st = azp_net_eval_leaves(e, 0, tv.n_leaves + parity * 2 + 0, 0, 0, s))) return st;
+  if ((st = azp_net_eval_leaves(e, two_nets ? 0 : net_slot, tv.n_leaves + parity * 2 + 0, 0, 0, s))) return st;
   if (two_nets && (st = azp_net_eval_leaves(e, 1, tv.n_leaves + parity * 2 + 1, 0, 1, s))) return st;
   return AZP_OK;
 }
@@ -317,18 +318,19 @@ static int eval_step(azp_engine* e, int two_nets, int parity, cudaStream_t s) {
 // sequence is identical from move to move: two consecutive iterations are captured ONCE into a CUDA graph and
 // replayed (removes per-launch CPU cost and most launch gaps).  The kernels of the chain are launched with
 // programmatic dependent launch, inside the graph too.
-static int search_move(azp_engine* e, int n, int add_noise, int two_nets, cudaStream_t s) {
+// `net_slot`: the weight slot that evaluates the (single) leaf batch when two_nets == 0
+static int search_move(azp_engine* e, int n, int add_noise, int two_nets, int net_slot, cudaStream_t s) {
   int st;
   TreeView& tv = e->tv;
   AZP_CUDA(e, cudaMemsetAsync(tv.n_leaves, 0, 4 * sizeof(int32_t), s));
   if ((st = azp_tree_begin_move(e, n, 1, 1, /*parity=*/1, s))) return st;
-  if ((st = eval_step(e, two_nets, 1, s))) return st;
+  if ((st = eval_step(e, two_nets, net_slot, 1, s))) return st;
   if ((st = azp_tree_root_expand(e, n, e->d_policy, 1, add_noise, e->policy_logits, s))) return st;
   const int steps = (e->cfg.sims + e->K - 1) / e->K;      // K descents per game per step
   if ((st = azp_tree_select(e, n, 1, 0, s))) return st;   // descent of step 0
   // iteration i: net(pair i&1), then expand+backup(i) fused with the descent of step i+1 (pair (i+1)&1)
   auto iteration = [&](int i, bool last) -> int {
-    int r = eval_step(e, two_nets, i & 1, s);
+    int r = eval_step(e, two_nets, net_slot, i & 1, s);
     if (r) return r;
     if (last) return azp_tree_expand_backup(e, n, e->d_policy, e->d_value, 1, e->policy_logits, 0, s);
     return azp_tree_advance(e, n, e->d_policy, e->d_value, 1, e->policy_logits, 1, (i + 1) & 1, s);
@@ -341,11 +343,12 @@ static int search_move(azp_engine* e, int n, int add_noise, int two_nets, cudaSt
   const int plain_tail = e->profiling ? (steps < AZP_PROF_TAIL ? steps : AZP_PROF_TAIL) : 1;
   if (want_graph) {
     const int key = n * 2 + two_nets;
-    if (e->graph_exec && (e->graph_key != key || e->graph_epoch != e->weights_epoch)) {
-      cudaGraphExecDestroy(e->graph_exec);
-      e->graph_exec = nullptr;
+    const int gi = two_nets ? 0 : (net_slot & 1);
+    if (e->graph_exec[gi] && (e->graph_key[gi] != key || e->graph_epoch[gi] != e->weights_epoch)) {
+      cudaGraphExecDestroy(e->graph_exec[gi]);
+      e->graph_exec[gi] = nullptr;
     }
-    if (!e->graph_exec) {
+    if (!e->graph_exec[gi]) {
       // capture is best effort: any failure falls back to plain stream launches for this engine
       cudaGraph_t graph = nullptr;
       const uint64_t launches_before = azp_launch_count();
@@ -356,25 +359,25 @@ static int search_move(azp_engine* e, int n, int add_noise, int two_nets, cudaSt
         if (!st) st = iteration(1, false);
         e->capturing = false;
         ce = cudaStreamEndCapture(s, &graph);
-        if (!st && ce == cudaSuccess && graph) ce = cudaGraphInstantiate(&e->graph_exec, graph, 0);
+        if (!st && ce == cudaSuccess && graph) ce = cudaGraphInstantiate(&e->graph_exec[gi], graph, 0);
         if (graph) cudaGraphDestroy(graph);
       }
-      if (st || ce != cudaSuccess || !e->graph_exec) {
+      if (st || ce != cudaSuccess || !e->graph_exec[gi]) {
         if (getenv("AZP_GRAPH_DEBUG")) fprintf(stderr, "[azp] graph capture failed: st=%d cuda=%s\n", st, cudaGetErrorString(ce));
         cudaGetLastError();                     // clear the sticky-free error state
-        e->graph_exec = nullptr;
+        e->graph_exec[gi] = nullptr;
         e->use_graph = false;
       } else {
-        e->graph_key = key;
-        e->graph_epoch = e->weights_epoch;
-        e->graph_launches_per_replay = (int)(azp_launch_count() - launches_before);   // kernels per replay
+        e->graph_key[gi] = key;
+        e->graph_epoch[gi] = e->weights_epoch;
+        e->graph_launches_per_replay[gi] = (int)(azp_launch_count() - launches_before);   // kernels per replay
       }
     }
     // the last iteration (no descent after it) always runs as plain launches
     e->note_stream(s);
-    for (; e->graph_exec && sim + 2 <= steps - plain_tail; sim += 2) {
-      AZP_CUDA(e, cudaGraphLaunch(e->graph_exec, s));
-      azp_count_launch(e->graph_launches_per_replay);
+    for (; e->graph_exec[gi] && sim + 2 <= steps - plain_tail; sim += 2) {
+      AZP_CUDA(e, cudaGraphLaunch(e->graph_exec[gi], s));
+      azp_count_launch(e->graph_launches_per_replay[gi]);
     }
   }
   for (; sim < steps; sim++)
@@ -391,7 +394,7 @@ extern "C" int azp_search(azp_engine* e, int slot, int n, const uint64_t* x, con
   set_roots_kernel<<<(e->cfg.games + 127) / 128, 128, 0, s>>>(e->tv, n, x, o, to_move, last, ply, game_id);
   azp_count_launch();
   e->search_n = n;
-  int st = search_move(e, n, add_noise, 0, s);
+  int st = search_move(e, n, add_noise, 0, 0, s);
   if (st) return st;
   if (visits && (st = azp_tree_root_visits(e, n, visits, s))) return st;
   return check_device_error(e, s);
@@ -437,7 +440,10 @@ static int episodes_run(azp_engine* e, long long first_game, long long n_games, 
   }
   long long* d_out_written = e->d_sched + 4;
   int st;
+  // arena mode of the kernels: 1 = two leaf batches per step, 2 = phase-aligned (one batch, one net per step; see azp_tree.cu)
+  const int amode = arena ? (e->arena_aligned ? 2 : 1) : 0;
   if (!resume) {
+    e->arena_step = 0;
     long long lfirst, lcount;
     rank_block(e, first_game, n_games, &lfirst, &lcount);
     long long sched[8] = {0, lcount, 0, lfirst, 0, 0, 0, 0};
@@ -445,7 +451,7 @@ static int episodes_run(azp_engine* e, long long first_game, long long n_games, 
     AZP_CUDA(e, cudaMemsetAsync(e->d_raw_count, 0, 2 * sizeof(int32_t), s));
     AZP_CUDA(e, cudaMemsetAsync(e->d_status, 0, G, s));
     AZP_CUDA(e, cudaStreamSynchronize(s));     // `sched` is a stack buffer
-    if ((st = azp_episode_seat(e, G, arena, s))) return st;
+    if ((st = azp_episode_seat(e, G, amode, /*next_phase=*/0, s))) return st;
     e->sp_total = lcount;
   } else {
     AZP_CUDA(e, cudaMemsetAsync(d_out_written, 0, sizeof(long long), s));
@@ -456,9 +462,12 @@ static int episodes_run(azp_engine* e, long long first_game, long long n_games, 
   if (e->sp_total == 0) return AZP_OK;
   for (int step = 0; max_move_steps <= 0 || step < max_move_steps; step++) {
     if (!arena && capacity - written < e->raw_capacity * mult) { *host_written = written; return AZP_MORE; }
-    if ((st = search_move(e, G, arena ? 0 : 1, arena, s))) return st;
-    if ((st = azp_episode_end_move(e, G, arena, s))) return st;
-    if ((st = azp_episode_finish(e, G, arena, s))) return st;
+    const int phase = (int)(e->arena_step & 1);
+    if (amode == 2 && (st = azp_episode_activate(e, G, phase, s))) return st;
+    if ((st = search_move(e, G, arena ? 0 : 1, amode == 1, amode == 2 ? phase : 0, s))) return st;
+    if ((st = azp_episode_end_move(e, G, amode, s))) return st;
+    if ((st = azp_episode_finish(e, G, amode, /*next_phase=*/phase ^ 1, s))) return st;
+    e->arena_step++;
     if (!arena) {
       azp_prof_begin(e, AZP_PROF_AUGMENT, e->d_raw_count, 0, s);        // units = raw positions of this move step
       if ((st = azp_augment_launch(e->cfg.board, mode, (int)e->raw_capacity, e->d_raw_count, e->d_raw_planes,

@@ -170,9 +170,11 @@ struct azp_engine {
   int parity = 0;                  // which pair of leaf counters the current step uses (step-by-step API)
   // CUDA graph of two consecutive simulation steps (see search_move)
   bool use_graph = true;
-  cudaGraphExec_t graph_exec = nullptr;
-  int graph_key = -1, graph_launches_per_replay = 0;
-  uint64_t weights_epoch = 0, graph_epoch = 0;
+  cudaGraphExec_t graph_exec[2] = {nullptr, nullptr};    // one per weight slot that evaluates the front batch
+  int graph_key[2] = {-1, -1}, graph_launches_per_replay[2] = {0, 0};
+  uint64_t weights_epoch = 0, graph_epoch[2] = {0, 0};
+  int arena_aligned = 1;           // phase-aligned arena (AZP_ARENA_ALIGNED=0: two leaf batches per step)
+  long long arena_step = 0;        // move steps since the current match started (its parity is the phase)
   bool capturing = false;          // inside cudaStreamBeginCapture/EndCapture of the step graph
   // per-kernel profiling of the dominant kernel (roofline.achieved in bench.py)
   bool profiling = false;
@@ -227,9 +229,10 @@ int azp_tree_advance(azp_engine* e, int n, const float* policy, const float* val
 int azp_tree_root_visits(azp_engine* e, int n, int32_t* visits, cudaStream_t s);
 int azp_tree_root_priors(azp_engine* e, int n, float* priors, cudaStream_t s);
 int azp_tree_leaf_states(azp_engine* e, int n, uint64_t* x, uint64_t* o, uint8_t* tm, int16_t* last, uint8_t* kind, cudaStream_t s);
-int azp_episode_seat(azp_engine* e, int n, int arena, cudaStream_t s);
+int azp_episode_seat(azp_engine* e, int n, int arena, int next_phase, cudaStream_t s);
+int azp_episode_activate(azp_engine* e, int n, int phase, cudaStream_t s);
 int azp_episode_end_move(azp_engine* e, int n, int arena, cudaStream_t s);
-int azp_episode_finish(azp_engine* e, int n, int arena, cudaStream_t s);
+int azp_episode_finish(azp_engine* e, int n, int arena, int next_phase, cudaStream_t s);
 int azp_episode_drain(azp_engine* e, long long* out_written_dev, int mult, cudaStream_t s);
 
 // profiling helpers (azp_engine.cu)

@@ -7,6 +7,7 @@
 #define SLOT_IDLE 0
 #define SLOT_PLAYING 1
 #define SLOT_PENDING 2     // game over, positions not yet emitted (raw slab was full)
+#define SLOT_DELAYED 3     // phase-aligned arena: seated, waits for the move step whose phase matches its first mover
 
 __device__ __forceinline__ void count(const TreeView& tv, int idx, unsigned long long v) {
   if (v) atomicAdd(tv.counters + idx, v);
@@ -453,7 +454,13 @@ struct EpisodeView {
 };
 
 // Hand the slot its next game (or park it).  Lane 0 only.
-__device__ __forceinline__ void seat_next_game(const TreeView& tv, const EpisodeView& ev, int g, int NW, int arena) {
+// `arena`: 0 self-play; 1 arena with two leaf batches per step (the games of a step are split between the two nets);
+// 2 PHASE-ALIGNED arena: X (candidate, weight slot 0) moves in the even move steps of the match and O (baseline, slot 1)
+// in the odd ones, in EVERY game -- a game whose first mover does not match the phase of the next step simply starts one
+// step later -- so a step evaluates ONE leaf batch with ONE net instead of two half batches with two nets.  Games are
+// independent and their random streams are keyed by (game id, ply), so the match is the same; only its kernel count halves.
+__device__ __forceinline__ void seat_next_game(const TreeView& tv, const EpisodeView& ev, int g, int NW, int arena,
+                                               int next_phase) {
   long long idx = atomicAdd((unsigned long long*)&ev.sched[0], 1ull);
   if (idx < ev.sched[1]) {
     long long gid = ev.sched[3] + idx;
@@ -465,18 +472,29 @@ __device__ __forceinline__ void seat_next_game(const TreeView& tv, const Episode
     tv.ply[g] = 0;
     tv.game_id[g] = gid;
     tv.active[g] = 1;
-    tv.net_of_game[g] = (uint8_t)(arena ? (first == 1 ? 0 : 1) : 0);
+    tv.net_of_game[g] = (uint8_t)(arena == 1 ? (first == 1 ? 0 : 1) : 0);
     ev.status[g] = SLOT_PLAYING;
+    if (arena == 2 && (first == 1) != (next_phase == 0)) {
+      tv.active[g] = 0;
+      ev.status[g] = SLOT_DELAYED;
+    }
   } else {
     tv.active[g] = 0;
     ev.status[g] = SLOT_IDLE;
   }
 }
 
-__global__ void seat_games_kernel(TreeView tv, EpisodeView ev, int n, int arena) {
+__global__ void seat_games_kernel(TreeView tv, EpisodeView ev, int n, int arena, int next_phase) {
   int g = blockIdx.x * blockDim.x + threadIdx.x;
   if (g >= n) return;
-  seat_next_game(tv, ev, g, tv.NW, arena);
+  seat_next_game(tv, ev, g, tv.NW, arena, next_phase);
+}
+
+// phase-aligned arena, start of a move step: the waiting games whose first mover matches this step's phase begin
+__global__ void arena_activate_kernel(TreeView tv, EpisodeView ev, int n, int phase) {
+  int g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= n || ev.status[g] != SLOT_DELAYED) return;
+  if ((tv.root_tm[g] == 1) == (phase == 0)) { ev.status[g] = SLOT_PLAYING; tv.active[g] = 1; }
 }
 
 // MCTS.run epilogue + the worker's bookkeeping: pi from root visits at T(ply), sample the move,
@@ -556,7 +574,7 @@ __global__ void end_move_kernel(RulesParams rp, TreeView tv, EpisodeView ev, int
     tv.root_tm[g] = (uint8_t)(3 - tm);
     tv.root_last[g] = (int16_t)action;
     tv.ply[g] = ply + 1;
-    if (arena) tv.net_of_game[g] = (uint8_t)((3 - tm) == 1 ? 0 : 1);
+    if (arena == 1) tv.net_of_game[g] = (uint8_t)((3 - tm) == 1 ? 0 : 1);
     count(tv, CNT_PLIES, 1);
     if (res) {
       ev.result[g] = (uint8_t)res;
@@ -571,7 +589,7 @@ __global__ void end_move_kernel(RulesParams rp, TreeView tv, EpisodeView ev, int
 // Emit the finished game's positions as raw (planes, pi, z) rows and seat the next game.
 // z = 0 on a draw, +1 if the player to move at that position won, else -1 (self_play.py:71).
 template <int NW>
-__global__ void finish_games_kernel(RulesParams rp, TreeView tv, EpisodeView ev, int n, int arena) {
+__global__ void finish_games_kernel(RulesParams rp, TreeView tv, EpisodeView ev, int n, int arena, int next_phase) {
   int g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (g >= n || ev.status[g] != SLOT_PENDING) return;
   const int A = rp.A;
@@ -611,7 +629,7 @@ __global__ void finish_games_kernel(RulesParams rp, TreeView tv, EpisodeView ev,
   }
   if (lane == 0) {
     atomicAdd((unsigned long long*)&ev.sched[2], 1ull);
-    seat_next_game(tv, ev, g, NW, arena);
+    seat_next_game(tv, ev, g, NW, arena, next_phase);
   }
 }
 
@@ -710,8 +728,8 @@ int azp_tree_leaf_states(azp_engine* e, int n, uint64_t* x, uint64_t* o, uint8_t
   azp_count_launch();
   return azp_check_launch();
 }
-int azp_episode_seat(azp_engine* e, int n, int arena, cudaStream_t s) {
-  seat_games_kernel<<<(n + 127) / 128, 128, 0, s>>>(e->tv, episode_view(e), n, arena);
+int azp_episode_seat(azp_engine* e, int n, int arena, int next_phase, cudaStream_t s) {
+  seat_games_kernel<<<(n + 127) / 128, 128, 0, s>>>(e->tv, episode_view(e), n, arena, next_phase);
   azp_count_launch();
   return azp_check_launch();
 }
@@ -723,10 +741,15 @@ int azp_episode_end_move(azp_engine* e, int n, int arena, cudaStream_t s) {
   azp_prof_end(e, AZP_PROF_END_MOVE, s);
   return azp_check_launch();
 }
-int azp_episode_finish(azp_engine* e, int n, int arena, cudaStream_t s) {
+int azp_episode_activate(azp_engine* e, int n, int phase, cudaStream_t s) {
+  arena_activate_kernel<<<(n + 127) / 128, 128, 0, s>>>(e->tv, episode_view(e), n, phase);
+  azp_count_launch();
+  return azp_check_launch();
+}
+int azp_episode_finish(azp_engine* e, int n, int arena, int next_phase, cudaStream_t s) {
   EpisodeView ev = episode_view(e);
   azp_prof_begin(e, AZP_PROF_FINISH, nullptr, n, s);
-  AZP_DISPATCH_NW(e->NW, finish_games_kernel, warp_grid(n), 128, 0, s, e->rp, e->tv, ev, n, arena);
+  AZP_DISPATCH_NW(e->NW, finish_games_kernel, warp_grid(n), 128, 0, s, e->rp, e->tv, ev, n, arena, next_phase);
   azp_count_launch();
   azp_prof_end(e, AZP_PROF_FINISH, s);
   return azp_check_launch();

@@ -200,7 +200,11 @@ int azp_selfplay_run(azp_engine* e, int64_t first_game, int64_t n_games, int res
                      int64_t capacity, int64_t* host_written, void* stream);
 /* ModelEvaluator.evaluate, evaluator.py:38-122: candidate (slot 0, plays X) vs baseline (slot 1,
  * plays O); game i has X to move first iff i is even; no root noise; T = table[step].
- * host_wld = {candidate wins, baseline wins, draws} for this rank's games. */
+ * host_wld = {candidate wins, baseline wins, draws} for this rank's games.
+ * The lockstep is PHASE-ALIGNED: X moves in the even move steps of the match and O in the odd ones in every game (a game
+ * whose first mover does not match the phase of the step it is seated for starts one step later), so each step
+ * evaluates one leaf batch with one net.  Games are independent and their random streams are keyed by (game id, ply):
+ * the match is the one the two-batch schedule plays (AZP_ARENA_ALIGNED=0), with half the network launches. */
 int azp_arena_run(azp_engine* e, int64_t first_game, int64_t n_games, int64_t* host_wld, void* stream);
 /* the same match in slices of at most max_move_steps lockstep moves (0 = run to the end): returns AZP_MORE while games
  * remain (call again with resume != 0); host_wld is the tally since the match started.  Lets a caller watch the loop
@@ -209,7 +213,8 @@ int azp_arena_run_steps(azp_engine* e, int64_t first_game, int64_t n_games, int 
                         int64_t* host_wld, void* stream);
 /* Episode state of every slot as the drivers hold it (self_play.py:47-58 / evaluator.py:64-90 bookkeeping), copied
  * device-to-device; any pointer may be NULL.  ply int32 [games] = moves played in the slot's current game; game_id
- * int64 [games]; status uint8 [games] (0 idle / 1 playing / 2 finished, not yet emitted); moves uint16 [games][max_plies]
+ * int64 [games]; status uint8 [games] (0 idle / 1 playing / 2 finished, not yet emitted / 3 seated, waiting for its
+ * phase of the aligned arena); moves uint16 [games][max_plies]
  * and pi_hist float32 [games][max_plies][B*B] = the move played and the pi it was drawn from at every ply of the slot's
  * game (rows of a finished game stay readable until the slot's next game overwrites them). */
 int azp_episode_snapshot(azp_engine* e, int32_t* ply, int64_t* game_id, uint8_t* status, uint16_t* moves,

@@ -20,7 +20,7 @@ from oracle import arena as oarena, gomoku, mcts as omcts, net as onet, selfplay
 
 pytestmark = pytest.mark.gpu
 
-PLAYING = 1
+IDLE, PLAYING, PENDING, DELAYED = 0, 1, 2, 3
 
 
 @pytest.fixture(scope="module")
@@ -168,17 +168,26 @@ def test_arena_first_mover_step_counters_nets_and_tally_match_the_oracle(az, tab
     tally = {gomoku.X: 0, gomoku.O: 0, gomoku.DRAW: 0}
     seen_first = set()
     status_before, done, step, distinguishing = None, 0, 0, 0
+    movers = {}                              # move step -> sides that searched in it
     while True:
         st, wld = eng.arena_steps(ngames, max_move_steps=1, resume=step > 0)
         visits = eng.root_visits(slots).cpu().numpy()
         snap = {k: v.cpu().numpy() for k, v in eng.episode_snapshot().items()}
         for g, tr in enumerate(trackers):
-            if step == 0:
-                assert snap["ply"][g] == 1 and snap["status"][g] == PLAYING
+            seated_now = snap["status"][g] in (PLAYING, DELAYED)
+            if tr.state is None or tr.state.is_terminal():             # no live game tracked in this slot
+                if not seated_now:
+                    continue                                           # parked: the match has no more games
                 gid = int(snap["game_id"][g])
-                tr.seat(gid, gomoku.X if gid % 2 == 0 else gomoku.O)      # evaluator.py:64-69
-            elif status_before[g] != PLAYING:
-                continue
+                tr.seat(gid, gomoku.X if gid % 2 == 0 else gomoku.O)   # evaluator.py:64-69
+            if seated_now and snap["game_id"][g] == tr.gid:
+                # the tracked game is still in the slot: it either searched and moved in this step, or -- phase-aligned
+                # arena -- it is waiting for the step whose phase matches its first mover (only ever before its first move)
+                if snap["ply"][g] == len(tr.moves):
+                    assert len(tr.moves) == 0
+                    continue
+                assert snap["ply"][g] == len(tr.moves) + 1
+            # (otherwise the tracked game made its LAST move in this step and the slot already holds its successor)
             p = len(tr.moves)
             side = tr.state.to_move
             first = gomoku.X if tr.gid % 2 == 0 else gomoku.O
@@ -207,12 +216,15 @@ def test_arena_first_mover_step_counters_nets_and_tally_match_the_oracle(az, tab
             if tr.state.is_terminal():
                 tally[tr.state.result()] += 1
                 done += 1
-                if snap["status"][g] == PLAYING:
+                if snap["status"][g] in (PLAYING, DELAYED):                       # the slot's next game is seated already
                     assert snap["ply"][g] == 0 and snap["game_id"][g] != tr.gid
                     gid = int(snap["game_id"][g])
                     tr.seat(gid, gomoku.X if gid % 2 == 0 else gomoku.O)
+                    # all games of a move step are evaluated by one net: X moves in even steps, O in odd ones
+                    assert (snap["status"][g] == PLAYING) == ((tr.state.to_move == gomoku.X) == ((step + 1) % 2 == 0))
             else:
                 assert snap["game_id"][g] == tr.gid and snap["ply"][g] == p + 1
+            movers.setdefault(step, set()).add(side)
         status_before = snap["status"].copy()
         step += 1
         assert wld == (tally[gomoku.X], tally[gomoku.O], tally[gomoku.DRAW])       # candidate wins == X wins
@@ -220,6 +232,7 @@ def test_arena_first_mover_step_counters_nets_and_tally_match_the_oracle(az, tab
             break
         assert step < 40 * ngames
     assert done == ngames and seen_first == {gomoku.X, gomoku.O}
+    assert all(m == {gomoku.X if k % 2 == 0 else gomoku.O} for k, m in movers.items())     # one net per move step
     assert distinguishing >= (100 if table_kind == "index_revealing" else 20)      # a wrong index would have been seen
     win_rate = (wld[0] + 0.5 * wld[2]) / ngames                                    # evaluator.py:103-105
     assert oarena.should_promote(win_rate) == az.should_promote(win_rate)
