@@ -73,6 +73,7 @@ SIGNATURES = {
     "azp_search": (C.c_int, [P, C.c_int, C.c_int, P, P, P, P, P, P, C.c_int, P, P]),
     "azp_set_temperature_table": (C.c_int, [P, P, C.c_int]),
     "azp_set_augment_mode": (C.c_int, [P, C.c_int]),
+    "azp_set_slab_capacity": (C.c_int, [P, C.c_int64]),
     "azp_selfplay_run": (C.c_int, [P, C.c_int64, C.c_int64, C.c_int, C.c_int, P, P, P, C.c_int64,
                                    C.POINTER(C.c_int64), P]),
     "azp_arena_run": (C.c_int, [P, C.c_int64, C.c_int64, C.POINTER(C.c_int64), P]),

@@ -108,6 +108,7 @@ static int create_impl(azp_engine* e) {
   if ((st = e->alloc(&e->d_status, G))) return st;
   e->raw_capacity = (long long)(G * MP < 16384 ? G * MP : 16384);
   if (e->raw_capacity < (long long)MP) e->raw_capacity = MP;
+  e->raw_allocated = e->raw_capacity;
   if ((st = e->alloc(&e->d_raw_planes, (size_t)e->raw_capacity * 4 * A))) return st;
   if ((st = e->alloc(&e->d_raw_pi, (size_t)e->raw_capacity * A))) return st;
   if ((st = e->alloc(&e->d_raw_z, (size_t)e->raw_capacity))) return st;
@@ -401,6 +402,13 @@ extern "C" int azp_search(azp_engine* e, int slot, int n, const uint64_t* x, con
 }
 
 // ---- drivers ------------------------------------------------------------------------------------------------
+extern "C" int azp_set_slab_capacity(azp_engine* e, int64_t positions) {
+  if (!e || positions < 1) return AZP_ERR_INVALID_ARG;
+  long long cap = positions < e->raw_allocated ? positions : e->raw_allocated;
+  if (cap < e->max_plies) cap = e->max_plies;            // one whole game must always fit
+  e->raw_capacity = cap;
+  return AZP_OK;
+}
 extern "C" int azp_set_augment_mode(azp_engine* e, int mode) {
   if (!e || mode < 0 || mode > 2) return AZP_ERR_INVALID_ARG;
   e->cfg.augment_mode = mode;          // read by the self-play driver at every call

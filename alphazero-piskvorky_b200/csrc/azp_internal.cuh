@@ -163,7 +163,7 @@ struct azp_engine {
   uint8_t* d_status = nullptr;     // [G] slot status (see azp_tree.cu)
   float* d_raw_planes = nullptr; float* d_raw_pi = nullptr; int32_t* d_raw_z = nullptr;
   int32_t* d_raw_count = nullptr;  // [1]
-  long long raw_capacity = 0;
+  long long raw_capacity = 0, raw_allocated = 0;     // positions one move step may emit (azp_set_slab_capacity) / rows allocated
   long long* d_sched = nullptr;    // [4]: next local game index, games to play, finished, (spare)
   int max_plies = 0;
   int search_n = 0;                // number of game slots in the current step-by-step search

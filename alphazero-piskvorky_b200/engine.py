@@ -205,10 +205,16 @@ class Engine:
         check(self.lib.azp_set_augment_mode(self.h, int(mode)), self.h)
         self.augment = mode
 
+    def set_slab_capacity(self, positions):
+        """Bound the raw positions one move step emits (finished games that do not fit are emitted a step later)."""
+        check(self.lib.azp_set_slab_capacity(self.h, int(positions)), self.h)
+        mp = self.cfg.max_plies if 0 < self.cfg.max_plies < self.A else self.A
+        self._slab = max(min(int(positions), min(self.games * mp, 16384)), mp)
+
     def example_capacity_floor(self) -> int:
         """Smallest output capacity (examples) azp_selfplay_run accepts."""
         mp = self.cfg.max_plies if 0 < self.cfg.max_plies < self.A else self.A
-        raw = max(min(self.games * mp, 16384), mp)
+        raw = getattr(self, "_slab", None) or max(min(self.games * mp, 16384), mp)
         return raw * AUGMENT_MULT[self.augment]
 
     def selfplay(self, n_games, first_game=0, capacity=None, max_move_steps=0, out=None, resume=False):

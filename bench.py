@@ -391,6 +391,9 @@ def run_engine_arm(args):
     blob_dev = [torch.empty(b.numel(), device="cuda") for b in blobs_host]
     total_games = 1 << 40                    # endless stream of games: finished slots are re-seated
     mult = 8                                 # D4 on the receiving side
+    slab_rows = args.slab if args.slab > 0 else max(4096, 2 * games)     # steady state emits ~games positions per move step
+    if not arena:
+        eng.set_slab_capacity(slab_rows)     # positions per rank per move step on the wire; games that do not fit wait a step
     raw_cap = eng.example_capacity_floor()   # raw positions one move step can emit at most (AUGMENT_NONE: mult 1)
     exch = ring = None
     if not arena:
@@ -570,6 +573,7 @@ def run_engine_arm(args):
                         augment=az.AUGMENT_NONE, seed=0, rank=rank, world=world, device=local,
                         leaves_per_step=args.vl_leaves, **net_kw)
         eng.load_blob(blobs_host[0].numpy())
+        eng.set_slab_capacity(slab_rows)
         state["first"] = True
         run_steps(3, "plain")
         barrier()
@@ -728,6 +732,9 @@ def main():
                     help="1 = exact search (reference-identical visit counts); K > 1 = virtual-loss throughput mode")
     ap.add_argument("--vl-leaves", type=int, default=4, help="K of the virtual-loss side measurement")
     ap.add_argument("--bcast-every", type=int, default=4, help="N > 1: broadcast rank 0's weights every this many steps")
+    ap.add_argument("--slab", type=int, default=0,
+                    help="raw positions per rank per move step in the all-gathered slab (default max(4096, 2 x games): the "
+                         "steady state emits ~games positions per step)")
     ap.add_argument("--no-vl", action="store_true")
     ap.add_argument("--no-train", action="store_true", help="skip the training-step side measurement")
     ap.add_argument("--no-match", action="store_true", help="config 5: skip the whole-match measurement")

@@ -190,6 +190,11 @@ int azp_set_temperature_table(azp_engine* e, const double* host_table, int n);
  * AZP_AUGMENT_NONE emits raw positions -- the form that is all-gathered across ranks, the receiving side augments
  * (self_play.py:94-108 runs in the parent process in the reference too). */
 int azp_set_augment_mode(azp_engine* e, int mode);
+/* Upper bound on the raw positions one move step of azp_selfplay_run emits (default and maximum: min(games * max_plies,
+ * 16384); never below one whole game).  Finished games that do not fit wait -- their slot stays occupied -- and are
+ * emitted by a later step, so a small fixed-capacity slab can be exchanged between ranks every step.
+ * The output capacity azp_selfplay_run asks for shrinks with it. */
+int azp_set_slab_capacity(azp_engine* e, int64_t positions);
 /* SelfPlayManager.generate_self_play, self_play.py:110-159 + _worker, :29-77.
  * Plays global game ids [first_game, first_game + n_games) that belong to this rank, S sims per
  * move with root noise, writes augmented examples to out_* (capacity in examples).  Returns
