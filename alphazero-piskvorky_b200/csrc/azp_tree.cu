@@ -345,8 +345,10 @@ __device__ __forceinline__ bool expand_backup_body(const RulesParams& rp, const 
 // ---- kernels: the two halves alone (step-by-step API) and fused ------------------------------------------------
 // 2048 games = 512 CTAs of four warps: at >128 registers only 3 CTAs fit an SM (444 per wave) and the latency-bound
 // descent ran as TWO waves; capped so that one wave holds them all (4 CTAs x 148 SMs = 592)
+// 9x9 boards (NW <= 2) run with up to 4096 concurrent games: 1024 CTAs of four warps need SEVEN resident CTAs per SM to
+// stay one wave (the latency-bound descent does not care about the few spilled registers, it cares about waves)
 template <int NW>
-__global__ void __launch_bounds__(128, 4) select_kernel(RulesParams rp, TreeView tv, int n, double c_puct, int compact, int parity) {
+__global__ void __launch_bounds__(128, NW <= 2 ? 7 : 4) select_kernel(RulesParams rp, TreeView tv, int n, double c_puct, int compact, int parity) {
   pdl_wait();
   pdl_launch_dependents();
   int g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
@@ -372,7 +374,7 @@ __global__ void expand_backup_kernel(RulesParams rp, TreeView tv, int n, const f
 // both halves, so the two launches of the lockstep loop collapse into one (the tree lines just written are still
 // in L1/L2 when the descent re-reads them)
 template <int NW>
-__global__ void __launch_bounds__(128, 4) advance_kernel(RulesParams rp, TreeView tv, int n, const float* __restrict__ policy,
+__global__ void __launch_bounds__(128, NW <= 2 ? 7 : 4) advance_kernel(RulesParams rp, TreeView tv, int n, const float* __restrict__ policy,
                                const float* __restrict__ value, int by_slot, int logits, double c_puct, int compact,
                                int parity) {
   pdl_wait();
