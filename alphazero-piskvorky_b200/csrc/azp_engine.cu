@@ -133,6 +133,7 @@ static int create_impl(azp_engine* e) {
   if ((st = azp_net_create(e))) return st;
   { const char* v = getenv("AZP_GRAPH"); e->use_graph = v ? atoi(v) != 0 : true; }
   { const char* v = getenv("AZP_ARENA_ALIGNED"); e->arena_aligned = v ? atoi(v) != 0 : 1; }
+  { const char* v = getenv("AZP_GRAPH_ITERS"); int k = v ? atoi(v) : 8; e->graph_iters = k < 2 ? 2 : (k > 62 ? 62 : k) & ~1; }
   AZP_CUDA(e, cudaDeviceSynchronize());
   return AZP_OK;
 }
@@ -316,8 +317,9 @@ static int eval_step(azp_engine* e, int two_nets, int net_slot, int parity, cuda
 //   root eval -> root expand (+noise) -> descent 0 -> steps x (net -> expand+backup [+ descent of the next step])
 // The expand+backup of step i and the descent of step i+1 are ONE launch (advance_kernel).
 // The leaf counters are zeroed at the start of every move, so step i always uses counter pair i&1 and the
-// sequence is identical from move to move: two consecutive iterations are captured ONCE into a CUDA graph and
-// replayed (removes per-launch CPU cost and most launch gaps).  The kernels of the chain are launched with
+// sequence is identical from move to move: an even number of consecutive iterations (graph_iters, default 8 = 40
+// kernels) is captured ONCE into a CUDA graph and replayed (removes per-launch CPU cost and most launch gaps; a graph
+// boundary is a full dependency, so the programmatic overlap of the first kernel is lost once per replay).  The kernels of the chain are launched with
 // programmatic dependent launch, inside the graph too.
 // `net_slot`: the weight slot that evaluates the (single) leaf batch when two_nets == 0
 static int search_move(azp_engine* e, int n, int add_noise, int two_nets, int net_slot, cudaStream_t s) {
@@ -343,7 +345,7 @@ static int search_move(azp_engine* e, int n, int add_noise, int two_nets, int ne
   // events; the iterations before them (and every move step with profiling off) replay the captured graph.
   const int plain_tail = e->profiling ? (steps < AZP_PROF_TAIL ? steps : AZP_PROF_TAIL) : 1;
   if (want_graph) {
-    const int key = n * 2 + two_nets;
+    const int key = (n * 2 + two_nets) * 64 + e->graph_iters;
     const int gi = two_nets ? 0 : (net_slot & 1);
     if (e->graph_exec[gi] && (e->graph_key[gi] != key || e->graph_epoch[gi] != e->weights_epoch)) {
       cudaGraphExecDestroy(e->graph_exec[gi]);
@@ -356,8 +358,7 @@ static int search_move(azp_engine* e, int n, int add_noise, int two_nets, int ne
       cudaError_t ce = cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal);
       if (ce == cudaSuccess) {
         e->capturing = true;
-        st = iteration(0, false);
-        if (!st) st = iteration(1, false);
+        for (int k = 0; k < e->graph_iters && !st; k++) st = iteration(k, false);
         e->capturing = false;
         ce = cudaStreamEndCapture(s, &graph);
         if (!st && ce == cudaSuccess && graph) ce = cudaGraphInstantiate(&e->graph_exec[gi], graph, 0);
@@ -376,7 +377,7 @@ static int search_move(azp_engine* e, int n, int add_noise, int two_nets, int ne
     }
     // the last iteration (no descent after it) always runs as plain launches
     e->note_stream(s);
-    for (; e->graph_exec[gi] && sim + 2 <= steps - plain_tail; sim += 2) {
+    for (; e->graph_exec[gi] && sim + e->graph_iters <= steps - plain_tail; sim += e->graph_iters) {
       AZP_CUDA(e, cudaGraphLaunch(e->graph_exec[gi], s));
       azp_count_launch(e->graph_launches_per_replay[gi]);
     }

@@ -173,6 +173,7 @@ struct azp_engine {
   cudaGraphExec_t graph_exec[2] = {nullptr, nullptr};    // one per weight slot that evaluates the front batch
   int graph_key[2] = {-1, -1}, graph_launches_per_replay[2] = {0, 0};
   uint64_t weights_epoch = 0, graph_epoch[2] = {0, 0};
+  int graph_iters = 8;             // simulation steps per captured graph (even; AZP_GRAPH_ITERS)
   int arena_aligned = 1;           // phase-aligned arena (AZP_ARENA_ALIGNED=0: two leaf batches per step)
   long long arena_step = 0;        // move steps since the current match started (its parity is the phase)
   bool capturing = false;          // inside cudaStreamBeginCapture/EndCapture of the step graph
