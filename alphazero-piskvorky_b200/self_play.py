@@ -78,6 +78,35 @@ class SelfPlayManager:
             resume = True
         self._first_game += num_games
 
+    def generate_to_ring(self, num_games: int, ring, slab_positions: int = None):
+        """Multi-GPU data path (replaces the result queue of self_play.py:140-148): this rank
+        plays its share of ``num_games``; every move step the RAW positions leave in one fixed-capacity slab that is
+        all-gathered over the ranks on a side stream (NCCL; a device copy in a single process), and every rank expands
+        everybody's positions by ``self.augment`` straight into ``ring`` (a ``ReplayBuffer``) -- identical rings on all
+        ranks, no host synchronisation besides the driver's own.  Returns the number of examples appended."""
+        from .dist import ExampleExchange
+        eng = self.engine(num_games)
+        eng.load_state_dict(self.controller.net.state_dict())
+        eng.set_augment(AUGMENT_NONE)                       # raw positions on the wire, augmentation on the receiving side
+        if slab_positions:
+            eng.set_slab_capacity(slab_positions)
+        ex = ExampleExchange(self.board_size, eng.example_capacity_floor(), eng.device)
+        before = ring.sync_head()
+        step, st = 0, MORE
+        with torch.cuda.stream(eng._driver_stream()):
+            while st == MORE:
+                k = step & 1
+                ex.wait_slab(k)
+                st, _, _, _, w = eng.selfplay(num_games, first_game=self._first_game, out=ex.out_views(k),
+                                              max_move_steps=1, resume=step > 0)
+                ex.exchange(k, w, ring=ring, augment=self.augment)
+                step += 1
+            ex.wait()
+        torch.cuda.synchronize(eng.device)
+        eng.set_augment(self.augment)
+        self._first_game += num_games
+        return ring.sync_head() - before
+
     def generate_self_play(self, num_games: int, num_workers: int = None, flatten=False) -> list:
         """Returns the reference's flat list of ``(state Tensor f32 (4,B,B), pi ndarray f32 (B,B), z int)``.
         ``num_workers`` and ``flatten`` are accepted and ignored (the reference ignores ``flatten`` too)."""

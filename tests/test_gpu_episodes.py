@@ -417,3 +417,47 @@ def test_per_kernel_profiling_brackets_every_step_kernel(az):
     assert prof["end_move"][1] == 1 and prof["root_expand"][1] == 1 and prof["end_move"][2] == n
     assert all(v == (0.0, 0, 0.0) for v in eng.get_profile_kernels().values())      # read-and-reset
     eng.close()
+
+
+def test_selfplay_manager_ring_path_and_live_weights(az):
+    """Facade level: (i) SelfPlayManager.generate_to_ring -- the multi-GPU example path at world size 1 -- fills a device
+    ring with 8 examples per position; (ii) engines cached by MCTS / make_policy_value_fn notice every way the
+    controller's weights can change (the reference evaluates controller.net live, controller.py:39-53): in-place
+    load_state_dict, a torch optimizer step, a re-assigned net."""
+    net = az.GomokuNet(board_size=5)
+    ctrl = az.NeuralNetworkController(net, device="cuda")
+    mgr = az.SelfPlayManager(ctrl, device="cuda", mcts_params={"num_simulations": 16, "c_puct": 2.0}, concurrent_games=8)
+    ring = az.ReplayBuffer(capacity=4096)
+    n = mgr.generate_to_ring(10, ring, slab_positions=64)
+    assert n > 0 and n % 8 == 0 and ring.device_len() == n
+    planes, pi, z = ring.device_all()
+    assert planes.shape[1:] == (4, 5, 5) and float(pi.sum(dim=(1, 2)).sub(1).abs().max()) < 1e-4
+    assert set(z.cpu().tolist()) <= {-1, 0, 1}
+
+    fn = az.make_policy_value_fn(ctrl)
+    state = az.Gomoku(5, 4)
+    p0, v0 = fn(state)
+    torch.manual_seed(7)
+    other = az.GomokuNet(board_size=5)
+    ctrl.net.load_state_dict(other.state_dict())                 # as the reference's worker does (self_play.py:36)
+    p1, v1 = fn(state)
+    assert not np.allclose(p0, p1)
+    with torch.no_grad():
+        ref_logits, ref_v = other(state.encode().unsqueeze(0))
+    assert np.abs(p1.reshape(-1) - torch.softmax(ref_logits[0], 0).numpy()).max() <= 1e-5 and abs(v1 - float(ref_v)) <= 1e-5
+    opt = torch.optim.SGD(ctrl.net.parameters(), lr=0.5)         # a torch optimizer on net.parameters()
+    for q in ctrl.net.parameters():
+        q.grad = torch.ones_like(q)
+    opt.step()
+    p2, _ = fn(state)
+    assert not np.allclose(p1, p2)
+    torch.manual_seed(9)
+    ctrl.net = az.GomokuNet(board_size=5)                        # re-assigned module
+    p3, _ = fn(state)
+    assert not np.allclose(p2, p3)
+    m = az.MCTS(fn, 24, 2.0, seed=1)
+    _, _, va = m.run_batch([state], 1.0)
+    ctrl.net.load_state_dict(other.state_dict())
+    _, _, vb = m.run_batch([state], 1.0)
+    assert va.sum() == vb.sum() == 24 and not np.array_equal(va, vb)          # the cached search engine reloaded too
+    m.close()
