@@ -29,6 +29,27 @@ bool azp_pdl_enabled() {
   return v != 0;
 }
 
+#ifdef AZP_BRINGUP
+__device__ AzpTimeline* g_azp_tl = nullptr;
+static AzpTimeline* g_tl_host_ptr = nullptr;
+// AZP_TIMELINE=1 in a bring-up build: allocate the ring once per process and publish it to the kernels
+static void azp_timeline_setup() {
+  if (g_tl_host_ptr || !getenv("AZP_TIMELINE")) return;
+  if (cudaMalloc(&g_tl_host_ptr, sizeof(AzpTimeline)) != cudaSuccess) { g_tl_host_ptr = nullptr; return; }
+  cudaMemset(g_tl_host_ptr, 0, sizeof(AzpTimeline));
+  cudaMemcpyToSymbol(g_azp_tl, &g_tl_host_ptr, sizeof(g_tl_host_ptr));
+}
+int azp_timeline_read(void* out_dev, size_t bytes, cudaStream_t s) {
+  if (g_tl_host_ptr && !out_dev) return cudaMemsetAsync(g_tl_host_ptr, 0, sizeof(AzpTimeline), s) == cudaSuccess ? AZP_OK : AZP_ERR_CUDA;   // reset
+  if (!g_tl_host_ptr || bytes < sizeof(AzpTimeline)) return AZP_ERR_UNSUPPORTED;
+  if (cudaMemcpyAsync(out_dev, g_tl_host_ptr, sizeof(AzpTimeline), cudaMemcpyDeviceToDevice, s) != cudaSuccess) return AZP_ERR_CUDA;
+  return AZP_OK;
+}
+#else
+static void azp_timeline_setup() {}
+int azp_timeline_read(void*, size_t, cudaStream_t) { return AZP_ERR_UNSUPPORTED; }
+#endif
+
 RulesParams azp_make_rules(int B, int WL) {
   RulesParams rp;
   memset(&rp, 0, sizeof(rp));
@@ -162,6 +183,7 @@ extern "C" int azp_create(const azp_config* cfg, azp_engine** out) {
   if (cfg->device < 0 || cfg->device >= ndev) return bad("device ordinal out of range");
   AzpDeviceGuard dev_guard(cfg->device);
   { int cur = -1; if (cudaGetDevice(&cur) != cudaSuccess || cur != cfg->device) { azp_set_global_error("cudaSetDevice failed"); return AZP_ERR_CUDA; } }
+  azp_timeline_setup();
   azp_engine* e = new azp_engine();
   e->cfg = *cfg;
   e->A = cfg->board * cfg->board;
@@ -215,6 +237,8 @@ extern "C" int azp_net_forward(azp_engine* e, int slot, int n, const float* plan
 extern "C" int azp_debug_activations(azp_engine* e, int layer, int n, float* out, void* stream) {
   if (!e || !out || n < 1 || n > e->cfg.games) return AZP_ERR_INVALID_ARG;
   AzpDeviceGuard dev_guard(e->cfg.device);
+  if (layer == 11) return azp_timeline_read(nullptr, 0, (cudaStream_t)stream);                      // bring-up: clear the ring
+  if (layer == 10) return azp_timeline_read(out, (size_t)n * 1024 * 1024, (cudaStream_t)stream);   // bring-up: step timeline ring, n = MiB of `out`
   if (e->cfg.net_dtype != AZP_DTYPE_BF16) { e->set_error("debug activations exist on the bf16 path only"); return AZP_ERR_UNSUPPORTED; }
   return azp_umma_debug(e, layer, n, out, (cudaStream_t)stream);
 }

@@ -42,6 +42,67 @@ __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;"
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 bool azp_pdl_enabled();                        // AZP_PDL (default 1)
 
+// ---- step timeline (bring-up builds only: make BRINGUP=1, AZP_TIMELINE=1) ------------------------------------
+// Every kernel of the simulation step records, per launch, the earliest CTA entry, the earliest moment a CTA got past
+// pdl_wait() and the latest CTA exit as %globaltimer nanoseconds: the real overlap / gaps of the chain inside the
+// captured graph, which neither ncu (serialised) nor event brackets (they cut the dependent-launch edges) can show.
+// tools/step_timeline.py reads the ring (done[k] / participants = launches so far).
+#define AZP_TL_KERNELS 8
+#define AZP_TL_RING 4096
+enum { AZP_TL_ADVANCE = 0, AZP_TL_CONV1, AZP_TL_CONV2, AZP_TL_CONV3, AZP_TL_FC };
+struct AzpTimeline {
+  unsigned long long rec[AZP_TL_KERNELS][AZP_TL_RING][4];     // ~entry (min), ~start (min), end (max), spare
+  unsigned int launch[AZP_TL_KERNELS], done[AZP_TL_KERNELS];
+  unsigned long long cta[AZP_TL_KERNELS][320][4];             // last launch: per-CTA start (past pdl_wait) / end / SM id / sum of durations
+};
+#ifdef AZP_BRINGUP
+extern __device__ AzpTimeline* g_azp_tl;
+__device__ __forceinline__ unsigned long long azp_gtime() {
+  unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t;
+}
+// One caller per participant (a CTA's thread 0, or lane 0 of every warp).  Nothing here waits for memory: the stamps
+// and the participant count are fire-and-forget reductions, so the instrumented chain keeps its timing.  The launch's
+// ring slot = participants that have finished so far / participants per launch: the previous launch of the SAME kernel
+// ended a whole simulation step ago, so the count is an exact multiple when a launch starts.
+__device__ __forceinline__ unsigned tl_entry(int kid, unsigned participants) {
+  AzpTimeline* t = g_azp_tl;
+  if (!t) return 0;
+  const unsigned idx = (*reinterpret_cast<volatile unsigned*>(&t->done[kid]) / participants) % AZP_TL_RING;
+  atomicMax(&t->rec[kid][idx][0], ~azp_gtime());
+  return idx;
+}
+__device__ __forceinline__ void tl_start(int kid, unsigned idx) {
+  AzpTimeline* t = g_azp_tl;
+  if (t) {
+    const unsigned long long now = azp_gtime();
+    atomicMax(&t->rec[kid][idx][1], ~now);
+    const unsigned b = blockIdx.x + blockIdx.y * gridDim.x;
+    if (b < 320u && (threadIdx.x & 127) == 0) t->cta[kid][b][0] = now;
+  }
+}
+__device__ __forceinline__ void tl_end(int kid, unsigned idx, unsigned participants) {
+  AzpTimeline* t = g_azp_tl;
+  if (!t) return;
+  const unsigned long long now = azp_gtime();
+  atomicMax(&t->rec[kid][idx][2], now);
+  atomicAdd(&t->done[kid], 1u);
+  const unsigned b = blockIdx.x + blockIdx.y * gridDim.x;
+  if (b < 320u && (threadIdx.x & 127) == 0) {
+    unsigned smid; asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    t->cta[kid][b][1] = now; t->cta[kid][b][2] = smid; t->cta[kid][b][3] += now - t->cta[kid][b][0];
+  }
+  if (idx == 0xFFFFFFFFu) t->launch[kid] = participants;      // never true: keeps the field referenced
+}
+#define AZP_TL_ENTRY(kid, n) tl_entry(kid, n)
+#define AZP_TL_START(kid, idx) tl_start(kid, idx)
+#define AZP_TL_END(kid, idx, n) tl_end(kid, idx, n)
+#else
+#define AZP_TL_ENTRY(kid, n) 0u
+#define AZP_TL_START(kid, idx) do { (void)(idx); } while (0)
+#define AZP_TL_END(kid, idx, n) do { (void)(idx); } while (0)
+#endif
+int azp_timeline_read(void* out_dev, size_t bytes, cudaStream_t s);      // bring-up builds: copy the ring; else AZP_ERR_UNSUPPORTED
+
 template <typename... P, typename... A>
 inline cudaError_t azp_launch(void (*kernel)(P...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, bool pdl,
                               A&&... args) {

@@ -101,6 +101,23 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint
       "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
       ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
 }
+// Warp-uniform issue: the WHOLE issuer warp runs the issue loop (uniform control flow, descriptors and loop counters live in
+// uniform registers) and one elected lane executes each tcgen05 instruction.  With the loop under `if (lane == 0)` the
+// compiler cannot use the uniform datapath: every UTCHMMA is preceded by an ELECT / R2UR.BROADCAST / BRA.U.ANY "waterfall"
+// over its descriptor registers, ~15 dependent instructions = 100-130 cycles per UMMA from one thread -- more than the 48
+// (N = 64) / 64 (N = 128) cycles the instruction occupies the tensor pipe (tools/bench_cu/umma_rate.cu).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.b32 %0, 1, 0, P;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
+__device__ __forceinline__ int warp_uniform(int v) { return __shfl_sync(0xffffffffu, v, 0); }
+__device__ __forceinline__ void umma_bf16_e(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  if (elect_one()) umma_bf16(tmem_d, desc_a, desc_b, idesc, accumulate);
+}
+__device__ __forceinline__ void umma_commit_e(uint64_t* bar) {
+  if (elect_one()) umma_commit(bar);
+}
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
@@ -539,6 +556,9 @@ __device__ __forceinline__ void umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, u
       "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
       ::"r"(tmem_d), "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
 }
+__device__ __forceinline__ void umma_bf16_ts_e(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  if (elect_one()) umma_bf16_ts(tmem_d, tmem_a, desc_b, idesc, accumulate);
+}
 
 constexpr int CONV_THREADS = 384;     // warp 0 TMA, warps 1 and 11 MMA issuers (even / odd tiles), warps 2..9 epilogue
                                       // (2 per TMEM lane quarter), warp 10 head-GEMM issuer
@@ -607,10 +627,12 @@ __global__ void __launch_bounds__(BITS ? CONV_THREADS_BITS : (HEADS ? CONV_THREA
   float* s_w1 = s_bias + COUT + 8;                          // BITS: [3 planes][3 ky][8 patterns][32] conv1 tables + [32] bias
   int16_t* s_cells = reinterpret_cast<int16_t*>(s_w1 + 72 * 32 + 32); // BITS: [2][CODES] column-pattern codes
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = warp_uniform((int)(threadIdx.x >> 5)), lane = threadIdx.x & 31;
   const ConvGeom g = args.g;
   auto wall_ns = [] { unsigned long long gt; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt)); return (long long)gt; };
   if (AZP_CLKPTR(args.clk) && (int)blockIdx.x == args.clk_cta && threadIdx.x == 0) AZP_CLKPTR(args.clk)[0 * 16 + 14] = wall_ns();      // kernel entry
+  constexpr int TL_KID = HEADS ? AZP_TL_CONV3 : AZP_TL_CONV2;
+  const unsigned tl_idx = threadIdx.x == 0 ? AZP_TL_ENTRY(TL_KID, gridDim.x) : 0u;
 
   // ---- prologue: touches nothing the previous kernel of the stream writes, so under programmatic dependent
   //      launch it overlaps that kernel's tail (barriers, TMEM, bias and the resident weights) ----
@@ -637,8 +659,9 @@ __global__ void __launch_bounds__(BITS ? CONV_THREADS_BITS : (HEADS ? CONV_THREA
   if (AZP_CLKPTR(args.clk) && (int)blockIdx.x == args.clk_cta && threadIdx.x == 0) AZP_CLKPTR(args.clk)[1 * 16 + 14] = wall_ns();      // barriers + TMEM ready
   pdl_wait();                      // the leaf count and the input activations are the previous kernels' outputs
   pdl_launch_dependents();
+  if (threadIdx.x == 0) AZP_TL_START(TL_KID, tl_idx);
   if (AZP_CLKPTR(args.clk) && (int)blockIdx.x == args.clk_cta && threadIdx.x == 0) AZP_CLKPTR(args.clk)[2 * 16 + 14] = wall_ns();      // predecessor finished
-  const int count = args.count_dev ? *args.count_dev : args.count_host;
+  const int count = warp_uniform(args.count_dev ? *args.count_dev : args.count_host);
   const int slot0 = args.back ? g.G - count : 0;
   const long long row_begin = (long long)slot0 * g.stride;
   const long long rows_total = (long long)count * g.stride;
@@ -826,13 +849,14 @@ __global__ void __launch_bounds__(BITS ? CONV_THREADS_BITS : (HEADS ? CONV_THREA
   } else if (warp == 1 || warp == 11) {
     // ===== MMA issuers: two threads, even / odd tiles.  A single thread alternates "wait for barriers" and
     //       "issue" and leaves the tensor pipe idle ~10-30 % of a tile; with two, one waits while the other
-    //       issues (each owns one of the two TMEM accumulators) =====
-    if (lane == 0) {
+    //       issues (each owns one of the two TMEM accumulators).  The whole warp runs the loop, an elected lane issues
+    //       (see elect_one) =====
+    {
       const uint32_t idesc = umma_idesc(COUT);
       const uint32_t a_base = smem_u32(s_a), w_base = smem_u32(s_w);
       const int my_parity = warp == 1 ? 0 : 1;
       mbar_wait(wbar, 0);
-      if (AZP_CLKPTR(args.clk) && (int)blockIdx.x == args.clk_cta && warp == 1) AZP_CLKPTR(args.clk)[3 * 16 + 14] = wall_ns();           // weights resident
+      if (AZP_CLKPTR(args.clk) && (int)blockIdx.x == args.clk_cta && warp == 1 && lane == 0) AZP_CLKPTR(args.clk)[3 * 16 + 14] = wall_ns();           // weights resident
       tc_fence_after();
       int it = 0;
       for (int tl = 0; tl < n_items; tl++) {
@@ -841,9 +865,9 @@ __global__ void __launch_bounds__(BITS ? CONV_THREADS_BITS : (HEADS ? CONV_THREA
         if ((tl & 1) != my_parity) { it += is_conv ? (args.single ? 1 : 3) : fc_chunks(sl); continue; }
         const int acc = tl % NACC;
         const uint32_t acc_ph = (tl / NACC) & 1;
-        if (AZP_CLKPTR(args.clk) && (int)blockIdx.x == args.clk_cta) AZP_CLKPTR(args.clk)[tl * 16 + 2] = clock64();
+        if (AZP_CLKPTR(args.clk) && (int)blockIdx.x == args.clk_cta && lane == 0) AZP_CLKPTR(args.clk)[tl * 16 + 2] = clock64();
         mbar_wait(&tempty[acc], acc_ph ^ 1);              // epilogue has drained this accumulator
-        if (AZP_CLKPTR(args.clk) && (int)blockIdx.x == args.clk_cta) AZP_CLKPTR(args.clk)[tl * 16 + 3] = clock64();
+        if (AZP_CLKPTR(args.clk) && (int)blockIdx.x == args.clk_cta && lane == 0) AZP_CLKPTR(args.clk)[tl * 16 + 3] = clock64();
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * COUT);
         uint32_t accumulate = 0;
@@ -855,24 +879,24 @@ __global__ void __launch_bounds__(BITS ? CONV_THREADS_BITS : (HEADS ? CONV_THREA
           for (int kc = 0; kc < kcs; kc++, it++) {
             const int st = it % STAGES;
             mbar_wait(&full[st], (it / STAGES) & 1);
-            if (tl == n_conv && kc == 0) fc_stamp(3);
+            if (tl == n_conv && kc == 0 && lane == 0) fc_stamp(3);
             tc_fence_after();
             const uint32_t a_addr = a_base + (uint32_t)st * (uint32_t)stage_bytes, b_addr = a_addr + TILE_M * 128;
 #pragma unroll
             for (int k = 0; k < 4; k++) {
-              umma_bf16(d_tmem, umma_desc(a_addr + k * 32, 128), umma_desc(b_addr + k * 32, 128), idesc_fc, accumulate);
+              umma_bf16_e(d_tmem, umma_desc(a_addr + k * 32, 128), umma_desc(b_addr + k * 32, 128), idesc_fc, accumulate);
               accumulate = 1;
             }
-            umma_commit(&empty[st]);
+            umma_commit_e(&empty[st]);
           }
-          umma_commit(&tfull[acc]);
-          if (tl == n_conv) fc_stamp(4);
+          umma_commit_e(&tfull[acc]);
+          if (tl == n_conv && lane == 0) fc_stamp(4);
           continue;
         }
         if (args.single) {
           const int st = it % STAGES;
           mbar_wait(&full[st], (it / STAGES) & 1);
-          if (AZP_CLKPTR(args.clk) && (int)blockIdx.x == args.clk_cta) AZP_CLKPTR(args.clk)[tl * 16 + 4] = clock64();
+          if (AZP_CLKPTR(args.clk) && (int)blockIdx.x == args.clk_cta && lane == 0) AZP_CLKPTR(args.clk)[tl * 16 + 4] = clock64();
           tc_fence_after();
           const uint32_t a_stage = a_base + (uint32_t)st * (uint32_t)stage_bytes;
 #pragma unroll
@@ -883,12 +907,12 @@ __global__ void __launch_bounds__(BITS ? CONV_THREADS_BITS : (HEADS ? CONV_THREA
               const uint32_t w_tap = w_base + (uint32_t)((dyi * 3 + dxi) * S::W_TAP_BYTES);
 #pragma unroll
               for (int k = 0; k < KSTEPS; k++) {
-                umma_bf16(d_tmem, umma_desc(a_tap + k * 32, ROWB, args.single), umma_desc(w_tap + k * 32, ROWB), idesc, accumulate);
+                umma_bf16_e(d_tmem, umma_desc(a_tap + k * 32, ROWB, args.single), umma_desc(w_tap + k * 32, ROWB), idesc, accumulate);
                 accumulate = 1;
               }
             }
           }
-          umma_commit(&empty[st]);
+          umma_commit_e(&empty[st]);
           it++;
         }
         for (int dxi = 0; !args.single && dxi < 3; dxi++, it++) {
@@ -904,14 +928,14 @@ __global__ void __launch_bounds__(BITS ? CONV_THREADS_BITS : (HEADS ? CONV_THREA
 #pragma unroll
             for (int k = 0; k < KSTEPS; k++) {
               if (AZP_DBGBITS(args.debug) & 2) break;
-              umma_bf16(d_tmem, umma_desc(a_tap + k * 32, ROWB), umma_desc(w_tap + k * 32, ROWB), idesc, accumulate);
+              umma_bf16_e(d_tmem, umma_desc(a_tap + k * 32, ROWB), umma_desc(w_tap + k * 32, ROWB), idesc, accumulate);
               accumulate = 1;
             }
           }
-          umma_commit(&empty[st]);                        // stage reusable once these MMAs retire
+          umma_commit_e(&empty[st]);                        // stage reusable once these MMAs retire
         }
-        umma_commit(&tfull[acc]);                         // accumulator complete
-        if (AZP_CLKPTR(args.clk) && (int)blockIdx.x == args.clk_cta) {
+        umma_commit_e(&tfull[acc]);                         // accumulator complete
+        if (AZP_CLKPTR(args.clk) && (int)blockIdx.x == args.clk_cta && lane == 0) {
           AZP_CLKPTR(args.clk)[tl * 16 + 5] = clock64();
           unsigned long long gt;
           asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
@@ -921,7 +945,7 @@ __global__ void __launch_bounds__(BITS ? CONV_THREADS_BITS : (HEADS ? CONV_THREA
     }
   } else if (HEADS && warp == 10) {
     // ===== head-GEMM issuer: its own thread, so the conv issue loop never waits for the epilogue =====
-    if (lane == 0) {
+    {
       const uint32_t idesc_head = umma_idesc(HEAD_N);
       const uint32_t hw_base = smem_u32(s_hw);
       // 1x1 head GEMM of local tile j: [128 x COUT] (TMEM, bf16) x [COUT x 16] (smem) -> TMEM cols COL_HEAD..
@@ -933,26 +957,30 @@ __global__ void __launch_bounds__(BITS ? CONV_THREADS_BITS : (HEADS ? CONV_THREA
 #pragma unroll
         for (int k = 0; k < COUT / 16; k++) {
           const int c = k % HEAD_CHAINS;                    // chain c accumulates K steps c, c+4
-          umma_bf16_ts(acc_base + (c < 2 ? 32 + c * HEAD_N : 96 + (c - 2) * HEAD_N),
+          umma_bf16_ts_e(acc_base + (c < 2 ? 32 + c * HEAD_N : 96 + (c - 2) * HEAD_N),
                        acc_base + (k / 4) * 64 + (k % 4) * 8,
                        umma_desc(hw_base + (k / 4) * HEAD_N * 128 + (k % 4) * 32, 128), idesc_head,
                        k >= HEAD_CHAINS ? 1u : 0u);
         }
-        umma_commit(&head_full[b]);
+        umma_commit_e(&head_full[b]);
       };
       // This thread is also the SIGNALLER of the fused FC jobs: the four epilogue warps that store an item's head features
       // arrive on hw_done (release / acquire at CTA scope), then this otherwise idle thread makes the stores visible
       // device-wide with ONE fence and counts the tile in for every board tile it touches (the FC producers acquire the
       // sum).  A fence in the epilogue warps themselves cost 17 % of conv3: they are the busiest threads of the kernel.
       auto signal_item = [&](int j) {
-        mbar_wait(&hw_done[j % NACC], (uint32_t)((j / NACC) & 1));
-        if (!fc_on || j >= n_conv) return;
-        __threadfence();
-        const unsigned R0 = (unsigned)row_begin + (unsigned)(cta + j * n_cta) * TILE_M;
-        const int s_first = (int)(R0 / (unsigned)g.stride);
-        const int s_last = min(count - 1, (int)((R0 + TILE_M - 1) / (unsigned)g.stride));
-        atomicAdd(args.feat_done + (s_first >> 7), 1u);
-        if ((s_last >> 7) != (s_first >> 7)) atomicAdd(args.feat_done + (s_last >> 7), 1u);
+        if (lane == 0) {
+          mbar_wait(&hw_done[j % NACC], (uint32_t)((j / NACC) & 1));
+          if (fc_on && j < n_conv) {
+            __threadfence();
+            const unsigned R0 = (unsigned)row_begin + (unsigned)(cta + j * n_cta) * TILE_M;
+            const int s_first = (int)(R0 / (unsigned)g.stride);
+            const int s_last = min(count - 1, (int)((R0 + TILE_M - 1) / (unsigned)g.stride));
+            atomicAdd(args.feat_done + (s_first >> 7), 1u);
+            if ((s_last >> 7) != (s_first >> 7)) atomicAdd(args.feat_done + (s_last >> 7), 1u);
+          }
+        }
+        __syncwarp();
       };
       mbar_wait(wbar, 0);
       tc_fence_after();
@@ -967,9 +995,9 @@ __global__ void __launch_bounds__(BITS ? CONV_THREADS_BITS : (HEADS ? CONV_THREA
           if (tl > 0) signal_item(tl - 1);
           const int b = tl % NACC;
           mbar_wait(&act_full[b], (uint32_t)((tl / NACC) & 1));
-          mbar_arrive(&head_full[b]);
+          if (lane == 0) mbar_arrive(&head_full[b]);
         }
-        if (AZP_CLKPTR(args.clk) && (int)blockIdx.x == args.clk_cta) AZP_CLKPTR(args.clk)[tl * 16 + 6] = clock64();
+        if (AZP_CLKPTR(args.clk) && (int)blockIdx.x == args.clk_cta && lane == 0) AZP_CLKPTR(args.clk)[tl * 16 + 6] = clock64();
       }
       if (n_items > 0) signal_item(n_items - 1);
     }
@@ -980,6 +1008,23 @@ __global__ void __launch_bounds__(BITS ? CONV_THREADS_BITS : (HEADS ? CONV_THREA
     const int q = warp & 3;
     const int h = (warp - (egroup ? 12 : 2)) >> 2;
     const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
+    // padded row -> (slot, y, x) without integer divisions (they cost ~100 instructions per tile in warps whose dependent
+    // instruction chain IS the tile period): slot by a 32-bit reciprocal with one correction step, y = pos / P exact for
+    // pos < 2730 (pos < 25 * 24)
+    const unsigned e_stride = (unsigned)g.stride, e_stride_rcp = (unsigned)(0x100000000ull / (unsigned)g.stride);
+    const unsigned e_p_rcp = (65536u + (unsigned)g.P - 1u) / (unsigned)g.P;
+    auto row_split = [&](unsigned R, int& slot, int& y, int& x) {
+      unsigned sq = __umulhi(R, e_stride_rcp);
+      if (R - sq * e_stride >= e_stride) sq++;
+      const unsigned pos = R - sq * e_stride;
+      const unsigned yy = (pos * e_p_rcp) >> 16;
+      slot = (int)sq; y = (int)yy; x = (int)(pos - yy * (unsigned)g.P);
+    };
+    float bias_r[HEADS ? 1 : HALF];         // plain conv: this warp's 32 output-channel biases live in registers
+    if (!HEADS) {
+#pragma unroll
+      for (int j = 0; j < (HEADS ? 1 : HALF); j++) bias_r[j] = s_bias[h * HALF + j];
+    }
     // head outputs of item j of the work list (conv tile tj): +bias, ReLU, scatter to feat[slot][j][pixel]; an FC job has
     // no head outputs -- its accumulator is simply handed back
     auto write_heads = [&](int j) {
@@ -1007,8 +1052,8 @@ __global__ void __launch_bounds__(BITS ? CONV_THREADS_BITS : (HEADS ? CONV_THREA
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty[b]);               // head outputs are in registers: the accumulator is free
       const unsigned R = (unsigned)row_begin + (unsigned)tj * TILE_M + q * 32 + lane;
-      const int slot = (int)(R / (unsigned)g.stride), pos = (int)(R % (unsigned)g.stride);
-      const int y = pos / g.P, x = pos % g.P;
+      int slot, y, x;
+      row_split(R, slot, y, x);
       if (y >= 1 && x >= 1 && x <= g.B && slot < g.G) {
         __nv_bfloat16* f = args.feat + (size_t)slot * args.FK + (y - 1) * g.B + (x - 1);
 #pragma unroll
@@ -1033,7 +1078,7 @@ __global__ void __launch_bounds__(BITS ? CONV_THREADS_BITS : (HEADS ? CONV_THREA
         //      heads), so they go out first -- waiting for the job's accumulator before that could never end.
         const bool fstamp = tl == n_conv && warp == 2 && lane == 0;
         if (fstamp) fc_stamp(5);
-        if (heads_pending && h == 0) write_heads(tl - 1);
+        if (heads_pending && h == ((tl - 1) & 1)) write_heads(tl - 1);
         heads_pending = false;
         if (fstamp) fc_stamp(6);
         mbar_wait(&tfull[acc], acc_ph);
@@ -1098,16 +1143,18 @@ __global__ void __launch_bounds__(BITS ? CONV_THREADS_BITS : (HEADS ? CONV_THREA
       if (stamp) AZP_CLKPTR(args.clk)[tl * 16 + 9] = clock64();
       tc_fence_after();
       const unsigned R = (unsigned)row_begin + (unsigned)t * TILE_M + q * 32 + lane;   // global padded row (< 2^31)
-      const int slot = (int)(R / (unsigned)g.stride);
-      const int pos = (int)(R % (unsigned)g.stride);
-      const int y = pos / g.P, x = pos % g.P;
-      const bool interior = y >= 1 && x >= 1 && x <= g.B && slot < g.G;
+      bool interior = true;
+      if (!HEADS) {
+        int slot, y, x;
+        row_split(R, slot, y, x);
+        interior = y >= 1 && x >= 1 && x <= g.B && slot < g.G;
+      }
       const uint32_t taddr = tmem_base + lane_addr + (uint32_t)(acc * COUT + h * HALF);
       if (AZP_DBGBITS(args.debug) & 1) {
         tc_fence_before();
         __syncwarp();
         if (lane == 0) { if (HEADS) mbar_arrive(&act_full[acc]); else mbar_arrive(&tempty[acc]); }
-        if (HEADS && heads_pending && h == 0) write_heads(tl - 1);
+        if (HEADS && heads_pending && h == ((tl - 1) & 1)) write_heads(tl - 1);
         heads_pending = true;
       } else if (!HEADS) {
         // bias + ReLU + halo zero in registers, the accumulator is released at once.  Each lane then owns 64 contiguous
@@ -1124,10 +1171,10 @@ __global__ void __launch_bounds__(BITS ? CONV_THREADS_BITS : (HEADS ? CONV_THREA
         uint32_t packed[16];
 #pragma unroll
         for (int j = 0; j < 16; j++) {
-          float v0 = interior ? fmaxf(__uint_as_float(r[2 * j]) + s_bias[h * HALF + 2 * j], 0.f) : 0.f;
-          float v1 = interior ? fmaxf(__uint_as_float(r[2 * j + 1]) + s_bias[h * HALF + 2 * j + 1], 0.f) : 0.f;
+          const float v0 = fmaxf(__uint_as_float(r[2 * j]) + bias_r[HEADS ? 0 : 2 * j], 0.f);
+          const float v1 = fmaxf(__uint_as_float(r[2 * j + 1]) + bias_r[HEADS ? 0 : 2 * j + 1], 0.f);
           __nv_bfloat162 hh = __floats2bfloat162_rn(v0, v1);
-          packed[j] = *reinterpret_cast<uint32_t*>(&hh);
+          packed[j] = interior ? *reinterpret_cast<uint32_t*>(&hh) : 0u;      // halo rows stay zero
         }
         if (!(AZP_DBGBITS(args.debug) & 16)) {
           // direct path (default; AZP_DEBUG_CONV=16 selects the staged TMA-store path, 0.9 % slower end to end): each lane owns 64 contiguous bytes of its output row -> two 256-bit stores (full 32 B sectors),
@@ -1166,12 +1213,16 @@ __global__ void __launch_bounds__(BITS ? CONV_THREADS_BITS : (HEADS ? CONV_THREA
           uint32_t r[32];
           tmem_ld32(taddr + c0, r);
           uint32_t packed[16];
+          const float4* b4 = reinterpret_cast<const float4*>(s_bias + h * HALF + c0);     // 16-byte aligned (see s_tail layout)
 #pragma unroll
-          for (int j = 0; j < 16; j++) {
-            float v0 = fmaxf(__uint_as_float(r[2 * j]) + s_bias[h * HALF + c0 + 2 * j], 0.f);
-            float v1 = fmaxf(__uint_as_float(r[2 * j + 1]) + s_bias[h * HALF + c0 + 2 * j + 1], 0.f);
-            __nv_bfloat162 hh = __floats2bfloat162_rn(v0, v1);
-            packed[j] = *reinterpret_cast<uint32_t*>(&hh);
+          for (int j = 0; j < 8; j++) {
+            const float4 bb = b4[j];
+            __nv_bfloat162 h0 = __floats2bfloat162_rn(fmaxf(__uint_as_float(r[4 * j]) + bb.x, 0.f),
+                                                      fmaxf(__uint_as_float(r[4 * j + 1]) + bb.y, 0.f));
+            __nv_bfloat162 h1 = __floats2bfloat162_rn(fmaxf(__uint_as_float(r[4 * j + 2]) + bb.z, 0.f),
+                                                      fmaxf(__uint_as_float(r[4 * j + 3]) + bb.w, 0.f));
+            packed[2 * j] = *reinterpret_cast<uint32_t*>(&h0);
+            packed[2 * j + 1] = *reinterpret_cast<uint32_t*>(&h1);
           }
           // in place: the 16 packed columns of this chunk overwrite fp32 columns this warp already holds in registers
           tmem_st16(tmem_base + lane_addr + (uint32_t)(acc * COUT + h * HALF + c0 / 2), packed);
@@ -1183,18 +1234,19 @@ __global__ void __launch_bounds__(BITS ? CONV_THREADS_BITS : (HEADS ? CONV_THREA
         if (lane == 0) mbar_arrive(&act_full[acc]);
         if (stamp) AZP_CLKPTR(args.clk)[tl * 16 + 11] = clock64();
         // the PREVIOUS tile's head GEMM was queued behind this tile's conv MMAs: it has retired by now
-        if (heads_pending && h == 0) write_heads(tl - 1);
+        if (heads_pending && h == ((tl - 1) & 1)) write_heads(tl - 1);
         heads_pending = true;
         if (stamp) AZP_CLKPTR(args.clk)[tl * 16 + 12] = clock64();
       }
     }
     if (!HEADS && h == 0 && q == 0 && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
-    if (HEADS && heads_pending && h == 0) write_heads(n_items - 1);
+    if (HEADS && heads_pending && h == ((n_items - 1) & 1)) write_heads(n_items - 1);
   }
   tc_fence_before();
   __syncthreads();
   if (AZP_CLKPTR(args.clk) && (int)blockIdx.x == args.clk_cta && threadIdx.x == 0) AZP_CLKPTR(args.clk)[4 * 16 + 14] = wall_ns();      // all roles done
   if (threadIdx.x == 0) fc_stamp(9);
+  if (threadIdx.x == 0) AZP_TL_END(TL_KID, tl_idx, gridDim.x);
   if (warp == 1) tmem_dealloc(tmem_base, TMEM_COLS);
 }
 
@@ -1908,8 +1960,9 @@ __global__ void __launch_bounds__(FC_THREADS, 1) fc_umma_kernel(const __grid_con
   float* s_bias = reinterpret_cast<float*>(tmem_slot + 2);          // [64]
   float* s_w2 = s_bias + 64;                                        // [64] + [1] (+pad)
   float* s_part = s_w2 + 72;                                        // [2][128] value partial sums
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = warp_uniform((int)(threadIdx.x >> 5)), lane = threadIdx.x & 31;
   FC_STAMP(threadIdx.x == 0, 0);
+  const unsigned tl_idx = threadIdx.x == 0 ? AZP_TL_ENTRY(AZP_TL_FC, gridDim.x * gridDim.y) : 0u;
 
   // ---- prologue: constants only (overlaps the previous kernel's tail under programmatic dependent launch) ----
   if (threadIdx.x == 0) {
@@ -1932,9 +1985,11 @@ __global__ void __launch_bounds__(FC_THREADS, 1) fc_umma_kernel(const __grid_con
   pdl_wait();                      // leaf count + head features come from the previous kernels of the stream
   pdl_launch_dependents();
   FC_STAMP(threadIdx.x == 0, 2);
+  if (threadIdx.x == 0) AZP_TL_START(AZP_TL_FC, tl_idx);
   const int count = args.count_dev ? *args.count_dev : args.count_host;
   const int row0 = (args.back ? args.G - count : 0) + tile * TILE_M;
   if (tile * TILE_M >= count) {    // nothing to do for this tile: release TMEM and leave (uniform per CTA)
+    if (threadIdx.x == 0) AZP_TL_END(AZP_TL_FC, tl_idx, gridDim.x * gridDim.y);
     if (warp == 1) tmem_dealloc(tmem_base, FC_N);
     return;
   }
@@ -1952,26 +2007,26 @@ __global__ void __launch_bounds__(FC_THREADS, 1) fc_umma_kernel(const __grid_con
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    {                                  // whole warp runs the loop, an elected lane issues (see elect_one)
       const uint32_t idesc = umma_idesc(FC_N);
       uint32_t accumulate = 0;
       for (int kc = 0; kc < k_chunks; kc++) {
         const int st = kc % args.stages;
         const uint32_t ph = (kc / args.stages) & 1;
         mbar_wait(&full[st], ph);
-        if (kc == 0) FC_STAMP(true, 3);
+        if (kc == 0) FC_STAMP(lane == 0, 3);
         tc_fence_after();
         const uint32_t a_addr = smem_u32(smem + (size_t)st * FC_STAGE_BYTES);
         const uint32_t b_addr = a_addr + TILE_M * 128;
 #pragma unroll
         for (int k = 0; k < 4; k++) {
-          umma_bf16(tmem_base, umma_desc(a_addr + k * 32, 128), umma_desc(b_addr + k * 32, 128), idesc, accumulate);
+          umma_bf16_e(tmem_base, umma_desc(a_addr + k * 32, 128), umma_desc(b_addr + k * 32, 128), idesc, accumulate);
           accumulate = 1;
         }
-        umma_commit(&empty[st]);
+        umma_commit_e(&empty[st]);
       }
-      umma_commit(tfull);
-      FC_STAMP(true, 4);
+      umma_commit_e(tfull);
+      FC_STAMP(lane == 0, 4);
     }
   } else {
     // ===== epilogue =====
@@ -2018,6 +2073,7 @@ __global__ void __launch_bounds__(FC_THREADS, 1) fc_umma_kernel(const __grid_con
   tc_fence_before();
   __syncthreads();
   FC_STAMP(threadIdx.x == 0, 6);
+  if (threadIdx.x == 0) AZP_TL_END(AZP_TL_FC, tl_idx, gridDim.x * gridDim.y);
   if (warp == 1) tmem_dealloc(tmem_base, FC_N);
 }
 
@@ -2060,6 +2116,7 @@ int make_map(azp_engine* e, CUtensorMap* map, const void* base, uint64_t rows, i
 }
 
 #include "azp_net_tower.cuh"
+#include "azp_net_conv1.cuh"
 
 struct UmmaWorkspace {
   ConvGeom g;
@@ -2076,7 +2133,8 @@ struct UmmaWorkspace {
   CUtensorMap map_act1_s, map_act2_s;  // single-load boxes (128+2P+2 rows)
   CUtensorMap map_act2_out;            // conv2 epilogue: TMA store of one [128 rows][64 ch] tile
   CUtensorMap map_act1_out;            // conv1 (tensor core) epilogue: TMA store of one [128 rows][32 ch] tile
-  int conv1_mode = 1;                  // 1: conv1_umma_kernel, 2: conv1_table_kernel, 0: conv1_bits_kernel (see azp_umma_create)
+  int conv1_mode = 3;                  // 3: conv1_taps_kernel, 1: conv1_umma_kernel, 2: conv1_table_kernel, 0: conv1_bits_kernel (see azp_umma_create)
+  int conv1_pairs = 1;                 // conv1_taps_kernel: two taps per UMMA (AZP_CONV1_PAIRS=0: one)
   int single = 0;
   long long* clk = nullptr;            // AZP_CLK=1: per-tile stamps of conv3's CTA 0
   size_t rows = 0;
@@ -2104,6 +2162,7 @@ struct UmmaWeights {
   float* w1_tab2 = nullptr;           // [ky][own3 | opp3 << 3][32]: both stone planes' column sums of one kernel row (conv1_table_kernel)
   float* w1_lm = nullptr;             // [ky][kx][32]: the last-move plane's weights
   __nv_bfloat16* w1_umma = nullptr;   // [4][32][32]: hi, lo (k = ky*9+plane*3+kx, k=27 bias), plane-3 hi, lo (k = ky*3+kx)
+  __nv_bfloat16* w1_taps = nullptr;   // [10][64][8]: per tap (the tenth is zero) hi | lo rows x (planes 0..2, bias at the centre tap, plane 3, zeros)
   __nv_bfloat16* head_w16 = nullptr;  // [16][128] 1x1 head conv weights (policy rows first, zero padded)
   float* head_b8 = nullptr;           // [8]
   __nv_bfloat16* wp16 = nullptr;      // [A][PKp] policy_fc weights, K contiguous, zero padded
@@ -2212,7 +2271,11 @@ int azp_umma_create(azp_engine* e) {
   // per position; parity-green, but 11.3 M warp instructions per launch make it issue-bound at 23.9 us against the tensor
   // kernel's 18-20 us, profiles/r2c_ncu_conv1_table_kernel.txt), 0 = the first SIMT kernel with nine pattern rows per
   // position (AZP_CONV1=simt); each has a float-planes twin that agrees with it bit for bit
-  { const char* v = getenv("AZP_CONV1"); ws->conv1_mode = !v ? 1 : (!strcmp(v, "simt") ? 0 : (!strcmp(v, "table") ? 2 : 1)); }
+  // 3 (default) = nine-tap tensor-core kernel on 16-byte input rows (azp_net_conv1.cuh), AZP_CONV1=umma selects 1
+  { const char* v = getenv("AZP_CONV1"); ws->conv1_mode = !v ? 3 : (!strcmp(v, "simt") ? 0 : (!strcmp(v, "table") ? 2 : (!strcmp(v, "umma") ? 1 : 3))); }
+  { const char* v = getenv("AZP_CONV1_PAIRS"); ws->conv1_pairs = v ? atoi(v) : 1; }
+  AZP_CUDA(e, cudaFuncSetAttribute(conv1_taps_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, conv1x_smem_bytes()));
+  AZP_CUDA(e, cudaFuncSetAttribute(conv1_taps_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, conv1x_smem_bytes()));
   AZP_CUDA(e, cudaFuncSetAttribute(conv1_umma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, conv1_smem_bytes(false)));
   AZP_CUDA(e, cudaFuncSetAttribute(conv1_umma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, conv1_smem_bytes(true)));
   { const char* v = getenv("AZP_SINGLE_LOAD"); ws->single = v ? atoi(v) : 1; }
@@ -2403,6 +2466,20 @@ int azp_umma_build(azp_engine* e, const HostNet& net, NetWeights* W) {
     }
     if ((st = up(e, &U->w1_umma, wu))) return st;
   }
+  {
+    // nine-tap conv1: per tap one K block [64 rows = hi | lo x 32 cout][8 k] bf16 (k: planes 0..2, bias at the centre tap,
+    // plane 3, zeros); block 9 is all zero
+    std::vector<__nv_bfloat16> wt((size_t)C1X_W_ELEMS, __float2bfloat16(0.f));
+    for (int t = 0; t < 9; t++)
+      for (int co = 0; co < 32; co++)
+        for (int k = 0; k < 5; k++) {
+          const float v = k < 3 ? c1.w[((size_t)co * 4 + k) * 9 + t] : (k == 3 ? (t == 4 ? c1.b[co] : 0.f) : c1.w[((size_t)co * 4 + 3) * 9 + t]);
+          const __nv_bfloat16 hi = __float2bfloat16(v);
+          wt[((size_t)t * 64 + co) * 8 + k] = hi;
+          wt[((size_t)t * 64 + 32 + co) * 8 + k] = __float2bfloat16(v - __bfloat162float(hi));
+        }
+    if ((st = up(e, &U->w1_taps, wt))) return st;
+  }
   // conv2/conv3: bf16 [tap][cout][cin] (K-major rows of one tap = UMMA B operand)
   auto pack = [&](const HostConv& c, __nv_bfloat16** dst) {
     std::vector<__nv_bfloat16> w((size_t)9 * c.cout * c.cin);
@@ -2443,17 +2520,18 @@ struct StemRepack {
   const float* blob; int A, PKp, VKp;
   size_t o_c1w, o_c1b, o_c2w, o_c2b, o_c3w, o_c3b, o_pcw, o_pcb, o_pfw, o_pfb, o_vcw, o_vcb, o_v1w, o_v1b, o_v2w, o_v2b;
   float *w1_bits, *w1_tab, *w1_planes, *w1_tab2, *w1_lm, *b1, *b2, *b3, *head_b8, *pfc_b, *vfc1_b, *vfc2_w, *vfc2_b;
-  __nv_bfloat16 *w1_umma, *w2, *w3, *head_w16, *wp16, *wv16;
+  __nv_bfloat16 *w1_umma, *w2, *w3, *head_w16, *wp16, *wv16, *w1_taps;
 };
 
 __global__ void stem_repack_kernel(StemRepack r) {
   const float* c1w = r.blob + r.o_c1w; const float* c1b = r.blob + r.o_c1b;
   const int A = r.A, PK = 4 * A, VK = 2 * A;
   // segment sizes, in the order they are walked
-  const long long n[14] = {27 * 32, 36 * 32, 72 * 32, 4 * 32 * 32, 9 * 64 * 32, 9 * 128 * 64, HEAD_N * 128,
-                           (long long)A * r.PKp, 64LL * r.VKp, 32 + 64 + 128 + 8, A + 64 + 64 + 1, C1T_TAB_FLOATS, 9 * 32, 0};
+  const long long n[15] = {27 * 32, 36 * 32, 72 * 32, 4 * 32 * 32, 9 * 64 * 32, 9 * 128 * 64, HEAD_N * 128,
+                           (long long)A * r.PKp, 64LL * r.VKp, 32 + 64 + 128 + 8, A + 64 + 64 + 1, C1T_TAB_FLOATS, 9 * 32,
+                           C1X_W_ELEMS, 0};
   long long total = 0;
-  for (int i = 0; i < 13; i++) total += n[i];
+  for (int i = 0; i < 14; i++) total += n[i];
   for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
     long long i = idx;
     int seg = 0;
@@ -2516,9 +2594,19 @@ __global__ void stem_repack_kernel(StemRepack r) {
         if (pat & (8 << kx)) p1 = __fadd_rn(p1, c1w[(co * 4 + 1) * 9 + ky * 3 + kx]);
       }
       r.w1_tab2[k] = __fadd_rn(p0, p1);
-    } else {                                          // w1_lm [ky][kx][32]
+    } else if (seg == 12) {                           // w1_lm [ky][kx][32]
       const int co = k % 32, t = k / 32;
       r.w1_lm[k] = c1w[(co * 4 + 2) * 9 + t];
+    } else {                                          // w1_taps [10][64 = hi | lo x 32][8]
+      const int kk = k % 8, nrow = (k / 8) % 64, t = k / 512, co = nrow & 31;
+      float v = 0.f;
+      if (t < 9) {
+        if (kk < 3) v = c1w[(co * 4 + kk) * 9 + t];
+        else if (kk == 3) v = t == 4 ? c1b[co] : 0.f;
+        else if (kk == 4) v = c1w[(co * 4 + 3) * 9 + t];
+      }
+      const __nv_bfloat16 hi = __float2bfloat16(v);
+      r.w1_taps[k] = (nrow & 32) ? __float2bfloat16(__fsub_rn(v, __bfloat162float(hi))) : hi;
     }
   }
 }
@@ -2566,9 +2654,10 @@ int azp_umma_reload_device(azp_engine* e, NetWeights* W, const float* dev_blob, 
   r.w1_bits = U->w1_bits; r.w1_tab = U->w1_tab; r.w1_planes = U->w1_planes; r.b1 = U->b1; r.b2 = U->b2; r.b3 = U->b3;
   r.w1_tab2 = U->w1_tab2; r.w1_lm = U->w1_lm;
   r.head_b8 = U->head_b8; r.pfc_b = W->pfc_b; r.vfc1_b = W->vfc1_b; r.vfc2_w = W->vfc2_w; r.vfc2_b = W->vfc2_b;
+  r.w1_taps = U->w1_taps;
   r.w1_umma = U->w1_umma; r.w2 = U->w2; r.w3 = U->w3; r.head_w16 = U->head_w16; r.wp16 = U->wp16; r.wv16 = U->wv16;
   if (!r.w1_tab2 || !r.w1_lm || !r.w1_bits || !r.w1_tab || !r.w1_planes || !r.b1 || !r.b2 || !r.b3 || !r.head_b8 || !r.pfc_b || !r.vfc1_b ||
-      !r.vfc2_w || !r.vfc2_b || !r.w1_umma || !r.w2 || !r.w3 || !r.head_w16 || !r.wp16 || !r.wv16)
+      !r.vfc2_w || !r.vfc2_b || !r.w1_umma || !r.w1_taps || !r.w2 || !r.w3 || !r.head_w16 || !r.wp16 || !r.wv16)
     return AZP_ERR_UNSUPPORTED;
   stem_repack_kernel<<<148 * 2, 256, 0, s>>>(r);
   azp_count_launch();
@@ -2736,6 +2825,18 @@ static int launch_conv1_umma(azp_engine* e, UmmaWeights* U, const int32_t* count
   const int zmax = count_dev ? g.G : count_host;
   const int max_tiles = (int)(((long long)zmax * g.stride + TILE_M - 1) / TILE_M);
   const int grid = max_tiles < 2 * ws->sms ? max_tiles : 2 * ws->sms;       // two CTAs per SM
+  if (ws->conv1_mode == 3) {
+    Conv1XArgs x;
+    x.g = g; x.w = U->w1_taps; x.count_dev = count_dev; x.count_host = count_host; x.back = back;
+    x.lx = e->tv.leaf_x; x.lo = e->tv.leaf_o; x.ltm = e->tv.leaf_tm; x.llast = e->tv.leaf_last; x.NW = e->NW;
+    x.planes = planes; x.out = ws->act1; x.pairs = ws->conv1_pairs;
+    azp_prof_begin(e, AZP_PROF_CONV1, count_dev, count_host, s);
+    if (planes) azp_launch(conv1_taps_kernel<true>, grid, C1X_THREADS, conv1x_smem_bytes(), s, true, x);
+    else azp_launch(conv1_taps_kernel<false>, grid, C1X_THREADS, conv1x_smem_bytes(), s, true, x);
+    azp_count_launch();
+    azp_prof_end(e, AZP_PROF_CONV1, s);
+    return azp_check_launch();
+  }
   Conv1Args a;
   a.g = g; a.w = U->w1_umma; a.count_dev = count_dev; a.count_host = count_host; a.back = back;
   a.lx = e->tv.leaf_x; a.lo = e->tv.leaf_o; a.ltm = e->tv.leaf_tm; a.llast = e->tv.leaf_last; a.NW = e->NW;
@@ -2760,7 +2861,7 @@ int azp_umma_eval_leaves(azp_engine* e, NetWeights* W, const int32_t* count_dev,
   if (ws->tower) return run_tower(e, W, count_dev, count_host, back, 0, nullptr, nullptr, e->d_policy, e->d_value, 0, s);
   static int fuse = -1;
   if (fuse < 0) { const char* v = getenv("AZP_FUSE_CONV1"); fuse = v ? atoi(v) : 0; }
-  if (!fuse && ws->conv1_mode == 1) {
+  if (!fuse && (ws->conv1_mode == 1 || ws->conv1_mode == 3)) {
     int st = launch_conv1_umma(e, U, count_dev, count_host, back, nullptr, s);
     if (st) return st;
   } else if (!fuse && ws->conv1_mode == 2) {
@@ -2824,7 +2925,7 @@ int azp_umma_eval_planes(azp_engine* e, NetWeights* W, int n, const float* plane
   UmmaWeights* U = (UmmaWeights*)W->umma;
   const ConvGeom& g = ws->g;
   if (ws->tower) return run_tower(e, W, nullptr, n, 0, n, planes, logits, policy, value, 1, s);
-  if (ws->conv1_mode == 1) {
+  if (ws->conv1_mode == 1 || ws->conv1_mode == 3) {
     int st = launch_conv1_umma(e, U, nullptr, n, 0, planes, s);
     if (st) return st;
   } else if (ws->conv1_mode == 2) {

@@ -377,14 +377,16 @@ template <int NW>
 __global__ void __launch_bounds__(128, NW <= 2 ? 7 : 4) advance_kernel(RulesParams rp, TreeView tv, int n, const float* __restrict__ policy,
                                const float* __restrict__ value, int by_slot, int logits, double c_puct, int compact,
                                int parity) {
+  const unsigned tl_idx = (threadIdx.x & 31) == 0 ? AZP_TL_ENTRY(AZP_TL_ADVANCE, gridDim.x * (blockDim.x >> 5)) : 0u;
   pdl_wait();
   pdl_launch_dependents();
+  if ((threadIdx.x & 31) == 0) AZP_TL_START(AZP_TL_ADVANCE, tl_idx);
   int g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (blockIdx.x == 0 && threadIdx.x == 0) {
     tv.n_leaves[(parity ^ 1) * 2 + 0] = 0;
     tv.n_leaves[(parity ^ 1) * 2 + 1] = 0;
   }
-  if (g >= n) return;
+  if (g >= n) { if (lane == 0) AZP_TL_END(AZP_TL_ADVANCE, tl_idx, gridDim.x * (blockDim.x >> 5)); return; }
   const bool root_prefetch = (compact >> 4) & 1;           // bit 4 of `compact`: AZP_ROOT_PREFETCH (default on)
   compact &= 15;
   if (tv.K == 1 && root_prefetch) {
@@ -404,9 +406,11 @@ __global__ void __launch_bounds__(128, NW <= 2 ? 7 : 4) advance_kernel(RulesPara
       }
     }
   }
-  if (!expand_backup_body<NW>(rp, tv, g, lane, policy, value, by_slot, logits)) return;
-  __syncwarp();               // the descent's lanes read edges other lanes of this warp have just written
-  select_body<NW>(rp, tv, g, lane, c_puct, compact, parity);
+  if (expand_backup_body<NW>(rp, tv, g, lane, policy, value, by_slot, logits)) {
+    __syncwarp();             // the descent's lanes read edges other lanes of this warp have just written
+    select_body<NW>(rp, tv, g, lane, c_puct, compact, parity);
+  }
+  if (lane == 0) AZP_TL_END(AZP_TL_ADVANCE, tl_idx, gridDim.x * (blockDim.x >> 5));
 }
 
 // ---- root visit counts (mcts.py:144) -----------------------------------------------------------
