@@ -112,6 +112,18 @@ __device__ __forceinline__ bool elect_one() {
   return pred != 0;
 }
 __device__ __forceinline__ int warp_uniform(int v) { return __shfl_sync(0xffffffffu, v, 0); }
+// AZP_DISCARD=1 (experiment, off by default): dead activations leave L2 WITHOUT a write-back.  act1 / act2 are written once
+// and read once per evaluation (100 MB per 2048 leaves at 15x15); the kernel that follows the last reader (it is past its
+// griddepcontrol.wait: the reader has completed) invalidates the lines, the next evaluation rewrites every byte of them before
+// anything reads them.  Measured: no gain (conv1 / conv2 are bound by their store pattern into L2, not by HBM write-backs)
+// and +3 us in the FC kernel that issues 524 k discards.  `bytes` is a multiple of 128, all threads of the grid take part.
+__device__ __forceinline__ void discard_l2(const void* base, long long bytes) {
+  const long long nthreads = (long long)gridDim.x * gridDim.y * blockDim.x;
+  const long long tid = ((long long)blockIdx.y * gridDim.x + blockIdx.x) * blockDim.x + threadIdx.x;
+  const char* p = static_cast<const char*>(base);
+  for (long long o = tid * 128; o < bytes; o += nthreads * 128)
+    asm volatile("discard.global.L2 [%0], 128;" ::"l"(p + o) : "memory");
+}
 __device__ __forceinline__ void umma_bf16_e(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
   if (elect_one()) umma_bf16(tmem_d, desc_a, desc_b, idesc, accumulate);
 }
@@ -489,6 +501,7 @@ struct ConvSmem {
   static constexpr int W_BYTES = 9 * W_TAP_BYTES;
 };
 
+constexpr int SCHED_GROUPS = 16;
 struct ConvArgs {
   ConvGeom g;
   const float* bias;              // [COUT]
@@ -506,6 +519,15 @@ struct ConvArgs {
   int single;                     // 0: three dx-shifted TMA loads per tile; 1/2: ONE load of 128+2P+2 rows, the nine taps are
                                   // row-offset descriptors into it (2 = descriptors carry the swizzle base offset)
   int stage_bytes;                // bytes of one ring stage
+  // Plain conv (conv2): DYNAMIC tile scheduling.  Per launch a few CTAs lose 3-9 us to stalls no SM owns (per-CTA durations
+  // average out to +-4 % over a thousand launches, the slowest CTA of a single launch takes 35 % longer than the median:
+  // tools/step_timeline.py), so a static tile list makes the launch as long as its unluckiest CTA.  The CTAs form
+  // SCHED_GROUPS groups (cta % SCHED_GROUPS) that each own the tiles their members would have had statically and hand them
+  // out through their own counter sched[group] -- ONE chip-wide counter serialises 4096 same-address atomics at ~27 cycles
+  // each (measured: the median CTA went from 23.6 to 27.9 us).  A CTA's first tile is its own index; sched[SCHED_GROUPS] =
+  // CTAs that have left: the last one out resets everything for the next launch.  null = static list t = cta + k * grid.
+  int* sched;
+  const void* dead; int dead_row_bytes;     // activations of the layer BEFORE this kernel's input (dead once we run), or null
   long long* clk;                 // bring-up: per-tile clock64 stamps of CTA clk_cta ([tile][16]) or null
   int clk_cta;                    // bring-up: which CTA stamps (AZP_CLK_CTA, default 0)
   // HEADS only: the FC layers (policy_fc, value_fc1 + ReLU + value_fc2 + tanh; net.py:64-70) run INSIDE this kernel as
@@ -623,7 +645,11 @@ __global__ void __launch_bounds__(BITS ? CONV_THREADS_BITS : (HEADS ? CONV_THREA
   uint64_t* head_full = act_full + 4;                       // [4] MMA -> epilogue: head outputs of accumulator a ready
   uint64_t* hw_done = head_full + 4;                        // [4] epilogue -> signaller: head features of the item are stored
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(hw_done + 4);
-  float* s_bias = reinterpret_cast<float*>(tmem_slot + 2);  // [COUT] (+ [8] head bias)
+  // dynamic scheduling: tile of local item tl at [tl & 15] (-1 = no more work).  NOT a static __shared__ array: with one in
+  // the kernel the dynamic window no longer starts at offset 0 while the compiler still folds the manual 1024-byte alignment
+  // above away on the strength of __align__(1024) -- every swizzled TMA / UMMA address is then misaligned
+  int* s_tile = reinterpret_cast<int*>(tmem_slot + 2);      // [16]
+  float* s_bias = reinterpret_cast<float*>(s_tile + 16);    // [COUT] (+ [8] head bias)
   float* s_w1 = s_bias + COUT + 8;                          // BITS: [3 planes][3 ky][8 patterns][32] conv1 tables + [32] bias
   int16_t* s_cells = reinterpret_cast<int16_t*>(s_w1 + 72 * 32 + 32); // BITS: [2][CODES] column-pattern codes
 
@@ -650,6 +676,7 @@ __global__ void __launch_bounds__(BITS ? CONV_THREADS_BITS : (HEADS ? CONV_THREA
   }
   for (int i = threadIdx.x; i < COUT; i += blockDim.x) s_bias[i] = args.bias[i];
   if (HEADS && threadIdx.x < 8) s_bias[COUT + threadIdx.x] = args.head_b[threadIdx.x];
+  if (threadIdx.x < 16) s_tile[threadIdx.x] = -1;           // no item's tag (see tile_of)
   if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
   tc_fence_before();
   __syncthreads();
@@ -666,6 +693,7 @@ __global__ void __launch_bounds__(BITS ? CONV_THREADS_BITS : (HEADS ? CONV_THREA
   const long long row_begin = (long long)slot0 * g.stride;
   const long long rows_total = (long long)count * g.stride;
   const int n_tiles = (int)((rows_total + TILE_M - 1) / TILE_M);
+  if (args.dead) discard_l2(static_cast<const char*>(args.dead) + row_begin * args.dead_row_bytes, (long long)n_tiles * TILE_M * args.dead_row_bytes);
   // ---- work list of this CTA: its conv tiles (t = blockIdx.x + k * gridDim.x) and then, with the FC layers fused in, its
   //      share of the FC jobs j = (board tile, slice); the jobs go to the CTAs with the FEWEST conv tiles first
   const int n_cta = (int)gridDim.x, cta = (int)blockIdx.x;
@@ -676,6 +704,22 @@ __global__ void __launch_bounds__(BITS ? CONV_THREADS_BITS : (HEADS ? CONV_THREA
   const int fc_first = n_cta - 1 - cta;
   const int n_fc = fc_first < fc_jobs ? (fc_jobs - 1 - fc_first) / n_cta + 1 : 0;
   const int n_items = n_conv + n_fc;
+  const bool dyn = !HEADS && !BITS && args.sched != nullptr && args.single != 0;      // never together with the fused FC jobs
+  // Dynamic scheduling: ring entry of local item tl = (tl & 0x7FF) << 20 | (tile + 1), tile + 1 == 0: no more work.  The
+  // producer publishes an entry when it requests the tile's data, several items before anyone needs it, so the consumers
+  // POLL the tag instead of learning the tile behind a barrier: the epilogue has its row arithmetic done before the
+  // accumulator is ready, as with the static list (behind the barrier it cost every CTA +18 %).
+  auto tile_of = [&](int tl) -> int {
+    const volatile int* e = s_tile + (tl & 15);
+    const int tag = tl & 0x7FF;
+    int v = *e;
+    if (((unsigned)v >> 20) != (unsigned)tag) {
+      const long long t0 = clock64();
+      while ((((unsigned)(v = *e)) >> 20) != (unsigned)tag)
+        if (clock64() - t0 > 4000000000ll) __trap();
+    }
+    return (v & 0xFFFFF) - 1;
+  };
   if (!BITS && !HEADS && blockIdx.x == 0 && args.feat_done) {
     // conv2 runs between two conv3 launches: it resets the counters of the fused FC jobs (every consumer of the previous
     // evaluation has finished -- this kernel is past its griddepcontrol.wait)
@@ -701,13 +745,41 @@ __global__ void __launch_bounds__(BITS ? CONV_THREADS_BITS : (HEADS ? CONV_THREA
       if (!BITS && args.single) {
         // one box of 128+2P+2 rows per tile, starting one row above/left of the dy=-1,dx=-1 window
         const uint32_t bytes = (uint32_t)(args.stage_rows + 2) * ROWB;
-        for (int tl = 0; tl < n_items; tl++) {
+        if (dyn) {
+          // every tile index is requested ONE item ahead, so the atomic's round trip hides behind the stage wait; two
+          // consecutive end markers, one for each issuer / epilogue-group parity
+          // group gi = cta % SCHED_GROUPS has m members; its k-th tile is round k / m of member k % m
+          const int gi = cta % SCHED_GROUPS, m = (n_cta - gi + SCHED_GROUPS - 1) / SCHED_GROUPS;
+          auto next_tile = [&]() {
+            const int k = m + atomicAdd(args.sched + gi, 1);
+            const int r = k / m;
+            return r * n_cta + gi + (k - r * m) * SCHED_GROUPS;
+          };
+          int t = cta, t_next = next_tile();
+          for (int tl = 0, ends = 0; ends < 2; tl++) {
+            const int st = tl % STAGES;
+            mbar_wait(&empty[st], ((tl / STAGES) & 1) ^ 1);
+            *reinterpret_cast<volatile int*>(s_tile + (tl & 15)) = ((tl & 0x7FF) << 20) | (t < n_tiles ? t + 1 : 0);
+            if (t < n_tiles) {
+              mbar_expect_tx(&full[st], bytes);
+              const long long row = row_begin + (long long)t * TILE_M - g.P - 1;
+              tma_load_2d(s_a + (size_t)st * stage_bytes, &map_act, &full[st], 0, (int)row);
+            } else {
+              mbar_arrive(&full[st]);
+              ends++;
+            }
+            t = t_next;
+            if (t < n_tiles) t_next = next_tile();
+          }
+        }
+        for (int tl = 0; !dyn && tl < n_items; tl++) {
           int t, bt, sl;
           if (item_is_conv(tl, t, bt, sl)) {
             const int st = it % STAGES;
             if (AZP_CLKPTR(args.clk) && (int)blockIdx.x == args.clk_cta) AZP_CLKPTR(args.clk)[it * 16 + 0] = clock64();
             mbar_wait(&empty[st], ((it / STAGES) & 1) ^ 1);
             if (AZP_CLKPTR(args.clk) && (int)blockIdx.x == args.clk_cta) AZP_CLKPTR(args.clk)[it * 16 + 1] = clock64();
+            if (AZP_DBGBITS(args.debug) & 4) { mbar_arrive(&full[st]); it++; continue; }
             mbar_expect_tx(&full[st], bytes);
             const long long row = row_begin + (long long)t * TILE_M - g.P - 1;
             tma_load_2d(s_a + (size_t)st * stage_bytes, &map_act, &full[st], 0, (int)row);
@@ -859,12 +931,21 @@ __global__ void __launch_bounds__(BITS ? CONV_THREADS_BITS : (HEADS ? CONV_THREA
       if (AZP_CLKPTR(args.clk) && (int)blockIdx.x == args.clk_cta && warp == 1 && lane == 0) AZP_CLKPTR(args.clk)[3 * 16 + 14] = wall_ns();           // weights resident
       tc_fence_after();
       int it = 0;
-      for (int tl = 0; tl < n_items; tl++) {
-        int t, bt, sl;
-        const bool is_conv = item_is_conv(tl, t, bt, sl);
+      for (int tl = 0; dyn || tl < n_items; tl++) {
+        int t = 0, bt = 0, sl = 0;
+        const bool is_conv = dyn ? true : item_is_conv(tl, t, bt, sl);
         if ((tl & 1) != my_parity) { it += is_conv ? (args.single ? 1 : 3) : fc_chunks(sl); continue; }
         const int acc = tl % NACC;
         const uint32_t acc_ph = (tl / NACC) & 1;
+        if (dyn) {
+          // the stage's tile index arrives with its data; an end marker is handed on to this parity's epilogue group
+          mbar_wait(&tempty[acc], acc_ph ^ 1);
+          mbar_wait(&full[it % STAGES], (it / STAGES) & 1);
+          if (warp_uniform(tile_of(tl)) < 0) {
+            if (elect_one()) mbar_arrive(&tfull[acc]);
+            break;
+          }
+        }
         if (AZP_CLKPTR(args.clk) && (int)blockIdx.x == args.clk_cta && lane == 0) AZP_CLKPTR(args.clk)[tl * 16 + 2] = clock64();
         mbar_wait(&tempty[acc], acc_ph ^ 1);              // epilogue has drained this accumulator
         if (AZP_CLKPTR(args.clk) && (int)blockIdx.x == args.clk_cta && lane == 0) AZP_CLKPTR(args.clk)[tl * 16 + 3] = clock64();
@@ -907,6 +988,7 @@ __global__ void __launch_bounds__(BITS ? CONV_THREADS_BITS : (HEADS ? CONV_THREA
               const uint32_t w_tap = w_base + (uint32_t)((dyi * 3 + dxi) * S::W_TAP_BYTES);
 #pragma unroll
               for (int k = 0; k < KSTEPS; k++) {
+                if ((AZP_DBGBITS(args.debug) & 2) && (dxi | dyi | k)) continue;       // bring-up: one UMMA per tile instead of 9 * KSTEPS
                 umma_bf16_e(d_tmem, umma_desc(a_tap + k * 32, ROWB, args.single), umma_desc(w_tap + k * 32, ROWB), idesc, accumulate);
                 accumulate = 1;
               }
@@ -1066,12 +1148,16 @@ __global__ void __launch_bounds__(BITS ? CONV_THREADS_BITS : (HEADS ? CONV_THREA
       if (lane == 0) mbar_arrive(&hw_done[b]);              // -> signaller (the head issuer's thread): fence + count
     };
     bool heads_pending = false;           // write_heads(tl - 1) still to be done when item tl starts
-    for (int tl = 0; tl < n_items; tl++) {
+    for (int tl = 0; dyn || tl < n_items; tl++) {
       if (EGROUPS == 2 && (tl & 1) != egroup) continue;
-      int t, fbt, fsl;
-      const bool is_conv = item_is_conv(tl, t, fbt, fsl);
+      int t = 0, fbt = 0, fsl = 0;
+      const bool is_conv = dyn ? true : item_is_conv(tl, t, fbt, fsl);
       const int acc = tl % NACC;
       const uint32_t acc_ph = (tl / NACC) & 1;
+      if (dyn) {
+        t = tile_of(tl);
+        if (t < 0) break;
+      }
       const bool stamp = AZP_CLKPTR(args.clk) && (int)blockIdx.x == args.clk_cta && (warp == 2 || warp == 12) && lane == 0;
       if (HEADS && !is_conv) {
         // ---- FC job.  The features it waits for may be the ones THIS warp still has to write (the previous item's
@@ -1164,7 +1250,12 @@ __global__ void __launch_bounds__(BITS ? CONV_THREADS_BITS : (HEADS ? CONV_THREA
         // bound by exactly that port
         static_assert(HEADS || HALF == 32, "plain-conv epilogue expects 64 output channels");
         uint32_t r[32];
-        tmem_ld32(taddr, r);
+        if (AZP_DBGBITS(args.debug) & 64) {
+#pragma unroll
+          for (int j = 0; j < 32; j++) r[j] = (uint32_t)(tl + j);        // bring-up: no TMEM load
+        } else {
+          tmem_ld32(taddr, r);
+        }
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&tempty[acc]);
@@ -1180,6 +1271,7 @@ __global__ void __launch_bounds__(BITS ? CONV_THREADS_BITS : (HEADS ? CONV_THREA
           // direct path (default; AZP_DEBUG_CONV=16 selects the staged TMA-store path, 0.9 % slower end to end): each lane owns 64 contiguous bytes of its output row -> two 256-bit stores (full 32 B sectors),
           // no shared-memory round trip (the staged path costs 32 KB of shared-memory port time per tile)
           uint8_t* gp = reinterpret_cast<uint8_t*>(args.out) + (size_t)R * 128 + h * 64;
+          if ((AZP_DBGBITS(args.debug) & 32) && packed[0] != 0x12345678u) continue;      // bring-up: no global stores
 #pragma unroll
           for (int v = 0; v < 2; v++)
             asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
@@ -1247,6 +1339,8 @@ __global__ void __launch_bounds__(BITS ? CONV_THREADS_BITS : (HEADS ? CONV_THREA
   if (AZP_CLKPTR(args.clk) && (int)blockIdx.x == args.clk_cta && threadIdx.x == 0) AZP_CLKPTR(args.clk)[4 * 16 + 14] = wall_ns();      // all roles done
   if (threadIdx.x == 0) fc_stamp(9);
   if (threadIdx.x == 0) AZP_TL_END(TL_KID, tl_idx, gridDim.x);
+  if (dyn && threadIdx.x == 0 && atomicInc(reinterpret_cast<unsigned*>(args.sched) + SCHED_GROUPS, gridDim.x - 1) == gridDim.x - 1)
+    for (int i = 0; i < SCHED_GROUPS; i++) args.sched[i] = 0;
   if (warp == 1) tmem_dealloc(tmem_base, TMEM_COLS);
 }
 
@@ -1930,6 +2024,7 @@ struct FcArgs {
   const float* vfc2_w; const float* vfc2_b;
   float* logits; float* value;
   const int32_t* count_dev; int count_host; int back; int out_by_index;
+  const void* dead; int dead_row_bytes, dead_stride;      // act2 (dead once conv3 has completed), see discard_l2; or null
   long long* clk;                 // bring-up (AZP_CLK=4): wall-clock ns stamps of CTA (0,0) or null
 };
 #define FC_STAMP(cond, k) do { if (AZP_CLKPTR(args.clk) && blockIdx.x == 0 && blockIdx.y == 0 && (cond)) { unsigned long long gt_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt_)); AZP_CLKPTR(args.clk)[k] = (long long)gt_; } } while (0)
@@ -1988,6 +2083,11 @@ __global__ void __launch_bounds__(FC_THREADS, 1) fc_umma_kernel(const __grid_con
   if (threadIdx.x == 0) AZP_TL_START(AZP_TL_FC, tl_idx);
   const int count = args.count_dev ? *args.count_dev : args.count_host;
   const int row0 = (args.back ? args.G - count : 0) + tile * TILE_M;
+  if (args.dead) {
+    const long long rb = (long long)(args.back ? args.G - count : 0) * args.dead_stride;
+    const long long nt = ((long long)count * args.dead_stride + TILE_M - 1) / TILE_M;
+    discard_l2(static_cast<const char*>(args.dead) + rb * args.dead_row_bytes, nt * TILE_M * args.dead_row_bytes);
+  }
   if (tile * TILE_M >= count) {    // nothing to do for this tile: release TMEM and leave (uniform per CTA)
     if (threadIdx.x == 0) AZP_TL_END(AZP_TL_FC, tl_idx, gridDim.x * gridDim.y);
     if (warp == 1) tmem_dealloc(tmem_base, FC_N);
@@ -2144,6 +2244,15 @@ struct UmmaWorkspace {
   int fuse_fc = 0;                     // AZP_FUSE_FC=1: FC layers inside the conv3 kernel instead of the fc_umma_kernel launch
   unsigned int* feat_done = nullptr;   // [FC_MAX_BOARD_TILES] see ConvArgs
   unsigned int* fc_done = nullptr;     // [FC_MAX_BOARD_TILES]
+  int discard = 0;                     // AZP_DISCARD=1: dead activations are invalidated in L2 (measured: no gain, see discard_l2)
+  // AZP_L2_PERSIST=1: act1 | act2 (ONE allocation) get an L2 access-policy window (persisting hits, streaming misses).
+  // Measured on B200 (79 MB carve-out of the 126 MB L2, hit ratio 0.82 over the 96 MB window): conv1 / conv2 unchanged --
+  // their stores are bound by the row-per-lane write pattern at 3.6 TB/s into L2 (tools/bench_cu/store_rate.cu), not by
+  // HBM write-backs -- and the tree kernel loses 3.5 us to the smaller unreserved L2: off by default
+  int l2_persist = 0;
+  void* window_base = nullptr; size_t window_bytes = 0; float window_hit = 1.f;
+  std::vector<cudaStream_t> policy_streams;
+  int* sched2 = nullptr;               // [SCHED_GROUPS + 1] conv2's dynamic tile scheduler (see ConvArgs::sched); AZP_DYN_TILES=0: static lists
 };
 struct UmmaWeights {
   // tower
@@ -2204,7 +2313,7 @@ template <int CIN, int COUT, int STAGES, bool HEADS, bool BITS>
 int conv_smem_bytes(int stage_rows, bool fc_fused = false) {
   using S = ConvSmem<CIN, COUT, STAGES, HEADS>;
   return 1024 + S::W_BYTES + STAGES * conv_stage_bytes(stage_rows, S::ROWB, fc_fused) + (HEADS ? (COUT / 64) * HEAD_N * 128 : 0) +
-         (HEADS ? 0 : 2 * TILE_M * 128) + (2 * STAGES + 21) * 8 + 16 + (COUT + 8) * 4 + (BITS ? (72 * 32 + 32) * 4 + 2 * CODES * 2 : 0) + 64;
+         (HEADS ? 0 : 2 * TILE_M * 128) + (2 * STAGES + 21) * 8 + 16 + 64 + (COUT + 8) * 4 + (BITS ? (72 * 32 + 32) * 4 + 2 * CODES * 2 : 0) + 64;
 }
 
 }  // namespace
@@ -2230,8 +2339,24 @@ int azp_umma_create(azp_engine* e) {
   int st;
   const int PCh = tower ? 2 : 4, VCh = tower ? 1 : 2;          // head channels (policy, value)
   if (!tower) {
-    if ((st = e->alloc(&ws->act1, ws->rows * 32))) return st;
-    if ((st = e->alloc(&ws->act2, ws->rows * 64))) return st;
+    if ((st = e->alloc(&ws->act1, ws->rows * (32 + 64)))) return st;         // act1 | act2 (one L2 access-policy window)
+    ws->act2 = ws->act1 + ws->rows * 32;
+    { const char* v = getenv("AZP_L2_PERSIST"); ws->l2_persist = v ? atoi(v) : 0; }
+    if (ws->l2_persist) {
+      cudaDeviceProp pp;
+      AZP_CUDA(e, cudaGetDeviceProperties(&pp, e->cfg.device));
+      const size_t want = ws->rows * (32 + 64) * sizeof(__nv_bfloat16);
+      size_t carve = (size_t)pp.persistingL2CacheMaxSize < want ? (size_t)pp.persistingL2CacheMaxSize : want;
+      if (carve == 0 || pp.accessPolicyMaxWindowSize <= 0 || cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, carve) != cudaSuccess) {
+        cudaGetLastError();
+        ws->l2_persist = 0;
+      } else {
+        ws->window_base = ws->act1;
+        ws->window_bytes = want < (size_t)pp.accessPolicyMaxWindowSize ? want : (size_t)pp.accessPolicyMaxWindowSize;
+        ws->window_hit = carve >= ws->window_bytes ? 1.f : (float)((double)carve / (double)ws->window_bytes);
+        if (getenv("AZP_VERBOSE")) fprintf(stderr, "[azp] L2 window %zu MB, persisting carve-out %zu MB (max %d MB), hit ratio %.2f\n", ws->window_bytes >> 20, carve >> 20, pp.persistingL2CacheMaxSize >> 20, ws->window_hit);
+      }
+    }
   } else {
     ws->t_a_rows = TILE_M + 2 * g.P + 2;
     ws->t_a_bytes = (ws->t_a_rows + 7) / 8 * 8 * 128;
@@ -2258,8 +2383,7 @@ int azp_umma_create(azp_engine* e) {
   ws->sms = prop0.multiProcessorCount;
   AZP_CUDA(e, cudaFuncSetAttribute(fc_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ws->fc_smem));
   if (tower) return AZP_OK;
-  AZP_CUDA(e, cudaMemset(ws->act1, 0, ws->rows * 32 * sizeof(__nv_bfloat16)));
-  AZP_CUDA(e, cudaMemset(ws->act2, 0, ws->rows * 64 * sizeof(__nv_bfloat16)));
+  AZP_CUDA(e, cudaMemset(ws->act1, 0, ws->rows * (32 + 64) * sizeof(__nv_bfloat16)));
   const int stage_rows = TILE_M + 2 * g.P;
   if ((st = make_map(e, &ws->map_act1, ws->act1, ws->rows, 32, stage_rows))) return st;
   if ((st = make_map(e, &ws->map_act2, ws->act2, ws->rows, 64, stage_rows))) return st;
@@ -2294,6 +2418,10 @@ int azp_umma_create(azp_engine* e) {
   if ((st = e->alloc(&ws->fc_done, (size_t)FC_MAX_BOARD_TILES))) return st;
   AZP_CUDA(e, cudaMemset(ws->feat_done, 0, FC_MAX_BOARD_TILES * sizeof(unsigned int)));
   AZP_CUDA(e, cudaMemset(ws->fc_done, 0, FC_MAX_BOARD_TILES * sizeof(unsigned int)));
+  { const char* v = getenv("AZP_DISCARD"); ws->discard = v ? atoi(v) : 0; }
+  // measured (profiles/r3_*): balancing the CTAs does not shorten conv2 -- the launch is bound by the chip-wide write stream, the
+  // per-CTA spread is unfair arbitration of it -- and the polling costs a little: opt-in (AZP_DYN_TILES=1)
+  { const char* v = getenv("AZP_DYN_TILES"); if (v && atoi(v) != 0) { if ((st = e->alloc(&ws->sched2, (size_t)SCHED_GROUPS + 1))) return st; AZP_CUDA(e, cudaMemset(ws->sched2, 0, (SCHED_GROUPS + 1) * sizeof(int))); } }
   ws->smem2 = conv_smem_bytes<32, 64, STAGES2, false, true>(stage_rows);
   ws->smem3 = conv_smem_bytes<64, 128, STAGES3, true, false>(stage_rows, ws->fuse_fc != 0);
   if (ws->smem3 > (int)prop.sharedMemPerBlockOptin) {       // cannot happen for boards <= 23; never launch an oversized kernel
@@ -2337,7 +2465,17 @@ int azp_umma_create(azp_engine* e) {
 }
 
 void azp_umma_destroy(azp_engine* e) {
-  if (e->ws && e->ws->umma) { delete (UmmaWorkspace*)e->ws->umma; e->ws->umma = nullptr; }
+  if (e->ws && e->ws->umma) {
+    UmmaWorkspace* ws = (UmmaWorkspace*)e->ws->umma;
+    if (ws->l2_persist) {                       // detach the window from the caller's streams, release the persisting lines
+      cudaStreamAttrValue v;
+      memset(&v, 0, sizeof(v));
+      for (cudaStream_t q : ws->policy_streams)
+        if (cudaStreamSetAttribute(q, cudaStreamAttributeAccessPolicyWindow, &v) != cudaSuccess) cudaGetLastError();
+      if (cudaCtxResetPersistingL2Cache() != cudaSuccess) cudaGetLastError();
+    }
+    delete ws; e->ws->umma = nullptr;
+  }
 
 }
 
@@ -2733,6 +2871,8 @@ static int run_trunk(azp_engine* e, NetWeights* W, const int32_t* count_dev, int
   a2.fc_fused = 0; a2.fc_slices = 0; a2.fc_pk_chunks = 0; a2.fc_vk_chunks = 0; a2.fc_v_off = 0; a2.fc_A = g.A;
   a2.fc_pbias = nullptr; a2.fc_vbias = nullptr; a2.fc_vw2 = nullptr; a2.fc_vb2 = nullptr; a2.fc_logits = nullptr; a2.fc_value = nullptr;
   a2.feat_done = ws->feat_done; a2.fc_done = ws->fc_done;       // conv2 resets them for the conv3 launch that follows
+  a2.sched = from_bits ? nullptr : ws->sched2;
+  a2.dead = nullptr; a2.dead_row_bytes = 0;
   a2.debug = bringup_debug_bits();
   { const char* v = getenv("AZP_CLK_CTA"); a2.clk_cta = v ? atoi(v) : 0; }
   azp_prof_begin(e, AZP_PROF_CONV2, count_dev, count_host, s);
@@ -2745,6 +2885,8 @@ static int run_trunk(azp_engine* e, NetWeights* W, const int32_t* count_dev, int
   azp_count_launch();
   azp_prof_end(e, AZP_PROF_CONV2, s);
   ConvArgs a3 = a2;
+  a3.sched = nullptr;
+  if (ws->discard && !from_bits) { a3.dead = ws->act1; a3.dead_row_bytes = 64; }
   a3.bias = U->b3; a3.out = nullptr; a3.head_b = U->head_b8; a3.feat = ws->feat;
   a3.NJ = W->PC + W->VC; a3.PC = W->PC; a3.PKp = ws->PKp; a3.FK = ws->FK;
   a3.single = ws->single;
@@ -2806,6 +2948,7 @@ static int launch_fc(azp_engine* e, NetWeights* W, const int32_t* count_dev, int
   fa.vfc2_w = W->vfc2_w; fa.vfc2_b = W->vfc2_b; fa.logits = logits_out; fa.value = value;
   fa.count_dev = count_dev; fa.count_host = count_host; fa.back = back; fa.out_by_index = out_by_index;
   fa.clk = bringup_clk(ws, 4);
+  fa.dead = (ws->discard && !ws->tower) ? ws->act2 : nullptr; fa.dead_row_bytes = 128; fa.dead_stride = g.stride;
   dim3 fc_grid((zmax + TILE_M - 1) / TILE_M, fa.n_slices + 1);
   azp_prof_begin(e, AZP_PROF_FC, count_dev, count_host, s);
   azp_launch(fc_umma_kernel, fc_grid, FC_THREADS, ws->fc_smem, s, true, ws->map_feat, U->map_wp, U->map_wv, fa);
@@ -2851,9 +2994,26 @@ static int launch_conv1_umma(azp_engine* e, UmmaWeights* U, const int32_t* count
   return azp_check_launch();
 }
 
+// first evaluation on a stream (outside graph capture): attach the activations' L2 access-policy window to it; kernels
+// captured from the stream later inherit it
+static void umma_stream_policy(azp_engine* e, UmmaWorkspace* ws, cudaStream_t s) {
+  if (!ws->l2_persist || e->capturing) return;
+  for (cudaStream_t q : ws->policy_streams) if (q == s) return;
+  ws->policy_streams.push_back(s);
+  cudaStreamAttrValue v;
+  memset(&v, 0, sizeof(v));
+  v.accessPolicyWindow.base_ptr = ws->window_base;
+  v.accessPolicyWindow.num_bytes = ws->window_bytes;
+  v.accessPolicyWindow.hitRatio = ws->window_hit;
+  v.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+  v.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+  if (cudaStreamSetAttribute(s, cudaStreamAttributeAccessPolicyWindow, &v) != cudaSuccess) cudaGetLastError();
+}
+
 int azp_umma_eval_leaves(azp_engine* e, NetWeights* W, const int32_t* count_dev, int count_host, int back,
                          cudaStream_t s) {
   UmmaWorkspace* ws = (UmmaWorkspace*)e->ws->umma;
+  umma_stream_policy(e, ws, s);
   UmmaWeights* U = (UmmaWeights*)W->umma;
   const ConvGeom& g = ws->g;
   const int zmax = count_dev ? g.G : count_host;
@@ -2924,6 +3084,7 @@ int azp_umma_eval_planes(azp_engine* e, NetWeights* W, int n, const float* plane
   UmmaWorkspace* ws = (UmmaWorkspace*)e->ws->umma;
   UmmaWeights* U = (UmmaWeights*)W->umma;
   const ConvGeom& g = ws->g;
+  umma_stream_policy(e, ws, s);
   if (ws->tower) return run_tower(e, W, nullptr, n, 0, n, planes, logits, policy, value, 1, s);
   if (ws->conv1_mode == 1 || ws->conv1_mode == 3) {
     int st = launch_conv1_umma(e, U, nullptr, n, 0, planes, s);

@@ -1,5 +1,6 @@
 """Bring-up diagnostics for the bf16 tcgen05 path: per-layer errors against torch fp32."""
 import sys, os
+os.environ.setdefault("AZP_DISCARD", "0")      # keep act1 / act2 readable after the evaluation (they are invalidated in L2 by default)
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
 import torch.nn.functional as F
