@@ -443,7 +443,7 @@ def test_selfplay_manager_ring_path_and_live_weights(az):
     p1, v1 = fn(state)
     assert not np.allclose(p0, p1)
     with torch.no_grad():
-        ref_logits, ref_v = other(state.encode().unsqueeze(0))
+        ref_logits, ref_v = other(state.encode().unsqueeze(0).cpu())
     assert np.abs(p1.reshape(-1) - torch.softmax(ref_logits[0], 0).numpy()).max() <= 1e-5 and abs(v1 - float(ref_v)) <= 1e-5
     opt = torch.optim.SGD(ctrl.net.parameters(), lr=0.5)         # a torch optimizer on net.parameters()
     for q in ctrl.net.parameters():
