@@ -354,12 +354,24 @@ static int search_move(azp_engine* e, int n, int add_noise, int two_nets, int ne
   if ((st = eval_step(e, two_nets, net_slot, 1, s))) return st;
   if ((st = azp_tree_root_expand(e, n, e->d_policy, 1, add_noise, e->policy_logits, s))) return st;
   const int steps = (e->cfg.sims + e->K - 1) / e->K;      // K descents per game per step
-  if ((st = azp_tree_select(e, n, 1, 0, s))) return st;   // descent of step 0
+  // Exact mode on the bf16 stem: the descent kernels also run conv1 of the leaves they emit (azp_conv1_tail.cuh), and the
+  // evaluation that follows starts at conv2.  Every descent of the loop does, the first one included, so that all captured
+  // iterations are alike.
+  Conv1TailArgs tail;
+  const bool fused = !two_nets && azp_umma_conv1_tail(e, net_slot, &tail) != 0;
+  if (fused) {
+    if ((st = azp_tree_descend_conv1(e, n, true, nullptr, nullptr, 1, e->policy_logits, 1, 0, tail, s))) return st;
+  } else {
+    if ((st = azp_tree_select(e, n, 1, 0, s))) return st;   // descent of step 0
+  }
   // iteration i: net(pair i&1), then expand+backup(i) fused with the descent of step i+1 (pair (i+1)&1)
   auto iteration = [&](int i, bool last) -> int {
+    e->conv1_done = fused;
     int r = eval_step(e, two_nets, net_slot, i & 1, s);
+    e->conv1_done = false;
     if (r) return r;
     if (last) return azp_tree_expand_backup(e, n, e->d_policy, e->d_value, 1, e->policy_logits, 0, s);
+    if (fused) return azp_tree_descend_conv1(e, n, false, e->d_policy, e->d_value, 1, e->policy_logits, 1, (i + 1) & 1, tail, s);
     return azp_tree_advance(e, n, e->d_policy, e->d_value, 1, e->policy_logits, 1, (i + 1) & 1, s);
   };
   int sim = 0;

@@ -235,6 +235,7 @@ struct azp_engine {
   int graph_key[2] = {-1, -1}, graph_launches_per_replay[2] = {0, 0};
   uint64_t weights_epoch = 0, graph_epoch[2] = {0, 0};
   int graph_iters = 8;             // simulation steps per captured graph (even; AZP_GRAPH_ITERS)
+  bool conv1_done = false;         // the descent kernel that emitted the current leaf batch has already written its act1 (azp_conv1_tail.cuh)
   int arena_aligned = 1;           // phase-aligned arena (AZP_ARENA_ALIGNED=0: two leaf batches per step)
   long long arena_step = 0;        // move steps since the current match started (its parity is the phase)
   bool capturing = false;          // inside cudaStreamBeginCapture/EndCapture of the step graph
@@ -270,6 +271,20 @@ struct azp_engine {
   }
 };
 
+// geometry of the padded NHWC activation layout (see azp_net_umma.cu)
+struct ConvGeom {
+  int B, A, P, stride;        // board side, cells, row pitch, rows per board = (B+1)*P
+  int G;                      // slots
+};
+// conv1 of freshly emitted leaves as the tail of the descent kernels (azp_conv1_tail.cuh); filled in by azp_umma_conv1_tail
+struct Conv1TailArgs {
+  ConvGeom g;
+  const __nv_bfloat16* w;          // [10][64][8] (UmmaWeights::w1_taps of the slot that evaluates these leaves)
+  __nv_bfloat16* out;              // act1 [rows][32]
+  int enabled;
+};
+int azp_umma_conv1_tail(azp_engine* e, int slot, Conv1TailArgs* out);      // 1: the bf16 stem of `slot` can take the tail, 0: no
+
 // azp_rules.cu
 int azp_augment_launch(int board, int mode, int n_max, const int* n_dev, const float* planes, const float* pi,
                        const int32_t* z, float* out_planes, float* out_pi, int32_t* out_z,
@@ -288,6 +303,9 @@ int azp_softmax_rows(int n, int A, const float* logits, float* policy, cudaStrea
 // expand+backup of the step just evaluated, then the descent of the next step (counter pair `parity`), one launch
 int azp_tree_advance(azp_engine* e, int n, const float* policy, const float* value, int by_slot, int logits, int compact,
                      int parity, cudaStream_t s);
+// the same two descents with conv1 of the emitted leaves as the kernel's tail (K == 1 only); `first`: the descent of step 0
+int azp_tree_descend_conv1(azp_engine* e, int n, bool first, const float* policy, const float* value, int by_slot, int logits,
+                           int compact, int parity, const Conv1TailArgs& ct, cudaStream_t s);
 int azp_tree_root_visits(azp_engine* e, int n, int32_t* visits, cudaStream_t s);
 int azp_tree_root_priors(azp_engine* e, int n, float* priors, cudaStream_t s);
 int azp_tree_leaf_states(azp_engine* e, int n, uint64_t* x, uint64_t* o, uint8_t* tm, int16_t* last, uint8_t* kind, cudaStream_t s);

@@ -23,10 +23,6 @@ constexpr int C1X_THREADS = 32 * (1 + 4 * C1X_NPG + 8);      // warp 0 issuer, 1
 constexpr int C1X_STAGES = 4;                                // input stages == TMEM accumulators (64 columns each)
 constexpr int C1X_STAGE_ROWS = 192;                          // >= 128 + 2P + 3 rows for P <= 24
 constexpr int C1X_STAGE_BYTES = C1X_STAGE_ROWS * 16;
-constexpr int C1X_TAP_BYTES = 64 * 16;                       // one K block of B: 64 rows (hi 32 | lo 32 output channels) x 8 bf16
-constexpr int C1X_TAPS = 10;                                 // nine taps + one all-zero block
-constexpr int C1X_W_BYTES = C1X_TAPS * C1X_TAP_BYTES;
-constexpr int C1X_W_ELEMS = C1X_TAPS * 64 * 8;
 constexpr int conv1x_smem_bytes() { return 1024 + C1X_W_BYTES + C1X_STAGES * C1X_STAGE_BYTES + 3 * C1X_STAGES * 8 + 64; }
 
 struct Conv1XArgs {
@@ -39,11 +35,6 @@ struct Conv1XArgs {
   int pairs;                       // 1: five two-tap UMMAs per tile, 0: nine
 };
 
-// no-swizzle K-major operand: rows 16 B apart (8-row core matrices 128 B apart), K blocks `lbo_bytes` apart
-__device__ __forceinline__ uint64_t umma_desc_rows16(uint32_t smem_addr, uint32_t lbo_bytes) {
-  return (uint64_t)((smem_addr >> 4) & 0x3FFF) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16) | ((uint64_t)(128u >> 4) << 32) |
-         (1ull << 46);
-}
 
 template <bool PLANES>
 __global__ void __launch_bounds__(C1X_THREADS, 2) conv1_taps_kernel(const Conv1XArgs args) {

@@ -19,6 +19,7 @@
 //                                                         convs (act3 never leaves the SM)
 //   fc_umma_kernel      features -> logits/softmax/value  tcgen05 GEMMs (policy_fc, value_fc1), thread-per-row tails
 #include "azp_net.cuh"
+#include "azp_tc.cuh"
 #include <cuda.h>
 #include <stdlib.h>
 
@@ -36,82 +37,12 @@
 
 namespace {
 
-constexpr int TILE_M = 128;
 
-// ---- PTX wrappers -----------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
-  uint32_t ok;
-  asm volatile(
-      "{\n\t.reg .pred P1;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n\t"
-      "selp.b32 %0, 1, 0, P1;\n\t}"
-      : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
-  return ok != 0;
-}
-// Bounded wait: a protocol bug must become a trapped launch, never a hung GPU.
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  if (mbar_try_wait(bar, parity)) return;
-  const long long t0 = clock64();
-  while (!mbar_try_wait(bar, parity)) {
-    if (clock64() - t0 > 4000000000ll) __trap();
-  }
-}
-// Same, for waits that are expected to be long and sit next to issue-bound warps (conv1 producers): back off with
-// nanosleep so the spinning warp does not eat the issue slots of the warps it is waiting for.
-__device__ __forceinline__ void mbar_wait_sleep(uint64_t* bar, uint32_t parity) {
-  if (mbar_try_wait(bar, parity)) return;
-  const long long t0 = clock64();
-  while (!mbar_try_wait(bar, parity)) {
-    __nanosleep(64);
-    if (clock64() - t0 > 4000000000ll) __trap();
-  }
-}
 __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c_inner, int c_row) {
   asm volatile(
       "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
       ::"r"(smem_u32(dst)), "l"((uint64_t)map), "r"(smem_u32(bar)), "r"(c_inner), "r"(c_row) : "memory");
 }
-__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
-  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols));
-  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
-}
-__device__ __forceinline__ void tmem_dealloc(uint32_t addr, uint32_t ncols) {
-  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(ncols));
-}
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void umma_commit(uint64_t* bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-// D[tmem] (+)= A[smem] * B[smem]^T, bf16 inputs, fp32 accumulate; one thread issues for the CTA
-__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
-}
-// Warp-uniform issue: the WHOLE issuer warp runs the issue loop (uniform control flow, descriptors and loop counters live in
-// uniform registers) and one elected lane executes each tcgen05 instruction.  With the loop under `if (lane == 0)` the
-// compiler cannot use the uniform datapath: every UTCHMMA is preceded by an ELECT / R2UR.BROADCAST / BRA.U.ANY "waterfall"
-// over its descriptor registers, ~15 dependent instructions = 100-130 cycles per UMMA from one thread -- more than the 48
-// (N = 64) / 64 (N = 128) cycles the instruction occupies the tensor pipe (tools/bench_cu/umma_rate.cu).
-__device__ __forceinline__ bool elect_one() {
-  uint32_t pred;
-  asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.b32 %0, 1, 0, P;\n\t}" : "=r"(pred));
-  return pred != 0;
-}
-__device__ __forceinline__ int warp_uniform(int v) { return __shfl_sync(0xffffffffu, v, 0); }
 // AZP_DISCARD=1 (experiment, off by default): dead activations leave L2 WITHOUT a write-back.  act1 / act2 are written once
 // and read once per evaluation (100 MB per 2048 leaves at 15x15); the kernel that follows the last reader (it is past its
 // griddepcontrol.wait: the reader has completed) invalidates the lines, the next evaluation rewrites every byte of them before
@@ -123,12 +54,6 @@ __device__ __forceinline__ void discard_l2(const void* base, long long bytes) {
   const char* p = static_cast<const char*>(base);
   for (long long o = tid * 128; o < bytes; o += nthreads * 128)
     asm volatile("discard.global.L2 [%0], 128;" ::"l"(p + o) : "memory");
-}
-__device__ __forceinline__ void umma_bf16_e(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
-  if (elect_one()) umma_bf16(tmem_d, desc_a, desc_b, idesc, accumulate);
-}
-__device__ __forceinline__ void umma_commit_e(uint64_t* bar) {
-  if (elect_one()) umma_commit(bar);
 }
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile(
@@ -152,15 +77,7 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr, uint32_t row_b
   const uint64_t base = base_mode == 2 ? (uint64_t)((smem_addr >> 7) & (row_bytes == 128 ? 7u : 3u)) : 0ull;
   return (uint64_t)((smem_addr >> 4) & 0x3FFF) | (1ull << 16) | (sbo << 32) | (1ull << 46) | (base << 49) | (layout << 61);
 }
-// instruction descriptor: D=f32, A=B=bf16, both K-major, M=128, N
-__device__ __forceinline__ uint32_t umma_idesc(uint32_t n) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | ((n >> 3) << 17) | ((uint32_t)(TILE_M >> 4) << 24);
-}
 
-struct ConvGeom {
-  int B, A, P, stride;        // board side, cells, row pitch, rows per board = (B+1)*P
-  int G;                      // slots
-};
 
 // ---- conv1 from bitboards (SIMT) ------------------------------------------------------------------------
 // One block per slot; work item = (padded position, 8 output channels).  Inputs are 0/1 planes
@@ -557,13 +474,6 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&v)[16
       ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]),
         "r"(v[8]), "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]) : "memory");
 }
-__device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, uint32_t (&r)[16]) {
-  asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-                 "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-               : "r"(taddr));
-}
-__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&r)[8]) {
   asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
@@ -2403,6 +2313,14 @@ int azp_umma_create(azp_engine* e) {
   AZP_CUDA(e, cudaFuncSetAttribute(conv1_umma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, conv1_smem_bytes(false)));
   AZP_CUDA(e, cudaFuncSetAttribute(conv1_umma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, conv1_smem_bytes(true)));
   { const char* v = getenv("AZP_SINGLE_LOAD"); ws->single = v ? atoi(v) : 1; }
+  if (getenv("AZP_VERBOSE")) {
+    int o1 = 0, o2 = 0, o3 = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o1, conv1_taps_kernel<false>, C1X_THREADS, conv1x_smem_bytes());
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o2, conv1_umma_kernel<false>, C1_THREADS, conv1_smem_bytes(false));
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o3, fc_umma_kernel, FC_THREADS, 1024);
+    fprintf(stderr, "[azp] resident CTAs per SM by the occupancy API: conv1_taps %d, conv1_umma %d, fc (1 KB smem) %d\n", o1, o2, o3);
+    cudaGetLastError();
+  }
 #ifdef AZP_BRINGUP
   if (getenv("AZP_CLK")) { if ((st = e->alloc(&ws->clk, (size_t)64 * 16))) return st; AZP_CUDA(e, cudaMemset(ws->clk, 0, 64 * 16 * 8)); }
 #endif
@@ -3010,6 +2928,25 @@ static void umma_stream_policy(azp_engine* e, UmmaWorkspace* ws, cudaStream_t s)
   if (cudaStreamSetAttribute(s, cudaStreamAttributeAccessPolicyWindow, &v) != cudaSuccess) cudaGetLastError();
 }
 
+// Can the descent kernels run conv1 of their leaves as their tail?  Exact mode on the bf16 stem with the nine-tap conv1 only
+// (AZP_FUSE_DESCENT=0: off).
+int azp_umma_conv1_tail(azp_engine* e, int slot, Conv1TailArgs* out) {
+  static int on = -1;
+  if (on < 0) { const char* v = getenv("AZP_FUSE_DESCENT"); on = v ? atoi(v) : 1; }
+  out->enabled = 0;
+  if (!on || e->cfg.net_dtype != AZP_DTYPE_BF16 || e->cfg.net_kind != AZP_NET_STEM || e->K != 1 || !e->ws || !e->ws->umma) return 0;
+  NetWeights* W = e->weights[slot];
+  if (!W || !W->loaded || !W->umma) return 0;
+  UmmaWorkspace* ws = (UmmaWorkspace*)e->ws->umma;
+  UmmaWeights* U = (UmmaWeights*)W->umma;
+  static int fuse = -1;
+  if (fuse < 0) { const char* v = getenv("AZP_FUSE_CONV1"); fuse = v ? atoi(v) : 0; }
+  if (ws->tower || ws->conv1_mode != 3 || !ws->conv1_pairs || fuse || !U->w1_taps) return 0;
+  if (e->cfg.games > 16 * ws->sms) return 0;       // one 16-game CTA per SM: more games would make the descent a second wave
+  out->g = ws->g; out->w = U->w1_taps; out->out = ws->act1; out->enabled = 1;
+  return 1;
+}
+
 int azp_umma_eval_leaves(azp_engine* e, NetWeights* W, const int32_t* count_dev, int count_host, int back,
                          cudaStream_t s) {
   UmmaWorkspace* ws = (UmmaWorkspace*)e->ws->umma;
@@ -3021,7 +2958,11 @@ int azp_umma_eval_leaves(azp_engine* e, NetWeights* W, const int32_t* count_dev,
   if (ws->tower) return run_tower(e, W, count_dev, count_host, back, 0, nullptr, nullptr, e->d_policy, e->d_value, 0, s);
   static int fuse = -1;
   if (fuse < 0) { const char* v = getenv("AZP_FUSE_CONV1"); fuse = v ? atoi(v) : 0; }
-  if (!fuse && (ws->conv1_mode == 1 || ws->conv1_mode == 3)) {
+  const bool conv1_done = e->conv1_done;       // one-shot: set by the engine after a descent kernel with the conv1 tail
+  e->conv1_done = false;
+  if (conv1_done) {
+    // act1 of this batch is already in place
+  } else if (!fuse && (ws->conv1_mode == 1 || ws->conv1_mode == 3)) {
     int st = launch_conv1_umma(e, U, count_dev, count_host, back, nullptr, s);
     if (st) return st;
   } else if (!fuse && ws->conv1_mode == 2) {

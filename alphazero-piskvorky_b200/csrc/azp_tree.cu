@@ -3,6 +3,7 @@
 // a6-a12, a16).  All PUCT arithmetic is float64 in the reference's operation order, so visit
 // counts are identical to alphazero/mcts.py whenever the evaluator numbers are identical.
 #include "azp_internal.cuh"
+#include "azp_conv1_tail.cuh"
 
 #define SLOT_IDLE 0
 #define SLOT_PLAYING 1
@@ -122,7 +123,7 @@ __global__ void root_expand_kernel(RulesParams rp, TreeView tv, int n, const flo
 // goes elsewhere; an unexpanded edge reached twice in one step is a collision and the later descent idles.
 template <int NW>
 __device__ __forceinline__ void select_body(const RulesParams& rp, const TreeView& tv, int g, int lane, double c_puct,
-                                            int compact, int parity) {
+                                            int compact, int parity, int* slot_out = nullptr, uint64_t* leaf_out = nullptr) {
   const int K = tv.K;
   const int rec0 = g * K;
   if (!tv.active[g]) {
@@ -233,7 +234,15 @@ __device__ __forceinline__ void select_body(const RulesParams& rp, const TreeVie
       node = ch;
       nparent = cn;
     }
-    if (kind == 0) emit_leaf<NW>(tv, g, rec, x, o, tm, last, compact, parity, lane);
+    if (kind == 0) {
+      const int slot = emit_leaf<NW>(tv, g, rec, x, o, tm, last, compact, parity, lane);
+      if (slot_out) *slot_out = slot;                 // K == 1 callers: the row of this game's leaf in the evaluation batch
+      if (leaf_out && lane == 0) {                    // ... and the leaf itself (x words, o words, to-move | last << 8), e.g. in shared memory
+#pragma unroll
+        for (int k = 0; k < NW; k++) { leaf_out[k] = x.w[k]; leaf_out[NW + k] = o.w[k]; }
+        leaf_out[2 * NW] = (uint64_t)(uint32_t)(tm | (last * 256));
+      }
+    }
     if (lane == 0) {
       tv.path_len[rec] = kind == 2 ? 0 : depth;
       tv.leaf_kind[rec] = (uint8_t)kind;
@@ -410,6 +419,69 @@ __global__ void __launch_bounds__(128, NW <= 2 ? 7 : 4) advance_kernel(RulesPara
     __syncwarp();             // the descent's lanes read edges other lanes of this warp have just written
     select_body<NW>(rp, tv, g, lane, c_puct, compact, parity);
   }
+  if (lane == 0) AZP_TL_END(AZP_TL_ADVANCE, tl_idx, gridDim.x * (blockDim.x >> 5));
+}
+
+// ---- descent kernels with the conv1 tail (exact mode, bf16 stem; azp_conv1_tail.cuh) ----------------------------------
+// FIRST = the descent of step 0 (select_kernel), else expand+backup of step i fused with the descent of step i+1
+// (advance_kernel).  No early exits: every thread reaches the CTA barriers of the tail.
+template <int NW, bool FIRST>
+__global__ void __launch_bounds__(C1T_THREADS, 1) descend_conv1_kernel(RulesParams rp, TreeView tv, int n, const float* __restrict__ policy,
+                                     const float* __restrict__ value, int by_slot, int logits, double c_puct, int compact,
+                                     int parity, Conv1TailArgs ct) {
+  extern __shared__ uint8_t dc_smem_raw[];
+  uint8_t* smem = dc_smem_raw + ((128u - (smem_u32(dc_smem_raw) & 127u)) & 127u);
+  __shared__ int s_slot[4 * C1T_GROUPS];
+  __shared__ int s_rank[4];     // warps of each lane quarter that have finished their descent
+  __shared__ uint64_t s_leaf[4 * C1T_GROUPS][2 * NW + 1];      // the leaves, by warp: the tail reads them here, not from global memory
+  if (threadIdx.x < 4) s_rank[threadIdx.x] = 0;
+  const unsigned tl_idx = (threadIdx.x & 31) == 0 ? AZP_TL_ENTRY(AZP_TL_ADVANCE, gridDim.x * (blockDim.x >> 5)) : 0u;
+  conv1_tail_prologue(ct, smem);
+  pdl_wait();
+  pdl_launch_dependents();
+  if ((threadIdx.x & 31) == 0) AZP_TL_START(AZP_TL_ADVANCE, tl_idx);
+  const uint32_t tmem = conv1_tail_alloc(smem);
+  const int g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    tv.n_leaves[(parity ^ 1) * 2 + 0] = 0;
+    tv.n_leaves[(parity ^ 1) * 2 + 1] = 0;
+  }
+  const bool root_prefetch = (compact >> 4) & 1;
+  compact &= 15;
+  int slot = -1;
+  if (g < n) {
+    if (!FIRST && root_prefetch) {
+      const size_t gb = (size_t)g * tv.cap * rp.A;
+      const char* pn = reinterpret_cast<const char*>(tv.N + gb);
+      const char* pw = reinterpret_cast<const char*>(tv.W + gb);
+      const char* pp = reinterpret_cast<const char*>(tv.P + gb);
+      const char* pc = reinterpret_cast<const char*>(tv.child + gb);
+      for (int o = lane * 128; o < rp.A * 8; o += 32 * 128) {
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(pw + o));
+        if (o < rp.A * 4) {
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(pn + o));
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(pp + o));
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(pc + o));
+        }
+      }
+    }
+    bool ok = true;
+    if (!FIRST) {
+      ok = expand_backup_body<NW>(rp, tv, g, lane, policy, value, by_slot, logits);
+      __syncwarp();             // the descent's lanes read edges other lanes of this warp have just written
+    }
+    if (ok) select_body<NW>(rp, tv, g, lane, c_puct, compact, parity, &slot, s_leaf[threadIdx.x >> 5]);
+  }
+  // team = how many warps of this lane quarter finished before this one (the team's barrier inside makes its members' leaf
+  // records and slots -- written by lane 0 of each warp -- visible to the team)
+  int team = 0;
+  if (lane == 0) {
+    team = atomicAdd(&s_rank[(threadIdx.x >> 5) & 3], 1);
+    s_slot[team * 4 + ((threadIdx.x >> 5) & 3)] = slot < 0 ? -1 : (slot | ((int)(threadIdx.x >> 5) << 20));     // slot | warp << 20
+  }
+  team = __shfl_sync(AZP_FULL, team, 0);
+  conv1_tail(ct, smem, tmem, team, s_slot, &s_leaf[0][0], 2 * NW + 1, NW);
+  conv1_tail_free(tmem);
   if (lane == 0) AZP_TL_END(AZP_TL_ADVANCE, tl_idx, gridDim.x * (blockDim.x >> 5));
 }
 
@@ -714,6 +786,55 @@ int azp_tree_advance(azp_engine* e, int n, const float* policy, const float* val
   azp_prof_begin(e, AZP_PROF_ADVANCE, nullptr, n, s);
   AZP_DISPATCH_NW_PDL(e->NW, advance_kernel, warp_grid(n), 128, 0, s, e->rp, e->tv, n, policy, value, by_slot, logits,
                       e->cfg.c_puct, compact | (prefetch << 4), parity);
+  azp_count_launch();
+  azp_prof_end(e, AZP_PROF_ADVANCE, s);
+  return azp_check_launch();
+}
+int azp_tree_descend_conv1(azp_engine* e, int n, bool first, const float* policy, const float* value, int by_slot, int logits,
+                           int compact, int parity, const Conv1TailArgs& ct, cudaStream_t s) {
+  static int prefetch = -1;
+  if (prefetch < 0) { const char* v = getenv("AZP_ROOT_PREFETCH"); prefetch = v ? atoi(v) != 0 : 1; }
+  const int cp = compact | (prefetch << 4);
+  static bool configured = false;
+  if (!configured) {
+    // static + dynamic shared memory exceed the 48 KB a kernel gets without opting in
+    configured = true;
+#define AZP_DC_CFG(NWV)                                                                                                               \
+    do {                                                                                                                            \
+      cudaFuncSetAttribute(descend_conv1_kernel<NWV, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, C1T_SMEM);                   \
+      cudaFuncSetAttribute(descend_conv1_kernel<NWV, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, C1T_SMEM);                  \
+      int occ = 0;                                                                                                                  \
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, descend_conv1_kernel<NWV, false>, C1T_THREADS, C1T_SMEM);                   \
+      if (getenv("AZP_VERBOSE")) {                                                                                                  \
+        cudaFuncAttributes fa; cudaFuncGetAttributes(&fa, descend_conv1_kernel<NWV, false>);                                          \
+        int occ0 = 0, occa = 0; cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ0, descend_conv1_kernel<NWV, false>, C1T_THREADS, 0); \
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occa, advance_kernel<NWV>, 128, 0);                                            \
+        fprintf(stderr, "[azp] descend_conv1_kernel<%d>: %d resident CTAs per SM (%d without dynamic smem; advance_kernel %d); regs %d, static smem %zu, local %zu, max threads %d\n", \
+                NWV, occ, occ0, occa, fa.numRegs, fa.sharedSizeBytes, fa.localSizeBytes, fa.maxThreadsPerBlock);                      \
+      }                                                                                                                             \
+    } while (0)
+    AZP_DC_CFG(1); AZP_DC_CFG(2); AZP_DC_CFG(3); AZP_DC_CFG(4); AZP_DC_CFG(5); AZP_DC_CFG(6);     // every instantiation, once per process
+#undef AZP_DC_CFG
+    cudaGetLastError();
+  }
+  const int dc_grid = (n * 32 + C1T_THREADS - 1) / C1T_THREADS;
+  azp_prof_begin(e, AZP_PROF_ADVANCE, nullptr, n, s);
+#define AZP_DC(NWV)                                                                                                        \
+  do {                                                                                                                     \
+    if (first) azp_launch(descend_conv1_kernel<NWV, true>, dc_grid, C1T_THREADS, C1T_SMEM, s, true, e->rp, e->tv, n, policy, value, by_slot, \
+                          logits, e->cfg.c_puct, cp, parity, ct);                                                          \
+    else azp_launch(descend_conv1_kernel<NWV, false>, dc_grid, C1T_THREADS, C1T_SMEM, s, true, e->rp, e->tv, n, policy, value, by_slot,     \
+                    logits, e->cfg.c_puct, cp, parity, ct);                                                                \
+  } while (0)
+  switch (e->NW) {
+    case 1: AZP_DC(1); break;
+    case 2: AZP_DC(2); break;
+    case 3: AZP_DC(3); break;
+    case 4: AZP_DC(4); break;
+    case 5: AZP_DC(5); break;
+    default: AZP_DC(6); break;
+  }
+#undef AZP_DC
   azp_count_launch();
   azp_prof_end(e, AZP_PROF_ADVANCE, s);
   return azp_check_launch();

@@ -332,10 +332,18 @@ def hbm_rooflines(prof, counters, A, NW, mult, peak_gbs):
     adv_bytes = (20.0 * counters["children_scanned"] + 24.0 * counters["path_length"]
                  + (20.0 * A + 4.0 * A + 4.0 + 16.0 * NW + 8.0) * counters["expansions"]) / steps_launches
     ms, n, _ = prof["advance"]
-    entry("advance", "advance_kernel: Node.expand + Node.backup + Node.select (mcts.py:50-82)", adv_bytes, ms, n,
-          "20*children_scanned + 24*path_length + (24*A + 16*NW + 12)*expansions, per launch")
+    n_c1 = prof["conv1"][1]
+    fused_tail = n > 4 and n_c1 * 2 < n       # the descent kernels ran conv1 of their leaves as their tail (azp_conv1_tail.cuh)
+    if fused_tail:
+        c1_bytes = (16.0 * NW + 3.0 + 64.0 * A) * counters["leaf_evals"] / steps_launches
+        entry("advance", "descend_conv1_kernel: Node.expand + Node.backup + Node.select (mcts.py:50-82) + conv1 of the emitted leaves "
+              "(games.py:86-129 encode -> act1 bf16 [A][32]) as the kernel's tail", adv_bytes + c1_bytes, ms, n,
+              "20*children_scanned + 24*path_length + (24*A + 16*NW + 12)*expansions + (16*NW + 3 + 64*A)*leaf_evals, per launch")
+    else:
+        entry("advance", "advance_kernel: Node.expand + Node.backup + Node.select (mcts.py:50-82)", adv_bytes, ms, n,
+              "20*children_scanned + 24*path_length + (24*A + 16*NW + 12)*expansions, per launch")
     ms, n, units = prof["conv1"]
-    if n:
+    if n and not fused_tail:
         entry("leaf_gather_conv1", "conv1: leaf bitboards -> encode (games.py:86-129) -> act1 bf16 [A][32]",
               (16.0 * NW + 3.0 + 64.0 * A) * units / n, ms, n, "(16*NW + 3 + 64*A) per leaf")
     ms, n, units = prof["end_move"]

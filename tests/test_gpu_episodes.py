@@ -11,6 +11,7 @@ The drivers run in slices of ONE lockstep move (``max_move_steps=1``); between s
 of the searches that have just ended (azp_root_visits) and the episode bookkeeping (azp_episode_snapshot), and replay
 everything with the oracle."""
 
+import os
 import numpy as np
 import pytest
 import torch
@@ -412,7 +413,11 @@ def test_per_kernel_profiling_brackets_every_step_kernel(az):
         eng.set_profiling(False)
     for name in ("dominant", "advance", "conv1", "conv2", "fc"):
         ms, launches, units = prof[name]
-        assert launches >= 39 and ms > 0, name                     # AZP_PROF_TAIL = 40 plain steps (advance: 39 + root)
+        # AZP_PROF_TAIL = 40 plain steps (advance: 39 + root).  In the exact mode on the bf16 stem the descent kernels run conv1
+        # of their leaves as their own tail (azp_conv1_tail.cuh): the only conv1 LAUNCH left is the root evaluation's
+        # (AZP_FUSE_DESCENT=0 brings the 40 launches back)
+        fused_tail = os.environ.get("AZP_FUSE_DESCENT", "1") != "0"
+        assert launches >= (1 if name == "conv1" and fused_tail else 39) and ms > 0, name
         assert units <= launches * n and units > 0
     assert prof["end_move"][1] == 1 and prof["root_expand"][1] == 1 and prof["end_move"][2] == n
     assert all(v == (0.0, 0, 0.0) for v in eng.get_profile_kernels().values())      # read-and-reset
