@@ -2942,7 +2942,9 @@ int azp_umma_conv1_tail(azp_engine* e, int slot, Conv1TailArgs* out) {
   static int fuse = -1;
   if (fuse < 0) { const char* v = getenv("AZP_FUSE_CONV1"); fuse = v ? atoi(v) : 0; }
   if (ws->tower || ws->conv1_mode != 3 || !ws->conv1_pairs || fuse || !U->w1_taps) return 0;
-  if (e->cfg.games > 16 * ws->sms) return 0;       // one 16-game CTA per SM: more games would make the descent a second wave
+  // one 16-game CTA per SM: more games would make the descent a second wave, and with few games the tail would squeeze the
+  // whole batch's conv1 into games / 16 SMs (measured: the 400-game arena lost 20 %)
+  if (e->cfg.games > 16 * ws->sms || e->cfg.games < 8 * ws->sms) return 0;
   out->g = ws->g; out->w = U->w1_taps; out->out = ws->act1; out->enabled = 1;
   return 1;
 }
