@@ -2154,6 +2154,7 @@ struct UmmaWorkspace {
   int fuse_fc = 0;                     // AZP_FUSE_FC=1: FC layers inside the conv3 kernel instead of the fc_umma_kernel launch
   unsigned int* feat_done = nullptr;   // [FC_MAX_BOARD_TILES] see ConvArgs
   unsigned int* fc_done = nullptr;     // [FC_MAX_BOARD_TILES]
+  int fuse_descent = 1;                // AZP_FUSE_DESCENT=0 (read when the engine is created): descent kernels without the conv1 tail
   int discard = 0;                     // AZP_DISCARD=1: dead activations are invalidated in L2 (measured: no gain, see discard_l2)
   // AZP_L2_PERSIST=1: act1 | act2 (ONE allocation) get an L2 access-policy window (persisting hits, streaming misses).
   // Measured on B200 (79 MB carve-out of the 126 MB L2, hit ratio 0.82 over the 96 MB window): conv1 / conv2 unchanged --
@@ -2337,6 +2338,7 @@ int azp_umma_create(azp_engine* e) {
   AZP_CUDA(e, cudaMemset(ws->feat_done, 0, FC_MAX_BOARD_TILES * sizeof(unsigned int)));
   AZP_CUDA(e, cudaMemset(ws->fc_done, 0, FC_MAX_BOARD_TILES * sizeof(unsigned int)));
   { const char* v = getenv("AZP_DISCARD"); ws->discard = v ? atoi(v) : 0; }
+  { const char* v = getenv("AZP_FUSE_DESCENT"); ws->fuse_descent = v ? atoi(v) : 1; }
   // measured (profiles/r3_*): balancing the CTAs does not shorten conv2 -- the launch is bound by the chip-wide write stream, the
   // per-CTA spread is unfair arbitration of it -- and the polling costs a little: opt-in (AZP_DYN_TILES=1)
   { const char* v = getenv("AZP_DYN_TILES"); if (v && atoi(v) != 0) { if ((st = e->alloc(&ws->sched2, (size_t)SCHED_GROUPS + 1))) return st; AZP_CUDA(e, cudaMemset(ws->sched2, 0, (SCHED_GROUPS + 1) * sizeof(int))); } }
@@ -2931,17 +2933,15 @@ static void umma_stream_policy(azp_engine* e, UmmaWorkspace* ws, cudaStream_t s)
 // Can the descent kernels run conv1 of their leaves as their tail?  Exact mode on the bf16 stem with the nine-tap conv1 only
 // (AZP_FUSE_DESCENT=0: off).
 int azp_umma_conv1_tail(azp_engine* e, int slot, Conv1TailArgs* out) {
-  static int on = -1;
-  if (on < 0) { const char* v = getenv("AZP_FUSE_DESCENT"); on = v ? atoi(v) : 1; }
   out->enabled = 0;
-  if (!on || e->cfg.net_dtype != AZP_DTYPE_BF16 || e->cfg.net_kind != AZP_NET_STEM || e->K != 1 || !e->ws || !e->ws->umma) return 0;
+  if (e->cfg.net_dtype != AZP_DTYPE_BF16 || e->cfg.net_kind != AZP_NET_STEM || e->K != 1 || !e->ws || !e->ws->umma) return 0;
   NetWeights* W = e->weights[slot];
   if (!W || !W->loaded || !W->umma) return 0;
   UmmaWorkspace* ws = (UmmaWorkspace*)e->ws->umma;
   UmmaWeights* U = (UmmaWeights*)W->umma;
   static int fuse = -1;
   if (fuse < 0) { const char* v = getenv("AZP_FUSE_CONV1"); fuse = v ? atoi(v) : 0; }
-  if (ws->tower || ws->conv1_mode != 3 || !ws->conv1_pairs || fuse || !U->w1_taps) return 0;
+  if (!ws->fuse_descent || ws->tower || ws->conv1_mode != 3 || !ws->conv1_pairs || fuse || !U->w1_taps) return 0;
   // one 16-game CTA per SM: more games would make the descent a second wave, and with few games the tail would squeeze the
   // whole batch's conv1 into games / 16 SMs (measured: the 400-game arena lost 20 %)
   if (e->cfg.games > 16 * ws->sms || e->cfg.games < 8 * ws->sms) return 0;

@@ -413,11 +413,9 @@ def test_per_kernel_profiling_brackets_every_step_kernel(az):
         eng.set_profiling(False)
     for name in ("dominant", "advance", "conv1", "conv2", "fc"):
         ms, launches, units = prof[name]
-        # AZP_PROF_TAIL = 40 plain steps (advance: 39 + root).  In the exact mode on the bf16 stem the descent kernels run conv1
-        # of their leaves as their own tail (azp_conv1_tail.cuh): the only conv1 LAUNCH left is the root evaluation's
-        # (AZP_FUSE_DESCENT=0 brings the 40 launches back)
-        fused_tail = os.environ.get("AZP_FUSE_DESCENT", "1") != "0"
-        assert launches >= (1 if name == "conv1" and fused_tail else 39) and ms > 0, name
+        # AZP_PROF_TAIL = 40 plain steps (advance: 39 + root).  (32 games: too few for the descent kernels' conv1 tail, which
+        # would leave the root evaluation's as the only conv1 LAUNCH -- test_descent_conv1_tail_matches_the_conv1_kernel)
+        assert launches >= 39 and ms > 0, name
         assert units <= launches * n and units > 0
     assert prof["end_move"][1] == 1 and prof["root_expand"][1] == 1 and prof["end_move"][2] == n
     assert all(v == (0.0, 0, 0.0) for v in eng.get_profile_kernels().values())      # read-and-reset
@@ -466,3 +464,40 @@ def test_selfplay_manager_ring_path_and_live_weights(az):
     _, _, vb = m.run_batch([state], 1.0)
     assert va.sum() == vb.sum() == 24 and not np.array_equal(va, vb)          # the cached search engine reloaded too
     m.close()
+
+
+@pytest.mark.parametrize("size,win", [(9, 5), (15, 5)])
+def test_descent_conv1_tail_matches_the_conv1_kernel(az, size, win):
+    """Exact mode on the bf16 stem with enough games to fill the machine: the descent kernels run conv1 of the leaves they emit as
+    their own tail (descend_conv1_kernel, azp_conv1_tail.cuh) instead of a conv1_taps_kernel launch.  Same operands, same UMMA
+    sequence per row -> bit-identical activations -> the SAME self-play: visit counts of every root, moves, pi and examples equal
+    those of an engine created with AZP_FUSE_DESCENT=0, and the per-kernel profile shows which path ran."""
+    sms = torch.cuda.get_device_properties(0).multi_processor_count
+    n, sims = 8 * sms + 16, 12
+    outs = {}
+    for fused in ("1", "0"):
+        os.environ["AZP_FUSE_DESCENT"] = fused
+        try:
+            eng = az.Engine(board=size, win_length=win, games=n, sims=sims, net_dtype=az.DTYPE_BF16, augment=az.AUGMENT_NONE, seed=3)
+        finally:
+            os.environ.pop("AZP_FUSE_DESCENT", None)
+        eng.load_state_dict(onet.synthetic_stem_params(size, seed=2, scale=2.0))
+        with torch.cuda.stream(torch.cuda.Stream()):
+            eng.set_profiling(True)
+            st, planes, pi, z, w = eng.selfplay(n, max_move_steps=3)
+            visits = eng.root_visits(n).cpu().numpy().copy()
+            prof = eng.get_profile_kernels()
+            eng.set_profiling(False)
+            snap = eng.episode_snapshot()
+        # slots grab their game ids with an atomic counter: the slot -> game mapping differs from run to run, the games do not
+        order = np.argsort(snap["game_id"].cpu().numpy(), kind="stable")
+        assert np.array_equal(np.sort(snap["game_id"].cpu().numpy()), np.arange(n))
+        outs[fused] = (visits[order], [t.cpu().numpy()[order].copy() for t in (snap["moves"], snap["pi"], snap["ply"])],
+                       prof["conv1"][1], prof["advance"][1])
+        eng.close()
+    (v1, s1, c1_fused, adv_fused), (v0, s0, c1_plain, adv_plain) = outs["1"], outs["0"]
+    assert adv_fused >= adv_plain >= sims - 1         # the fused path also brackets the descent of step 0
+    assert c1_plain > adv_plain and c1_fused < c1_plain and c1_fused <= 3        # fused: only the root evaluations launch conv1
+    assert v1.sum() > 0 and np.array_equal(v1, v0)
+    for a, b in zip(s1, s0):
+        assert np.array_equal(a, b)
