@@ -153,9 +153,9 @@ __global__ void __launch_bounds__(TW_THREADS, 1) conv_tower_kernel(const __grid_
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
   float* s_bias = reinterpret_cast<float*>(tmem_slot + 2);  // [C]
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = warp_uniform((int)(threadIdx.x >> 5)), lane = threadIdx.x & 31;
   const ConvGeom g = args.g;
-  const int count = args.count_dev ? *args.count_dev : args.count_host;
+  const int count = warp_uniform(args.count_dev ? *args.count_dev : args.count_host);
   const int slot0 = args.back ? g.G - count : 0;
   const long long row_begin = (long long)slot0 * g.stride;
   const long long rows_total = (long long)count * g.stride;
@@ -207,8 +207,9 @@ __global__ void __launch_bounds__(TW_THREADS, 1) conv_tower_kernel(const __grid_
       }
     }
   } else if (warp == 1 || warp == 10) {
-    // ===== MMA issuers: thread j accumulates tile j of every pair =====
-    if (lane == 0) {
+    // ===== MMA issuers: warp j accumulates tile j of every pair; the whole warp runs the loop, an elected lane issues
+    //       (uniform control flow keeps the descriptors in uniform registers: see elect_one in azp_tc.cuh / azp_net_umma.cu) =====
+    {
       const int j = warp == 1 ? 0 : 1;
       const uint32_t idesc = umma_idesc(C);
       const uint32_t a_base = smem_u32(s_a), w_base = smem_u32(s_w);
@@ -231,14 +232,14 @@ __global__ void __launch_bounds__(TW_THREADS, 1) conv_tower_kernel(const __grid_
             const uint32_t w_tap = w_base + (uint32_t)st * W_BYTES;
 #pragma unroll
             for (int k = 0; k < 4; k++) {
-              umma_bf16(d_tmem, umma_desc(a_tap + k * 32, 128), umma_desc(w_tap + k * 32, 128), idesc, accumulate);
+              umma_bf16_e(d_tmem, umma_desc(a_tap + k * 32, 128), umma_desc(w_tap + k * 32, 128), idesc, accumulate);
               accumulate = 1;
             }
-            umma_commit(&w_empty[st]);
+            umma_commit_e(&w_empty[st]);
           }
-          umma_commit(&a_empty[kc]);
+          umma_commit_e(&a_empty[kc]);
         }
-        umma_commit(&tfull[aset]);
+        umma_commit_e(&tfull[aset]);
       }
     }
   } else if (warp >= 2 && warp < 10) {
