@@ -145,14 +145,10 @@ static __device__ __forceinline__ void conv1_tail(const Conv1TailArgs& a, uint8_
             packed[hf * 8 + j] = *reinterpret_cast<uint32_t*>(&hh);
           }
         }
-        if (pos < g.stride) {                                          // rows past the board belong to the next slot
+        {                                                              // rows past the board belong to the next slot: not stored
           uint8_t* gp = reinterpret_cast<uint8_t*>(a.out) + ((size_t)slot * g.stride + pos) * 64;
-#pragma unroll
-          for (int v = 0; v < 2; v++)
-            asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
-                         ::"l"(gp + v * 32), "r"(packed[8 * v]), "r"(packed[8 * v + 1]), "r"(packed[8 * v + 2]),
-                           "r"(packed[8 * v + 3]), "r"(packed[8 * v + 4]), "r"(packed[8 * v + 5]), "r"(packed[8 * v + 6]),
-                           "r"(packed[8 * v + 7]) : "memory");
+          const int pos_even = pos & ~1;
+          store_rows64_paired(packed, gp, 64, pos_even < g.stride, pos_even + 1 < g.stride, lane);
         }
       }
       tc_fence_before();

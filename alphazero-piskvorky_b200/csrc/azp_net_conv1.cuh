@@ -229,14 +229,10 @@ __global__ void __launch_bounds__(C1X_THREADS, 2) conv1_taps_kernel(const Conv1X
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty[st]);
-      // each lane owns the 64 contiguous bytes of its output row: two 256-bit stores (full 32-byte sectors)
+      // each lane owns the 64 bytes of its output row; lane pairs exchange halves so that every store instruction writes whole
+      // 64-byte rows (store_rows64_paired)
       uint8_t* gp = reinterpret_cast<uint8_t*>(args.out) + (size_t)R * 64;
-#pragma unroll
-      for (int v = 0; v < 2; v++)
-        asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
-                     ::"l"(gp + v * 32), "r"(packed[8 * v]), "r"(packed[8 * v + 1]), "r"(packed[8 * v + 2]),
-                       "r"(packed[8 * v + 3]), "r"(packed[8 * v + 4]), "r"(packed[8 * v + 5]), "r"(packed[8 * v + 6]),
-                       "r"(packed[8 * v + 7]) : "memory");
+      store_rows64_paired(packed, gp, 64, true, true, lane);
     }
   }
   tc_fence_before();

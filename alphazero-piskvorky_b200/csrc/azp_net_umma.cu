@@ -445,6 +445,7 @@ struct ConvArgs {
   // CTAs that have left: the last one out resets everything for the next launch.  null = static list t = cta + k * grid.
   int* sched;
   const void* dead; int dead_row_bytes;     // activations of the layer BEFORE this kernel's input (dead once we run), or null
+  int paired_stores;              // plain conv epilogue: AZP_PAIRED_STORES=1 lane pairs write whole 64-byte row segments (default: one row half per lane)
   long long* clk;                 // bring-up: per-tile clock64 stamps of CTA clk_cta ([tile][16]) or null
   int clk_cta;                    // bring-up: which CTA stamps (AZP_CLK_CTA, default 0)
   // HEADS only: the FC layers (policy_fc, value_fc1 + ReLU + value_fc2 + tanh; net.py:64-70) run INSIDE this kernel as
@@ -1182,12 +1183,16 @@ __global__ void __launch_bounds__(BITS ? CONV_THREADS_BITS : (HEADS ? CONV_THREA
           // no shared-memory round trip (the staged path costs 32 KB of shared-memory port time per tile)
           uint8_t* gp = reinterpret_cast<uint8_t*>(args.out) + (size_t)R * 128 + h * 64;
           if ((AZP_DBGBITS(args.debug) & 32) && packed[0] != 0x12345678u) continue;      // bring-up: no global stores
+          if (args.paired_stores) {
+            store_rows64_paired(packed, gp, 128, true, true, lane);
+          } else {
 #pragma unroll
-          for (int v = 0; v < 2; v++)
-            asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
-                         ::"l"(gp + v * 32), "r"(packed[8 * v]), "r"(packed[8 * v + 1]), "r"(packed[8 * v + 2]),
-                           "r"(packed[8 * v + 3]), "r"(packed[8 * v + 4]), "r"(packed[8 * v + 5]), "r"(packed[8 * v + 6]),
-                           "r"(packed[8 * v + 7]) : "memory");
+            for (int v = 0; v < 2; v++)
+              asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+                           ::"l"(gp + v * 32), "r"(packed[8 * v]), "r"(packed[8 * v + 1]), "r"(packed[8 * v + 2]),
+                             "r"(packed[8 * v + 3]), "r"(packed[8 * v + 4]), "r"(packed[8 * v + 5]), "r"(packed[8 * v + 6]),
+                             "r"(packed[8 * v + 7]) : "memory");
+          }
           if (stamp) AZP_CLKPTR(args.clk)[tl * 16 + 11] = clock64();
           continue;
         }
@@ -2793,6 +2798,7 @@ static int run_trunk(azp_engine* e, NetWeights* W, const int32_t* count_dev, int
   a2.feat_done = ws->feat_done; a2.fc_done = ws->fc_done;       // conv2 resets them for the conv3 launch that follows
   a2.sched = from_bits ? nullptr : ws->sched2;
   a2.dead = nullptr; a2.dead_row_bytes = 0;
+  { static int ps = -1; if (ps < 0) { const char* v = getenv("AZP_PAIRED_STORES"); ps = v ? atoi(v) : 0; } a2.paired_stores = ps; }      // measured in the default build, same call: 15.16 M with, 15.22-15.25 M without
   a2.debug = bringup_debug_bits();
   { const char* v = getenv("AZP_CLK_CTA"); a2.clk_cta = v ? atoi(v) : 0; }
   azp_prof_begin(e, AZP_PROF_CONV2, count_dev, count_host, s);

@@ -105,3 +105,30 @@ static __device__ __forceinline__ uint64_t umma_desc_rows16(uint32_t smem_addr, 
   return (uint64_t)((smem_addr >> 4) & 0x3FFF) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16) | ((uint64_t)(128u >> 4) << 32) |
          (1ull << 46);
 }
+
+// ---- epilogue row stores --------------------------------------------------------------------------------------------
+// tcgen05.ld 32x32b pins lane == tile row, so an epilogue lane owns 64 bytes of ITS row, and two 32-byte stores per lane put
+// 32 bytes into each of 32 lines per instruction: 3.6 TB/s into L2 chip-wide.  64 CONTIGUOUS bytes per line and instruction
+// reach the coalesced rate, 5.4 TB/s (tools/bench_cu/store_rate.cu, profiles/r3_store_rate.txt).  Lanes 2k / 2k+1 own rows 2k / 2k+1:
+// after ONE exchange of eight registers with the partner lane, instruction 0 writes row 2k (even lane bytes 0-31, odd lane
+// bytes 32-63) and instruction 1 row 2k+1.  `mine`: this lane's 64-byte segment; `pitch`: bytes between consecutive rows;
+// `st_even` / `st_odd`: whether the pair's even / odd row is stored at all.  Every lane of the warp must call this.
+static __device__ __forceinline__ void store_rows64_paired(const uint32_t (&p)[16], uint8_t* mine, int pitch, bool st_even, bool st_odd,
+                                                           int lane) {
+  const bool odd = (lane & 1) != 0;
+  uint32_t a[8], b[8];
+#pragma unroll
+  for (int j = 0; j < 8; j++) {
+    const uint32_t recv = __shfl_xor_sync(0xffffffffu, odd ? p[j] : p[8 + j], 1);
+    a[j] = odd ? recv : p[j];            // row 2k:   even lane its own first half, odd lane the partner's second half
+    b[j] = odd ? p[8 + j] : recv;        // row 2k+1: even lane the partner's first half, odd lane its own second half
+  }
+  uint8_t* seg_even = mine - (odd ? pitch : 0) + (odd ? 32 : 0);
+  uint8_t* seg_odd = mine + (odd ? 0 : pitch) + (odd ? 32 : 0);
+  if (st_even)
+    asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+                 ::"l"(seg_even), "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(a[4]), "r"(a[5]), "r"(a[6]), "r"(a[7]) : "memory");
+  if (st_odd)
+    asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+                 ::"l"(seg_odd), "r"(b[0]), "r"(b[1]), "r"(b[2]), "r"(b[3]), "r"(b[4]), "r"(b[5]), "r"(b[6]), "r"(b[7]) : "memory");
+}

@@ -20,6 +20,24 @@ __global__ void store_rows(uint8_t* out, size_t rows, int mode, const uint4* rd,
         asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(gp + q * 32), "r"(v[0]), "r"(v[1]), "r"(v[2]),
                      "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]) : "memory");
     }
+  } else if (mode == 2) {     // lane pairs cover 64 contiguous bytes of a 128-byte row: 16 rows x 64 B per instruction, the other half by the twin warp
+    for (size_t w = warp; w < rows / 32 * 2; w += nwarps) {
+#pragma unroll
+      for (int q = 0; q < 2; q++) {
+        uint8_t* gp = out + ((w >> 1) * 32 + q * 16 + (lane >> 1)) * 128 + (w & 1) * 64 + (lane & 1) * 32;
+        asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(gp), "r"(v[0]), "r"(v[1]), "r"(v[2]),
+                     "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]) : "memory");
+      }
+    }
+  } else if (mode == 3) {     // four lanes cover a full 128-byte row: 8 rows x 128 B per instruction (one warp owns whole rows)
+    for (size_t w = warp; w < rows / 32; w += nwarps) {
+#pragma unroll
+      for (int q = 0; q < 4; q++) {
+        uint8_t* gp = out + (w * 32 + q * 8 + (lane >> 2)) * 128 + (lane & 3) * 32;
+        asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(gp), "r"(v[0]), "r"(v[1]), "r"(v[2]),
+                     "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]) : "memory");
+      }
+    }
   } else {                    // coalesced: a warp writes 512 contiguous bytes per instruction
     for (size_t w = warp; w < rows * 128 / 512; w += nwarps)
       *reinterpret_cast<uint4*>(out + w * 512 + lane * 16) = make_uint4(v[0], v[1], v[2], v[3]);
@@ -38,8 +56,8 @@ int main() {
   cudaMemset(out, 0, rows * 128); cudaMemset(rd, 1, rows * 64);
   cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
   for (int with_read = 0; with_read < 2; with_read++)
-    for (int mode = 0; mode < 2; mode++)
-      for (int ctas_per_sm : {1, 2, 4}) {
+    for (int mode : {0, 2, 3, 1})
+      for (int ctas_per_sm : {2}) {
         for (int it = 0; it < 3; it++) store_rows<<<148 * ctas_per_sm, 512>>>(out, rows, mode, with_read ? rd : nullptr, rows * 64 / 16, sink);
         cudaEventRecord(e0);
         const int reps = 20;
@@ -47,7 +65,7 @@ int main() {
         cudaEventRecord(e1); cudaEventSynchronize(e1);
         float ms; cudaEventElapsedTime(&ms, e0, e1);
         const double us = ms * 1e3 / reps;
-        printf("%s stores, %d x 512 threads per SM%s: %.1f us per 67 MB -> %.2f TB/s written%s\n", mode ? "coalesced 16 B/lane" : "row-per-lane 2 x 32 B",
+        printf("%s stores, %d x 512 threads per SM%s: %.1f us per 67 MB -> %.2f TB/s written%s\n", mode == 1 ? "coalesced 16 B/lane" : mode == 2 ? "lane pairs, 64 B per row" : mode == 3 ? "lane quads, 128 B per row" : "row-per-lane 2 x 32 B",
                ctas_per_sm, with_read ? " + 33.5 MB read" : "", us, rows * 128 / us * 1e-6, cudaGetLastError() == cudaSuccess ? "" : " ERR");
       }
   return 0;
