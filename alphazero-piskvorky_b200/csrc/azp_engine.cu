@@ -29,7 +29,7 @@ bool azp_pdl_enabled() {
   return v != 0;
 }
 
-#ifdef AZP_BRINGUP
+#if defined(AZP_BRINGUP) || defined(AZP_TIMELINE_BUILD)
 __device__ AzpTimeline* g_azp_tl = nullptr;
 static AzpTimeline* g_tl_host_ptr = nullptr;
 // AZP_TIMELINE=1 in a bring-up build: allocate the ring once per process and publish it to the kernels

@@ -55,7 +55,7 @@ struct AzpTimeline {
   unsigned int launch[AZP_TL_KERNELS], done[AZP_TL_KERNELS];
   unsigned long long cta[AZP_TL_KERNELS][320][4];             // last launch: per-CTA start (past pdl_wait) / end / SM id / sum of durations
 };
-#ifdef AZP_BRINGUP
+#if defined(AZP_BRINGUP) || defined(AZP_TIMELINE_BUILD)
 extern __device__ AzpTimeline* g_azp_tl;
 __device__ __forceinline__ unsigned long long azp_gtime() {
   unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t;
