@@ -13,10 +13,12 @@
 #include "azp_tc.cuh"
 
 constexpr int C1T_MAX_ROWS = 4 * TILE_M + 2 * 24 + 8;        // <= 4 tiles per board (19x19: 400 rows) + halo rows above / below
-constexpr int C1T_GROUPS = 4;                                // warp groups (4 warps = 128 TMEM lanes each) per CTA: 16 games per CTA
-constexpr int C1T_THREADS = 128 * C1T_GROUPS;
+// GROUPS = warp groups (4 warps = one team's worth of tensor-memory lanes) per CTA: 4 games per group.  The kernel is instantiated
+// for 1, 2 and 4 groups and the launcher takes the smallest that seats all games in one CTA per SM (4 * GROUPS * SMs games): few
+// games are then spread over many SMs instead of being squeezed into games / 16 of them.
 constexpr int C1T_GROUP_BYTES = C1T_MAX_ROWS * 16;
-constexpr int C1T_SMEM = 1024 + C1X_W_BYTES + C1T_GROUPS * C1T_GROUP_BYTES + 128;
+constexpr int c1t_threads(int groups) { return 128 * groups; }
+constexpr int c1t_smem(int groups) { return 1024 + C1X_W_BYTES + groups * C1T_GROUP_BYTES + 128; }
 
 // Why ONE 512-thread CTA per SM instead of the descent kernels' four 128-thread CTAs: a kernel that contains tcgen05.alloc was
 // given ONE resident CTA per SM on this driver (cudaOccupancyMaxActiveBlocksPerMultiprocessor reports 1 for every tcgen05
@@ -24,6 +26,7 @@ constexpr int C1T_SMEM = 1024 + C1X_W_BYTES + C1T_GROUPS * C1T_GROUP_BYTES + 128
 // SM are what the four small CTAs gave the latency-bound tree walk anyway.
 
 // Prologue part (before griddepcontrol.wait: touches nothing a predecessor writes): conv1 weights -> shared memory, barrier init.
+template <int C1T_GROUPS>
 static __device__ __forceinline__ void conv1_tail_prologue(const Conv1TailArgs& a, uint8_t* smem) {
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem + C1X_W_BYTES + C1T_GROUPS * C1T_GROUP_BYTES);
   if (threadIdx.x == 0) {
@@ -34,22 +37,24 @@ static __device__ __forceinline__ void conv1_tail_prologue(const Conv1TailArgs& 
     reinterpret_cast<uint4*>(smem)[i] = reinterpret_cast<const uint4*>(a.w)[i];
 }
 
-// After griddepcontrol.wait (the previous kernel of the chain, which held tensor memory on this SM, has completed): all 512
-// columns -- this CTA is alone on its SM (see above).  Every thread of the CTA calls this; returns the base address.
+// After griddepcontrol.wait (the previous kernel of the chain, which held tensor memory on this SM, has completed): 128 columns
+// per group -- this CTA is alone on its SM (see above).  Every thread of the CTA calls this; returns the base address.
+template <int C1T_GROUPS>
 static __device__ __forceinline__ uint32_t conv1_tail_alloc(uint8_t* smem) {
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C1X_W_BYTES + C1T_GROUPS * C1T_GROUP_BYTES);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + C1T_GROUPS);
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");         // the prologue's weight copy -> visible to UMMA
-  if ((threadIdx.x >> 5) == 0) tmem_alloc(tmem_slot, 512);
+  if ((threadIdx.x >> 5) == 0) tmem_alloc(tmem_slot, 128 * C1T_GROUPS);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   return *tmem_slot;
 }
+template <int C1T_GROUPS>
 static __device__ __forceinline__ void conv1_tail_free(uint32_t tmem) {
   tc_fence_before();
   __syncthreads();
-  if ((threadIdx.x >> 5) == 0) tmem_dealloc(tmem, 512);
+  if ((threadIdx.x >> 5) == 0) tmem_dealloc(tmem, 128 * C1T_GROUPS);
 }
 
 // `slots`: shared array of the CTA's (<= 16) leaf slots, -1 = that warp emitted no leaf.  The four warps of TEAM `wg` -- one of
@@ -59,6 +64,7 @@ static __device__ __forceinline__ void conv1_tail_free(uint32_t tmem) {
 // and mbarrier.  slots[4 * wg + (warp % 4)] is this warp's entry.
 // slots[] entries are (slot | emitting warp << 20); `leaves` = the CTA's leaf records in shared memory, `leaf_words` 64-bit words
 // per warp: x words, o words, (to-move | last move << 8).
+template <int C1T_GROUPS>
 static __device__ __forceinline__ void conv1_tail(const Conv1TailArgs& a, uint8_t* smem, uint32_t tmem, int wg, const int* slots,
                                                   const uint64_t* leaves, int leaf_words, int NW) {
   const ConvGeom g = a.g;

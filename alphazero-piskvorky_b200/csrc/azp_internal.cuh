@@ -281,7 +281,7 @@ struct Conv1TailArgs {
   ConvGeom g;
   const __nv_bfloat16* w;          // [10][64][8] (UmmaWeights::w1_taps of the slot that evaluates these leaves)
   __nv_bfloat16* out;              // act1 [rows][32]
-  int enabled;
+  int enabled;                     // 0: no tail; else the warp groups per CTA (1, 2 or 4: four games each)
 };
 int azp_umma_conv1_tail(azp_engine* e, int slot, Conv1TailArgs* out);      // 1: the bf16 stem of `slot` can take the tail, 0: no
 

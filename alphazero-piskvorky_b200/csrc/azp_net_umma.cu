@@ -2159,6 +2159,7 @@ struct UmmaWorkspace {
   int fuse_fc = 0;                     // AZP_FUSE_FC=1: FC layers inside the conv3 kernel instead of the fc_umma_kernel launch
   unsigned int* feat_done = nullptr;   // [FC_MAX_BOARD_TILES] see ConvArgs
   unsigned int* fc_done = nullptr;     // [FC_MAX_BOARD_TILES]
+  int fuse_min_games = -1;             // AZP_FUSE_DESCENT_MIN_GAMES; -1: 8 x SMs
   int fuse_descent = 1;                // AZP_FUSE_DESCENT=0 (read when the engine is created): descent kernels without the conv1 tail
   int discard = 0;                     // AZP_DISCARD=1: dead activations are invalidated in L2 (measured: no gain, see discard_l2)
   // AZP_L2_PERSIST=1: act1 | act2 (ONE allocation) get an L2 access-policy window (persisting hits, streaming misses).
@@ -2344,6 +2345,7 @@ int azp_umma_create(azp_engine* e) {
   AZP_CUDA(e, cudaMemset(ws->fc_done, 0, FC_MAX_BOARD_TILES * sizeof(unsigned int)));
   { const char* v = getenv("AZP_DISCARD"); ws->discard = v ? atoi(v) : 0; }
   { const char* v = getenv("AZP_FUSE_DESCENT"); ws->fuse_descent = v ? atoi(v) : 1; }
+  { const char* v = getenv("AZP_FUSE_DESCENT_MIN_GAMES"); ws->fuse_min_games = v ? atoi(v) : -1; }
   // measured (profiles/r3_*): balancing the CTAs does not shorten conv2 -- the launch is bound by the chip-wide write stream, the
   // per-CTA spread is unfair arbitration of it -- and the polling costs a little: opt-in (AZP_DYN_TILES=1)
   { const char* v = getenv("AZP_DYN_TILES"); if (v && atoi(v) != 0) { if ((st = e->alloc(&ws->sched2, (size_t)SCHED_GROUPS + 1))) return st; AZP_CUDA(e, cudaMemset(ws->sched2, 0, (SCHED_GROUPS + 1) * sizeof(int))); } }
@@ -2948,10 +2950,17 @@ int azp_umma_conv1_tail(azp_engine* e, int slot, Conv1TailArgs* out) {
   static int fuse = -1;
   if (fuse < 0) { const char* v = getenv("AZP_FUSE_CONV1"); fuse = v ? atoi(v) : 0; }
   if (!ws->fuse_descent || ws->tower || ws->conv1_mode != 3 || !ws->conv1_pairs || fuse || !U->w1_taps) return 0;
-  // one 16-game CTA per SM: more games would make the descent a second wave, and with few games the tail would squeeze the
-  // whole batch's conv1 into games / 16 SMs (measured: the 400-game arena lost 20 %)
-  if (e->cfg.games > 16 * ws->sms || e->cfg.games < 8 * ws->sms) return 0;
-  out->g = ws->g; out->w = U->w1_taps; out->out = ws->act1; out->enabled = 1;
+  // one CTA per SM (see azp_conv1_tail.cuh): 4, 8 or 16 games per CTA, the fewest that seats every game -- with 16 per CTA the
+  // 400-game arena squeezed its conv1 into 25 SMs and lost 20 %; more than 16 * SMs games would make the descent a second wave
+  const int g4 = (e->cfg.games + 3) / 4;
+  const int groups = g4 <= ws->sms ? 1 : (g4 <= 2 * ws->sms ? 2 : 4);
+  if (e->cfg.games > 16 * ws->sms) return 0;
+  // Fewer games than half a machine-full: every CTA's boards go through its tail one after the other while the conv1 KERNEL
+  // spreads the same tiles over two CTAs per SM -- measured at config 5 (400 games of 19x19, four games per CTA on 100 SMs):
+  // 4.88 M simulations/s with the tail, 5.20 M without.  AZP_FUSE_DESCENT_MIN_GAMES (read when the engine is created) moves the
+  // threshold; the tests lower it to cover the one- and two-group instantiations.
+  if (e->cfg.games < (ws->fuse_min_games >= 0 ? ws->fuse_min_games : 8 * ws->sms)) return 0;
+  out->g = ws->g; out->w = U->w1_taps; out->out = ws->act1; out->enabled = groups;
   return 1;
 }
 

@@ -425,22 +425,22 @@ __global__ void __launch_bounds__(128, NW <= 2 ? 7 : 4) advance_kernel(RulesPara
 // ---- descent kernels with the conv1 tail (exact mode, bf16 stem; azp_conv1_tail.cuh) ----------------------------------
 // FIRST = the descent of step 0 (select_kernel), else expand+backup of step i fused with the descent of step i+1
 // (advance_kernel).  No early exits: every thread reaches the CTA barriers of the tail.
-template <int NW, bool FIRST>
-__global__ void __launch_bounds__(C1T_THREADS, 1) descend_conv1_kernel(RulesParams rp, TreeView tv, int n, const float* __restrict__ policy,
+template <int NW, bool FIRST, int GROUPS>
+__global__ void __launch_bounds__(c1t_threads(GROUPS), 1) descend_conv1_kernel(RulesParams rp, TreeView tv, int n, const float* __restrict__ policy,
                                      const float* __restrict__ value, int by_slot, int logits, double c_puct, int compact,
                                      int parity, Conv1TailArgs ct) {
   extern __shared__ uint8_t dc_smem_raw[];
   uint8_t* smem = dc_smem_raw + ((128u - (smem_u32(dc_smem_raw) & 127u)) & 127u);
-  __shared__ int s_slot[4 * C1T_GROUPS];
+  __shared__ int s_slot[4 * GROUPS];
   __shared__ int s_rank[4];     // warps of each lane quarter that have finished their descent
-  __shared__ uint64_t s_leaf[4 * C1T_GROUPS][2 * NW + 1];      // the leaves, by warp: the tail reads them here, not from global memory
+  __shared__ uint64_t s_leaf[4 * GROUPS][2 * NW + 1];      // the leaves, by warp: the tail reads them here, not from global memory
   if (threadIdx.x < 4) s_rank[threadIdx.x] = 0;
   const unsigned tl_idx = (threadIdx.x & 31) == 0 ? AZP_TL_ENTRY(AZP_TL_ADVANCE, gridDim.x * (blockDim.x >> 5)) : 0u;
-  conv1_tail_prologue(ct, smem);
+  conv1_tail_prologue<GROUPS>(ct, smem);
   pdl_wait();
   pdl_launch_dependents();
   if ((threadIdx.x & 31) == 0) AZP_TL_START(AZP_TL_ADVANCE, tl_idx);
-  const uint32_t tmem = conv1_tail_alloc(smem);
+  const uint32_t tmem = conv1_tail_alloc<GROUPS>(smem);
   const int g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (blockIdx.x == 0 && threadIdx.x == 0) {
     tv.n_leaves[(parity ^ 1) * 2 + 0] = 0;
@@ -480,8 +480,8 @@ __global__ void __launch_bounds__(C1T_THREADS, 1) descend_conv1_kernel(RulesPara
     s_slot[team * 4 + ((threadIdx.x >> 5) & 3)] = slot < 0 ? -1 : (slot | ((int)(threadIdx.x >> 5) << 20));     // slot | warp << 20
   }
   team = __shfl_sync(AZP_FULL, team, 0);
-  conv1_tail(ct, smem, tmem, team, s_slot, &s_leaf[0][0], 2 * NW + 1, NW);
-  conv1_tail_free(tmem);
+  conv1_tail<GROUPS>(ct, smem, tmem, team, s_slot, &s_leaf[0][0], 2 * NW + 1, NW);
+  conv1_tail_free<GROUPS>(tmem);
   if (lane == 0) AZP_TL_END(AZP_TL_ADVANCE, tl_idx, gridDim.x * (blockDim.x >> 5));
 }
 
@@ -790,51 +790,47 @@ int azp_tree_advance(azp_engine* e, int n, const float* policy, const float* val
   azp_prof_end(e, AZP_PROF_ADVANCE, s);
   return azp_check_launch();
 }
+template <int NW, int GROUPS>
+static void descend_conv1_launch(azp_engine* e, int n, bool first, const float* policy, const float* value, int by_slot, int logits,
+                                 int cp, int parity, const Conv1TailArgs& ct, cudaStream_t s) {
+  static bool configured = false;          // per instantiation: static + dynamic shared memory may exceed the 48 KB a kernel gets without opting in
+  if (!configured) {
+    configured = true;
+    cudaFuncSetAttribute(descend_conv1_kernel<NW, true, GROUPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, c1t_smem(GROUPS));
+    cudaFuncSetAttribute(descend_conv1_kernel<NW, false, GROUPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, c1t_smem(GROUPS));
+    cudaGetLastError();
+  }
+  const int grid = (n * 32 + c1t_threads(GROUPS) - 1) / c1t_threads(GROUPS);
+  if (first)
+    azp_launch(descend_conv1_kernel<NW, true, GROUPS>, grid, c1t_threads(GROUPS), c1t_smem(GROUPS), s, true, e->rp, e->tv, n, policy, value,
+               by_slot, logits, e->cfg.c_puct, cp, parity, ct);
+  else
+    azp_launch(descend_conv1_kernel<NW, false, GROUPS>, grid, c1t_threads(GROUPS), c1t_smem(GROUPS), s, true, e->rp, e->tv, n, policy, value,
+               by_slot, logits, e->cfg.c_puct, cp, parity, ct);
+}
+template <int NW>
+static void descend_conv1_groups(azp_engine* e, int groups, int n, bool first, const float* policy, const float* value, int by_slot,
+                                 int logits, int cp, int parity, const Conv1TailArgs& ct, cudaStream_t s) {
+  if (groups == 1) descend_conv1_launch<NW, 1>(e, n, first, policy, value, by_slot, logits, cp, parity, ct, s);
+  else if (groups == 2) descend_conv1_launch<NW, 2>(e, n, first, policy, value, by_slot, logits, cp, parity, ct, s);
+  else descend_conv1_launch<NW, 4>(e, n, first, policy, value, by_slot, logits, cp, parity, ct, s);
+}
+// `groups` (1, 2 or 4 warp groups of four games per CTA) comes from azp_umma_conv1_tail: the smallest that seats every game in one
+// CTA per SM
 int azp_tree_descend_conv1(azp_engine* e, int n, bool first, const float* policy, const float* value, int by_slot, int logits,
                            int compact, int parity, const Conv1TailArgs& ct, cudaStream_t s) {
   static int prefetch = -1;
   if (prefetch < 0) { const char* v = getenv("AZP_ROOT_PREFETCH"); prefetch = v ? atoi(v) != 0 : 1; }
   const int cp = compact | (prefetch << 4);
-  static bool configured = false;
-  if (!configured) {
-    // static + dynamic shared memory exceed the 48 KB a kernel gets without opting in
-    configured = true;
-#define AZP_DC_CFG(NWV)                                                                                                               \
-    do {                                                                                                                            \
-      cudaFuncSetAttribute(descend_conv1_kernel<NWV, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, C1T_SMEM);                   \
-      cudaFuncSetAttribute(descend_conv1_kernel<NWV, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, C1T_SMEM);                  \
-      int occ = 0;                                                                                                                  \
-      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, descend_conv1_kernel<NWV, false>, C1T_THREADS, C1T_SMEM);                   \
-      if (getenv("AZP_VERBOSE")) {                                                                                                  \
-        cudaFuncAttributes fa; cudaFuncGetAttributes(&fa, descend_conv1_kernel<NWV, false>);                                          \
-        int occ0 = 0, occa = 0; cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ0, descend_conv1_kernel<NWV, false>, C1T_THREADS, 0); \
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occa, advance_kernel<NWV>, 128, 0);                                            \
-        fprintf(stderr, "[azp] descend_conv1_kernel<%d>: %d resident CTAs per SM (%d without dynamic smem; advance_kernel %d); regs %d, static smem %zu, local %zu, max threads %d\n", \
-                NWV, occ, occ0, occa, fa.numRegs, fa.sharedSizeBytes, fa.localSizeBytes, fa.maxThreadsPerBlock);                      \
-      }                                                                                                                             \
-    } while (0)
-    AZP_DC_CFG(1); AZP_DC_CFG(2); AZP_DC_CFG(3); AZP_DC_CFG(4); AZP_DC_CFG(5); AZP_DC_CFG(6);     // every instantiation, once per process
-#undef AZP_DC_CFG
-    cudaGetLastError();
-  }
-  const int dc_grid = (n * 32 + C1T_THREADS - 1) / C1T_THREADS;
   azp_prof_begin(e, AZP_PROF_ADVANCE, nullptr, n, s);
-#define AZP_DC(NWV)                                                                                                        \
-  do {                                                                                                                     \
-    if (first) azp_launch(descend_conv1_kernel<NWV, true>, dc_grid, C1T_THREADS, C1T_SMEM, s, true, e->rp, e->tv, n, policy, value, by_slot, \
-                          logits, e->cfg.c_puct, cp, parity, ct);                                                          \
-    else azp_launch(descend_conv1_kernel<NWV, false>, dc_grid, C1T_THREADS, C1T_SMEM, s, true, e->rp, e->tv, n, policy, value, by_slot,     \
-                    logits, e->cfg.c_puct, cp, parity, ct);                                                                \
-  } while (0)
   switch (e->NW) {
-    case 1: AZP_DC(1); break;
-    case 2: AZP_DC(2); break;
-    case 3: AZP_DC(3); break;
-    case 4: AZP_DC(4); break;
-    case 5: AZP_DC(5); break;
-    default: AZP_DC(6); break;
+    case 1: descend_conv1_groups<1>(e, ct.enabled, n, first, policy, value, by_slot, logits, cp, parity, ct, s); break;
+    case 2: descend_conv1_groups<2>(e, ct.enabled, n, first, policy, value, by_slot, logits, cp, parity, ct, s); break;
+    case 3: descend_conv1_groups<3>(e, ct.enabled, n, first, policy, value, by_slot, logits, cp, parity, ct, s); break;
+    case 4: descend_conv1_groups<4>(e, ct.enabled, n, first, policy, value, by_slot, logits, cp, parity, ct, s); break;
+    case 5: descend_conv1_groups<5>(e, ct.enabled, n, first, policy, value, by_slot, logits, cp, parity, ct, s); break;
+    default: descend_conv1_groups<6>(e, ct.enabled, n, first, policy, value, by_slot, logits, cp, parity, ct, s); break;
   }
-#undef AZP_DC
   azp_count_launch();
   azp_prof_end(e, AZP_PROF_ADVANCE, s);
   return azp_check_launch();

@@ -466,21 +466,24 @@ def test_selfplay_manager_ring_path_and_live_weights(az):
     m.close()
 
 
-@pytest.mark.parametrize("size,win", [(9, 5), (15, 5)])
-def test_descent_conv1_tail_matches_the_conv1_kernel(az, size, win):
+@pytest.mark.parametrize("size,win,games", [(9, 5, 0), (15, 5, 0), (9, 5, 400), (15, 5, 900), (19, 5, 96), (6, 4, 200)])
+def test_descent_conv1_tail_matches_the_conv1_kernel(az, size, win, games):
     """Exact mode on the bf16 stem with enough games to fill the machine: the descent kernels run conv1 of the leaves they emit as
     their own tail (descend_conv1_kernel, azp_conv1_tail.cuh) instead of a conv1_taps_kernel launch.  Same operands, same UMMA
     sequence per row -> bit-identical activations -> the SAME self-play: visit counts of every root, moves, pi and examples equal
-    those of an engine created with AZP_FUSE_DESCENT=0, and the per-kernel profile shows which path ran."""
+    those of an engine created with AZP_FUSE_DESCENT=0, and the per-kernel profile shows which path ran.  Board sizes with one,
+    two and four 128-row tiles per board, pitch 16 (6x6) and B+1."""
     sms = torch.cuda.get_device_properties(0).multi_processor_count
-    n, sims = 8 * sms + 16, 12
+    n, sims = games or 8 * sms + 16, 12          # 4, 8 or 16 games per CTA: the fewest that seats every game in one CTA per SM
     outs = {}
     for fused in ("1", "0"):
         os.environ["AZP_FUSE_DESCENT"] = fused
+        os.environ["AZP_FUSE_DESCENT_MIN_GAMES"] = "64"      # by default the tail needs half a machine-full of games (8 per SM)
         try:
             eng = az.Engine(board=size, win_length=win, games=n, sims=sims, net_dtype=az.DTYPE_BF16, augment=az.AUGMENT_NONE, seed=3)
         finally:
             os.environ.pop("AZP_FUSE_DESCENT", None)
+            os.environ.pop("AZP_FUSE_DESCENT_MIN_GAMES", None)
         eng.load_state_dict(onet.synthetic_stem_params(size, seed=2, scale=2.0))
         with torch.cuda.stream(torch.cuda.Stream()):
             eng.set_profiling(True)
