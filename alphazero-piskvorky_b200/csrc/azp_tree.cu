@@ -793,9 +793,12 @@ int azp_tree_advance(azp_engine* e, int n, const float* policy, const float* val
 template <int NW, int GROUPS>
 static void descend_conv1_launch(azp_engine* e, int n, bool first, const float* policy, const float* value, int by_slot, int logits,
                                  int cp, int parity, const Conv1TailArgs& ct, cudaStream_t s) {
-  static bool configured = false;          // per instantiation: static + dynamic shared memory may exceed the 48 KB a kernel gets without opting in
-  if (!configured) {
-    configured = true;
+  // per instantiation AND device (function attributes belong to the device's context): static + dynamic shared memory may
+  // exceed the 48 KB a kernel gets without opting in
+  static bool configured[64] = {false};
+  const int dev = e->cfg.device & 63;
+  if (!configured[dev]) {
+    configured[dev] = true;
     cudaFuncSetAttribute(descend_conv1_kernel<NW, true, GROUPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, c1t_smem(GROUPS));
     cudaFuncSetAttribute(descend_conv1_kernel<NW, false, GROUPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, c1t_smem(GROUPS));
     cudaGetLastError();
