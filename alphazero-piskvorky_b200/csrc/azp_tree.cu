@@ -379,6 +379,26 @@ __global__ void expand_backup_kernel(RulesParams rp, TreeView tv, int n, const f
   expand_backup_body<NW>(rp, tv, g, lane, policy, value, by_slot, logits, value_f64);
 }
 
+// The descent starts with the ROOT's edge arrays (20 B x A, evicted from L2 by ~100 MB of activations per step): ask L2 for
+// them ahead of use.  They are tree data only this kernel family writes, so the request may even be issued BEFORE
+// griddepcontrol.wait (`early`, AZP_ROOT_PREFETCH=2), while the FC kernel is still running.
+template <int NW>
+__device__ __forceinline__ void prefetch_root(const RulesParams& rp, const TreeView& tv, int g, int lane) {
+  const size_t gb = (size_t)g * tv.cap * rp.A;
+  const char* pn = reinterpret_cast<const char*>(tv.N + gb);
+  const char* pw = reinterpret_cast<const char*>(tv.W + gb);
+  const char* pp = reinterpret_cast<const char*>(tv.P + gb);
+  const char* pc = reinterpret_cast<const char*>(tv.child + gb);
+  for (int o = lane * 128; o < rp.A * 8; o += 32 * 128) {
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(pw + o));
+    if (o < rp.A * 4) {
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(pn + o));
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(pp + o));
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(pc + o));
+    }
+  }
+}
+
 // expand+backup of simulation step i followed at once by the descent of step i+1: the same warp owns the game in
 // both halves, so the two launches of the lockstep loop collapse into one (the tree lines just written are still
 // in L1/L2 when the descent re-reads them)
@@ -387,16 +407,17 @@ __global__ void __launch_bounds__(128, NW <= 2 ? 7 : 4) advance_kernel(RulesPara
                                const float* __restrict__ value, int by_slot, int logits, double c_puct, int compact,
                                int parity) {
   const unsigned tl_idx = (threadIdx.x & 31) == 0 ? AZP_TL_ENTRY(AZP_TL_ADVANCE, gridDim.x * (blockDim.x >> 5)) : 0u;
+  int g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (tv.K == 1 && ((compact >> 5) & 1) && g < n) prefetch_root<NW>(rp, tv, g, lane);      // bit 5: before the wait (see prefetch_root)
   pdl_wait();
   pdl_launch_dependents();
   if ((threadIdx.x & 31) == 0) AZP_TL_START(AZP_TL_ADVANCE, tl_idx);
-  int g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (blockIdx.x == 0 && threadIdx.x == 0) {
     tv.n_leaves[(parity ^ 1) * 2 + 0] = 0;
     tv.n_leaves[(parity ^ 1) * 2 + 1] = 0;
   }
   if (g >= n) { if (lane == 0) AZP_TL_END(AZP_TL_ADVANCE, tl_idx, gridDim.x * (blockDim.x >> 5)); return; }
-  const bool root_prefetch = (compact >> 4) & 1;           // bit 4 of `compact`: AZP_ROOT_PREFETCH (default on)
+  const bool root_prefetch = ((compact >> 4) & 1) && !((compact >> 5) & 1);      // bit 4 of `compact`: AZP_ROOT_PREFETCH
   compact &= 15;
   if (tv.K == 1 && root_prefetch) {
     // The descent below starts with the ROOT's edge arrays (20 B x A, evicted from L2 by ~100 MB of activations per
@@ -437,6 +458,10 @@ __global__ void __launch_bounds__(c1t_threads(GROUPS), 1) descend_conv1_kernel(R
   if (threadIdx.x < 4) s_rank[threadIdx.x] = 0;
   const unsigned tl_idx = (threadIdx.x & 31) == 0 ? AZP_TL_ENTRY(AZP_TL_ADVANCE, gridDim.x * (blockDim.x >> 5)) : 0u;
   conv1_tail_prologue<GROUPS>(ct, smem);
+  {
+    const int g0 = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (!FIRST && ((compact >> 5) & 1) && g0 < n) prefetch_root<NW>(rp, tv, g0, threadIdx.x & 31);
+  }
   pdl_wait();
   pdl_launch_dependents();
   if ((threadIdx.x & 31) == 0) AZP_TL_START(AZP_TL_ADVANCE, tl_idx);
@@ -446,7 +471,7 @@ __global__ void __launch_bounds__(c1t_threads(GROUPS), 1) descend_conv1_kernel(R
     tv.n_leaves[(parity ^ 1) * 2 + 0] = 0;
     tv.n_leaves[(parity ^ 1) * 2 + 1] = 0;
   }
-  const bool root_prefetch = (compact >> 4) & 1;
+  const bool root_prefetch = ((compact >> 4) & 1) && !((compact >> 5) & 1);
   compact &= 15;
   int slot = -1;
   if (g < n) {
@@ -782,10 +807,10 @@ int azp_tree_expand_backup(azp_engine* e, int n, const float* policy, const void
 int azp_tree_advance(azp_engine* e, int n, const float* policy, const float* value, int by_slot, int logits, int compact,
                      int parity, cudaStream_t s) {
   static int prefetch = -1;
-  if (prefetch < 0) { const char* v = getenv("AZP_ROOT_PREFETCH"); prefetch = v ? atoi(v) != 0 : 1; }
+  if (prefetch < 0) { const char* v = getenv("AZP_ROOT_PREFETCH"); prefetch = v ? atoi(v) : 2; }     // 0 off, 1 after the wait, 2 before it
   azp_prof_begin(e, AZP_PROF_ADVANCE, nullptr, n, s);
   AZP_DISPATCH_NW_PDL(e->NW, advance_kernel, warp_grid(n), 128, 0, s, e->rp, e->tv, n, policy, value, by_slot, logits,
-                      e->cfg.c_puct, compact | (prefetch << 4), parity);
+                      e->cfg.c_puct, compact | ((prefetch != 0) << 4) | ((prefetch == 2) << 5), parity);
   azp_count_launch();
   azp_prof_end(e, AZP_PROF_ADVANCE, s);
   return azp_check_launch();
@@ -823,8 +848,8 @@ static void descend_conv1_groups(azp_engine* e, int groups, int n, bool first, c
 int azp_tree_descend_conv1(azp_engine* e, int n, bool first, const float* policy, const float* value, int by_slot, int logits,
                            int compact, int parity, const Conv1TailArgs& ct, cudaStream_t s) {
   static int prefetch = -1;
-  if (prefetch < 0) { const char* v = getenv("AZP_ROOT_PREFETCH"); prefetch = v ? atoi(v) != 0 : 1; }
-  const int cp = compact | (prefetch << 4);
+  if (prefetch < 0) { const char* v = getenv("AZP_ROOT_PREFETCH"); prefetch = v ? atoi(v) : 2; }     // 0 off, 1 after the wait, 2 before it
+  const int cp = compact | ((prefetch != 0) << 4) | ((prefetch == 2) << 5);
   azp_prof_begin(e, AZP_PROF_ADVANCE, nullptr, n, s);
   switch (e->NW) {
     case 1: descend_conv1_groups<1>(e, ct.enabled, n, first, policy, value, by_slot, logits, cp, parity, ct, s); break;
