@@ -277,31 +277,59 @@ __device__ __forceinline__ void select_body(const RulesParams& rp, const TreeVie
 
 // ---- expand the evaluated leaves and back the values up (mcts.py:136-141, 50-64, 76-82) --------
 // returns false on a capacity overflow (error flag set)
+// Everything expand+backup needs that the NETWORK kernels do not write -- the leaf record of the previous descent, its
+// bitboards, the path -- can be loaded before griddepcontrol.wait (exact mode, K == 1): two dependent memory round trips
+// (record -> slot -> bitboards) leave the critical path of the step.
+template <int NW>
+struct ExpandPre {
+  int active, kind, depth, slot, nid, edge;      // edge = path[lane] (lane < depth)
+  BB<NW> lx, lo;
+};
+template <int NW>
+__device__ __forceinline__ ExpandPre<NW> expand_preload(const TreeView& tv, int g, int lane) {
+  ExpandPre<NW> p;
+  p.kind = 2; p.depth = 0; p.slot = -1; p.nid = 0; p.edge = 0;
+  p.active = tv.active[g];
+  if (!p.active) return p;
+  p.kind = tv.leaf_kind[g];
+  p.depth = tv.path_len[g];
+  p.slot = tv.leaf_slot[g];
+  p.nid = tv.node_count[g];
+  if (lane < p.depth) p.edge = tv.path[(size_t)g * tv.maxd + lane];
+  if (p.kind == 0 && p.slot >= 0) {
+    p.lx = bb_load<NW>(tv.leaf_x + (size_t)p.slot * NW);
+    p.lo = bb_load<NW>(tv.leaf_o + (size_t)p.slot * NW);
+  }
+  return p;
+}
+
 template <int NW>
 __device__ __forceinline__ bool expand_backup_body(const RulesParams& rp, const TreeView& tv, int g, int lane,
                                                    const float* __restrict__ policy, const void* __restrict__ value,
-                                                   int by_slot, int logits, int value_f64 = 0) {
-  if (!tv.active[g]) return true;
+                                                   int by_slot, int logits, int value_f64 = 0, const ExpandPre<NW>* pre = nullptr) {
+  if (!(pre ? pre->active : tv.active[g])) return true;
   const int A = rp.A, K = tv.K;
   const size_t gbase = (size_t)g * tv.cap * A;
   unsigned long long n_exp = 0, n_sims = 0;
   for (int kd = 0; kd < K; kd++) {
     const int rec = g * K + kd;
-    const int kind = tv.leaf_kind[rec];
+    const int kind = pre ? pre->kind : tv.leaf_kind[rec];
     if (kind == 2) continue;
     const int32_t* path = tv.path + (size_t)rec * tv.maxd;
-    const int depth = tv.path_len[rec];
+    const int depth = pre ? pre->depth : tv.path_len[rec];
     double v;                                     // the reference backs up a Python float (float64), mcts.py:137-141
     if (kind == 0) {
-      const int slot = tv.leaf_slot[rec];
+      const int slot = pre ? pre->slot : tv.leaf_slot[rec];
       const size_t row = (size_t)(by_slot ? slot : rec);
       v = value_f64 ? static_cast<const double*>(value)[row] : (double)static_cast<const float*>(value)[row];
-      int nid = tv.node_count[g];
+      int nid = pre ? pre->nid : tv.node_count[g];
       if (nid >= tv.cap) {
         if (lane == 0) atomicExch(tv.error_flag, AZP_ERR_CAPACITY);
         return false;
       }
-      BB<NW> lx = bb_load<NW>(tv.leaf_x + (size_t)slot * NW), lo = bb_load<NW>(tv.leaf_o + (size_t)slot * NW);
+      BB<NW> lx, lo;
+      if (pre) { lx = pre->lx; lo = pre->lo; }
+      else { lx = bb_load<NW>(tv.leaf_x + (size_t)slot * NW); lo = bb_load<NW>(tv.leaf_o + (size_t)slot * NW); }
       const size_t nb = gbase + (size_t)nid * A;
       const float* prow = policy + row * A;
       float sm_m = 0.f, sm_inv = 1.f;             // `logits`: raw logits in, softmax over all cells here (controller.py:49)
@@ -331,7 +359,7 @@ __device__ __forceinline__ bool expand_backup_body(const RulesParams& rp, const 
     // node.backup(-value): the leaf's own statistics (last edge) take -v, signs alternate upwards.
     // Throughput mode: the edge already carries this descent's virtual visit (N+1, W-1): swap it for the value.
     for (int i = lane; i < depth; i += 32) {
-      const size_t e = gbase + path[i];
+      const size_t e = gbase + ((pre && i < 32) ? pre->edge : path[i]);
       const double val = ((depth - 1 - i) & 1) ? v : -v;
       if (K == 1) {
         tv.N[e] += 1;
@@ -409,6 +437,10 @@ __global__ void __launch_bounds__(128, NW <= 2 ? 7 : 4) advance_kernel(RulesPara
   const unsigned tl_idx = (threadIdx.x & 31) == 0 ? AZP_TL_ENTRY(AZP_TL_ADVANCE, gridDim.x * (blockDim.x >> 5)) : 0u;
   int g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (tv.K == 1 && ((compact >> 5) & 1) && g < n) prefetch_root<NW>(rp, tv, g, lane);      // bit 5: before the wait (see prefetch_root)
+  ExpandPre<NW> pre;
+  pre.active = 0;
+  const bool use_pre = tv.K == 1 && !((compact >> 6) & 1) && g < n;                       // bit 6: AZP_EXPAND_PRELOAD=0
+  if (use_pre) pre = expand_preload<NW>(tv, g, lane);
   pdl_wait();
   pdl_launch_dependents();
   if ((threadIdx.x & 31) == 0) AZP_TL_START(AZP_TL_ADVANCE, tl_idx);
@@ -436,7 +468,7 @@ __global__ void __launch_bounds__(128, NW <= 2 ? 7 : 4) advance_kernel(RulesPara
       }
     }
   }
-  if (expand_backup_body<NW>(rp, tv, g, lane, policy, value, by_slot, logits)) {
+  if (expand_backup_body<NW>(rp, tv, g, lane, policy, value, by_slot, logits, 0, use_pre ? &pre : nullptr)) {
     __syncwarp();             // the descent's lanes read edges other lanes of this warp have just written
     select_body<NW>(rp, tv, g, lane, c_puct, compact, parity);
   }
@@ -458,10 +490,16 @@ __global__ void __launch_bounds__(c1t_threads(GROUPS), 1) descend_conv1_kernel(R
   if (threadIdx.x < 4) s_rank[threadIdx.x] = 0;
   const unsigned tl_idx = (threadIdx.x & 31) == 0 ? AZP_TL_ENTRY(AZP_TL_ADVANCE, gridDim.x * (blockDim.x >> 5)) : 0u;
   conv1_tail_prologue<GROUPS>(ct, smem);
+  ExpandPre<NW> pre;
+  pre.active = 0;
   {
     const int g0 = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    if (!FIRST && ((compact >> 5) & 1) && g0 < n) prefetch_root<NW>(rp, tv, g0, threadIdx.x & 31);
+    if (!FIRST && g0 < n) {
+      if ((compact >> 5) & 1) prefetch_root<NW>(rp, tv, g0, threadIdx.x & 31);
+      if (!((compact >> 6) & 1)) pre = expand_preload<NW>(tv, g0, threadIdx.x & 31);
+    }
   }
+  const bool use_pre = !FIRST && !((compact >> 6) & 1);      // bit 6: AZP_EXPAND_PRELOAD=0
   pdl_wait();
   pdl_launch_dependents();
   if ((threadIdx.x & 31) == 0) AZP_TL_START(AZP_TL_ADVANCE, tl_idx);
@@ -492,7 +530,7 @@ __global__ void __launch_bounds__(c1t_threads(GROUPS), 1) descend_conv1_kernel(R
     }
     bool ok = true;
     if (!FIRST) {
-      ok = expand_backup_body<NW>(rp, tv, g, lane, policy, value, by_slot, logits);
+      ok = expand_backup_body<NW>(rp, tv, g, lane, policy, value, by_slot, logits, 0, use_pre ? &pre : nullptr);
       __syncwarp();             // the descent's lanes read edges other lanes of this warp have just written
     }
     if (ok) select_body<NW>(rp, tv, g, lane, c_puct, compact, parity, &slot, s_leaf[threadIdx.x >> 5]);
@@ -808,9 +846,11 @@ int azp_tree_advance(azp_engine* e, int n, const float* policy, const float* val
                      int parity, cudaStream_t s) {
   static int prefetch = -1;
   if (prefetch < 0) { const char* v = getenv("AZP_ROOT_PREFETCH"); prefetch = v ? atoi(v) : 2; }     // 0 off, 1 after the wait, 2 before it
+  static int preload = -1;
+  if (preload < 0) { const char* v = getenv("AZP_EXPAND_PRELOAD"); preload = v ? atoi(v) : 1; }
   azp_prof_begin(e, AZP_PROF_ADVANCE, nullptr, n, s);
   AZP_DISPATCH_NW_PDL(e->NW, advance_kernel, warp_grid(n), 128, 0, s, e->rp, e->tv, n, policy, value, by_slot, logits,
-                      e->cfg.c_puct, compact | ((prefetch != 0) << 4) | ((prefetch == 2) << 5), parity);
+                      e->cfg.c_puct, compact | ((prefetch != 0) << 4) | ((prefetch == 2) << 5) | ((preload == 0) << 6), parity);
   azp_count_launch();
   azp_prof_end(e, AZP_PROF_ADVANCE, s);
   return azp_check_launch();
@@ -849,7 +889,9 @@ int azp_tree_descend_conv1(azp_engine* e, int n, bool first, const float* policy
                            int compact, int parity, const Conv1TailArgs& ct, cudaStream_t s) {
   static int prefetch = -1;
   if (prefetch < 0) { const char* v = getenv("AZP_ROOT_PREFETCH"); prefetch = v ? atoi(v) : 2; }     // 0 off, 1 after the wait, 2 before it
-  const int cp = compact | ((prefetch != 0) << 4) | ((prefetch == 2) << 5);
+  static int preload = -1;
+  if (preload < 0) { const char* v = getenv("AZP_EXPAND_PRELOAD"); preload = v ? atoi(v) : 1; }
+  const int cp = compact | ((prefetch != 0) << 4) | ((prefetch == 2) << 5) | ((preload == 0) << 6);
   azp_prof_begin(e, AZP_PROF_ADVANCE, nullptr, n, s);
   switch (e->NW) {
     case 1: descend_conv1_groups<1>(e, ct.enabled, n, first, policy, value, by_slot, logits, cp, parity, ct, s); break;
