@@ -283,19 +283,24 @@ __device__ __forceinline__ void select_body(const RulesParams& rp, const TreeVie
 template <int NW>
 struct ExpandPre {
   int active, kind, depth, slot, nid, edge;      // edge = path[lane] (lane < depth)
+  int en; double ew;                             // that edge's N and W: the backup's read-modify-write starts from registers
   BB<NW> lx, lo;
 };
 template <int NW>
-__device__ __forceinline__ ExpandPre<NW> expand_preload(const TreeView& tv, int g, int lane) {
+__device__ __forceinline__ ExpandPre<NW> expand_preload(const TreeView& tv, int A, int g, int lane) {
   ExpandPre<NW> p;
-  p.kind = 2; p.depth = 0; p.slot = -1; p.nid = 0; p.edge = 0;
+  p.kind = 2; p.depth = 0; p.slot = -1; p.nid = 0; p.edge = 0; p.en = 0; p.ew = 0.0;
   p.active = tv.active[g];
   if (!p.active) return p;
   p.kind = tv.leaf_kind[g];
   p.depth = tv.path_len[g];
   p.slot = tv.leaf_slot[g];
   p.nid = tv.node_count[g];
-  if (lane < p.depth) p.edge = tv.path[(size_t)g * tv.maxd + lane];
+  if (lane < p.depth) {
+    p.edge = tv.path[(size_t)g * tv.maxd + lane];
+    const size_t e = (size_t)g * tv.cap * (size_t)A + (size_t)p.edge;
+    p.en = tv.N[e]; p.ew = tv.W[e];
+  }
   if (p.kind == 0 && p.slot >= 0) {
     p.lx = bb_load<NW>(tv.leaf_x + (size_t)p.slot * NW);
     p.lo = bb_load<NW>(tv.leaf_o + (size_t)p.slot * NW);
@@ -362,8 +367,9 @@ __device__ __forceinline__ bool expand_backup_body(const RulesParams& rp, const 
       const size_t e = gbase + ((pre && i < 32) ? pre->edge : path[i]);
       const double val = ((depth - 1 - i) & 1) ? v : -v;
       if (K == 1) {
-        tv.N[e] += 1;
-        tv.W[e] = __dadd_rn(tv.W[e], val);
+        const bool have = pre && i < 32;
+        tv.N[e] = (have ? pre->en : tv.N[e]) + 1;
+        tv.W[e] = __dadd_rn(have ? pre->ew : tv.W[e], val);
       } else {
         tv.W[e] += 1.0 + val;
       }
@@ -440,7 +446,7 @@ __global__ void __launch_bounds__(128, NW <= 2 ? 7 : 4) advance_kernel(RulesPara
   ExpandPre<NW> pre;
   pre.active = 0;
   const bool use_pre = tv.K == 1 && !((compact >> 6) & 1) && g < n;                       // bit 6: AZP_EXPAND_PRELOAD=0
-  if (use_pre) pre = expand_preload<NW>(tv, g, lane);
+  if (use_pre) pre = expand_preload<NW>(tv, rp.A, g, lane);
   pdl_wait();
   pdl_launch_dependents();
   if ((threadIdx.x & 31) == 0) AZP_TL_START(AZP_TL_ADVANCE, tl_idx);
@@ -496,7 +502,7 @@ __global__ void __launch_bounds__(c1t_threads(GROUPS), 1) descend_conv1_kernel(R
     const int g0 = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (!FIRST && g0 < n) {
       if ((compact >> 5) & 1) prefetch_root<NW>(rp, tv, g0, threadIdx.x & 31);
-      if (!((compact >> 6) & 1)) pre = expand_preload<NW>(tv, g0, threadIdx.x & 31);
+      if (!((compact >> 6) & 1)) pre = expand_preload<NW>(tv, rp.A, g0, threadIdx.x & 31);
     }
   }
   const bool use_pre = !FIRST && !((compact >> 6) & 1);      // bit 6: AZP_EXPAND_PRELOAD=0
