@@ -13,11 +13,14 @@
 // address bits), so ONE TMA box of 128+2P+2 rows per 128-row output tile feeds all nine taps.
 //
 // Pipeline per step (leaf batch of n positions):
-//   conv1_bits_kernel   bitboards -> act1 [rows][32]      SIMT (inputs are 0/1: pattern-indexed tables of pre-summed weights)
+//   conv1               bitboards -> act1 [rows][32]      tcgen05: nine-tap implicit GEMM on 16-byte input rows, two taps per UMMA
+//                                                         (azp_net_conv1.cuh; in the exact mode with a machine-full of games it
+//                                                         runs as the TAIL of the descent kernel instead: azp_conv1_tail.cuh)
 //   conv_umma<32,64>    act1 -> act2 [rows][64]           tcgen05, bias+ReLU+pad-zero epilogue
 //   conv_umma<64,128>   act2 -> head features [n][6][A]   tcgen05, epilogue = bias+ReLU + both 1x1 head
 //                                                         convs (act3 never leaves the SM)
-//   fc_umma_kernel      features -> logits/softmax/value  tcgen05 GEMMs (policy_fc, value_fc1), thread-per-row tails
+//   fc_umma_kernel      features -> logits / value        tcgen05 GEMMs (policy_fc, value_fc1), thread-per-row tails
+// Every issuer WARP runs its issue loop whole and elects one lane per tcgen05 instruction (azp_tc.cuh: elect_one).
 #include "azp_net.cuh"
 #include "azp_tc.cuh"
 #include <cuda.h>
