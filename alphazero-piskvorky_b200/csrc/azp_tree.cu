@@ -117,13 +117,66 @@ __global__ void root_expand_kernel(RulesParams rp, TreeView tv, int n, const flo
 #define CHILD_NONE (-1)
 #define CHILD_PENDING (-2)      // claimed by an earlier descent of this step (throughput mode only)
 
+// ---- one node's PUCT scan (mcts.py:66-74) ----------------------------------------------------------------------
+// score = Q + c_puct * P * sqrt(N_parent + 1e-8) / (1 + N_child), float64, left to right; argmax with the lowest cell winning
+// ties; `ex` (or -1): a cell left out of the scan (root_prescan).  Returns the winner's N / child pointer too.
+template <int NW>
+__device__ __forceinline__ void scan_node(const TreeView& tv, size_t nb, int A, const uint64_t (&occw)[NW], int nparent,
+                                          double c_puct, int lane, int ex, double& best, int& besta, int& cn, int& ch) {
+  const double sq = __dsqrt_rn(__dadd_rn((double)nparent, 1e-8));
+  best = -1.0e308;
+  besta = 0x7fffffff;
+  // all of a node's edge statistics are fetched before any arithmetic: one memory round trip per level
+  constexpr int MAXI = (2 * NW < (AZP_MAX_BOARD * AZP_MAX_BOARD + 31) / 32) ? 2 * NW   // A <= 64*NW cells = 2*NW per lane
+                                                                         : (AZP_MAX_BOARD * AZP_MAX_BOARD + 31) / 32;
+  int nn_[MAXI], ch_[MAXI];
+  double ww_[MAXI];
+  float pp_[MAXI];
+#pragma unroll
+  for (int i = 0; i < MAXI; i++) {
+    const int a = lane + 32 * i;
+    nn_[i] = 0; ww_[i] = 0.0; pp_[i] = 0.f; ch_[i] = CHILD_NONE;
+    if (a < A) { nn_[i] = tv.N[nb + a]; ww_[i] = tv.W[nb + a]; pp_[i] = tv.P[nb + a]; ch_[i] = tv.child[nb + a]; }
+  }
+#pragma unroll
+  for (int i = 0; i < MAXI; i++) {
+    const int a = lane + 32 * i;
+    const bool occupied = a >= A || a == ex || ((occw[i >> 1] >> (lane + 32 * (i & 1))) & 1ull);
+    if (occupied) continue;
+    const int nn = nn_[i];
+    // unvisited children (the vast majority of slots) need no fp64 division: Q = 0 and x / 1.0 == x exactly
+    const double num = __dmul_rn(__dmul_rn(c_puct, (double)pp_[i]), sq);
+    double q = 0.0, u = num;
+    if (nn) {
+      q = __ddiv_rn(ww_[i], (double)nn);
+      u = __ddiv_rn(num, (double)(1 + nn));
+    }
+    const double s = nn ? __dadd_rn(q, u) : u;   // 0.0 + u == u exactly (u >= 0)
+    if (s > best) { best = s; besta = a; }    // ascending a: the FIRST maximum is kept
+  }
+#pragma unroll
+  for (int off = 16; off; off >>= 1) {       // argmax with lowest-cell tie-break
+    double ob = __shfl_xor_sync(AZP_FULL, best, off);
+    int oa = __shfl_xor_sync(AZP_FULL, besta, off);
+    if (ob > best || (ob == best && oa < besta)) { best = ob; besta = oa; }
+  }
+  // the winning edge's N / child pointer are already in the owning lane's registers
+  cn = 0; ch = CHILD_NONE;
+#pragma unroll
+  for (int i = 0; i < MAXI; i++) if (i == (besta >> 5)) { cn = nn_[i]; ch = ch_[i]; }
+  cn = __shfl_sync(AZP_FULL, cn, besta & 31);
+  ch = __shfl_sync(AZP_FULL, ch, besta & 31);
+}
+struct RootScan { double best; int besta, cn, ch; };      // argmax over the root's children (see root_prescan)
+
 // ---- K PUCT descents per game (mcts.py:126-129 + 66-74) ---------------------------------------
 // K == 1 is the exact mode: the tree is only read here.  K > 1 (throughput mode): after each descent its
 // path takes a VIRTUAL LOSS (N += 1, W -= 1, undone by expand_backup) so the next descent of the same step
 // goes elsewhere; an unexpanded edge reached twice in one step is a collision and the later descent idles.
 template <int NW>
 __device__ __forceinline__ void select_body(const RulesParams& rp, const TreeView& tv, int g, int lane, double c_puct,
-                                            int compact, int parity, int* slot_out = nullptr, uint64_t* leaf_out = nullptr) {
+                                            int compact, int parity, int* slot_out = nullptr, uint64_t* leaf_out = nullptr,
+                                            const RootScan* rs = nullptr) {
   const int K = tv.K;
   const int rec0 = g * K;
   if (!tv.active[g]) {
@@ -157,47 +210,16 @@ __device__ __forceinline__ void select_body(const RulesParams& rp, const TreeVie
         break;
       }
       const size_t nb = gbase + (size_t)node * A;
-      // score = Q + c_puct * P * sqrt(N_parent + 1e-8) / (1 + N_child), float64, left to right
-      const double sq = __dsqrt_rn(__dadd_rn((double)nparent, 1e-8));
-      double best = -1.0e308;
-      int besta = 0x7fffffff;
       int stones = 0;
       uint64_t occw[NW];                         // occupancy: cell a = lane + 32i is bit lane + 32(i&1) of word i>>1
 #pragma unroll
       for (int k = 0; k < NW; k++) { occw[k] = x.w[k] | o.w[k]; stones += __popcll(occw[k]); }
-      // all of a node's edge statistics are fetched before any arithmetic: one memory round trip per level
-      constexpr int MAXI = (2 * NW < (AZP_MAX_BOARD * AZP_MAX_BOARD + 31) / 32) ? 2 * NW   // A <= 64*NW cells = 2*NW per lane
-                                                                             : (AZP_MAX_BOARD * AZP_MAX_BOARD + 31) / 32;
-      int nn_[MAXI], ch_[MAXI];
-      double ww_[MAXI];
-      float pp_[MAXI];
-#pragma unroll
-      for (int i = 0; i < MAXI; i++) {
-        const int a = lane + 32 * i;
-        nn_[i] = 0; ww_[i] = 0.0; pp_[i] = 0.f; ch_[i] = CHILD_NONE;
-        if (a < A) { nn_[i] = tv.N[nb + a]; ww_[i] = tv.W[nb + a]; pp_[i] = tv.P[nb + a]; ch_[i] = tv.child[nb + a]; }
-      }
-#pragma unroll
-      for (int i = 0; i < MAXI; i++) {
-        const int a = lane + 32 * i;
-        const bool occupied = a >= A || ((occw[i >> 1] >> (lane + 32 * (i & 1))) & 1ull);
-        if (occupied) continue;
-        const int nn = nn_[i];
-        // unvisited children (the vast majority of slots) need no fp64 division: Q = 0 and x / 1.0 == x exactly
-        const double num = __dmul_rn(__dmul_rn(c_puct, (double)pp_[i]), sq);
-        double q = 0.0, u = num;
-        if (nn) {
-          q = __ddiv_rn(ww_[i], (double)nn);
-          u = __ddiv_rn(num, (double)(1 + nn));
-        }
-        const double s = nn ? __dadd_rn(q, u) : u;   // 0.0 + u == u exactly (u >= 0)
-        if (s > best) { best = s; besta = a; }    // ascending a: the FIRST maximum is kept
-      }
-#pragma unroll
-      for (int off = 16; off; off >>= 1) {       // argmax with lowest-cell tie-break
-        double ob = __shfl_xor_sync(AZP_FULL, best, off);
-        int oa = __shfl_xor_sync(AZP_FULL, besta, off);
-        if (ob > best || (ob == best && oa < besta)) { best = ob; besta = oa; }
+      double best;
+      int besta, cn, ch;
+      if (rs && node == 0 && depth == 0) {       // the root's scan was done before the dependency wait (root_prescan)
+        best = rs->best; besta = rs->besta; cn = rs->cn; ch = rs->ch;
+      } else {
+        scan_node<NW>(tv, nb, A, occw, nparent, c_puct, lane, -1, best, besta, cn, ch);
       }
       scanned += (unsigned long long)(A - stones);
       const int a = besta;
@@ -206,12 +228,6 @@ __device__ __forceinline__ void select_body(const RulesParams& rp, const TreeVie
         kind = 2;
         break;
       }
-      // the winning edge's N / child pointer are already in the owning lane's registers
-      int cn = 0, ch = CHILD_NONE;
-#pragma unroll
-      for (int i = 0; i < MAXI; i++) if (i == (a >> 5)) { cn = nn_[i]; ch = ch_[i]; }
-      cn = __shfl_sync(AZP_FULL, cn, a & 31);
-      ch = __shfl_sync(AZP_FULL, ch, a & 31);
       if (lane == 0) path[depth] = node * A + a;
       depth++;
       if (tm == 1) bb_set<NW>(x, a); else bb_set<NW>(o, a);
@@ -311,7 +327,7 @@ __device__ __forceinline__ ExpandPre<NW> expand_preload(const TreeView& tv, int 
 template <int NW>
 __device__ __forceinline__ bool expand_backup_body(const RulesParams& rp, const TreeView& tv, int g, int lane,
                                                    const float* __restrict__ policy, const void* __restrict__ value,
-                                                   int by_slot, int logits, int value_f64 = 0, const ExpandPre<NW>* pre = nullptr) {
+                                                   int by_slot, int logits, int value_f64 = 0, ExpandPre<NW>* pre = nullptr) {
   if (!(pre ? pre->active : tv.active[g])) return true;
   const int A = rp.A, K = tv.K;
   const size_t gbase = (size_t)g * tv.cap * A;
@@ -368,8 +384,11 @@ __device__ __forceinline__ bool expand_backup_body(const RulesParams& rp, const 
       const double val = ((depth - 1 - i) & 1) ? v : -v;
       if (K == 1) {
         const bool have = pre && i < 32;
-        tv.N[e] = (have ? pre->en : tv.N[e]) + 1;
-        tv.W[e] = __dadd_rn(have ? pre->ew : tv.W[e], val);
+        const int n_new = (have ? pre->en : tv.N[e]) + 1;
+        const double w_new = __dadd_rn(have ? pre->ew : tv.W[e], val);
+        tv.N[e] = n_new;
+        tv.W[e] = w_new;
+        if (have) { pre->en = n_new; pre->ew = w_new; }     // lane 0: the ROOT edge's new statistics (root_merge)
       } else {
         tv.W[e] += 1.0 + val;
       }
@@ -383,6 +402,55 @@ __device__ __forceinline__ bool expand_backup_body(const RulesParams& rp, const 
     count(tv, CNT_EXPANSIONS, n_exp);
   }
   return true;
+}
+
+// ---- the root's PUCT scan, before the dependency wait (exact mode, K == 1) -------------------------------------------
+// The descent of step i+1 starts with a scan of the root's children.  The backup of step i changes exactly ONE of them (the
+// root edge of the pending path: N + 1, W +- v, and its child pointer if the new node hangs right under the root), and the
+// root's own visit count becomes root_n + 1 whatever the network says.  So the scan of every OTHER child runs before
+// griddepcontrol.wait with the post-backup parent count, and after the backup the one changed child is scored with the same
+// arithmetic and merged in with the same tie-break (lowest cell).  Decisions are identical to scanning after the backup
+// (parity tests green with it on).  OPT-IN (AZP_ROOT_PRESCAN=1): measured 15.19 M against 15.54 M simulations/s at config 3 --
+// unlike the handful of loads of expand_preload, a whole scan before the wait is not hidden: on the 80 SMs the FC kernel
+// occupies, the descent's CTA only becomes resident when FC leaves, so its pre-wait work IS the critical path there.
+template <int NW>
+struct RootPre {
+  int have, ex, ex_ch, np;       // ex = root cell of the pending path (-1: none), its child pointer before the expansion, parent count
+  float ex_p;
+  RootScan rs;
+};
+template <int NW>
+__device__ __forceinline__ RootPre<NW> root_prescan(const RulesParams& rp, const TreeView& tv, int g, int lane, double c_puct,
+                                                    const ExpandPre<NW>& pre) {
+  RootPre<NW> r;
+  r.have = 0; r.ex = -1; r.ex_ch = CHILD_NONE; r.np = 0; r.ex_p = 0.f;
+  if (!pre.active || tv.root_result[g] != 0) return r;
+  const int A = rp.A;
+  const size_t gbase = (size_t)g * tv.cap * A;
+  const BB<NW> rx = bb_load<NW>(tv.root_x + (size_t)g * NW), ro = bb_load<NW>(tv.root_o + (size_t)g * NW);
+  uint64_t occw[NW];
+#pragma unroll
+  for (int k = 0; k < NW; k++) occw[k] = rx.w[k] | ro.w[k];
+  const bool pending = pre.kind != 2;                                 // a simulation is about to be backed up
+  const int e0 = __shfl_sync(AZP_FULL, pre.edge, 0);                  // path[0] = the root cell (node 0)
+  r.ex = (pending && pre.depth >= 1) ? e0 : -1;
+  r.np = tv.root_n[g] + (pending ? 1 : 0);
+  if (r.ex >= 0) { r.ex_p = tv.P[gbase + r.ex]; r.ex_ch = tv.child[gbase + r.ex]; }
+  scan_node<NW>(tv, gbase, A, occw, r.np, c_puct, lane, r.ex, r.rs.best, r.rs.besta, r.rs.cn, r.rs.ch);
+  r.have = 1;
+  return r;
+}
+// after expand_backup_body: score the one changed root child and merge it into the pre-scan
+template <int NW>
+__device__ __forceinline__ void root_merge(RootPre<NW>& r, const ExpandPre<NW>& pre, double c_puct) {
+  if (!r.have || r.ex < 0) return;
+  const int n0 = __shfl_sync(AZP_FULL, pre.en, 0);
+  const double w0 = __shfl_sync(AZP_FULL, pre.ew, 0);
+  const double sq = __dsqrt_rn(__dadd_rn((double)r.np, 1e-8));
+  const double num = __dmul_rn(__dmul_rn(c_puct, (double)r.ex_p), sq);
+  const double s = __dadd_rn(__ddiv_rn(w0, (double)n0), __ddiv_rn(num, (double)(1 + n0)));      // n0 >= 1
+  const int chx = (pre.kind == 0 && pre.depth == 1) ? pre.nid : r.ex_ch;    // the new node hangs under this very edge
+  if (s > r.rs.best || (s == r.rs.best && r.ex < r.rs.besta)) { r.rs.best = s; r.rs.besta = r.ex; r.rs.cn = n0; r.rs.ch = chx; }
 }
 
 // ---- kernels: the two halves alone (step-by-step API) and fused ------------------------------------------------
@@ -446,7 +514,12 @@ __global__ void __launch_bounds__(128, NW <= 2 ? 7 : 4) advance_kernel(RulesPara
   ExpandPre<NW> pre;
   pre.active = 0;
   const bool use_pre = tv.K == 1 && !((compact >> 6) & 1) && g < n;                       // bit 6: AZP_EXPAND_PRELOAD=0
-  if (use_pre) pre = expand_preload<NW>(tv, rp.A, g, lane);
+  RootPre<NW> rpre;
+  rpre.have = 0;
+  if (use_pre) {
+    pre = expand_preload<NW>(tv, rp.A, g, lane);
+    if (!((compact >> 7) & 1)) rpre = root_prescan<NW>(rp, tv, g, lane, c_puct, pre);      // bit 7: AZP_ROOT_PRESCAN=0
+  }
   pdl_wait();
   pdl_launch_dependents();
   if ((threadIdx.x & 31) == 0) AZP_TL_START(AZP_TL_ADVANCE, tl_idx);
@@ -476,7 +549,8 @@ __global__ void __launch_bounds__(128, NW <= 2 ? 7 : 4) advance_kernel(RulesPara
   }
   if (expand_backup_body<NW>(rp, tv, g, lane, policy, value, by_slot, logits, 0, use_pre ? &pre : nullptr)) {
     __syncwarp();             // the descent's lanes read edges other lanes of this warp have just written
-    select_body<NW>(rp, tv, g, lane, c_puct, compact, parity);
+    root_merge<NW>(rpre, pre, c_puct);
+    select_body<NW>(rp, tv, g, lane, c_puct, compact, parity, nullptr, nullptr, rpre.have ? &rpre.rs : nullptr);
   }
   if (lane == 0) AZP_TL_END(AZP_TL_ADVANCE, tl_idx, gridDim.x * (blockDim.x >> 5));
 }
@@ -498,11 +572,16 @@ __global__ void __launch_bounds__(c1t_threads(GROUPS), 1) descend_conv1_kernel(R
   conv1_tail_prologue<GROUPS>(ct, smem);
   ExpandPre<NW> pre;
   pre.active = 0;
+  RootPre<NW> rpre;
+  rpre.have = 0;
   {
     const int g0 = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (!FIRST && g0 < n) {
       if ((compact >> 5) & 1) prefetch_root<NW>(rp, tv, g0, threadIdx.x & 31);
-      if (!((compact >> 6) & 1)) pre = expand_preload<NW>(tv, rp.A, g0, threadIdx.x & 31);
+      if (!((compact >> 6) & 1)) {
+        pre = expand_preload<NW>(tv, rp.A, g0, threadIdx.x & 31);
+        if (!((compact >> 7) & 1)) rpre = root_prescan<NW>(rp, tv, g0, threadIdx.x & 31, c_puct, pre);     // bit 7: AZP_ROOT_PRESCAN=0
+      }
     }
   }
   const bool use_pre = !FIRST && !((compact >> 6) & 1);      // bit 6: AZP_EXPAND_PRELOAD=0
@@ -539,7 +618,10 @@ __global__ void __launch_bounds__(c1t_threads(GROUPS), 1) descend_conv1_kernel(R
       ok = expand_backup_body<NW>(rp, tv, g, lane, policy, value, by_slot, logits, 0, use_pre ? &pre : nullptr);
       __syncwarp();             // the descent's lanes read edges other lanes of this warp have just written
     }
-    if (ok) select_body<NW>(rp, tv, g, lane, c_puct, compact, parity, &slot, s_leaf[threadIdx.x >> 5]);
+    if (ok) {
+      if (!FIRST) root_merge<NW>(rpre, pre, c_puct);
+      select_body<NW>(rp, tv, g, lane, c_puct, compact, parity, &slot, s_leaf[threadIdx.x >> 5], (!FIRST && rpre.have) ? &rpre.rs : nullptr);
+    }
   }
   // team = how many warps of this lane quarter finished before this one (the team's barrier inside makes its members' leaf
   // records and slots -- written by lane 0 of each warp -- visible to the team)
@@ -854,9 +936,11 @@ int azp_tree_advance(azp_engine* e, int n, const float* policy, const float* val
   if (prefetch < 0) { const char* v = getenv("AZP_ROOT_PREFETCH"); prefetch = v ? atoi(v) : 2; }     // 0 off, 1 after the wait, 2 before it
   static int preload = -1;
   if (preload < 0) { const char* v = getenv("AZP_EXPAND_PRELOAD"); preload = v ? atoi(v) : 1; }
+  static int prescan = -1;
+  if (prescan < 0) { const char* v = getenv("AZP_ROOT_PRESCAN"); prescan = v ? atoi(v) : 0; }      // measured: -2.3 % (the scan is not free before the wait: most CTAs only become resident when the FC kernel leaves)
   azp_prof_begin(e, AZP_PROF_ADVANCE, nullptr, n, s);
   AZP_DISPATCH_NW_PDL(e->NW, advance_kernel, warp_grid(n), 128, 0, s, e->rp, e->tv, n, policy, value, by_slot, logits,
-                      e->cfg.c_puct, compact | ((prefetch != 0) << 4) | ((prefetch == 2) << 5) | ((preload == 0) << 6), parity);
+                      e->cfg.c_puct, compact | ((prefetch != 0) << 4) | ((prefetch == 2) << 5) | ((preload == 0) << 6) | ((prescan == 0) << 7), parity);
   azp_count_launch();
   azp_prof_end(e, AZP_PROF_ADVANCE, s);
   return azp_check_launch();
@@ -897,7 +981,9 @@ int azp_tree_descend_conv1(azp_engine* e, int n, bool first, const float* policy
   if (prefetch < 0) { const char* v = getenv("AZP_ROOT_PREFETCH"); prefetch = v ? atoi(v) : 2; }     // 0 off, 1 after the wait, 2 before it
   static int preload = -1;
   if (preload < 0) { const char* v = getenv("AZP_EXPAND_PRELOAD"); preload = v ? atoi(v) : 1; }
-  const int cp = compact | ((prefetch != 0) << 4) | ((prefetch == 2) << 5) | ((preload == 0) << 6);
+  static int prescan = -1;
+  if (prescan < 0) { const char* v = getenv("AZP_ROOT_PRESCAN"); prescan = v ? atoi(v) : 0; }      // measured: -2.3 % (the scan is not free before the wait: most CTAs only become resident when the FC kernel leaves)
+  const int cp = compact | ((prefetch != 0) << 4) | ((prefetch == 2) << 5) | ((preload == 0) << 6) | ((prescan == 0) << 7);
   azp_prof_begin(e, AZP_PROF_ADVANCE, nullptr, n, s);
   switch (e->NW) {
     case 1: descend_conv1_groups<1>(e, ct.enabled, n, first, policy, value, by_slot, logits, cp, parity, ct, s); break;
