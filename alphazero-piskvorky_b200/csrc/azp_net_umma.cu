@@ -571,7 +571,7 @@ __global__ void __launch_bounds__(BITS ? CONV_THREADS_BITS : (HEADS ? CONV_THREA
   const ConvGeom g = args.g;
   auto wall_ns = [] { unsigned long long gt; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt)); return (long long)gt; };
   if (AZP_CLKPTR(args.clk) && (int)blockIdx.x == args.clk_cta && threadIdx.x == 0) AZP_CLKPTR(args.clk)[0 * 16 + 14] = wall_ns();      // kernel entry
-  constexpr int TL_KID = HEADS ? AZP_TL_CONV3 : AZP_TL_CONV2;
+  [[maybe_unused]] constexpr int TL_KID = HEADS ? AZP_TL_CONV3 : AZP_TL_CONV2;
   const unsigned tl_idx = threadIdx.x == 0 ? AZP_TL_ENTRY(TL_KID, gridDim.x) : 0u;
 
   // ---- prologue: touches nothing the previous kernel of the stream writes, so under programmatic dependent
@@ -2468,7 +2468,6 @@ int azp_umma_build(azp_engine* e, const HostNet& net, NetWeights* W) {
     e->set_error("bf16 path expects the 4->32->64->128 stem");
     return AZP_ERR_UNSUPPORTED;
   }
-  const int A = e->A;
   UmmaWeights* U = new UmmaWeights();
   W->umma = U;
   W->umma_free = [](void* q) { delete (UmmaWeights*)q; };
