@@ -366,3 +366,32 @@ def test_bench_reference_arm_sampler_runs_on_cpu():
         rv, rcores, rsample = bench.cpu_throughput("reference", budget_s=1.0, procs=2, board=5, win=4, nsims=20)
         assert rv > 0 and rcores == 2 and "UNMODIFIED reference" in rsample
         assert v > rv                          # the port does not clone a board per legal child
+
+
+def test_bench_presets_are_the_baseline_configs():
+    """`bench.py --config N` must reproduce BASELINE.json's configs[N-1] at its STATED size: board, WIN_LENGTH, simulations
+    per move, concurrent games (config 3: 16384 over 8 GPUs = 2048 per GPU, weak scaling), leaf batch (config 4), match size
+    (config 5) are parsed out of the config strings and compared with the presets; the default is the headline config."""
+    import json
+    import re
+    sys.path.insert(0, ROOT)
+    import bench
+    cfgs = json.load(open(os.path.join(ROOT, "BASELINE.json")))["configs"]
+    assert len(cfgs) == 5 and sorted(bench.CONFIGS) == [1, 2, 3, 4, 5]
+    for i, text in enumerate(cfgs, 1):
+        p = bench.CONFIGS[i]
+        m = re.search(r"(\d+)\s*[x×]\s*(\d+)", text)
+        assert int(m.group(1)) == int(m.group(2)) == p["board"], (i, text)
+        w = re.search(r"WIN_LENGTH=(\d+)", text)
+        assert p["win"] == (int(w.group(1)) if w else 5), (i, text)
+        s = re.search(r"(\d+) sims/move", text)
+        if s:
+            assert p["sims"] == int(s.group(1)), (i, text)
+    assert bench.CONFIGS[1]["sims"] == 200                      # constants.py:NUM_SIMULATIONS of the reference (config 1)
+    assert bench.CONFIGS[2]["games"] == 4096
+    assert bench.CONFIGS[3]["games"] * 8 == 16384
+    assert bench.CONFIGS[4]["net"] == "tower" and bench.CONFIGS[4]["games"] * bench.CONFIGS[4]["leaves"] == 8192
+    assert bench.CONFIGS[4]["sims"] == 800
+    assert bench.CONFIGS[5]["mode"] == "arena" and bench.CONFIGS[5]["games"] == 400
+    assert all(bench.CONFIGS[i]["leaves"] == 1 for i in (1, 2, 3, 5))     # exact mode: reference-identical visit counts
+    assert all(c in bench.FLOPS_PER_LEAF for c in {p["board"] for p in bench.CONFIGS.values()})
